@@ -1,0 +1,917 @@
+// C ABI of libhsearch_b200.so: orchestration of the kernels (include/hsearch_b200.h).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "hash.cuh"
+#include "host_tables.h"
+#include "sort.cuh"
+#include "verify.cuh"
+#include "internal.cuh"
+
+namespace hs {
+int setup_projection(hs_ctx *ctx, const double *a, const double *b);
+int cluster_impl(hs_ctx *ctx, uint32_t *label_out);
+int extract_windows_impl(hs_ctx *ctx, const uint8_t *residues, const uint32_t *start_index, uint32_t nprot,
+                         uint32_t stride, uint64_t id_base, uint32_t *pos_out, uint64_t pos_cap, uint64_t *nfrag);
+int comm_gather_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t *nhits, uint64_t cap);
+int comm_broadcast(hs_ctx *ctx, void *d_buf, size_t bytes);
+void comm_destroy(hs_ctx *ctx);
+
+static int upload_tables(hs_ctx *ctx) {
+  HS_TRY(ctx->d_table64.reserve(sizeof(double) * HS_AA * HS_CDIM));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_table64.p, ctx->table64, sizeof(double) * HS_AA * HS_CDIM,
+                          cudaMemcpyHostToDevice, ctx->stream));
+  float dsq[HS_AA * HS_AA];
+  for (int c = 0; c < HS_AA; ++c)
+    for (int d = 0; d < HS_AA; ++d) {
+      double s = 0.0;
+      for (int j = 0; j < HS_CDIM; ++j) {
+        const double r = ctx->table64[c * HS_CDIM + j] - ctx->table64[d * HS_CDIM + j];
+        s += r * r;
+      }
+      dsq[c * HS_AA + d] = (float)s;
+    }
+  HS_TRY(ctx->d_dsq32.reserve(sizeof dsq));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_dsq32.p, dsq, sizeof dsq, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t metric[HS_AA * HS_AA];
+  blosum_metric(metric);
+  HS_TRY(ctx->d_metric.reserve(sizeof metric));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_metric.p, metric, sizeof metric, cudaMemcpyHostToDevice, ctx->stream));
+  float metric32[HS_AA * HS_AA];
+  for (int i = 0; i < HS_AA * HS_AA; ++i) metric32[i] = (float)metric[i];
+  HS_TRY(ctx->d_metric32.reserve(sizeof metric32));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_metric32.p, metric32, sizeof metric32, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+
+void stats_begin(hs_ctx *ctx) {
+  hs_stats &s = ctx->stats;
+  const uint64_t nf = ctx->N;
+  const uint32_t kw = ctx->key_words;
+  memset(&s, 0, sizeof s);
+  s.n_fragments = nf;
+  s.key_words = kw;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+    cudaGetLastError();
+    return 0.f;
+  }
+  return ms;
+}
+
+// Filter threshold: pass iff filter distance <= thr.  Euclid: the FP32 table sum
+// s^ satisfies s^ <= s_true * (1 + (len+1) * 2^-24), and a reference hit has
+// s_true <= R^2 * (1 + 1e-13); thr = R^2 * (1 + (len+2) * 2^-23) rounded up
+// doubles that margin.  Integer metric: the filter sum is exact.
+float filter_threshold(const hs_ctx *ctx) {
+  if (ctx->prm.metric == HS_METRIC_BLOSUM_INT) return (float)(int)ctx->prm.R;
+  const double r2 = ctx->prm.R * ctx->prm.R;
+  const double t = r2 * (1.0 + (double)(ctx->prm.len + 2) * ldexp(1.0, -23)) + 1e-30;
+  float f = (float)t;
+  if ((double)f < t) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+// Device tables of per-table pointers; entry L is the identity-order store.
+static int upload_table_pointers(hs_ctx *ctx) {
+  const uint32_t L = ctx->prm.L;
+  std::vector<const void *> h(3 * (HS_MAX_L + 1), nullptr);
+  for (uint32_t l = 0; l < L; ++l) {
+    h[l] = ctx->tables[l].codes_sorted.p;
+    h[(HS_MAX_L + 1) + l] = ctx->tables[l].sorted_ids.p;
+    h[2 * (HS_MAX_L + 1) + l] = ctx->d_keys[l].p;
+  }
+  h[L] = ctx->d_codes_pm.p;
+  h[(HS_MAX_L + 1) + L] = nullptr;
+  HS_TRY(ctx->d_tabptrs.reserve(h.size() * sizeof(void *)));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_tabptrs.p, h.data(), h.size() * sizeof(void *), cudaMemcpyHostToDevice,
+                          ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+const uint8_t *const *dev_stores(hs_ctx *ctx) { return ctx->d_tabptrs.as<const uint8_t *>(); }
+const uint32_t *const *dev_sorted_ids(hs_ctx *ctx) {
+  return reinterpret_cast<const uint32_t *const *>(ctx->d_tabptrs.as<const void *>() + (HS_MAX_L + 1));
+}
+const uint64_t *const *dev_keys(hs_ctx *ctx) {
+  return reinterpret_cast<const uint64_t *const *>(ctx->d_tabptrs.as<const void *>() + 2 * (HS_MAX_L + 1));
+}
+
+int ensure_identity_store(hs_ctx *ctx) {
+  if (ctx->have_codes_pm) return HS_OK;
+  HS_TRY(build_code_store(ctx, nullptr, ctx->d_codes_pm));
+  ctx->have_codes_pm = true;
+  return upload_table_pointers(ctx);
+}
+
+// Run the filter, growing the survivor buffer and retrying if it overflowed.
+int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out) {
+  unsigned long long *cnt = ctx->d_counters.as<unsigned long long>() + 8;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if (ctx->d_surv.cap < sizeof(Survivor) * (1u << 20)) HS_TRY(ctx->d_surv.reserve(sizeof(Survivor) * (1u << 22)));
+    fa.surv = ctx->d_surv.as<Survivor>();
+    fa.surv_cap = ctx->d_surv.cap / sizeof(Survivor);
+    fa.surv_count = cnt;
+    HS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
+    HS_TRY(launch_filter(ctx, fa, nblocks, mode));
+    unsigned long long n = 0;
+    HS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n <= fa.surv_cap) {
+      *nsurv_out = n;
+      return HS_OK;
+    }
+    HS_TRY(ctx->d_surv.reserve(sizeof(Survivor) * (size_t)(n + n / 8 + 1024)));
+  }
+  set_error("filter: survivor buffer kept overflowing");
+  return HS_ERR_NOMEM;
+}
+
+// ---- hits in the reference's output order -----------------------------------------
+__global__ void hit_keys_kernel(const hs_hit *__restrict__ hits, uint64_t n, uint64_t *__restrict__ k0,
+                                uint64_t *__restrict__ k1) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const hs_hit h = hits[i];
+  k0[i] = h.db_id;
+  k1[i] = ((uint64_t)h.query << 32) | (uint64_t)h.table_first;
+}
+__global__ void hit_gather_kernel(const hs_hit *__restrict__ in, const uint32_t *__restrict__ perm, uint64_t n,
+                                  hs_hit *__restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[perm[i]];
+}
+
+// Sort d_hits[0..n) by (query, first table, db id); result in ctx->d_hits_sorted.
+static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
+  if (n == 0) return HS_OK;
+  if (n >= (1ull << 32)) {
+    set_error("sort_hits: more than 2^32 hits");
+    return HS_ERR_UNSUPPORTED;
+  }
+  HS_TRY(ctx->d_hit_keys[0].reserve(sizeof(uint64_t) * n));
+  HS_TRY(ctx->d_hit_keys[1].reserve(sizeof(uint64_t) * n));
+  HS_TRY(ctx->d_hit_perm.reserve(sizeof(uint32_t) * 2 * n));
+  HS_TRY(ctx->d_hits_sorted.reserve(sizeof(hs_hit) * n));
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  hit_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, n, ctx->d_hit_keys[0].as<uint64_t>(),
+                                                ctx->d_hit_keys[1].as<uint64_t>());
+  ctx->stats.kernel_launches++;
+  KeyPtrs in, sorted;
+  memset(&in, 0, sizeof in);
+  in.w[0] = ctx->d_hit_keys[0].as<uint64_t>();
+  in.w[1] = ctx->d_hit_keys[1].as<uint64_t>();
+  uint32_t *perm = ctx->d_hit_perm.as<uint32_t>();
+  const uint32_t passes_before = ctx->stats.sort_passes;
+  HS_TRY(radix_sort_pairs(ctx, in, nullptr, n, 2, perm, perm + n, &sorted));
+  ctx->stats.sort_passes = passes_before;  // sort_passes counts index passes only
+  hit_gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, perm, n, ctx->d_hits_sorted.as<hs_hit>());
+  ctx->stats.kernel_launches++;
+  HS_CUDA(cudaGetLastError());
+  return HS_OK;
+}
+
+// ---- search ----------------------------------------------------------------------------
+struct QueryInput {
+  const double *h_points = nullptr;  // host [Q][dim]
+  const void *d_points = nullptr;    // device [Q][dim]
+  const uint8_t *h_codes = nullptr;  // host [Q][len]
+};
+
+static int stage_queries(hs_ctx *ctx, const QueryInput &in, uint32_t Q) {
+  const uint32_t dim = ctx->dim, len = ctx->prm.len;
+  HS_TRY(ctx->d_q64.reserve(sizeof(double) * std::max<size_t>(1, (size_t)Q * dim)));
+  ctx->have_qcodes = false;
+  if (in.d_points) {
+    HS_CUDA(cudaMemcpyAsync(ctx->d_q64.p, in.d_points, sizeof(double) * Q * dim, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else if (in.h_points) {
+    HS_CUDA(cudaMemcpyAsync(ctx->d_q64.p, in.h_points, sizeof(double) * Q * dim, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    // residue-code queries: embed with the ctx table (M1) on the host; Q is small
+    std::vector<double> pts((size_t)Q * dim);
+    for (uint32_t q = 0; q < Q; ++q)
+      for (uint32_t p = 0; p < len; ++p) {
+        const uint8_t c = in.h_codes[(size_t)q * len + p];
+        if (c >= HS_AA) {
+          set_error("query %u has residue code %u (must be 0..19)", q, (unsigned)c);
+          return HS_ERR_INVALID;
+        }
+        memcpy(&pts[(size_t)q * dim + p * HS_CDIM], ctx->table64 + c * HS_CDIM, sizeof(double) * HS_CDIM);
+      }
+    HS_CUDA(cudaMemcpyAsync(ctx->d_q64.p, pts.data(), sizeof(double) * Q * dim, cudaMemcpyHostToDevice, ctx->stream));
+    HS_TRY(ctx->d_qcodes.reserve(std::max<size_t>(1, (size_t)Q * len)));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_qcodes.p, in.h_codes, (size_t)Q * len, cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->have_qcodes = true;
+  }
+  if (ctx->nranks > 1) {
+    HS_TRY(comm_broadcast(ctx, ctx->d_q64.p, sizeof(double) * Q * dim));
+    if (ctx->have_qcodes) HS_TRY(comm_broadcast(ctx, ctx->d_qcodes.p, (size_t)Q * len));
+  }
+  if (ctx->prm.metric == HS_METRIC_BLOSUM_INT && !ctx->have_qcodes) {
+    set_error("the integer BLOSUM metric needs residue-code queries");
+    return HS_ERR_INVALID;
+  }
+  return HS_OK;
+}
+
+static int build_tq(hs_ctx *ctx, uint32_t Q) {
+  HS_TRY(ctx->d_tq.reserve(sizeof(float) * std::max<size_t>(1, (size_t)Q * ctx->prm.len * HS_AA)));
+  if (ctx->prm.metric == HS_METRIC_BLOSUM_INT)
+    return launch_build_tq_int(ctx, ctx->d_qcodes.as<uint8_t>(), Q, ctx->d_tq.as<float>());
+  return launch_build_tq_points(ctx, ctx->d_q64.as<double>(), Q, ctx->d_tq.as<float>());
+}
+
+void fill_exact_common(hs_ctx *ctx, ExactArgs &ea, uint32_t Q) {
+  memset(&ea, 0, sizeof ea);
+  ea.metric = (int)ctx->prm.metric;
+  ea.predicate = (int)ctx->prm.predicate;
+  ea.len = (int)ctx->prm.len;
+  ea.dim = (int)ctx->dim;
+  ea.key_words = (int)ctx->key_words;
+  ea.L = (int)ctx->prm.L;
+  ea.R = ctx->prm.R;
+  ea.sorted_ids = dev_sorted_ids(ctx);
+  ea.codes = ctx->d_codes.as<uint8_t>();
+  ea.N = ctx->N;
+  ea.id_base = ctx->id_base;
+  ea.table64 = ctx->d_table64.as<double>();
+  ea.metric_tab = ctx->d_metric.as<int32_t>();
+  ea.Q = Q;
+  ea.keys = dev_keys(ctx);
+}
+
+// Finish a search / brute-force call: optional ordering, multi-GPU gather, copy out.
+static int deliver_hits(hs_ctx *ctx, uint64_t nh, uint64_t dev_cap, hs_hit *hits_host, void *hits_dev,
+                        uint64_t cap, uint64_t *nhits, cudaEvent_t ev_sort0, cudaEvent_t ev_sort1) {
+  hs_hit *d_src = ctx->d_hits.as<hs_hit>();
+  uint64_t nvalid = std::min<uint64_t>(nh, dev_cap);
+  HS_CUDA(cudaEventRecord(ev_sort0, ctx->stream));
+  if ((ctx->prm.flags & HS_FLAG_SORT_HITS) && nh <= dev_cap) {
+    HS_TRY(sort_hits(ctx, d_src, nvalid));
+    if (nvalid) d_src = ctx->d_hits_sorted.as<hs_hit>();
+  }
+  HS_CUDA(cudaEventRecord(ev_sort1, ctx->stream));
+  if (ctx->nranks > 1) {
+    HS_TRY(comm_gather_hits(ctx, d_src, &nh, dev_cap));
+    d_src = ctx->d_hits_gathered.as<hs_hit>();
+    nvalid = ctx->rank == 0 ? nh : 0;
+    if (ctx->rank == 0 && (ctx->prm.flags & HS_FLAG_SORT_HITS) && nvalid) {
+      HS_TRY(sort_hits(ctx, d_src, nvalid));
+      d_src = ctx->d_hits_sorted.as<hs_hit>();
+    }
+  }
+  *nhits = nh;
+  ctx->stats.n_hits = nh;
+  const uint64_t ncopy = std::min<uint64_t>(nvalid, cap);
+  if (ncopy) {
+    if (hits_dev)
+      HS_CUDA(cudaMemcpyAsync(hits_dev, d_src, sizeof(hs_hit) * ncopy, cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+      HS_CUDA(cudaMemcpyAsync(hits_host, d_src, sizeof(hs_hit) * ncopy, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (nh > cap) {
+    set_error("hit buffer too small: %llu hits, capacity %llu", (unsigned long long)nh, (unsigned long long)cap);
+    return HS_ERR_CAPACITY;
+  }
+  return HS_OK;
+}
+
+static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hits_host, void *hits_dev,
+                       uint64_t cap, uint64_t *nhits) {
+  if (!ctx->indexed) {
+    set_error("hs_search: call hs_build_index first");
+    return HS_ERR_INVALID;
+  }
+  const uint32_t L = ctx->prm.L, KW = ctx->key_words;
+  stats_begin(ctx);
+  cudaEvent_t *ev = ctx->ev;
+  HS_CUDA(cudaEventRecord(ev[0], ctx->stream));
+  HS_TRY(stage_queries(ctx, in, Q));
+
+  // query keys + probe
+  HS_TRY(ctx->d_qkeys.reserve(sizeof(uint64_t) * std::max<size_t>(1, (size_t)L * Q * KW)));
+  HS_TRY(ctx->d_qvalid.reserve(std::max<size_t>(1, (size_t)L * Q)));
+  HS_TRY(ctx->d_qrange.reserve(sizeof(uint2) * std::max<size_t>(1, (size_t)L * Q)));
+  HS_TRY(launch_hash_queries(ctx, ctx->d_q64.as<double>(), Q, ctx->d_qkeys.as<uint64_t>(), ctx->d_qvalid.as<uint8_t>()));
+  HS_CUDA(cudaEventRecord(ev[1], ctx->stream));
+  for (uint32_t l = 0; l < L; ++l)
+    HS_TRY(launch_probe(ctx, l, ctx->d_qkeys.as<uint64_t>(), ctx->d_qvalid.as<uint8_t>(), Q, ctx->d_qrange.as<uint2>()));
+  HS_TRY(build_tq(ctx, Q));
+  std::vector<uint2> qrange((size_t)L * Q);
+  if (!qrange.empty())
+    HS_CUDA(cudaMemcpyAsync(qrange.data(), ctx->d_qrange.p, sizeof(uint2) * qrange.size(), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  HS_CUDA(cudaEventRecord(ev[2], ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+
+  // work list: queries grouped by bucket, chunked
+  std::vector<WorkItem> items;
+  std::vector<uint32_t> qlist;
+  uint64_t ncand = 0;
+  uint32_t nblocks = 0;
+  std::vector<uint64_t> order;
+  for (uint32_t l = 0; l < L; ++l) {
+    order.clear();
+    for (uint32_t q = 0; q < Q; ++q) {
+      const uint2 r = qrange[(size_t)l * Q + q];
+      if (r.y > r.x) order.push_back(((uint64_t)r.x << 32) | q);
+    }
+    std::sort(order.begin(), order.end());
+    size_t i = 0;
+    while (i < order.size()) {
+      const uint32_t mb = (uint32_t)(order[i] >> 32);
+      size_t j = i;
+      while (j < order.size() && (uint32_t)(order[j] >> 32) == mb) ++j;
+      const uint32_t me = qrange[(size_t)l * Q + (uint32_t)order[i]].y;
+      const uint32_t ntiles = (me - (mb & ~3u) + kFilterTile - 1) / kFilterTile;
+      for (size_t c = i; c < j; c += kQueriesPerItem) {
+        const size_t ce = std::min(j, c + kQueriesPerItem);
+        WorkItem it;
+        it.table = l;
+        it.m_begin = mb;
+        it.m_end = me;
+        it.q_begin = (uint32_t)qlist.size();
+        for (size_t t = c; t < ce; ++t) qlist.push_back((uint32_t)order[t]);
+        it.q_end = (uint32_t)qlist.size();
+        it.block_begin = nblocks;
+        if ((uint64_t)nblocks + ntiles > 0x7fffffffull) {
+          set_error("hs_search: work list exceeds 2^31 blocks");
+          return HS_ERR_UNSUPPORTED;
+        }
+        nblocks += ntiles;
+        items.push_back(it);
+        ncand += (uint64_t)(me - mb) * (ce - c);
+      }
+      i = j;
+    }
+  }
+  ctx->stats.n_candidates = ncand;
+  ctx->stats.n_work_items = items.size();
+
+  uint64_t nsurv = 0;
+  if (!items.empty()) {
+    HS_TRY(ctx->d_work.reserve(sizeof(WorkItem) * items.size()));
+    HS_TRY(ctx->d_qlist.reserve(sizeof(uint32_t) * qlist.size()));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_work.p, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, qlist.data(), sizeof(uint32_t) * qlist.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FilterArgs fa;
+    memset(&fa, 0, sizeof fa);
+    fa.items = ctx->d_work.as<WorkItem>();
+    fa.nitems = (uint32_t)items.size();
+    fa.qlist = ctx->d_qlist.as<uint32_t>();
+    fa.tq = ctx->d_tq.as<float>();
+    fa.dsq32 = ctx->d_dsq32.as<float>();
+    fa.stores = dev_stores(ctx);
+    fa.npad = ctx->npad;
+    fa.len = (int)ctx->prm.len;
+    fa.thr = filter_threshold(ctx);
+    HS_TRY(run_filter(ctx, fa, nblocks, kModeSearch, &nsurv));
+  }
+  HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
+  ctx->stats.n_survivors = nsurv;
+
+  // exact + dedup + emit
+  const uint64_t dev_cap = std::max<uint64_t>(cap, 1);
+  HS_TRY(ctx->d_hits.reserve(sizeof(hs_hit) * dev_cap));
+  unsigned long long *hit_count = ctx->d_counters.as<unsigned long long>() + 9;
+  HS_CUDA(cudaMemsetAsync(hit_count, 0, sizeof(unsigned long long), ctx->stream));
+  ExactArgs ea;
+  fill_exact_common(ctx, ea, Q);
+  ea.surv = ctx->d_surv.as<Survivor>();
+  ea.nsurv = nsurv;
+  ea.mode = kModeSearch;
+  ea.q64 = ctx->prm.metric == HS_METRIC_EUCLID_FP64 ? ctx->d_q64.as<double>() : nullptr;
+  ea.qcodes = ctx->have_qcodes ? ctx->d_qcodes.as<uint8_t>() : nullptr;
+  ea.qkeys = ctx->d_qkeys.as<uint64_t>();
+  ea.qvalid = ctx->d_qvalid.as<uint8_t>();
+  ea.hits = ctx->d_hits.as<hs_hit>();
+  ea.hit_cap = dev_cap;
+  ea.hit_count = hit_count;
+  HS_TRY(launch_exact(ctx, ea));
+  unsigned long long nh = 0;
+  HS_CUDA(cudaMemcpyAsync(&nh, hit_count, sizeof nh, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+
+  int rc = deliver_hits(ctx, nh, dev_cap, hits_host, hits_dev, cap, nhits, ev[5], ev[6]);
+  HS_CUDA(cudaEventRecord(ev[7], ctx->stream));
+  HS_CUDA(cudaEventSynchronize(ev[7]));
+  ctx->stats.ms_qhash = ev_ms(ev[0], ev[1]);
+  ctx->stats.ms_probe = ev_ms(ev[1], ev[2]);
+  ctx->stats.ms_filter = ev_ms(ev[2], ev[3]);
+  ctx->stats.ms_exact = ev_ms(ev[3], ev[4]);
+  ctx->stats.ms_hitsort = ev_ms(ev[5], ev[6]);
+  ctx->stats.ms_total = ev_ms(ev[0], ev[7]);
+  return rc;
+}
+
+// ---- brute force ------------------------------------------------------------------------
+__global__ void build_tq_from_db_kernel(const uint8_t *__restrict__ codes, uint64_t q0, uint32_t nq, int len,
+                                        const float *__restrict__ dsq32, const int32_t *__restrict__ metric,
+                                        int use_int, float *__restrict__ tq) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n = (uint64_t)nq * len * HS_AA;
+  if (i >= n) return;
+  const int c = (int)(i % HS_AA);
+  const uint64_t qp = i / HS_AA;
+  const int cq = codes[q0 * len + qp];
+  tq[i] = use_int ? (float)metric[c * HS_AA + cq] : dsq32[c * HS_AA + cq];
+}
+
+static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit *hits, uint64_t cap,
+                           uint64_t *nhits) {
+  if (ctx->N == 0) {
+    set_error("hs_bruteforce: no fragments loaded");
+    return HS_ERR_INVALID;
+  }
+  stats_begin(ctx);
+  cudaEvent_t *ev = ctx->ev;
+  HS_CUDA(cudaEventRecord(ev[0], ctx->stream));
+  HS_TRY(ensure_identity_store(ctx));
+  const uint32_t L = ctx->prm.L;
+  const bool allpairs = (in == nullptr);
+  const uint64_t N = ctx->N;
+  const uint64_t dev_cap = std::max<uint64_t>(cap, 1);
+  HS_TRY(ctx->d_hits.reserve(sizeof(hs_hit) * dev_cap));
+  unsigned long long *hit_count = ctx->d_counters.as<unsigned long long>() + 9;
+  HS_CUDA(cudaMemsetAsync(hit_count, 0, sizeof(unsigned long long), ctx->stream));
+  if (!allpairs) HS_TRY(stage_queries(ctx, *in, Q));
+
+  const uint64_t total_q = allpairs ? N : Q;
+  // all pairs: the DB is its own query set, taken in blocks whose filter tables
+  // are resident at once; explicit queries: one block
+  const uint64_t qblock = allpairs ? (1u << 20) : std::max<uint64_t>(total_q, 1);
+  uint64_t ncand = 0, nsurv_total = 0;
+  float ms_filter = 0.f, ms_exact = 0.f;
+  for (uint64_t q0 = 0; q0 < total_q; q0 += qblock) {
+    const uint32_t nq = (uint32_t)std::min<uint64_t>(qblock, total_q - q0);
+    HS_TRY(ctx->d_tq.reserve(sizeof(float) * (size_t)nq * ctx->prm.len * HS_AA));
+    if (allpairs) {
+      const uint64_t n = (uint64_t)nq * ctx->prm.len * HS_AA;
+      build_tq_from_db_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->d_codes.as<uint8_t>(), q0, nq, (int)ctx->prm.len, ctx->d_dsq32.as<float>(),
+          ctx->d_metric.as<int32_t>(), ctx->prm.metric == HS_METRIC_BLOSUM_INT, ctx->d_tq.as<float>());
+      ctx->stats.kernel_launches++;
+    } else {
+      HS_TRY(build_tq(ctx, Q));
+    }
+    // work items: query chunks x member range
+    std::vector<WorkItem> items;
+    std::vector<uint32_t> qlist(nq);
+    for (uint32_t i = 0; i < nq; ++i) qlist[i] = (uint32_t)(q0 + i);  // all pairs: DB ids
+    uint32_t nblocks = 0;
+    for (uint32_t c = 0; c < nq; c += kQueriesPerItem) {
+      const uint32_t ce = std::min<uint32_t>(nq, c + kQueriesPerItem);
+      WorkItem it;
+      it.table = L;
+      it.m_begin = allpairs ? (uint32_t)std::min<uint64_t>(N, q0 + c + 1) : 0u;
+      it.m_end = (uint32_t)N;
+      if (it.m_end <= it.m_begin) continue;
+      it.q_begin = c;
+      it.q_end = ce;
+      it.block_begin = nblocks;
+      const uint32_t ntiles = (it.m_end - (it.m_begin & ~3u) + kFilterTile - 1) / kFilterTile;
+      if ((uint64_t)nblocks + ntiles > 0x7fffffffull) {
+        set_error("hs_bruteforce: work list exceeds 2^31 blocks");
+        return HS_ERR_UNSUPPORTED;
+      }
+      nblocks += ntiles;
+      items.push_back(it);
+      ncand += (uint64_t)(it.m_end - it.m_begin) * (ce - c);
+    }
+    if (items.empty()) continue;
+    HS_TRY(ctx->d_work.reserve(sizeof(WorkItem) * items.size()));
+    HS_TRY(ctx->d_qlist.reserve(sizeof(uint32_t) * qlist.size()));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_work.p, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, qlist.data(), sizeof(uint32_t) * qlist.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaEventRecord(ev[1], ctx->stream));
+    FilterArgs fa;
+    memset(&fa, 0, sizeof fa);
+    fa.items = ctx->d_work.as<WorkItem>();
+    fa.nitems = (uint32_t)items.size();
+    fa.qlist = ctx->d_qlist.as<uint32_t>();
+    fa.tq = ctx->d_tq.as<float>();
+    fa.dsq32 = ctx->d_dsq32.as<float>();
+    fa.stores = dev_stores(ctx);
+    fa.npad = ctx->npad;
+    fa.len = (int)ctx->prm.len;
+    fa.thr = filter_threshold(ctx);
+    fa.tq_base = (uint32_t)q0;  // tq rows are block-relative
+    uint64_t nsurv = 0;
+    HS_TRY(run_filter(ctx, fa, nblocks, allpairs ? kModeAllPairs : kModeBrute, &nsurv));
+    HS_CUDA(cudaEventRecord(ev[2], ctx->stream));
+    nsurv_total += nsurv;
+    ExactArgs ea;
+    fill_exact_common(ctx, ea, allpairs ? 0 : Q);
+    ea.surv = ctx->d_surv.as<Survivor>();
+    ea.nsurv = nsurv;
+    ea.mode = allpairs ? kModeAllPairs : kModeBrute;
+    if (!allpairs) {
+      ea.q64 = ctx->prm.metric == HS_METRIC_EUCLID_FP64 ? ctx->d_q64.as<double>() : nullptr;
+      ea.qcodes = ctx->have_qcodes ? ctx->d_qcodes.as<uint8_t>() : nullptr;
+    }
+    ea.hits = ctx->d_hits.as<hs_hit>();
+    ea.hit_cap = dev_cap;
+    ea.hit_count = hit_count;
+    HS_TRY(launch_exact(ctx, ea));
+    HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
+    HS_CUDA(cudaEventSynchronize(ev[3]));
+    ms_filter += ev_ms(ev[1], ev[2]);
+    ms_exact += ev_ms(ev[2], ev[3]);
+  }
+  ctx->stats.n_candidates = ncand;
+  ctx->stats.n_survivors = nsurv_total;
+  unsigned long long nh = 0;
+  HS_CUDA(cudaMemcpyAsync(&nh, hit_count, sizeof nh, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  int rc = deliver_hits(ctx, nh, dev_cap, hits, nullptr, cap, nhits, ev[5], ev[6]);
+  HS_CUDA(cudaEventRecord(ev[7], ctx->stream));
+  HS_CUDA(cudaEventSynchronize(ev[7]));
+  ctx->stats.ms_filter = ms_filter;
+  ctx->stats.ms_exact = ms_exact;
+  ctx->stats.ms_hitsort = ev_ms(ev[5], ev[6]);
+  ctx->stats.ms_total = ev_ms(ev[0], ev[7]);
+  return rc;
+}
+
+}  // namespace hs
+
+using namespace hs;
+
+extern "C" {
+
+int hs_device_available(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) return 1;
+  }
+  return 0;
+}
+
+int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
+  if (!out || !params) {
+    set_error("hs_create: null argument");
+    return HS_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (params->len == 0 || params->len > HS_MAX_LEN || params->K == 0 || params->K > HS_MAX_K || params->L == 0 ||
+      params->L > HS_MAX_L) {
+    set_error("hs_create: len must be 1..%d, K 1..%d, L 1..%d", HS_MAX_LEN, HS_MAX_K, HS_MAX_L);
+    return HS_ERR_UNSUPPORTED;
+  }
+  if (!(params->W > 0.0) || !(params->R >= 0.0) || params->table_variant > HS_TABLE_PRINT6 ||
+      params->metric > HS_METRIC_BLOSUM_INT || params->predicate > HS_PRED_SQRT_LE_R) {
+    set_error("hs_create: bad W / R / enum value");
+    return HS_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("hs_create: no CUDA device (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return HS_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("hs_create: device %d out of range (0..%d)", device, ndev - 1);
+    return HS_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  HS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("hs_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+              prop.minor);
+    return HS_ERR_CUDA;
+  }
+  HS_CUDA(cudaSetDevice(device));
+  hs_ctx *ctx = new (std::nothrow) hs_ctx();
+  if (!ctx) return HS_ERR_NOMEM;
+  ctx->device = device;
+  ctx->prm = *params;
+  ctx->dim = params->len * HS_CDIM;
+  coordinates_table(params->table_variant, ctx->table64);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("hs_create: cudaStreamCreate failed");
+    delete ctx;
+    return HS_ERR_CUDA;
+  }
+  for (int i = 0; i < 16; ++i) cudaEventCreate(&ctx->ev[i]);
+  int rc = ctx->d_counters.reserve(sizeof(unsigned long long) * 16);
+  if (rc == HS_OK) rc = upload_tables(ctx);
+  if (rc != HS_OK) {
+    hs_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return HS_OK;
+}
+
+void hs_destroy(hs_ctx_t *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
+  DevBuf *bufs[] = {&ctx->d_table64, &ctx->d_dsq32, &ctx->d_metric, &ctx->d_a64, &ctx->d_b64, &ctx->d_T32,
+                    &ctx->d_b32, &ctx->d_eps32, &ctx->d_codes, &ctx->d_buckets, &ctx->d_codes_pm, &ctx->d_q64,
+                    &ctx->d_qcodes, &ctx->d_qkeys, &ctx->d_qvalid, &ctx->d_qrange, &ctx->d_tq, &ctx->d_work,
+                    &ctx->d_qlist, &ctx->d_surv, &ctx->d_hits, &ctx->d_counters, &ctx->d_hit_keys[0],
+                    &ctx->d_hit_keys[1], &ctx->d_hit_keys[2], &ctx->d_hit_perm, &ctx->d_hits_sorted,
+                    &ctx->d_hits_gathered, &ctx->d_misc, &ctx->d_parent, &ctx->d_tabptrs, &ctx->d_residues,
+                    &ctx->d_starts, &ctx->d_metric32, &ctx->d_large, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
+                    &ctx->sort.flags, &ctx->sort.block_sums, &ctx->sort.or_and};
+  for (DevBuf *b : bufs) b->release();
+  for (int w = 0; w < kMaxKeyWords; ++w) {
+    ctx->sort.keys_alt[w].release();
+    ctx->sort.keys_cur[w].release();
+  }
+  for (int l = 0; l < HS_MAX_L; ++l) {
+    ctx->d_keys[l].release();
+    ctx->tables[l].sorted_ids.release();
+    ctx->tables[l].ukeys.release();
+    ctx->tables[l].bstart.release();
+    ctx->tables[l].codes_sorted.release();
+  }
+  for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->ev[i]);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int hs_get_stats(hs_ctx_t *ctx, hs_stats *out) {
+  if (!ctx || !out) return HS_ERR_INVALID;
+  *out = ctx->stats;
+  return HS_OK;
+}
+
+int hs_set_coordinates(hs_ctx_t *ctx, const double *table160) {
+  if (!ctx || !table160) return HS_ERR_INVALID;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  memcpy(ctx->table64, table160, sizeof ctx->table64);
+  HS_TRY(upload_tables(ctx));
+  if (ctx->have_projection) {
+    std::vector<double> a = ctx->h_a, b = ctx->h_b;
+    HS_TRY(setup_projection(ctx, a.data(), b.data()));
+  }
+  return HS_OK;
+}
+
+int hs_set_projection(hs_ctx_t *ctx, const double *a, const double *b) {
+  if (!ctx || !a || !b) {
+    set_error("hs_set_projection: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  return setup_projection(ctx, a, b);
+}
+
+static int load_common(hs_ctx *ctx, uint64_t N, uint64_t id_base) {
+  if (N >= (1ull << 32) - 4096) {
+    set_error("hs_load_fragments: at most 2^32-4096 fragments per GPU (ids are 32-bit)");
+    return HS_ERR_UNSUPPORTED;
+  }
+  ctx->N = N;
+  ctx->id_base = id_base;
+  ctx->npad = (N + 15) & ~15ull;
+  ctx->hashed = false;
+  ctx->indexed = false;
+  ctx->have_codes_pm = false;
+  return ctx->d_codes.reserve((size_t)N * ctx->prm.len + 64);
+}
+
+int hs_load_fragments(hs_ctx_t *ctx, const uint8_t *codes, uint64_t N, uint64_t id_base) {
+  if (!ctx || (!codes && N)) {
+    set_error("hs_load_fragments: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  HS_TRY(load_common(ctx, N, id_base));
+  if (N) HS_CUDA(cudaMemcpyAsync(ctx->d_codes.p, codes, (size_t)N * ctx->prm.len, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+
+int hs_load_fragments_dev(hs_ctx_t *ctx, const void *codes_dev, uint64_t N, uint64_t id_base) {
+  if (!ctx || (!codes_dev && N)) {
+    set_error("hs_load_fragments_dev: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  HS_TRY(load_common(ctx, N, id_base));
+  if (N) HS_CUDA(cudaMemcpyAsync(ctx->d_codes.p, codes_dev, (size_t)N * ctx->prm.len, cudaMemcpyDeviceToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+
+int hs_extract_windows(hs_ctx_t *ctx, const uint8_t *residues, const uint32_t *start_index, uint32_t nprot,
+                       uint32_t stride, uint64_t id_base, uint32_t *pos_out, uint64_t pos_cap, uint64_t *nfrag) {
+  if (!ctx || !residues || !start_index || !nfrag || stride == 0) {
+    set_error("hs_extract_windows: bad argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  return extract_windows_impl(ctx, residues, start_index, nprot, stride, id_base, pos_out, pos_cap, nfrag);
+}
+
+uint64_t hs_num_fragments(hs_ctx_t *ctx) { return ctx ? ctx->N : 0; }
+
+int hs_hash(hs_ctx_t *ctx, int32_t *buckets_out) {
+  if (!ctx) return HS_ERR_INVALID;
+  if (!ctx->have_projection) {
+    set_error("hs_hash: call hs_set_projection first");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  const uint32_t L = ctx->prm.L, K = ctx->prm.K;
+  const uint64_t N = ctx->N;
+  stats_begin(ctx);
+  if (N == 0) {
+    ctx->hashed = true;
+    return HS_OK;
+  }
+  for (uint32_t l = 0; l < L; ++l) HS_TRY(ctx->d_keys[l].reserve(sizeof(uint64_t) * ctx->key_words * N));
+  if (buckets_out) HS_TRY(ctx->d_buckets.reserve(sizeof(int32_t) * N * L * K));
+  unsigned long long *cnt = ctx->d_counters.as<unsigned long long>();
+  HS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 8, ctx->stream));
+  HS_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (ctx->prm.flags & HS_FLAG_HASH_EXACT) HS_TRY(launch_hash_exact(ctx, buckets_out != nullptr, false));
+  else HS_TRY(launch_hash_fast(ctx, buckets_out != nullptr));
+  HS_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (ctx->prm.flags & HS_FLAG_HASH_AUDIT) HS_TRY(launch_hash_exact(ctx, false, true));
+  unsigned long long h[4];
+  HS_CUDA(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  if (buckets_out)
+    HS_CUDA(cudaMemcpyAsync(buckets_out, ctx->d_buckets.p, sizeof(int32_t) * N * L * K, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.guard_hits = h[0];
+  ctx->stats.guard_corrected = h[1];
+  ctx->stats.residual_flips = h[3];
+  ctx->stats.ms_hash = ev_ms(ctx->ev[0], ctx->ev[1]);
+  ctx->stats.ms_total = ctx->stats.ms_hash;
+  if (h[2]) {
+    set_error("hs_hash: %llu keys exceeded %u characters (internal bound violated)", h[2], 16 * ctx->key_words);
+    return HS_ERR_UNSUPPORTED;
+  }
+  ctx->hashed = true;
+  ctx->indexed = false;
+  return HS_OK;
+}
+
+int hs_get_keys(hs_ctx_t *ctx, uint32_t table, uint64_t *keys_out) {
+  if (!ctx || !keys_out || table >= ctx->prm.L || !ctx->hashed) {
+    set_error("hs_get_keys: bad argument or hs_hash not run");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  const uint64_t N = ctx->N;
+  const uint32_t KW = ctx->key_words;
+  std::vector<uint64_t> tmp((size_t)KW * N);
+  if (N) HS_CUDA(cudaMemcpy(tmp.data(), ctx->d_keys[table].p, sizeof(uint64_t) * KW * N, cudaMemcpyDeviceToHost));
+  for (uint64_t i = 0; i < N; ++i)
+    for (uint32_t w = 0; w < KW; ++w) keys_out[i * KW + w] = tmp[(size_t)w * N + i];
+  return HS_OK;
+}
+
+int hs_build_index(hs_ctx_t *ctx) {
+  if (!ctx) return HS_ERR_INVALID;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  hs_stats hash_stats;
+  memset(&hash_stats, 0, sizeof hash_stats);
+  if (!ctx->hashed) HS_TRY(hs_hash(ctx, nullptr));
+  hash_stats = ctx->stats;
+  const uint32_t L = ctx->prm.L;
+  ctx->stats.sort_passes = 0;
+  float ms_sort = 0.f, ms_group = 0.f, ms_permute = 0.f;
+  cudaEvent_t *ev = ctx->ev;
+  HS_CUDA(cudaEventRecord(ev[8], ctx->stream));
+  if (ctx->N) {
+    for (uint32_t l = 0; l < L; ++l) {
+      HS_CUDA(cudaEventRecord(ev[2], ctx->stream));
+      HS_TRY(build_table_index(ctx, l, ev[3], ev[4]));
+      HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
+      HS_CUDA(cudaEventSynchronize(ev[5]));
+      ms_sort += ev_ms(ev[2], ev[3]);
+      ms_group += ev_ms(ev[3], ev[4]);
+      ms_permute += ev_ms(ev[4], ev[5]);
+    }
+  } else {
+    for (uint32_t l = 0; l < L; ++l) ctx->tables[l].nb = 0;
+  }
+  HS_CUDA(cudaEventRecord(ev[9], ctx->stream));
+  HS_CUDA(cudaEventSynchronize(ev[9]));
+  HS_TRY(upload_table_pointers(ctx));
+  ctx->stats.ms_hash = hash_stats.ms_hash;
+  ctx->stats.ms_sort = ms_sort;
+  ctx->stats.ms_group = ms_group;
+  ctx->stats.ms_permute = ms_permute;
+  ctx->stats.ms_total = hash_stats.ms_hash + ev_ms(ev[8], ev[9]);
+  ctx->indexed = true;
+  return HS_OK;
+}
+
+int hs_table_sizes(hs_ctx_t *ctx, uint64_t *sizes_out) {
+  if (!ctx || !sizes_out || !ctx->indexed) {
+    set_error("hs_table_sizes: index not built");
+    return HS_ERR_INVALID;
+  }
+  for (uint32_t l = 0; l < ctx->prm.L; ++l) sizes_out[l] = ctx->tables[l].nb;
+  return HS_OK;
+}
+
+int hs_get_table(hs_ctx_t *ctx, uint32_t table, uint32_t *ids_out, uint32_t *starts_out) {
+  if (!ctx || !ctx->indexed || table >= ctx->prm.L) {
+    set_error("hs_get_table: index not built or bad table");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  const TableIndex &T = ctx->tables[table];
+  if (ids_out && ctx->N) HS_CUDA(cudaMemcpy(ids_out, T.sorted_ids.p, sizeof(uint32_t) * ctx->N, cudaMemcpyDeviceToHost));
+  if (starts_out && ctx->N) HS_CUDA(cudaMemcpy(starts_out, T.bstart.p, sizeof(uint32_t) * (T.nb + 1), cudaMemcpyDeviceToHost));
+  return HS_OK;
+}
+
+int hs_search_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hit *hits, uint64_t cap, uint64_t *nhits) {
+  if (!ctx || (!qpoints && Q) || (!hits && cap) || !nhits) {
+    set_error("hs_search_points: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  QueryInput in;
+  in.h_points = qpoints;
+  return search_impl(ctx, in, Q, hits, nullptr, cap, nhits);
+}
+
+int hs_search_codes(hs_ctx_t *ctx, const uint8_t *qcodes, uint32_t Q, hs_hit *hits, uint64_t cap, uint64_t *nhits) {
+  if (!ctx || (!qcodes && Q) || (!hits && cap) || !nhits) {
+    set_error("hs_search_codes: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  QueryInput in;
+  in.h_codes = qcodes;
+  return search_impl(ctx, in, Q, hits, nullptr, cap, nhits);
+}
+
+int hs_search_points_dev(hs_ctx_t *ctx, const void *qpoints_dev, uint32_t Q, void *hits_dev, uint64_t cap,
+                         uint64_t *nhits) {
+  if (!ctx || (!qpoints_dev && Q) || (!hits_dev && cap) || !nhits) {
+    set_error("hs_search_points_dev: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  QueryInput in;
+  in.d_points = qpoints_dev;
+  return search_impl(ctx, in, Q, nullptr, hits_dev, cap, nhits);
+}
+
+int hs_bruteforce_codes(hs_ctx_t *ctx, const uint8_t *qcodes, uint32_t Q, hs_hit *hits, uint64_t cap,
+                        uint64_t *nhits) {
+  if (!ctx || (!hits && cap) || !nhits) {
+    set_error("hs_bruteforce_codes: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  if (!qcodes) return bruteforce_impl(ctx, nullptr, 0, hits, cap, nhits);
+  QueryInput in;
+  in.h_codes = qcodes;
+  return bruteforce_impl(ctx, &in, Q, hits, cap, nhits);
+}
+
+int hs_bruteforce_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hit *hits, uint64_t cap,
+                         uint64_t *nhits) {
+  if (!ctx || (!qpoints && Q) || (!hits && cap) || !nhits) {
+    set_error("hs_bruteforce_points: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  QueryInput in;
+  in.h_points = qpoints;
+  return bruteforce_impl(ctx, &in, Q, hits, cap, nhits);
+}
+
+int hs_cluster(hs_ctx_t *ctx, uint32_t *label_out) {
+  if (!ctx || !label_out) {
+    set_error("hs_cluster: null argument");
+    return HS_ERR_INVALID;
+  }
+  if (!ctx->indexed) {
+    set_error("hs_cluster: call hs_build_index first");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  return cluster_impl(ctx, label_out);
+}
+}

@@ -1,0 +1,150 @@
+// Internal definitions shared by the translation units of libhsearch_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hsearch_b200.h"
+
+namespace hs {
+
+void set_error(const char *fmt, ...);
+
+#define HS_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      hs::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return HS_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define HS_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != HS_OK) return _s; \
+  } while (0)
+
+// Device buffer that grows but never shrinks (sized once for the 180 GB part;
+// avoids cudaMalloc inside timed regions after the first call).
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return HS_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      p = nullptr;
+      return HS_ERR_NOMEM;
+    }
+    cap = want;
+    return HS_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+// ---- geometry of the packed structures -------------------------------------
+constexpr int kMaxKeyWords = HS_MAX_KEY_WORDS;
+constexpr int kCodeScale = 4;  // bucket-ordered code store keeps code*4 (a byte offset into a float row)
+
+struct TableIndex {
+  DevBuf sorted_ids;    // u32 [N]  fragment ids in bucket order
+  DevBuf ukeys;         // u64 [key_words][nb]  distinct keys, ascending
+  DevBuf bstart;        // u32 [nb+1]           bucket boundaries into sorted_ids
+  DevBuf codes_sorted;  // u8  [len][npad]      code*4, position-major, bucket order
+  uint64_t nb = 0;
+};
+
+struct SortScratch {
+  DevBuf keys_alt[kMaxKeyWords];  // ping-pong key words
+  DevBuf keys_cur[kMaxKeyWords];
+  DevBuf vals_alt;
+  DevBuf tile_hist;  // u32 [256][ntiles] (+1)
+  DevBuf digit_hist; // u32 [ndigits][256]
+  DevBuf flags;      // u32 [N] scan scratch
+  DevBuf block_sums;
+  DevBuf or_and;     // small reduction scratch
+};
+
+struct Stats : hs_stats {};
+
+}  // namespace hs
+
+// The opaque context (C name so the header's forward declaration matches).
+struct hs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  hs_params prm{};
+  uint32_t dim = 0;
+
+  // tables
+  double table64[HS_AA * HS_CDIM];
+  hs::DevBuf d_table64;  // f64 [20][8]
+  hs::DevBuf d_dsq32;    // f32 [20][20] squared residue distances (filter)
+  hs::DevBuf d_metric;   // i32 [20][20] integer BLOSUM metric
+  hs::DevBuf d_metric32; // f32 copy (filter tables of the integer metric)
+  hs::DevBuf d_large;    // cluster: (begin, end) of large buckets
+
+  // projection
+  bool have_projection = false;
+  std::vector<double> h_a, h_b;
+  hs::DevBuf d_a64, d_b64;   // f64 [L][K][DIM], [L][K]
+  hs::DevBuf d_T32;          // f32 [L][len][20][Kp]  residue-projection partial sums
+  hs::DevBuf d_b32, d_eps32; // f32 [L][Kp]
+  uint32_t Kp = 0;           // K rounded up to a multiple of 4
+  uint32_t tpc = 1;          // tables per hash chunk
+  uint32_t nchunks = 1;      // hash chunks
+  uint32_t nq = 1;           // float4 quads of projections per chunk
+  uint32_t key_words = 1;
+  uint32_t max_chars = 0;
+
+  // database
+  uint64_t N = 0, id_base = 0;
+  uint64_t npad = 0;         // N rounded up to 16
+  hs::DevBuf d_codes;        // u8 [N][len]
+  bool hashed = false, indexed = false;
+  hs::DevBuf d_keys[HS_MAX_L];     // u64 [key_words][N] per table, original order
+  hs::DevBuf d_buckets;            // i32 [N][L][K] (only when requested)
+  hs::TableIndex tables[HS_MAX_L];
+  hs::DevBuf d_codes_pm;           // u8 [len][npad] code*4, original order (brute force / cluster)
+  bool have_codes_pm = false;
+  hs::SortScratch sort;
+
+  // search scratch
+  hs::DevBuf d_q64, d_qkeys, d_qvalid, d_qrange, d_tq, d_work, d_qlist, d_surv, d_hits, d_counters;
+  hs::DevBuf d_hit_keys[3], d_hit_perm, d_hits_sorted;
+  hs::DevBuf d_misc, d_tabptrs, d_qcodes, d_hits_gathered, d_residues, d_starts;
+  bool have_qcodes = false;
+  void *h_pinned = nullptr;
+  size_t h_pinned_cap = 0;
+
+  // cluster
+  hs::DevBuf d_parent;
+
+  // comm
+  void *nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+
+  hs_stats stats{};
+  cudaEvent_t ev[16];
+};

@@ -1,0 +1,356 @@
+// K1 kernels: fragment hash (FP32 fast path with FP64 guard), all-FP64 hash /
+// audit, and the exact query hash.  See hash.cuh for the method.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "hash.cuh"
+
+namespace hs {
+
+constexpr int kHashThreads = 256;
+
+// counters[0] guard_hits, [1] guard_corrected, [2] key overflow, [3] residual flips
+template <int NQ, int KW>
+__global__ void __launch_bounds__(kHashThreads)
+hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
+                 const float *__restrict__ T32,    // [len][20][4*NQ] of this chunk
+                 const float *__restrict__ b32,    // [4*NQ]
+                 const float *__restrict__ eps32,  // [4*NQ]
+                 float invW, const double *__restrict__ table64, const double *__restrict__ a64,
+                 const double *__restrict__ b64, double W, int K, int Kp, int L, int dim,
+                 HashChunkArgs args, int32_t *__restrict__ buckets_out,
+                 unsigned long long *__restrict__ counters) {
+  constexpr int P = 4 * NQ;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *sT = reinterpret_cast<float *>(smem_raw);                    // len*20*P floats
+  uint8_t *sC = smem_raw + (size_t)len * HS_AA * P * sizeof(float);   // kHashThreads*len bytes
+
+  const int tid = threadIdx.x;
+  {
+    const int n4 = len * HS_AA * NQ;
+    const float4 *src = reinterpret_cast<const float4 *>(T32);
+    float4 *dst = reinterpret_cast<float4 *>(sT);
+    for (int i = tid; i < n4; i += kHashThreads) dst[i] = src[i];
+  }
+  const uint64_t frag0 = (uint64_t)blockIdx.x * kHashThreads;
+  const uint64_t nfrag = min((uint64_t)kHashThreads, N - frag0);
+  {
+    // tile of code bytes: contiguous in global memory, 16-byte aligned start
+    const uint64_t byte0 = frag0 * (uint64_t)len;
+    const uint32_t nbytes = (uint32_t)(nfrag * (uint64_t)len);
+    const uint32_t nvec = nbytes >> 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(codes + byte0);
+    uint4 *dst = reinterpret_cast<uint4 *>(sC);
+    for (uint32_t i = tid; i < nvec; i += kHashThreads) dst[i] = __ldg(src + i);
+    for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += kHashThreads) sC[i] = codes[byte0 + i];
+  }
+  __syncthreads();
+  if ((uint64_t)tid >= nfrag) return;
+  const uint64_t frag = frag0 + tid;
+  const uint8_t *myc = sC + tid * len;
+
+  float acc[P];
+#pragma unroll
+  for (int s = 0; s < P; ++s) acc[s] = 0.f;
+  for (int pos = 0; pos < len; ++pos) {
+    const int c = myc[pos];
+    const float4 *row = reinterpret_cast<const float4 *>(sT + (pos * HS_AA + c) * P);
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const float4 v = row[j];
+      acc[4 * j + 0] += v.x;
+      acc[4 * j + 1] += v.y;
+      acc[4 * j + 2] += v.z;
+      acc[4 * j + 3] += v.w;
+    }
+  }
+
+  KeyBuilder<KW> kb;
+  kb.reset();
+  int t = 0, k = 0;  // table within chunk, projection within table (uniform across the block)
+  unsigned int my_guard = 0, my_corr = 0, my_over = 0;
+#pragma unroll
+  for (int s = 0; s < P; ++s) {
+    if (t < args.ntab && k < K) {
+      const float val = acc[s] + __ldg(b32 + s);
+      const float tt = val * invW;
+      const float f = floorf(tt);
+      int bucket = (int)f;
+      const float e = __ldg(eps32 + s);
+      if ((tt - f) < e || ((f + 1.0f) - tt) < e) {
+        const int l = args.l0 + t;
+        const int ex = exact_bucket_codes(myc, len, table64, a64 + ((size_t)l * K + k) * dim,
+                                          b64[l * K + k], W);
+        ++my_guard;
+        if (ex != bucket) ++my_corr;
+        bucket = ex;
+      }
+      kb.push_int(bucket);
+      if (buckets_out) buckets_out[(frag * L + (args.l0 + t)) * K + k] = bucket;
+      if (k == K - 1) {
+        if (kb.nchars > 16 * KW) ++my_over;
+        uint64_t *dst = args.keys[t];
+#pragma unroll
+        for (int w = 0; w < KW; ++w) dst[(uint64_t)w * N + frag] = kb.w[w];
+        kb.reset();
+      }
+    }
+    if (++k == Kp) {
+      k = 0;
+      ++t;
+    }
+  }
+  if (my_guard) atomicAdd(counters + 0, (unsigned long long)my_guard);
+  if (my_corr) atomicAdd(counters + 1, (unsigned long long)my_corr);
+  if (my_over) atomicAdd(counters + 2, (unsigned long long)my_over);
+}
+
+// All-FP64 hash in reference order.  audit == 0: writes keys (and buckets).
+// audit == 1: compares the recomputed key with the stored one and counts
+// mismatching (fragment, table) keys in counters[3].
+template <int KW>
+__global__ void __launch_bounds__(kHashThreads)
+hash_exact_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
+                  const double *__restrict__ table64, const double *__restrict__ a64,
+                  const double *__restrict__ b64, double W, int K, int L, int dim, int l0, int l1,
+                  uint64_t *const *__restrict__ keys, int32_t *__restrict__ buckets_out, int audit,
+                  unsigned long long *__restrict__ counters) {
+  const uint64_t frag = (uint64_t)blockIdx.x * kHashThreads + threadIdx.x;
+  if (frag >= N) return;
+  uint8_t c[HS_MAX_LEN];
+  for (int i = 0; i < len; ++i) c[i] = codes[frag * len + i];
+  unsigned int over = 0, flips = 0;
+  for (int l = l0; l < l1; ++l) {
+    KeyBuilder<KW> kb;
+    kb.reset();
+    for (int k = 0; k < K; ++k) {
+      const int bucket = exact_bucket_codes(c, len, table64, a64 + ((size_t)l * K + k) * dim, b64[l * K + k], W);
+      kb.push_int(bucket);
+      if (!audit && buckets_out) buckets_out[(frag * L + l) * K + k] = bucket;
+    }
+    if (kb.nchars > 16 * KW) ++over;
+    uint64_t *dst = keys[l];
+    if (audit) {
+      bool same = true;
+#pragma unroll
+      for (int w = 0; w < KW; ++w) same = same && (dst[(uint64_t)w * N + frag] == kb.w[w]);
+      if (!same) ++flips;
+    } else {
+#pragma unroll
+      for (int w = 0; w < KW; ++w) dst[(uint64_t)w * N + frag] = kb.w[w];
+    }
+  }
+  if (over) atomicAdd(counters + 2, (unsigned long long)over);
+  if (flips) atomicAdd(counters + 3, (unsigned long long)flips);
+}
+
+// Query hash (motif_both_points.cpp:227): one thread per (query, table), FP64
+// in reference order.  qkeys [L][Q][KW]; qvalid[L][Q] = 0 when the key string
+// is longer than any DB key can be (then it matches no bucket).
+template <int KW>
+__global__ void hash_queries_kernel(const double *__restrict__ q64, uint32_t Q, int dim,
+                                    const double *__restrict__ a64, const double *__restrict__ b64,
+                                    double W, int K, int L, uint64_t *__restrict__ qkeys,
+                                    uint8_t *__restrict__ qvalid) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Q * (uint32_t)L) return;
+  const uint32_t l = idx / Q, q = idx - l * Q;
+  KeyBuilder<KW> kb;
+  kb.reset();
+  const double *pt = q64 + (size_t)q * dim;
+  for (int k = 0; k < K; ++k)
+    kb.push_int(exact_bucket_point(pt, dim, a64 + ((size_t)l * K + k) * dim, b64[l * K + k], W));
+#pragma unroll
+  for (int w = 0; w < KW; ++w) qkeys[((size_t)l * Q + q) * KW + w] = kb.w[w];
+  qvalid[(size_t)l * Q + q] = kb.nchars <= 16 * KW ? 1 : 0;
+}
+
+// ---- host side ---------------------------------------------------------------
+template <int NQ, int KW>
+static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
+                            unsigned long long *counters) {
+  const int P = 4 * NQ;
+  const int len = (int)ctx->prm.len;
+  const size_t smem = (size_t)len * HS_AA * P * sizeof(float) + (size_t)kHashThreads * len;
+  auto kern = hash_fast_kernel<NQ, KW>;
+  if (smem > 48 * 1024) HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((ctx->N + kHashThreads - 1) / kHashThreads);
+  const float *T = ctx->d_T32.as<float>() + (size_t)chunk * len * HS_AA * P;
+  kern<<<grid, kHashThreads, smem, ctx->stream>>>(
+      ctx->d_codes.as<uint8_t>(), ctx->N, len, T, ctx->d_b32.as<float>() + (size_t)chunk * P,
+      ctx->d_eps32.as<float>() + (size_t)chunk * P, (float)(1.0 / ctx->prm.W), ctx->d_table64.as<double>(),
+      ctx->d_a64.as<double>(), ctx->d_b64.as<double>(), ctx->prm.W, (int)ctx->prm.K, (int)ctx->Kp,
+      (int)ctx->prm.L, (int)ctx->dim, args, buckets, counters);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+template <int NQ>
+static int launch_fast_kw(hs_ctx *ctx, int chunk, const HashChunkArgs &a, int32_t *b, unsigned long long *c) {
+  switch (ctx->key_words) {
+    case 1: return launch_fast_inst<NQ, 1>(ctx, chunk, a, b, c);
+    case 2: return launch_fast_inst<NQ, 2>(ctx, chunk, a, b, c);
+    case 3: return launch_fast_inst<NQ, 3>(ctx, chunk, a, b, c);
+    default: return launch_fast_inst<NQ, 4>(ctx, chunk, a, b, c);
+  }
+}
+
+int launch_hash_fast(hs_ctx *ctx, bool want_buckets) {
+  int32_t *buckets = want_buckets ? ctx->d_buckets.as<int32_t>() : nullptr;
+  unsigned long long *counters = ctx->d_counters.as<unsigned long long>();
+  for (uint32_t chunk = 0; chunk < ctx->nchunks; ++chunk) {
+    HashChunkArgs args;
+    memset(&args, 0, sizeof args);
+    args.l0 = (int)(chunk * ctx->tpc);
+    args.ntab = (int)std::min<uint32_t>(ctx->tpc, ctx->prm.L - args.l0);
+    for (int t = 0; t < args.ntab; ++t) args.keys[t] = ctx->d_keys[args.l0 + t].as<uint64_t>();
+    switch (ctx->nq) {
+      case 1: HS_TRY((launch_fast_kw<1>(ctx, chunk, args, buckets, counters))); break;
+      case 2: HS_TRY((launch_fast_kw<2>(ctx, chunk, args, buckets, counters))); break;
+      case 4: HS_TRY((launch_fast_kw<4>(ctx, chunk, args, buckets, counters))); break;
+      default: HS_TRY((launch_fast_kw<8>(ctx, chunk, args, buckets, counters))); break;
+    }
+  }
+  return HS_OK;
+}
+
+template <int KW>
+static int launch_exact_inst(hs_ctx *ctx, int32_t *buckets, int audit, uint64_t *const *d_keyptrs,
+                             unsigned long long *counters) {
+  const unsigned grid = (unsigned)((ctx->N + kHashThreads - 1) / kHashThreads);
+  hash_exact_kernel<KW><<<grid, kHashThreads, 0, ctx->stream>>>(
+      ctx->d_codes.as<uint8_t>(), ctx->N, (int)ctx->prm.len, ctx->d_table64.as<double>(),
+      ctx->d_a64.as<double>(), ctx->d_b64.as<double>(), ctx->prm.W, (int)ctx->prm.K, (int)ctx->prm.L,
+      (int)ctx->dim, 0, (int)ctx->prm.L, d_keyptrs, buckets, audit, counters);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+int launch_hash_exact(hs_ctx *ctx, bool want_buckets, bool audit) {
+  int32_t *buckets = want_buckets ? ctx->d_buckets.as<int32_t>() : nullptr;
+  unsigned long long *counters = ctx->d_counters.as<unsigned long long>();
+  // table of per-table key pointers in device memory
+  uint64_t *h_ptrs[HS_MAX_L];
+  for (uint32_t l = 0; l < ctx->prm.L; ++l) h_ptrs[l] = ctx->d_keys[l].as<uint64_t>();
+  HS_TRY(ctx->d_misc.reserve(sizeof h_ptrs));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_misc.p, h_ptrs, sizeof(uint64_t *) * ctx->prm.L, cudaMemcpyHostToDevice,
+                          ctx->stream));
+  uint64_t *const *d_ptrs = ctx->d_misc.as<uint64_t *>();
+  switch (ctx->key_words) {
+    case 1: return launch_exact_inst<1>(ctx, buckets, audit, d_ptrs, counters);
+    case 2: return launch_exact_inst<2>(ctx, buckets, audit, d_ptrs, counters);
+    case 3: return launch_exact_inst<3>(ctx, buckets, audit, d_ptrs, counters);
+    default: return launch_exact_inst<4>(ctx, buckets, audit, d_ptrs, counters);
+  }
+}
+
+int launch_hash_queries(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint64_t *d_qkeys, uint8_t *d_qvalid) {
+  const uint32_t n = Q * ctx->prm.L;
+  if (n == 0) return HS_OK;
+  const unsigned grid = (n + 127) / 128;
+#define HS_QH(KWV)                                                                                        \
+  hash_queries_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(d_q64, Q, (int)ctx->dim, ctx->d_a64.as<double>(), \
+                                                          ctx->d_b64.as<double>(), ctx->prm.W,             \
+                                                          (int)ctx->prm.K, (int)ctx->prm.L, d_qkeys, d_qvalid)
+  switch (ctx->key_words) {
+    case 1: HS_QH(1); break;
+    case 2: HS_QH(2); break;
+    case 3: HS_QH(3); break;
+    default: HS_QH(4); break;
+  }
+#undef HS_QH
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+// Build the device-side projection data: FP64 matrix, FP32 residue-projection
+// tables per chunk, guard bands, key width.
+int setup_projection(hs_ctx *ctx, const double *a, const double *b) {
+  const uint32_t K = ctx->prm.K, L = ctx->prm.L, len = ctx->prm.len, dim = ctx->dim;
+  const double W = ctx->prm.W;
+  ctx->h_a.assign(a, a + (size_t)L * K * dim);
+  ctx->h_b.assign(b, b + (size_t)L * K);
+  HS_TRY(ctx->d_a64.reserve(sizeof(double) * L * K * dim));
+  HS_TRY(ctx->d_b64.reserve(sizeof(double) * L * K));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_a64.p, a, sizeof(double) * L * K * dim, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_b64.p, b, sizeof(double) * L * K, cudaMemcpyHostToDevice, ctx->stream));
+
+  ctx->Kp = (K + 3u) & ~3u;
+  ctx->tpc = std::max<uint32_t>(1u, std::min<uint32_t>(L, 32u / ctx->Kp));
+  if (ctx->tpc > 8) ctx->tpc = 8;
+  ctx->nchunks = (L + ctx->tpc - 1) / ctx->tpc;
+  uint32_t quads = ctx->tpc * ctx->Kp / 4;
+  ctx->nq = quads <= 1 ? 1 : quads <= 2 ? 2 : quads <= 4 ? 4 : 8;
+  const uint32_t P = 4 * ctx->nq;
+
+  std::vector<float> T32((size_t)ctx->nchunks * len * HS_AA * P, 0.f), b32((size_t)ctx->nchunks * P, 0.f),
+      eps32((size_t)ctx->nchunks * P, 0.f);
+  uint32_t max_chars = 0;
+  for (uint32_t l = 0; l < L; ++l) {
+    const uint32_t chunk = l / ctx->tpc, t = l % ctx->tpc;
+    uint32_t chars = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+      const double *row = a + ((size_t)l * K + k) * dim;
+      const uint32_t slot = t * ctx->Kp + k;
+      double A = 0.0, Bmax = 0.0;
+      for (uint32_t pos = 0; pos < len; ++pos) {
+        double amax = 0.0, tmax = 0.0;
+        for (int c = 0; c < HS_AA; ++c) {
+          double s = 0.0, sa = 0.0;
+          for (int j = 0; j < HS_CDIM; ++j) {
+            const double term = ctx->table64[c * HS_CDIM + j] * row[pos * HS_CDIM + j];
+            s += term;
+            sa += fabs(term);
+          }
+          T32[(((size_t)chunk * len + pos) * HS_AA + c) * P + slot] = (float)s;
+          amax = std::max(amax, sa);
+          tmax = std::max(tmax, fabs(s));
+        }
+        A += amax;
+        Bmax += tmax;
+      }
+      const double bb = b[(size_t)l * K + k];
+      b32[(size_t)chunk * P + slot] = (float)bb;
+      // |t_fp32 - t_real| <= (len + 6) * 2^-24 * (A + |b|) / W  (see DESIGN.md);
+      // doubled, plus an absolute floor.
+      const double Et = (double)(len + 6) * ldexp(1.0, -24) * (A + fabs(bb)) / W;
+      eps32[(size_t)chunk * P + slot] = (float)(2.0 * Et + 1e-6);
+      // bucket range over all possible fragments -> characters of to_string
+      const double slack = 1e-9 * (Bmax + fabs(bb)) + 1.0;
+      const long long lo = (long long)floor((-Bmax + bb) / W - slack);
+      const long long hi = (long long)floor((Bmax + bb) / W + slack);
+      char buf[32];
+      uint32_t c1 = (uint32_t)snprintf(buf, sizeof buf, "%lld", lo);
+      uint32_t c2 = (uint32_t)snprintf(buf, sizeof buf, "%lld", hi);
+      chars += std::max(c1, c2);
+    }
+    max_chars = std::max(max_chars, chars);
+  }
+  ctx->max_chars = max_chars;
+  ctx->key_words = (max_chars + 15) / 16;
+  if (ctx->key_words == 0) ctx->key_words = 1;
+  if (ctx->key_words > HS_MAX_KEY_WORDS) {
+    set_error("hs_set_projection: key strings need up to %u characters (> %d); raise W or lower K", max_chars,
+              16 * HS_MAX_KEY_WORDS);
+    return HS_ERR_UNSUPPORTED;
+  }
+  HS_TRY(ctx->d_T32.reserve(T32.size() * sizeof(float)));
+  HS_TRY(ctx->d_b32.reserve(b32.size() * sizeof(float)));
+  HS_TRY(ctx->d_eps32.reserve(eps32.size() * sizeof(float)));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_T32.p, T32.data(), T32.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_b32.p, b32.data(), b32.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_eps32.p, eps32.data(), eps32.size() * sizeof(float), cudaMemcpyHostToDevice,
+                          ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  ctx->have_projection = true;
+  ctx->hashed = false;
+  ctx->indexed = false;
+  return HS_OK;
+}
+
+}  // namespace hs

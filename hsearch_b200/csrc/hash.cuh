@@ -1,0 +1,94 @@
+// K1: p-stable LSH hash of residue-code fragments (H2-H4 of SURVEY.md 8a).
+//
+// Reference: LSH::DotProduct / HashBucketIndex / HashKey, hclust/src/hclust/
+// lsh.hpp:33-59, over the build loop motif_both_points.cpp:212-216.
+//
+// Fast path (FP32): because a fragment is a string over 20 letters, the dot
+// product a.v splits into `len` residue terms.  The host precomputes
+// T[pos][code][proj] = sum_j table[code][j] * a[proj][8*pos+j] (FP64, rounded
+// to FP32); a fragment's dot product is then `len` shared-memory lookups and
+// FP32 adds per projection instead of 8*len FMAs.  Each projection carries a
+// rigorous error bound eps (host, hash_host.cpp): if (dot+b)/W lies within eps
+// of an integer the projection is recomputed in FP64 in the reference's exact
+// operation order (sequential multiply, then add; division; floor).  Outside
+// the guard band FP32 and FP64 buckets provably agree, so keys are bit-exact.
+#pragma once
+#include "common.cuh"
+
+namespace hs {
+
+// ---- packed digit-string key -------------------------------------------------
+// HashKey (lsh.hpp:51-59) concatenates std::to_string(bucket) with no
+// separator, so (1,23) and (12,3) share a bucket.  The packed key therefore
+// encodes the *string*: one nibble per character ('0'..'9' -> 1..10, '-' ->
+// 11), appended left to right into a KW*64-bit big integer (word 0 least
+// significant).  All nibbles are non-zero, so two strings are equal iff their
+// packed integers are equal, whatever their lengths.
+template <int KW>
+struct KeyBuilder {
+  uint64_t w[KW];
+  int nchars;
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < KW; ++i) w[i] = 0;
+    nchars = 0;
+  }
+  __device__ __forceinline__ void push(uint32_t nib) {
+#pragma unroll
+    for (int j = KW - 1; j > 0; --j) w[j] = (w[j] << 4) | (w[j - 1] >> 60);
+    w[0] = (w[0] << 4) | (uint64_t)nib;
+    ++nchars;
+  }
+  // std::to_string(int)
+  __device__ __forceinline__ void push_int(int v) {
+    uint32_t u = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+    if (v < 0) push(11u);
+    if (u < 10u) {
+      push(u + 1u);
+      return;
+    }
+    uint32_t p = 10u;
+    while (u / p >= 10u) p *= 10u;
+    for (; p > 0u; p /= 10u) {
+      uint32_t d = u / p;
+      u -= d * p;
+      push(d + 1u);
+    }
+  }
+};
+
+// FP64 bucket of one projection in the reference's operation order
+// (lsh.hpp:33-49): dot += point[i] * a[i] with separate multiply and add,
+// val = dot + b, floor(val / W).
+__device__ __forceinline__ int exact_bucket_codes(const uint8_t *codes, int len,
+                                                  const double *__restrict__ table64,
+                                                  const double *__restrict__ a_row, double b, double W) {
+  double dot = 0.0;
+  for (int pos = 0; pos < len; ++pos) {
+    const double *row = table64 + (int)codes[pos] * HS_CDIM;
+#pragma unroll
+    for (int j = 0; j < HS_CDIM; ++j) dot = __dadd_rn(dot, __dmul_rn(row[j], a_row[pos * HS_CDIM + j]));
+  }
+  double val = __dadd_rn(dot, b);
+  return (int)floor(__ddiv_rn(val, W));
+}
+
+__device__ __forceinline__ int exact_bucket_point(const double *__restrict__ pt, int dim,
+                                                  const double *__restrict__ a_row, double b, double W) {
+  double dot = 0.0;
+  for (int i = 0; i < dim; ++i) dot = __dadd_rn(dot, __dmul_rn(pt[i], a_row[i]));
+  double val = __dadd_rn(dot, b);
+  return (int)floor(__ddiv_rn(val, W));
+}
+
+struct HashChunkArgs {
+  uint64_t *keys[8];  // per table of the chunk: [KW][N]
+  int l0;             // first table of the chunk
+  int ntab;           // tables in the chunk
+};
+
+int launch_hash_fast(hs_ctx *ctx, bool want_buckets);
+int launch_hash_exact(hs_ctx *ctx, bool want_buckets, bool audit);
+int launch_hash_queries(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint64_t *d_qkeys, uint8_t *d_qvalid);
+
+}  // namespace hs

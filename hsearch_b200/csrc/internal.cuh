@@ -1,0 +1,15 @@
+// Helpers shared between api.cu and cluster.cu.
+#pragma once
+#include "common.cuh"
+#include "verify.cuh"
+namespace hs {
+void stats_begin(hs_ctx *ctx);
+float ev_ms(cudaEvent_t a, cudaEvent_t b);
+float filter_threshold(const hs_ctx *ctx);
+const uint8_t *const *dev_stores(hs_ctx *ctx);
+const uint32_t *const *dev_sorted_ids(hs_ctx *ctx);
+const uint64_t *const *dev_keys(hs_ctx *ctx);
+void fill_exact_common(hs_ctx *ctx, ExactArgs &ea, uint32_t Q);
+int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out);
+int ensure_identity_store(hs_ctx *ctx);
+}  // namespace hs

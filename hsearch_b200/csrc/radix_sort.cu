@@ -1,0 +1,522 @@
+// K2: hand-written LSD radix sort of (packed key, fragment id) pairs, bucket
+// grouping, and the bucket-ordered code store.  Replaces the
+// unordered_map<string, vector<uint32_t>> insert of motif_both_points.cpp:212-216
+// (HashTable, :25): after a stable sort by key, one bucket is one contiguous
+// run of ids in ascending id order -- the reference's insertion order.
+//
+// Sort structure (per 8-bit digit pass): upsweep (per-tile digit histogram) ->
+// device-wide exclusive scan of the digit-major histogram -> downsweep (stable
+// in-tile ranking with warp match, shared-memory reorder, coalesced scatter).
+// Keys are KW 64-bit words stored word-major (SoA); a pass ranks on one word
+// and moves all words.  Digit windows are placed only over bits that actually
+// vary across the input (OR/AND reduction), so constant nibbles cost nothing.
+#include <algorithm>
+
+#include "sort.cuh"
+
+namespace hs {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile
+constexpr int kSortWarps = kSortThreads / 32;
+
+// ---- OR / AND reduction of the key words -------------------------------------
+__global__ void key_bits_kernel(const uint64_t *__restrict__ keys, uint64_t n, int nw,
+                                unsigned long long *__restrict__ or_and /* [nw][2] */) {
+  for (int w = 0; w < nw; ++w) {
+    unsigned long long o = 0ull, a = ~0ull;
+    const uint64_t *kw = keys + (uint64_t)w * n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+      const unsigned long long v = kw[i];
+      o |= v;
+      a &= v;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      o |= __shfl_xor_sync(0xffffffffu, o, s);
+      a &= __shfl_xor_sync(0xffffffffu, a, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicOr(or_and + 2 * w, o);
+      atomicAnd(or_and + 2 * w + 1, a);
+    }
+  }
+}
+
+// ---- upsweep: per-tile digit histogram, digit-major output --------------------
+__global__ void __launch_bounds__(kSortThreads)
+radix_upsweep_kernel(const uint64_t *__restrict__ kword, uint64_t n, int shift, uint32_t mask,
+                     uint32_t *__restrict__ tile_hist, uint32_t ntiles) {
+  __shared__ uint32_t s_hist[256];
+  const int tid = threadIdx.x;
+  s_hist[tid] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+#pragma unroll 4
+  for (int j = 0; j < kSortItems; ++j) {
+    const uint64_t idx = base + (uint64_t)j * kSortThreads + tid;
+    if (idx < n) {
+      const uint32_t d = (uint32_t)(kword[idx] >> shift) & mask;
+      atomicAdd(&s_hist[d], 1u);
+    }
+  }
+  __syncthreads();
+  tile_hist[(uint64_t)tid * ntiles + blockIdx.x] = s_hist[tid];
+}
+
+// ---- device-wide exclusive scan (u32), three phases ---------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp /*[8]*/, uint32_t &total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, s);
+    if (lane >= s) x += y;
+  }
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  uint32_t woff = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t t = s_warp[i];
+    if (i < wid) woff += t;
+    tot += t;
+  }
+  total = tot;
+  __syncthreads();
+  return woff + x - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_reduce_kernel(const uint32_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ block_sums) {
+  __shared__ uint32_t s_warp[8];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    const uint64_t idx = base + (uint64_t)j * kScanThreads + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  uint32_t total;
+  block_exclusive_scan_256(s, s_warp, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_sums in place; total -> *total_out
+__global__ void __launch_bounds__(kScanThreads)
+scan_sums_kernel(uint32_t *__restrict__ block_sums, uint32_t nblocks, uint32_t *__restrict__ total_out) {
+  __shared__ uint32_t s_warp[8];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nblocks; base += kScanThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? block_sums[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan_256(v, s_warp, total);
+    if (i < nblocks) block_sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_downsweep_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t n,
+                      const uint32_t *__restrict__ block_sums) {
+  __shared__ uint32_t s_warp[8];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    v[j] = (base + j < n) ? in[base + j] : 0u;
+    s += v[j];
+  }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan_256(s, s_warp, total) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    if (base + j < n) out[base + j] = off;
+    off += v[j];
+  }
+}
+
+int exclusive_scan_u32(hs_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *d_total) {
+  if (n == 0) {
+    if (d_total) HS_CUDA(cudaMemsetAsync(d_total, 0, sizeof(uint32_t), ctx->stream));
+    return HS_OK;
+  }
+  const uint32_t nblocks = (uint32_t)((n + kScanTile - 1) / kScanTile);
+  HS_TRY(ctx->sort.block_sums.reserve(sizeof(uint32_t) * (nblocks + 1)));
+  uint32_t *sums = ctx->sort.block_sums.as<uint32_t>();
+  scan_reduce_kernel<<<nblocks, kScanThreads, 0, ctx->stream>>>(in, n, sums);
+  scan_sums_kernel<<<1, kScanThreads, 0, ctx->stream>>>(sums, nblocks, d_total);
+  scan_downsweep_kernel<<<nblocks, kScanThreads, 0, ctx->stream>>>(in, out, n, sums);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches += 3;
+  return HS_OK;
+}
+
+// ---- downsweep: stable rank + reorder + scatter -------------------------------
+constexpr size_t kDownsweepSmem = sizeof(uint64_t) * kSortTile + sizeof(uint32_t) * kSortTile;
+
+template <int NW>
+__global__ void __launch_bounds__(kSortThreads)
+radix_downsweep_kernel(KeyPtrs in, const uint32_t *__restrict__ val_in, KeyPtrs out,
+                       uint32_t *__restrict__ val_out, uint64_t n, int word, int shift, uint32_t mask,
+                       const uint32_t *__restrict__ tile_off, uint32_t ntiles) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  uint64_t *s_key = reinterpret_cast<uint64_t *>(sort_smem);                               // 32 KB
+  uint32_t *s_val = reinterpret_cast<uint32_t *>(sort_smem + sizeof(uint64_t) * kSortTile);  // 16 KB
+  __shared__ uint32_t s_whist[kSortWarps][257];         // per-warp digit counters (+ tail bin)
+  __shared__ uint32_t s_dstart[257];
+  __shared__ uint32_t s_goff[256];
+  __shared__ uint32_t s_warp[8];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int i = tid; i < kSortWarps * 257; i += kSortThreads) (&s_whist[0][0])[i] = 0;
+  __syncthreads();
+
+  const uint64_t tile_base = (uint64_t)blockIdx.x * kSortTile;
+  const uint64_t warp_base = tile_base + (uint64_t)wid * (32 * kSortItems);
+  const uint64_t *kw = in.w[word];
+
+  uint64_t key[kSortItems];
+  uint32_t rank[kSortItems];  // rank within (warp, digit)
+  uint32_t dig[kSortItems];
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
+    const bool valid = idx < n;
+    key[j] = valid ? kw[idx] : ~0ull;
+    dig[j] = valid ? ((uint32_t)(key[j] >> shift) & mask) : 256u;
+  }
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const uint32_t d = dig[j];
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t pre = s_whist[wid][d];
+    __syncwarp();
+    rank[j] = pre + __popc(peers & lt_mask);
+    if ((peers & lt_mask) == 0) s_whist[wid][d] = pre + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // per digit: exclusive prefix over warps, tile count
+  uint32_t cnt = 0;
+  {
+    const int d = tid;  // 256 threads <-> 256 digits
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = s_whist[w][d];
+      s_whist[w][d] = cnt;
+      cnt += c;
+    }
+  }
+  uint32_t total_valid;
+  const uint32_t dstart = block_exclusive_scan_256(cnt, s_warp, total_valid);
+  s_dstart[tid] = dstart;
+  s_goff[tid] = tile_off[(uint64_t)tid * ntiles + blockIdx.x] - dstart;  // dst = goff[d] + p (mod 2^32)
+  if (tid == 0) {
+    s_dstart[256] = total_valid;
+    uint32_t run = 0;
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = s_whist[w][256];
+      s_whist[w][256] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+
+  uint32_t lp[kSortItems];
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const uint32_t d = dig[j];
+    lp[j] = s_dstart[d] + s_whist[wid][d] + rank[j];
+    s_key[lp[j]] = key[j];
+    const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
+    s_val[lp[j]] = val_in ? (idx < n ? val_in[idx] : 0u) : (uint32_t)idx;
+  }
+  __syncthreads();
+
+  uint32_t dst[kSortItems];
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const uint32_t p = (uint32_t)j * kSortThreads + tid;
+    if (p < total_valid) {
+      const uint64_t k = s_key[p];
+      const uint32_t d = (uint32_t)(k >> shift) & mask;
+      dst[j] = s_goff[d] + p;
+      out.w[word][dst[j]] = k;
+      val_out[dst[j]] = s_val[p];
+    }
+  }
+  // remaining key words ride along through the same staging buffer
+#pragma unroll
+  for (int w2 = 0; w2 < NW; ++w2) {
+    if (w2 == word) continue;
+    __syncthreads();
+    const uint64_t *src = in.w[w2];
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
+      s_key[lp[j]] = idx < n ? src[idx] : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const uint32_t p = (uint32_t)j * kSortThreads + tid;
+      if (p < total_valid) out.w[w2][dst[j]] = s_key[p];
+    }
+  }
+}
+
+// ---- bucket grouping ------------------------------------------------------------
+template <int NW>
+__global__ void head_flags_kernel(KeyPtrs keys, uint64_t n, uint32_t *__restrict__ flags) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool head = (i == 0);
+  if (!head) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) head = head || (keys.w[w][i] != keys.w[w][i - 1]);
+  }
+  flags[i] = head ? 1u : 0u;
+}
+
+template <int NW>
+__global__ void bucket_scatter_kernel(KeyPtrs keys, uint64_t n, const uint32_t *__restrict__ flags,
+                                      const uint32_t *__restrict__ scanned, uint64_t nb,
+                                      uint64_t *__restrict__ ukeys /* [NW][nb] */,
+                                      uint32_t *__restrict__ bstart /* [nb+1] */) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) bstart[nb] = (uint32_t)n;
+  if (i >= n) return;
+  if (flags[i]) {
+    const uint32_t b = scanned[i];
+    bstart[b] = (uint32_t)i;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) ukeys[(uint64_t)w * nb + b] = keys.w[w][i];
+  }
+}
+
+// ---- bucket-ordered, position-major code store ---------------------------------
+// out[pos][i] = 4 * codes[ids[i]][pos]; four consecutive i per thread so that
+// stores are 32-bit and coalesced.  ids == nullptr: identity order.
+__global__ void permute_codes_kernel(const uint8_t *__restrict__ codes, const uint32_t *__restrict__ ids,
+                                     uint64_t n, uint64_t npad, int len, uint8_t *__restrict__ out) {
+  const uint64_t i4 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  uint64_t id[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const uint64_t i = i4 + m;
+    id[m] = i < n ? (ids ? (uint64_t)ids[i] : i) : ~0ull;
+  }
+  for (int pos = 0; pos < len; ++pos) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const uint32_t c = id[m] != ~0ull ? (uint32_t)codes[id[m] * len + pos] * kCodeScale : 0u;
+      packed |= c << (8 * m);
+    }
+    *reinterpret_cast<uint32_t *>(out + (uint64_t)pos * npad + i4) = packed;
+  }
+}
+
+__global__ void iota_kernel(uint32_t *out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+}
+
+// ---- host orchestration ---------------------------------------------------------
+struct Pass {
+  int word, shift;
+  uint32_t mask;
+};
+
+static void plan_passes(const unsigned long long *or_and, int nw, std::vector<Pass> &passes) {
+  for (int w = 0; w < nw; ++w) {
+    uint64_t vary = or_and[2 * w] & ~or_and[2 * w + 1];
+    int bit = 0;
+    while (vary >> bit) {
+      if (!((vary >> bit) & 1ull)) {
+        ++bit;
+        continue;
+      }
+      const int width = std::min(8, 64 - bit);
+      passes.push_back({w, bit, (uint32_t)((1u << width) - 1u)});
+      bit += width;
+      if (bit >= 64) break;
+    }
+  }
+}
+
+template <int NW>
+static void launch_downsweep(hs_ctx *ctx, const KeyPtrs &in, const uint32_t *vin, const KeyPtrs &out,
+                             uint32_t *vout, uint64_t n, const Pass &p, const uint32_t *tile_off,
+                             uint32_t ntiles) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(radix_downsweep_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kDownsweepSmem);
+    attr_set = true;
+  }
+  radix_downsweep_kernel<NW><<<ntiles, kSortThreads, kDownsweepSmem, ctx->stream>>>(
+      in, vin, out, vout, n, p.word, p.shift, p.mask, tile_off, ntiles);
+}
+
+// Stable LSD sort of n (key, value) pairs.  keys_in: nw word arrays (not
+// modified).  Values are the implicit index 0..n-1 when vals_in == nullptr.
+// The sorted values land in v_final (v_tmp is the ping-pong partner); the
+// sorted key words are left in the scratch (or in keys_in when no bit varies)
+// and returned through *sorted_keys, valid until the next sort.
+int radix_sort_pairs(hs_ctx *ctx, const KeyPtrs &keys_in, const uint32_t *vals_in, uint64_t n, int nw,
+                     uint32_t *v_final, uint32_t *v_tmp, KeyPtrs *sorted_keys) {
+  SortScratch &S = ctx->sort;
+  *sorted_keys = keys_in;
+  if (n == 0) return HS_OK;
+  for (int w = 0; w < nw; ++w) {
+    HS_TRY(S.keys_cur[w].reserve(sizeof(uint64_t) * n));
+    HS_TRY(S.keys_alt[w].reserve(sizeof(uint64_t) * n));
+  }
+  HS_TRY(S.or_and.reserve(sizeof(unsigned long long) * 2 * kMaxKeyWords));
+  unsigned long long h_init[2 * kMaxKeyWords], h_oa[2 * kMaxKeyWords];
+  for (int w = 0; w < kMaxKeyWords; ++w) {
+    h_init[2 * w] = 0ull;
+    h_init[2 * w + 1] = ~0ull;
+  }
+  unsigned long long *d_oa = S.or_and.as<unsigned long long>();
+  HS_CUDA(cudaMemcpyAsync(d_oa, h_init, sizeof h_init, cudaMemcpyHostToDevice, ctx->stream));
+  for (int w = 0; w < nw; ++w) {
+    key_bits_kernel<<<148 * 4, 256, 0, ctx->stream>>>(keys_in.w[w], n, 1, d_oa + 2 * w);
+    ctx->stats.kernel_launches++;
+  }
+  HS_CUDA(cudaMemcpyAsync(h_oa, d_oa, sizeof h_oa, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<Pass> passes;
+  plan_passes(h_oa, nw, passes);
+
+  KeyPtrs A, B;
+  for (int w = 0; w < kMaxKeyWords; ++w) {
+    A.w[w] = w < nw ? S.keys_cur[w].as<uint64_t>() : nullptr;
+    B.w[w] = w < nw ? S.keys_alt[w].as<uint64_t>() : nullptr;
+  }
+  if (passes.empty()) {
+    if (vals_in) {
+      HS_CUDA(cudaMemcpyAsync(v_final, vals_in, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v_final, n);
+      ctx->stats.kernel_launches++;
+    }
+    HS_CUDA(cudaGetLastError());
+    return HS_OK;
+  }
+  const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+  HS_TRY(S.tile_hist.reserve(sizeof(uint32_t) * ((uint64_t)ntiles * 256 + 1)));
+  uint32_t *tile_hist = S.tile_hist.as<uint32_t>();
+
+  KeyPtrs src = keys_in, dst = A;
+  const uint32_t *vsrc = vals_in;
+  // values ping-pong so that the last pass lands in v_final
+  uint32_t *vdst = (passes.size() & 1) ? v_final : v_tmp;
+  for (size_t pi = 0; pi < passes.size(); ++pi) {
+    const Pass &p = passes[pi];
+    radix_upsweep_kernel<<<ntiles, kSortThreads, 0, ctx->stream>>>(src.w[p.word], n, p.shift, p.mask, tile_hist,
+                                                                  ntiles);
+    ctx->stats.kernel_launches++;
+    HS_TRY(exclusive_scan_u32(ctx, tile_hist, tile_hist, (uint64_t)ntiles * 256, nullptr));
+    switch (nw) {
+      case 1: launch_downsweep<1>(ctx, src, vsrc, dst, vdst, n, p, tile_hist, ntiles); break;
+      case 2: launch_downsweep<2>(ctx, src, vsrc, dst, vdst, n, p, tile_hist, ntiles); break;
+      case 3: launch_downsweep<3>(ctx, src, vsrc, dst, vdst, n, p, tile_hist, ntiles); break;
+      default: launch_downsweep<4>(ctx, src, vsrc, dst, vdst, n, p, tile_hist, ntiles); break;
+    }
+    ctx->stats.kernel_launches++;
+    ctx->stats.sort_passes++;
+    HS_CUDA(cudaGetLastError());
+    vsrc = vdst;
+    vdst = (vdst == v_final) ? v_tmp : v_final;
+    src = dst;
+    dst = (dst.w[0] == A.w[0]) ? B : A;
+  }
+  *sorted_keys = src;
+  return HS_OK;
+}
+
+static int sort_table(hs_ctx *ctx, uint32_t table, KeyPtrs *sorted_keys) {
+  const uint64_t n = ctx->N;
+  const int nw = (int)ctx->key_words;
+  TableIndex &T = ctx->tables[table];
+  HS_TRY(T.sorted_ids.reserve(sizeof(uint32_t) * n));
+  HS_TRY(ctx->sort.vals_alt.reserve(sizeof(uint32_t) * n));
+  KeyPtrs in;
+  for (int w = 0; w < kMaxKeyWords; ++w)
+    in.w[w] = w < nw ? ctx->d_keys[table].as<uint64_t>() + (uint64_t)w * n : nullptr;
+  return radix_sort_pairs(ctx, in, nullptr, n, nw, T.sorted_ids.as<uint32_t>(), ctx->sort.vals_alt.as<uint32_t>(),
+                          sorted_keys);
+}
+
+template <int NW>
+static int group_inst(hs_ctx *ctx, uint32_t table, const KeyPtrs &keys) {
+  const uint64_t n = ctx->N;
+  SortScratch &S = ctx->sort;
+  TableIndex &T = ctx->tables[table];
+  HS_TRY(S.flags.reserve(sizeof(uint32_t) * 2 * n + 16));
+  uint32_t *flags = S.flags.as<uint32_t>();
+  uint32_t *scanned = flags + n;
+  HS_TRY(S.or_and.reserve(sizeof(unsigned long long) * 2 * kMaxKeyWords));
+  uint32_t *d_total = S.or_and.as<uint32_t>();
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  head_flags_kernel<NW><<<grid, 256, 0, ctx->stream>>>(keys, n, flags);
+  ctx->stats.kernel_launches++;
+  HS_TRY(exclusive_scan_u32(ctx, flags, scanned, n, d_total));
+  uint32_t nb = 0;
+  HS_CUDA(cudaMemcpyAsync(&nb, d_total, sizeof nb, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  T.nb = nb;
+  HS_TRY(T.ukeys.reserve(sizeof(uint64_t) * NW * (uint64_t)std::max<uint32_t>(nb, 1)));
+  HS_TRY(T.bstart.reserve(sizeof(uint32_t) * ((uint64_t)nb + 1)));
+  bucket_scatter_kernel<NW><<<grid, 256, 0, ctx->stream>>>(keys, n, flags, scanned, nb, T.ukeys.as<uint64_t>(),
+                                                         T.bstart.as<uint32_t>());
+  ctx->stats.kernel_launches++;
+  HS_CUDA(cudaGetLastError());
+  return HS_OK;
+}
+
+int build_code_store(hs_ctx *ctx, const uint32_t *ids, DevBuf &out) {
+  const uint64_t n = ctx->N;
+  const size_t bytes = (size_t)ctx->prm.len * ctx->npad + 16;
+  if (out.cap < bytes) {
+    HS_TRY(out.reserve(bytes));
+    HS_CUDA(cudaMemsetAsync(out.p, 0, out.cap, ctx->stream));
+  }
+  const uint64_t nthreads = (n + 3) / 4;
+  permute_codes_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
+      ctx->d_codes.as<uint8_t>(), ids, n, ctx->npad, (int)ctx->prm.len, out.as<uint8_t>());
+  ctx->stats.kernel_launches++;
+  HS_CUDA(cudaGetLastError());
+  return HS_OK;
+}
+
+int build_table_index(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cudaEvent_t ev_group_end) {
+  KeyPtrs sorted;
+  HS_TRY(sort_table(ctx, table, &sorted));
+  HS_CUDA(cudaEventRecord(ev_sort_end, ctx->stream));
+  switch (ctx->key_words) {
+    case 1: HS_TRY(group_inst<1>(ctx, table, sorted)); break;
+    case 2: HS_TRY(group_inst<2>(ctx, table, sorted)); break;
+    case 3: HS_TRY(group_inst<3>(ctx, table, sorted)); break;
+    default: HS_TRY(group_inst<4>(ctx, table, sorted)); break;
+  }
+  HS_CUDA(cudaEventRecord(ev_group_end, ctx->stream));
+  HS_TRY(build_code_store(ctx, ctx->tables[table].sorted_ids.as<uint32_t>(), ctx->tables[table].codes_sorted));
+  return HS_OK;
+}
+
+}  // namespace hs

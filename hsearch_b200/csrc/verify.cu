@@ -1,0 +1,368 @@
+// K3 (probe + candidate verification), K4 (brute force) and the pair stage of
+// K5 (in-bucket near pairs) share one pair engine:
+//
+//   filter kernel  -- for every (query, member) pair of a work item, a cheap
+//                     bound on the distance: `len` shared-memory lookups of a
+//                     per-query residue table Tq[pos][code] and FP32 adds
+//                     (exact integer arithmetic for the BLOSUM metric).  Pairs
+//                     that cannot be within R are dropped here.
+//   exact kernel   -- the survivors are re-evaluated exactly as the reference
+//                     does (PairwiseDistance_square, motif_both_points.cpp:
+//                     176-183: sequential FP64 subtract, multiply, add; or
+//                     DistanceScore, evaluate_correlation.cpp:34-41), the
+//                     reference's threshold predicate is applied, the
+//                     first-table-wins rule of label[] (:232-238) is enforced
+//                     by comparing the pair's keys in earlier tables, and hits
+//                     (or union-find edges) are emitted.
+//
+// The filter never decides a hit; it only rejects pairs whose distance is
+// provably above the threshold (margin derivation in DESIGN.md), so hit sets
+// and distances are bit-exact.
+#include <math.h>
+
+#include "verify.cuh"
+
+namespace hs {
+
+// ---- probe: query key -> bucket range (HashTable::find, :228-231) -------------
+template <int KW>
+__global__ void probe_kernel(const uint64_t *__restrict__ qkeys /* [Q][KW] of this table */,
+                             const uint8_t *__restrict__ qvalid, uint32_t Q,
+                             const uint64_t *__restrict__ ukeys /* [KW][nb] */, uint64_t nb,
+                             const uint32_t *__restrict__ bstart, uint2 *__restrict__ qrange) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  uint2 r = make_uint2(0u, 0u);
+  if (qvalid[q] && nb > 0) {
+    uint64_t k[KW];
+#pragma unroll
+    for (int w = 0; w < KW; ++w) k[w] = qkeys[(size_t)q * KW + w];
+    uint64_t lo = 0, hi = nb;  // lower bound
+    while (lo < hi) {
+      const uint64_t m = (lo + hi) >> 1;
+      bool less = false, decided = false;
+#pragma unroll
+      for (int w = KW - 1; w >= 0; --w) {
+        const uint64_t u = ukeys[(uint64_t)w * nb + m];
+        if (!decided && u != k[w]) {
+          less = u < k[w];
+          decided = true;
+        }
+      }
+      if (less) lo = m + 1; else hi = m;
+    }
+    if (lo < nb) {
+      bool eq = true;
+#pragma unroll
+      for (int w = 0; w < KW; ++w) eq = eq && (ukeys[(uint64_t)w * nb + lo] == k[w]);
+      if (eq) r = make_uint2(bstart[lo], bstart[lo + 1]);
+    }
+  }
+  qrange[q] = r;
+}
+
+int launch_probe(hs_ctx *ctx, uint32_t table, const uint64_t *d_qkeys, const uint8_t *d_qvalid, uint32_t Q,
+                 uint2 *d_qrange) {
+  if (Q == 0) return HS_OK;
+  const TableIndex &T = ctx->tables[table];
+  const unsigned grid = (Q + 127) / 128;
+  const uint64_t *qk = d_qkeys + (size_t)table * Q * ctx->key_words;
+  const uint8_t *qv = d_qvalid + (size_t)table * Q;
+  uint2 *qr = d_qrange + (size_t)table * Q;
+#define HS_PROBE(KWV)                                                                                      \
+  probe_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(qk, qv, Q, T.ukeys.as<uint64_t>(), T.nb,                \
+                                                   T.bstart.as<uint32_t>(), qr)
+  switch (ctx->key_words) {
+    case 1: HS_PROBE(1); break;
+    case 2: HS_PROBE(2); break;
+    case 3: HS_PROBE(3); break;
+    default: HS_PROBE(4); break;
+  }
+#undef HS_PROBE
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+// ---- per-query filter tables ----------------------------------------------------
+// Tq[q][pos][c] = fl32( sum_j (table[c][j] - q[8*pos+j])^2 ): the squared distance
+// contribution of residue c at position pos.
+__global__ void build_tq_points_kernel(const double *__restrict__ q64, uint32_t Q, int len,
+                                       const double *__restrict__ table64, float *__restrict__ tq) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n = (uint64_t)Q * len * HS_AA;
+  if (i >= n) return;
+  const int c = (int)(i % HS_AA);
+  const uint64_t qp = i / HS_AA;  // q*len + pos
+  const double *qv = q64 + qp * HS_CDIM;
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < HS_CDIM; ++j) {
+    const double r = table64[c * HS_CDIM + j] - qv[j];
+    s += r * r;
+  }
+  tq[i] = (float)s;
+}
+// Integer metric: Tq[q][pos][c] = D[c][qcode[pos]] (exact in FP32).
+__global__ void build_tq_int_kernel(const uint8_t *__restrict__ qcodes, uint32_t Q, int len,
+                                    const int32_t *__restrict__ metric, float *__restrict__ tq) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n = (uint64_t)Q * len * HS_AA;
+  if (i >= n) return;
+  const int c = (int)(i % HS_AA);
+  const uint64_t qp = i / HS_AA;
+  tq[i] = (float)metric[c * HS_AA + qcodes[qp]];
+}
+
+int launch_build_tq_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, float *d_tq) {
+  const uint64_t n = (uint64_t)Q * ctx->prm.len * HS_AA;
+  if (n == 0) return HS_OK;
+  build_tq_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      d_q64, Q, (int)ctx->prm.len, ctx->d_table64.as<double>(), d_tq);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+int launch_build_tq_int(hs_ctx *ctx, const uint8_t *d_qcodes, uint32_t Q, float *d_tq) {
+  const uint64_t n = (uint64_t)Q * ctx->prm.len * HS_AA;
+  if (n == 0) return HS_OK;
+  build_tq_int_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      d_qcodes, Q, (int)ctx->prm.len, ctx->d_metric.as<int32_t>(), d_tq);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+// ---- filter -----------------------------------------------------------------------
+template <int MODE, int LENB>
+__global__ void __launch_bounds__(kFilterThreads)
+filter_kernel(FilterArgs a) {
+  extern __shared__ __align__(16) float s_tq[];  // [kFilterQChunk][len*20]
+  __shared__ WorkItem s_item;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    uint32_t lo = 0, hi = a.nitems;  // last item with block_begin <= blockIdx.x
+    while (hi - lo > 1) {
+      const uint32_t m = (lo + hi) >> 1;
+      if (a.items[m].block_begin <= blockIdx.x) lo = m; else hi = m;
+    }
+    s_item = a.items[lo];
+  }
+  __syncthreads();
+  const WorkItem it = s_item;
+  const int len = a.len;
+  const int rowlen = len * HS_AA;
+  const uint32_t tile = blockIdx.x - it.block_begin;
+  const uint32_t pos0 = (it.m_begin & ~3u) + tile * kFilterTile + (uint32_t)tid * kFilterMembers;
+  const uint8_t *store = a.stores[it.table];
+
+  uint32_t cw[LENB];
+#pragma unroll
+  for (int p = 0; p < LENB; ++p)
+    cw[p] = (p < len && pos0 < it.m_end) ? *reinterpret_cast<const uint32_t *>(store + (uint64_t)p * a.npad + pos0) : 0u;
+  bool mvalid[kFilterMembers];
+#pragma unroll
+  for (int m = 0; m < kFilterMembers; ++m) mvalid[m] = (pos0 + m >= it.m_begin) && (pos0 + m < it.m_end);
+
+  // self join: only queries positioned before the last member of this tile matter
+  const uint32_t q_end = (MODE == kModeSelfJoin)
+                             ? min(it.q_end, (it.m_begin & ~3u) + (tile + 1) * kFilterTile)
+                             : it.q_end;
+  for (uint32_t qc = it.q_begin; qc < q_end; qc += kFilterQChunk) {
+    const int nq = (int)min((uint32_t)kFilterQChunk, q_end - qc);
+    __syncthreads();
+    for (int i = tid; i < nq * rowlen; i += kFilterThreads) {
+      const int qq = i / rowlen, r = i - qq * rowlen;
+      if (MODE == kModeSelfJoin) {
+        const int p = r / HS_AA, c = r - p * HS_AA;
+        const int cq = store[(uint64_t)p * a.npad + (qc + qq)] / kCodeScale;
+        s_tq[i] = a.dsq32[cq * HS_AA + c];
+      } else {
+        s_tq[i] = a.tq[(uint64_t)(a.qlist[qc + qq] - a.tq_base) * rowlen + r];
+      }
+    }
+    __syncthreads();
+    for (int qq = 0; qq < nq; ++qq) {
+      const char *row = reinterpret_cast<const char *>(s_tq + qq * rowlen);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int p = 0; p < LENB; ++p) {
+        if (p < len) {
+          const uint32_t w = cw[p];
+          const char *rp = row + p * (HS_AA * 4);
+          s0 += *reinterpret_cast<const float *>(rp + (w & 0xffu));
+          s1 += *reinterpret_cast<const float *>(rp + ((w >> 8) & 0xffu));
+          s2 += *reinterpret_cast<const float *>(rp + ((w >> 16) & 0xffu));
+          s3 += *reinterpret_cast<const float *>(rp + (w >> 24));
+        }
+      }
+      const float sv[kFilterMembers] = {s0, s1, s2, s3};
+      const uint32_t qid = (MODE == kModeSelfJoin) ? (qc + qq) : a.qlist[qc + qq];
+#pragma unroll
+      for (int m = 0; m < kFilterMembers; ++m) {
+        bool ok = mvalid[m] && sv[m] <= a.thr;
+        if (MODE != kModeSearch) ok = ok && (qid < pos0 + m);  // each unordered pair once
+        if (ok) {
+          const unsigned long long idx = atomicAdd(a.surv_count, 1ull);
+          if (idx < a.surv_cap) {
+            Survivor s;
+            s.query = qid;
+            s.table = it.table;
+            s.pos = pos0 + m;
+            s.pad = 0;
+            a.surv[idx] = s;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int MODE>
+static int launch_filter_mode(hs_ctx *ctx, const FilterArgs &a, uint32_t nblocks) {
+  const size_t smem = (size_t)kFilterQChunk * a.len * HS_AA * sizeof(float);
+#define HS_FILT(LB)                                                                     \
+  do {                                                                                  \
+    auto kern = filter_kernel<MODE, LB>;                                                \
+    if (smem > 48 * 1024)                                                               \
+      HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<nblocks, kFilterThreads, smem, ctx->stream>>>(a);                            \
+  } while (0)
+  if (a.len <= 8) HS_FILT(8);
+  else if (a.len <= 10) HS_FILT(10);
+  else if (a.len <= 12) HS_FILT(12);
+  else if (a.len <= 16) HS_FILT(16);
+  else if (a.len <= 20) HS_FILT(20);
+  else if (a.len <= 25) HS_FILT(25);
+  else HS_FILT(32);
+#undef HS_FILT
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+int launch_filter(hs_ctx *ctx, const FilterArgs &args, uint32_t nblocks, int mode) {
+  if (nblocks == 0) return HS_OK;
+  switch (mode) {
+    case kModeSearch:
+    case kModeBrute: return launch_filter_mode<kModeSearch>(ctx, args, nblocks);
+    case kModeAllPairs: return launch_filter_mode<kModeAllPairs>(ctx, args, nblocks);
+    default: return launch_filter_mode<kModeSelfJoin>(ctx, args, nblocks);
+  }
+}
+
+// ---- exact stage --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x) {
+  // path halving; parent[] only ever decreases, so racing updates stay valid
+  volatile uint32_t *p = parent;
+  while (true) {
+    const uint32_t px = p[x];
+    if (px == x) return x;
+    const uint32_t ppx = p[px];
+    if (ppx != px) p[x] = ppx;
+    x = px;
+  }
+}
+// JoinUnion (union_find.cpp:31-33) made order-independent: the larger root is
+// hooked under the smaller, so the final root of a component is its min id.
+__device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
+    if (atomicCAS(parent + hi, hi, lo) == hi) return;
+  }
+}
+
+__global__ void exact_kernel(ExactArgs a) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nsurv) return;
+  const Survivor s = a.surv[i];
+  const uint32_t *ids = a.sorted_ids[s.table];
+  const uint64_t id = ids ? (uint64_t)ids[s.pos] : (uint64_t)s.pos;
+  const uint8_t *mc = a.codes + id * a.len;
+  uint64_t qid = s.query;
+  const uint8_t *qc = nullptr;
+  if (a.mode == kModeSelfJoin) {
+    qid = ids ? (uint64_t)ids[s.query] : (uint64_t)s.query;
+    qc = a.codes + qid * a.len;
+  } else if (a.mode == kModeAllPairs && a.q64 == nullptr && a.qcodes == nullptr) {
+    qc = a.codes + qid * a.len;  // all pairs of the DB: the query is a DB fragment
+  } else if (a.qcodes) {
+    qc = a.qcodes + qid * a.len;
+  }
+
+  double d2;
+  bool hit;
+  if (a.metric == HS_METRIC_BLOSUM_INT) {
+    int d = 0;
+    for (int p = 0; p < a.len; ++p) d += a.metric_tab[(int)qc[p] * HS_AA + (int)mc[p]];
+    d2 = (double)d;
+    hit = d <= (int)a.R;
+  } else {
+    double dis = 0.0;
+    if (a.q64 && a.mode != kModeSelfJoin) {
+      const double *qp = a.q64 + qid * a.dim;
+      for (int p = 0; p < a.len; ++p) {
+        const double *row = a.table64 + (int)mc[p] * HS_CDIM;
+#pragma unroll
+        for (int j = 0; j < HS_CDIM; ++j) {
+          const double r = __dsub_rn(row[j], qp[p * HS_CDIM + j]);
+          dis = __dadd_rn(dis, __dmul_rn(r, r));
+        }
+      }
+    } else {
+      for (int p = 0; p < a.len; ++p) {
+        const double *row = a.table64 + (int)mc[p] * HS_CDIM;
+        const double *qrow = a.table64 + (int)qc[p] * HS_CDIM;
+#pragma unroll
+        for (int j = 0; j < HS_CDIM; ++j) {
+          const double r = __dsub_rn(row[j], qrow[j]);
+          dis = __dadd_rn(dis, __dmul_rn(r, r));
+        }
+      }
+    }
+    d2 = dis;
+    if (a.predicate == HS_PRED_D2_LE_R2) hit = dis <= __dmul_rn(a.R, a.R);
+    else hit = !(sqrt(dis) > a.R);
+  }
+  if (!hit) return;
+
+  if (a.mode == kModeSelfJoin) {
+    uf_union(a.parent, (uint32_t)qid, (uint32_t)id);
+    atomicAdd(a.edge_count, 1ull);
+    return;
+  }
+  if (a.mode == kModeSearch) {
+    // label[] (motif_both_points.cpp:232-238): the pair was already handled if an
+    // earlier table put this fragment in the query's bucket.
+    for (uint32_t l = 0; l < s.table; ++l) {
+      if (!a.qvalid[(size_t)l * a.Q + qid]) continue;
+      bool same = true;
+      for (int w = 0; w < a.key_words; ++w)
+        same = same && (a.keys[l][(uint64_t)w * a.N + id] == a.qkeys[((size_t)l * a.Q + qid) * a.key_words + w]);
+      if (same) return;
+    }
+  }
+  const unsigned long long idx = atomicAdd(a.hit_count, 1ull);
+  if (idx < a.hit_cap) {
+    hs_hit h;
+    h.query = (uint32_t)qid;
+    h.table_first = a.mode == kModeSearch ? s.table : 0u;
+    h.db_id = a.id_base + id;
+    h.dist2 = d2;
+    a.hits[idx] = h;
+  }
+}
+
+int launch_exact(hs_ctx *ctx, const ExactArgs &args) {
+  if (args.nsurv == 0) return HS_OK;
+  const unsigned grid = (unsigned)((args.nsurv + 127) / 128);
+  exact_kernel<<<grid, 128, 0, ctx->stream>>>(args);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+}  // namespace hs

@@ -1,0 +1,84 @@
+// K3/K4/K5 interfaces (verify.cu): probe, candidate filter, exact verify + emit.
+#pragma once
+#include "common.cuh"
+
+namespace hs {
+
+// One unit of filter work: the members [m_begin, m_end) of one bucket (positions
+// in the bucket-ordered store of `table`) against the queries
+// qlist[q_begin .. q_end).  It owns blocks [block_begin, block_begin + ntiles).
+struct WorkItem {
+  uint32_t table;
+  uint32_t m_begin, m_end;
+  uint32_t q_begin, q_end;
+  uint32_t block_begin;
+};
+
+// A (query, member) pair that passed the filter.
+struct Survivor {
+  uint32_t query;  // query index (search / brute force) or member position (self join)
+  uint32_t table;
+  uint32_t pos;    // member position in the table's bucket order
+  uint32_t pad;
+};
+
+constexpr int kFilterThreads = 256;
+constexpr int kFilterMembers = 4;                                  // members per thread
+constexpr int kFilterTile = kFilterThreads * kFilterMembers;       // members per block
+constexpr int kFilterQChunk = 8;                                   // query tables staged per step
+constexpr uint32_t kQueriesPerItem = 256;
+
+// Search: LSH query loop (dedup across tables).  AllPairs: all pairs i<j of the
+// DB.  SelfJoin: pairs i<j inside one bucket (cluster).  Brute: explicit queries
+// against the whole DB, no dedup.
+enum FilterMode { kModeSearch = 0, kModeAllPairs = 1, kModeSelfJoin = 2, kModeBrute = 3 };
+
+struct FilterArgs {
+  const WorkItem *items;
+  uint32_t nitems;
+  const uint32_t *qlist;         // query indices (search / brute force)
+  const float *tq;               // [Q][len][20] filter tables (search / brute force)
+  uint32_t tq_base;              // tq row of query id x is x - tq_base
+  const float *dsq32;            // [20][20] residue-pair table (self join)
+  const uint8_t *const *stores;  // per table: position-major code*4 store
+  uint64_t npad;
+  int len;
+  float thr;                     // pass iff filter distance <= thr
+  Survivor *surv;
+  unsigned long long surv_cap;
+  unsigned long long *surv_count;
+};
+
+int launch_probe(hs_ctx *ctx, uint32_t table, const uint64_t *d_qkeys, const uint8_t *d_qvalid, uint32_t Q,
+                 uint2 *d_qrange);
+int launch_build_tq_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, float *d_tq);
+int launch_build_tq_int(hs_ctx *ctx, const uint8_t *d_qcodes, uint32_t Q, float *d_tq);
+int launch_filter(hs_ctx *ctx, const FilterArgs &args, uint32_t nblocks, int mode);
+
+struct ExactArgs {
+  const Survivor *surv;
+  unsigned long long nsurv;
+  int mode;                      // FilterMode
+  int metric, predicate;
+  int len, dim, key_words, L;
+  double R;
+  const uint32_t *const *sorted_ids;  // per table (nullptr entry: identity)
+  const uint8_t *codes;               // [N][len]
+  uint64_t N, id_base;
+  const double *table64;
+  const int32_t *metric_tab;          // [20][20]
+  const double *q64;                  // [Q][dim]   (Euclid, search / brute force)
+  const uint8_t *qcodes;              // [Q][len]   (integer metric)
+  uint32_t Q;
+  const uint64_t *const *keys;        // per table: [KW][N] original-order keys (dedup)
+  const uint64_t *qkeys;              // [L][Q][KW]
+  const uint8_t *qvalid;              // [L][Q]
+  hs_hit *hits;
+  unsigned long long hit_cap;
+  unsigned long long *hit_count;
+  uint32_t *parent;                   // self join: union-find forest
+  unsigned long long *edge_count;
+};
+int launch_exact(hs_ctx *ctx, const ExactArgs &args);
+
+}  // namespace hs

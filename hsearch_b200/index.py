@@ -1,0 +1,202 @@
+"""Host-side mirror of the reference's search/cluster drivers over the C ABI.
+
+`HSearch` plays the role of the reference's `Search()` (hclust/src/hclust/
+motif_both_points.cpp:195-250), its brute-force twin
+(motif_both_points_noLSH.cpp:36-56) and the union-find cluster composition
+(pcluster/src/pcluster/union_find.cpp:3-33): same parameter names (hash_K,
+hash_L, hash_W, hash_R), same meaning, errors raised instead of exit codes.
+All compute goes through libhsearch_b200.so; there is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import (HIT_DTYPE, HS_FLAG_HASH_AUDIT, HS_FLAG_HASH_EXACT, HS_FLAG_SORT_HITS, HS_METRIC_BLOSUM_INT,
+                   HS_METRIC_EUCLID_FP64, HS_PRED_D2_LE_R2, HS_PRED_SQRT_LE_R, HS_TABLE_FULL, HS_TABLE_PRINT6,
+                   HsError, Params, Stats, check, ptr)
+
+AA_ORDER = "ARNDCQEGHILKMFPSTWYV"  # residue code i <-> letter (row order of `coordinates`, util.hpp:21-42)
+
+
+def coordinates(table_variant=HS_TABLE_FULL):
+    t = np.zeros(160, dtype=np.float64)
+    check(capi.load().hs_get_coordinates(table_variant, ptr(t, C.c_double)))
+    return t.reshape(20, 8)
+
+
+def blosum_metric():
+    t = np.zeros(400, dtype=np.int32)
+    check(capi.load().hs_get_blosum_metric(ptr(t, C.c_int32)))
+    return t.reshape(20, 20)
+
+
+def generate_projection(seed_base, dim, hash_K, hash_L, hash_W):
+    """LSH::LSH (lsh.hpp:10-31) for hash_L tables; table l is seeded seed_base + l.
+    Returns a [L][K][dim], b [L][K]."""
+    lib = capi.load()
+    a = np.zeros((hash_L, hash_K, dim), dtype=np.float64)
+    b = np.zeros((hash_L, hash_K), dtype=np.float64)
+    for l in range(hash_L):
+        check(lib.hs_generate_projection(seed_base + l, dim, hash_K, hash_W, ptr(a[l], C.c_double),
+                                         ptr(b[l], C.c_double)))
+    return a, b
+
+
+def encode(seqs):
+    """Letters -> residue codes (base[c-'A'], util.hpp:92)."""
+    lib = capi.load()
+    out = np.zeros((len(seqs), len(seqs[0]) if seqs else 0), dtype=np.uint8)
+    for i, s in enumerate(seqs):
+        for j, ch in enumerate(s):
+            c = lib.hs_letter_to_code(ch.encode())
+            if c < 0:
+                raise ValueError(f"'{ch}' is not one of the 20 amino-acid letters")
+            out[i, j] = c
+    return out
+
+
+def pack_key_string(s, key_words):
+    w = np.zeros(key_words, dtype=np.uint64)
+    check(capi.load().hs_pack_key_string(s.encode(), key_words, ptr(w, C.c_uint64)))
+    return w
+
+
+class HSearch:
+    def __init__(self, kmer_length, hash_K=4, hash_L=4, hash_W=50.0, hash_R=200.0, table_variant=HS_TABLE_PRINT6,
+                 metric=HS_METRIC_EUCLID_FP64, predicate=HS_PRED_D2_LE_R2, flags=HS_FLAG_SORT_HITS, device=0):
+        self.lib = capi.load()
+        self.params = Params(kmer_length, hash_K, hash_L, float(hash_W), float(hash_R), table_variant, metric,
+                             predicate, flags)
+        self.ctx = C.c_void_p()
+        check(self.lib.hs_create(C.byref(self.ctx), device, C.byref(self.params)))
+        self.len = kmer_length
+        self.dim = 8 * kmer_length
+        self.K, self.L = hash_K, hash_L
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx.value:
+            self.lib.hs_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- setup ---------------------------------------------------------------
+    def set_projection(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        assert a.shape == (self.L, self.K, self.dim) and b.shape == (self.L, self.K)
+        check(self.lib.hs_set_projection(self.ctx, ptr(a, C.c_double), ptr(b, C.c_double)))
+
+    def seed_projection(self, seed_base):
+        a, b = generate_projection(seed_base, self.dim, self.K, self.L, self.params.W)
+        self.set_projection(a, b)
+        return a, b
+
+    def set_coordinates(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float64).reshape(160)
+        check(self.lib.hs_set_coordinates(self.ctx, ptr(t, C.c_double)))
+
+    def load_fragments(self, codes, id_base=0):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        assert codes.ndim == 2 and codes.shape[1] == self.len
+        check(self.lib.hs_load_fragments(self.ctx, ptr(codes, C.c_uint8), codes.shape[0], id_base))
+
+    def load_fragments_dev(self, dev_ptr, n, id_base=0):
+        check(self.lib.hs_load_fragments_dev(self.ctx, C.c_void_p(dev_ptr), n, id_base))
+
+    def extract_windows(self, residues, start_index, stride=1, id_base=0, want_pos=True):
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        start_index = np.ascontiguousarray(start_index, dtype=np.uint32)
+        nprot = len(start_index) - 1
+        nfrag = C.c_uint64(0)
+        cap = max(1, len(residues)) if want_pos else 0
+        pos = np.zeros(cap, dtype=np.uint32) if want_pos else None
+        check(self.lib.hs_extract_windows(self.ctx, ptr(residues, C.c_uint8), ptr(start_index, C.c_uint32), nprot,
+                                          stride, id_base, ptr(pos, C.c_uint32) if want_pos else None, cap,
+                                          C.byref(nfrag)))
+        return nfrag.value, (pos[:nfrag.value] if want_pos else None)
+
+    @property
+    def num_fragments(self):
+        return int(self.lib.hs_num_fragments(self.ctx))
+
+    # ---- hash / index ----------------------------------------------------------
+    def hash(self, want_buckets=False):
+        n = self.num_fragments
+        out = np.zeros((n, self.L, self.K), dtype=np.int32) if want_buckets else None
+        check(self.lib.hs_hash(self.ctx, ptr(out, C.c_int32) if want_buckets else None))
+        return out
+
+    def keys(self, table):
+        kw = self.stats().key_words
+        out = np.zeros((self.num_fragments, kw), dtype=np.uint64)
+        check(self.lib.hs_get_keys(self.ctx, table, ptr(out, C.c_uint64)))
+        return out
+
+    def build_index(self):
+        check(self.lib.hs_build_index(self.ctx))
+
+    def table_sizes(self):
+        s = np.zeros(self.L, dtype=np.uint64)
+        check(self.lib.hs_table_sizes(self.ctx, ptr(s, C.c_uint64)))
+        return s
+
+    def table(self, l):
+        n = self.num_fragments
+        nb = int(self.table_sizes()[l])
+        ids = np.zeros(n, dtype=np.uint32)
+        starts = np.zeros(nb + 1, dtype=np.uint32)
+        check(self.lib.hs_get_table(self.ctx, l, ptr(ids, C.c_uint32), ptr(starts, C.c_uint32)))
+        return ids, starts
+
+    def stats(self):
+        s = Stats()
+        check(self.lib.hs_get_stats(self.ctx, C.byref(s)))
+        return s
+
+    # ---- search ------------------------------------------------------------------
+    def _call_hits(self, fn, qarr, qctype, Q, cap):
+        cap = int(cap)
+        while True:
+            hits = np.zeros(max(cap, 1), dtype=HIT_DTYPE)
+            n = C.c_uint64(0)
+            rc = fn(self.ctx, ptr(qarr, qctype) if qarr is not None else None, Q, hits.ctypes.data, cap, C.byref(n))
+            if rc == capi.HS_ERR_CAPACITY:
+                cap = int(n.value)
+                continue
+            check(rc)
+            return hits[:n.value]
+
+    def search_points(self, qpoints, cap=1 << 20):
+        q = np.ascontiguousarray(qpoints, dtype=np.float64).reshape(-1, self.dim)
+        return self._call_hits(self.lib.hs_search_points, q, C.c_double, q.shape[0], cap)
+
+    def search_codes(self, qcodes, cap=1 << 20):
+        q = np.ascontiguousarray(qcodes, dtype=np.uint8).reshape(-1, self.len)
+        return self._call_hits(self.lib.hs_search_codes, q, C.c_uint8, q.shape[0], cap)
+
+    def bruteforce_points(self, qpoints, cap=1 << 20):
+        q = np.ascontiguousarray(qpoints, dtype=np.float64).reshape(-1, self.dim)
+        return self._call_hits(self.lib.hs_bruteforce_points, q, C.c_double, q.shape[0], cap)
+
+    def bruteforce_codes(self, qcodes=None, cap=1 << 20):
+        if qcodes is None:
+            return self._call_hits(self.lib.hs_bruteforce_codes, None, C.c_uint8, 0, cap)
+        q = np.ascontiguousarray(qcodes, dtype=np.uint8).reshape(-1, self.len)
+        return self._call_hits(self.lib.hs_bruteforce_codes, q, C.c_uint8, q.shape[0], cap)
+
+    def cluster(self):
+        out = np.zeros(self.num_fragments, dtype=np.uint32)
+        check(self.lib.hs_cluster(self.ctx, ptr(out, C.c_uint32)))
+        return out

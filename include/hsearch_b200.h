@@ -1,0 +1,232 @@
+/*
+ * hsearch_b200.h -- C ABI of the B200-native HSEARCH hot path.
+ *
+ * The reference (acgtun/hsearch) has no plugin / FFI interface: it is a set of
+ * single-threaded CLI programs.  The drop-in boundary is therefore (i) this C
+ * ABI, which the flag-compatible CLI mains in hsearch_b200/cli/ call, and
+ * (ii) the reference's argv grammar and text file formats, which those mains
+ * keep.  Each entry point cites the reference code it replaces (paths relative
+ * to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller allocates and frees every
+ *     buffer, the library owns only the opaque hs_ctx;
+ *   - every call returns 0 (HS_OK) or a negative hs_status; hs_last_error()
+ *     gives the message of the calling thread's last failure; the library
+ *     never throws across the boundary and never exits;
+ *   - one hs_ctx per GPU; calls on one ctx are serialised by the caller; each
+ *     ctx owns one CUDA stream;
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     HS_ERR_CUDA when no sm_100 device is usable;
+ *   - residue codes are 0..19 in BLOSUM order A R N D C Q E G H I L K M F P S
+ *     T W Y V (the row index of `coordinates`, hclust/src/hclust/util.hpp:21-42,
+ *     i.e. base[letter-'A'], util.hpp:92).
+ */
+#ifndef HSEARCH_B200_H
+#define HSEARCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hs_ctx hs_ctx_t;
+
+#define HS_AA 20
+#define HS_CDIM 8            /* AACoordinateSize, util.hpp:94 */
+#define HS_MAX_LEN 32        /* fragment length limit of this build */
+#define HS_MAX_K 32
+#define HS_MAX_L 64
+#define HS_MAX_KEY_WORDS 4   /* packed digit-string key: <= 64 characters */
+
+typedef enum {
+  HS_OK = 0,
+  HS_ERR_INVALID = -1,     /* bad argument / call order */
+  HS_ERR_CUDA = -2,        /* CUDA runtime failure, or no usable sm_100 GPU */
+  HS_ERR_CAPACITY = -3,    /* caller's hit buffer too small; *nhits = needed */
+  HS_ERR_UNSUPPORTED = -4, /* parameter outside this build's limits */
+  HS_ERR_NOMEM = -5,
+  HS_ERR_COMM = -6         /* NCCL failure */
+} hs_status;
+
+/* Which 20x8 embedding table the DB fragments are embedded with (M1).
+ * FULL   = util.hpp:21-42 as written (hclust2.cpp:49-62, kmer_search.cpp:52-62).
+ * PRINT6 = the same table after the 6-significant-digit text round trip of
+ *          protein2datapoints.cpp:23-29 -> motif_both_points.cpp:347-351, which
+ *          is what motif_both_points really hashes. */
+enum { HS_TABLE_FULL = 0, HS_TABLE_PRINT6 = 1 };
+/* EUCLID_FP64 = PairwiseDistance(_square), motif_both_points.cpp:167-183.
+ * BLOSUM_INT  = DistanceScore, BLOSUM-Metric/src/BLOSUM-metric/evaluate_correlation.cpp:34-41
+ *               over distance_matrix.hpp:13-20. */
+enum { HS_METRIC_EUCLID_FP64 = 0, HS_METRIC_BLOSUM_INT = 1 };
+/* D2_LE_R2  : hit iff d2 <= R*R        (motif_both_points.cpp:204,239)
+ * SQRT_LE_R : hit iff !(sqrt(d2) > R)  (motif_both_points_noLSH.cpp:46-47, hclust2.cpp:119-120)
+ * ignored for BLOSUM_INT (hit iff d <= (int)R). */
+enum { HS_PRED_D2_LE_R2 = 0, HS_PRED_SQRT_LE_R = 1 };
+enum {
+  HS_FLAG_SORT_HITS = 1u,   /* return hits in the reference's output order:
+                               query, first-finding table, ascending db id */
+  HS_FLAG_HASH_EXACT = 2u,  /* hash every projection in FP64 reference order
+                               (no FP32 fast path); for validation */
+  HS_FLAG_HASH_AUDIT = 4u   /* after hashing, recompute every projection in
+                               FP64 and count residual flips (must be 0) */
+};
+
+typedef struct {
+  uint32_t len;           /* fragment length in residues; DIM = 8*len (motif_both_points.cpp:337-338) */
+  uint32_t K;             /* projections per table (hash_K) */
+  uint32_t L;             /* tables (hash_L) */
+  double W;               /* bucket width (hash_W) */
+  double R;               /* distance threshold (hash_R) */
+  uint32_t table_variant; /* HS_TABLE_* */
+  uint32_t metric;        /* HS_METRIC_* */
+  uint32_t predicate;     /* HS_PRED_* */
+  uint32_t flags;         /* HS_FLAG_* */
+} hs_params;
+
+/* One verified pair.  dist2 = squared Euclidean distance exactly as the
+ * reference's FP64 loop produces it (EUCLID_FP64), or the integer window
+ * distance as a double (BLOSUM_INT).  db_id = id_base + local index. */
+typedef struct {
+  uint32_t query;
+  uint32_t table_first; /* first table whose bucket held the pair (label[], motif_both_points.cpp:232-238) */
+  uint64_t db_id;
+  double dist2;
+} hs_hit;
+
+/* Counters and device timings (CUDA events on the ctx stream) of the most
+ * recent hs_hash / hs_build_index / hs_search_* / hs_bruteforce_* / hs_cluster. */
+typedef struct {
+  uint64_t n_fragments;
+  uint64_t guard_hits;      /* projections re-evaluated in FP64 (inside the FP32 guard band) */
+  uint64_t guard_corrected; /* of those, FP32 bucket != FP64 bucket (flips the guard caught) */
+  uint64_t residual_flips;  /* HS_FLAG_HASH_AUDIT: final bucket != FP64 bucket over ALL projections */
+  uint64_t n_candidates;    /* (query, member) pairs examined by the filter kernel */
+  uint64_t n_survivors;     /* pairs passed to the exact FP64 / dedup stage */
+  uint64_t n_hits;
+  uint64_t n_edges;         /* hs_cluster: near pairs found */
+  uint64_t n_work_items;
+  uint32_t key_words;       /* 64-bit words per packed key */
+  uint32_t sort_passes;     /* radix passes actually executed (all tables) */
+  uint32_t kernel_launches; /* kernels launched by the most recent call */
+  uint32_t reserved;
+  float ms_hash, ms_sort, ms_group, ms_permute;      /* index build stages */
+  float ms_qhash, ms_probe, ms_filter, ms_exact, ms_hitsort; /* search stages */
+  float ms_total;           /* whole call, first to last event */
+} hs_stats;
+
+/* ---- lifetime -------------------------------------------------------------- */
+/* Replaces the per-process state of motif_both_points.cpp:252-383 (parameters
+ * parsed at :302-335, K=L=4 forced at :380-381 -- here K and L are honoured). */
+int hs_create(hs_ctx_t **out, int device, const hs_params *params);
+void hs_destroy(hs_ctx_t *ctx);
+const char *hs_last_error(void);
+int hs_get_stats(hs_ctx_t *ctx, hs_stats *out);
+/* 1 if a CUDA device of compute capability 10.x is visible, else 0. */
+int hs_device_available(void);
+
+/* ---- embedding tables (M1..M3) ---------------------------------------------- */
+/* out160 <- the 20x8 table of the given HS_TABLE_* variant. */
+int hs_get_coordinates(uint32_t table_variant, double *out160);
+/* out400 <- D[i][j] = B[i][i]+B[j][j]-2B[i][j] (distance_matrix.hpp:13-20). */
+int hs_get_blosum_metric(int32_t *out400);
+/* Override the ctx's embedding table (default: params.table_variant). */
+int hs_set_coordinates(hs_ctx_t *ctx, const double *table160);
+/* letter -> code (base[letter-'A'], util.hpp:92); -1 for non-amino-acid letters. */
+int hs_letter_to_code(char letter);
+/* ProteinDB storage rule (protein.hpp:58-64): code after the AA20 round trip
+ * (E and Q swap). */
+int hs_proteindb_code(char letter);
+
+/* ---- projection (H1) -------------------------------------------------------- */
+/* LSH::LSH (lsh.hpp:10-31) for one table: default_random_engine(seed), per k
+ * DIM normals then one uniform[0,W).  a[K][dim], b[K].  Host-side, libstdc++
+ * <random>, exactly the reference's calls. */
+int hs_generate_projection(uint64_t seed, uint32_t dim, uint32_t K, double W, double *a, double *b);
+/* a[L][K][DIM], b[L][K] -> device; builds the FP32 residue-projection tables
+ * and guard bands; fixes the packed-key width. */
+int hs_set_projection(hs_ctx_t *ctx, const double *a, const double *b);
+
+/* ---- database (E1, E2) ------------------------------------------------------ */
+/* codes[N][len] host -> device.  Replaces the DB read loop
+ * motif_both_points.cpp:343-354 (points are stored as 1-byte codes, not 8*len
+ * doubles). */
+int hs_load_fragments(hs_ctx_t *ctx, const uint8_t *codes, uint64_t N, uint64_t id_base);
+/* Same, codes already in device memory (copied device-to-device). */
+int hs_load_fragments_dev(hs_ctx_t *ctx, const void *codes_dev, uint64_t N, uint64_t id_base);
+/* Sliding windows over a concatenated residue store (ProteinDB, protein.hpp:7-72;
+ * window loop kmer_search.cpp:64-83 with the :73 bug fixed): every window start
+ * j = 0, stride, 2*stride ... <= len_i - len of every protein becomes one
+ * fragment, in protein order.  residues are codes; start_index has nprot+1
+ * entries.  pos_out (optional, host, capacity pos_cap) receives the global
+ * start position of each fragment; *nfrag the fragment count. */
+int hs_extract_windows(hs_ctx_t *ctx, const uint8_t *residues, const uint32_t *start_index,
+                       uint32_t nprot, uint32_t stride, uint64_t id_base, uint32_t *pos_out,
+                       uint64_t pos_cap, uint64_t *nfrag);
+uint64_t hs_num_fragments(hs_ctx_t *ctx);
+
+/* ---- hash (H2..H4) ---------------------------------------------------------- */
+/* Bucket ints floor((a.v+b)/W) for every fragment, table and projection, and
+ * the packed digit-string keys.  buckets_out[N][L][K] (host) may be NULL.
+ * Replaces LSH::HashKey over motif_both_points.cpp:212-216. */
+int hs_hash(hs_ctx_t *ctx, int32_t *buckets_out);
+/* keys_out[N][key_words] (host, word 0 = least significant) of table `table`. */
+int hs_get_keys(hs_ctx_t *ctx, uint32_t table, uint64_t *keys_out);
+/* Pack a reference key string (digits and '-') the way the device does:
+ * right-aligned nibbles '0'..'9' -> 1..10, '-' -> 11.  words_out[key_words]. */
+int hs_pack_key_string(const char *s, uint32_t key_words, uint64_t *words_out);
+
+/* ---- index build (B1) ------------------------------------------------------- */
+/* Radix sort of (key, id) per table + bucket grouping + bucket-ordered code
+ * store.  Replaces the unordered_map insert of motif_both_points.cpp:212-216.
+ * Calls hs_hash first if it has not run. */
+int hs_build_index(hs_ctx_t *ctx);
+/* sizes_out[L] = number of buckets per table ("table size", :217). */
+int hs_table_sizes(hs_ctx_t *ctx, uint64_t *sizes_out);
+/* ids_out[N] = fragment ids of table `table` in bucket order (ascending id
+ * inside a bucket); starts_out[nb+1] bucket boundaries (either may be NULL). */
+int hs_get_table(hs_ctx_t *ctx, uint32_t table, uint32_t *ids_out, uint32_t *starts_out);
+
+/* ---- search (V1, V2, V3) ---------------------------------------------------- */
+/* Query loop of motif_both_points.cpp:224-245 for Q queries given as dense
+ * points [Q][DIM] (centres may be arbitrary real vectors) or as residue codes
+ * [Q][len] (embedded with the ctx table).  hits (host, capacity cap) receives
+ * *nhits hits; if *nhits > cap the call returns HS_ERR_CAPACITY and the first
+ * cap hits are valid only as a set. */
+int hs_search_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hit *hits, uint64_t cap,
+                     uint64_t *nhits);
+int hs_search_codes(hs_ctx_t *ctx, const uint8_t *qcodes, uint32_t Q, hs_hit *hits, uint64_t cap,
+                    uint64_t *nhits);
+/* Device-resident variants: queries and the hit buffer are device pointers;
+ * nothing crosses PCIe except the hit count. */
+int hs_search_points_dev(hs_ctx_t *ctx, const void *qpoints_dev, uint32_t Q, void *hits_dev,
+                         uint64_t cap, uint64_t *nhits);
+
+/* ---- brute force (G1) ------------------------------------------------------- */
+/* All Q x N distances, hits only (motif_both_points_noLSH.cpp:36-56; the
+ * non-hit dump :47-49 is not produced).  qcodes == NULL: all pairs i<j of the
+ * DB (query = i, db_id = j).  Uses params.metric / predicate / R. */
+int hs_bruteforce_codes(hs_ctx_t *ctx, const uint8_t *qcodes, uint32_t Q, hs_hit *hits, uint64_t cap,
+                        uint64_t *nhits);
+int hs_bruteforce_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hit *hits, uint64_t cap,
+                         uint64_t *nhits);
+
+/* ---- cluster (U1) ----------------------------------------------------------- */
+/* Connected components of the near-pair graph: every pair sharing a bucket in
+ * some table with distance within R is an edge; UnionFind
+ * (pcluster/src/pcluster/union_find.cpp:3-33) over the edges.  label_out[N]
+ * (host) = smallest local id of the fragment's component. */
+int hs_cluster(hs_ctx_t *ctx, uint32_t *label_out);
+
+/* ---- multi-GPU -------------------------------------------------- */
+/* Join an NCCL communicator (nccl_unique_id: the 128-byte ncclUniqueId made by
+ * rank 0).  After this, hs_search_* on every rank takes the queries of rank 0
+ * (ncclBroadcast) and gathers all ranks' hits to rank 0. */
+int hs_comm_init(hs_ctx_t *ctx, const void *nccl_unique_id, int rank, int nranks);
+int hs_comm_unique_id(void *out128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSEARCH_B200_H */

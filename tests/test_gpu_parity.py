@@ -1,0 +1,292 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the
+same seeded inputs.  Bit-exact for bucket ints, packed keys, bucket membership,
+hit sets, hit order and FP64 distances."""
+import numpy as np
+import pytest
+
+import hsearch_b200 as hb
+from tests.util import hits_as_tuples, planted_families, planted_queries, random_codes
+
+pytestmark = pytest.mark.gpu
+
+
+def make(length, K, L, W, R, seed=12345, **kw):
+    h = hb.HSearch(length, K, L, W, R, **kw)
+    a, b = h.seed_projection(seed)
+    return h, a, b
+
+
+def table_for(oracle, variant):
+    return oracle.coordinates(print6=(variant == hb.HS_TABLE_PRINT6))
+
+
+# ---------------------------------------------------------------- K1: hash
+@pytest.mark.parametrize("length,K,L,W", [(10, 4, 4, 50.0), (10, 4, 4, 20.0), (10, 4, 4, 4.0), (25, 4, 4, 50.0),
+                                          (8, 2, 1, 10.0), (30, 8, 3, 50.0), (10, 16, 2, 50.0), (12, 3, 5, 7.5),
+                                          (10, 16, 32, 10.0), (1, 1, 1, 1.0)])
+@pytest.mark.parametrize("variant", [hb.HS_TABLE_PRINT6, hb.HS_TABLE_FULL])
+def test_hash_buckets_and_keys(oracle, length, K, L, W, variant):
+    n = 20000 if K * L <= 64 else 3000
+    codes = random_codes(n, length, seed=1)
+    h, a, b = make(length, K, L, W, 30.0, table_variant=variant, flags=hb.HS_FLAG_HASH_AUDIT)
+    h.load_fragments(codes)
+    got = h.hash(want_buckets=True)
+    want = oracle.hash_codes(codes, table_for(oracle, variant), a, b, W)
+    assert np.array_equal(got, want)
+    st = h.stats()
+    assert st.residual_flips == 0
+    kw = st.key_words
+    strings = oracle.key_strings(want)
+    for l in range(L):
+        keys = h.keys(l)
+        uniq = {}
+        for s in set(strings[:, l].tolist()):
+            uniq[s] = hb.pack_key_string(s, kw)
+        expect = np.stack([uniq[s] for s in strings[:, l]])
+        assert np.array_equal(keys, expect)
+    h.close()
+
+
+def test_hash_projection_matches_oracle_rng(oracle):
+    a, b = hb.generate_projection(12345, 80, 4, 4, 50.0)
+    oa, ob = oracle.lsh_tables(12345, 80, 4, 4, 50.0)
+    assert np.array_equal(a, oa) and np.array_equal(b, ob)
+
+
+def test_hash_exact_mode_equals_fast_mode(oracle):
+    codes = random_codes(50000, 10, seed=3)
+    res = []
+    for flags in (0, hb.HS_FLAG_HASH_EXACT):
+        h, a, b = make(10, 4, 4, 50.0, 30.0, flags=flags)
+        h.load_fragments(codes)
+        res.append(h.hash(want_buckets=True))
+        if flags == 0:
+            st = h.stats()
+            # the guard band is exercised but rare
+            assert st.guard_hits < 0.01 * codes.shape[0] * 16
+        h.close()
+    assert np.array_equal(res[0], res[1])
+
+
+def test_hash_guard_band_forced(oracle):
+    """W tiny -> nearly every projection sits inside the guard band; the FP64
+    re-evaluation must still reproduce the oracle."""
+    codes = random_codes(5000, 10, seed=4)
+    W = 1e-3
+    h = hb.HSearch(10, 2, 2, W, 30.0)
+    a, b = hb.generate_projection(7, 80, 2, 2, W)
+    try:
+        h.set_projection(a, b)
+    except hb.HsError as e:  # key too wide for this W is a legitimate refusal
+        assert e.code == -4
+        return
+    h.load_fragments(codes)
+    got = h.hash(want_buckets=True)
+    want = oracle.hash_codes(codes, oracle.coordinates(True), a, b, W)
+    assert np.array_equal(got, want)
+    assert h.stats().guard_hits > 0
+    h.close()
+
+
+# ---------------------------------------------------------------- K2: sort + buckets
+@pytest.mark.parametrize("n", [1, 2, 255, 4096, 4097, 100003])
+@pytest.mark.parametrize("K,W", [(4, 50.0), (4, 4.0), (16, 50.0)])
+def test_index_buckets(oracle, n, K, W):
+    L = 3
+    codes = random_codes(n, 10, seed=n)
+    h, a, b = make(10, K, L, W, 30.0)
+    h.load_fragments(codes)
+    h.build_index()
+    strings = oracle.key_strings(oracle.hash_codes(codes, oracle.coordinates(True), a, b, W))
+    sizes = h.table_sizes()
+    for l in range(L):
+        ids, starts = h.table(l)
+        assert sorted(ids.tolist()) == list(range(n))
+        groups = {}
+        for i, s in enumerate(strings[:, l]):
+            groups.setdefault(s, []).append(i)
+        assert sizes[l] == len(groups)
+        assert starts[0] == 0 and starts[-1] == n
+        seen = set()
+        for bidx in range(len(starts) - 1):
+            members = ids[starts[bidx]:starts[bidx + 1]].tolist()
+            s = strings[members[0], l]
+            assert members == groups[s], "bucket members must be the ascending ids sharing the key string"
+            seen.add(s)
+        assert len(seen) == len(groups)
+    h.close()
+
+
+# ---------------------------------------------------------------- K3: search
+@pytest.mark.parametrize("length,K,L,W,R", [(10, 4, 4, 50.0, 30.0), (10, 4, 4, 20.0, 30.0), (10, 2, 6, 30.0, 25.0),
+                                            (25, 4, 4, 50.0, 60.0), (8, 4, 4, 50.0, 30.0), (30, 4, 2, 80.0, 70.0),
+                                            (10, 16, 4, 200.0, 30.0)])
+def test_search_hits_bit_exact(oracle, length, K, L, W, R):
+    n, q = 30000, 300
+    codes = random_codes(n, length, seed=11)
+    qcodes = planted_queries(codes, q, seed=12)
+    tab = oracle.coordinates(True)
+    h, a, b = make(length, K, L, W, R)
+    h.load_fragments(codes)
+    h.build_index()
+    got = h.search_codes(qcodes)
+    want, ts, ncand = oracle.search(oracle.embed(codes, tab), oracle.embed(qcodes, tab), a, b, W, R, pred=0)
+    assert np.array_equal(h.table_sizes(), ts)
+    assert len(got) == len(want) and len(want) > 0
+    assert hits_as_tuples(got) == hits_as_tuples(want)  # order, first table, id, FP64 distance
+    h.close()
+
+
+def test_search_dense_query_points(oracle):
+    """Centres may be arbitrary real vectors (cluster means), not embeddings."""
+    n, q, length = 20000, 200, 10
+    codes = random_codes(n, length, seed=21)
+    tab = oracle.coordinates(True)
+    rng = np.random.default_rng(22)
+    qpts = oracle.embed(planted_queries(codes, q, seed=23), tab) + rng.normal(0, 0.3, size=(q, 8 * length))
+    h, a, b = make(length, 4, 4, 50.0, 30.0)
+    h.load_fragments(codes)
+    h.build_index()
+    got = h.search_points(qpts)
+    want, ts, _ = oracle.search(oracle.embed(codes, tab), qpts, a, b, 50.0, 30.0, pred=0)
+    assert len(want) > 0
+    assert hits_as_tuples(got) == hits_as_tuples(want)
+    h.close()
+
+
+def test_search_edge_cases(oracle):
+    tab = oracle.coordinates(True)
+    codes = random_codes(5000, 10, seed=31)
+    h, a, b = make(10, 4, 4, 50.0, 30.0)
+    h.load_fragments(codes)
+    h.build_index()
+    # no queries
+    assert len(h.search_codes(np.zeros((0, 10), dtype=np.uint8))) == 0
+    # a query far from everything: dense point way outside the embedding
+    far = np.full((1, 80), 1e4)
+    assert len(h.search_points(far)) == 0
+    # duplicates in the DB and query == DB fragment (distance 0)
+    got = h.search_codes(codes[:5])
+    want, _, _ = oracle.search(oracle.embed(codes, tab), oracle.embed(codes[:5], tab), a, b, 50.0, 30.0)
+    assert hits_as_tuples(got) == hits_as_tuples(want)
+    assert any(t[3] == 0.0 for t in hits_as_tuples(got))
+    # capacity error path: caller buffer too small -> retried inside the wrapper
+    got2 = h.search_codes(codes[:50], cap=1)
+    want2, _, _ = oracle.search(oracle.embed(codes, tab), oracle.embed(codes[:50], tab), a, b, 50.0, 30.0)
+    assert hits_as_tuples(got2) == hits_as_tuples(want2)
+    h.close()
+    # empty database
+    h, a, b = make(10, 4, 4, 50.0, 30.0)
+    h.load_fragments(np.zeros((0, 10), dtype=np.uint8))
+    h.build_index()
+    assert len(h.search_codes(codes[:3])) == 0
+    h.close()
+
+
+def test_search_against_reference_itself(oracle, reference):
+    """The reference's own Search() (compiled in place) on the same inputs."""
+    n, q = 20000, 200
+    codes = random_codes(n, 10, seed=41)
+    qcodes = planted_queries(codes, q, seed=42)
+    tab = oracle.coordinates(True)
+    db, qp = oracle.embed(codes, tab), oracle.embed(qcodes, tab)
+    for W in (20.0, 50.0):
+        h, a, b = make(10, 4, 4, W, 30.0, seed=12345)
+        h.load_fragments(codes)
+        h.build_index()
+        got = h.search_codes(qcodes)
+        ref, printed, ts, _ = reference.search(db, qp, 4, 4, W, 30.0, 12345)
+        assert np.array_equal(h.table_sizes(), ts)
+        assert hits_as_tuples(got, with_table=False) == hits_as_tuples(ref, with_table=False)
+        h.close()
+
+
+# ---------------------------------------------------------------- K4: brute force
+@pytest.mark.parametrize("length,R", [(10, 30.0), (25, 60.0), (8, 25.0)])
+def test_bruteforce_points(oracle, length, R):
+    n, q = 20000, 100
+    codes = random_codes(n, length, seed=51)
+    qcodes = planted_queries(codes, q, seed=52)
+    tab = oracle.coordinates(True)
+    h = hb.HSearch(length, 4, 4, 50.0, R, predicate=hb.HS_PRED_SQRT_LE_R)
+    h.load_fragments(codes)
+    got = h.bruteforce_codes(qcodes)
+    want = oracle.bruteforce(oracle.embed(codes, tab), oracle.embed(qcodes, tab), R, pred=1)
+    assert len(want) > 0
+    assert hits_as_tuples(got, False) == hits_as_tuples(want, False)
+    h.close()
+
+
+@pytest.mark.parametrize("length,R", [(8, 30), (10, 40), (16, 80), (30, 200)])
+def test_bruteforce_int_metric_all_pairs(oracle, length, R):
+    n = 3000
+    codes = planted_families(n, length, seed=61)
+    h = hb.HSearch(length, 4, 4, 50.0, float(R), metric=hb.HS_METRIC_BLOSUM_INT)
+    h.load_fragments(codes)
+    got = h.bruteforce_codes(None, cap=1 << 22)
+    want = oracle.bruteforce_int(codes, None, R)
+    assert len(want) > 0
+    assert hits_as_tuples(got, False) == hits_as_tuples(want, False)
+    # and with explicit queries
+    got = h.bruteforce_codes(codes[:64], cap=1 << 22)
+    want = oracle.bruteforce_int(codes, codes[:64], R)
+    assert hits_as_tuples(got, False) == hits_as_tuples(want, False)
+    h.close()
+
+
+def test_search_int_metric(oracle):
+    """LSH candidates verified with the integer window distance (V3)."""
+    n, q, R = 20000, 200, 40
+    codes = random_codes(n, 10, seed=71)
+    qcodes = planted_queries(codes, q, seed=72)
+    tab = oracle.coordinates(True)
+    h, a, b = make(10, 4, 4, 50.0, float(R), metric=hb.HS_METRIC_BLOSUM_INT)
+    h.load_fragments(codes)
+    h.build_index()
+    got = h.search_codes(qcodes)
+    # oracle: candidate sets from the reference search with R = inf, then V3 on each candidate
+    cand, _, _ = oracle.search(oracle.embed(codes, tab), oracle.embed(qcodes, tab), a, b, 50.0, 1e9)
+    exp = []
+    for c in cand:
+        d = oracle.distance_int(qcodes[c["query"]], codes[c["db_id"]])
+        if d <= R:
+            exp.append((int(c["query"]), int(c["table_first"]), int(c["db_id"]), float(d)))
+    assert len(exp) > 0
+    assert hits_as_tuples(got) == exp
+    h.close()
+
+
+# ---------------------------------------------------------------- K5: cluster
+@pytest.mark.parametrize("metric,R", [(hb.HS_METRIC_EUCLID_FP64, 25.0), (hb.HS_METRIC_BLOSUM_INT, 30.0)])
+@pytest.mark.parametrize("K,W", [(4, 50.0), (8, 30.0)])
+def test_cluster_partition(oracle, metric, R, K, W):
+    n, L = 6000, 4
+    codes = planted_families(n, 10, seed=81)
+    tab = oracle.coordinates(True)
+    h, a, b = make(10, K, L, W, R, metric=metric, predicate=hb.HS_PRED_SQRT_LE_R)
+    h.load_fragments(codes)
+    h.build_index()
+    got = h.cluster()
+    want, ne = oracle.cluster(codes, tab, a, b, W, R, metric=0 if metric == hb.HS_METRIC_EUCLID_FP64 else 1)
+    assert ne > 0 and len(set(want.tolist())) < n
+    assert np.array_equal(got, want)
+    h.close()
+
+
+# ---------------------------------------------------------------- E2: windows
+def test_extract_windows(oracle):
+    rng = np.random.default_rng(91)
+    lens = rng.integers(0, 60, size=200)
+    lens[3] = 9   # shorter than the window
+    lens[4] = 10  # exactly one window
+    start = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    residues = rng.integers(0, 20, size=int(start[-1]), dtype=np.uint8)
+    for stride in (1, 3):
+        h, a, b = make(10, 4, 4, 50.0, 30.0)
+        nfrag, pos = h.extract_windows(residues, start, stride=stride)
+        ocodes, opos = oracle.extract_windows(residues, start, 10, stride)
+        assert nfrag == len(ocodes) and np.array_equal(pos, opos)
+        got = h.hash(want_buckets=True)
+        want = oracle.hash_codes(ocodes, oracle.coordinates(True), a, b, 50.0)
+        assert np.array_equal(got, want)
+        h.close()
