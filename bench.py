@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- the HSEARCH hot path on B200: DB fragments hashed + bucketed +
+verified per second (BASELINE.json `metric`), on BASELINE.json configs[1]
+(10k queries vs 100M synthetic fragments per GPU, len 10, K = L = 4).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU code
+
+One "step" is one pass of the whole path over one batch: hash every fragment
+(K1), radix-sort + group + bucket-order the L tables (K2), hash / probe / filter
+/ exactly verify the Q queries and put the hits in the reference's order (K3).
+`value` times that with the DB codes and queries resident in HBM; `e2e` times
+the same through the C ABI with host buffers (H2D of the codes and queries and
+D2H of the hits inside the timed region).
+
+Only the `cpu_baseline` leg and `--impl reference` touch oracle/ (the checker);
+the product path is libhsearch_b200.so and fails loudly without a GPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "db_fragments_hashed_bucketed_verified_per_s"
+UNIT = "fragments/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--n-db", type=int, default=100_000_000, help="DB fragments per GPU")
+    ap.add_argument("--n-query", type=int, default=10_000)
+    ap.add_argument("--len", type=int, default=10)
+    ap.add_argument("--K", type=int, default=4)
+    ap.add_argument("--L", type=int, default=4)
+    ap.add_argument("--W", type=float, default=50.0)
+    ap.add_argument("--R", type=float, default=30.0)
+    ap.add_argument("--planted", type=float, default=0.1, help="fraction of queries planted as DB mutants")
+    ap.add_argument("--cpu-sample", type=int, default=20_000, help="DB fragments per host core in the CPU leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--audit", action="store_true", help="FP64 audit of every projection (residual flips)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"LSH search: {a.n_query} queries vs {a.n_db} synthetic fragments per GPU, len {a.len}, "
+            f"K={a.K} L={a.L} W={a.W:g} R={a.R:g}")
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smmax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ CPU legs
+def _cpu_worker(args):
+    """One host core: the reference's own Search() (oracle/_ref) -- or the oracle
+    port when oracle/_ref is absent -- on a disjoint DB sample."""
+    wid, n, q, length, K, L, W, R, planted = args
+    from oracle.pyoracle import Oracle, Reference
+    from tests.util import planted_queries, random_codes
+    o = Oracle()
+    tab = o.coordinates(True)
+    db = random_codes(n, length, seed=1000 + wid)
+    qc = planted_queries(random_codes(n, length, seed=1000), q, seed=2, frac=planted)
+    dbp, qp = o.embed(db, tab), o.embed(qc, tab)
+    if Reference.available():
+        r = Reference()
+        hits, _, _, sec = r.search(dbp, qp, K, L, W, R, 12345, cap=1 << 22)
+        return "reference", sec, len(hits)
+    a, b = o.lsh_tables(12345, 8 * length, K, L, W)
+    t0 = time.perf_counter()
+    hits, _, _ = o.search(dbp, qp, a, b, W, R, pred=0, cap=1 << 22)
+    return "port", time.perf_counter() - t0, len(hits)
+
+
+def cpu_leg(a, n_sample, cores=None):
+    """Runs one process per host core on disjoint DB samples with the full query
+    set; returns aggregate fragments/s.  Text parsing excluded on both sides."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    work = [(w, n_sample, a.n_query, a.len, a.K, a.L, a.W, a.R, a.planted) for w in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, work)
+    wall = time.perf_counter() - t0
+    kind = res[0][0]
+    slowest = max(r[1] for r in res)  # all cores run concurrently; the job ends with the slowest
+    value = cores * n_sample / slowest
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": (f"{cores} processes x {n_sample} DB fragments each vs all {a.n_query} queries, "
+                       f"Search() seconds (clock(), index build + query loop), slowest core {slowest:.2f} s, "
+                       f"wall {wall:.1f} s incl. input generation"),
+            "seconds": slowest}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = min(a.cpu_sample, 10_000)
+    vals, last = [], None
+    for i in range(a.warmup + a.steps):
+        last = cpu_leg(a, n_sample)
+        if i >= a.warmup:
+            vals.append(last)
+    secs = [v["seconds"] for v in vals]
+    value = last["cores"] * n_sample / (sum(secs) / len(secs))
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(a), "sample": last["sample"]},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
+                            "sample": last["sample"]},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------ native
+def run_native(a):
+    import torch
+    import torch.distributed as dist
+
+    import hsearch_b200 as hb
+    from hsearch_b200 import dist as hdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    length, dim, Q, N = a.len, 8 * a.len, a.n_query, a.n_db
+    flags = hb.HS_FLAG_SORT_HITS | (hb.HS_FLAG_HASH_AUDIT if a.audit else 0)
+    h = hb.HSearch(length, a.K, a.L, a.W, a.R, table_variant=hb.HS_TABLE_PRINT6, flags=flags, device=local)
+    h.seed_projection(12345)
+    stream = torch.cuda.ExternalStream(h.stream_ptr(), device=dev)
+
+    # synthetic inputs: i.i.d. uniform over the 20 letters, per-rank seed
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    codes = torch.randint(0, 20, (N, length), dtype=torch.uint8, device=dev, generator=g)
+    table = torch.tensor(hb.coordinates(hb.HS_TABLE_PRINT6), dtype=torch.float64, device=dev)
+    qcodes = torch.randint(0, 20, (Q, length), dtype=torch.uint8, device=dev, generator=g)
+    nplant = int(Q * a.planted)
+    if nplant:
+        src = torch.randint(0, N, (nplant,), device=dev, generator=g)
+        mut = codes[src].clone()
+        for _ in range(2):
+            pos = torch.randint(0, length, (nplant,), device=dev, generator=g)
+            val = torch.randint(0, 20, (nplant,), dtype=torch.uint8, device=dev, generator=g)
+            keep = torch.rand(nplant, device=dev, generator=g) < 0.5
+            cur = mut[torch.arange(nplant, device=dev), pos]
+            mut[torch.arange(nplant, device=dev), pos] = torch.where(keep, cur, val)
+        qcodes[:nplant] = mut
+    qpts = table[qcodes.long()].reshape(Q, dim).contiguous()
+    if world > 1:
+        hdist.broadcast_queries(qpts, 0)
+    torch.cuda.synchronize()
+
+    h.load_fragments_dev(codes.data_ptr(), N, id_base=rank * N)
+
+    # size the hit buffer with one untimed pass
+    h.build_index()
+    nh0 = h.search_points_dev(qpts.data_ptr(), Q, 0, 0)
+    cap = int(nh0 * 1.05) + 1024
+    hits_dev = torch.empty(cap * 24, dtype=torch.uint8, device=dev)
+
+    acc = {}
+
+    def add_stats(prefix_keys):
+        s = h.stats().as_dict()
+        for k in prefix_keys:
+            acc[k] = acc.get(k, 0.0) + s[k]
+        acc["kernel_launches"] = acc.get("kernel_launches", 0) + s["kernel_launches"]
+        return s
+
+    def step(collect):
+        h.hash()
+        s_hash = add_stats(["ms_hash"]) if collect else h.stats().as_dict()
+        h.build_index()
+        s_build = add_stats(["ms_sort", "ms_group", "ms_permute", "ms_sort_upsweep", "ms_sort_scan",
+                             "ms_sort_downsweep"]) if collect else h.stats().as_dict()
+        n = h.search_points_dev(qpts.data_ptr(), Q, hits_dev.data_ptr(), cap)
+        s_search = add_stats(["ms_qhash", "ms_probe", "ms_filter", "ms_exact", "ms_hitsort"]) if collect \
+            else h.stats().as_dict()
+        total = n
+        if world > 1:
+            _, counts = hdist.gather_hits(hits_dev, min(n, cap), 0)
+            total = sum(counts)
+        return n, total, s_search, s_build, s_hash
+
+    with torch.cuda.stream(stream):
+        for _ in range(a.warmup):
+            step(False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(a.steps):
+            nh, nh_total, s_search, s_build, s_hash = step(True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = t.tolist()
+    ms_per_step = dev_ms / a.steps
+    value = N * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ------------------------
+    e2e = None
+    if not a.no_e2e:
+        host_codes = torch.empty((N, length), dtype=torch.uint8).pin_memory()
+        host_codes.copy_(codes)
+        host_q = torch.empty((Q, dim), dtype=torch.float64).pin_memory()
+        host_q.copy_(qpts)
+        host_hits = torch.empty(cap * 24, dtype=torch.uint8).pin_memory()
+        torch.cuda.synchronize()
+        import ctypes as C
+        from hsearch_b200 import capi
+        lib = capi.load()
+        nh_e = C.c_uint64(0)
+
+        def e2e_step():
+            capi.check(lib.hs_load_fragments(h.ctx, C.cast(host_codes.data_ptr(), C.POINTER(C.c_uint8)), N, rank * N))
+            capi.check(lib.hs_build_index(h.ctx))
+            capi.check(lib.hs_search_points(h.ctx, C.cast(host_q.data_ptr(), C.POINTER(C.c_double)), Q,
+                                            C.c_void_p(host_hits.data_ptr()), cap, C.byref(nh_e)))
+        with torch.cuda.stream(stream):
+            e2e_step()  # warm the pinned path
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(a.steps):
+                e2e_step()
+            f1.record(stream)
+            torch.cuda.synchronize()
+        te = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = te.item() / a.steps
+        e2e = {"value": N * world / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(N * length + Q * dim * 8), "d2h_bytes_per_step": int(nh_e.value * 24),
+               "api": "hs_load_fragments + hs_build_index + hs_search_points (host buffers, pinned)"}
+        del host_codes, host_hits
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    KW = s_search["key_words"]
+    steps = a.steps
+    ncand, nsurv = s_search["n_candidates"], s_search["n_survivors"]
+    passes = s_build["sort_passes"]  # over all L tables
+    kern = {
+        "hash_fast_kernel": {"ms": acc["ms_hash"] / steps, "bytes": N * (length + 8 * KW * a.L), "launches": 1},
+        "radix_downsweep_kernel": {"ms": acc["ms_sort_downsweep"] / steps,
+                                   "bytes": N * ((8 * KW + 4) * 2 * passes - 4 * a.L), "launches": passes},
+        "radix_upsweep_kernel": {"ms": acc["ms_sort_upsweep"] / steps, "bytes": N * 8 * passes, "launches": passes},
+        "bucket_grouping (head flags + scan + scatter)": {"ms": acc["ms_group"] / steps,
+                                                           "bytes": N * a.L * (8 * KW + 4), "launches": 5 * a.L},
+        "permute_codes_kernel": {"ms": acc["ms_permute"] / steps, "bytes": N * a.L * (4 + 2 * length),
+                                 "launches": a.L},
+        "filter_kernel": {"ms": acc["ms_filter"] / steps, "bytes": ncand * (length + 4) + nsurv * 16, "launches": 1},
+        "exact_kernel": {"ms": acc["ms_exact"] / steps, "bytes": nsurv * (16 + length + 4) + nh * 24, "launches": 1},
+    }
+    for k, v in kern.items():
+        v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
+        v["share_of_step"] = v["ms"] / ms_per_step
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except (OSError, ValueError):
+            traffic = None
+    d = kern[dom]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": d["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launches"]),
+                "avg_launch_ms": d["ms"] / max(1, d["launches"]), "share_of_step": d["share_of_step"],
+                "note": ("filter_kernel: algorithmic bytes = candidates*(len+4) + survivors*16 (SURVEY 8d); the "
+                         "bucket-major tiling reads each member once per tile and reuses it across the bucket's "
+                         "queries from registers, so DRAM traffic is far below the algorithmic figure and the "
+                         "kernel is bound by shared-memory lookups (len per pair), not HBM")
+                if dom == "filter_kernel" else ""}
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_leg(a, a.cpu_sample)
+        cpu.pop("seconds", None)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32 filter + f64 exact (hash guard, distances); u64 keys", "data": "synthetic",
+           "config": {"workload": workload_name(a), "n_db_per_gpu": N, "n_query": Q, "len": length, "K": a.K,
+                      "L": a.L, "W": a.W, "R": a.R, "table": "print6", "sharding": f"db-block x{world}",
+                      "l2": "inputs (>= 1 GB codes, multi-GB keys) exceed the 126 MB L2; no flush needed"},
+           "clocks": clocks, "wall_ms_per_step": wall_ms / a.steps,
+           "e2e": e2e, "gpu_launches": int(acc["kernel_launches"]),
+           "roofline": roofline, "cpu_baseline": cpu,
+           "kernels": {k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "share": round(v["share_of_step"], 4)}
+                       for k, v in kern.items()},
+           "counts": {"candidates": int(ncand), "survivors": int(nsurv), "hits_rank0": int(nh),
+                      "hits_total": int(nh_total), "query_frags_per_s": Q / ((acc["ms_qhash"] + acc["ms_probe"] +
+                                                                             acc["ms_filter"] + acc["ms_exact"] +
+                                                                             acc["ms_hitsort"]) / steps * 1e-3),
+                      "sort_passes": int(passes), "key_words": int(KW),
+                      "guard_hits": int(s_hash["guard_hits"]), "guard_corrected": int(s_hash["guard_corrected"]),
+                      "residual_flips": int(s_hash["residual_flips"]) if a.audit else None}}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)
+
+
+if __name__ == "__main__":
+    main()

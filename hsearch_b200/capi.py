@@ -21,7 +21,7 @@ HS_FLAG_SORT_HITS, HS_FLAG_HASH_EXACT, HS_FLAG_HASH_AUDIT = 1, 2, 4
 
 # every symbol include/hsearch_b200.h declares
 EXPORTS = [
-    "hs_create", "hs_destroy", "hs_last_error", "hs_get_stats", "hs_device_available", "hs_get_coordinates",
+    "hs_create", "hs_destroy", "hs_last_error", "hs_get_stats", "hs_device_available", "hs_get_stream", "hs_get_coordinates",
     "hs_get_blosum_metric", "hs_set_coordinates", "hs_letter_to_code", "hs_proteindb_code",
     "hs_generate_projection", "hs_set_projection", "hs_load_fragments", "hs_load_fragments_dev",
     "hs_extract_windows", "hs_num_fragments", "hs_hash", "hs_get_keys", "hs_pack_key_string", "hs_build_index",
@@ -43,6 +43,7 @@ class Stats(C.Structure):
                 ("key_words", C.c_uint32), ("sort_passes", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("reserved", C.c_uint32),
                 ("ms_hash", C.c_float), ("ms_sort", C.c_float), ("ms_group", C.c_float), ("ms_permute", C.c_float),
+                ("ms_sort_upsweep", C.c_float), ("ms_sort_scan", C.c_float), ("ms_sort_downsweep", C.c_float),
                 ("ms_qhash", C.c_float), ("ms_probe", C.c_float), ("ms_filter", C.c_float), ("ms_exact", C.c_float),
                 ("ms_hitsort", C.c_float), ("ms_total", C.c_float)]
 
@@ -74,6 +75,7 @@ def load(build_if_missing=True):
     lib.hs_destroy.restype = None
     lib.hs_last_error.restype = C.c_char_p
     lib.hs_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.hs_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.hs_get_coordinates.argtypes = [C.c_uint32, dblp]
     lib.hs_get_blosum_metric.argtypes = [i32p]
     lib.hs_set_coordinates.argtypes = [vp, dblp]

@@ -170,9 +170,13 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
   in.w[0] = ctx->d_hit_keys[0].as<uint64_t>();
   in.w[1] = ctx->d_hit_keys[1].as<uint64_t>();
   uint32_t *perm = ctx->d_hit_perm.as<uint32_t>();
-  const uint32_t passes_before = ctx->stats.sort_passes;
+  const hs_stats before = ctx->stats;
   HS_TRY(radix_sort_pairs(ctx, in, nullptr, n, 2, perm, perm + n, &sorted));
-  ctx->stats.sort_passes = passes_before;  // sort_passes counts index passes only
+  // sort_passes / ms_sort_* describe the index build only
+  ctx->stats.sort_passes = before.sort_passes;
+  ctx->stats.ms_sort_upsweep = before.ms_sort_upsweep;
+  ctx->stats.ms_sort_scan = before.ms_sort_scan;
+  ctx->stats.ms_sort_downsweep = before.ms_sort_downsweep;
   hit_gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, perm, n, ctx->d_hits_sorted.as<hs_hit>());
   ctx->stats.kernel_launches++;
   HS_CUDA(cudaGetLastError());
@@ -647,8 +651,15 @@ void hs_destroy(hs_ctx_t *ctx) {
     ctx->tables[l].codes_sorted.release();
   }
   for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+int hs_get_stream(hs_ctx_t *ctx, void **stream_out) {
+  if (!ctx || !stream_out) return HS_ERR_INVALID;
+  *stream_out = (void *)ctx->stream;
+  return HS_OK;
 }
 
 int hs_get_stats(hs_ctx_t *ctx, hs_stats *out) {
@@ -790,10 +801,16 @@ int hs_build_index(hs_ctx_t *ctx) {
   HS_CUDA(cudaSetDevice(ctx->device));
   hs_stats hash_stats;
   memset(&hash_stats, 0, sizeof hash_stats);
-  if (!ctx->hashed) HS_TRY(hs_hash(ctx, nullptr));
-  hash_stats = ctx->stats;
+  if (!ctx->hashed) {
+    HS_TRY(hs_hash(ctx, nullptr));
+    hash_stats = ctx->stats;
+  }
+  stats_begin(ctx);
+  ctx->stats.guard_hits = hash_stats.guard_hits;
+  ctx->stats.guard_corrected = hash_stats.guard_corrected;
+  ctx->stats.residual_flips = hash_stats.residual_flips;
+  ctx->stats.kernel_launches = hash_stats.kernel_launches;
   const uint32_t L = ctx->prm.L;
-  ctx->stats.sort_passes = 0;
   float ms_sort = 0.f, ms_group = 0.f, ms_permute = 0.f;
   cudaEvent_t *ev = ctx->ev;
   HS_CUDA(cudaEventRecord(ev[8], ctx->stream));

@@ -147,4 +147,5 @@ struct hs_ctx {
 
   hs_stats stats{};
   cudaEvent_t ev[16];
+  std::vector<cudaEvent_t> ev_pool;  // per-pass sort timing
 };

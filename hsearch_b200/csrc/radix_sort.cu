@@ -425,12 +425,21 @@ int radix_sort_pairs(hs_ctx *ctx, const KeyPtrs &keys_in, const uint32_t *vals_i
   const uint32_t *vsrc = vals_in;
   // values ping-pong so that the last pass lands in v_final
   uint32_t *vdst = (passes.size() & 1) ? v_final : v_tmp;
+  while (ctx->ev_pool.size() < 4 * passes.size()) {
+    cudaEvent_t e;
+    HS_CUDA(cudaEventCreate(&e));
+    ctx->ev_pool.push_back(e);
+  }
   for (size_t pi = 0; pi < passes.size(); ++pi) {
     const Pass &p = passes[pi];
+    cudaEvent_t *pe = &ctx->ev_pool[4 * pi];
+    HS_CUDA(cudaEventRecord(pe[0], ctx->stream));
     radix_upsweep_kernel<<<ntiles, kSortThreads, 0, ctx->stream>>>(src.w[p.word], n, p.shift, p.mask, tile_hist,
                                                                   ntiles);
     ctx->stats.kernel_launches++;
+    HS_CUDA(cudaEventRecord(pe[1], ctx->stream));
     HS_TRY(exclusive_scan_u32(ctx, tile_hist, tile_hist, (uint64_t)ntiles * 256, nullptr));
+    HS_CUDA(cudaEventRecord(pe[2], ctx->stream));
     switch (nw) {
       case 1: launch_downsweep<1>(ctx, src, vsrc, dst, vdst, n, p, tile_hist, ntiles); break;
       case 2: launch_downsweep<2>(ctx, src, vsrc, dst, vdst, n, p, tile_hist, ntiles); break;
@@ -440,12 +449,24 @@ int radix_sort_pairs(hs_ctx *ctx, const KeyPtrs &keys_in, const uint32_t *vals_i
     ctx->stats.kernel_launches++;
     ctx->stats.sort_passes++;
     HS_CUDA(cudaGetLastError());
+    HS_CUDA(cudaEventRecord(pe[3], ctx->stream));
     vsrc = vdst;
     vdst = (vdst == v_final) ? v_tmp : v_final;
     src = dst;
     dst = (dst.w[0] == A.w[0]) ? B : A;
   }
   *sorted_keys = src;
+  HS_CUDA(cudaEventSynchronize(ctx->ev_pool[4 * passes.size() - 1]));
+  for (size_t pi = 0; pi < passes.size(); ++pi) {
+    cudaEvent_t *pe = &ctx->ev_pool[4 * pi];
+    float a = 0.f, b = 0.f, c = 0.f;
+    cudaEventElapsedTime(&a, pe[0], pe[1]);
+    cudaEventElapsedTime(&b, pe[1], pe[2]);
+    cudaEventElapsedTime(&c, pe[2], pe[3]);
+    ctx->stats.ms_sort_upsweep += a;
+    ctx->stats.ms_sort_scan += b;
+    ctx->stats.ms_sort_downsweep += c;
+  }
   return HS_OK;
 }
 

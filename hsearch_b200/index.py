@@ -165,6 +165,20 @@ class HSearch:
         check(self.lib.hs_get_stats(self.ctx, C.byref(s)))
         return s
 
+    def stream_ptr(self):
+        p = C.c_void_p()
+        check(self.lib.hs_get_stream(self.ctx, C.byref(p)))
+        return p.value or 0
+
+    def search_points_dev(self, q_dev_ptr, Q, hits_dev_ptr, cap):
+        """Device-resident queries and hit buffer; returns the hit count (may exceed cap)."""
+        n = C.c_uint64(0)
+        rc = self.lib.hs_search_points_dev(self.ctx, C.c_void_p(q_dev_ptr), Q, C.c_void_p(hits_dev_ptr), cap,
+                                           C.byref(n))
+        if rc != capi.HS_ERR_CAPACITY:
+            check(rc)
+        return n.value
+
     # ---- search ------------------------------------------------------------------
     def _call_hits(self, fn, qarr, qctype, Q, cap):
         cap = int(cap)

@@ -112,6 +112,7 @@ typedef struct {
   uint32_t kernel_launches; /* kernels launched by the most recent call */
   uint32_t reserved;
   float ms_hash, ms_sort, ms_group, ms_permute;      /* index build stages */
+  float ms_sort_upsweep, ms_sort_scan, ms_sort_downsweep; /* inside ms_sort, per kernel family */
   float ms_qhash, ms_probe, ms_filter, ms_exact, ms_hitsort; /* search stages */
   float ms_total;           /* whole call, first to last event */
 } hs_stats;
@@ -125,6 +126,9 @@ const char *hs_last_error(void);
 int hs_get_stats(hs_ctx_t *ctx, hs_stats *out);
 /* 1 if a CUDA device of compute capability 10.x is visible, else 0. */
 int hs_device_available(void);
+/* The ctx's cudaStream_t (as void*), so that a caller can record its own CUDA
+ * events around calls or order its own work after them. */
+int hs_get_stream(hs_ctx_t *ctx, void **stream_out);
 
 /* ---- embedding tables (M1..M3) ---------------------------------------------- */
 /* out160 <- the 20x8 table of the given HS_TABLE_* variant. */
