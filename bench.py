@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--audit", action="store_true", help="FP64 audit of every projection (residual flips)")
+    ap.add_argument("--scalar-filter", action="store_true", help="A/B: keep all candidates on the scalar filter")
     return ap.parse_args()
 
 
@@ -191,7 +192,8 @@ def run_native(a):
         dist.init_process_group("nccl", device_id=dev)
 
     length, dim, Q, N = a.len, 8 * a.len, a.n_query, a.n_db
-    flags = hb.HS_FLAG_SORT_HITS | (hb.HS_FLAG_HASH_AUDIT if a.audit else 0)
+    flags = hb.HS_FLAG_SORT_HITS | (hb.HS_FLAG_HASH_AUDIT if a.audit else 0) | \
+        (hb.HS_FLAG_SCALAR_FILTER if a.scalar_filter else 0)
     h = hb.HSearch(length, a.K, a.L, a.W, a.R, table_variant=hb.HS_TABLE_PRINT6, flags=flags, device=local)
     h.seed_projection(12345)
     stream = torch.cuda.ExternalStream(h.stream_ptr(), device=dev)
@@ -242,7 +244,7 @@ def run_native(a):
         s_build = add_stats(["ms_sort", "ms_group", "ms_permute", "ms_sort_upsweep", "ms_sort_scan",
                              "ms_sort_downsweep"]) if collect else h.stats().as_dict()
         n = h.search_points_dev(qpts.data_ptr(), Q, hits_dev.data_ptr(), cap)
-        s_search = add_stats(["ms_qhash", "ms_probe", "ms_filter", "ms_exact", "ms_hitsort"]) if collect \
+        s_search = add_stats(["ms_qhash", "ms_probe", "ms_host", "ms_filter", "ms_filter_tc", "ms_exact", "ms_hitsort"]) if collect \
             else h.stats().as_dict()
         total = n
         if world > 1:
@@ -333,6 +335,7 @@ def run_native(a):
     KW = s_search["key_words"]
     steps = a.steps
     ncand, nsurv = s_search["n_candidates"], s_search["n_survivors"]
+    ncand_tc = s_search["n_candidates_tc"]
     passes = s_build["sort_passes"]  # over all L tables
     kern = {
         "hash_fast_kernel": {"ms": acc["ms_hash"] / steps, "bytes": N * (length + 8 * KW * a.L), "launches": 1},
@@ -343,7 +346,10 @@ def run_native(a):
                                                            "bytes": N * a.L * (8 * KW + 4), "launches": 5 * a.L},
         "permute_codes_kernel": {"ms": acc["ms_permute"] / steps, "bytes": N * a.L * (4 + 2 * length),
                                  "launches": a.L},
-        "filter_kernel": {"ms": acc["ms_filter"] / steps, "bytes": ncand * (length + 4) + nsurv * 16, "launches": 1},
+        "filter_kernel": {"ms": (acc["ms_filter"] - acc["ms_filter_tc"]) / steps,
+                          "bytes": (ncand - ncand_tc) * (length + 4) + nsurv * 16, "launches": 1},
+        "filter_tc_kernel": {"ms": acc["ms_filter_tc"] / steps, "bytes": ncand_tc * (length + 4), "launches": 1,
+                             "flops": 2.0 * ncand_tc * 20 * length},
         "exact_kernel": {"ms": acc["ms_exact"] / steps, "bytes": nsurv * (16 + length + 4) + nh * 24, "launches": 1},
     }
     for k, v in kern.items():

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhsearch_b200.so")
-CU = ["api.cu", "hash.cu", "radix_sort.cu", "verify.cu", "cluster.cu", "extract.cu"]
+CU = ["api.cu", "hash.cu", "radix_sort.cu", "verify.cu", "filter_tc.cu", "cluster.cu", "extract.cu"]
 CPP = ["tables.cpp", "comm.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -52,7 +52,42 @@ def build(force=False, verbose=False, ptxas_verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    build_cli(force=force or bool(procs), verbose=verbose)
     return LIB
+
+
+CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints"]
+BIN = os.path.join(HERE, "bin")
+
+
+def build_cli(force=False, verbose=False):
+    """The drop-in command-line programs (host C++ over the C ABI): hsearch_b200/bin/<name>."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    src_dir = os.path.join(HERE, "cli")
+    hdrs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith(".hpp")]
+    hdrs.append(os.path.join(HERE, "..", "include", "hsearch_b200.h"))
+    os.makedirs(BIN, exist_ok=True)
+    procs = []
+    for name in CLI:
+        src = os.path.join(src_dir, name + ".cpp")
+        out = os.path.join(BIN, name)
+        if force or _newer(out, [src, LIB] + hdrs):
+            cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-o", out, src, "-L" + HERE, "-lhsearch_b200",
+                   "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + "/usr/local/cuda/lib64"]
+            if verbose:
+                print(" ".join(cmd))
+            procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for name, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- {name} ---\n{out}\n")
+        elif verbose and out.strip():
+            print(f"--- {name} ---\n{out}")
+    if failed:
+        raise RuntimeError("g++ failed building the CLI programs")
+    return [os.path.join(BIN, n) for n in CLI]
 
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@ HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_CAPACITY, HS_ERR_UNSUPPORTED, HS_ERR_NOMEM, 
 HS_TABLE_FULL, HS_TABLE_PRINT6 = 0, 1
 HS_METRIC_EUCLID_FP64, HS_METRIC_BLOSUM_INT = 0, 1
 HS_PRED_D2_LE_R2, HS_PRED_SQRT_LE_R = 0, 1
-HS_FLAG_SORT_HITS, HS_FLAG_HASH_EXACT, HS_FLAG_HASH_AUDIT = 1, 2, 4
+HS_FLAG_SORT_HITS, HS_FLAG_HASH_EXACT, HS_FLAG_HASH_AUDIT, HS_FLAG_SCALAR_FILTER = 1, 2, 4, 8
 
 # every symbol include/hsearch_b200.h declares
 EXPORTS = [
@@ -45,7 +45,8 @@ class Stats(C.Structure):
                 ("ms_hash", C.c_float), ("ms_sort", C.c_float), ("ms_group", C.c_float), ("ms_permute", C.c_float),
                 ("ms_sort_upsweep", C.c_float), ("ms_sort_scan", C.c_float), ("ms_sort_downsweep", C.c_float),
                 ("ms_qhash", C.c_float), ("ms_probe", C.c_float), ("ms_filter", C.c_float), ("ms_exact", C.c_float),
-                ("ms_hitsort", C.c_float), ("ms_total", C.c_float)]
+                ("ms_hitsort", C.c_float), ("ms_total", C.c_float), ("ms_filter_tc", C.c_float),
+                ("ms_host", C.c_float), ("n_candidates_tc", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

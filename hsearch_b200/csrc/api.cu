@@ -112,8 +112,10 @@ int ensure_identity_store(hs_ctx *ctx) {
   return upload_table_pointers(ctx);
 }
 
-// Run the filter, growing the survivor buffer and retrying if it overflowed.
-int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out) {
+// Run the filter (scalar leg and, when given, the tensor-core leg; both append to
+// the same survivor list), growing the survivor buffer and retrying on overflow.
+int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out, FilterArgs *fa_tc,
+               uint32_t nblocks_tc) {
   unsigned long long *cnt = ctx->d_counters.as<unsigned long long>() + 8;
   for (int attempt = 0; attempt < 3; ++attempt) {
     if (ctx->d_surv.cap < sizeof(Survivor) * (1u << 20)) HS_TRY(ctx->d_surv.reserve(sizeof(Survivor) * (1u << 22)));
@@ -122,9 +124,18 @@ int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t
     fa.surv_count = cnt;
     HS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
     HS_TRY(launch_filter(ctx, fa, nblocks, mode));
+    if (fa_tc && nblocks_tc) {
+      fa_tc->surv = fa.surv;
+      fa_tc->surv_cap = fa.surv_cap;
+      fa_tc->surv_count = cnt;
+      HS_CUDA(cudaEventRecord(ctx->ev[10], ctx->stream));
+      HS_TRY(launch_filter_tc(ctx, *fa_tc, ctx->d_tq16.p, kTcTilesPerBlock, nblocks_tc, mode));
+      HS_CUDA(cudaEventRecord(ctx->ev[11], ctx->stream));
+    }
     unsigned long long n = 0;
     HS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (fa_tc && nblocks_tc) ctx->stats.ms_filter_tc += ev_ms(ctx->ev[10], ctx->ev[11]);
     if (n <= fa.surv_cap) {
       *nsurv_out = n;
       return HS_OK;
@@ -133,6 +144,111 @@ int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t
   }
   set_error("filter: survivor buffer kept overflowing");
   return HS_ERR_NOMEM;
+}
+
+// ---- filter work list ------------------------------------------------------------------
+// One group = the members [mb, me) of one bucket (or of the whole store) against a
+// list of queries.  Groups probed by enough queries go to the tensor-core filter
+// in items of <= kTcQueriesPerItem queries; the rest stay on the scalar filter.
+struct FilterPlan {
+  std::vector<WorkItem> items, items_tc;
+  std::vector<uint32_t> qlist, qlist_tc;
+  uint32_t nblocks = 0, nblocks_tc = 0;
+  uint64_t ncand = 0, ncand_tc = 0;
+};
+
+static int plan_add(const hs_ctx *ctx, FilterPlan &P, uint32_t table, uint32_t mb, uint32_t me, const uint32_t *q,
+                    size_t nq, bool allpairs_block) {
+  if (me <= mb || nq == 0) return HS_OK;
+  const bool tc = !(ctx->prm.flags & HS_FLAG_SCALAR_FILTER) && nq >= (size_t)tc_min_queries() &&
+                  (me - mb) >= kTcMinMembers;
+  if (tc) {
+    const size_t nchunks = (nq + kTcQueriesPerItem - 1) / kTcQueriesPerItem;
+    const size_t per = (nq + nchunks - 1) / nchunks;
+    for (size_t c = 0; c < nq; c += per) {
+      const size_t ce = std::min(nq, c + per);
+      WorkItem it;
+      it.table = table;
+      // all pairs i<j: members at or below the chunk's first query never pair with it
+      it.m_begin = allpairs_block ? std::max(mb, q[c] + 1) : mb;
+      it.m_end = me;
+      if (it.m_end <= it.m_begin) continue;
+      it.q_begin = (uint32_t)P.qlist_tc.size();
+      P.qlist_tc.insert(P.qlist_tc.end(), q + c, q + ce);
+      it.q_end = (uint32_t)P.qlist_tc.size();
+      it.block_begin = P.nblocks_tc;
+      const uint64_t per_block = (uint64_t)kTcTilesPerBlock * kTcTileMembers;
+      const uint64_t nb = ((uint64_t)(it.m_end - it.m_begin) + per_block - 1) / per_block;
+      if ((uint64_t)P.nblocks_tc + nb > 0x7fffffffull) {
+        set_error("filter work list exceeds 2^31 blocks");
+        return HS_ERR_UNSUPPORTED;
+      }
+      P.nblocks_tc += (uint32_t)nb;
+      P.items_tc.push_back(it);
+      const uint64_t pairs = (uint64_t)(it.m_end - it.m_begin) * (ce - c);
+      P.ncand += pairs;
+      P.ncand_tc += pairs;
+    }
+    return HS_OK;
+  }
+  for (size_t c = 0; c < nq; c += kQueriesPerItem) {
+    const size_t ce = std::min(nq, c + (size_t)kQueriesPerItem);
+    WorkItem it;
+    it.table = table;
+    it.m_begin = allpairs_block ? std::max(mb, q[c] + 1) : mb;
+    it.m_end = me;
+    if (it.m_end <= it.m_begin) continue;
+    it.q_begin = (uint32_t)P.qlist.size();
+    P.qlist.insert(P.qlist.end(), q + c, q + ce);
+    it.q_end = (uint32_t)P.qlist.size();
+    it.block_begin = P.nblocks;
+    const uint32_t ntiles = (it.m_end - (it.m_begin & ~3u) + kFilterTile - 1) / kFilterTile;
+    if ((uint64_t)P.nblocks + ntiles > 0x7fffffffull) {
+      set_error("filter work list exceeds 2^31 blocks");
+      return HS_ERR_UNSUPPORTED;
+    }
+    P.nblocks += ntiles;
+    P.items.push_back(it);
+    P.ncand += (uint64_t)(it.m_end - it.m_begin) * (ce - c);
+  }
+  return HS_OK;
+}
+
+// Upload the plan and run both filter legs.  tq_base: tq row of query id x is x - tq_base.
+static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_base, int mode, uint64_t *nsurv) {
+  *nsurv = 0;
+  if (P.items.empty() && P.items_tc.empty()) return HS_OK;
+  FilterArgs fa, ft;
+  memset(&fa, 0, sizeof fa);
+  fa.tq = ctx->d_tq.as<float>();
+  fa.dsq32 = ctx->d_dsq32.as<float>();
+  fa.stores = dev_stores(ctx);
+  fa.npad = ctx->npad;
+  fa.len = (int)ctx->prm.len;
+  fa.thr = filter_threshold(ctx);
+  fa.tq_base = tq_base;
+  ft = fa;
+  if (!P.items.empty()) {
+    HS_TRY(ctx->d_work.reserve(sizeof(WorkItem) * P.items.size()));
+    HS_TRY(ctx->d_qlist.reserve(sizeof(uint32_t) * P.qlist.size()));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_work.p, P.items.data(), sizeof(WorkItem) * P.items.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, P.qlist.data(), sizeof(uint32_t) * P.qlist.size(), cudaMemcpyHostToDevice, ctx->stream));
+    fa.items = ctx->d_work.as<WorkItem>();
+    fa.nitems = (uint32_t)P.items.size();
+    fa.qlist = ctx->d_qlist.as<uint32_t>();
+  }
+  if (!P.items_tc.empty()) {
+    HS_TRY(ctx->d_work_tc.reserve(sizeof(WorkItem) * P.items_tc.size()));
+    HS_TRY(ctx->d_qlist_tc.reserve(sizeof(uint32_t) * P.qlist_tc.size()));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_work_tc.p, P.items_tc.data(), sizeof(WorkItem) * P.items_tc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist_tc.p, P.qlist_tc.data(), sizeof(uint32_t) * P.qlist_tc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    ft.items = ctx->d_work_tc.as<WorkItem>();
+    ft.nitems = (uint32_t)P.items_tc.size();
+    ft.qlist = ctx->d_qlist_tc.as<uint32_t>();
+    HS_TRY(ctx->d_tq16.reserve(sizeof(uint16_t) * (size_t)tq_rows * tc_padded_k(ctx->prm.len) + 16));
+    HS_TRY(launch_tq_to_half(ctx, ctx->d_tq.as<float>(), tq_rows, ctx->d_tq16.p));
+  }
+  return run_filter(ctx, fa, P.nblocks, mode, nsurv, &ft, P.nblocks_tc);
 }
 
 // ---- hits in the reference's output order -----------------------------------------
@@ -319,68 +435,36 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
 
   // work list: queries grouped by bucket, chunked
-  std::vector<WorkItem> items;
-  std::vector<uint32_t> qlist;
-  uint64_t ncand = 0;
-  uint32_t nblocks = 0;
-  std::vector<uint64_t> order;
-  for (uint32_t l = 0; l < L; ++l) {
-    order.clear();
-    for (uint32_t q = 0; q < Q; ++q) {
-      const uint2 r = qrange[(size_t)l * Q + q];
-      if (r.y > r.x) order.push_back(((uint64_t)r.x << 32) | q);
-    }
-    std::sort(order.begin(), order.end());
-    size_t i = 0;
-    while (i < order.size()) {
-      const uint32_t mb = (uint32_t)(order[i] >> 32);
-      size_t j = i;
-      while (j < order.size() && (uint32_t)(order[j] >> 32) == mb) ++j;
-      const uint32_t me = qrange[(size_t)l * Q + (uint32_t)order[i]].y;
-      const uint32_t ntiles = (me - (mb & ~3u) + kFilterTile - 1) / kFilterTile;
-      for (size_t c = i; c < j; c += kQueriesPerItem) {
-        const size_t ce = std::min(j, c + kQueriesPerItem);
-        WorkItem it;
-        it.table = l;
-        it.m_begin = mb;
-        it.m_end = me;
-        it.q_begin = (uint32_t)qlist.size();
-        for (size_t t = c; t < ce; ++t) qlist.push_back((uint32_t)order[t]);
-        it.q_end = (uint32_t)qlist.size();
-        it.block_begin = nblocks;
-        if ((uint64_t)nblocks + ntiles > 0x7fffffffull) {
-          set_error("hs_search: work list exceeds 2^31 blocks");
-          return HS_ERR_UNSUPPORTED;
-        }
-        nblocks += ntiles;
-        items.push_back(it);
-        ncand += (uint64_t)(me - mb) * (ce - c);
+  FilterPlan plan;
+  {
+    std::vector<uint64_t> order;
+    std::vector<uint32_t> group;
+    for (uint32_t l = 0; l < L; ++l) {
+      order.clear();
+      for (uint32_t q = 0; q < Q; ++q) {
+        const uint2 r = qrange[(size_t)l * Q + q];
+        if (r.y > r.x) order.push_back(((uint64_t)r.x << 32) | q);
       }
-      i = j;
+      std::sort(order.begin(), order.end());
+      size_t i = 0;
+      while (i < order.size()) {
+        const uint32_t mb = (uint32_t)(order[i] >> 32);
+        size_t j = i;
+        group.clear();
+        while (j < order.size() && (uint32_t)(order[j] >> 32) == mb) group.push_back((uint32_t)order[j++]);
+        const uint32_t me = qrange[(size_t)l * Q + group[0]].y;
+        HS_TRY(plan_add(ctx, plan, l, mb, me, group.data(), group.size(), false));
+        i = j;
+      }
     }
   }
-  ctx->stats.n_candidates = ncand;
-  ctx->stats.n_work_items = items.size();
+  ctx->stats.n_candidates = plan.ncand;
+  ctx->stats.n_candidates_tc = plan.ncand_tc;
+  ctx->stats.n_work_items = plan.items.size() + plan.items_tc.size();
+  HS_CUDA(cudaEventRecord(ev[12], ctx->stream));
 
   uint64_t nsurv = 0;
-  if (!items.empty()) {
-    HS_TRY(ctx->d_work.reserve(sizeof(WorkItem) * items.size()));
-    HS_TRY(ctx->d_qlist.reserve(sizeof(uint32_t) * qlist.size()));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_work.p, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, qlist.data(), sizeof(uint32_t) * qlist.size(), cudaMemcpyHostToDevice, ctx->stream));
-    FilterArgs fa;
-    memset(&fa, 0, sizeof fa);
-    fa.items = ctx->d_work.as<WorkItem>();
-    fa.nitems = (uint32_t)items.size();
-    fa.qlist = ctx->d_qlist.as<uint32_t>();
-    fa.tq = ctx->d_tq.as<float>();
-    fa.dsq32 = ctx->d_dsq32.as<float>();
-    fa.stores = dev_stores(ctx);
-    fa.npad = ctx->npad;
-    fa.len = (int)ctx->prm.len;
-    fa.thr = filter_threshold(ctx);
-    HS_TRY(run_filter(ctx, fa, nblocks, kModeSearch, &nsurv));
-  }
+  HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
   HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
   ctx->stats.n_survivors = nsurv;
 
@@ -412,7 +496,8 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   HS_CUDA(cudaEventSynchronize(ev[7]));
   ctx->stats.ms_qhash = ev_ms(ev[0], ev[1]);
   ctx->stats.ms_probe = ev_ms(ev[1], ev[2]);
-  ctx->stats.ms_filter = ev_ms(ev[2], ev[3]);
+  ctx->stats.ms_host = ev_ms(ev[2], ev[12]);
+  ctx->stats.ms_filter = ev_ms(ev[12], ev[3]);
   ctx->stats.ms_exact = ev_ms(ev[3], ev[4]);
   ctx->stats.ms_hitsort = ev_ms(ev[5], ev[6]);
   ctx->stats.ms_total = ev_ms(ev[0], ev[7]);
@@ -470,49 +555,16 @@ static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit
       HS_TRY(build_tq(ctx, Q));
     }
     // work items: query chunks x member range
-    std::vector<WorkItem> items;
-    std::vector<uint32_t> qlist(nq);
-    for (uint32_t i = 0; i < nq; ++i) qlist[i] = (uint32_t)(q0 + i);  // all pairs: DB ids
-    uint32_t nblocks = 0;
-    for (uint32_t c = 0; c < nq; c += kQueriesPerItem) {
-      const uint32_t ce = std::min<uint32_t>(nq, c + kQueriesPerItem);
-      WorkItem it;
-      it.table = L;
-      it.m_begin = allpairs ? (uint32_t)std::min<uint64_t>(N, q0 + c + 1) : 0u;
-      it.m_end = (uint32_t)N;
-      if (it.m_end <= it.m_begin) continue;
-      it.q_begin = c;
-      it.q_end = ce;
-      it.block_begin = nblocks;
-      const uint32_t ntiles = (it.m_end - (it.m_begin & ~3u) + kFilterTile - 1) / kFilterTile;
-      if ((uint64_t)nblocks + ntiles > 0x7fffffffull) {
-        set_error("hs_bruteforce: work list exceeds 2^31 blocks");
-        return HS_ERR_UNSUPPORTED;
-      }
-      nblocks += ntiles;
-      items.push_back(it);
-      ncand += (uint64_t)(it.m_end - it.m_begin) * (ce - c);
-    }
-    if (items.empty()) continue;
-    HS_TRY(ctx->d_work.reserve(sizeof(WorkItem) * items.size()));
-    HS_TRY(ctx->d_qlist.reserve(sizeof(uint32_t) * qlist.size()));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_work.p, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, qlist.data(), sizeof(uint32_t) * qlist.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FilterPlan plan;
+    std::vector<uint32_t> qall(nq);
+    for (uint32_t i = 0; i < nq; ++i) qall[i] = (uint32_t)(q0 + i);  // all pairs: DB ids
+    HS_TRY(plan_add(ctx, plan, L, 0u, (uint32_t)N, qall.data(), nq, allpairs));
+    ncand += plan.ncand;
+    ctx->stats.n_candidates_tc += plan.ncand_tc;
+    if (plan.items.empty() && plan.items_tc.empty()) continue;
     HS_CUDA(cudaEventRecord(ev[1], ctx->stream));
-    FilterArgs fa;
-    memset(&fa, 0, sizeof fa);
-    fa.items = ctx->d_work.as<WorkItem>();
-    fa.nitems = (uint32_t)items.size();
-    fa.qlist = ctx->d_qlist.as<uint32_t>();
-    fa.tq = ctx->d_tq.as<float>();
-    fa.dsq32 = ctx->d_dsq32.as<float>();
-    fa.stores = dev_stores(ctx);
-    fa.npad = ctx->npad;
-    fa.len = (int)ctx->prm.len;
-    fa.thr = filter_threshold(ctx);
-    fa.tq_base = (uint32_t)q0;  // tq rows are block-relative
     uint64_t nsurv = 0;
-    HS_TRY(run_filter(ctx, fa, nblocks, allpairs ? kModeAllPairs : kModeBrute, &nsurv));
+    HS_TRY(plan_run(ctx, plan, nq, (uint32_t)q0, allpairs ? kModeAllPairs : kModeBrute, &nsurv));
     HS_CUDA(cudaEventRecord(ev[2], ctx->stream));
     nsurv_total += nsurv;
     ExactArgs ea;
@@ -636,7 +688,7 @@ void hs_destroy(hs_ctx_t *ctx) {
                     &ctx->d_qlist, &ctx->d_surv, &ctx->d_hits, &ctx->d_counters, &ctx->d_hit_keys[0],
                     &ctx->d_hit_keys[1], &ctx->d_hit_keys[2], &ctx->d_hit_perm, &ctx->d_hits_sorted,
                     &ctx->d_hits_gathered, &ctx->d_misc, &ctx->d_parent, &ctx->d_tabptrs, &ctx->d_residues,
-                    &ctx->d_starts, &ctx->d_metric32, &ctx->d_large, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
+                    &ctx->d_starts, &ctx->d_metric32, &ctx->d_tq16, &ctx->d_work_tc, &ctx->d_qlist_tc, &ctx->d_large, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
                     &ctx->sort.flags, &ctx->sort.block_sums, &ctx->sort.or_and};
   for (DevBuf *b : bufs) b->release();
   for (int w = 0; w < kMaxKeyWords; ++w) {

@@ -10,6 +10,7 @@ const uint8_t *const *dev_stores(hs_ctx *ctx);
 const uint32_t *const *dev_sorted_ids(hs_ctx *ctx);
 const uint64_t *const *dev_keys(hs_ctx *ctx);
 void fill_exact_common(hs_ctx *ctx, ExactArgs &ea, uint32_t Q);
-int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out);
+int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out,
+               FilterArgs *fa_tc = nullptr, uint32_t nblocks_tc = 0);
 int ensure_identity_store(hs_ctx *ctx);
 }  // namespace hs

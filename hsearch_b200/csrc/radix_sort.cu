@@ -16,8 +16,8 @@
 
 namespace hs {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
+constexpr int kSortThreads = 512;
+constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile
 constexpr int kSortWarps = kSortThreads / 32;
 
@@ -50,7 +50,7 @@ radix_upsweep_kernel(const uint64_t *__restrict__ kword, uint64_t n, int shift, 
                      uint32_t *__restrict__ tile_hist, uint32_t ntiles) {
   __shared__ uint32_t s_hist[256];
   const int tid = threadIdx.x;
-  s_hist[tid] = 0;
+  if (tid < 256) s_hist[tid] = 0;
   __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
 #pragma unroll 4
@@ -62,7 +62,7 @@ radix_upsweep_kernel(const uint64_t *__restrict__ kword, uint64_t n, int shift, 
     }
   }
   __syncthreads();
-  tile_hist[(uint64_t)tid * ntiles + blockIdx.x] = s_hist[tid];
+  if (tid < 256) tile_hist[(uint64_t)tid * ntiles + blockIdx.x] = s_hist[tid];
 }
 
 // ---- device-wide exclusive scan (u32), three phases ---------------------------
@@ -70,7 +70,8 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
-__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp /*[8]*/, uint32_t &total) {
+template <int NWARPS = 8>
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp /*[NWARPS]*/, uint32_t &total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t x = v;
 #pragma unroll
@@ -82,7 +83,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
   __syncthreads();
   uint32_t woff = 0, tot = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < NWARPS; ++i) {
     const uint32_t t = s_warp[i];
     if (i < wid) woff += t;
     tot += t;
@@ -164,7 +165,7 @@ int exclusive_scan_u32(hs_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t 
 constexpr size_t kDownsweepSmem = sizeof(uint64_t) * kSortTile + sizeof(uint32_t) * kSortTile;
 
 template <int NW>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 2)
 radix_downsweep_kernel(KeyPtrs in, const uint32_t *__restrict__ val_in, KeyPtrs out,
                        uint32_t *__restrict__ val_out, uint64_t n, int word, int shift, uint32_t mask,
                        const uint32_t *__restrict__ tile_off, uint32_t ntiles) {
@@ -174,7 +175,7 @@ radix_downsweep_kernel(KeyPtrs in, const uint32_t *__restrict__ val_in, KeyPtrs 
   __shared__ uint32_t s_whist[kSortWarps][257];         // per-warp digit counters (+ tail bin)
   __shared__ uint32_t s_dstart[257];
   __shared__ uint32_t s_goff[256];
-  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_warp[kSortWarps];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -186,42 +187,41 @@ radix_downsweep_kernel(KeyPtrs in, const uint32_t *__restrict__ val_in, KeyPtrs 
   const uint64_t *kw = in.w[word];
 
   uint64_t key[kSortItems];
-  uint32_t rank[kSortItems];  // rank within (warp, digit)
-  uint32_t dig[kSortItems];
+  uint32_t lp[kSortItems];  // rank within (warp, digit), then position in the tile
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
-    const bool valid = idx < n;
-    key[j] = valid ? kw[idx] : ~0ull;
-    dig[j] = valid ? ((uint32_t)(key[j] >> shift) & mask) : 256u;
+    key[j] = idx < n ? kw[idx] : ~0ull;
   }
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
-    const uint32_t d = dig[j];
+    const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
+    const uint32_t d = idx < n ? ((uint32_t)(key[j] >> shift) & mask) : 256u;
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
     const uint32_t pre = s_whist[wid][d];
     __syncwarp();
-    rank[j] = pre + __popc(peers & lt_mask);
+    lp[j] = pre + __popc(peers & lt_mask);
     if ((peers & lt_mask) == 0) s_whist[wid][d] = pre + __popc(peers);
     __syncwarp();
   }
   __syncthreads();
 
-  // per digit: exclusive prefix over warps, tile count
+  // per digit: exclusive prefix over warps, tile count (threads 0..255 <-> digits)
   uint32_t cnt = 0;
-  {
-    const int d = tid;  // 256 threads <-> 256 digits
+  if (tid < 256) {
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
-      const uint32_t c = s_whist[w][d];
-      s_whist[w][d] = cnt;
+      const uint32_t c = s_whist[w][tid];
+      s_whist[w][tid] = cnt;
       cnt += c;
     }
   }
   uint32_t total_valid;
-  const uint32_t dstart = block_exclusive_scan_256(cnt, s_warp, total_valid);
-  s_dstart[tid] = dstart;
-  s_goff[tid] = tile_off[(uint64_t)tid * ntiles + blockIdx.x] - dstart;  // dst = goff[d] + p (mod 2^32)
+  const uint32_t dstart = block_exclusive_scan_256<kSortWarps>(cnt, s_warp, total_valid);
+  if (tid < 256) {
+    s_dstart[tid] = dstart;
+    s_goff[tid] = tile_off[(uint64_t)tid * ntiles + blockIdx.x] - dstart;  // dst = goff[d] + p (mod 2^32)
+  }
   if (tid == 0) {
     s_dstart[256] = total_valid;
     uint32_t run = 0;
@@ -233,45 +233,51 @@ radix_downsweep_kernel(KeyPtrs in, const uint32_t *__restrict__ val_in, KeyPtrs 
   }
   __syncthreads();
 
-  uint32_t lp[kSortItems];
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
-    const uint32_t d = dig[j];
-    lp[j] = s_dstart[d] + s_whist[wid][d] + rank[j];
-    s_key[lp[j]] = key[j];
     const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
+    const uint32_t d = idx < n ? ((uint32_t)(key[j] >> shift) & mask) : 256u;
+    lp[j] += s_dstart[d] + s_whist[wid][d];
+    s_key[lp[j]] = key[j];
     s_val[lp[j]] = val_in ? (idx < n ? val_in[idx] : 0u) : (uint32_t)idx;
   }
   __syncthreads();
 
-  uint32_t dst[kSortItems];
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     const uint32_t p = (uint32_t)j * kSortThreads + tid;
     if (p < total_valid) {
       const uint64_t k = s_key[p];
-      const uint32_t d = (uint32_t)(k >> shift) & mask;
-      dst[j] = s_goff[d] + p;
-      out.w[word][dst[j]] = k;
-      val_out[dst[j]] = s_val[p];
+      const uint32_t dst = s_goff[(uint32_t)(k >> shift) & mask] + p;
+      out.w[word][dst] = k;
+      val_out[dst] = s_val[p];
     }
   }
-  // remaining key words ride along through the same staging buffer
-#pragma unroll
-  for (int w2 = 0; w2 < NW; ++w2) {
-    if (w2 == word) continue;
-    __syncthreads();
-    const uint64_t *src = in.w[w2];
-#pragma unroll
-    for (int j = 0; j < kSortItems; ++j) {
-      const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
-      s_key[lp[j]] = idx < n ? src[idx] : 0ull;
-    }
-    __syncthreads();
+  if (NW > 1) {
+    // remaining key words ride along through the same staging buffer; the
+    // destination of slot p is recomputed from the ranking word kept in key[]
+    uint32_t dst[kSortItems];
 #pragma unroll
     for (int j = 0; j < kSortItems; ++j) {
       const uint32_t p = (uint32_t)j * kSortThreads + tid;
-      if (p < total_valid) out.w[w2][dst[j]] = s_key[p];
+      dst[j] = p < total_valid ? s_goff[(uint32_t)(s_key[p] >> shift) & mask] + p : 0u;
+    }
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) {
+      if (w2 == word) continue;
+      __syncthreads();
+      const uint64_t *src = in.w[w2];
+#pragma unroll
+      for (int j = 0; j < kSortItems; ++j) {
+        const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
+        s_key[lp[j]] = idx < n ? src[idx] : 0ull;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kSortItems; ++j) {
+        const uint32_t p = (uint32_t)j * kSortThreads + tid;
+        if (p < total_valid) out.w[w2][dst[j]] = s_key[p];
+      }
     }
   }
 }

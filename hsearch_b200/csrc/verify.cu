@@ -275,7 +275,14 @@ __device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t 
   }
 }
 
-__global__ void exact_kernel(ExactArgs a) {
+__global__ void __launch_bounds__(128) exact_kernel(ExactArgs a) {
+  // the 20x8 embedding table and the 20x20 integer metric live in shared memory:
+  // every thread walks different rows, which thrashes L1 when read from global
+  __shared__ __align__(16) double s_table[HS_AA * HS_CDIM];
+  __shared__ int s_metric[HS_AA * HS_AA];
+  for (int i = threadIdx.x; i < HS_AA * HS_CDIM; i += blockDim.x) s_table[i] = a.table64[i];
+  for (int i = threadIdx.x; i < HS_AA * HS_AA; i += blockDim.x) s_metric[i] = a.metric_tab[i];
+  __syncthreads();
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.nsurv) return;
   const Survivor s = a.surv[i];
@@ -297,29 +304,38 @@ __global__ void exact_kernel(ExactArgs a) {
   bool hit;
   if (a.metric == HS_METRIC_BLOSUM_INT) {
     int d = 0;
-    for (int p = 0; p < a.len; ++p) d += a.metric_tab[(int)qc[p] * HS_AA + (int)mc[p]];
+    for (int p = 0; p < a.len; ++p) d += s_metric[(int)qc[p] * HS_AA + (int)mc[p]];
     d2 = (double)d;
     hit = d <= (int)a.R;
   } else {
+    // PairwiseDistance_square (motif_both_points.cpp:176-183): r = a - b; dis += r * r,
+    // strictly sequential, separate multiply and add
     double dis = 0.0;
     if (a.q64 && a.mode != kModeSelfJoin) {
-      const double *qp = a.q64 + qid * a.dim;
+      const double2 *qp = reinterpret_cast<const double2 *>(a.q64 + qid * a.dim);
       for (int p = 0; p < a.len; ++p) {
-        const double *row = a.table64 + (int)mc[p] * HS_CDIM;
+        const double2 *row = reinterpret_cast<const double2 *>(s_table + (int)mc[p] * HS_CDIM);
 #pragma unroll
-        for (int j = 0; j < HS_CDIM; ++j) {
-          const double r = __dsub_rn(row[j], qp[p * HS_CDIM + j]);
-          dis = __dadd_rn(dis, __dmul_rn(r, r));
+        for (int j = 0; j < HS_CDIM / 2; ++j) {
+          const double2 t = row[j];
+          const double2 q = __ldg(qp + p * (HS_CDIM / 2) + j);
+          const double r0 = __dsub_rn(t.x, q.x);
+          dis = __dadd_rn(dis, __dmul_rn(r0, r0));
+          const double r1 = __dsub_rn(t.y, q.y);
+          dis = __dadd_rn(dis, __dmul_rn(r1, r1));
         }
       }
     } else {
       for (int p = 0; p < a.len; ++p) {
-        const double *row = a.table64 + (int)mc[p] * HS_CDIM;
-        const double *qrow = a.table64 + (int)qc[p] * HS_CDIM;
+        const double2 *row = reinterpret_cast<const double2 *>(s_table + (int)mc[p] * HS_CDIM);
+        const double2 *qrow = reinterpret_cast<const double2 *>(s_table + (int)qc[p] * HS_CDIM);
 #pragma unroll
-        for (int j = 0; j < HS_CDIM; ++j) {
-          const double r = __dsub_rn(row[j], qrow[j]);
-          dis = __dadd_rn(dis, __dmul_rn(r, r));
+        for (int j = 0; j < HS_CDIM / 2; ++j) {
+          const double2 t = row[j], q = qrow[j];
+          const double r0 = __dsub_rn(t.x, q.x);
+          dis = __dadd_rn(dis, __dmul_rn(r0, r0));
+          const double r1 = __dsub_rn(t.y, q.y);
+          dis = __dadd_rn(dis, __dmul_rn(r1, r1));
         }
       }
     }

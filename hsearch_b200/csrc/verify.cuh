@@ -55,6 +55,18 @@ int launch_build_tq_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, float *
 int launch_build_tq_int(hs_ctx *ctx, const uint8_t *d_qcodes, uint32_t Q, float *d_tq);
 int launch_filter(hs_ctx *ctx, const FilterArgs &args, uint32_t nblocks, int mode);
 
+// Tensor-core filter (filter_tc.cu).  A TC work item holds <= kTcQueriesPerItem
+// queries; its block_begin counts blocks of kTcTilesPerBlock 128-member tiles.
+constexpr uint32_t kTcQueriesPerItem = 128;
+constexpr uint32_t kTcTileMembers = 128;
+constexpr uint32_t kTcTilesPerBlock = 16;
+constexpr uint32_t kTcMinMembers = 64;
+int tc_min_queries();           // buckets probed by fewer queries stay on the scalar filter
+uint32_t tc_padded_k(uint32_t len);
+int launch_tq_to_half(hs_ctx *ctx, const float *d_tq, uint64_t nq, void *d_tq16);
+int launch_filter_tc(hs_ctx *ctx, const FilterArgs &args, const void *d_tq16, uint32_t tiles_per_block,
+                     uint32_t nblocks, int mode);
+
 struct ExactArgs {
   const Survivor *surv;
   unsigned long long nsurv;

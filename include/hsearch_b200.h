@@ -69,8 +69,10 @@ enum {
                                query, first-finding table, ascending db id */
   HS_FLAG_HASH_EXACT = 2u,  /* hash every projection in FP64 reference order
                                (no FP32 fast path); for validation */
-  HS_FLAG_HASH_AUDIT = 4u   /* after hashing, recompute every projection in
+  HS_FLAG_HASH_AUDIT = 4u,  /* after hashing, recompute every projection in
                                FP64 and count residual flips (must be 0) */
+  HS_FLAG_SCALAR_FILTER = 8u /* keep every candidate on the scalar filter kernel
+                               (no tcgen05 filter); for A/B validation */
 };
 
 typedef struct {
@@ -115,6 +117,9 @@ typedef struct {
   float ms_sort_upsweep, ms_sort_scan, ms_sort_downsweep; /* inside ms_sort, per kernel family */
   float ms_qhash, ms_probe, ms_filter, ms_exact, ms_hitsort; /* search stages */
   float ms_total;           /* whole call, first to last event */
+  float ms_filter_tc;       /* inside ms_filter: the tensor-core (tcgen05) filter kernel */
+  float ms_host;            /* search: host-side work-list construction between probe and filter */
+  uint64_t n_candidates_tc; /* of n_candidates, pairs examined by the tensor-core filter */
 } hs_stats;
 
 /* ---- lifetime -------------------------------------------------------------- */

@@ -290,3 +290,49 @@ def test_extract_windows(oracle):
         want = oracle.hash_codes(ocodes, oracle.coordinates(True), a, b, 50.0)
         assert np.array_equal(got, want)
         h.close()
+
+
+# ---------------------------------------------------------------- tensor-core filter
+@pytest.mark.parametrize("length,R,metric", [(10, 30.0, hb.HS_METRIC_EUCLID_FP64), (25, 60.0, hb.HS_METRIC_EUCLID_FP64),
+                                             (32, 80.0, hb.HS_METRIC_EUCLID_FP64), (10, 40.0, hb.HS_METRIC_BLOSUM_INT),
+                                             (3, 12.0, hb.HS_METRIC_EUCLID_FP64)])
+def test_tensor_filter_equals_scalar_filter(oracle, length, R, metric):
+    """The tcgen05 filter and the scalar filter must hand the exact stage survivor
+    sets that produce identical hits (same order, same FP64 distances), and the
+    tensor-core leg must actually have run."""
+    n, q = 60000, 500
+    codes = random_codes(n, length, seed=101)
+    qcodes = planted_queries(codes, q, seed=102)
+    res = []
+    for flags in (hb.HS_FLAG_SORT_HITS, hb.HS_FLAG_SORT_HITS | hb.HS_FLAG_SCALAR_FILTER):
+        h, a, b = make(length, 4, 4, 50.0, R, metric=metric, flags=flags)
+        h.load_fragments(codes)
+        h.build_index()
+        got = h.search_codes(qcodes, cap=1 << 22)
+        st = h.stats()
+        if flags & hb.HS_FLAG_SCALAR_FILTER:
+            assert st.n_candidates_tc == 0
+        else:
+            assert st.n_candidates_tc > 0
+        res.append((hits_as_tuples(got), st.n_candidates))
+        h.close()
+    assert res[0][1] == res[1][1]
+    assert len(res[0][0]) > 0 and res[0][0] == res[1][0]
+
+
+def test_tensor_filter_full_query_tiles(oracle):
+    """Buckets probed by more than 128 queries are split into several items; odd
+    query counts exercise the N padding."""
+    n, q, length = 40000, 1111, 10
+    codes = random_codes(n, length, seed=111)
+    qcodes = planted_queries(codes, q, seed=112)
+    tab = oracle.coordinates(True)
+    h, a, b = make(length, 2, 2, 80.0, 28.0)
+    h.load_fragments(codes)
+    h.build_index()
+    got = h.search_codes(qcodes, cap=1 << 23)
+    assert h.stats().n_candidates_tc > 0
+    want, ts, _ = oracle.search(oracle.embed(codes, tab), oracle.embed(qcodes, tab), a, b, 80.0, 28.0, pred=0)
+    assert len(want) > 0
+    assert hits_as_tuples(got) == hits_as_tuples(want)
+    h.close()
