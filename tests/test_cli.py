@@ -1,0 +1,164 @@
+"""The drop-in command-line programs (hsearch_b200/bin/*, host C++ over the C ABI)
+against the reference's own programs compiled in place (oracle/_ref/bin/*):
+same argv grammar, same messages and exit codes, same output files.
+
+CPU part: option parsing / help / missing-argument protocol
+(smithlab OptionParser semantics, hclust/src/smithlab_cpp/OptionParser.cpp:156-184;
+motif_both_points.cpp:324-335) and protein2datapoints (host-only program).
+GPU part: protein2datapoints -> motif_both_points_noLSH -> evaluate2 ->
+motif_both_points end to end, output files byte-identical to the reference's.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "hsearch_b200", "bin")
+REF = os.path.join(ROOT, "oracle", "_ref", "bin")
+PROGS = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints"]
+AA = "ARNDCQEGHILKMFPSTWYV"
+
+
+def _have(dirname, prog):
+    return os.access(os.path.join(dirname, prog), os.X_OK)
+
+
+def _ensure_built():
+    if not all(_have(OURS, p) for p in PROGS):
+        from hsearch_b200 import build
+        build.build()
+
+
+def run(dirname, prog, args, cwd, env=None):
+    """argv[0] is the bare program name for both builds so that the echoed
+    command line (motif_both_points.cpp:268-273) compares equal."""
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([prog] + args, executable=os.path.join(dirname, prog), cwd=cwd, env=e,
+                       capture_output=True, text=True, timeout=600)
+    return p.returncode, p.stdout, p.stderr
+
+
+needs_ref = pytest.mark.skipif(not all(_have(REF, p) for p in PROGS),
+                               reason="oracle/_ref/bin not built (no /root/reference here and no prebuilt copy)")
+
+
+@needs_ref
+@pytest.mark.parametrize("prog", PROGS)
+@pytest.mark.parametrize("args", [[], ["-help"], ["-?"], ["-about"], ["-d", "x"], ["-db", "x", "-l", "10"],
+                                  ["db", "x"], ["-o", "out", "-l", "7"]])
+def test_option_protocol_matches_reference(tmp_path, prog, args):
+    _ensure_built()
+    want = run(REF, prog, args, tmp_path)
+    got = run(OURS, prog, args, tmp_path)
+    assert got == want
+
+
+@pytest.mark.parametrize("prog", PROGS)
+def test_missing_required_option_exits_zero(tmp_path, prog):
+    """First missing required option -> message on stderr, exit status SUCCESS
+    (motif_both_points.cpp:332-335), also without the reference binaries."""
+    _ensure_built()
+    rc, out, err = run(OURS, prog, ["-l", "10"], tmp_path)
+    assert rc == 0
+    assert "required argument missing" in err and "-d" in err
+    assert out.startswith("[WELCOME TO HSEARCH v1.0]\n[%s -l 10]\n" % prog)
+
+
+def write_fasta(path, n, plen, seed, with_eq=True):
+    rng = np.random.default_rng(seed)
+    with open(path, "w") as f:
+        for i in range(n):
+            seq = "".join(AA[c] for c in rng.integers(0, 20, size=plen))
+            f.write(f">prot{i} some description\n{seq}\n")
+
+
+@needs_ref
+@pytest.mark.parametrize("length,plen", [(10, 30), (25, 40), (8, 8)])
+def test_protein2datapoints_matches_reference(tmp_path, length, plen):
+    """Proteins no longer than len + 29 yield exactly one window (j = 0), so the
+    random stride (rand(), protein2datapoints.cpp:57,70) never matters; E/Q are
+    present, so the ProteinDB swap (protein.hpp:59-63) is exercised."""
+    _ensure_built()
+    write_fasta(tmp_path / "db.fa", 300, plen, seed=5)
+    a = run(REF, "protein2datapoints", ["-d", "db.fa", "-l", str(length), "-n", "250", "-o", "ref.pts"], tmp_path)
+    b = run(OURS, "protein2datapoints", ["-d", "db.fa", "-l", str(length), "-n", "250", "-o", "our.pts"], tmp_path)
+    assert a[0] == b[0] == 0
+    ref, our = open(tmp_path / "ref.pts").read(), open(tmp_path / "our.pts").read()
+    assert ref == our and ref.count("\n") == 2 * 250
+
+    def strip_time(s):
+        return [l for l in s.splitlines() if not l.startswith("It takes")]
+    assert strip_time(a[1]) == strip_time(b[1].replace("our.pts", "ref.pts"))
+
+
+def strip_volatile(stdout):
+    """Drop the lines that carry timings."""
+    keep = []
+    for l in stdout.splitlines():
+        if l.startswith("ACCURACY:"):
+            l = " ".join(l.split()[:2])  # recall only; the second number is seconds
+        if l.startswith("It takes") or l.startswith("time "):
+            continue
+        keep.append(l)
+    return keep
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("W", ["50", "20"])
+def test_search_pipeline_matches_reference(tmp_path, W):
+    """The reference's own workflow, both builds side by side,
+    LSH seeded identically through HS_REF_SEED (oracle/fixed_rd.hpp)."""
+    _ensure_built()
+    length, R = 10, "30"
+    write_fasta(tmp_path / "db.fa", 4000, 36, seed=7)
+    write_fasta(tmp_path / "q.fa", 60, 12, seed=8)
+    # plant near neighbours: queries 0..29 copy DB windows with one substitution
+    db = open(tmp_path / "db.fa").read().splitlines()
+    q = open(tmp_path / "q.fa").read().splitlines()
+    rng = np.random.default_rng(9)
+    for i in range(30):
+        s = list(db[2 * int(rng.integers(0, 4000)) + 1][:12])
+        s[int(rng.integers(0, 10))] = AA[int(rng.integers(0, 20))]
+        q[2 * i + 1] = "".join(s)
+    open(tmp_path / "q.fa", "w").write("\n".join(q) + "\n")
+    env = {"HS_REF_SEED": "12345"}
+    for d, tag in ((REF, "ref"), (OURS, "our")):
+        assert run(d, "protein2datapoints", ["-d", "db.fa", "-l", str(length), "-n", "4000", "-o", f"{tag}.db"],
+                   tmp_path)[0] == 0
+        assert run(d, "protein2datapoints", ["-d", "q.fa", "-l", str(length), "-n", "60", "-o", f"{tag}.q"],
+                   tmp_path)[0] == 0
+    assert open(tmp_path / "ref.db").read() == open(tmp_path / "our.db").read()
+    assert open(tmp_path / "ref.q").read() == open(tmp_path / "our.q").read()
+
+    # brute force ground truth
+    a = run(REF, "motif_both_points_noLSH", ["-d", "ref.db", "-c", "ref.q", "-l", str(length), "-T", R, "-o", "ref.gt"],
+            tmp_path, env)
+    b = run(OURS, "motif_both_points_noLSH", ["-d", "our.db", "-c", "our.q", "-l", str(length), "-T", R, "-o", "our.gt"],
+            tmp_path, dict(env, HS_NOLSH_NONHITS="1"))
+    assert a[0] == 0 and b[0] == 0, b[2]
+    ref_gt, our_gt = open(tmp_path / "ref.gt").read(), open(tmp_path / "our.gt").read()
+    assert ref_gt == our_gt and ref_gt.count("\n") > 30
+    # the dump of every non-hit (motif_both_points_noLSH.cpp:47-49)
+    assert open(tmp_path / "ref.gtnotlessthan.txt").read() == open(tmp_path / "our.gtnotlessthan.txt").read()
+
+    # evaluate2 sorts the ground truth (evaluate2.cpp:88-96); both searches read the same sorted file
+    ev = os.path.join(REF, "evaluate2")
+    subprocess.run([ev, "ref.gt"], cwd=tmp_path, capture_output=True, timeout=120)
+    gts = "ref.gtsort.txt"
+    assert os.path.exists(tmp_path / gts)
+
+    a = run(REF, "motif_both_points", ["-d", "ref.db", "-c", "ref.q", "-l", str(length), "-W", W, "-T", R, "-g", gts,
+                                       "-o", "ref.hits"], tmp_path, env)
+    b = run(OURS, "motif_both_points", ["-d", "our.db", "-c", "our.q", "-l", str(length), "-W", W, "-T", R, "-g", gts,
+                                        "-o", "our.hits"], tmp_path, env)
+    assert a[0] == 0 and b[0] == 0, b[2]
+    ref_hits, our_hits = open(tmp_path / "ref.hits").read(), open(tmp_path / "our.hits").read()
+    assert ref_hits == our_hits and ref_hits.count("\n") > 10
+    assert open(tmp_path / "ref.hits.accuracy.txt").read() == open(tmp_path / "our.hits.accuracy.txt").read()
+    sa, sb = strip_volatile(a[1]), strip_volatile(b[1])
+    sb = [l.replace("our.", "ref.") for l in sb]
+    assert sa == sb
