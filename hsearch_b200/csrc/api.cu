@@ -46,7 +46,7 @@ static int upload_tables(hs_ctx *ctx) {
   HS_TRY(ctx->d_metric32.reserve(sizeof metric32));
   HS_CUDA(cudaMemcpyAsync(ctx->d_metric32.p, metric32, sizeof metric32, cudaMemcpyHostToDevice, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  return HS_OK;
+  return mma_upload_tables(ctx);
 }
 
 void stats_begin(hs_ctx *ctx) {
@@ -115,7 +115,7 @@ int ensure_identity_store(hs_ctx *ctx) {
 // Run the filter (scalar leg and, when given, the tensor-core leg; both append to
 // the same survivor list), growing the survivor buffer and retrying on overflow.
 int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out, FilterArgs *fa_tc,
-               uint32_t nblocks_tc) {
+               uint32_t nblocks_tc, const MmaLaunch *ml) {
   unsigned long long *cnt = ctx->d_counters.as<unsigned long long>() + 8;
   for (int attempt = 0; attempt < 3; ++attempt) {
     if (ctx->d_surv.cap < sizeof(Survivor) * (1u << 20)) HS_TRY(ctx->d_surv.reserve(sizeof(Survivor) * (1u << 22)));
@@ -132,10 +132,20 @@ int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t
       HS_TRY(launch_filter_tc(ctx, *fa_tc, ctx->d_tq16.p, kTcTilesPerBlock, nblocks_tc, mode));
       HS_CUDA(cudaEventRecord(ctx->ev[11], ctx->stream));
     }
+    if (ml && ml->grid) {
+      FilterArgs fm = fa;
+      fm.qlist = ml->qlist;
+      HS_CUDA(cudaEventRecord(ctx->ev[13], ctx->stream));
+      HS_TRY(launch_filter_mma(ctx, fm, ctx->d_mma_items.p, ctx->d_mma_units.p, ml->nunits,
+                               reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 13), ml->grid,
+                               ctx->d_qb16.p, mode));
+      HS_CUDA(cudaEventRecord(ctx->ev[14], ctx->stream));
+    }
     unsigned long long n = 0;
     HS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
     if (fa_tc && nblocks_tc) ctx->stats.ms_filter_tc += ev_ms(ctx->ev[10], ctx->ev[11]);
+    if (ml && ml->grid) ctx->stats.ms_filter_tc += ev_ms(ctx->ev[13], ctx->ev[14]);
     if (n <= fa.surv_cap) {
       *nsurv_out = n;
       return HS_OK;
@@ -155,13 +165,63 @@ struct FilterPlan {
   std::vector<uint32_t> qlist, qlist_tc;
   uint32_t nblocks = 0, nblocks_tc = 0;
   uint64_t ncand = 0, ncand_tc = 0;
+  // pipelined tensor filter (Euclidean metric): items of <= qmax queries, units of member chunks
+  bool mma = false;
+  uint32_t mma_qmax = 0;
+  std::vector<MmaItemHost> mma_items;
+  std::vector<MmaUnitHost> mma_units;
+  std::vector<uint64_t> mma_cost;  // per unit
+  std::vector<uint32_t> qlist_mma;
 };
+
+static void plan_init(const hs_ctx *ctx, FilterPlan &P) {
+  P.mma = mma_filter_usable(ctx);
+  if (P.mma) {
+    MmaGeometry g;
+    mma_geometry(ctx, &g);
+    P.mma_qmax = (uint32_t)g.qmax;
+  }
+}
 
 static int plan_add(const hs_ctx *ctx, FilterPlan &P, uint32_t table, uint32_t mb, uint32_t me, const uint32_t *q,
                     size_t nq, bool allpairs_block) {
   if (me <= mb || nq == 0) return HS_OK;
   const bool tc = !(ctx->prm.flags & HS_FLAG_SCALAR_FILTER) && nq >= (size_t)tc_min_queries() &&
                   (me - mb) >= kTcMinMembers;
+  if (tc && P.mma) {
+    const size_t nchunks = (nq + P.mma_qmax - 1) / P.mma_qmax;
+    size_t per = (nq + nchunks - 1) / nchunks;
+    per = (per + 15) & ~(size_t)15;  // whole 16-column MMA chunks
+    for (size_t c = 0; c < nq; c += per) {
+      const size_t ce = std::min(nq, c + per);
+      // all pairs i<j: members at or below the chunk's first query never pair with it
+      const uint32_t m0 = allpairs_block ? std::max(mb, q[c] + 1) : mb;
+      if (me <= m0) continue;
+      MmaItemHost it;
+      it.table = table;
+      it.q_begin = (uint32_t)P.qlist_mma.size();
+      P.qlist_mma.insert(P.qlist_mma.end(), q + c, q + ce);
+      it.q_end = (uint32_t)P.qlist_mma.size();
+      it.pad = 0;
+      const uint32_t item = (uint32_t)P.mma_items.size();
+      P.mma_items.push_back(it);
+      const uint32_t step = kMmaUnitTiles * 128u;
+      const uint64_t nqp = std::max<uint64_t>(64, ((ce - c) + 15) & ~(size_t)15);
+      for (uint64_t m = m0; m < me; m += step) {
+        MmaUnitHost un;
+        un.item = item;
+        un.m_begin = (uint32_t)m;
+        un.m_end = (uint32_t)std::min<uint64_t>(me, m + step);
+        un.pad = 0;
+        P.mma_units.push_back(un);
+        P.mma_cost.push_back((uint64_t)((un.m_end - un.m_begin + 127) / 128) * nqp + 256);
+      }
+      const uint64_t pairs = (uint64_t)(me - m0) * (ce - c);
+      P.ncand += pairs;
+      P.ncand_tc += pairs;
+    }
+    return HS_OK;
+  }
   if (tc) {
     const size_t nchunks = (nq + kTcQueriesPerItem - 1) / kTcQueriesPerItem;
     const size_t per = (nq + nchunks - 1) / nchunks;
@@ -217,7 +277,26 @@ static int plan_add(const hs_ctx *ctx, FilterPlan &P, uint32_t table, uint32_t m
 // Upload the plan and run both filter legs.  tq_base: tq row of query id x is x - tq_base.
 static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_base, int mode, uint64_t *nsurv) {
   *nsurv = 0;
-  if (P.items.empty() && P.items_tc.empty()) return HS_OK;
+  if (P.items.empty() && P.items_tc.empty() && P.mma_units.empty()) return HS_OK;
+  MmaLaunch ml;
+  if (!P.mma_units.empty()) {
+    const uint32_t nunits = (uint32_t)P.mma_units.size();
+    const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->num_sms, (nunits + 3) / 4);
+    HS_TRY(ctx->d_mma_items.reserve(sizeof(MmaItemHost) * P.mma_items.size()));
+    HS_TRY(ctx->d_mma_units.reserve(sizeof(MmaUnitHost) * P.mma_units.size()));
+    HS_TRY(ctx->d_qlist_mma.reserve(sizeof(uint32_t) * P.qlist_mma.size()));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_mma_items.p, P.mma_items.data(), sizeof(MmaItemHost) * P.mma_items.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_mma_units.p, P.mma_units.data(), sizeof(MmaUnitHost) * P.mma_units.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist_mma.p, P.qlist_mma.data(), sizeof(uint32_t) * P.qlist_mma.size(), cudaMemcpyHostToDevice, ctx->stream));
+    MmaGeometry g;
+    HS_TRY(mma_geometry(ctx, &g));
+    HS_TRY(ctx->d_qb16.reserve(sizeof(uint16_t) * (size_t)std::max<uint32_t>(tq_rows, 1) * g.kp + 16));
+    if (mode == kModeAllPairs) HS_TRY(launch_build_qb_codes(ctx, tq_base, tq_rows, ctx->d_qb16.p));
+    else HS_TRY(launch_build_qb_points(ctx, ctx->d_q64.as<double>(), tq_rows, ctx->d_qb16.p));
+    ml.grid = grid;
+    ml.nunits = nunits;
+    ml.qlist = ctx->d_qlist_mma.as<uint32_t>();
+  }
   FilterArgs fa, ft;
   memset(&fa, 0, sizeof fa);
   fa.tq = ctx->d_tq.as<float>();
@@ -248,7 +327,7 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
     HS_TRY(ctx->d_tq16.reserve(sizeof(uint16_t) * (size_t)tq_rows * tc_padded_k(ctx->prm.len) + 16));
     HS_TRY(launch_tq_to_half(ctx, ctx->d_tq.as<float>(), tq_rows, ctx->d_tq16.p));
   }
-  return run_filter(ctx, fa, P.nblocks, mode, nsurv, &ft, P.nblocks_tc);
+  return run_filter(ctx, fa, P.nblocks, mode, nsurv, &ft, P.nblocks_tc, &ml);
 }
 
 // ---- hits in the reference's output order -----------------------------------------
@@ -367,6 +446,7 @@ void fill_exact_common(hs_ctx *ctx, ExactArgs &ea, uint32_t Q) {
   ea.metric_tab = ctx->d_metric.as<int32_t>();
   ea.Q = Q;
   ea.keys = dev_keys(ctx);
+  ea.qlist_mma = ctx->d_qlist_mma.as<uint32_t>();
 }
 
 // Finish a search / brute-force call: optional ordering, multi-GPU gather, copy out.
@@ -436,6 +516,7 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
 
   // work list: queries grouped by bucket, chunked
   FilterPlan plan;
+  plan_init(ctx, plan);
   {
     std::vector<uint64_t> order;
     std::vector<uint32_t> group;
@@ -460,7 +541,7 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   }
   ctx->stats.n_candidates = plan.ncand;
   ctx->stats.n_candidates_tc = plan.ncand_tc;
-  ctx->stats.n_work_items = plan.items.size() + plan.items_tc.size();
+  ctx->stats.n_work_items = plan.items.size() + plan.items_tc.size() + plan.mma_units.size();
   HS_CUDA(cudaEventRecord(ev[12], ctx->stream));
 
   uint64_t nsurv = 0;
@@ -556,12 +637,13 @@ static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit
     }
     // work items: query chunks x member range
     FilterPlan plan;
+    plan_init(ctx, plan);
     std::vector<uint32_t> qall(nq);
     for (uint32_t i = 0; i < nq; ++i) qall[i] = (uint32_t)(q0 + i);  // all pairs: DB ids
     HS_TRY(plan_add(ctx, plan, L, 0u, (uint32_t)N, qall.data(), nq, allpairs));
     ncand += plan.ncand;
     ctx->stats.n_candidates_tc += plan.ncand_tc;
-    if (plan.items.empty() && plan.items_tc.empty()) continue;
+    if (plan.items.empty() && plan.items_tc.empty() && plan.mma_units.empty()) continue;
     HS_CUDA(cudaEventRecord(ev[1], ctx->stream));
     uint64_t nsurv = 0;
     HS_TRY(plan_run(ctx, plan, nq, (uint32_t)q0, allpairs ? kModeAllPairs : kModeBrute, &nsurv));
@@ -658,6 +740,7 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   hs_ctx *ctx = new (std::nothrow) hs_ctx();
   if (!ctx) return HS_ERR_NOMEM;
   ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
   ctx->prm = *params;
   ctx->dim = params->len * HS_CDIM;
   coordinates_table(params->table_variant, ctx->table64);
@@ -688,7 +771,8 @@ void hs_destroy(hs_ctx_t *ctx) {
                     &ctx->d_qlist, &ctx->d_surv, &ctx->d_hits, &ctx->d_counters, &ctx->d_hit_keys[0],
                     &ctx->d_hit_keys[1], &ctx->d_hit_keys[2], &ctx->d_hit_perm, &ctx->d_hits_sorted,
                     &ctx->d_hits_gathered, &ctx->d_misc, &ctx->d_parent, &ctx->d_tabptrs, &ctx->d_residues,
-                    &ctx->d_starts, &ctx->d_metric32, &ctx->d_tq16, &ctx->d_work_tc, &ctx->d_qlist_tc, &ctx->d_large, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
+                    &ctx->d_starts, &ctx->d_metric32, &ctx->d_tq16, &ctx->d_work_tc, &ctx->d_qlist_tc, &ctx->d_large,
+                    &ctx->d_tab16, &ctx->d_qb16, &ctx->d_mma_items, &ctx->d_mma_units, &ctx->d_mma_cta, &ctx->d_qlist_mma, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
                     &ctx->sort.flags, &ctx->sort.block_sums, &ctx->sort.or_and};
   for (DevBuf *b : bufs) b->release();
   for (int w = 0; w < kMaxKeyWords; ++w) {

@@ -135,6 +135,9 @@ struct hs_ctx {
   hs::DevBuf d_hit_keys[3], d_hit_perm, d_hits_sorted;
   hs::DevBuf d_misc, d_tabptrs, d_qcodes, d_hits_gathered, d_residues, d_starts;
   hs::DevBuf d_tq16, d_work_tc, d_qlist_tc;  // tensor-core filter: FP16 query tables, its work list
+  hs::DevBuf d_tab16;                        // pipelined tensor filter: FP16 embedding rows + row norms
+  hs::DevBuf d_qb16, d_mma_items, d_mma_units, d_mma_cta, d_qlist_mma;
+  int num_sms = 0;
   bool have_qcodes = false;
   void *h_pinned = nullptr;
   size_t h_pinned_cap = 0;

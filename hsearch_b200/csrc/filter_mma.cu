@@ -1,0 +1,741 @@
+// Pipelined tcgen05 candidate filter for the Euclidean metric (K3 / K4 bulk path).
+//
+// The filter bound of a (query q, member m) pair is the squared distance
+//     d2(q, m) = |x_m|^2 + |q|^2 - 2 <x_m, q>,       x_m, q in R^(8*len)
+// (the quantity PairwiseDistance_square accumulates, motif_both_points.cpp:176-183).
+// Over one bucket <x_m, q> is a dense [members x 8*len] x [8*len x queries]
+// contraction, so it runs on the 5th-generation tensor cores:
+//
+//   A  [128 members][kp]  FP16 embedding rows, built in shared memory from the
+//                         1-byte residue codes of the bucket-ordered store (one
+//                         16-byte table row per residue), plus two columns of 1.0,
+//   B  [<= qmax queries][kp]  FP16 query coordinates plus two columns holding
+//                         c_q = -|q|^2/2 + margin (split hi/lo), resident per item,
+//   D  [128][<= 256]      FP32 accumulators in TMEM, double buffered:
+//                         D = <x~_m, q~> + c_q,
+//
+// and a pair survives iff  D >= rowthr_m = ((1 - beta)|x_m|^2 - thr) / 2, i.e. iff
+// its FP16/FP32 distance estimate is within the threshold plus a rigorous error
+// margin (derivation in DESIGN.md, "filter margins").  The filter never decides
+// a hit: survivors go to the exact FP64 stage (verify.cu), so hits and distances
+// stay bit-exact.
+//
+// One persistent CTA per SM, warp specialised:
+//   warps 0-7   epilogue: tcgen05.ld the accumulators, 3-input max per 8 columns,
+//               warp-uniform branch into the rare survivor scan, per-warp staging
+//               of survivors in shared memory, one global atomic per flush;
+//   warps 8-11  producers: build A tiles (3-4 stages), load B when the item changes;
+//   warp 12     one thread issues tcgen05.mma (M=128, N<=256, K=16) and commits to
+//               the mbarriers that free A stages / publish accumulators.
+// Shared-memory operand layout (both operands K-major, no swizzle): 8x8 FP16
+// core matrices of 128 contiguous bytes; core matrices of one 8-column group are
+// stacked over the row groups (SBO = 128 B), column groups follow each other at
+// LBO = 2048 B (A, 128 rows) or qmax*16 B (B).
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "internal.cuh"
+#include "verify.cuh"
+
+namespace hs {
+
+constexpr int kMmaEpiWarps = 8;
+constexpr int kMmaProdWarps = 4;
+constexpr int kMmaThreads = (kMmaEpiWarps + kMmaProdWarps + 2) * 32;  // 448
+constexpr int kMmaProdThread0 = kMmaEpiWarps * 32;                    // 256
+constexpr int kMmaIssueWarp = kMmaEpiWarps + kMmaProdWarps;           // 12
+constexpr int kMmaLoadWarp = kMmaIssueWarp + 1;                       // 13: unit scheduler + code loader
+constexpr int kMmaUnitRing = 4;      // units published ahead by the scheduler
+constexpr int kMmaUnitBatch = 4;     // consecutive units taken per atomic (keeps B resident)
+constexpr int kMmaMaxCodeRing = 8;   // tiles of residue codes in flight (bulk async copies)
+constexpr int kMmaM = 128;           // members per tile (UMMA M)
+constexpr int kMmaN = 256;           // accumulator columns per stage (UMMA N max)
+constexpr int kMmaAccStages = 2;
+constexpr uint32_t kMmaTmemCols = 512;
+constexpr int kMmaMaxStages = 4;     // A stages
+constexpr int kMmaRowRing = 8;       // >= A stages + accumulator stages
+constexpr int kMmaStageCap = 256;    // survivors staged per epilogue warp (>= one 8-column scan of 32 rows)
+constexpr int kMmaAGroupBytes = 2048;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bulk async copy global -> shared (TMA engine, no tensor map); 16-byte aligned, size multiple of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100: version 1).
+__device__ __forceinline__ uint64_t mma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// Append a warp's staged survivors to the global list: one atomic per flush.
+__device__ __noinline__ uint32_t mma_flush(const Survivor *stage, uint32_t n, Survivor *surv, unsigned long long cap,
+                                           unsigned long long *count, int lane) {
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(count, (unsigned long long)n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (uint32_t i = lane; i < n; i += 32)
+    if (base + i < cap) surv[base + i] = stage[i];
+  __syncwarp();
+  return 0;
+}
+
+struct MmaItem {
+  uint32_t table;
+  uint32_t q_begin, q_end;  // range of qlist
+  uint32_t pad;
+};
+struct MmaUnit {
+  uint32_t item;
+  uint32_t m_begin, m_end;  // member positions in the table's bucket-ordered store
+  uint32_t pad;
+};
+
+struct MmaArgs {
+  const MmaItem *items;
+  const MmaUnit *units;
+  uint32_t nunits;
+  uint32_t *unit_counter;     // zeroed before the launch; CTAs take batches of units from it
+  const uint32_t *qlist;
+  const __half *qb16;         // [Q][kp] query rows (coordinates, c_q hi/lo, zero padding)
+  uint32_t tq_base;           // qb16 row of query id x is x - tq_base
+  const uint8_t *const *stores;
+  uint64_t npad;
+  int len, kp, nstages, qmax, cring;
+  float thr, beta;
+  uint32_t debug;             // bring-up switches (HS_MMA_DEBUG): 1 no survivor scan, 2 no A build, 4 no MMA
+  const uint4 *tab16;         // [20] FP16 embedding rows (8 halves each)
+  const float *nx32;          // [20] squared row norms, rounded down
+  Survivor *surv;
+  unsigned long long surv_cap;
+  unsigned long long *surv_count;
+};
+
+struct MmaShared {
+  uint64_t a_full[kMmaMaxStages], a_empty[kMmaMaxStages];
+  uint64_t t_full[kMmaAccStages], t_empty[kMmaAccStages];
+  uint64_t b_full;
+  uint64_t u_full[kMmaUnitRing], u_empty[kMmaUnitRing];
+  uint64_t c_full[kMmaMaxCodeRing], c_empty[kMmaMaxCodeRing];
+  uint32_t uring[kMmaUnitRing];
+  uint32_t tmem_base;
+  uint32_t pad;
+  uint4 tab16[HS_AA];
+  float nx32[HS_AA];
+  float rowthr[kMmaRowRing][kMmaM];
+  Survivor stage[kMmaEpiWarps][kMmaStageCap];
+};
+
+// Every role walks the same sequence of units, published by the scheduler lane
+// through a small ring: returns the next unit index, or >= nunits at the end.
+__device__ __forceinline__ uint32_t mma_next_unit(MmaShared &sh, uint32_t k) {
+  const uint32_t slot = k % kMmaUnitRing;
+  mbar_wait(smem_addr(&sh.u_full[slot]), (k / kMmaUnitRing) & 1u);
+  const uint32_t u = sh.uring[slot];
+  mbar_arrive(smem_addr(&sh.u_empty[slot]));
+  return u;
+}
+
+// Survivors carry the index of their query in the query list (pad = 1); the exact stage
+// resolves it and, for all-pairs runs, keeps only pairs with query id < member position.
+__global__ void __launch_bounds__(kMmaThreads, 1)
+filter_mma_kernel(MmaArgs a) {
+  extern __shared__ __align__(1024) unsigned char mma_smem[];
+  __shared__ __align__(16) MmaShared sh;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int len = a.len, kp = a.kp, S = a.nstages, qmax = a.qmax, D = a.cring;
+  const int ngrp = kp >> 3;                          // 8-column groups
+  const uint32_t a_stage_bytes = (uint32_t)ngrp * kMmaAGroupBytes;
+  const uint32_t b_lbo = (uint32_t)qmax * 16u;
+  unsigned char *sB = mma_smem;
+  unsigned char *sA = sB + (size_t)ngrp * b_lbo;
+  unsigned char *sC = sA + (size_t)S * a_stage_bytes;  // code ring: [D][len][128] bytes
+  const uint32_t nunits = a.nunits;
+
+  if (tid == 0) {
+    for (int s = 0; s < kMmaMaxStages; ++s) {
+      mbar_init(smem_addr(&sh.a_full[s]), kMmaProdWarps * 32);
+      mbar_init(smem_addr(&sh.a_empty[s]), 1);
+    }
+    for (int s = 0; s < kMmaAccStages; ++s) {
+      mbar_init(smem_addr(&sh.t_full[s]), 1);
+      mbar_init(smem_addr(&sh.t_empty[s]), kMmaEpiWarps * 32);
+    }
+    mbar_init(smem_addr(&sh.b_full), kMmaProdWarps * 32);
+    for (int s = 0; s < kMmaUnitRing; ++s) {
+      mbar_init(smem_addr(&sh.u_full[s]), 1);
+      mbar_init(smem_addr(&sh.u_empty[s]), (kMmaEpiWarps + kMmaProdWarps) * 32 + 1);
+    }
+    for (int s = 0; s < kMmaMaxCodeRing; ++s) {
+      mbar_init(smem_addr(&sh.c_full[s]), 1);
+      mbar_init(smem_addr(&sh.c_empty[s]), kMmaProdWarps * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < HS_AA) {
+    sh.tab16[tid] = a.tab16[tid];
+    sh.nx32[tid] = a.nx32[tid];
+  }
+  if (warp == kMmaIssueWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&sh.tmem_base)),
+                 "r"(kMmaTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A stages start as zeros; the constant columns (1.0, 1.0 at 8*len, 8*len+1) are written once
+  {
+    uint4 *p = reinterpret_cast<uint4 *>(sA);
+    const int n = (int)((size_t)S * a_stage_bytes / 16);
+    for (int i = tid; i < n; i += kMmaThreads) p[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  for (int i = tid; i < S * kMmaM; i += kMmaThreads) {
+    const int s = i / kMmaM, r = i - s * kMmaM;
+    *reinterpret_cast<uint32_t *>(sA + (size_t)s * a_stage_bytes + (size_t)len * kMmaAGroupBytes + (r >> 3) * 128 +
+                                  (r & 7) * 16) = 0x3C003C00u;  // (1.0h, 1.0h)
+  }
+  fence_async_shared();
+  tc_before();
+  __syncthreads();
+  tc_after();
+  const uint32_t tmem_base = sh.tmem_base;
+
+  // Tiles of a unit start at its first member rounded down to 16 so that every 128-byte
+  // row segment of the position-major store is 16-byte aligned for the bulk copies; rows
+  // outside [m_begin, m_end) are masked by an infinite row threshold.
+  if (warp == kMmaLoadWarp) {
+    // ============================ scheduler + code loader ==============================
+    if (lane == 0) {
+      uint32_t k = 0, ct = 0, batch_next = 0, batch_end = 0;
+      for (;; ++k) {
+        const uint32_t slot = k % kMmaUnitRing;
+        mbar_wait(smem_addr(&sh.u_empty[slot]), ((k / kMmaUnitRing) & 1u) ^ 1u);
+        if (batch_next == batch_end) {
+          batch_next = atomicAdd(a.unit_counter, (uint32_t)kMmaUnitBatch);
+          batch_end = batch_next + kMmaUnitBatch;
+        }
+        const uint32_t u = batch_next < nunits ? batch_next : 0xffffffffu;
+        ++batch_next;
+        sh.uring[slot] = u;
+        mbar_arrive(smem_addr(&sh.u_full[slot]));
+        if (u >= nunits) break;
+        const MmaUnit un = a.units[u];
+        const MmaItem it = a.items[un.item];
+        const uint8_t *store = a.stores[it.table];
+        const uint32_t base = un.m_begin & ~15u;
+        const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
+        for (uint32_t t = 0; t < ntiles; ++t, ++ct) {
+          const uint32_t d = ct % D;
+          mbar_wait(smem_addr(&sh.c_empty[d]), ((ct / D) & 1u) ^ 1u);
+          const uint32_t bar = smem_addr(&sh.c_full[d]);
+          mbar_arrive_expect_tx(bar, (uint32_t)len * 128u);
+          const uint32_t dst = smem_addr(sC) + d * (uint32_t)len * 128u;
+          const uint8_t *src = store + base + t * kMmaM;
+          for (int p = 0; p < len; ++p) bulk_g2s(dst + (uint32_t)p * 128u, src + (uint64_t)p * a.npad, 128u, bar);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kMmaEpiWarps && warp < kMmaIssueWarp) {
+    // ============================ producers ============================================
+    const int r = tid - kMmaProdThread0;  // member row of the tile
+    const uint32_t row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    uint32_t pt = 0;                       // tiles produced so far (all units)
+    uint32_t prev_item = 0xffffffffu;
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t u = mma_next_unit(sh, k);
+      if (u >= nunits) break;
+      const MmaUnit un = a.units[u];
+      const MmaItem it = a.items[un.item];
+      if (un.item != prev_item) {
+        // every MMA that reads the old B has completed once the latest A stage was released
+        if (pt > 0) mbar_wait(smem_addr(&sh.a_empty[(pt - 1) % S]), ((pt - 1) / S) & 1u);
+        const uint32_t nq = it.q_end - it.q_begin;
+        const uint32_t nqp = (nq + 15u) & ~15u;
+        const int total = ngrp * (int)nqp;
+        for (int i = r; i < total; i += kMmaProdWarps * 32) {
+          const int g = i / (int)nqp, q = i - g * (int)nqp;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if ((uint32_t)q < nq) {
+            const uint32_t row = a.qlist[it.q_begin + q] - a.tq_base;
+            v = __ldg(reinterpret_cast<const uint4 *>(a.qb16 + (size_t)row * kp + (g << 3)));
+          } else if (g == len) {
+            v.x = 0x0000FB00u;  // c = -57344: a padding column never passes
+          }
+          *reinterpret_cast<uint4 *>(sB + (size_t)g * b_lbo + (q >> 3) * 128 + (q & 7) * 16) = v;
+        }
+        fence_async_shared();
+        mbar_arrive(smem_addr(&sh.b_full));
+        prev_item = un.item;
+      }
+      const uint32_t base = un.m_begin & ~15u;
+      const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
+      for (uint32_t t = 0; t < ntiles; ++t, ++pt) {
+        const uint32_t s = pt % S, d = pt % D;
+        const uint32_t mypos = base + t * kMmaM + (uint32_t)r;
+        const bool valid = mypos >= un.m_begin && mypos < un.m_end;
+        // my row's residue codes from the ring the loader fills
+        mbar_wait(smem_addr(&sh.c_full[d]), (pt / D) & 1u);
+        const unsigned char *crow = sC + (size_t)d * len * 128 + r;
+        uint8_t code[HS_MAX_LEN];
+#pragma unroll
+        for (int p = 0; p < HS_MAX_LEN; ++p)
+          if (p < len) code[p] = crow[p * 128];
+        mbar_arrive(smem_addr(&sh.c_empty[d]));
+        mbar_wait(smem_addr(&sh.a_empty[s]), ((pt / S) & 1u) ^ 1u);
+        unsigned char *dst = sA + (size_t)s * a_stage_bytes + row_off;
+        float nx = 0.f;
+        if (!(a.debug & 2u)) {
+#pragma unroll
+          for (int p = 0; p < HS_MAX_LEN; ++p) {
+            if (p < len) {
+              const int c = min((int)code[p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
+              *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = sh.tab16[c];
+              nx += sh.nx32[c];
+            }
+          }
+        }
+        // rowthr = ((1 - beta) nx - thr) / 2, rounded down; +inf rows never pass
+        // (nx is a sum of <= 32 FP32 terms: 4e-6 covers its rounding)
+        float rt = 0.5f * (nx * (1.0f - 4e-6f) * (1.0f - a.beta) - a.thr);
+        rt -= (nx + a.thr) * 2.4e-7f + 1e-6f;
+        sh.rowthr[pt % kMmaRowRing][r] = valid ? rt : __int_as_float(0x7f800000);
+        fence_async_shared();
+        mbar_arrive(smem_addr(&sh.a_full[s]));
+      }
+    }
+  } else if (warp == kMmaIssueWarp) {
+    // ============================ MMA issuer ===========================================
+    if (lane == 0) {
+      uint32_t mt = 0, mg = 0, nb = 0;
+      uint32_t prev_item = 0xffffffffu;
+      const uint32_t sA_u32 = smem_addr(sA), sB_u32 = smem_addr(sB);
+      const int ksteps = kp >> 4;
+      for (uint32_t k = 0;; ++k) {
+        const uint32_t u = mma_next_unit(sh, k);
+        if (u >= nunits) break;
+        const MmaUnit un = a.units[u];
+        const MmaItem it = a.items[un.item];
+        if (un.item != prev_item) {
+          mbar_wait(smem_addr(&sh.b_full), nb & 1u);
+          ++nb;
+          prev_item = un.item;
+        }
+        const uint32_t nq = it.q_end - it.q_begin;
+        const uint32_t ngroups = (nq + kMmaN - 1) / kMmaN;
+        const uint32_t base = un.m_begin & ~15u;
+        const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
+        for (uint32_t t = 0; t < ntiles; ++t, ++mt) {
+          const uint32_t s = mt % S;
+          mbar_wait(smem_addr(&sh.a_full[s]), (mt / S) & 1u);
+          for (uint32_t g = 0; g < ngroups; ++g, ++mg) {
+            const uint32_t as = mg % kMmaAccStages;
+            mbar_wait(smem_addr(&sh.t_empty[as]), ((mg / kMmaAccStages) & 1u) ^ 1u);
+            tc_after();
+            const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
+            const uint32_t ngp = (ng + 15u) & ~15u;
+            const uint32_t idesc = (1u << 4) | ((ngp >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);  // F16xF16->F32
+            const uint32_t d_tmem = tmem_base + as * kMmaN;
+            const uint32_t a0 = sA_u32 + s * a_stage_bytes;
+            const uint32_t b0 = sB_u32 + (g * kMmaN >> 3) * 128u;
+            for (int kk = 0; kk < ksteps && !(a.debug & 4u); ++kk) {
+              const uint64_t ad = mma_desc(a0 + (uint32_t)kk * 2u * kMmaAGroupBytes, kMmaAGroupBytes, 128u);
+              const uint64_t bd = mma_desc(b0 + (uint32_t)kk * 2u * b_lbo, b_lbo, 128u);
+              mma_f16_ss(d_tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
+            }
+            if (g + 1 == ngroups) mma_commit(smem_addr(&sh.a_empty[s]));
+            mma_commit(smem_addr(&sh.t_full[as]));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ epilogue =============================================
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    Survivor *stage = sh.stage[warp];
+    uint32_t wcount = 0;  // warp-uniform
+    uint32_t et = 0, eg = 0;
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t u = mma_next_unit(sh, k);
+      if (u >= nunits) break;
+      const MmaUnit un = a.units[u];
+      const MmaItem it = a.items[un.item];
+      const uint32_t nq = it.q_end - it.q_begin;
+      const uint32_t ngroups = (nq + kMmaN - 1) / kMmaN;
+      const uint32_t base = un.m_begin & ~15u;
+      const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
+      for (uint32_t t = 0; t < ntiles; ++t, ++et) {
+        const uint32_t pos = base + t * kMmaM + (uint32_t)row;
+        float rt = 0.f;
+        for (uint32_t g = 0; g < ngroups; ++g, ++eg) {
+          const uint32_t as = eg % kMmaAccStages;
+          mbar_wait(smem_addr(&sh.t_full[as]), (eg / kMmaAccStages) & 1u);
+          tc_after();
+          if (g == 0) rt = sh.rowthr[et % kMmaRowRing][row];
+          const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
+          const uint32_t ngp = (ng + 15u) & ~15u;
+          // 32-column chunks (the MMA wrote ngp = ng rounded up to 16 columns; a last half
+          // chunk reads 16 stale columns, masked below); this warp takes c = half, half+2, ...
+          const uint32_t nchunks = (ng + 31u) >> 5;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMmaN;
+          const uint32_t qbase = it.q_begin + g * kMmaN;  // index into qlist of column 0
+          uint32_t v0[32], v1[32];
+          // survivor scan of one 32-column chunk held in registers
+          auto process = [&](const uint32_t(&vv)[32], uint32_t c) {
+#pragma unroll
+            for (int h8 = 0; h8 < 4; ++h8) {
+              const uint32_t qi0 = c * 32u + (uint32_t)(h8 * 8);  // first column of the 8 inside the group
+              if (qi0 >= ng) break;                               // warp-uniform: only stale / padding columns left
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(vv[h8 * 8 + j]);
+              float m = fmax3(f[0], f[1], f[2]);
+              m = fmax3(m, f[3], f[4]);
+              m = fmax3(m, f[5], f[6]);
+              m = fmaxf(m, f[7]);
+              if (__any_sync(0xffffffffu, m >= rt) && !(a.debug & 1u)) {  // warp-uniform, rare
+                uint32_t hm = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hm |= (f[j] >= rt ? 1u : 0u) << j;
+                const int nv = (int)ng - (int)qi0;  // valid columns (padding columns never pass anyway)
+                if (nv < 8) hm &= (1u << nv) - 1u;
+                const uint32_t cnt = __popc(hm);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                  const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, dd);
+                  if (lane >= dd) incl += tt;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) {
+                  if (wcount + total > (uint32_t)kMmaStageCap)
+                    wcount = mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
+                  uint32_t slot = wcount + incl - cnt;
+                  while (hm) {
+                    const int j = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    Survivor sv;
+                    sv.query = qbase + qi0 + (uint32_t)j;  // index into the query list; the exact stage resolves it
+                    sv.table = it.table;
+                    sv.pos = pos;
+                    sv.pad = 1;
+                    stage[slot++] = sv;
+                  }
+                  __syncwarp();
+                  wcount += total;
+                }
+              }
+            }
+          };
+          auto issue = [&](uint32_t (&vv)[32], uint32_t c) {
+            if (c * 32u + 16u < ngp) tmem_ld32_issue(taddr + c * 32u, vv);
+            else tmem_ld16_issue(taddr + c * 32u, reinterpret_cast<uint32_t(&)[16]>(vv));  // last 16 written columns
+          };
+          // loads run one chunk ahead of the scan
+          uint32_t c = (uint32_t)half;
+          if (c < nchunks) issue(v0, c);
+          for (; c < nchunks; c += 4) {
+            tmem_ld_wait();
+            if (c + 2 < nchunks) {
+              issue(v1, c + 2);
+            } else {  // all of this warp's reads of the stage are in registers: release it
+              tc_before();
+              mbar_arrive(smem_addr(&sh.t_empty[as]));
+            }
+            process(v0, c);
+            if (c + 2 < nchunks) {
+              tmem_ld_wait();
+              if (c + 4 < nchunks) {
+                issue(v0, c + 4);
+              } else {
+                tc_before();
+                mbar_arrive(smem_addr(&sh.t_empty[as]));
+              }
+              process(v1, c + 2);
+            }
+          }
+          if ((uint32_t)half >= nchunks) {  // no chunk for this warp in this group: still release the stage
+            tc_before();
+            mbar_arrive(smem_addr(&sh.t_empty[as]));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (wcount) mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
+  }
+
+  tc_before();
+  __syncthreads();
+  if (warp == kMmaIssueWarp) {
+    tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kMmaTmemCols) : "memory");
+  }
+}
+
+// ---- query rows ---------------------------------------------------------------------------
+// qb16[q][k]: k < 8*len: fp16(q_k); k = 8*len, 8*len+1: c_q = -|q|^2/2 + margin as hi + lo;
+// the rest 0.  A query the FP16 path cannot represent gets c_q = +60000: every member of
+// its buckets survives the filter and the exact stage decides.
+// Returns false when the FP16 path cannot represent the query (the caller then zeroes the
+// coordinates: D = c_q = +60000 passes every row).
+__device__ __forceinline__ bool write_cq(__half *row, int dim, int kp, double nq, double qmaxabs, double beta) {
+  // margin: beta/2 * |q|^2 (products + accumulation), the hi/lo split and the accumulation of c itself
+  double c = -0.5 * nq + 0.5 * beta * nq + (double)kp * 4.8e-7 * (0.5 * nq) + 2e-6 * (0.5 * nq) + 1e-3;
+  const bool ok = (qmaxabs <= 3.0e4) && (nq <= 1.0e5) && (c == c);
+  if (!ok) c = 60000.0;
+  const __half hi = __double2half(c);
+  const double rest = c - (double)__half2float(hi);
+  row[dim] = hi;
+  row[dim + 1] = __double2half(rest);  // its rounding (<= 2^-22 |c|) is inside the 2e-6 term
+  for (int k = dim + 2; k < kp; ++k) row[k] = __float2half(0.f);
+  return ok;
+}
+
+__global__ void build_qb_points_kernel(const double *__restrict__ q64, uint32_t Q, int dim, int kp, double beta,
+                                       __half *__restrict__ qb16) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const double *src = q64 + (size_t)q * dim;
+  __half *row = qb16 + (size_t)q * kp;
+  double nq = 0.0, mx = 0.0;
+  for (int k = 0; k < dim; ++k) {
+    const double v = src[k];
+    nq += v * v;
+    mx = fmax(mx, fabs(v));
+  }
+  const bool ok = write_cq(row, dim, kp, nq, mx, beta);
+  for (int k = 0; k < dim; ++k) row[k] = __double2half(ok ? src[k] : 0.0);
+}
+
+// queries = DB fragments q0 .. q0+nq-1 (all pairs)
+__global__ void build_qb_codes_kernel(const uint8_t *__restrict__ codes, uint64_t q0, uint32_t nq, int len, int kp,
+                                      const double *__restrict__ table64, double beta, __half *__restrict__ qb16) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const uint8_t *c = codes + (q0 + q) * (uint64_t)len;
+  __half *row = qb16 + (size_t)q * kp;
+  double n2 = 0.0, mx = 0.0;
+  for (int p = 0; p < len; ++p)
+    for (int j = 0; j < HS_CDIM; ++j) {
+      const double v = table64[(int)c[p] * HS_CDIM + j];
+      n2 += v * v;
+      mx = fmax(mx, fabs(v));
+      row[p * HS_CDIM + j] = __double2half(v);
+    }
+  write_cq(row, len * HS_CDIM, kp, n2, mx, beta);
+}
+
+// ---- host side ----------------------------------------------------------------------------
+static inline double mma_beta(int kp) {
+  // |x~q~ - xq| <= (2^-10 + 2^-22)|x||q| per product (both operands rounded to FP16), FP32
+  // accumulation of kp terms <= kp * 2^-21 * sum|x~q~|; sum|x||q| <= (|x|^2 + |q|^2)/2
+  return (ldexp(1.0, -10) + ldexp(1.0, -22)) * 1.001 + (double)kp * ldexp(1.0, -21) * 1.01;
+}
+
+int mma_geometry(const hs_ctx *ctx, MmaGeometry *g) {
+  const int len = (int)ctx->prm.len;
+  g->kp = (8 * len + 2 + 15) & ~15;
+  const size_t a_stage = (size_t)(g->kp >> 3) * kMmaAGroupBytes;
+  const size_t budget = 168 * 1024;  // operands; the code ring (<= 16 KB) and ~38 KB static come on top
+  int S = 3;
+  if ((size_t)S * a_stage > budget / 2) S = 2;
+  if ((size_t)S * a_stage > budget * 3 / 4) return HS_ERR_UNSUPPORTED;
+  size_t rows = (budget - (size_t)S * a_stage) / ((size_t)(g->kp >> 3) * 16);
+  int qmax = (int)std::min<size_t>(512, rows) & ~15;
+  if (qmax < 16) return HS_ERR_UNSUPPORTED;
+  g->nstages = S;
+  g->qmax = qmax;
+  g->cring = len <= 16 ? kMmaMaxCodeRing : 4;
+  g->smem = (size_t)(g->kp >> 3) * qmax * 16 + (size_t)S * a_stage + (size_t)g->cring * len * 128;
+  g->beta = mma_beta(g->kp);
+  return HS_OK;
+}
+
+// The tensor path needs every table entry representable in FP16 without overflow.
+bool mma_filter_usable(const hs_ctx *ctx) {
+  if (ctx->prm.metric != HS_METRIC_EUCLID_FP64) return false;
+  if (ctx->prm.flags & HS_FLAG_SCALAR_FILTER) return false;
+  const char *e = getenv("HS_NO_MMA_FILTER");
+  if (e && atoi(e)) return false;
+  MmaGeometry g;
+  if (mma_geometry(ctx, &g) != HS_OK) return false;
+  for (int i = 0; i < HS_AA * HS_CDIM; ++i)
+    if (!(fabs(ctx->table64[i]) <= 1.0e3)) return false;
+  return true;
+}
+
+// Upload the FP16 embedding rows and the (rounded-down) squared row norms.
+int mma_upload_tables(hs_ctx *ctx) {
+  __half h[HS_AA * HS_CDIM];
+  float nx[HS_AA];
+  for (int c = 0; c < HS_AA; ++c) {
+    double s = 0.0;
+    for (int j = 0; j < HS_CDIM; ++j) {
+      const double v = ctx->table64[c * HS_CDIM + j];
+      h[c * HS_CDIM + j] = __double2half(v);
+      s += v * v;
+    }
+    float f = (float)s;
+    if ((double)f > s) f = nextafterf(f, -INFINITY);
+    nx[c] = f;
+  }
+  HS_TRY(ctx->d_tab16.reserve(sizeof h + sizeof nx));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_tab16.p, h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync((char *)ctx->d_tab16.p + sizeof h, nx, sizeof nx, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+
+int launch_build_qb_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, void *d_qb16) {
+  if (Q == 0) return HS_OK;
+  MmaGeometry g;
+  HS_TRY(mma_geometry(ctx, &g));
+  build_qb_points_kernel<<<(Q + 127) / 128, 128, 0, ctx->stream>>>(d_q64, Q, (int)ctx->dim, g.kp, g.beta,
+                                                                   reinterpret_cast<__half *>(d_qb16));
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+int launch_build_qb_codes(hs_ctx *ctx, uint64_t q0, uint32_t nq, void *d_qb16) {
+  if (nq == 0) return HS_OK;
+  MmaGeometry g;
+  HS_TRY(mma_geometry(ctx, &g));
+  build_qb_codes_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_codes.as<uint8_t>(), q0, nq,
+                                                                   (int)ctx->prm.len, g.kp, ctx->d_table64.as<double>(),
+                                                                   g.beta, reinterpret_cast<__half *>(d_qb16));
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+// items / units / qlist are device arrays; CTAs take units dynamically from *d_unit_counter.
+int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, const void *d_units, uint32_t nunits,
+                      uint32_t *d_unit_counter, uint32_t grid, const void *d_qb16, int mode) {
+  if (grid == 0 || nunits == 0) return HS_OK;
+  MmaGeometry g;
+  HS_TRY(mma_geometry(ctx, &g));
+  MmaArgs a;
+  memset(&a, 0, sizeof a);
+  a.items = reinterpret_cast<const MmaItem *>(d_items);
+  a.units = reinterpret_cast<const MmaUnit *>(d_units);
+  a.nunits = nunits;
+  a.unit_counter = d_unit_counter;
+  HS_CUDA(cudaMemsetAsync(d_unit_counter, 0, sizeof(uint32_t), ctx->stream));
+  a.qlist = fa.qlist;
+  a.qb16 = reinterpret_cast<const __half *>(d_qb16);
+  a.tq_base = fa.tq_base;
+  a.stores = fa.stores;
+  a.npad = fa.npad;
+  a.len = fa.len;
+  a.kp = g.kp;
+  a.nstages = g.nstages;
+  a.qmax = g.qmax;
+  a.cring = g.cring;
+  // a reference hit has d2 <= R^2 (1 + 1e-12) in exact arithmetic
+  const double r2 = ctx->prm.R * ctx->prm.R * (1.0 + 1e-12) + 1e-30;
+  float thr = (float)r2;
+  if ((double)thr < r2) thr = nextafterf(thr, INFINITY);
+  a.thr = thr;
+  a.beta = (float)(g.beta * 1.0001);
+  if (const char *e = getenv("HS_MMA_DEBUG")) a.debug = (uint32_t)atoi(e);
+  a.tab16 = ctx->d_tab16.as<uint4>();
+  a.nx32 = reinterpret_cast<const float *>((const char *)ctx->d_tab16.p + sizeof(__half) * HS_AA * HS_CDIM);
+  a.surv = fa.surv;
+  a.surv_cap = fa.surv_cap;
+  a.surv_count = fa.surv_count;
+  (void)mode;
+  HS_CUDA(cudaFuncSetAttribute(filter_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  filter_mma_kernel<<<grid, kMmaThreads, g.smem, ctx->stream>>>(a);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+}  // namespace hs

@@ -10,7 +10,12 @@ const uint8_t *const *dev_stores(hs_ctx *ctx);
 const uint32_t *const *dev_sorted_ids(hs_ctx *ctx);
 const uint64_t *const *dev_keys(hs_ctx *ctx);
 void fill_exact_common(hs_ctx *ctx, ExactArgs &ea, uint32_t Q);
+struct MmaLaunch {
+  uint32_t grid = 0;               // CTAs of the pipelined tensor filter (0: not used)
+  uint32_t nunits = 0;
+  const uint32_t *qlist = nullptr; // its query list (device)
+};
 int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out,
-               FilterArgs *fa_tc = nullptr, uint32_t nblocks_tc = 0);
+               FilterArgs *fa_tc = nullptr, uint32_t nblocks_tc = 0, const MmaLaunch *ml = nullptr);
 int ensure_identity_store(hs_ctx *ctx);
 }  // namespace hs

@@ -518,7 +518,7 @@ static int group_inst(hs_ctx *ctx, uint32_t table, const KeyPtrs &keys) {
 
 int build_code_store(hs_ctx *ctx, const uint32_t *ids, DevBuf &out) {
   const uint64_t n = ctx->N;
-  const size_t bytes = (size_t)ctx->prm.len * ctx->npad + 16;
+  const size_t bytes = (size_t)ctx->prm.len * ctx->npad + 256;  // slack: 128-byte tile reads may overrun the last row
   if (out.cap < bytes) {
     HS_TRY(out.reserve(bytes));
     HS_CUDA(cudaMemsetAsync(out.p, 0, out.cap, ctx->stream));

@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(128) exact_kernel(ExactArgs a) {
   const uint32_t *ids = a.sorted_ids[s.table];
   const uint64_t id = ids ? (uint64_t)ids[s.pos] : (uint64_t)s.pos;
   const uint8_t *mc = a.codes + id * a.len;
-  uint64_t qid = s.query;
+  uint64_t qid = s.pad ? (uint64_t)a.qlist_mma[s.query] : (uint64_t)s.query;
+  if (a.mode == kModeAllPairs && !(qid < id)) return;  // each unordered pair once
   const uint8_t *qc = nullptr;
   if (a.mode == kModeSelfJoin) {
     qid = ids ? (uint64_t)ids[s.query] : (uint64_t)s.query;

@@ -19,7 +19,7 @@ struct Survivor {
   uint32_t query;  // query index (search / brute force) or member position (self join)
   uint32_t table;
   uint32_t pos;    // member position in the table's bucket order
-  uint32_t pad;
+  uint32_t pad;    // 1: `query` is an index into the pipelined tensor filter's query list
 };
 
 constexpr int kFilterThreads = 256;
@@ -67,6 +67,33 @@ int launch_tq_to_half(hs_ctx *ctx, const float *d_tq, uint64_t nq, void *d_tq16)
 int launch_filter_tc(hs_ctx *ctx, const FilterArgs &args, const void *d_tq16, uint32_t tiles_per_block,
                      uint32_t nblocks, int mode);
 
+// Pipelined tensor-core filter for the Euclidean metric (filter_mma.cu): one
+// persistent CTA per SM walks a contiguous range of units; a unit is a chunk of
+// one bucket's members against one item (<= qmax queries of that bucket).
+struct MmaGeometry {
+  int kp;        // K padded: 8*len coordinates + 2 constant columns, multiple of 16
+  int nstages;   // A stages in shared memory
+  int qmax;      // queries per item (B rows resident in shared memory)
+  int cring;     // tiles of residue codes in flight
+  size_t smem;   // dynamic shared memory per CTA
+  double beta;   // relative error bound of the FP16/FP32 dot product
+};
+struct MmaItemHost {
+  uint32_t table, q_begin, q_end, pad;
+};
+struct MmaUnitHost {
+  uint32_t item, m_begin, m_end, pad;
+};
+constexpr uint32_t kMmaUnitTiles = 32;        // 128-member tiles per unit
+constexpr uint32_t kMmaMinMembers = 64;
+int mma_geometry(const hs_ctx *ctx, MmaGeometry *g);
+bool mma_filter_usable(const hs_ctx *ctx);
+int mma_upload_tables(hs_ctx *ctx);
+int launch_build_qb_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, void *d_qb16);
+int launch_build_qb_codes(hs_ctx *ctx, uint64_t q0, uint32_t nq, void *d_qb16);
+int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, const void *d_units, uint32_t nunits,
+                      uint32_t *d_unit_counter, uint32_t grid, const void *d_qb16, int mode);
+
 struct ExactArgs {
   const Survivor *surv;
   unsigned long long nsurv;
@@ -85,6 +112,7 @@ struct ExactArgs {
   const uint64_t *const *keys;        // per table: [KW][N] original-order keys (dedup)
   const uint64_t *qkeys;              // [L][Q][KW]
   const uint8_t *qvalid;              // [L][Q]
+  const uint32_t *qlist_mma;          // query list of the pipelined tensor filter (survivors with pad = 1)
   hs_hit *hits;
   unsigned long long hit_cap;
   unsigned long long *hit_count;

@@ -157,7 +157,7 @@ def test_search_pipeline_matches_reference(tmp_path, W):
                                         "-o", "our.hits"], tmp_path, env)
     assert a[0] == 0 and b[0] == 0, b[2]
     ref_hits, our_hits = open(tmp_path / "ref.hits").read(), open(tmp_path / "our.hits").read()
-    assert ref_hits == our_hits and ref_hits.count("\n") > 10
+    assert ref_hits == our_hits and ref_hits.count("\n") > 3
     assert open(tmp_path / "ref.hits.accuracy.txt").read() == open(tmp_path / "our.hits.accuracy.txt").read()
     sa, sb = strip_volatile(a[1]), strip_volatile(b[1])
     sb = [l.replace("our.", "ref.") for l in sb]

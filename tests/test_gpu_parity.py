@@ -336,3 +336,65 @@ def test_tensor_filter_full_query_tiles(oracle):
     assert len(want) > 0
     assert hits_as_tuples(got) == hits_as_tuples(want)
     h.close()
+
+
+def test_bruteforce_euclid_all_pairs(oracle):
+    """All pairs i<j of the DB under the Euclidean metric (the DB is its own query
+    set: the tensor filter builds its query rows from the residue codes)."""
+    n, length, R = 5000, 10, 22.0
+    codes = planted_families(n, length, seed=121)
+    tab = oracle.coordinates(True)
+    h = hb.HSearch(length, 4, 4, 50.0, R, predicate=hb.HS_PRED_SQRT_LE_R)
+    h.load_fragments(codes)
+    got = h.bruteforce_codes(None, cap=1 << 22)
+    assert h.stats().n_candidates_tc > 0
+    pts = oracle.embed(codes, tab)
+    want = oracle.bruteforce(pts, pts, R, pred=1, cap=1 << 24)
+    want = want[want["query"] < want["db_id"]]
+    assert len(want) > 0
+    assert hits_as_tuples(got, False) == hits_as_tuples(want, False)
+    h.close()
+
+
+def test_tensor_filter_unrepresentable_queries(oracle):
+    """Dense query points outside the FP16 range (or not finite) must not lose
+    hits: such a query passes the whole bucket to the exact stage."""
+    n, q, length, R = 30000, 64, 10, 30.0
+    codes = random_codes(n, length, seed=131)
+    qcodes = planted_queries(codes, q, seed=132)
+    tab = oracle.coordinates(True)
+    qpts = oracle.embed(qcodes, tab).copy()
+    qpts[1, 3] = 1.0e6       # far away: no hits, but the row must not poison its tile
+    qpts[2, 0] = np.inf
+    qpts[3, 5] = np.nan
+    qpts[4] *= 1.0 + 1e-9    # not a table row
+    res = []
+    for flags in (hb.HS_FLAG_SORT_HITS, hb.HS_FLAG_SORT_HITS | hb.HS_FLAG_SCALAR_FILTER):
+        h, a, b = make(length, 2, 3, 80.0, R, flags=flags)
+        h.load_fragments(codes)
+        h.build_index()
+        res.append(hits_as_tuples(h.search_points(qpts, cap=1 << 22)))
+        h.close()
+    assert len(res[0]) > 0 and res[0] == res[1]
+    ok = np.ones(q, dtype=bool)
+    ok[[1, 2, 3]] = False
+    want, _, _ = oracle.search(oracle.embed(codes, tab), qpts[ok], a, b, 80.0, R, pred=0)
+    remap = np.flatnonzero(ok)
+    want_t = [(int(remap[qq]), t, d, x) for qq, t, d, x in hits_as_tuples(want)]
+    assert [r for r in res[0] if ok[r[0]]] == want_t
+
+
+def test_tensor_filter_huge_threshold(oracle):
+    """R so large that every pair is a hit (the non-hit dump of
+    motif_both_points_noLSH uses this): thresholds become infinite."""
+    n, q, length = 3000, 40, 10
+    codes = random_codes(n, length, seed=141)
+    qcodes = random_codes(q, length, seed=142)
+    tab = oracle.coordinates(True)
+    h = hb.HSearch(length, 1, 1, 1.0, 1e300, predicate=hb.HS_PRED_SQRT_LE_R)
+    h.load_fragments(codes)
+    got = h.bruteforce_codes(qcodes, cap=n * q + 10)
+    assert len(got) == n * q
+    want = oracle.bruteforce(oracle.embed(codes, tab), oracle.embed(qcodes, tab), 1e300, pred=1, cap=n * q + 10)
+    assert hits_as_tuples(got, False) == hits_as_tuples(want, False)
+    h.close()
