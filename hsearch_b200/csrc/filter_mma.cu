@@ -37,6 +37,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "internal.cuh"
@@ -59,7 +60,7 @@ constexpr int kMmaAccStages = 2;
 constexpr uint32_t kMmaTmemCols = 512;
 constexpr int kMmaMaxStages = 4;     // A stages
 constexpr int kMmaRowRing = 8;       // >= A stages + accumulator stages
-constexpr int kMmaStageCap = 256;    // survivors staged per epilogue warp (>= one 8-column scan of 32 rows)
+constexpr int kMmaQueueCap = 8;      // survivors queued per epilogue lane before the warp flushes
 constexpr int kMmaAGroupBytes = 2048;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,6 +86,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// one arrival per warp: every lane's prior work is ordered before it by the warp barrier
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -150,14 +156,46 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
-// Append a warp's staged survivors to the global list: one atomic per flush.
-__device__ __noinline__ uint32_t mma_flush(const Survivor *stage, uint32_t n, Survivor *surv, unsigned long long cap,
+// Append the pairs of mask hm (bit j = column q0 + j passed) to the calling lane's queue;
+// a full queue overflows straight into the global list.  Returns the new queue length.
+__device__ __noinline__ uint32_t mma_push_hits(uint32_t hm, uint32_t q0, uint32_t table, uint32_t pos, Survivor *queue,
+                                               uint32_t lc, Survivor *surv, unsigned long long cap,
+                                               unsigned long long *count) {
+  while (hm) {
+    const int j = __ffs(hm) - 1;
+    hm &= hm - 1;
+    Survivor sv;
+    sv.query = q0 + (uint32_t)j;  // index into the query list; the exact stage resolves it
+    sv.table = table;
+    sv.pos = pos;
+    sv.pad = 1;
+    if (lc < (uint32_t)kMmaQueueCap) {
+      queue[lc++] = sv;
+    } else {
+      const unsigned long long idx = atomicAdd(count, 1ull);
+      if (idx < cap) surv[idx] = sv;
+    }
+  }
+  return lc;
+}
+
+// Empty the 32 lane queues of a warp into the global survivor list: one atomic per flush.
+// queues: [32][kMmaQueueCap]; n = entries in the calling lane's queue.  Returns 0.
+__device__ __noinline__ uint32_t mma_flush(const Survivor *queues, uint32_t n, Survivor *surv, unsigned long long cap,
                                            unsigned long long *count, int lane) {
+  uint32_t incl = n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(count, (unsigned long long)n);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  for (uint32_t i = lane; i < n; i += 32)
-    if (base + i < cap) surv[base + i] = stage[i];
+  if (lane == 31) base = atomicAdd(count, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 31) + (incl - n);
+  const Survivor *mine = queues + (size_t)lane * kMmaQueueCap;
+  for (uint32_t i = 0; i < n; ++i)
+    if (base + i < cap) surv[base + i] = mine[i];
   __syncwarp();
   return 0;
 }
@@ -185,7 +223,7 @@ struct MmaArgs {
   uint64_t npad;
   int len, kp, nstages, qmax, cring;
   float thr, beta;
-  uint32_t debug;             // bring-up switches (HS_MMA_DEBUG): 1 no survivor scan, 2 no A build, 4 no MMA
+  uint32_t debug;             // bring-up switches (HS_MMA_DEBUG): 1 no survivor scan, 2 no A build, 4 no MMA, 8 no code copies
   const uint4 *tab16;         // [20] FP16 embedding rows (8 halves each)
   const float *nx32;          // [20] squared row norms, rounded down
   Survivor *surv;
@@ -205,16 +243,17 @@ struct MmaShared {
   uint4 tab16[HS_AA];
   float nx32[HS_AA];
   float rowthr[kMmaRowRing][kMmaM];
-  Survivor stage[kMmaEpiWarps][kMmaStageCap];
+  Survivor queue[kMmaEpiWarps][32][kMmaQueueCap];
 };
 
 // Every role walks the same sequence of units, published by the scheduler lane
 // through a small ring: returns the next unit index, or >= nunits at the end.
-__device__ __forceinline__ uint32_t mma_next_unit(MmaShared &sh, uint32_t k) {
+__device__ __forceinline__ uint32_t mma_next_unit(MmaShared &sh, uint32_t k, int lane, bool whole_warp) {
   const uint32_t slot = k % kMmaUnitRing;
   mbar_wait(smem_addr(&sh.u_full[slot]), (k / kMmaUnitRing) & 1u);
   const uint32_t u = sh.uring[slot];
-  mbar_arrive(smem_addr(&sh.u_empty[slot]));
+  if (whole_warp) mbar_arrive_warp(smem_addr(&sh.u_empty[slot]), lane);
+  else mbar_arrive(smem_addr(&sh.u_empty[slot]));
   return u;
 }
 
@@ -237,21 +276,21 @@ filter_mma_kernel(MmaArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < kMmaMaxStages; ++s) {
-      mbar_init(smem_addr(&sh.a_full[s]), kMmaProdWarps * 32);
+      mbar_init(smem_addr(&sh.a_full[s]), kMmaProdWarps);
       mbar_init(smem_addr(&sh.a_empty[s]), 1);
     }
     for (int s = 0; s < kMmaAccStages; ++s) {
       mbar_init(smem_addr(&sh.t_full[s]), 1);
-      mbar_init(smem_addr(&sh.t_empty[s]), kMmaEpiWarps * 32);
+      mbar_init(smem_addr(&sh.t_empty[s]), kMmaEpiWarps);
     }
-    mbar_init(smem_addr(&sh.b_full), kMmaProdWarps * 32);
+    mbar_init(smem_addr(&sh.b_full), kMmaProdWarps);
     for (int s = 0; s < kMmaUnitRing; ++s) {
       mbar_init(smem_addr(&sh.u_full[s]), 1);
-      mbar_init(smem_addr(&sh.u_empty[s]), (kMmaEpiWarps + kMmaProdWarps) * 32 + 1);
+      mbar_init(smem_addr(&sh.u_empty[s]), kMmaEpiWarps + kMmaProdWarps + 1);
     }
     for (int s = 0; s < kMmaMaxCodeRing; ++s) {
       mbar_init(smem_addr(&sh.c_full[s]), 1);
-      mbar_init(smem_addr(&sh.c_empty[s]), kMmaProdWarps * 32);
+      mbar_init(smem_addr(&sh.c_empty[s]), kMmaProdWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -326,7 +365,7 @@ filter_mma_kernel(MmaArgs a) {
     uint32_t pt = 0;                       // tiles produced so far (all units)
     uint32_t prev_item = 0xffffffffu;
     for (uint32_t k = 0;; ++k) {
-      const uint32_t u = mma_next_unit(sh, k);
+      const uint32_t u = mma_next_unit(sh, k, lane, true);
       if (u >= nunits) break;
       const MmaUnit un = a.units[u];
       const MmaItem it = a.items[un.item];
@@ -335,20 +374,26 @@ filter_mma_kernel(MmaArgs a) {
         if (pt > 0) mbar_wait(smem_addr(&sh.a_empty[(pt - 1) % S]), ((pt - 1) / S) & 1u);
         const uint32_t nq = it.q_end - it.q_begin;
         const uint32_t nqp = (nq + 15u) & ~15u;
-        const int total = ngrp * (int)nqp;
-        for (int i = r; i < total; i += kMmaProdWarps * 32) {
-          const int g = i / (int)nqp, q = i - g * (int)nqp;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if ((uint32_t)q < nq) {
-            const uint32_t row = a.qlist[it.q_begin + q] - a.tq_base;
-            v = __ldg(reinterpret_cast<const uint4 *>(a.qb16 + (size_t)row * kp + (g << 3)));
-          } else if (g == len) {
-            v.x = 0x0000FB00u;  // c = -57344: a padding column never passes
+        for (uint32_t q = (uint32_t)r; q < nqp; q += kMmaProdWarps * 32) {
+          unsigned char *drow = sB + (q >> 3) * 128 + (q & 7) * 16;
+          if (q < nq) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.qb16 + (size_t)(a.qlist[it.q_begin + q] - a.tq_base) * kp);
+            for (int g0 = 0; g0 < ngrp; g0 += 6) {  // six 16-byte loads in flight per step
+              uint4 v[6];
+#pragma unroll
+              for (int j = 0; j < 6; ++j)
+                if (g0 + j < ngrp) v[j] = __ldg(src + g0 + j);
+#pragma unroll
+              for (int j = 0; j < 6; ++j)
+                if (g0 + j < ngrp) *reinterpret_cast<uint4 *>(drow + (size_t)(g0 + j) * b_lbo) = v[j];
+            }
+          } else {
+            for (int g = 0; g < ngrp; ++g)  // padding column: c = -57344 never passes
+              *reinterpret_cast<uint4 *>(drow + (size_t)g * b_lbo) = make_uint4(g == len ? 0x0000FB00u : 0u, 0u, 0u, 0u);
           }
-          *reinterpret_cast<uint4 *>(sB + (size_t)g * b_lbo + (q >> 3) * 128 + (q & 7) * 16) = v;
         }
         fence_async_shared();
-        mbar_arrive(smem_addr(&sh.b_full));
+        mbar_arrive_warp(smem_addr(&sh.b_full), lane);
         prev_item = un.item;
       }
       const uint32_t base = un.m_begin & ~15u;
@@ -364,18 +409,16 @@ filter_mma_kernel(MmaArgs a) {
 #pragma unroll
         for (int p = 0; p < HS_MAX_LEN; ++p)
           if (p < len) code[p] = crow[p * 128];
-        mbar_arrive(smem_addr(&sh.c_empty[d]));
+        mbar_arrive_warp(smem_addr(&sh.c_empty[d]), lane);
         mbar_wait(smem_addr(&sh.a_empty[s]), ((pt / S) & 1u) ^ 1u);
         unsigned char *dst = sA + (size_t)s * a_stage_bytes + row_off;
         float nx = 0.f;
-        if (!(a.debug & 2u)) {
 #pragma unroll
-          for (int p = 0; p < HS_MAX_LEN; ++p) {
-            if (p < len) {
-              const int c = min((int)code[p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
-              *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = sh.tab16[c];
-              nx += sh.nx32[c];
-            }
+        for (int p = 0; p < HS_MAX_LEN; ++p) {
+          if (p < len) {
+            const int c = min((int)code[p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
+            *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = sh.tab16[c];
+            nx += sh.nx32[c];
           }
         }
         // rowthr = ((1 - beta) nx - thr) / 2, rounded down; +inf rows never pass
@@ -384,7 +427,7 @@ filter_mma_kernel(MmaArgs a) {
         rt -= (nx + a.thr) * 2.4e-7f + 1e-6f;
         sh.rowthr[pt % kMmaRowRing][r] = valid ? rt : __int_as_float(0x7f800000);
         fence_async_shared();
-        mbar_arrive(smem_addr(&sh.a_full[s]));
+        mbar_arrive_warp(smem_addr(&sh.a_full[s]), lane);
       }
     }
   } else if (warp == kMmaIssueWarp) {
@@ -395,7 +438,7 @@ filter_mma_kernel(MmaArgs a) {
       const uint32_t sA_u32 = smem_addr(sA), sB_u32 = smem_addr(sB);
       const int ksteps = kp >> 4;
       for (uint32_t k = 0;; ++k) {
-        const uint32_t u = mma_next_unit(sh, k);
+        const uint32_t u = mma_next_unit(sh, k, lane, false);
         if (u >= nunits) break;
         const MmaUnit un = a.units[u];
         const MmaItem it = a.items[un.item];
@@ -421,7 +464,7 @@ filter_mma_kernel(MmaArgs a) {
             const uint32_t d_tmem = tmem_base + as * kMmaN;
             const uint32_t a0 = sA_u32 + s * a_stage_bytes;
             const uint32_t b0 = sB_u32 + (g * kMmaN >> 3) * 128u;
-            for (int kk = 0; kk < ksteps && !(a.debug & 4u); ++kk) {
+            for (int kk = 0; kk < ksteps; ++kk) {
               const uint64_t ad = mma_desc(a0 + (uint32_t)kk * 2u * kMmaAGroupBytes, kMmaAGroupBytes, 128u);
               const uint64_t bd = mma_desc(b0 + (uint32_t)kk * 2u * b_lbo, b_lbo, 128u);
               mma_f16_ss(d_tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
@@ -435,13 +478,18 @@ filter_mma_kernel(MmaArgs a) {
     __syncwarp();
   } else {
     // ============================ epilogue =============================================
+    // Lane = member row.  Per 16 accumulator columns: four 4-column maxima and their
+    // maximum (3-input max); a lane whose maximum reaches its row threshold narrows down
+    // through the 4-column maxima and appends the passing pairs to its own small queue in
+    // shared memory (no cross-lane traffic); the queues of a warp are emptied together with
+    // one global atomic when any of them is half full.
     const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;
-    Survivor *stage = sh.stage[warp];
-    uint32_t wcount = 0;  // warp-uniform
+    Survivor *queue = &sh.queue[warp][lane][0];
+    uint32_t lc = 0;  // entries in my queue
     uint32_t et = 0, eg = 0;
     for (uint32_t k = 0;; ++k) {
-      const uint32_t u = mma_next_unit(sh, k);
+      const uint32_t u = mma_next_unit(sh, k, lane, true);
       if (u >= nunits) break;
       const MmaUnit un = a.units[u];
       const MmaItem it = a.items[un.item];
@@ -458,65 +506,42 @@ filter_mma_kernel(MmaArgs a) {
           tc_after();
           if (g == 0) rt = sh.rowthr[et % kMmaRowRing][row];
           const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
-          const uint32_t ngp = (ng + 15u) & ~15u;
-          // 32-column chunks (the MMA wrote ngp = ng rounded up to 16 columns; a last half
-          // chunk reads 16 stale columns, masked below); this warp takes c = half, half+2, ...
-          const uint32_t nchunks = (ng + 31u) >> 5;
+          const uint32_t ngp = (ng + 15u) & ~15u;  // columns the MMA wrote
+          // 32-column chunks; a last half chunk loads 16 columns only.  This warp takes
+          // chunks c = half, half + 2, ...; loads run one chunk ahead of the scan.
+          const uint32_t nchunks = (ngp + 31u) >> 5;
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMmaN;
-          const uint32_t qbase = it.q_begin + g * kMmaN;  // index into qlist of column 0
+          const uint32_t qbase = it.q_begin + g * kMmaN;  // index into the query list of column 0
           uint32_t v0[32], v1[32];
-          // survivor scan of one 32-column chunk held in registers
-          auto process = [&](const uint32_t(&vv)[32], uint32_t c) {
+          // 16 accumulators vw[OFF .. OFF+15] = columns col0 .. col0+15 of the group
+          auto scan16 = [&](const uint32_t(&vw)[32], auto off, uint32_t col0) {
+            constexpr int OFF = decltype(off)::value;
+            float vf[16];
 #pragma unroll
-            for (int h8 = 0; h8 < 4; ++h8) {
-              const uint32_t qi0 = c * 32u + (uint32_t)(h8 * 8);  // first column of the 8 inside the group
-              if (qi0 >= ng) break;                               // warp-uniform: only stale / padding columns left
-              float f[8];
+            for (int i = 0; i < 16; ++i) vf[i] = __uint_as_float(vw[OFF + i]);
+            float m = fmax3(vf[0], vf[1], vf[2]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(vv[h8 * 8 + j]);
-              float m = fmax3(f[0], f[1], f[2]);
-              m = fmax3(m, f[3], f[4]);
-              m = fmax3(m, f[5], f[6]);
-              m = fmaxf(m, f[7]);
-              if (__any_sync(0xffffffffu, m >= rt) && !(a.debug & 1u)) {  // warp-uniform, rare
-                uint32_t hm = 0;
+            for (int i = 3; i < 15; i += 2) m = fmax3(m, vf[i], vf[i + 1]);
+            m = fmaxf(m, vf[15]);
+            if (m >= rt) {  // rare, divergent: only the lanes with a passing pair work
+              uint32_t hm = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) hm |= (f[j] >= rt ? 1u : 0u) << j;
-                const int nv = (int)ng - (int)qi0;  // valid columns (padding columns never pass anyway)
-                if (nv < 8) hm &= (1u << nv) - 1u;
-                const uint32_t cnt = __popc(hm);
-                uint32_t incl = cnt;
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                  const uint32_t tt = __shfl_up_sync(0xffffffffu, incl, dd);
-                  if (lane >= dd) incl += tt;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total) {
-                  if (wcount + total > (uint32_t)kMmaStageCap)
-                    wcount = mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
-                  uint32_t slot = wcount + incl - cnt;
-                  while (hm) {
-                    const int j = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    Survivor sv;
-                    sv.query = qbase + qi0 + (uint32_t)j;  // index into the query list; the exact stage resolves it
-                    sv.table = it.table;
-                    sv.pos = pos;
-                    sv.pad = 1;
-                    stage[slot++] = sv;
-                  }
-                  __syncwarp();
-                  wcount += total;
-                }
-              }
+              for (int i = 0; i < 16; ++i) hm |= (vf[i] >= rt ? 1u : 0u) << i;
+              const uint32_t nv = ng - col0;  // valid columns from col0 on (col0 < ng here)
+              if (nv < 16u) hm &= (1u << nv) - 1u;
+              lc = mma_push_hits(hm, qbase + col0, it.table, pos, queue, lc, a.surv, a.surv_cap, a.surv_count);
             }
           };
-          auto issue = [&](uint32_t (&vv)[32], uint32_t c) {
-            if (c * 32u + 16u < ngp) tmem_ld32_issue(taddr + c * 32u, vv);
-            else tmem_ld16_issue(taddr + c * 32u, reinterpret_cast<uint32_t(&)[16]>(vv));  // last 16 written columns
+          auto process = [&](const uint32_t(&vv)[32], uint32_t c) {
+            scan16(vv, std::integral_constant<int, 0>{}, c * 32u);
+            if (c * 32u + 16u < ngp) scan16(vv, std::integral_constant<int, 16>{}, c * 32u + 16u);
+            if (__any_sync(0xffffffffu, lc >= (uint32_t)(kMmaQueueCap / 2)))
+              lc = mma_flush(&sh.queue[warp][0][0], lc, a.surv, a.surv_cap, a.surv_count, lane);
           };
-          // loads run one chunk ahead of the scan
+          auto issue = [&](uint32_t(&vv)[32], uint32_t c) {
+            if (c * 32u + 16u < ngp) tmem_ld32_issue(taddr + c * 32u, vv);
+            else tmem_ld16_issue(taddr + c * 32u, reinterpret_cast<uint32_t(&)[16]>(vv));
+          };
           uint32_t c = (uint32_t)half;
           if (c < nchunks) issue(v0, c);
           for (; c < nchunks; c += 4) {
@@ -525,7 +550,7 @@ filter_mma_kernel(MmaArgs a) {
               issue(v1, c + 2);
             } else {  // all of this warp's reads of the stage are in registers: release it
               tc_before();
-              mbar_arrive(smem_addr(&sh.t_empty[as]));
+              mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
             }
             process(v0, c);
             if (c + 2 < nchunks) {
@@ -534,20 +559,20 @@ filter_mma_kernel(MmaArgs a) {
                 issue(v0, c + 4);
               } else {
                 tc_before();
-                mbar_arrive(smem_addr(&sh.t_empty[as]));
+                mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
               }
               process(v1, c + 2);
             }
           }
           if ((uint32_t)half >= nchunks) {  // no chunk for this warp in this group: still release the stage
             tc_before();
-            mbar_arrive(smem_addr(&sh.t_empty[as]));
+            mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
           }
         }
       }
     }
     __syncwarp();
-    if (wcount) mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
+    if (__any_sync(0xffffffffu, lc > 0)) mma_flush(&sh.queue[warp][0][0], lc, a.surv, a.surv_cap, a.surv_count, lane);
   }
 
   tc_before();
