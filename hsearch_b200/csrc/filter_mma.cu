@@ -60,7 +60,7 @@ constexpr int kMmaAccStages = 2;
 constexpr uint32_t kMmaTmemCols = 512;
 constexpr int kMmaMaxStages = 4;     // A stages
 constexpr int kMmaRowRing = 8;       // >= A stages + accumulator stages
-constexpr int kMmaQueueCap = 8;      // survivors queued per epilogue lane before the warp flushes
+constexpr int kMmaStageCap = 128;    // survivors staged per epilogue warp between flushes
 constexpr int kMmaAGroupBytes = 2048;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,48 +156,51 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
-// Append the pairs of mask hm (bit j = column q0 + j passed) to the calling lane's queue;
-// a full queue overflows straight into the global list.  Returns the new queue length.
-__device__ __noinline__ uint32_t mma_push_hits(uint32_t hm, uint32_t q0, uint32_t table, uint32_t pos, Survivor *queue,
-                                               uint32_t lc, Survivor *surv, unsigned long long cap,
-                                               unsigned long long *count) {
-  while (hm) {
-    const int j = __ffs(hm) - 1;
-    hm &= hm - 1;
-    Survivor sv;
-    sv.query = q0 + (uint32_t)j;  // index into the query list; the exact stage resolves it
-    sv.table = table;
-    sv.pos = pos;
-    sv.pad = 1;
-    if (lc < (uint32_t)kMmaQueueCap) {
-      queue[lc++] = sv;
-    } else {
-      const unsigned long long idx = atomicAdd(count, 1ull);
-      if (idx < cap) surv[idx] = sv;
-    }
-  }
-  return lc;
-}
-
-// Empty the 32 lane queues of a warp into the global survivor list: one atomic per flush.
-// queues: [32][kMmaQueueCap]; n = entries in the calling lane's queue.  Returns 0.
-__device__ __noinline__ uint32_t mma_flush(const Survivor *queues, uint32_t n, Survivor *surv, unsigned long long cap,
+// Append a warp's staged survivors to the global list: one atomic per flush.  Returns 0.
+__device__ __noinline__ uint32_t mma_flush(const Survivor *stage, uint32_t n, Survivor *surv, unsigned long long cap,
                                            unsigned long long *count, int lane) {
-  uint32_t incl = n;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += t;
-  }
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   unsigned long long base = 0;
-  if (lane == 31) base = atomicAdd(count, (unsigned long long)total);
-  base = __shfl_sync(0xffffffffu, base, 31) + (incl - n);
-  const Survivor *mine = queues + (size_t)lane * kMmaQueueCap;
-  for (uint32_t i = 0; i < n; ++i)
-    if (base + i < cap) surv[base + i] = mine[i];
+  if (lane == 0) base = atomicAdd(count, (unsigned long long)n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (uint32_t i = lane; i < n; i += 32)
+    if (base + i < cap) surv[base + i] = stage[i];
   __syncwarp();
   return 0;
+}
+
+// Rare path of the epilogue, executed by the whole warp: `lanes` = rows whose 16-column
+// maximum reached their threshold; each of them has put its 16 accumulators into its
+// scratch slot.  16 lanes test one column each; passing pairs are appended to the warp's
+// staging list.  Returns the new staged count.
+__device__ __noinline__ uint32_t mma_collect(uint32_t lanes, float rt, uint32_t pos, uint32_t qidx0, uint32_t nvalid,
+                                             uint32_t table, const float *scratch, Survivor *stage, uint32_t wcount,
+                                             Survivor *surv, unsigned long long cap, unsigned long long *count,
+                                             int lane) {
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  while (lanes) {
+    const int src = __ffs(lanes) - 1;
+    lanes &= lanes - 1;
+    const float x = scratch[src * 16 + (lane & 15)];
+    const float rt_s = __shfl_sync(0xffffffffu, rt, src);
+    const uint32_t pos_s = __shfl_sync(0xffffffffu, pos, src);
+    const bool p = lane < 16 && (uint32_t)lane < nvalid && x >= rt_s;
+    const uint32_t mask = __ballot_sync(0xffffffffu, p);
+    if (p) {
+      Survivor sv;
+      sv.query = qidx0 + (uint32_t)lane;  // index into the query list; the exact stage resolves it
+      sv.table = table;
+      sv.pos = pos_s;
+      sv.pad = 1;
+      stage[wcount + __popc(mask & lt_mask)] = sv;
+    }
+    wcount += __popc(mask);
+    if (wcount > (uint32_t)(kMmaStageCap - 16)) {
+      __syncwarp();
+      wcount = mma_flush(stage, wcount, surv, cap, count, lane);
+    }
+  }
+  __syncwarp();  // scratch may be rewritten by the caller
+  return wcount;
 }
 
 struct MmaItem {
@@ -243,7 +246,8 @@ struct MmaShared {
   uint4 tab16[HS_AA];
   float nx32[HS_AA];
   float rowthr[kMmaRowRing][kMmaM];
-  Survivor queue[kMmaEpiWarps][32][kMmaQueueCap];
+  Survivor stage[kMmaEpiWarps][kMmaStageCap];
+  float scratch[kMmaEpiWarps][32][16];  // per lane: the 16 accumulators of a row that reached its threshold
 };
 
 // Every role walks the same sequence of units, published by the scheduler lane
@@ -478,15 +482,14 @@ filter_mma_kernel(MmaArgs a) {
     __syncwarp();
   } else {
     // ============================ epilogue =============================================
-    // Lane = member row.  Per 16 accumulator columns: four 4-column maxima and their
-    // maximum (3-input max); a lane whose maximum reaches its row threshold narrows down
-    // through the 4-column maxima and appends the passing pairs to its own small queue in
-    // shared memory (no cross-lane traffic); the queues of a warp are emptied together with
-    // one global atomic when any of them is half full.
+    // Lane = member row.  Per 16 accumulator columns: their maximum (3-input max) against
+    // the row threshold and one warp vote; the rare rows that reach it are resolved by the
+    // whole warp (mma_collect) and staged per warp, one global atomic per flush.
     const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;
-    Survivor *queue = &sh.queue[warp][lane][0];
-    uint32_t lc = 0;  // entries in my queue
+    Survivor *stage = sh.stage[warp];
+    float *scratch = &sh.scratch[warp][0][0];
+    uint32_t wcount = 0;  // staged survivors (warp-uniform)
     uint32_t et = 0, eg = 0;
     for (uint32_t k = 0;; ++k) {
       const uint32_t u = mma_next_unit(sh, k, lane, true);
@@ -523,20 +526,24 @@ filter_mma_kernel(MmaArgs a) {
 #pragma unroll
             for (int i = 3; i < 15; i += 2) m = fmax3(m, vf[i], vf[i + 1]);
             m = fmaxf(m, vf[15]);
-            if (m >= rt) {  // rare, divergent: only the lanes with a passing pair work
-              uint32_t hm = 0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) hm |= (vf[i] >= rt ? 1u : 0u) << i;
-              const uint32_t nv = ng - col0;  // valid columns from col0 on (col0 < ng here)
-              if (nv < 16u) hm &= (1u << nv) - 1u;
-              lc = mma_push_hits(hm, qbase + col0, it.table, pos, queue, lc, a.surv, a.surv_cap, a.surv_count);
+            const bool reach = m >= rt;
+            const uint32_t lanes = __ballot_sync(0xffffffffu, reach);
+            if (lanes) {  // rare, warp-uniform
+              if (reach) {
+                float4 *d = reinterpret_cast<float4 *>(scratch + lane * 16);
+                d[0] = make_float4(vf[0], vf[1], vf[2], vf[3]);
+                d[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
+                d[2] = make_float4(vf[8], vf[9], vf[10], vf[11]);
+                d[3] = make_float4(vf[12], vf[13], vf[14], vf[15]);
+              }
+              __syncwarp();
+              wcount = mma_collect(lanes, rt, pos, qbase + col0, ng - col0, it.table, scratch, stage, wcount, a.surv,
+                                   a.surv_cap, a.surv_count, lane);
             }
           };
           auto process = [&](const uint32_t(&vv)[32], uint32_t c) {
             scan16(vv, std::integral_constant<int, 0>{}, c * 32u);
             if (c * 32u + 16u < ngp) scan16(vv, std::integral_constant<int, 16>{}, c * 32u + 16u);
-            if (__any_sync(0xffffffffu, lc >= (uint32_t)(kMmaQueueCap / 2)))
-              lc = mma_flush(&sh.queue[warp][0][0], lc, a.surv, a.surv_cap, a.surv_count, lane);
           };
           auto issue = [&](uint32_t(&vv)[32], uint32_t c) {
             if (c * 32u + 16u < ngp) tmem_ld32_issue(taddr + c * 32u, vv);
@@ -572,7 +579,7 @@ filter_mma_kernel(MmaArgs a) {
       }
     }
     __syncwarp();
-    if (__any_sync(0xffffffffu, lc > 0)) mma_flush(&sh.queue[warp][0][0], lc, a.surv, a.surv_cap, a.surv_count, lane);
+    if (wcount) mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
   }
 
   tc_before();
