@@ -45,12 +45,12 @@
 
 namespace hs {
 
-constexpr int kMmaEpiWarps = 8;
+constexpr int kMmaEpiWarps = 16;     // 4 per TMEM lane quadrant
 constexpr int kMmaProdWarps = 4;
-constexpr int kMmaThreads = (kMmaEpiWarps + kMmaProdWarps + 2) * 32;  // 448
-constexpr int kMmaProdThread0 = kMmaEpiWarps * 32;                    // 256
-constexpr int kMmaIssueWarp = kMmaEpiWarps + kMmaProdWarps;           // 12
-constexpr int kMmaLoadWarp = kMmaIssueWarp + 1;                       // 13: unit scheduler + code loader
+constexpr int kMmaThreads = (kMmaEpiWarps + kMmaProdWarps + 2) * 32;  // 704
+constexpr int kMmaProdThread0 = kMmaEpiWarps * 32;                    // 512
+constexpr int kMmaIssueWarp = kMmaEpiWarps + kMmaProdWarps;           // 20
+constexpr int kMmaLoadWarp = kMmaIssueWarp + 1;                       // 21: unit scheduler + code loader
 constexpr int kMmaUnitRing = 4;      // units published ahead by the scheduler
 constexpr int kMmaUnitBatch = 4;     // consecutive units taken per atomic (keeps B resident)
 constexpr int kMmaMaxCodeRing = 8;   // tiles of residue codes in flight (bulk async copies)
@@ -60,7 +60,8 @@ constexpr int kMmaAccStages = 2;
 constexpr uint32_t kMmaTmemCols = 512;
 constexpr int kMmaMaxStages = 4;     // A stages
 constexpr int kMmaRowRing = 8;       // >= A stages + accumulator stages
-constexpr int kMmaStageCap = 128;    // survivors staged per epilogue warp between flushes
+constexpr int kMmaStageCap = 96;     // survivors staged per epilogue warp between flushes
+constexpr int kMmaSlots = 4;         // rows resolved per round of the rare path
 constexpr int kMmaAGroupBytes = 2048;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,41 +169,6 @@ __device__ __noinline__ uint32_t mma_flush(const Survivor *stage, uint32_t n, Su
   return 0;
 }
 
-// Rare path of the epilogue, executed by the whole warp: `lanes` = rows whose 16-column
-// maximum reached their threshold; each of them has put its 16 accumulators into its
-// scratch slot.  16 lanes test one column each; passing pairs are appended to the warp's
-// staging list.  Returns the new staged count.
-__device__ __noinline__ uint32_t mma_collect(uint32_t lanes, float rt, uint32_t pos, uint32_t qidx0, uint32_t nvalid,
-                                             uint32_t table, const float *scratch, Survivor *stage, uint32_t wcount,
-                                             Survivor *surv, unsigned long long cap, unsigned long long *count,
-                                             int lane) {
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  while (lanes) {
-    const int src = __ffs(lanes) - 1;
-    lanes &= lanes - 1;
-    const float x = scratch[src * 16 + (lane & 15)];
-    const float rt_s = __shfl_sync(0xffffffffu, rt, src);
-    const uint32_t pos_s = __shfl_sync(0xffffffffu, pos, src);
-    const bool p = lane < 16 && (uint32_t)lane < nvalid && x >= rt_s;
-    const uint32_t mask = __ballot_sync(0xffffffffu, p);
-    if (p) {
-      Survivor sv;
-      sv.query = qidx0 + (uint32_t)lane;  // index into the query list; the exact stage resolves it
-      sv.table = table;
-      sv.pos = pos_s;
-      sv.pad = 1;
-      stage[wcount + __popc(mask & lt_mask)] = sv;
-    }
-    wcount += __popc(mask);
-    if (wcount > (uint32_t)(kMmaStageCap - 16)) {
-      __syncwarp();
-      wcount = mma_flush(stage, wcount, surv, cap, count, lane);
-    }
-  }
-  __syncwarp();  // scratch may be rewritten by the caller
-  return wcount;
-}
-
 struct MmaItem {
   uint32_t table;
   uint32_t q_begin, q_end;  // range of qlist
@@ -234,6 +200,14 @@ struct MmaArgs {
   unsigned long long *surv_count;
 };
 
+// One row of 16 accumulators handed to the warp for resolution.
+struct __align__(16) MmaSlot {
+  float v[16];
+  float rt;
+  uint32_t pos;
+  uint32_t pad[2];
+};
+
 struct MmaShared {
   uint64_t a_full[kMmaMaxStages], a_empty[kMmaMaxStages];
   uint64_t t_full[kMmaAccStages], t_empty[kMmaAccStages];
@@ -247,7 +221,7 @@ struct MmaShared {
   float nx32[HS_AA];
   float rowthr[kMmaRowRing][kMmaM];
   Survivor stage[kMmaEpiWarps][kMmaStageCap];
-  float scratch[kMmaEpiWarps][32][16];  // per lane: the 16 accumulators of a row that reached its threshold
+  MmaSlot slot[kMmaEpiWarps][kMmaSlots];  // rows that reached their threshold, being resolved
 };
 
 // Every role walks the same sequence of units, published by the scheduler lane
@@ -263,6 +237,8 @@ __device__ __forceinline__ uint32_t mma_next_unit(MmaShared &sh, uint32_t k, int
 
 // Survivors carry the index of their query in the query list (pad = 1); the exact stage
 // resolves it and, for all-pairs runs, keeps only pairs with query id < member position.
+// LENB: compile-time bound of the fragment length (unroll bound of the A-tile producers).
+template <int LENB>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 filter_mma_kernel(MmaArgs a) {
   extern __shared__ __align__(1024) unsigned char mma_smem[];
@@ -409,16 +385,16 @@ filter_mma_kernel(MmaArgs a) {
         // my row's residue codes from the ring the loader fills
         mbar_wait(smem_addr(&sh.c_full[d]), (pt / D) & 1u);
         const unsigned char *crow = sC + (size_t)d * len * 128 + r;
-        uint8_t code[HS_MAX_LEN];
+        uint8_t code[LENB];
 #pragma unroll
-        for (int p = 0; p < HS_MAX_LEN; ++p)
+        for (int p = 0; p < LENB; ++p)
           if (p < len) code[p] = crow[p * 128];
         mbar_arrive_warp(smem_addr(&sh.c_empty[d]), lane);
         mbar_wait(smem_addr(&sh.a_empty[s]), ((pt / S) & 1u) ^ 1u);
         unsigned char *dst = sA + (size_t)s * a_stage_bytes + row_off;
         float nx = 0.f;
 #pragma unroll
-        for (int p = 0; p < HS_MAX_LEN; ++p) {
+        for (int p = 0; p < LENB; ++p) {
           if (p < len) {
             const int c = min((int)code[p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
             *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = sh.tab16[c];
@@ -482,13 +458,17 @@ filter_mma_kernel(MmaArgs a) {
     __syncwarp();
   } else {
     // ============================ epilogue =============================================
-    // Lane = member row.  Per 16 accumulator columns: their maximum (3-input max) against
-    // the row threshold and one warp vote; the rare rows that reach it are resolved by the
-    // whole warp (mma_collect) and staged per warp, one global atomic per flush.
-    const int quad = warp & 3, half = warp >> 2;
+    // Lane = member row; four warps per TMEM lane quadrant share the columns of a stage in
+    // 32-column chunks.  Per 16 accumulator columns: their maximum (tree of 3-input max)
+    // against the row threshold and one warp vote.  The rare rows that reach it hand their
+    // 16 accumulators to the warp through a slot in shared memory; 16 lanes test one column
+    // each (two rows per pass) and passing pairs are staged per warp, one global atomic per
+    // flush.
+    const int quad = warp & 3, sub = warp >> 2;
     const int row = quad * 32 + lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     Survivor *stage = sh.stage[warp];
-    float *scratch = &sh.scratch[warp][0][0];
+    MmaSlot *slots = sh.slot[warp];
     uint32_t wcount = 0;  // staged survivors (warp-uniform)
     uint32_t et = 0, eg = 0;
     for (uint32_t k = 0;; ++k) {
@@ -510,68 +490,76 @@ filter_mma_kernel(MmaArgs a) {
           if (g == 0) rt = sh.rowthr[et % kMmaRowRing][row];
           const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
           const uint32_t ngp = (ng + 15u) & ~15u;  // columns the MMA wrote
-          // 32-column chunks; a last half chunk loads 16 columns only.  This warp takes
-          // chunks c = half, half + 2, ...; loads run one chunk ahead of the scan.
-          const uint32_t nchunks = (ngp + 31u) >> 5;
+          const uint32_t nchunks = (ngp + 31u) >> 5;  // 32-column chunks; a last half chunk loads 16 columns
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMmaN;
           const uint32_t qbase = it.q_begin + g * kMmaN;  // index into the query list of column 0
-          uint32_t v0[32], v1[32];
-          // 16 accumulators vw[OFF .. OFF+15] = columns col0 .. col0+15 of the group
-          auto scan16 = [&](const uint32_t(&vw)[32], auto off, uint32_t col0) {
+          uint32_t vv[32];
+          // 16 accumulators vv[OFF .. OFF+15] = columns col0 .. col0+15 of the group
+          auto scan16 = [&](auto off, uint32_t col0) {
             constexpr int OFF = decltype(off)::value;
             float vf[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) vf[i] = __uint_as_float(vw[OFF + i]);
-            float m = fmax3(vf[0], vf[1], vf[2]);
-#pragma unroll
-            for (int i = 3; i < 15; i += 2) m = fmax3(m, vf[i], vf[i + 1]);
-            m = fmaxf(m, vf[15]);
-            const bool reach = m >= rt;
-            const uint32_t lanes = __ballot_sync(0xffffffffu, reach);
-            if (lanes) {  // rare, warp-uniform
-              if (reach) {
-                float4 *d = reinterpret_cast<float4 *>(scratch + lane * 16);
+            for (int i = 0; i < 16; ++i) vf[i] = __uint_as_float(vv[OFF + i]);
+            const float t0 = fmax3(vf[0], vf[1], vf[2]), t1 = fmax3(vf[3], vf[4], vf[5]), t2 = fmax3(vf[6], vf[7], vf[8]);
+            const float t3 = fmax3(vf[9], vf[10], vf[11]), t4 = fmax3(vf[12], vf[13], vf[14]);
+            const float m = fmaxf(fmax3(t0, t1, t2), fmax3(t3, t4, vf[15]));
+            bool reach = m >= rt;
+            uint32_t lanes = __ballot_sync(0xffffffffu, reach);
+            while (lanes) {  // rare, warp-uniform: rounds of up to kMmaSlots rows
+              const uint32_t rank = __popc(lanes & lt_mask);
+              if (reach && rank < (uint32_t)kMmaSlots) {
+                MmaSlot *sl = slots + rank;
+                float4 *d = reinterpret_cast<float4 *>(sl->v);
                 d[0] = make_float4(vf[0], vf[1], vf[2], vf[3]);
                 d[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
                 d[2] = make_float4(vf[8], vf[9], vf[10], vf[11]);
                 d[3] = make_float4(vf[12], vf[13], vf[14], vf[15]);
+                sl->rt = rt;
+                sl->pos = pos;
+                reach = false;
               }
               __syncwarp();
-              wcount = mma_collect(lanes, rt, pos, qbase + col0, ng - col0, it.table, scratch, stage, wcount, a.surv,
-                                   a.surv_cap, a.surv_count, lane);
+              const uint32_t nrows = min((uint32_t)kMmaSlots, (uint32_t)__popc(lanes));
+              const uint32_t col = (uint32_t)lane & 15u;
+              for (uint32_t r0 = 0; r0 < nrows; r0 += 2) {  // two rows per pass: lanes 0-15 and 16-31
+                const uint32_t si = r0 + ((uint32_t)lane >> 4);
+                const MmaSlot *sl = slots + min(si, (uint32_t)kMmaSlots - 1u);
+                const bool p = si < nrows && col0 + col < ng && sl->v[col] >= sl->rt;
+                const uint32_t mask = __ballot_sync(0xffffffffu, p);
+                if (p) {
+                  Survivor sv;
+                  sv.query = qbase + col0 + col;  // index into the query list; the exact stage resolves it
+                  sv.table = it.table;
+                  sv.pos = sl->pos;
+                  sv.pad = 1;
+                  stage[wcount + __popc(mask & lt_mask)] = sv;
+                }
+                wcount += __popc(mask);
+                if (wcount > (uint32_t)(kMmaStageCap - 32)) {
+                  __syncwarp();
+                  wcount = mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
+                }
+              }
+              __syncwarp();  // the slots are rewritten in the next round / next call
+              lanes = __ballot_sync(0xffffffffu, reach);
             }
           };
-          auto process = [&](const uint32_t(&vv)[32], uint32_t c) {
-            scan16(vv, std::integral_constant<int, 0>{}, c * 32u);
-            if (c * 32u + 16u < ngp) scan16(vv, std::integral_constant<int, 16>{}, c * 32u + 16u);
-          };
-          auto issue = [&](uint32_t(&vv)[32], uint32_t c) {
-            if (c * 32u + 16u < ngp) tmem_ld32_issue(taddr + c * 32u, vv);
+          // this warp takes chunks c = sub, sub + 4, ...
+          uint32_t nmine = 0;
+          for (uint32_t c = (uint32_t)sub; c < nchunks; c += 4) {
+            const bool full = c * 32u + 16u < ngp;
+            if (full) tmem_ld32_issue(taddr + c * 32u, vv);
             else tmem_ld16_issue(taddr + c * 32u, reinterpret_cast<uint32_t(&)[16]>(vv));
-          };
-          uint32_t c = (uint32_t)half;
-          if (c < nchunks) issue(v0, c);
-          for (; c < nchunks; c += 4) {
             tmem_ld_wait();
-            if (c + 2 < nchunks) {
-              issue(v1, c + 2);
-            } else {  // all of this warp's reads of the stage are in registers: release it
+            if (c + 4 >= nchunks) {  // all of this warp's reads of the stage are in registers: release it
               tc_before();
               mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
             }
-            process(v0, c);
-            if (c + 2 < nchunks) {
-              tmem_ld_wait();
-              if (c + 4 < nchunks) {
-                issue(v0, c + 4);
-              } else {
-                tc_before();
-                mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
-              }
-              process(v1, c + 2);
-            }
+            scan16(std::integral_constant<int, 0>{}, c * 32u);
+            if (full) scan16(std::integral_constant<int, 16>{}, c * 32u + 16u);
+            ++nmine;
           }
-          if ((uint32_t)half >= nchunks) {  // no chunk for this warp in this group: still release the stage
+          if (nmine == 0) {  // no chunk for this warp in this group: still release the stage
             tc_before();
             mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
           }
@@ -763,8 +751,19 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
   a.surv_cap = fa.surv_cap;
   a.surv_count = fa.surv_count;
   (void)mode;
-  HS_CUDA(cudaFuncSetAttribute(filter_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-  filter_mma_kernel<<<grid, kMmaThreads, g.smem, ctx->stream>>>(a);
+#define HS_MMA(LB)                                                                                            \
+  do {                                                                                                        \
+    HS_CUDA(cudaFuncSetAttribute(filter_mma_kernel<LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
+    filter_mma_kernel<LB><<<grid, kMmaThreads, g.smem, ctx->stream>>>(a);                                     \
+  } while (0)
+  if (a.len <= 8) HS_MMA(8);
+  else if (a.len <= 10) HS_MMA(10);
+  else if (a.len <= 12) HS_MMA(12);
+  else if (a.len <= 16) HS_MMA(16);
+  else if (a.len <= 20) HS_MMA(20);
+  else if (a.len <= 25) HS_MMA(25);
+  else HS_MMA(32);
+#undef HS_MMA
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;
