@@ -348,8 +348,10 @@ def run_native(a):
                                  "launches": a.L},
         "filter_kernel": {"ms": (acc["ms_filter"] - acc["ms_filter_tc"]) / steps,
                           "bytes": (ncand - ncand_tc) * (length + 4) + nsurv * 16, "launches": 1},
-        "filter_tc_kernel": {"ms": acc["ms_filter_tc"] / steps, "bytes": ncand_tc * (length + 4), "launches": 1,
-                             "flops": 2.0 * ncand_tc * 20 * length},
+        # tensor-core candidate filter (Euclidean metric: filter_mma_kernel): algorithmic flops =
+        # 2 * 8*len per (query, member) pair (the <x_m, q> contraction; DESIGN.md "roofline")
+        "filter_mma_kernel": {"ms": acc["ms_filter_tc"] / steps, "bytes": ncand_tc * (length + 4), "launches": 1,
+                              "flops": 2.0 * ncand_tc * 8 * length},
         "exact_kernel": {"ms": acc["ms_exact"] / steps, "bytes": nsurv * (16 + length + 4) + nh * 24, "launches": 1},
     }
     for k, v in kern.items():
@@ -364,15 +366,26 @@ def run_native(a):
         except (OSError, ValueError):
             traffic = None
     d = kern[dom]
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": d["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launches"]),
-                "avg_launch_ms": d["ms"] / max(1, d["launches"]), "share_of_step": d["share_of_step"],
-                "note": ("filter_kernel: algorithmic bytes = candidates*(len+4) + survivors*16 (SURVEY 8d); the "
-                         "bucket-major tiling reads each member once per tile and reuses it across the bucket's "
-                         "queries from registers, so DRAM traffic is far below the algorithmic figure and the "
-                         "kernel is bound by shared-memory lookups (len per pair), not HBM")
-                if dom == "filter_kernel" else ""}
+    if "flops" in d:
+        # timed inside a long step: the sustained cuBLAS figure is the denominator
+        tpeak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        tsrc = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained; FP16 and BF16 run at the same tensor rate)"
+                if "bf16_tflops_sustained" in peaks else "fallback 1590 TFLOP/s")
+        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": ach / tpeak, "traffic": traffic, "peak_source": tsrc,
+                    "algorithmic_flops_per_launch": d["flops"] / max(1, d["launches"]),
+                    "avg_launch_ms": d["ms"] / max(1, d["launches"]), "share_of_step": d["share_of_step"],
+                    "note": ("tcgen05 FP16 contraction <x_m, q> over every (query, bucket member) pair, 2*8*len flops "
+                             "per pair; the kernel is paced by its TMEM epilogue (one 3-input max per 2 accumulators "
+                             "+ survivor extraction), not by the MMA issue rate; DRAM traffic is ~len bytes per "
+                             "member per item")}
+    else:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": d["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launches"]),
+                    "avg_launch_ms": d["ms"] / max(1, d["launches"]), "share_of_step": d["share_of_step"],
+                    "note": ""}
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -381,7 +394,8 @@ def run_native(a):
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32 filter + f64 exact (hash guard, distances); u64 keys", "data": "synthetic",
+           "dtype": "f16 tensor filter (f32 accumulate) + f64 exact (hash guard, distances); u64 keys",
+           "data": "synthetic",
            "config": {"workload": workload_name(a), "n_db_per_gpu": N, "n_query": Q, "len": length, "K": a.K,
                       "L": a.L, "W": a.W, "R": a.R, "table": "print6", "sharding": f"db-block x{world}",
                       "l2": "inputs (>= 1 GB codes, multi-GB keys) exceed the 126 MB L2; no flush needed"},
