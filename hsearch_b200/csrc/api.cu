@@ -419,6 +419,12 @@ static int stage_queries(hs_ctx *ctx, const QueryInput &in, uint32_t Q) {
     set_error("the integer BLOSUM metric needs residue-code queries");
     return HS_ERR_INVALID;
   }
+  if (ctx->prm.metric == HS_METRIC_EUCLID_FP64) {
+    HS_TRY(ctx->d_qcodes_det.reserve(std::max<size_t>(1, (size_t)Q * len)));
+    HS_TRY(ctx->d_qrow.reserve(std::max<size_t>(1, (size_t)Q)));
+    HS_TRY(launch_detect_query_codes(ctx, ctx->d_q64.as<double>(), Q, ctx->d_qcodes_det.as<uint8_t>(),
+                                     ctx->d_qrow.as<uint8_t>()));
+  }
   return HS_OK;
 }
 
@@ -561,6 +567,10 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   ea.mode = kModeSearch;
   ea.q64 = ctx->prm.metric == HS_METRIC_EUCLID_FP64 ? ctx->d_q64.as<double>() : nullptr;
   ea.qcodes = ctx->have_qcodes ? ctx->d_qcodes.as<uint8_t>() : nullptr;
+  if (ctx->prm.metric == HS_METRIC_EUCLID_FP64) {
+    ea.qcodes = ctx->d_qcodes_det.as<uint8_t>();
+    ea.qrow = ctx->d_qrow.as<uint8_t>();
+  }
   ea.qkeys = ctx->d_qkeys.as<uint64_t>();
   ea.qvalid = ctx->d_qvalid.as<uint8_t>();
   ea.hits = ctx->d_hits.as<hs_hit>();
@@ -657,6 +667,10 @@ static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit
     if (!allpairs) {
       ea.q64 = ctx->prm.metric == HS_METRIC_EUCLID_FP64 ? ctx->d_q64.as<double>() : nullptr;
       ea.qcodes = ctx->have_qcodes ? ctx->d_qcodes.as<uint8_t>() : nullptr;
+      if (ctx->prm.metric == HS_METRIC_EUCLID_FP64) {
+        ea.qcodes = ctx->d_qcodes_det.as<uint8_t>();
+        ea.qrow = ctx->d_qrow.as<uint8_t>();
+      }
     }
     ea.hits = ctx->d_hits.as<hs_hit>();
     ea.hit_cap = dev_cap;
@@ -772,7 +786,7 @@ void hs_destroy(hs_ctx_t *ctx) {
                     &ctx->d_hit_keys[1], &ctx->d_hit_keys[2], &ctx->d_hit_perm, &ctx->d_hits_sorted,
                     &ctx->d_hits_gathered, &ctx->d_misc, &ctx->d_parent, &ctx->d_tabptrs, &ctx->d_residues,
                     &ctx->d_starts, &ctx->d_metric32, &ctx->d_tq16, &ctx->d_work_tc, &ctx->d_qlist_tc, &ctx->d_large,
-                    &ctx->d_tab16, &ctx->d_qb16, &ctx->d_mma_items, &ctx->d_mma_units, &ctx->d_mma_cta, &ctx->d_qlist_mma, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
+                    &ctx->d_qcodes_det, &ctx->d_qrow, &ctx->d_tab16, &ctx->d_qb16, &ctx->d_mma_items, &ctx->d_mma_units, &ctx->d_mma_cta, &ctx->d_qlist_mma, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
                     &ctx->sort.flags, &ctx->sort.block_sums, &ctx->sort.or_and};
   for (DevBuf *b : bufs) b->release();
   for (int w = 0; w < kMaxKeyWords; ++w) {

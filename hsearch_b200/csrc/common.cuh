@@ -139,6 +139,7 @@ struct hs_ctx {
   hs::DevBuf d_qb16, d_mma_items, d_mma_units, d_mma_cta, d_qlist_mma;
   int num_sms = 0;
   bool have_qcodes = false;
+  hs::DevBuf d_qcodes_det, d_qrow;  // codes recovered from dense queries (Euclid exact stage)
   void *h_pinned = nullptr;
   size_t h_pinned_cap = 0;
 

@@ -57,9 +57,12 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
   for (int pos = 0; pos < len; ++pos) {
     const int c = myc[pos];
     const float4 *row = reinterpret_cast<const float4 *>(sT + (pos * HS_AA + c) * P);
+    // the quads of row c are stored rotated by c/2 (setup_projection), so that lanes with
+    // different residues hit different banks when they all want logical quad j
+    const int rot = c >> 1;
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
-      const float4 v = row[j];
+      const float4 v = row[(j + rot) & (NQ - 1)];
       acc[4 * j + 0] += v.x;
       acc[4 * j + 1] += v.y;
       acc[4 * j + 2] += v.z;
@@ -307,7 +310,9 @@ int setup_projection(hs_ctx *ctx, const double *a, const double *b) {
             s += term;
             sa += fabs(term);
           }
-          T32[(((size_t)chunk * len + pos) * HS_AA + c) * P + slot] = (float)s;
+          // quads of a row are rotated by c/2 (bank-conflict avoidance, hash_fast_kernel)
+          const uint32_t pq = ((slot >> 2) + ((uint32_t)c >> 1)) & (ctx->nq - 1);
+          T32[(((size_t)chunk * len + pos) * HS_AA + c) * P + pq * 4 + (slot & 3)] = (float)s;
           amax = std::max(amax, sa);
           tmax = std::max(tmax, fabs(s));
         }

@@ -114,6 +114,41 @@ __global__ void build_tq_int_kernel(const uint8_t *__restrict__ qcodes, uint32_t
   tq[i] = (float)metric[c * HS_AA + qcodes[qp]];
 }
 
+// A dense query whose every 8-vector is bit-identical to a row of the embedding table is
+// an embedded residue string (what protein2datapoints writes): recover its codes so that the
+// exact stage reads 1 byte per position instead of 8 doubles.  qrow[q] = 1 when all positions
+// matched.  The arithmetic downstream is unchanged (same values, same operation order).
+__global__ void detect_query_codes_kernel(const double *__restrict__ q64, uint32_t Q, int len,
+                                          const double *__restrict__ table64, uint8_t *__restrict__ qcodes,
+                                          uint8_t *__restrict__ qrow) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const unsigned long long *tab = reinterpret_cast<const unsigned long long *>(table64);
+  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(q64) + (size_t)q * len * HS_CDIM;
+  bool all = true;
+  for (int p = 0; p < len; ++p) {
+    int found = -1;
+    for (int c = 0; c < HS_AA && found < 0; ++c) {
+      bool same = true;
+#pragma unroll
+      for (int j = 0; j < HS_CDIM; ++j) same = same && (src[p * HS_CDIM + j] == tab[c * HS_CDIM + j]);
+      if (same) found = c;
+    }
+    qcodes[(size_t)q * len + p] = found < 0 ? (uint8_t)0 : (uint8_t)found;
+    all = all && found >= 0;
+  }
+  qrow[q] = all ? 1 : 0;
+}
+
+int launch_detect_query_codes(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint8_t *d_qcodes, uint8_t *d_qrow) {
+  if (Q == 0) return HS_OK;
+  detect_query_codes_kernel<<<(Q + 127) / 128, 128, 0, ctx->stream>>>(d_q64, Q, (int)ctx->prm.len,
+                                                                      ctx->d_table64.as<double>(), d_qcodes, d_qrow);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
 int launch_build_tq_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, float *d_tq) {
   const uint64_t n = (uint64_t)Q * ctx->prm.len * HS_AA;
   if (n == 0) return HS_OK;
@@ -300,6 +335,8 @@ __global__ void __launch_bounds__(128) exact_kernel(ExactArgs a) {
   } else if (a.qcodes) {
     qc = a.qcodes + qid * a.len;
   }
+  // dense query that is an embedded residue string: take its rows from the shared table
+  const bool dense = a.q64 && a.mode != kModeSelfJoin && !(a.qrow && a.qrow[qid] && qc);
 
   double d2;
   bool hit;
@@ -312,7 +349,7 @@ __global__ void __launch_bounds__(128) exact_kernel(ExactArgs a) {
     // PairwiseDistance_square (motif_both_points.cpp:176-183): r = a - b; dis += r * r,
     // strictly sequential, separate multiply and add
     double dis = 0.0;
-    if (a.q64 && a.mode != kModeSelfJoin) {
+    if (dense) {
       const double2 *qp = reinterpret_cast<const double2 *>(a.q64 + qid * a.dim);
       for (int p = 0; p < a.len; ++p) {
         const double2 *row = reinterpret_cast<const double2 *>(s_table + (int)mc[p] * HS_CDIM);

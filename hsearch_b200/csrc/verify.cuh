@@ -52,6 +52,7 @@ struct FilterArgs {
 int launch_probe(hs_ctx *ctx, uint32_t table, const uint64_t *d_qkeys, const uint8_t *d_qvalid, uint32_t Q,
                  uint2 *d_qrange);
 int launch_build_tq_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, float *d_tq);
+int launch_detect_query_codes(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint8_t *d_qcodes, uint8_t *d_qrow);
 int launch_build_tq_int(hs_ctx *ctx, const uint8_t *d_qcodes, uint32_t Q, float *d_tq);
 int launch_filter(hs_ctx *ctx, const FilterArgs &args, uint32_t nblocks, int mode);
 
@@ -107,7 +108,8 @@ struct ExactArgs {
   const double *table64;
   const int32_t *metric_tab;          // [20][20]
   const double *q64;                  // [Q][dim]   (Euclid, search / brute force)
-  const uint8_t *qcodes;              // [Q][len]   (integer metric)
+  const uint8_t *qcodes;              // [Q][len]   (integer metric; Euclid: codes of embedded-string queries)
+  const uint8_t *qrow;                // [Q] 1: the dense query equals the embedding of qcodes (Euclid)
   uint32_t Q;
   const uint64_t *const *keys;        // per table: [KW][N] original-order keys (dedup)
   const uint64_t *qkeys;              // [L][Q][KW]
