@@ -33,7 +33,8 @@ def build(force=False, verbose=False, ptxas_verbose=False):
         o = os.path.join(objdir, src + ".o")
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + ["-x", "cu", "-c", s, "-o", o]
+            extra = os.environ.get("HS_NVCC_EXTRA", "").split()
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas_verbose else []) + ["-x", "cu", "-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -73,11 +73,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin on issue slots
       : "memory");
   return ok != 0;
 }
@@ -169,6 +169,18 @@ __device__ __noinline__ uint32_t mma_flush(const Survivor *stage, uint32_t n, Su
   return 0;
 }
 
+#ifdef HS_MMA_PROF
+#define PROF_DECL(n) unsigned long long n = 0
+#define PROF_T0() const long long _t0 = clock64()
+#define PROF_ADD(n) n += (unsigned long long)(clock64() - _t0)
+#define PROF_OUT(i, n) atomicAdd(a.prof + (i), n)
+#else
+#define PROF_DECL(n)
+#define PROF_T0()
+#define PROF_ADD(n)
+#define PROF_OUT(i, n)
+#endif
+
 struct MmaItem {
   uint32_t table;
   uint32_t q_begin, q_end;  // range of qlist
@@ -192,7 +204,8 @@ struct MmaArgs {
   uint64_t npad;
   int len, kp, nstages, qmax, cring;
   float thr, beta;
-  uint32_t debug;             // bring-up switches (HS_MMA_DEBUG): 1 no survivor scan, 2 no A build, 4 no MMA, 8 no code copies
+  unsigned long long *prof;   // HS_MMA_PROF builds only: per-role cycle counters [16]
+  uint32_t debug;             // HS_MMA_PROF builds only (HS_MMA_DEBUG): 1 = epilogue loads but does not scan
   const uint4 *tab16;         // [20] FP16 embedding rows (8 halves each)
   const float *nx32;          // [20] squared row norms, rounded down
   Survivor *surv;
@@ -344,12 +357,19 @@ filter_mma_kernel(MmaArgs a) {
     const uint32_t row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
     uint32_t pt = 0;                       // tiles produced so far (all units)
     uint32_t prev_item = 0xffffffffu;
+    PROF_DECL(p_wait_c);
+    PROF_DECL(p_wait_a);
+    PROF_DECL(p_bload);
+#ifdef HS_MMA_PROF
+    const long long p_start = clock64();
+#endif
     for (uint32_t k = 0;; ++k) {
       const uint32_t u = mma_next_unit(sh, k, lane, true);
       if (u >= nunits) break;
       const MmaUnit un = a.units[u];
       const MmaItem it = a.items[un.item];
       if (un.item != prev_item) {
+        PROF_T0();
         // every MMA that reads the old B has completed once the latest A stage was released
         if (pt > 0) mbar_wait(smem_addr(&sh.a_empty[(pt - 1) % S]), ((pt - 1) / S) & 1u);
         const uint32_t nq = it.q_end - it.q_begin;
@@ -375,6 +395,7 @@ filter_mma_kernel(MmaArgs a) {
         fence_async_shared();
         mbar_arrive_warp(smem_addr(&sh.b_full), lane);
         prev_item = un.item;
+        PROF_ADD(p_bload);
       }
       const uint32_t base = un.m_begin & ~15u;
       const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
@@ -383,14 +404,22 @@ filter_mma_kernel(MmaArgs a) {
         const uint32_t mypos = base + t * kMmaM + (uint32_t)r;
         const bool valid = mypos >= un.m_begin && mypos < un.m_end;
         // my row's residue codes from the ring the loader fills
-        mbar_wait(smem_addr(&sh.c_full[d]), (pt / D) & 1u);
+        {
+          PROF_T0();
+          mbar_wait(smem_addr(&sh.c_full[d]), (pt / D) & 1u);
+          PROF_ADD(p_wait_c);
+        }
         const unsigned char *crow = sC + (size_t)d * len * 128 + r;
         uint8_t code[LENB];
 #pragma unroll
         for (int p = 0; p < LENB; ++p)
           if (p < len) code[p] = crow[p * 128];
         mbar_arrive_warp(smem_addr(&sh.c_empty[d]), lane);
-        mbar_wait(smem_addr(&sh.a_empty[s]), ((pt / S) & 1u) ^ 1u);
+        {
+          PROF_T0();
+          mbar_wait(smem_addr(&sh.a_empty[s]), ((pt / S) & 1u) ^ 1u);
+          PROF_ADD(p_wait_a);
+        }
         unsigned char *dst = sA + (size_t)s * a_stage_bytes + row_off;
         float nx = 0.f;
 #pragma unroll
@@ -410,11 +439,23 @@ filter_mma_kernel(MmaArgs a) {
         mbar_arrive_warp(smem_addr(&sh.a_full[s]), lane);
       }
     }
+#ifdef HS_MMA_PROF
+    if (tid == kMmaProdThread0) {
+      PROF_OUT(0, (unsigned long long)(clock64() - p_start));
+      PROF_OUT(1, p_wait_c);
+      PROF_OUT(2, p_wait_a);
+      PROF_OUT(3, p_bload);
+    }
+#endif
   } else if (warp == kMmaIssueWarp) {
     // ============================ MMA issuer ===========================================
     if (lane == 0) {
       uint32_t mt = 0, mg = 0, nb = 0;
       uint32_t prev_item = 0xffffffffu;
+      PROF_DECL(m_wait_a);
+      PROF_DECL(m_wait_t);
+      PROF_DECL(m_wait_b);
+      PROF_DECL(m_groups);
       const uint32_t sA_u32 = smem_addr(sA), sB_u32 = smem_addr(sB);
       const int ksteps = kp >> 4;
       for (uint32_t k = 0;; ++k) {
@@ -423,7 +464,11 @@ filter_mma_kernel(MmaArgs a) {
         const MmaUnit un = a.units[u];
         const MmaItem it = a.items[un.item];
         if (un.item != prev_item) {
-          mbar_wait(smem_addr(&sh.b_full), nb & 1u);
+          {
+            PROF_T0();
+            mbar_wait(smem_addr(&sh.b_full), nb & 1u);
+            PROF_ADD(m_wait_b);
+          }
           ++nb;
           prev_item = un.item;
         }
@@ -433,10 +478,21 @@ filter_mma_kernel(MmaArgs a) {
         const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
         for (uint32_t t = 0; t < ntiles; ++t, ++mt) {
           const uint32_t s = mt % S;
-          mbar_wait(smem_addr(&sh.a_full[s]), (mt / S) & 1u);
+          {
+            PROF_T0();
+            mbar_wait(smem_addr(&sh.a_full[s]), (mt / S) & 1u);
+            PROF_ADD(m_wait_a);
+          }
           for (uint32_t g = 0; g < ngroups; ++g, ++mg) {
             const uint32_t as = mg % kMmaAccStages;
-            mbar_wait(smem_addr(&sh.t_empty[as]), ((mg / kMmaAccStages) & 1u) ^ 1u);
+            {
+              PROF_T0();
+              mbar_wait(smem_addr(&sh.t_empty[as]), ((mg / kMmaAccStages) & 1u) ^ 1u);
+              PROF_ADD(m_wait_t);
+            }
+#ifdef HS_MMA_PROF
+            ++m_groups;
+#endif
             tc_after();
             const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
             const uint32_t ngp = (ng + 15u) & ~15u;
@@ -454,6 +510,12 @@ filter_mma_kernel(MmaArgs a) {
           }
         }
       }
+#ifdef HS_MMA_PROF
+      PROF_OUT(4, m_wait_a);
+      PROF_OUT(5, m_wait_t);
+      PROF_OUT(6, m_wait_b);
+      PROF_OUT(7, m_groups);
+#endif
     }
     __syncwarp();
   } else {
@@ -471,11 +533,26 @@ filter_mma_kernel(MmaArgs a) {
     MmaSlot *slots = sh.slot[warp];
     uint32_t wcount = 0;  // staged survivors (warp-uniform)
     uint32_t et = 0, eg = 0;
+    PROF_DECL(e_wait_t);
+    PROF_DECL(e_ld);
+    PROF_DECL(e_rare);
+    PROF_DECL(e_issue);
+    PROF_DECL(e_arrive);
+    PROF_DECL(e_unit);
+#ifdef HS_MMA_PROF
+    const long long e_start = clock64();
+#endif
     for (uint32_t k = 0;; ++k) {
+#ifdef HS_MMA_PROF
+      const long long _u0 = clock64();
+#endif
       const uint32_t u = mma_next_unit(sh, k, lane, true);
       if (u >= nunits) break;
       const MmaUnit un = a.units[u];
       const MmaItem it = a.items[un.item];
+#ifdef HS_MMA_PROF
+      e_unit += (unsigned long long)(clock64() - _u0);
+#endif
       const uint32_t nq = it.q_end - it.q_begin;
       const uint32_t ngroups = (nq + kMmaN - 1) / kMmaN;
       const uint32_t base = un.m_begin & ~15u;
@@ -485,26 +562,37 @@ filter_mma_kernel(MmaArgs a) {
         float rt = 0.f;
         for (uint32_t g = 0; g < ngroups; ++g, ++eg) {
           const uint32_t as = eg % kMmaAccStages;
-          mbar_wait(smem_addr(&sh.t_full[as]), (eg / kMmaAccStages) & 1u);
-          tc_after();
+          {
+            PROF_T0();
+            mbar_wait(smem_addr(&sh.t_full[as]), (eg / kMmaAccStages) & 1u);
+            PROF_ADD(e_wait_t);
+          }
+          {
+            PROF_T0();
+            tc_after();
+            PROF_ADD(e_unit);
+          }
           if (g == 0) rt = sh.rowthr[et % kMmaRowRing][row];
           const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
           const uint32_t ngp = (ng + 15u) & ~15u;  // columns the MMA wrote
-          const uint32_t nchunks = (ngp + 31u) >> 5;  // 32-column chunks; a last half chunk loads 16 columns
+          const uint32_t nchunks = ngp >> 4;  // 16-column chunks; this warp takes c = sub, sub + 4, ...
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMmaN;
           const uint32_t qbase = it.q_begin + g * kMmaN;  // index into the query list of column 0
-          uint32_t vv[32];
-          // 16 accumulators vv[OFF .. OFF+15] = columns col0 .. col0+15 of the group
-          auto scan16 = [&](auto off, uint32_t col0) {
-            constexpr int OFF = decltype(off)::value;
+          uint32_t vv[16];
+          // the 16 accumulators in vv = columns col0 .. col0+15 of the group
+          auto scan16 = [&](uint32_t col0) {
             float vf[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) vf[i] = __uint_as_float(vv[OFF + i]);
+            for (int i = 0; i < 16; ++i) vf[i] = __uint_as_float(vv[i]);
             const float t0 = fmax3(vf[0], vf[1], vf[2]), t1 = fmax3(vf[3], vf[4], vf[5]), t2 = fmax3(vf[6], vf[7], vf[8]);
             const float t3 = fmax3(vf[9], vf[10], vf[11]), t4 = fmax3(vf[12], vf[13], vf[14]);
             const float m = fmaxf(fmax3(t0, t1, t2), fmax3(t3, t4, vf[15]));
             bool reach = m >= rt;
             uint32_t lanes = __ballot_sync(0xffffffffu, reach);
+#ifdef HS_MMA_PROF
+            const long long _r0 = lanes ? clock64() : 0;
+            const bool _had = lanes != 0;
+#endif
             while (lanes) {  // rare, warp-uniform: rounds of up to kMmaSlots rows
               const uint32_t rank = __popc(lanes & lt_mask);
               if (reach && rank < (uint32_t)kMmaSlots) {
@@ -543,20 +631,19 @@ filter_mma_kernel(MmaArgs a) {
               __syncwarp();  // the slots are rewritten in the next round / next call
               lanes = __ballot_sync(0xffffffffu, reach);
             }
+#ifdef HS_MMA_PROF
+            if (_had) e_rare += (unsigned long long)(clock64() - _r0);
+#endif
           };
-          // this warp takes chunks c = sub, sub + 4, ...
           uint32_t nmine = 0;
           for (uint32_t c = (uint32_t)sub; c < nchunks; c += 4) {
-            const bool full = c * 32u + 16u < ngp;
-            if (full) tmem_ld32_issue(taddr + c * 32u, vv);
-            else tmem_ld16_issue(taddr + c * 32u, reinterpret_cast<uint32_t(&)[16]>(vv));
+            tmem_ld16_issue(taddr + c * 16u, vv);
             tmem_ld_wait();
             if (c + 4 >= nchunks) {  // all of this warp's reads of the stage are in registers: release it
               tc_before();
               mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
             }
-            scan16(std::integral_constant<int, 0>{}, c * 32u);
-            if (full) scan16(std::integral_constant<int, 16>{}, c * 32u + 16u);
+            scan16(c * 16u);
             ++nmine;
           }
           if (nmine == 0) {  // no chunk for this warp in this group: still release the stage
@@ -568,6 +655,17 @@ filter_mma_kernel(MmaArgs a) {
     }
     __syncwarp();
     if (wcount) mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
+#ifdef HS_MMA_PROF
+    if (tid == 0) {
+      PROF_OUT(8, (unsigned long long)(clock64() - e_start));
+      PROF_OUT(9, e_wait_t);
+      PROF_OUT(10, e_ld);
+      PROF_OUT(11, e_rare);
+      PROF_OUT(12, e_issue);
+      PROF_OUT(13, e_arrive);
+      PROF_OUT(14, e_unit);
+    }
+#endif
   }
 
   tc_before();
@@ -744,7 +842,12 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
   if ((double)thr < r2) thr = nextafterf(thr, INFINITY);
   a.thr = thr;
   a.beta = (float)(g.beta * 1.0001);
+#ifdef HS_MMA_PROF
+  HS_TRY(ctx->d_misc.reserve(sizeof(unsigned long long) * 16));
+  HS_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, sizeof(unsigned long long) * 16, ctx->stream));
+  a.prof = ctx->d_misc.as<unsigned long long>();
   if (const char *e = getenv("HS_MMA_DEBUG")) a.debug = (uint32_t)atoi(e);
+#endif
   a.tab16 = ctx->d_tab16.as<uint4>();
   a.nx32 = reinterpret_cast<const float *>((const char *)ctx->d_tab16.p + sizeof(__half) * HS_AA * HS_CDIM);
   a.surv = fa.surv;
@@ -764,6 +867,20 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
   else if (a.len <= 25) HS_MMA(25);
   else HS_MMA(32);
 #undef HS_MMA
+#ifdef HS_MMA_PROF
+  {
+    unsigned long long h[16];
+    cudaMemcpyAsync(h, a.prof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    const double g = (double)grid;
+    fprintf(stderr,
+            "[mma prof] grid %u units %u | producer: total %.0f wait_codes %.0f wait_a_empty %.0f bload %.0f | "
+            "issuer: wait_a_full %.0f wait_t_empty %.0f wait_b %.0f groups %.0f | epilogue(warp0): total %.0f "
+            "wait_t_full %.0f ld_wait %.0f rare %.0f ld_issue %.0f arrive %.0f unit_fetch %.0f  (cycles per CTA)\n",
+            grid, nunits, h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g, h[5] / g, h[6] / g, h[7] / g, h[8] / g,
+            h[9] / g, h[10] / g, h[11] / g, h[12] / g, h[13] / g, h[14] / g);
+  }
+#endif
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;
