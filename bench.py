@@ -402,6 +402,7 @@ def run_native(a):
            "clocks": clocks, "wall_ms_per_step": wall_ms / a.steps,
            "e2e": e2e, "gpu_launches": int(acc["kernel_launches"]),
            "roofline": roofline, "cpu_baseline": cpu,
+           "stages_ms": {k[3:]: round(acc[k] / steps, 4) for k in sorted(acc) if k.startswith("ms_")},
            "kernels": {k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "share": round(v["share_of_step"], 4)}
                        for k, v in kern.items()},
            "counts": {"candidates": int(ncand), "survivors": int(nsurv), "hits_rank0": int(nh),

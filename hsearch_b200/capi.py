@@ -41,7 +41,7 @@ class Stats(C.Structure):
                 ("residual_flips", C.c_uint64), ("n_candidates", C.c_uint64), ("n_survivors", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_edges", C.c_uint64), ("n_work_items", C.c_uint64),
                 ("key_words", C.c_uint32), ("sort_passes", C.c_uint32), ("kernel_launches", C.c_uint32),
-                ("reserved", C.c_uint32),
+                ("rank_path", C.c_uint32),
                 ("ms_hash", C.c_float), ("ms_sort", C.c_float), ("ms_group", C.c_float), ("ms_permute", C.c_float),
                 ("ms_sort_upsweep", C.c_float), ("ms_sort_scan", C.c_float), ("ms_sort_downsweep", C.c_float),
                 ("ms_qhash", C.c_float), ("ms_probe", C.c_float), ("ms_filter", C.c_float), ("ms_exact", C.c_float),
@@ -49,7 +49,7 @@ class Stats(C.Structure):
                 ("ms_host", C.c_float), ("n_candidates_tc", C.c_uint64)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 HIT_DTYPE = np.dtype([("query", "<u4"), ("table_first", "<u4"), ("db_id", "<u8"), ("dist2", "<f8")])

@@ -1,5 +1,6 @@
 // C ABI of libhsearch_b200.so: orchestration of the kernels (include/hsearch_b200.h).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,6 +57,7 @@ void stats_begin(hs_ctx *ctx) {
   memset(&s, 0, sizeof s);
   s.n_fragments = nf;
   s.key_words = kw;
+  s.rank_path = ctx->rank_mode ? 1u : 0u;
 }
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
@@ -87,7 +89,7 @@ static int upload_table_pointers(hs_ctx *ctx) {
   for (uint32_t l = 0; l < L; ++l) {
     h[l] = ctx->tables[l].codes_sorted.p;
     h[(HS_MAX_L + 1) + l] = ctx->tables[l].sorted_ids.p;
-    h[2 * (HS_MAX_L + 1) + l] = ctx->d_keys[l].p;
+    h[2 * (HS_MAX_L + 1) + l] = ctx->rank_mode ? nullptr : ctx->d_keys[l].p;
   }
   h[L] = ctx->d_codes_pm.p;
   h[(HS_MAX_L + 1) + L] = nullptr;
@@ -281,6 +283,27 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
   MmaLaunch ml;
   if (!P.mma_units.empty()) {
     const uint32_t nunits = (uint32_t)P.mma_units.size();
+    if (const char *e = getenv("HS_PLAN_STATS")) {
+      if (atoi(e)) {
+        // width histogram of the tensor filter's (tile, query group) work: columns per MMA group
+        uint64_t hist[9] = {0}, groups = 0, padded = 0;
+        for (const MmaUnitHost &un : P.mma_units) {
+          const MmaItemHost &it = P.mma_items[un.item];
+          const uint64_t tiles = (un.m_end - (un.m_begin & ~15u) + 127) / 128;
+          for (uint32_t q0 = it.q_begin; q0 < it.q_end; q0 += 256) {
+            const uint32_t ng = std::min<uint32_t>(256, it.q_end - q0), ngp = (ng + 15u) & ~15u;
+            groups += tiles;
+            padded += tiles * 128 * ngp;
+            hist[std::min<uint32_t>(8, ngp / 32)] += tiles;
+          }
+        }
+        fprintf(stderr, "[plan] mma items %zu units %zu tile-groups %llu padded pairs %llu real pairs %llu | groups by width/32:",
+                P.mma_items.size(), P.mma_units.size(), (unsigned long long)groups, (unsigned long long)padded,
+                (unsigned long long)P.ncand_tc);
+        for (int i = 0; i < 9; ++i) fprintf(stderr, " %llu", (unsigned long long)hist[i]);
+        fprintf(stderr, "\n");
+      }
+    }
     const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->num_sms, (nunits + 3) / 4);
     HS_TRY(ctx->d_mma_items.reserve(sizeof(MmaItemHost) * P.mma_items.size()));
     HS_TRY(ctx->d_mma_units.reserve(sizeof(MmaUnitHost) * P.mma_units.size()));
@@ -345,6 +368,24 @@ __global__ void hit_gather_kernel(const hs_hit *__restrict__ in, const uint32_t 
   if (i < n) out[i] = in[perm[i]];
 }
 
+// (query, first table, db id) as one 64-bit key: query in the top qbits, table in the next
+// tbits, db id below.  *overflow is set when a field does not fit.
+__global__ void hit_key1_kernel(const hs_hit *__restrict__ hits, uint64_t n, int tshift, int qshift,
+                                uint64_t *__restrict__ k0, unsigned int *__restrict__ overflow) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const hs_hit h = hits[i];
+  if ((h.db_id >> tshift) || ((uint64_t)h.table_first >> (qshift - tshift)) || ((uint64_t)h.query >> (64 - qshift)))
+    *overflow = 1u;
+  k0[i] = ((uint64_t)h.query << qshift) | ((uint64_t)h.table_first << tshift) | h.db_id;
+}
+
+static int bits_for(uint64_t nvalues) {  // bits that hold 0 .. nvalues-1
+  int b = 1;
+  while (b < 64 && (nvalues - 1) >> b) ++b;
+  return b;
+}
+
 // Sort d_hits[0..n) by (query, first table, db id); result in ctx->d_hits_sorted.
 static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
   if (n == 0) return HS_OK;
@@ -353,20 +394,39 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
     return HS_ERR_UNSUPPORTED;
   }
   HS_TRY(ctx->d_hit_keys[0].reserve(sizeof(uint64_t) * n));
-  HS_TRY(ctx->d_hit_keys[1].reserve(sizeof(uint64_t) * n));
   HS_TRY(ctx->d_hit_perm.reserve(sizeof(uint32_t) * 2 * n));
   HS_TRY(ctx->d_hits_sorted.reserve(sizeof(hs_hit) * n));
   const unsigned grid = (unsigned)((n + 255) / 256);
-  hit_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, n, ctx->d_hit_keys[0].as<uint64_t>(),
-                                                ctx->d_hit_keys[1].as<uint64_t>());
-  ctx->stats.kernel_launches++;
   KeyPtrs in, sorted;
   memset(&in, 0, sizeof in);
-  in.w[0] = ctx->d_hit_keys[0].as<uint64_t>();
-  in.w[1] = ctx->d_hit_keys[1].as<uint64_t>();
   uint32_t *perm = ctx->d_hit_perm.as<uint32_t>();
   const hs_stats before = ctx->stats;
-  HS_TRY(radix_sort_pairs(ctx, in, nullptr, n, 2, perm, perm + n, &sorted));
+  // one-word key when the three fields fit 64 bits (they do unless ids are astronomically large)
+  const int qbits = bits_for(std::max<uint64_t>(ctx->hit_qmax, 1)), tbits = bits_for((uint64_t)ctx->prm.L + 1);
+  const int qshift = 64 - qbits, tshift = qshift - tbits;
+  bool one_word = tshift >= 20;
+  if (one_word) {
+    unsigned int *ovf = reinterpret_cast<unsigned int *>(ctx->d_counters.as<unsigned long long>() + 14);
+    HS_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned int), ctx->stream));
+    hit_key1_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, n, tshift, qshift, ctx->d_hit_keys[0].as<uint64_t>(), ovf);
+    ctx->stats.kernel_launches++;
+    unsigned int h_ovf = 0;
+    HS_CUDA(cudaMemcpyAsync(&h_ovf, ovf, sizeof h_ovf, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    one_word = h_ovf == 0;
+  }
+  if (one_word) {
+    in.w[0] = ctx->d_hit_keys[0].as<uint64_t>();
+    HS_TRY(radix_sort_pairs(ctx, in, nullptr, n, 1, perm, perm + n, &sorted));
+  } else {
+    HS_TRY(ctx->d_hit_keys[1].reserve(sizeof(uint64_t) * n));
+    hit_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, n, ctx->d_hit_keys[0].as<uint64_t>(),
+                                                  ctx->d_hit_keys[1].as<uint64_t>());
+    ctx->stats.kernel_launches++;
+    in.w[0] = ctx->d_hit_keys[0].as<uint64_t>();
+    in.w[1] = ctx->d_hit_keys[1].as<uint64_t>();
+    HS_TRY(radix_sort_pairs(ctx, in, nullptr, n, 2, perm, perm + n, &sorted));
+  }
   // sort_passes / ms_sort_* describe the index build only
   ctx->stats.sort_passes = before.sort_passes;
   ctx->stats.ms_sort_upsweep = before.ms_sort_upsweep;
@@ -406,7 +466,7 @@ static int stage_queries(hs_ctx *ctx, const QueryInput &in, uint32_t Q) {
         memcpy(&pts[(size_t)q * dim + p * HS_CDIM], ctx->table64 + c * HS_CDIM, sizeof(double) * HS_CDIM);
       }
     HS_CUDA(cudaMemcpyAsync(ctx->d_q64.p, pts.data(), sizeof(double) * Q * dim, cudaMemcpyHostToDevice, ctx->stream));
-    HS_TRY(ctx->d_qcodes.reserve(std::max<size_t>(1, (size_t)Q * len)));
+    HS_TRY(ctx->d_qcodes.reserve((size_t)Q * len + 16));  // slack: word-wise reads (load_bytes)
     HS_CUDA(cudaMemcpyAsync(ctx->d_qcodes.p, in.h_codes, (size_t)Q * len, cudaMemcpyHostToDevice, ctx->stream));
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->have_qcodes = true;
@@ -420,7 +480,7 @@ static int stage_queries(hs_ctx *ctx, const QueryInput &in, uint32_t Q) {
     return HS_ERR_INVALID;
   }
   if (ctx->prm.metric == HS_METRIC_EUCLID_FP64) {
-    HS_TRY(ctx->d_qcodes_det.reserve(std::max<size_t>(1, (size_t)Q * len)));
+    HS_TRY(ctx->d_qcodes_det.reserve((size_t)Q * len + 16));
     HS_TRY(ctx->d_qrow.reserve(std::max<size_t>(1, (size_t)Q)));
     HS_TRY(launch_detect_query_codes(ctx, ctx->d_q64.as<double>(), Q, ctx->d_qcodes_det.as<uint8_t>(),
                                      ctx->d_qrow.as<uint8_t>()));
@@ -446,6 +506,9 @@ void fill_exact_common(hs_ctx *ctx, ExactArgs &ea, uint32_t Q) {
   ea.R = ctx->prm.R;
   ea.sorted_ids = dev_sorted_ids(ctx);
   ea.codes = ctx->d_codes.as<uint8_t>();
+  ea.rec = ctx->d_rec.as<uint8_t>();
+  ea.rec_stride = ctx->rec_stride;
+  ea.rec_rank_off = ctx->rec_rank_off;
   ea.N = ctx->N;
   ea.id_base = ctx->id_base;
   ea.table64 = ctx->d_table64.as<double>();
@@ -508,10 +571,12 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   HS_TRY(ctx->d_qkeys.reserve(sizeof(uint64_t) * std::max<size_t>(1, (size_t)L * Q * KW)));
   HS_TRY(ctx->d_qvalid.reserve(std::max<size_t>(1, (size_t)L * Q)));
   HS_TRY(ctx->d_qrange.reserve(sizeof(uint2) * std::max<size_t>(1, (size_t)L * Q)));
+  HS_TRY(ctx->d_qrank.reserve(sizeof(uint32_t) * std::max<size_t>(1, (size_t)L * Q)));
   HS_TRY(launch_hash_queries(ctx, ctx->d_q64.as<double>(), Q, ctx->d_qkeys.as<uint64_t>(), ctx->d_qvalid.as<uint8_t>()));
   HS_CUDA(cudaEventRecord(ev[1], ctx->stream));
   for (uint32_t l = 0; l < L; ++l)
-    HS_TRY(launch_probe(ctx, l, ctx->d_qkeys.as<uint64_t>(), ctx->d_qvalid.as<uint8_t>(), Q, ctx->d_qrange.as<uint2>()));
+    HS_TRY(launch_probe(ctx, l, ctx->d_qkeys.as<uint64_t>(), ctx->d_qvalid.as<uint8_t>(), Q, ctx->d_qrange.as<uint2>(),
+                         ctx->d_qrank.as<uint32_t>()));
   HS_TRY(build_tq(ctx, Q));
   std::vector<uint2> qrange((size_t)L * Q);
   if (!qrange.empty())
@@ -550,6 +615,7 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   ctx->stats.n_work_items = plan.items.size() + plan.items_tc.size() + plan.mma_units.size();
   HS_CUDA(cudaEventRecord(ev[12], ctx->stream));
 
+  ctx->hit_qmax = Q;
   uint64_t nsurv = 0;
   HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
   HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
@@ -573,6 +639,7 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   }
   ea.qkeys = ctx->d_qkeys.as<uint64_t>();
   ea.qvalid = ctx->d_qvalid.as<uint8_t>();
+  ea.qrank = ctx->rank_mode ? ctx->d_qrank.as<uint32_t>() : nullptr;
   ea.hits = ctx->d_hits.as<hs_hit>();
   ea.hit_cap = dev_cap;
   ea.hit_count = hit_count;
@@ -628,6 +695,7 @@ static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit
   if (!allpairs) HS_TRY(stage_queries(ctx, *in, Q));
 
   const uint64_t total_q = allpairs ? N : Q;
+  ctx->hit_qmax = total_q;
   // all pairs: the DB is its own query set, taken in blocks whose filter tables
   // are resident at once; explicit queries: one block
   const uint64_t qblock = allpairs ? (1u << 20) : std::max<uint64_t>(total_q, 1);
@@ -757,6 +825,8 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->prm = *params;
   ctx->dim = params->len * HS_CDIM;
+  ctx->rec_rank_off = (params->len + 1u) & ~1u;
+  ctx->rec_stride = (params->len + 15u) & ~15u;
   coordinates_table(params->table_variant, ctx->table64);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("hs_create: cudaStreamCreate failed");
@@ -786,7 +856,7 @@ void hs_destroy(hs_ctx_t *ctx) {
                     &ctx->d_hit_keys[1], &ctx->d_hit_keys[2], &ctx->d_hit_perm, &ctx->d_hits_sorted,
                     &ctx->d_hits_gathered, &ctx->d_misc, &ctx->d_parent, &ctx->d_tabptrs, &ctx->d_residues,
                     &ctx->d_starts, &ctx->d_metric32, &ctx->d_tq16, &ctx->d_work_tc, &ctx->d_qlist_tc, &ctx->d_large,
-                    &ctx->d_qcodes_det, &ctx->d_qrow, &ctx->d_tab16, &ctx->d_qb16, &ctx->d_mma_items, &ctx->d_mma_units, &ctx->d_mma_cta, &ctx->d_qlist_mma, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
+                    &ctx->d_qcodes_det, &ctx->d_qrow, &ctx->d_tab16, &ctx->d_qb16, &ctx->d_mma_items, &ctx->d_mma_units, &ctx->d_mma_cta, &ctx->d_qlist_mma, &ctx->d_lut, &ctx->d_rinfo, &ctx->d_ranks, &ctx->d_rec, &ctx->d_qrank, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
                     &ctx->sort.flags, &ctx->sort.block_sums, &ctx->sort.or_and};
   for (DevBuf *b : bufs) b->release();
   for (int w = 0; w < kMaxKeyWords; ++w) {
@@ -850,6 +920,7 @@ static int load_common(hs_ctx *ctx, uint64_t N, uint64_t id_base) {
   ctx->hashed = false;
   ctx->indexed = false;
   ctx->have_codes_pm = false;
+  ctx->have_rec = false;
   return ctx->d_codes.reserve((size_t)N * ctx->prm.len + 64);
 }
 
@@ -903,7 +974,8 @@ int hs_hash(hs_ctx_t *ctx, int32_t *buckets_out) {
     ctx->hashed = true;
     return HS_OK;
   }
-  for (uint32_t l = 0; l < L; ++l) HS_TRY(ctx->d_keys[l].reserve(sizeof(uint64_t) * ctx->key_words * N));
+  if (!ctx->rank_mode)
+    for (uint32_t l = 0; l < L; ++l) HS_TRY(ctx->d_keys[l].reserve(sizeof(uint64_t) * ctx->key_words * N));
   if (buckets_out) HS_TRY(ctx->d_buckets.reserve(sizeof(int32_t) * N * L * K));
   unsigned long long *cnt = ctx->d_counters.as<unsigned long long>();
   HS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 8, ctx->stream));
@@ -939,6 +1011,18 @@ int hs_get_keys(hs_ctx_t *ctx, uint32_t table, uint64_t *keys_out) {
   HS_CUDA(cudaSetDevice(ctx->device));
   const uint64_t N = ctx->N;
   const uint32_t KW = ctx->key_words;
+  if (ctx->rank_mode) {
+    // rank path: the key of a fragment is the key string of its bucket rank
+    std::vector<uint16_t> rk(N);
+    if (N)
+      HS_CUDA(cudaMemcpy(rk.data(), ctx->d_ranks.as<uint16_t>() + (size_t)table * ctx->npad, sizeof(uint16_t) * N,
+                         cudaMemcpyDeviceToHost));
+    const uint32_t nr = ctx->rank_nr[table];
+    const std::vector<uint64_t> &keys = ctx->h_rkeys[table];
+    for (uint64_t i = 0; i < N; ++i)
+      for (uint32_t w = 0; w < KW; ++w) keys_out[i * KW + w] = keys[(size_t)w * nr + rk[i]];
+    return HS_OK;
+  }
   std::vector<uint64_t> tmp((size_t)KW * N);
   if (N) HS_CUDA(cudaMemcpy(tmp.data(), ctx->d_keys[table].p, sizeof(uint64_t) * KW * N, cudaMemcpyDeviceToHost));
   for (uint64_t i = 0; i < N; ++i)
@@ -975,7 +1059,7 @@ int hs_build_index(hs_ctx_t *ctx) {
       ms_permute += ev_ms(ev[4], ev[5]);
     }
   } else {
-    for (uint32_t l = 0; l < L; ++l) ctx->tables[l].nb = 0;
+    for (uint32_t l = 0; l < L; ++l) ctx->tables[l].nb = ctx->tables[l].nslots = 0;
   }
   HS_CUDA(cudaEventRecord(ev[9], ctx->stream));
   HS_CUDA(cudaEventSynchronize(ev[9]));
@@ -1006,7 +1090,18 @@ int hs_get_table(hs_ctx_t *ctx, uint32_t table, uint32_t *ids_out, uint32_t *sta
   HS_CUDA(cudaSetDevice(ctx->device));
   const TableIndex &T = ctx->tables[table];
   if (ids_out && ctx->N) HS_CUDA(cudaMemcpy(ids_out, T.sorted_ids.p, sizeof(uint32_t) * ctx->N, cudaMemcpyDeviceToHost));
-  if (starts_out && ctx->N) HS_CUDA(cudaMemcpy(starts_out, T.bstart.p, sizeof(uint32_t) * (T.nb + 1), cudaMemcpyDeviceToHost));
+  if (starts_out && ctx->N) {
+    if (T.nslots == T.nb) {
+      HS_CUDA(cudaMemcpy(starts_out, T.bstart.p, sizeof(uint32_t) * (T.nb + 1), cudaMemcpyDeviceToHost));
+    } else {  // rank path: drop the empty bucket slots
+      std::vector<uint32_t> all(T.nslots + 1);
+      HS_CUDA(cudaMemcpy(all.data(), T.bstart.p, sizeof(uint32_t) * (T.nslots + 1), cudaMemcpyDeviceToHost));
+      uint64_t o = 0;
+      for (uint64_t i = 0; i < T.nslots; ++i)
+        if (all[i + 1] != all[i]) starts_out[o++] = all[i];
+      starts_out[o] = all[T.nslots];
+    }
+  }
   return HS_OK;
 }
 

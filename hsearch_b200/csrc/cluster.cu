@@ -107,7 +107,7 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
 
   for (uint32_t l = 0; l < L; ++l) {
     const TableIndex &T = ctx->tables[l];
-    if (T.nb == 0) continue;
+    if (T.nslots == 0) continue;
     HS_CUDA(cudaEventRecord(ev[1], ctx->stream));
     // --- small buckets on the device, large ones collected ---
     HS_TRY(ctx->d_large.reserve(sizeof(uint2) * (N / kSmallBucket + 2)));
@@ -119,9 +119,9 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
       HS_CUDA(cudaMemsetAsync(scnt, 0, sizeof(unsigned long long), ctx->stream));
       HS_CUDA(cudaMemsetAsync(nlarge, 0, sizeof(unsigned int), ctx->stream));
       HS_CUDA(cudaMemsetAsync(npairs, 0, sizeof(unsigned long long), ctx->stream));
-      const uint64_t nthreads = T.nb * 32;
+      const uint64_t nthreads = T.nslots * 32;
       small_bucket_pairs_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
-          T.bstart.as<uint32_t>(), T.nb, l, T.codes_sorted.as<uint8_t>(), ctx->npad, (int)ctx->prm.len, pair32, thr,
+          T.bstart.as<uint32_t>(), T.nslots, l, T.codes_sorted.as<uint8_t>(), ctx->npad, (int)ctx->prm.len, pair32, thr,
           ctx->d_surv.as<Survivor>(), ctx->d_surv.cap / sizeof(Survivor), scnt, ctx->d_large.as<uint2>(), nlarge,
           npairs);
       HS_CUDA(cudaGetLastError());

@@ -69,10 +69,12 @@ constexpr int kCodeScale = 4;  // bucket-ordered code store keeps code*4 (a byte
 
 struct TableIndex {
   DevBuf sorted_ids;    // u32 [N]  fragment ids in bucket order
-  DevBuf ukeys;         // u64 [key_words][nb]  distinct keys, ascending
-  DevBuf bstart;        // u32 [nb+1]           bucket boundaries into sorted_ids
+  DevBuf ukeys;         // u64 [key_words][nslots]  keys of the bucket slots, ascending
+  DevBuf bstart;        // u32 [nslots+1]           bucket boundaries into sorted_ids
   DevBuf codes_sorted;  // u8  [len][npad]      code*4, position-major, bucket order
-  uint64_t nb = 0;
+  uint64_t nb = 0;      // non-empty buckets (the reference's "table size")
+  uint64_t nslots = 0;  // bucket slots: == nb on the packed-key path; on the rank path one slot
+                        // per possible key string (empty slots have start == end)
 };
 
 struct SortScratch {
@@ -118,6 +120,23 @@ struct hs_ctx {
   uint32_t key_words = 1;
   uint32_t max_chars = 0;
 
+  // Dense bucket ranks (hash.cu, setup_projection): when every table has at most 65536
+  // possible key strings, a fragment's bucket is the rank of its key string among them
+  // (ascending packed key) -- a u16 instead of a KW*64-bit key.
+  bool rank_mode = false;
+  uint32_t rank_nr[HS_MAX_L];                 // possible key strings per table
+  uint32_t rank_lut_off[HS_MAX_L];            // offset of the table's tuple->rank LUT in d_lut
+  std::vector<int> rank_lo, rank_rng;         // [L][K] bucket range of every projection
+  std::vector<uint64_t> h_rkeys[HS_MAX_L];    // [KW][nr] packed key of every rank (host copy)
+  hs::DevBuf d_lut;                           // u16 tuple index -> rank, all tables
+  hs::DevBuf d_rinfo;                         // i32 [L*K] lo, [L*K] rng, [L] lut offsets (audit kernel)
+  hs::DevBuf d_ranks;                         // u16 [L][N] ranks, table-major (sort input)
+  // Fragment records: codes, then (rank mode) the L u16 ranks; one aligned vector load
+  // gives the exact stage / the bucket-order gather everything they need of a fragment.
+  hs::DevBuf d_rec;                           // u8 [N][rec_stride]
+  uint32_t rec_stride = 0, rec_rank_off = 0;
+  bool have_rec = false;
+
   // database
   uint64_t N = 0, id_base = 0;
   uint64_t npad = 0;         // N rounded up to 16
@@ -138,8 +157,10 @@ struct hs_ctx {
   hs::DevBuf d_tab16;                        // pipelined tensor filter: FP16 embedding rows + row norms
   hs::DevBuf d_qb16, d_mma_items, d_mma_units, d_mma_cta, d_qlist_mma;
   int num_sms = 0;
+  uint64_t hit_qmax = 0;   // query ids of the current call are < hit_qmax (hit sort key width)
   bool have_qcodes = false;
   hs::DevBuf d_qcodes_det, d_qrow;  // codes recovered from dense queries (Euclid exact stage)
+  hs::DevBuf d_qrank;               // u32 [L][Q] bucket slot of every query (0xffffffff: none)
   void *h_pinned = nullptr;
   size_t h_pinned_cap = 0;
 

@@ -1,9 +1,11 @@
 // K1 kernels: fragment hash (FP32 fast path with FP64 guard), all-FP64 hash /
 // audit, and the exact query hash.  See hash.cuh for the method.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "hash.cuh"
 
@@ -11,8 +13,9 @@ namespace hs {
 
 constexpr int kHashThreads = 256;
 
-// counters[0] guard_hits, [1] guard_corrected, [2] key overflow, [3] residual flips
-template <int NQ, int KW>
+// counters[0] guard_hits, [1] guard_corrected, [2] key overflow / bucket out of range, [3] residual flips
+// RANK: write dense u16 bucket ranks (and the fragment records) instead of packed keys.
+template <int NQ, int KW, bool RANK>
 __global__ void __launch_bounds__(kHashThreads)
 hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                  const float *__restrict__ T32,    // [len][20][4*NQ] of this chunk
@@ -26,8 +29,11 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *sT = reinterpret_cast<float *>(smem_raw);                    // len*20*P floats
   uint8_t *sC = smem_raw + (size_t)len * HS_AA * P * sizeof(float);   // kHashThreads*len bytes
+  uint8_t *sRec = sC + (size_t)kHashThreads * len;                    // kHashThreads*rec_stride (full_rec)
 
   const int tid = threadIdx.x;
+  const bool full_rec = RANK && args.full_rec;
+  const uint32_t RS = args.rec_stride;
   {
     const int n4 = len * HS_AA * NQ;
     const float4 *src = reinterpret_cast<const float4 *>(T32);
@@ -46,80 +52,135 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
     for (uint32_t i = tid; i < nvec; i += kHashThreads) dst[i] = __ldg(src + i);
     for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += kHashThreads) sC[i] = codes[byte0 + i];
   }
+  if (full_rec) {
+    uint4 *z = reinterpret_cast<uint4 *>(sRec);
+    for (uint32_t i = tid; i < (uint32_t)kHashThreads * RS / 16; i += kHashThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
-  if ((uint64_t)tid >= nfrag) return;
-  const uint64_t frag = frag0 + tid;
-  const uint8_t *myc = sC + tid * len;
+  if ((uint64_t)tid < nfrag) {
+    const uint64_t frag = frag0 + tid;
+    const uint8_t *myc = sC + tid * len;
+    uint8_t *myrec = sRec + (size_t)tid * RS;
 
-  float acc[P];
+    float acc[P];
 #pragma unroll
-  for (int s = 0; s < P; ++s) acc[s] = 0.f;
-  for (int pos = 0; pos < len; ++pos) {
-    const int c = myc[pos];
-    const float4 *row = reinterpret_cast<const float4 *>(sT + (pos * HS_AA + c) * P);
-    // the quads of row c are stored rotated by c/2 (setup_projection), so that lanes with
-    // different residues hit different banks when they all want logical quad j
-    const int rot = c >> 1;
+    for (int s = 0; s < P; ++s) acc[s] = 0.f;
+    for (int pos = 0; pos < len; ++pos) {
+      const int c = myc[pos];
+      if (full_rec) myrec[pos] = (uint8_t)c;
+      const float4 *row = reinterpret_cast<const float4 *>(sT + (pos * HS_AA + c) * P);
+      // the quads of row c are stored rotated by c/2 (setup_projection), so that lanes with
+      // different residues hit different banks when they all want logical quad j
+      const int rot = c >> 1;
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-      const float4 v = row[(j + rot) & (NQ - 1)];
-      acc[4 * j + 0] += v.x;
-      acc[4 * j + 1] += v.y;
-      acc[4 * j + 2] += v.z;
-      acc[4 * j + 3] += v.w;
-    }
-  }
-
-  KeyBuilder<KW> kb;
-  kb.reset();
-  int t = 0, k = 0;  // table within chunk, projection within table (uniform across the block)
-  unsigned int my_guard = 0, my_corr = 0, my_over = 0;
-#pragma unroll
-  for (int s = 0; s < P; ++s) {
-    if (t < args.ntab && k < K) {
-      const float val = acc[s] + __ldg(b32 + s);
-      const float tt = val * invW;
-      const float f = floorf(tt);
-      int bucket = (int)f;
-      const float e = __ldg(eps32 + s);
-      if ((tt - f) < e || ((f + 1.0f) - tt) < e) {
-        const int l = args.l0 + t;
-        const int ex = exact_bucket_codes(myc, len, table64, a64 + ((size_t)l * K + k) * dim,
-                                          b64[l * K + k], W);
-        ++my_guard;
-        if (ex != bucket) ++my_corr;
-        bucket = ex;
-      }
-      kb.push_int(bucket);
-      if (buckets_out) buckets_out[(frag * L + (args.l0 + t)) * K + k] = bucket;
-      if (k == K - 1) {
-        if (kb.nchars > 16 * KW) ++my_over;
-        uint64_t *dst = args.keys[t];
-#pragma unroll
-        for (int w = 0; w < KW; ++w) dst[(uint64_t)w * N + frag] = kb.w[w];
-        kb.reset();
+      for (int j = 0; j < NQ; ++j) {
+        const float4 v = row[(j + rot) & (NQ - 1)];
+        acc[4 * j + 0] += v.x;
+        acc[4 * j + 1] += v.y;
+        acc[4 * j + 2] += v.z;
+        acc[4 * j + 3] += v.w;
       }
     }
-    if (++k == Kp) {
-      k = 0;
-      ++t;
+
+    KeyBuilder<KW> kb;
+    kb.reset();
+    uint32_t tix = 0;
+    bool in_range = true;
+    int t = 0, k = 0;  // table within chunk, projection within table (uniform across the block)
+    unsigned int my_guard = 0, my_corr = 0, my_over = 0;
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+      if (t < args.ntab && k < K) {
+        const float val = acc[s] + __ldg(b32 + s);
+        const float tt = val * invW;
+        const float f = floorf(tt);
+        int bucket = (int)f;
+        const float e = __ldg(eps32 + s);
+        if ((tt - f) < e || ((f + 1.0f) - tt) < e) {
+          const int l = args.l0 + t;
+          const int ex = exact_bucket_codes(myc, len, table64, a64 + ((size_t)l * K + k) * dim,
+                                            b64[l * K + k], W);
+          ++my_guard;
+          if (ex != bucket) ++my_corr;
+          bucket = ex;
+        }
+        if (RANK) in_range = rank_tuple_push(tix, bucket, args.lo[s], args.rng[s]) && in_range;
+        else kb.push_int(bucket);
+        if (buckets_out) buckets_out[(frag * L + (args.l0 + t)) * K + k] = bucket;
+        if (k == K - 1) {
+          if (RANK) {
+            uint16_t rank = 0;
+            if (in_range) rank = __ldg(args.lut[t] + tix);
+            else ++my_over;
+            args.ranks[t][frag] = rank;
+            if (full_rec)
+              *reinterpret_cast<uint16_t *>(myrec + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
+            else
+              *reinterpret_cast<uint16_t *>(args.rec + frag * RS + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
+            tix = 0;
+            in_range = true;
+          } else {
+            if (kb.nchars > 16 * KW) ++my_over;
+            uint64_t *dst = args.keys[t];
+#pragma unroll
+            for (int w = 0; w < KW; ++w) dst[(uint64_t)w * N + frag] = kb.w[w];
+            kb.reset();
+          }
+        }
+      }
+      if (++k == Kp) {
+        k = 0;
+        ++t;
+      }
     }
+    if (my_guard) atomicAdd(counters + 0, (unsigned long long)my_guard);
+    if (my_corr) atomicAdd(counters + 1, (unsigned long long)my_corr);
+    if (my_over) atomicAdd(counters + 2, (unsigned long long)my_over);
   }
-  if (my_guard) atomicAdd(counters + 0, (unsigned long long)my_guard);
-  if (my_corr) atomicAdd(counters + 1, (unsigned long long)my_corr);
-  if (my_over) atomicAdd(counters + 2, (unsigned long long)my_over);
+  if (full_rec) {
+    // the block's records are contiguous in global memory: coalesced 16-byte copies
+    __syncthreads();
+    const uint32_t nvec = (uint32_t)(nfrag * RS / 16);
+    const uint4 *src = reinterpret_cast<const uint4 *>(sRec);
+    uint4 *dst = reinterpret_cast<uint4 *>(args.rec + frag0 * RS);
+    for (uint32_t i = tid; i < nvec; i += kHashThreads) dst[i] = src[i];
+  }
+}
+
+// Fragment records without ranks: codes copied into rows of rec_stride bytes (zero padded).
+__global__ void __launch_bounds__(kHashThreads)
+build_records_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len, uint32_t RS, uint8_t *__restrict__ rec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint8_t *sRec = smem_raw;
+  const int tid = threadIdx.x;
+  const uint64_t frag0 = (uint64_t)blockIdx.x * kHashThreads;
+  const uint64_t nfrag = min((uint64_t)kHashThreads, N - frag0);
+  uint4 *z = reinterpret_cast<uint4 *>(sRec);
+  for (uint32_t i = tid; i < (uint32_t)kHashThreads * RS / 16; i += kHashThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const uint64_t byte0 = frag0 * (uint64_t)len;
+  const uint32_t nbytes = (uint32_t)(nfrag * (uint64_t)len);
+  for (uint32_t i = tid; i < nbytes; i += kHashThreads) {
+    const uint32_t f = i / (uint32_t)len, p = i - f * (uint32_t)len;
+    sRec[f * RS + p] = codes[byte0 + i];
+  }
+  __syncthreads();
+  const uint32_t nvec = (uint32_t)(nfrag * RS / 16);
+  uint4 *dst = reinterpret_cast<uint4 *>(rec + frag0 * RS);
+  for (uint32_t i = tid; i < nvec; i += kHashThreads) dst[i] = z[i];
 }
 
 // All-FP64 hash in reference order.  audit == 0: writes keys (and buckets).
-// audit == 1: compares the recomputed key with the stored one and counts
-// mismatching (fragment, table) keys in counters[3].
+// audit == 1: compares the recomputed key (rank path: the recomputed rank) with the
+// stored one and counts mismatching (fragment, table) keys in counters[3].
 template <int KW>
 __global__ void __launch_bounds__(kHashThreads)
 hash_exact_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                   const double *__restrict__ table64, const double *__restrict__ a64,
                   const double *__restrict__ b64, double W, int K, int L, int dim, int l0, int l1,
                   uint64_t *const *__restrict__ keys, int32_t *__restrict__ buckets_out, int audit,
-                  unsigned long long *__restrict__ counters) {
+                  const int *__restrict__ rinfo /* rank path, audit only */, const uint16_t *__restrict__ lut,
+                  const uint16_t *__restrict__ ranks, uint64_t rstride, unsigned long long *__restrict__ counters) {
   const uint64_t frag = (uint64_t)blockIdx.x * kHashThreads + threadIdx.x;
   if (frag >= N) return;
   uint8_t c[HS_MAX_LEN];
@@ -128,12 +189,20 @@ hash_exact_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
   for (int l = l0; l < l1; ++l) {
     KeyBuilder<KW> kb;
     kb.reset();
+    uint32_t tix = 0;
+    bool in_range = true;
     for (int k = 0; k < K; ++k) {
       const int bucket = exact_bucket_codes(c, len, table64, a64 + ((size_t)l * K + k) * dim, b64[l * K + k], W);
       kb.push_int(bucket);
+      if (rinfo) in_range = rank_tuple_push(tix, bucket, rinfo[l * K + k], rinfo[L * K + l * K + k]) && in_range;
       if (!audit && buckets_out) buckets_out[(frag * L + l) * K + k] = bucket;
     }
     if (kb.nchars > 16 * KW) ++over;
+    if (rinfo) {  // rank path (audit only)
+      const uint32_t off = (uint32_t)rinfo[2 * L * K + l];
+      if (!in_range || lut[off + tix] != ranks[(uint64_t)l * rstride + frag]) ++flips;
+      continue;
+    }
     uint64_t *dst = keys[l];
     if (audit) {
       bool same = true;
@@ -171,13 +240,14 @@ __global__ void hash_queries_kernel(const double *__restrict__ q64, uint32_t Q, 
 }
 
 // ---- host side ---------------------------------------------------------------
-template <int NQ, int KW>
+template <int NQ, int KW, bool RANK>
 static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
                             unsigned long long *counters) {
   const int P = 4 * NQ;
   const int len = (int)ctx->prm.len;
-  const size_t smem = (size_t)len * HS_AA * P * sizeof(float) + (size_t)kHashThreads * len;
-  auto kern = hash_fast_kernel<NQ, KW>;
+  const size_t smem = (size_t)len * HS_AA * P * sizeof(float) + (size_t)kHashThreads * len +
+                      (args.full_rec ? (size_t)kHashThreads * args.rec_stride : 0);
+  auto kern = hash_fast_kernel<NQ, KW, RANK>;
   if (smem > 48 * 1024) HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((ctx->N + kHashThreads - 1) / kHashThreads);
   const float *T = ctx->d_T32.as<float>() + (size_t)chunk * len * HS_AA * P;
@@ -193,23 +263,67 @@ static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, i
 
 template <int NQ>
 static int launch_fast_kw(hs_ctx *ctx, int chunk, const HashChunkArgs &a, int32_t *b, unsigned long long *c) {
+  if (ctx->rank_mode) return launch_fast_inst<NQ, 1, true>(ctx, chunk, a, b, c);
   switch (ctx->key_words) {
-    case 1: return launch_fast_inst<NQ, 1>(ctx, chunk, a, b, c);
-    case 2: return launch_fast_inst<NQ, 2>(ctx, chunk, a, b, c);
-    case 3: return launch_fast_inst<NQ, 3>(ctx, chunk, a, b, c);
-    default: return launch_fast_inst<NQ, 4>(ctx, chunk, a, b, c);
+    case 1: return launch_fast_inst<NQ, 1, false>(ctx, chunk, a, b, c);
+    case 2: return launch_fast_inst<NQ, 2, false>(ctx, chunk, a, b, c);
+    case 3: return launch_fast_inst<NQ, 3, false>(ctx, chunk, a, b, c);
+    default: return launch_fast_inst<NQ, 4, false>(ctx, chunk, a, b, c);
   }
+}
+
+int ensure_records(hs_ctx *ctx) {
+  if (ctx->have_rec || ctx->N == 0) return HS_OK;
+  HS_TRY(ctx->d_rec.reserve((size_t)ctx->N * ctx->rec_stride + 64));
+  const unsigned grid = (unsigned)((ctx->N + kHashThreads - 1) / kHashThreads);
+  const size_t smem = (size_t)kHashThreads * ctx->rec_stride;
+  if (smem > 48 * 1024)
+    HS_CUDA(cudaFuncSetAttribute(build_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  build_records_kernel<<<grid, kHashThreads, smem, ctx->stream>>>(ctx->d_codes.as<uint8_t>(), ctx->N,
+                                                                 (int)ctx->prm.len, ctx->rec_stride,
+                                                                 ctx->d_rec.as<uint8_t>());
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  ctx->have_rec = true;
+  return HS_OK;
 }
 
 int launch_hash_fast(hs_ctx *ctx, bool want_buckets) {
   int32_t *buckets = want_buckets ? ctx->d_buckets.as<int32_t>() : nullptr;
   unsigned long long *counters = ctx->d_counters.as<unsigned long long>();
+  const uint32_t K = ctx->prm.K;
+  // the single-chunk rank launch writes whole records through shared memory; otherwise the
+  // records must exist before the per-table ranks are stored into them
+  const bool full_rec = ctx->rank_mode && ctx->nchunks == 1 &&
+                        (size_t)ctx->prm.len * HS_AA * 4 * ctx->nq * sizeof(float) +
+                                (size_t)kHashThreads * (ctx->prm.len + ctx->rec_stride) <= 200 * 1024;
+  if (ctx->rank_mode) {
+    HS_TRY(ctx->d_ranks.reserve(sizeof(uint16_t) * (size_t)ctx->prm.L * ctx->npad + 64));  // table stride npad: 16-byte aligned rows
+    if (full_rec) HS_TRY(ctx->d_rec.reserve((size_t)ctx->N * ctx->rec_stride + 64));
+    else HS_TRY(ensure_records(ctx));
+  }
   for (uint32_t chunk = 0; chunk < ctx->nchunks; ++chunk) {
     HashChunkArgs args;
     memset(&args, 0, sizeof args);
     args.l0 = (int)(chunk * ctx->tpc);
     args.ntab = (int)std::min<uint32_t>(ctx->tpc, ctx->prm.L - args.l0);
-    for (int t = 0; t < args.ntab; ++t) args.keys[t] = ctx->d_keys[args.l0 + t].as<uint64_t>();
+    for (int t = 0; t < args.ntab; ++t) {
+      const uint32_t l = (uint32_t)args.l0 + t;
+      if (ctx->rank_mode) {
+        args.ranks[t] = ctx->d_ranks.as<uint16_t>() + (size_t)l * ctx->npad;
+        args.lut[t] = ctx->d_lut.as<uint16_t>() + ctx->rank_lut_off[l];
+        for (uint32_t k = 0; k < K; ++k) {
+          args.lo[t * ctx->Kp + k] = ctx->rank_lo[(size_t)l * K + k];
+          args.rng[t * ctx->Kp + k] = ctx->rank_rng[(size_t)l * K + k];
+        }
+      } else {
+        args.keys[t] = ctx->d_keys[l].as<uint64_t>();
+      }
+    }
+    args.rec = ctx->d_rec.as<uint8_t>();
+    args.rec_stride = ctx->rec_stride;
+    args.rec_rank_off = ctx->rec_rank_off;
+    args.full_rec = full_rec ? 1 : 0;
     switch (ctx->nq) {
       case 1: HS_TRY((launch_fast_kw<1>(ctx, chunk, args, buckets, counters))); break;
       case 2: HS_TRY((launch_fast_kw<2>(ctx, chunk, args, buckets, counters))); break;
@@ -217,6 +331,7 @@ int launch_hash_fast(hs_ctx *ctx, bool want_buckets) {
       default: HS_TRY((launch_fast_kw<8>(ctx, chunk, args, buckets, counters))); break;
     }
   }
+  if (full_rec) ctx->have_rec = true;
   return HS_OK;
 }
 
@@ -224,10 +339,12 @@ template <int KW>
 static int launch_exact_inst(hs_ctx *ctx, int32_t *buckets, int audit, uint64_t *const *d_keyptrs,
                              unsigned long long *counters) {
   const unsigned grid = (unsigned)((ctx->N + kHashThreads - 1) / kHashThreads);
+  const bool rank = ctx->rank_mode;  // (the all-FP64 hash itself never runs on the rank path)
   hash_exact_kernel<KW><<<grid, kHashThreads, 0, ctx->stream>>>(
       ctx->d_codes.as<uint8_t>(), ctx->N, (int)ctx->prm.len, ctx->d_table64.as<double>(),
       ctx->d_a64.as<double>(), ctx->d_b64.as<double>(), ctx->prm.W, (int)ctx->prm.K, (int)ctx->prm.L,
-      (int)ctx->dim, 0, (int)ctx->prm.L, d_keyptrs, buckets, audit, counters);
+      (int)ctx->dim, 0, (int)ctx->prm.L, d_keyptrs, buckets, audit, rank ? ctx->d_rinfo.as<int>() : nullptr,
+      ctx->d_lut.as<uint16_t>(), ctx->d_ranks.as<uint16_t>(), ctx->npad, counters);
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;
@@ -271,6 +388,107 @@ int launch_hash_queries(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint64_t *
   return HS_OK;
 }
 
+// std::to_string(int) strings of a bucket tuple, packed like KeyBuilder does (hash.cuh).
+static void host_pack_tuple(const int *vals, uint32_t K, uint32_t KW, uint64_t *w) {
+  for (uint32_t i = 0; i < KW; ++i) w[i] = 0;
+  char buf[16];
+  for (uint32_t k = 0; k < K; ++k) {
+    const int n = snprintf(buf, sizeof buf, "%d", vals[k]);
+    for (int i = 0; i < n; ++i) {
+      const uint64_t nib = buf[i] == '-' ? 11u : (uint64_t)(buf[i] - '0') + 1u;
+      for (uint32_t j = KW - 1; j > 0; --j) w[j] = (w[j] << 4) | (w[j - 1] >> 60);
+      w[0] = (w[0] << 4) | nib;
+    }
+  }
+}
+
+constexpr uint32_t kMaxRanks = 65536;  // ranks are u16
+
+// Dense bucket ranks.  Every projection's bucket lies in [lo, lo + rng) for every possible
+// residue string (setup_projection), so a table has at most prod(rng) bucket tuples.  When
+// that is <= 65536 for every table, all tuples are enumerated on the host, their key strings
+// (HashKey, lsh.hpp:51-59: concatenated without separator, so distinct tuples may collide)
+// are packed and sorted, and lut[tuple] = rank of the tuple's string.  The device then
+// carries a u16 rank per (fragment, table) instead of a KW*64-bit packed key; rank order is
+// packed-key order, so bucket order, bucket contents and the probe are unchanged.
+static int setup_ranks(hs_ctx *ctx) {
+  const uint32_t K = ctx->prm.K, L = ctx->prm.L, KW = ctx->key_words, len = ctx->prm.len;
+  ctx->rank_mode = false;
+  ctx->have_rec = false;
+  ctx->rec_rank_off = (len + 1u) & ~1u;
+  ctx->rec_stride = (len + 15u) & ~15u;
+  const char *e = getenv("HS_NO_RANK");
+  if ((ctx->prm.flags & HS_FLAG_HASH_EXACT) || (e && atoi(e))) return HS_OK;
+  std::vector<uint32_t> prod(L);
+  uint64_t total = 0;
+  for (uint32_t l = 0; l < L; ++l) {
+    uint64_t p = 1;
+    for (uint32_t k = 0; k < K; ++k) {
+      p *= (uint64_t)ctx->rank_rng[(size_t)l * K + k];
+      if (p > kMaxRanks) return HS_OK;  // too many possible buckets: packed-key path
+    }
+    prod[l] = (uint32_t)p;
+    total += p;
+  }
+  std::vector<uint16_t> lut(total);
+  std::vector<int> rinfo(2 * (size_t)L * K + L);
+  uint64_t off = 0;
+  std::vector<int> vals(K);
+  for (uint32_t l = 0; l < L; ++l) {
+    const uint32_t np = prod[l];
+    std::vector<uint64_t> keys((size_t)np * KW);
+    for (uint32_t t = 0; t < np; ++t) {
+      uint32_t rem = t;
+      for (int k = (int)K - 1; k >= 0; --k) {  // first projection is the most significant digit
+        const uint32_t r = (uint32_t)ctx->rank_rng[(size_t)l * K + k];
+        vals[k] = ctx->rank_lo[(size_t)l * K + k] + (int)(rem % r);
+        rem /= r;
+      }
+      host_pack_tuple(vals.data(), K, KW, &keys[(size_t)t * KW]);
+    }
+    std::vector<uint32_t> order(np);
+    for (uint32_t t = 0; t < np; ++t) order[t] = t;
+    auto less = [&](uint32_t x, uint32_t y) {
+      for (int w = (int)KW - 1; w >= 0; --w) {
+        const uint64_t a = keys[(size_t)x * KW + w], b = keys[(size_t)y * KW + w];
+        if (a != b) return a < b;
+      }
+      return false;
+    };
+    std::sort(order.begin(), order.end(), less);
+    std::vector<uint64_t> &rk = ctx->h_rkeys[l];
+    rk.clear();
+    uint32_t nr = 0;
+    std::vector<uint64_t> uniq;  // [nr][KW]
+    for (uint32_t i = 0; i < np; ++i) {
+      if (i == 0 || less(order[i - 1], order[i])) {
+        for (uint32_t w = 0; w < KW; ++w) uniq.push_back(keys[(size_t)order[i] * KW + w]);
+        ++nr;
+      }
+      lut[off + order[i]] = (uint16_t)(nr - 1);
+    }
+    rk.resize((size_t)KW * nr);  // word-major like the device tables
+    for (uint32_t r = 0; r < nr; ++r)
+      for (uint32_t w = 0; w < KW; ++w) rk[(size_t)w * nr + r] = uniq[(size_t)r * KW + w];
+    ctx->rank_nr[l] = nr;
+    ctx->rank_lut_off[l] = (uint32_t)off;
+    rinfo[2 * (size_t)L * K + l] = (int)off;
+    off += np;
+  }
+  for (size_t i = 0; i < (size_t)L * K; ++i) {
+    rinfo[i] = ctx->rank_lo[i];
+    rinfo[(size_t)L * K + i] = ctx->rank_rng[i];
+  }
+  HS_TRY(ctx->d_lut.reserve(sizeof(uint16_t) * lut.size() + 16));
+  HS_TRY(ctx->d_rinfo.reserve(sizeof(int) * rinfo.size()));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_lut.p, lut.data(), sizeof(uint16_t) * lut.size(), cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_rinfo.p, rinfo.data(), sizeof(int) * rinfo.size(), cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->rank_mode = true;
+  ctx->rec_stride = (ctx->rec_rank_off + 2u * L + 15u) & ~15u;
+  return HS_OK;
+}
+
 // Build the device-side projection data: FP64 matrix, FP32 residue-projection
 // tables per chunk, guard bands, key width.
 int setup_projection(hs_ctx *ctx, const double *a, const double *b) {
@@ -294,6 +512,8 @@ int setup_projection(hs_ctx *ctx, const double *a, const double *b) {
   std::vector<float> T32((size_t)ctx->nchunks * len * HS_AA * P, 0.f), b32((size_t)ctx->nchunks * P, 0.f),
       eps32((size_t)ctx->nchunks * P, 0.f);
   uint32_t max_chars = 0;
+  ctx->rank_lo.assign((size_t)L * K, 0);
+  ctx->rank_rng.assign((size_t)L * K, 1);
   for (uint32_t l = 0; l < L; ++l) {
     const uint32_t chunk = l / ctx->tpc, t = l % ctx->tpc;
     uint32_t chars = 0;
@@ -326,13 +546,18 @@ int setup_projection(hs_ctx *ctx, const double *a, const double *b) {
       const double Et = (double)(len + 6) * ldexp(1.0, -24) * (A + fabs(bb)) / W;
       eps32[(size_t)chunk * P + slot] = (float)(2.0 * Et + 1e-6);
       // bucket range over all possible fragments -> characters of to_string
-      const double slack = 1e-9 * (Bmax + fabs(bb)) + 1.0;
+      // (the FP64 reference sum differs from the real value by < 1e-13 relative; a bucket
+      // outside [lo, hi] is still detected on the device and reported, never mis-keyed)
+      const double slack = 1e-9 * (Bmax + fabs(bb)) / W + 1e-9;
       const long long lo = (long long)floor((-Bmax + bb) / W - slack);
       const long long hi = (long long)floor((Bmax + bb) / W + slack);
       char buf[32];
       uint32_t c1 = (uint32_t)snprintf(buf, sizeof buf, "%lld", lo);
       uint32_t c2 = (uint32_t)snprintf(buf, sizeof buf, "%lld", hi);
       chars += std::max(c1, c2);
+      const long long lo_c = std::max<long long>(lo, -2000000000ll), hi_c = std::min<long long>(hi, 2000000000ll);
+      ctx->rank_lo[(size_t)l * K + k] = (int)lo_c;
+      ctx->rank_rng[(size_t)l * K + k] = (int)std::min<long long>(hi_c - lo_c + 1, 1ll << 30);
     }
     max_chars = std::max(max_chars, chars);
   }
@@ -344,6 +569,7 @@ int setup_projection(hs_ctx *ctx, const double *a, const double *b) {
               16 * HS_MAX_KEY_WORDS);
     return HS_ERR_UNSUPPORTED;
   }
+  HS_TRY(setup_ranks(ctx));
   HS_TRY(ctx->d_T32.reserve(T32.size() * sizeof(float)));
   HS_TRY(ctx->d_b32.reserve(b32.size() * sizeof(float)));
   HS_TRY(ctx->d_eps32.reserve(eps32.size() * sizeof(float)));

@@ -82,13 +82,29 @@ __device__ __forceinline__ int exact_bucket_point(const double *__restrict__ pt,
 }
 
 struct HashChunkArgs {
-  uint64_t *keys[8];  // per table of the chunk: [KW][N]
+  uint64_t *keys[8];  // per table of the chunk: [KW][N]   (packed-key path)
   int l0;             // first table of the chunk
   int ntab;           // tables in the chunk
+  // dense bucket ranks (rank path): rank = lut[mixed-radix index of the bucket tuple]
+  uint16_t *ranks[8];        // per table of the chunk: [N]
+  const uint16_t *lut[8];    // per table of the chunk
+  int lo[32], rng[32];       // per projection slot of the chunk: smallest bucket, bucket count
+  uint8_t *rec;              // fragment records [N][rec_stride]
+  uint32_t rec_stride, rec_rank_off;
+  int full_rec;              // 1: this launch writes whole records (codes + ranks) through shared memory
 };
+
+// Mixed-radix index of one table's bucket tuple; returns false when a bucket lies
+// outside the range setup_projection derived (cannot happen for residue strings).
+__device__ __forceinline__ bool rank_tuple_push(uint32_t &tix, int bucket, int lo, int rng) {
+  const int d = bucket - lo;
+  tix = tix * (uint32_t)rng + (uint32_t)d;
+  return d >= 0 && d < rng;
+}
 
 int launch_hash_fast(hs_ctx *ctx, bool want_buckets);
 int launch_hash_exact(hs_ctx *ctx, bool want_buckets, bool audit);
+int ensure_records(hs_ctx *ctx);  // fragment records hold at least the codes
 int launch_hash_queries(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint64_t *d_qkeys, uint8_t *d_qvalid);
 
 }  // namespace hs

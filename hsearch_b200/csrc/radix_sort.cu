@@ -12,6 +12,7 @@
 // vary across the input (OR/AND reduction), so constant nibbles cost nothing.
 #include <algorithm>
 
+#include "hash.cuh"
 #include "sort.cuh"
 
 namespace hs {
@@ -312,26 +313,45 @@ __global__ void bucket_scatter_kernel(KeyPtrs keys, uint64_t n, const uint32_t *
 }
 
 // ---- bucket-ordered, position-major code store ---------------------------------
-// out[pos][i] = 4 * codes[ids[i]][pos]; four consecutive i per thread so that
-// stores are 32-bit and coalesced.  ids == nullptr: identity order.
-__global__ void permute_codes_kernel(const uint8_t *__restrict__ codes, const uint32_t *__restrict__ ids,
-                                     uint64_t n, uint64_t npad, int len, uint8_t *__restrict__ out) {
+// out[pos][i] = 4 * code[ids[i]][pos]; four consecutive i per thread so that stores are
+// 32-bit and coalesced.  The codes come from the fragment records (one aligned 16-byte
+// load per 16 residues, a single 32-byte sector per fragment at len <= 16) instead of
+// `len` byte gathers.  ids == nullptr: identity order.
+template <int NV>
+__global__ void __launch_bounds__(256)
+permute_rec_kernel(const uint8_t *__restrict__ rec, uint32_t RS, const uint32_t *__restrict__ ids, uint64_t n,
+                   uint64_t npad, int len, uint8_t *__restrict__ out) {
   const uint64_t i4 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
-  uint64_t id[4];
+  uint32_t w[4][4 * NV];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     const uint64_t i = i4 + m;
-    id[m] = i < n ? (ids ? (uint64_t)ids[i] : i) : ~0ull;
-  }
-  for (int pos = 0; pos < len; ++pos) {
-    uint32_t packed = 0;
+    if (i < n) {
+      const uint64_t id = ids ? (uint64_t)__ldg(ids + i) : i;
+      const uint4 *src = reinterpret_cast<const uint4 *>(rec + id * RS);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const uint32_t c = id[m] != ~0ull ? (uint32_t)codes[id[m] * len + pos] * kCodeScale : 0u;
-      packed |= c << (8 * m);
+      for (int v = 0; v < NV; ++v) {
+        const uint4 r = __ldg(src + v);
+        w[m][4 * v + 0] = r.x;
+        w[m][4 * v + 1] = r.y;
+        w[m][4 * v + 2] = r.z;
+        w[m][4 * v + 3] = r.w;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < 4 * NV; ++v) w[m][v] = 0u;
     }
-    *reinterpret_cast<uint32_t *>(out + (uint64_t)pos * npad + i4) = packed;
+  }
+#pragma unroll
+  for (int pos = 0; pos < 16 * NV; ++pos) {
+    if (pos < len) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) packed |= ((w[m][pos >> 2] >> (8 * (pos & 3))) & 0xffu) << (8 * m);
+      // codes are < 20: scaling all four bytes at once cannot carry across bytes
+      *reinterpret_cast<uint32_t *>(out + (uint64_t)pos * npad + i4) = packed * (uint32_t)kCodeScale;
+    }
   }
 }
 
@@ -507,6 +527,7 @@ static int group_inst(hs_ctx *ctx, uint32_t table, const KeyPtrs &keys) {
   HS_CUDA(cudaMemcpyAsync(&nb, d_total, sizeof nb, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   T.nb = nb;
+  T.nslots = nb;
   HS_TRY(T.ukeys.reserve(sizeof(uint64_t) * NW * (uint64_t)std::max<uint32_t>(nb, 1)));
   HS_TRY(T.bstart.reserve(sizeof(uint32_t) * ((uint64_t)nb + 1)));
   bucket_scatter_kernel<NW><<<grid, 256, 0, ctx->stream>>>(keys, n, flags, scanned, nb, T.ukeys.as<uint64_t>(),
@@ -523,15 +544,246 @@ int build_code_store(hs_ctx *ctx, const uint32_t *ids, DevBuf &out) {
     HS_TRY(out.reserve(bytes));
     HS_CUDA(cudaMemsetAsync(out.p, 0, out.cap, ctx->stream));
   }
+  HS_TRY(ensure_records(ctx));
   const uint64_t nthreads = (n + 3) / 4;
-  permute_codes_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
-      ctx->d_codes.as<uint8_t>(), ids, n, ctx->npad, (int)ctx->prm.len, out.as<uint8_t>());
+  const unsigned grid = (unsigned)((nthreads + 255) / 256);
+  if (ctx->prm.len <= 16)
+    permute_rec_kernel<1><<<grid, 256, 0, ctx->stream>>>(ctx->d_rec.as<uint8_t>(), ctx->rec_stride, ids, n, ctx->npad,
+                                                         (int)ctx->prm.len, out.as<uint8_t>());
+  else
+    permute_rec_kernel<2><<<grid, 256, 0, ctx->stream>>>(ctx->d_rec.as<uint8_t>(), ctx->rec_stride, ids, n, ctx->npad,
+                                                         (int)ctx->prm.len, out.as<uint8_t>());
   ctx->stats.kernel_launches++;
   HS_CUDA(cudaGetLastError());
   return HS_OK;
 }
 
+// ---- rank path: sort of u16 bucket ranks ----------------------------------------
+// Same upsweep / scan / downsweep structure as above, specialised for 16-bit keys:
+// at most two 8-bit passes, the first takes the implicit index as value, the last
+// writes only the ids.
+constexpr int kRkThreads = 256;
+constexpr int kRkItems = 16;
+constexpr int kRkTile = kRkThreads * kRkItems;  // 4096 ranks per tile
+constexpr int kRkWarps = kRkThreads / 32;
+
+__global__ void __launch_bounds__(kRkThreads)
+rank_upsweep_kernel(const uint16_t *__restrict__ keys, uint64_t n, int shift, uint32_t mask,
+                    uint32_t *__restrict__ tile_hist, uint32_t ntiles) {
+  __shared__ uint32_t s_hist[256];
+  const int tid = threadIdx.x;
+  s_hist[tid] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * kRkTile;
+  if (base + kRkTile <= n) {
+    // whole tile: two 16-byte loads (8 ranks each) per thread
+    const uint4 *src = reinterpret_cast<const uint4 *>(keys + base);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 v = __ldg(src + j * kRkThreads + tid);
+      const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        atomicAdd(&s_hist[(ww[q] >> shift) & mask], 1u);
+        atomicAdd(&s_hist[(ww[q] >> (16 + shift)) & mask], 1u);
+      }
+    }
+  } else {
+    for (int j = 0; j < kRkItems; ++j) {
+      const uint64_t idx = base + (uint64_t)j * kRkThreads + tid;
+      if (idx < n) atomicAdd(&s_hist[((uint32_t)keys[idx] >> shift) & mask], 1u);
+    }
+  }
+  __syncthreads();
+  tile_hist[(uint64_t)tid * ntiles + blockIdx.x] = s_hist[tid];
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kRkThreads, 4)
+rank_downsweep_kernel(const uint16_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
+                      uint16_t *__restrict__ key_out, uint32_t *__restrict__ val_out, uint64_t n, int shift,
+                      uint32_t mask, const uint32_t *__restrict__ tile_off, uint32_t ntiles) {
+  __shared__ uint32_t s_val[kRkTile];            // 16 KB
+  __shared__ uint16_t s_key[kRkTile];            // 8 KB
+  __shared__ uint32_t s_whist[kRkWarps][257];    // per-warp digit counters (+ tail bin)
+  __shared__ uint32_t s_dstart[257];
+  __shared__ uint32_t s_goff[256];
+  __shared__ uint32_t s_warp[kRkWarps];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int i = tid; i < kRkWarps * 257; i += kRkThreads) (&s_whist[0][0])[i] = 0;
+  __syncthreads();
+
+  const uint64_t tile_base = (uint64_t)blockIdx.x * kRkTile;
+  const uint64_t warp_base = tile_base + (uint64_t)wid * (32 * kRkItems);
+
+  uint32_t key[kRkItems];
+  uint32_t lp[kRkItems];
+#pragma unroll
+  for (int j = 0; j < kRkItems; ++j) {
+    const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
+    key[j] = idx < n ? (uint32_t)key_in[idx] : 0xffffffffu;
+  }
+#pragma unroll
+  for (int j = 0; j < kRkItems; ++j) {
+    const uint32_t d = key[j] != 0xffffffffu ? ((key[j] >> shift) & mask) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t pre = s_whist[wid][d];
+    __syncwarp();
+    lp[j] = pre + __popc(peers & lt_mask);
+    if ((peers & lt_mask) == 0) s_whist[wid][d] = pre + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int w = 0; w < kRkWarps; ++w) {
+    const uint32_t c = s_whist[w][tid];
+    s_whist[w][tid] = cnt;
+    cnt += c;
+  }
+  uint32_t total_valid;
+  const uint32_t dstart = block_exclusive_scan_256<kRkWarps>(cnt, s_warp, total_valid);
+  s_dstart[tid] = dstart;
+  s_goff[tid] = tile_off[(uint64_t)tid * ntiles + blockIdx.x] - dstart;  // dst = goff[d] + p (mod 2^32)
+  if (tid == 0) {
+    s_dstart[256] = total_valid;
+    uint32_t run = 0;
+    for (int w = 0; w < kRkWarps; ++w) {
+      const uint32_t c = s_whist[w][256];
+      s_whist[w][256] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int j = 0; j < kRkItems; ++j) {
+    const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
+    const uint32_t d = key[j] != 0xffffffffu ? ((key[j] >> shift) & mask) : 256u;
+    const uint32_t p = lp[j] + s_dstart[d] + s_whist[wid][d];
+    s_key[p] = (uint16_t)key[j];
+    s_val[p] = FIRST ? (uint32_t)idx : (idx < n ? val_in[idx] : 0u);
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int j = 0; j < kRkItems; ++j) {
+    const uint32_t p = (uint32_t)j * kRkThreads + tid;
+    if (p < total_valid) {
+      const uint32_t k = s_key[p];
+      const uint32_t dst = s_goff[(k >> shift) & mask] + p;
+      key_out[dst] = (uint16_t)k;  // (the last pass's sorted ranks give the bucket boundaries)
+      val_out[dst] = s_val[p];
+    }
+  }
+}
+
+// Bucket boundaries from the sorted ranks: slot r starts at the first position whose rank
+// is >= r (empty slots get start == end); *nb counts the non-empty slots.
+__global__ void __launch_bounds__(256)
+rank_bounds_kernel(const uint16_t *__restrict__ sorted, uint64_t n, uint32_t nr, uint32_t *__restrict__ bstart,
+                   unsigned int *__restrict__ nb) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool head = false;
+  if (i < n) {
+    const int k = (int)sorted[i];
+    const int prev = i ? (int)sorted[i - 1] : -1;
+    head = k != prev;
+    for (int r = prev + 1; r <= k; ++r) bstart[r] = (uint32_t)i;
+    if (i == n - 1)
+      for (uint32_t r = (uint32_t)k + 1; r <= nr; ++r) bstart[r] = (uint32_t)n;
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, head);
+  if (m && (threadIdx.x & 31) == 0) atomicAdd(nb, (unsigned int)__popc(m));
+}
+
+// Rank path of build_table_index: two-pass (or one-pass) sort of the table's u16 ranks,
+// bucket boundaries from the rank histogram (one slot per possible key string).
+static int build_table_index_ranks(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cudaEvent_t ev_group_end) {
+  const uint64_t n = ctx->N;
+  SortScratch &S = ctx->sort;
+  TableIndex &T = ctx->tables[table];
+  const uint32_t nr = ctx->rank_nr[table];
+  const uint32_t KW = ctx->key_words;
+  const uint16_t *ranks = ctx->d_ranks.as<uint16_t>() + (size_t)table * ctx->npad;
+  HS_TRY(T.sorted_ids.reserve(sizeof(uint32_t) * n));
+  HS_TRY(S.vals_alt.reserve(sizeof(uint32_t) * n));
+  HS_TRY(S.keys_alt[0].reserve(sizeof(uint16_t) * n + 16));
+  HS_TRY(S.keys_cur[0].reserve(sizeof(uint16_t) * n + 16));
+  const uint32_t ntiles = (uint32_t)((n + kRkTile - 1) / kRkTile);
+  HS_TRY(S.tile_hist.reserve(sizeof(uint32_t) * ((uint64_t)ntiles * 256 + 1)));
+  uint32_t *tile_hist = S.tile_hist.as<uint32_t>();
+  uint32_t *ids = T.sorted_ids.as<uint32_t>();
+  uint32_t *vtmp = S.vals_alt.as<uint32_t>();
+  uint16_t *ktmp = S.keys_alt[0].as<uint16_t>();
+  uint16_t *ksorted = S.keys_cur[0].as<uint16_t>();
+  while (ctx->ev_pool.size() < 8) {
+    cudaEvent_t e;
+    HS_CUDA(cudaEventCreate(&e));
+    ctx->ev_pool.push_back(e);
+  }
+  int hibits = 0;
+  while (((uint64_t)256 << hibits) < nr) ++hibits;
+  const int npass = nr > 256 ? 2 : 1;
+  for (int pi = 0; pi < npass; ++pi) {
+    cudaEvent_t *pe = &ctx->ev_pool[4 * pi];
+    const int shift = 8 * pi;
+    const uint32_t mask = pi == 0 ? 0xffu : ((1u << hibits) - 1u);
+    const uint16_t *kin = pi == 0 ? ranks : ktmp;
+    HS_CUDA(cudaEventRecord(pe[0], ctx->stream));
+    rank_upsweep_kernel<<<ntiles, kRkThreads, 0, ctx->stream>>>(kin, n, shift, mask, tile_hist, ntiles);
+    ctx->stats.kernel_launches++;
+    HS_CUDA(cudaEventRecord(pe[1], ctx->stream));
+    HS_TRY(exclusive_scan_u32(ctx, tile_hist, tile_hist, (uint64_t)ntiles * 256, nullptr));
+    HS_CUDA(cudaEventRecord(pe[2], ctx->stream));
+    if (npass == 1)
+      rank_downsweep_kernel<true, true><<<ntiles, kRkThreads, 0, ctx->stream>>>(kin, nullptr, ksorted, ids, n, shift, mask, tile_hist, ntiles);
+    else if (pi == 0)
+      rank_downsweep_kernel<true, false><<<ntiles, kRkThreads, 0, ctx->stream>>>(kin, nullptr, ktmp, vtmp, n, shift, mask, tile_hist, ntiles);
+    else
+      rank_downsweep_kernel<false, true><<<ntiles, kRkThreads, 0, ctx->stream>>>(kin, vtmp, ksorted, ids, n, shift, mask, tile_hist, ntiles);
+    ctx->stats.kernel_launches++;
+    ctx->stats.sort_passes++;
+    HS_CUDA(cudaGetLastError());
+    HS_CUDA(cudaEventRecord(pe[3], ctx->stream));
+  }
+  HS_CUDA(cudaEventRecord(ev_sort_end, ctx->stream));
+
+  // bucket boundaries from the sorted ranks
+  HS_TRY(T.bstart.reserve(sizeof(uint32_t) * ((uint64_t)nr + 1)));
+  HS_TRY(S.or_and.reserve(sizeof(unsigned long long) * 2 * kMaxKeyWords));
+  unsigned int *d_nb = S.or_and.as<unsigned int>();
+  HS_CUDA(cudaMemsetAsync(d_nb, 0, sizeof(unsigned int), ctx->stream));
+  rank_bounds_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ksorted, n, nr, T.bstart.as<uint32_t>(), d_nb);
+  ctx->stats.kernel_launches++;
+  HS_TRY(T.ukeys.reserve(sizeof(uint64_t) * KW * (uint64_t)nr));
+  HS_CUDA(cudaMemcpyAsync(T.ukeys.p, ctx->h_rkeys[table].data(), sizeof(uint64_t) * KW * nr, cudaMemcpyHostToDevice,
+                          ctx->stream));
+  unsigned int h_nb = 0;
+  HS_CUDA(cudaMemcpyAsync(&h_nb, d_nb, sizeof h_nb, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaEventRecord(ev_group_end, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  T.nb = h_nb;
+  T.nslots = nr;
+  for (int pi = 0; pi < npass; ++pi) {
+    cudaEvent_t *pe = &ctx->ev_pool[4 * pi];
+    float a = 0.f, b = 0.f, c = 0.f;
+    cudaEventElapsedTime(&a, pe[0], pe[1]);
+    cudaEventElapsedTime(&b, pe[1], pe[2]);
+    cudaEventElapsedTime(&c, pe[2], pe[3]);
+    ctx->stats.ms_sort_upsweep += a;
+    ctx->stats.ms_sort_scan += b;
+    ctx->stats.ms_sort_downsweep += c;
+  }
+  HS_TRY(build_code_store(ctx, ids, T.codes_sorted));
+  return HS_OK;
+}
+
 int build_table_index(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cudaEvent_t ev_group_end) {
+  if (ctx->rank_mode) return build_table_index_ranks(ctx, table, ev_sort_end, ev_group_end);
   KeyPtrs sorted;
   HS_TRY(sort_table(ctx, table, &sorted));
   HS_CUDA(cudaEventRecord(ev_sort_end, ctx->stream));

@@ -20,6 +20,8 @@
 // and distances are bit-exact.
 #include <math.h>
 
+#include <algorithm>
+
 #include "verify.cuh"
 
 namespace hs {
@@ -29,10 +31,12 @@ template <int KW>
 __global__ void probe_kernel(const uint64_t *__restrict__ qkeys /* [Q][KW] of this table */,
                              const uint8_t *__restrict__ qvalid, uint32_t Q,
                              const uint64_t *__restrict__ ukeys /* [KW][nb] */, uint64_t nb,
-                             const uint32_t *__restrict__ bstart, uint2 *__restrict__ qrange) {
+                             const uint32_t *__restrict__ bstart, uint2 *__restrict__ qrange,
+                             uint32_t *__restrict__ qrank) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
   uint2 r = make_uint2(0u, 0u);
+  uint32_t slot = 0xffffffffu;
   if (qvalid[q] && nb > 0) {
     uint64_t k[KW];
 #pragma unroll
@@ -55,23 +59,28 @@ __global__ void probe_kernel(const uint64_t *__restrict__ qkeys /* [Q][KW] of th
       bool eq = true;
 #pragma unroll
       for (int w = 0; w < KW; ++w) eq = eq && (ukeys[(uint64_t)w * nb + lo] == k[w]);
-      if (eq) r = make_uint2(bstart[lo], bstart[lo + 1]);
+      if (eq) {
+        r = make_uint2(bstart[lo], bstart[lo + 1]);
+        slot = (uint32_t)lo;
+      }
     }
   }
   qrange[q] = r;
+  qrank[q] = slot;
 }
 
 int launch_probe(hs_ctx *ctx, uint32_t table, const uint64_t *d_qkeys, const uint8_t *d_qvalid, uint32_t Q,
-                 uint2 *d_qrange) {
+                 uint2 *d_qrange, uint32_t *d_qrank) {
   if (Q == 0) return HS_OK;
   const TableIndex &T = ctx->tables[table];
   const unsigned grid = (Q + 127) / 128;
   const uint64_t *qk = d_qkeys + (size_t)table * Q * ctx->key_words;
   const uint8_t *qv = d_qvalid + (size_t)table * Q;
   uint2 *qr = d_qrange + (size_t)table * Q;
+  uint32_t *qs = d_qrank + (size_t)table * Q;
 #define HS_PROBE(KWV)                                                                                      \
-  probe_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(qk, qv, Q, T.ukeys.as<uint64_t>(), T.nb,                \
-                                                   T.bstart.as<uint32_t>(), qr)
+  probe_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(qk, qv, Q, T.ukeys.as<uint64_t>(), T.nslots,            \
+                                                   T.bstart.as<uint32_t>(), qr, qs)
   switch (ctx->key_words) {
     case 1: HS_PROBE(1); break;
     case 2: HS_PROBE(2); break;
@@ -310,110 +319,201 @@ __device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t 
   }
 }
 
-__global__ void __launch_bounds__(128) exact_kernel(ExactArgs a) {
-  // the 20x8 embedding table and the 20x20 integer metric live in shared memory:
-  // every thread walks different rows, which thrashes L1 when read from global
+// `len` bytes at an arbitrarily aligned address as little-endian words: aligned 32-bit
+// loads realigned by funnel shifts (reads at most 7 bytes past the end; buffers carry slack).
+template <int NWORDS>
+__device__ __forceinline__ void load_bytes(const uint8_t *p, int len, uint32_t (&w)[NWORDS]) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+  const int nw = (len + 3) >> 2;
+  uint32_t prev = __ldg(base);
+#pragma unroll
+  for (int i = 0; i < NWORDS; ++i) {
+    w[i] = 0u;
+    if (i < nw) {
+      const uint32_t next = __ldg(base + i + 1);
+      w[i] = __funnelshift_r(prev, next, sh);
+      prev = next;
+    }
+  }
+}
+// fragment record (16-byte aligned): NV 16-byte loads
+template <int NV>
+__device__ __forceinline__ void load_record(const uint8_t *p, uint32_t (&w)[4 * NV]) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 r = __ldg(src + v);
+    w[4 * v + 0] = r.x;
+    w[4 * v + 1] = r.y;
+    w[4 * v + 2] = r.z;
+    w[4 * v + 3] = r.w;
+  }
+}
+
+constexpr int kExactThreads = 256;
+constexpr int kSqStride = 10;  // doubles per residue-pair row (8 + 2 padding: spreads rows over the banks)
+
+// One thread per survivor, grid-stride.  NV: 16-byte words of residue codes per fragment
+// (len <= 16 * NV).  The member's codes (and, on the rank path, its bucket ranks) come from
+// its fragment record: one 32-byte sector per survivor.  Distances between residue strings
+// read the squared coordinate differences from a shared residue-pair table, in the
+// reference's summation order; hits are appended with one atomic per warp.
+template <int NV>
+__global__ void __launch_bounds__(kExactThreads) exact_kernel(ExactArgs a) {
+  __shared__ __align__(16) double s_sq[HS_AA * HS_AA * kSqStride];  // (table[x][j] - table[q][j])^2
   __shared__ __align__(16) double s_table[HS_AA * HS_CDIM];
   __shared__ int s_metric[HS_AA * HS_AA];
   for (int i = threadIdx.x; i < HS_AA * HS_CDIM; i += blockDim.x) s_table[i] = a.table64[i];
   for (int i = threadIdx.x; i < HS_AA * HS_AA; i += blockDim.x) s_metric[i] = a.metric_tab[i];
+  if (a.metric != HS_METRIC_BLOSUM_INT) {
+    for (int i = threadIdx.x; i < HS_AA * HS_AA * HS_CDIM; i += blockDim.x) {
+      const int j = i % HS_CDIM, pair = i / HS_CDIM;
+      const int qc = pair / HS_AA, xc = pair - qc * HS_AA;
+      // r = a - b; r * r (motif_both_points.cpp:180-181); (-r) * (-r) is the same double
+      const double r = __dsub_rn(a.table64[xc * HS_CDIM + j], a.table64[qc * HS_CDIM + j]);
+      s_sq[pair * kSqStride + j] = __dmul_rn(r, r);
+    }
+  }
   __syncthreads();
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.nsurv) return;
-  const Survivor s = a.surv[i];
-  const uint32_t *ids = a.sorted_ids[s.table];
-  const uint64_t id = ids ? (uint64_t)ids[s.pos] : (uint64_t)s.pos;
-  const uint8_t *mc = a.codes + id * a.len;
-  uint64_t qid = s.pad ? (uint64_t)a.qlist_mma[s.query] : (uint64_t)s.query;
-  if (a.mode == kModeAllPairs && !(qid < id)) return;  // each unordered pair once
-  const uint8_t *qc = nullptr;
-  if (a.mode == kModeSelfJoin) {
-    qid = ids ? (uint64_t)ids[s.query] : (uint64_t)s.query;
-    qc = a.codes + qid * a.len;
-  } else if (a.mode == kModeAllPairs && a.q64 == nullptr && a.qcodes == nullptr) {
-    qc = a.codes + qid * a.len;  // all pairs of the DB: the query is a DB fragment
-  } else if (a.qcodes) {
-    qc = a.qcodes + qid * a.len;
-  }
-  // dense query that is an embedded residue string: take its rows from the shared table
-  const bool dense = a.q64 && a.mode != kModeSelfJoin && !(a.qrow && a.qrow[qid] && qc);
-
-  double d2;
-  bool hit;
-  if (a.metric == HS_METRIC_BLOSUM_INT) {
-    int d = 0;
-    for (int p = 0; p < a.len; ++p) d += s_metric[(int)qc[p] * HS_AA + (int)mc[p]];
-    d2 = (double)d;
-    hit = d <= (int)a.R;
-  } else {
-    // PairwiseDistance_square (motif_both_points.cpp:176-183): r = a - b; dis += r * r,
-    // strictly sequential, separate multiply and add
-    double dis = 0.0;
-    if (dense) {
-      const double2 *qp = reinterpret_cast<const double2 *>(a.q64 + qid * a.dim);
-      for (int p = 0; p < a.len; ++p) {
-        const double2 *row = reinterpret_cast<const double2 *>(s_table + (int)mc[p] * HS_CDIM);
-#pragma unroll
-        for (int j = 0; j < HS_CDIM / 2; ++j) {
-          const double2 t = row[j];
-          const double2 q = __ldg(qp + p * (HS_CDIM / 2) + j);
-          const double r0 = __dsub_rn(t.x, q.x);
-          dis = __dadd_rn(dis, __dmul_rn(r0, r0));
-          const double r1 = __dsub_rn(t.y, q.y);
-          dis = __dadd_rn(dis, __dmul_rn(r1, r1));
+  const int lane = threadIdx.x & 31;
+  const int len = a.len;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  // all lanes of a warp run the same number of iterations (warp-level hit aggregation)
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < a.nsurv;
+       i0 += stride) {
+    const unsigned long long i = i0 + lane;
+    bool hit = false;
+    double d2 = 0.0;
+    uint64_t id = 0, qid = 0;
+    Survivor s;
+    s.table = 0;
+    if (i < a.nsurv) {
+      s = a.surv[i];
+      const uint32_t *ids = a.sorted_ids[s.table];
+      id = ids ? (uint64_t)__ldg(ids + s.pos) : (uint64_t)s.pos;
+      qid = s.pad ? (uint64_t)a.qlist_mma[s.query] : (uint64_t)s.query;
+      bool live = !(a.mode == kModeAllPairs && !(qid < id));  // each unordered pair once
+      const uint8_t *recp = a.rec + id * a.rec_stride;
+      uint32_t mw[4 * NV], qw[4 * NV];
+      if (live) load_record<NV>(recp, mw);
+      bool have_qc = false;
+      if (live) {
+        if (a.mode == kModeSelfJoin) {
+          qid = ids ? (uint64_t)__ldg(ids + s.query) : (uint64_t)s.query;
+          load_record<NV>(a.rec + qid * a.rec_stride, qw);
+          have_qc = true;
+        } else if (a.mode == kModeAllPairs && a.q64 == nullptr && a.qcodes == nullptr) {
+          load_record<NV>(a.rec + qid * a.rec_stride, qw);  // all pairs of the DB: the query is a DB fragment
+          have_qc = true;
+        } else if (a.qcodes) {
+          load_bytes<4 * NV>(a.qcodes + qid * len, len, qw);
+          have_qc = true;
         }
       }
-    } else {
-      for (int p = 0; p < a.len; ++p) {
-        const double2 *row = reinterpret_cast<const double2 *>(s_table + (int)mc[p] * HS_CDIM);
-        const double2 *qrow = reinterpret_cast<const double2 *>(s_table + (int)qc[p] * HS_CDIM);
+      // dense query that is an embedded residue string: its rows come from the shared table
+      const bool dense = a.q64 && a.mode != kModeSelfJoin && !(a.qrow && a.qrow[qid] && have_qc);
+      if (live) {
+        if (a.metric == HS_METRIC_BLOSUM_INT) {
+          int d = 0;
 #pragma unroll
-        for (int j = 0; j < HS_CDIM / 2; ++j) {
-          const double2 t = row[j], q = qrow[j];
-          const double r0 = __dsub_rn(t.x, q.x);
-          dis = __dadd_rn(dis, __dmul_rn(r0, r0));
-          const double r1 = __dsub_rn(t.y, q.y);
-          dis = __dadd_rn(dis, __dmul_rn(r1, r1));
+          for (int p = 0; p < 16 * NV; ++p)
+            if (p < len) {
+              const int xc = (mw[p >> 2] >> (8 * (p & 3))) & 0xff, qc = (qw[p >> 2] >> (8 * (p & 3))) & 0xff;
+              d += s_metric[qc * HS_AA + xc];
+            }
+          d2 = (double)d;
+          hit = d <= (int)a.R;
+        } else {
+          // PairwiseDistance_square (motif_both_points.cpp:176-183): r = a - b; dis += r * r,
+          // strictly sequential, separate multiply and add
+          double dis = 0.0;
+          if (dense) {
+            const double2 *qp = reinterpret_cast<const double2 *>(a.q64 + qid * a.dim);
+#pragma unroll
+            for (int p = 0; p < 16 * NV; ++p) {
+              if (p >= len) break;
+              const int xc = (mw[p >> 2] >> (8 * (p & 3))) & 0xff;
+              const double2 *row = reinterpret_cast<const double2 *>(s_table + xc * HS_CDIM);
+#pragma unroll
+              for (int j = 0; j < HS_CDIM / 2; ++j) {
+                const double2 t = row[j];
+                const double2 q = __ldg(qp + p * (HS_CDIM / 2) + j);
+                const double r0 = __dsub_rn(t.x, q.x);
+                dis = __dadd_rn(dis, __dmul_rn(r0, r0));
+                const double r1 = __dsub_rn(t.y, q.y);
+                dis = __dadd_rn(dis, __dmul_rn(r1, r1));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int p = 0; p < 16 * NV; ++p)
+              if (p < len) {
+                const int xc = (mw[p >> 2] >> (8 * (p & 3))) & 0xff, qc = (qw[p >> 2] >> (8 * (p & 3))) & 0xff;
+                const double2 *row = reinterpret_cast<const double2 *>(s_sq + (qc * HS_AA + xc) * kSqStride);
+#pragma unroll
+                for (int j = 0; j < HS_CDIM / 2; ++j) {
+                  const double2 t = row[j];
+                  dis = __dadd_rn(dis, t.x);
+                  dis = __dadd_rn(dis, t.y);
+                }
+              }
+          }
+          d2 = dis;
+          if (a.predicate == HS_PRED_D2_LE_R2) hit = dis <= __dmul_rn(a.R, a.R);
+          else hit = !(sqrt(dis) > a.R);
+        }
+      }
+      if (hit && a.mode == kModeSelfJoin) {
+        uf_union(a.parent, (uint32_t)qid, (uint32_t)id);
+        atomicAdd(a.edge_count, 1ull);
+        hit = false;
+      }
+      if (hit && a.mode == kModeSearch) {
+        // label[] (motif_both_points.cpp:232-238): the pair was already handled if an
+        // earlier table put this fragment in the query's bucket.
+        if (a.qrank) {
+          const uint16_t *rk = reinterpret_cast<const uint16_t *>(recp + a.rec_rank_off);
+          for (uint32_t l = 0; l < s.table; ++l) {
+            const uint32_t qr = __ldg(a.qrank + (size_t)l * a.Q + qid);
+            if (qr != 0xffffffffu && qr == (uint32_t)__ldg(rk + l)) hit = false;
+          }
+        } else {
+          for (uint32_t l = 0; l < s.table && hit; ++l) {
+            if (!a.qvalid[(size_t)l * a.Q + qid]) continue;
+            bool same = true;
+            for (int w = 0; w < a.key_words; ++w)
+              same = same && (a.keys[l][(uint64_t)w * a.N + id] == a.qkeys[((size_t)l * a.Q + qid) * a.key_words + w]);
+            if (same) hit = false;
+          }
         }
       }
     }
-    d2 = dis;
-    if (a.predicate == HS_PRED_D2_LE_R2) hit = dis <= __dmul_rn(a.R, a.R);
-    else hit = !(sqrt(dis) > a.R);
-  }
-  if (!hit) return;
-
-  if (a.mode == kModeSelfJoin) {
-    uf_union(a.parent, (uint32_t)qid, (uint32_t)id);
-    atomicAdd(a.edge_count, 1ull);
-    return;
-  }
-  if (a.mode == kModeSearch) {
-    // label[] (motif_both_points.cpp:232-238): the pair was already handled if an
-    // earlier table put this fragment in the query's bucket.
-    for (uint32_t l = 0; l < s.table; ++l) {
-      if (!a.qvalid[(size_t)l * a.Q + qid]) continue;
-      bool same = true;
-      for (int w = 0; w < a.key_words; ++w)
-        same = same && (a.keys[l][(uint64_t)w * a.N + id] == a.qkeys[((size_t)l * a.Q + qid) * a.key_words + w]);
-      if (same) return;
+    const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+    if (hm) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.hit_count, (unsigned long long)__popc(hm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const unsigned long long idx = base + __popc(hm & ((1u << lane) - 1u));
+      if (hit && idx < a.hit_cap) {
+        hs_hit h;
+        h.query = (uint32_t)qid;
+        h.table_first = a.mode == kModeSearch ? s.table : 0u;
+        h.db_id = a.id_base + id;
+        h.dist2 = d2;
+        a.hits[idx] = h;
+      }
     }
-  }
-  const unsigned long long idx = atomicAdd(a.hit_count, 1ull);
-  if (idx < a.hit_cap) {
-    hs_hit h;
-    h.query = (uint32_t)qid;
-    h.table_first = a.mode == kModeSearch ? s.table : 0u;
-    h.db_id = a.id_base + id;
-    h.dist2 = d2;
-    a.hits[idx] = h;
   }
 }
 
 int launch_exact(hs_ctx *ctx, const ExactArgs &args) {
   if (args.nsurv == 0) return HS_OK;
-  const unsigned grid = (unsigned)((args.nsurv + 127) / 128);
-  exact_kernel<<<grid, 128, 0, ctx->stream>>>(args);
+  const unsigned long long want = (args.nsurv + kExactThreads - 1) / kExactThreads;
+  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->num_sms * 8);
+  if (args.len <= 16) exact_kernel<1><<<grid, kExactThreads, 0, ctx->stream>>>(args);
+  else exact_kernel<2><<<grid, kExactThreads, 0, ctx->stream>>>(args);
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;

@@ -50,7 +50,7 @@ struct FilterArgs {
 };
 
 int launch_probe(hs_ctx *ctx, uint32_t table, const uint64_t *d_qkeys, const uint8_t *d_qvalid, uint32_t Q,
-                 uint2 *d_qrange);
+                 uint2 *d_qrange, uint32_t *d_qrank);
 int launch_build_tq_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, float *d_tq);
 int launch_detect_query_codes(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint8_t *d_qcodes, uint8_t *d_qrow);
 int launch_build_tq_int(hs_ctx *ctx, const uint8_t *d_qcodes, uint32_t Q, float *d_tq);
@@ -104,6 +104,9 @@ struct ExactArgs {
   double R;
   const uint32_t *const *sorted_ids;  // per table (nullptr entry: identity)
   const uint8_t *codes;               // [N][len]
+  const uint8_t *rec;                 // fragment records [N][rec_stride]: codes, then (rank path) u16 ranks
+  uint32_t rec_stride, rec_rank_off;
+  const uint32_t *qrank;              // rank path: [L][Q] bucket slot of every query (dedup); else nullptr
   uint64_t N, id_base;
   const double *table64;
   const int32_t *metric_tab;          // [20][20]

@@ -112,7 +112,8 @@ typedef struct {
   uint32_t key_words;       /* 64-bit words per packed key */
   uint32_t sort_passes;     /* radix passes actually executed (all tables) */
   uint32_t kernel_launches; /* kernels launched by the most recent call */
-  uint32_t reserved;
+  uint32_t rank_path;       /* 1: buckets are dense u16 ranks of the key strings (<= 65536 possible
+                               strings per table); 0: packed KW*64-bit key path */
   float ms_hash, ms_sort, ms_group, ms_permute;      /* index build stages */
   float ms_sort_upsweep, ms_sort_scan, ms_sort_downsweep; /* inside ms_sort, per kernel family */
   float ms_qhash, ms_probe, ms_filter, ms_exact, ms_hitsort; /* search stages */

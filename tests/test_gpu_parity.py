@@ -398,3 +398,41 @@ def test_tensor_filter_huge_threshold(oracle):
     want = oracle.bruteforce(oracle.embed(codes, tab), oracle.embed(qcodes, tab), 1e300, pred=1, cap=n * q + 10)
     assert hits_as_tuples(got, False) == hits_as_tuples(want, False)
     h.close()
+
+
+# ---------------------------------------------------------------- dense bucket ranks vs packed keys
+@pytest.mark.parametrize("length,K,L,W,R", [(10, 4, 4, 50.0, 30.0), (10, 2, 6, 30.0, 25.0), (25, 3, 2, 80.0, 60.0),
+                                            (10, 4, 20, 50.0, 30.0), (16, 4, 3, 50.0, 40.0)])
+def test_rank_path_equals_packed_key_path(oracle, monkeypatch, length, K, L, W, R):
+    """The u16 bucket-rank index (<= 65536 possible key strings per table) and the packed
+    64-bit-key index must agree on keys, bucket order, table sizes and hits."""
+    codes = planted_families(30011, length, seed=5)
+    qcodes = planted_queries(codes, 200, seed=6)
+    res = []
+    for no_rank in ("0", "1"):
+        monkeypatch.setenv("HS_NO_RANK", no_rank)
+        h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS | hb.HS_FLAG_HASH_AUDIT)
+        h.load_fragments(codes)
+        h.hash()
+        st = h.stats()
+        assert st.residual_flips == 0
+        if no_rank == "1":
+            assert st.rank_path == 0
+        elif length <= 10 or K <= 3:
+            assert st.rank_path == 1   # few enough possible key strings: dense ranks in use
+        keys = [h.keys(l) for l in range(L)]
+        h.build_index()
+        sizes = h.table_sizes()
+        tabs = [h.table(l) for l in range(L)]
+        hits = h.search_codes(qcodes)
+        labels = h.cluster() if L <= 6 else None
+        res.append((keys, sizes, tabs, hits_as_tuples(hits), labels))
+        h.close()
+    (k0, s0, t0, h0, l0), (k1, s1, t1, h1, l1) = res
+    for l in range(L):
+        assert np.array_equal(k0[l], k1[l])
+        assert np.array_equal(t0[l][0], t1[l][0]) and np.array_equal(t0[l][1], t1[l][1])
+    assert np.array_equal(s0, s1)
+    assert len(h0) > 0 and h0 == h1
+    if l0 is not None:
+        assert np.array_equal(l0, l1)
