@@ -113,6 +113,7 @@ struct hs_ctx {
   hs::DevBuf d_a64, d_b64;   // f64 [L][K][DIM], [L][K]
   hs::DevBuf d_T32;          // f32 [L][len][20][Kp]  residue-projection partial sums
   hs::DevBuf d_b32, d_eps32; // f32 [L][Kp]
+  std::vector<float> h_b32, h_eps32;  // host copies (passed to the hash kernel as parameters)
   uint32_t Kp = 0;           // K rounded up to a multiple of 4
   uint32_t tpc = 1;          // tables per hash chunk
   uint32_t nchunks = 1;      // hash chunks

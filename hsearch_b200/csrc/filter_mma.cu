@@ -55,13 +55,16 @@ constexpr int kMmaUnitRing = 4;      // units published ahead by the scheduler
 constexpr int kMmaUnitBatch = 4;     // consecutive units taken per atomic (keeps B resident)
 constexpr int kMmaMaxCodeRing = 8;   // tiles of residue codes in flight (bulk async copies)
 constexpr int kMmaM = 128;           // members per tile (UMMA M)
-constexpr int kMmaN = 256;           // accumulator columns per stage (UMMA N max)
-constexpr int kMmaAccStages = 2;
+#ifndef HS_MMA_N
+#define HS_MMA_N 256
+#endif
+constexpr int kMmaN = HS_MMA_N;      // accumulator columns per stage (<= 256, the UMMA N limit)
+constexpr int kMmaAccStages = 512 / kMmaN;  // the stages fill the 512 TMEM columns
 constexpr uint32_t kMmaTmemCols = 512;
 constexpr int kMmaMaxStages = 4;     // A stages
 constexpr int kMmaRowRing = 8;       // >= A stages + accumulator stages
-constexpr int kMmaStageCap = 96;     // survivors staged per epilogue warp between flushes
-constexpr int kMmaSlots = 4;         // rows resolved per round of the rare path
+constexpr int kMmaStageCap = 128;    // survivors staged per epilogue warp between flushes
+constexpr int kMmaFlushAt = 64;      // staged survivors that trigger a flush (one global atomic each)
 constexpr int kMmaAGroupBytes = 2048;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,6 +73,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#ifdef HS_MBAR_HINT
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -77,8 +81,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n"
       "}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin on issue slots
+      : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint
       : "memory");
+#else
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -213,14 +228,6 @@ struct MmaArgs {
   unsigned long long *surv_count;
 };
 
-// One row of 16 accumulators handed to the warp for resolution.
-struct __align__(16) MmaSlot {
-  float v[16];
-  float rt;
-  uint32_t pos;
-  uint32_t pad[2];
-};
-
 struct MmaShared {
   uint64_t a_full[kMmaMaxStages], a_empty[kMmaMaxStages];
   uint64_t t_full[kMmaAccStages], t_empty[kMmaAccStages];
@@ -230,11 +237,13 @@ struct MmaShared {
   uint32_t uring[kMmaUnitRing];
   uint32_t tmem_base;
   uint32_t pad;
-  uint4 tab16[HS_AA];
+  // every embedding row stored 8 times, copy j in bank group j (16 bytes = 4 banks): lane i of a
+  // quarter warp reads copy i & 7, so the 8 lanes of one LDS.128 phase never share a bank
+  uint4 tab16[HS_AA][8];
   float nx32[HS_AA];
   float rowthr[kMmaRowRing][kMmaM];
   Survivor stage[kMmaEpiWarps][kMmaStageCap];
-  MmaSlot slot[kMmaEpiWarps][kMmaSlots];  // rows that reached their threshold, being resolved
+  uint32_t wcount[kMmaEpiWarps];  // survivors staged per epilogue warp
 };
 
 // Every role walks the same sequence of units, published by the scheduler lane
@@ -287,10 +296,9 @@ filter_mma_kernel(MmaArgs a) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < HS_AA) {
-    sh.tab16[tid] = a.tab16[tid];
-    sh.nx32[tid] = a.nx32[tid];
-  }
+  if (tid < HS_AA * 8) sh.tab16[tid >> 3][tid & 7] = a.tab16[tid >> 3];
+  if (tid < HS_AA) sh.nx32[tid] = a.nx32[tid];
+  if (tid < kMmaEpiWarps) sh.wcount[tid] = 0u;
   if (warp == kMmaIssueWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&sh.tmem_base)),
                  "r"(kMmaTmemCols)
@@ -424,9 +432,12 @@ filter_mma_kernel(MmaArgs a) {
         float nx = 0.f;
 #pragma unroll
         for (int p = 0; p < LENB; ++p) {
+#ifdef HS_MMA_PROF
+          if (a.debug & 4u) break;  // experiment: no A build
+#endif
           if (p < len) {
             const int c = min((int)code[p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
-            *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = sh.tab16[c];
+            *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = sh.tab16[c][lane & 7];
             nx += sh.nx32[c];
           }
         }
@@ -458,11 +469,23 @@ filter_mma_kernel(MmaArgs a) {
       PROF_DECL(m_groups);
       const uint32_t sA_u32 = smem_addr(sA), sB_u32 = smem_addr(sB);
       const int ksteps = kp >> 4;
+      PROF_DECL(m_unit);
+      PROF_DECL(m_issue);
+      PROF_DECL(m_commit);
+#ifdef HS_MMA_PROF
+      const long long m_start = clock64();
+#endif
       for (uint32_t k = 0;; ++k) {
+#ifdef HS_MMA_PROF
+        const long long _mu0 = clock64();
+#endif
         const uint32_t u = mma_next_unit(sh, k, lane, false);
         if (u >= nunits) break;
         const MmaUnit un = a.units[u];
         const MmaItem it = a.items[un.item];
+#ifdef HS_MMA_PROF
+        m_unit += (unsigned long long)(clock64() - _mu0) + (it.table == 0xffffffffu ? 1 : 0);
+#endif
         if (un.item != prev_item) {
           {
             PROF_T0();
@@ -500,13 +523,26 @@ filter_mma_kernel(MmaArgs a) {
             const uint32_t d_tmem = tmem_base + as * kMmaN;
             const uint32_t a0 = sA_u32 + s * a_stage_bytes;
             const uint32_t b0 = sB_u32 + (g * kMmaN >> 3) * 128u;
+#ifdef HS_MMA_PROF
+            const long long _mi0 = clock64();
+#endif
             for (int kk = 0; kk < ksteps; ++kk) {
               const uint64_t ad = mma_desc(a0 + (uint32_t)kk * 2u * kMmaAGroupBytes, kMmaAGroupBytes, 128u);
               const uint64_t bd = mma_desc(b0 + (uint32_t)kk * 2u * b_lbo, b_lbo, 128u);
+#ifdef HS_MMA_PROF
+              if ((a.debug & 2u) && kk > 0) continue;  // experiment: one MMA per group instead of kp/16
+#endif
               mma_f16_ss(d_tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
             }
+#ifdef HS_MMA_PROF
+            const long long _mi1 = clock64();
+            m_issue += (unsigned long long)(_mi1 - _mi0);
+#endif
             if (g + 1 == ngroups) mma_commit(smem_addr(&sh.a_empty[s]));
             mma_commit(smem_addr(&sh.t_full[as]));
+#ifdef HS_MMA_PROF
+            m_commit += (unsigned long long)(clock64() - _mi1);
+#endif
           }
         }
       }
@@ -515,6 +551,10 @@ filter_mma_kernel(MmaArgs a) {
       PROF_OUT(5, m_wait_t);
       PROF_OUT(6, m_wait_b);
       PROF_OUT(7, m_groups);
+      PROF_OUT(10, m_unit);
+      PROF_OUT(12, m_issue);
+      PROF_OUT(13, m_commit);
+      PROF_OUT(15, (unsigned long long)(clock64() - m_start));
 #endif
     }
     __syncwarp();
@@ -528,10 +568,8 @@ filter_mma_kernel(MmaArgs a) {
     // flush.
     const int quad = warp & 3, sub = warp >> 2;
     const int row = quad * 32 + lane;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     Survivor *stage = sh.stage[warp];
-    MmaSlot *slots = sh.slot[warp];
-    uint32_t wcount = 0;  // staged survivors (warp-uniform)
+    uint32_t *wcount = &sh.wcount[warp];  // staged survivors (entries past the capacity went to global memory)
     uint32_t et = 0, eg = 0;
     PROF_DECL(e_wait_t);
     PROF_DECL(e_ld);
@@ -587,53 +625,39 @@ filter_mma_kernel(MmaArgs a) {
             const float t0 = fmax3(vf[0], vf[1], vf[2]), t1 = fmax3(vf[3], vf[4], vf[5]), t2 = fmax3(vf[6], vf[7], vf[8]);
             const float t3 = fmax3(vf[9], vf[10], vf[11]), t4 = fmax3(vf[12], vf[13], vf[14]);
             const float m = fmaxf(fmax3(t0, t1, t2), fmax3(t3, t4, vf[15]));
-            bool reach = m >= rt;
-            uint32_t lanes = __ballot_sync(0xffffffffu, reach);
+            if (m >= rt) {
+              // a row that reaches its threshold (about 2 % of the rows of a chunk) appends its
+              // passing columns itself: one shared-memory atomic per survivor, no warp-wide round
 #ifdef HS_MMA_PROF
-            const long long _r0 = lanes ? clock64() : 0;
-            const bool _had = lanes != 0;
+              const long long _r0 = clock64();
 #endif
-            while (lanes) {  // rare, warp-uniform: rounds of up to kMmaSlots rows
-              const uint32_t rank = __popc(lanes & lt_mask);
-              if (reach && rank < (uint32_t)kMmaSlots) {
-                MmaSlot *sl = slots + rank;
-                float4 *d = reinterpret_cast<float4 *>(sl->v);
-                d[0] = make_float4(vf[0], vf[1], vf[2], vf[3]);
-                d[1] = make_float4(vf[4], vf[5], vf[6], vf[7]);
-                d[2] = make_float4(vf[8], vf[9], vf[10], vf[11]);
-                d[3] = make_float4(vf[12], vf[13], vf[14], vf[15]);
-                sl->rt = rt;
-                sl->pos = pos;
-                reach = false;
-              }
-              __syncwarp();
-              const uint32_t nrows = min((uint32_t)kMmaSlots, (uint32_t)__popc(lanes));
-              const uint32_t col = (uint32_t)lane & 15u;
-              for (uint32_t r0 = 0; r0 < nrows; r0 += 2) {  // two rows per pass: lanes 0-15 and 16-31
-                const uint32_t si = r0 + ((uint32_t)lane >> 4);
-                const MmaSlot *sl = slots + min(si, (uint32_t)kMmaSlots - 1u);
-                const bool p = si < nrows && col0 + col < ng && sl->v[col] >= sl->rt;
-                const uint32_t mask = __ballot_sync(0xffffffffu, p);
-                if (p) {
-                  Survivor sv;
-                  sv.query = qbase + col0 + col;  // index into the query list; the exact stage resolves it
-                  sv.table = it.table;
-                  sv.pos = sl->pos;
-                  sv.pad = 1;
-                  stage[wcount + __popc(mask & lt_mask)] = sv;
+              // branch-free column mask, one shared-memory atomic reserving all of the row's slots
+              uint32_t pm = 0u;
+#pragma unroll
+              for (int c = 0; c < 16; ++c) pm |= (vf[c] >= rt ? 1u : 0u) << c;
+              const uint32_t ncol = ng - col0;  // valid columns of this chunk (>= 1)
+              if (ncol < 16u) pm &= (1u << ncol) - 1u;
+              uint32_t k = atomicAdd(wcount, (uint32_t)__popc(pm));
+              while (pm) {
+                const uint32_t c = (uint32_t)__ffs((int)pm) - 1u;
+                pm &= pm - 1u;
+                Survivor sv;
+                sv.query = qbase + col0 + c;  // index into the query list; the exact stage resolves it
+                sv.table = it.table;
+                sv.pos = pos;
+                sv.pad = 1;
+                if (k < (uint32_t)kMmaStageCap) {
+                  stage[k] = sv;
+                } else {  // staging buffer full (dense hit regions): straight to the global list
+                  const unsigned long long gi = atomicAdd(a.surv_count, 1ull);
+                  if (gi < a.surv_cap) a.surv[gi] = sv;
                 }
-                wcount += __popc(mask);
-                if (wcount > (uint32_t)(kMmaStageCap - 32)) {
-                  __syncwarp();
-                  wcount = mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
-                }
+                ++k;
               }
-              __syncwarp();  // the slots are rewritten in the next round / next call
-              lanes = __ballot_sync(0xffffffffu, reach);
+#ifdef HS_MMA_PROF
+              e_rare += (unsigned long long)(clock64() - _r0);
+#endif
             }
-#ifdef HS_MMA_PROF
-            if (_had) e_rare += (unsigned long long)(clock64() - _r0);
-#endif
           };
           uint32_t nmine = 0;
           for (uint32_t c = (uint32_t)sub; c < nchunks; c += 4) {
@@ -643,6 +667,9 @@ filter_mma_kernel(MmaArgs a) {
               tc_before();
               mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
             }
+#ifdef HS_MMA_PROF
+            if (!(a.debug & 1u))
+#endif
             scan16(c * 16u);
             ++nmine;
           }
@@ -650,11 +677,21 @@ filter_mma_kernel(MmaArgs a) {
             tc_before();
             mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
           }
+          __syncwarp();
+          const uint32_t wc = *(volatile uint32_t *)wcount;  // warp-uniform
+          if (wc >= (uint32_t)kMmaFlushAt) {
+            mma_flush(stage, min(wc, (uint32_t)kMmaStageCap), a.surv, a.surv_cap, a.surv_count, lane);
+            if (lane == 0) *(volatile uint32_t *)wcount = 0u;
+            __syncwarp();
+          }
         }
       }
     }
     __syncwarp();
-    if (wcount) mma_flush(stage, wcount, a.surv, a.surv_cap, a.surv_count, lane);
+    {
+      const uint32_t wc = min(*(volatile uint32_t *)wcount, (uint32_t)kMmaStageCap);
+      if (wc) mma_flush(stage, wc, a.surv, a.surv_cap, a.surv_count, lane);
+    }
 #ifdef HS_MMA_PROF
     if (tid == 0) {
       PROF_OUT(8, (unsigned long long)(clock64() - e_start));
@@ -876,9 +913,9 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
     fprintf(stderr,
             "[mma prof] grid %u units %u | producer: total %.0f wait_codes %.0f wait_a_empty %.0f bload %.0f | "
             "issuer: wait_a_full %.0f wait_t_empty %.0f wait_b %.0f groups %.0f | epilogue(warp0): total %.0f "
-            "wait_t_full %.0f ld_wait %.0f rare %.0f ld_issue %.0f arrive %.0f unit_fetch %.0f  (cycles per CTA)\n",
+            "wait_t_full %.0f issuer_unit %.0f rare %.0f issuer_mma %.0f issuer_commit %.0f unit_fetch %.0f issuer_total %.0f (cycles per CTA)\n",
             grid, nunits, h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g, h[5] / g, h[6] / g, h[7] / g, h[8] / g,
-            h[9] / g, h[10] / g, h[11] / g, h[12] / g, h[13] / g, h[14] / g);
+            h[9] / g, h[10] / g, h[11] / g, h[12] / g, h[13] / g, h[14] / g, h[15] / g);
   }
 #endif
   HS_CUDA(cudaGetLastError());

@@ -15,8 +15,11 @@ constexpr int kHashThreads = 256;
 
 // counters[0] guard_hits, [1] guard_corrected, [2] key overflow / bucket out of range, [3] residual flips
 // RANK: write dense u16 bucket ranks (and the fragment records) instead of packed keys.
-template <int NQ, int KW, bool RANK>
-__global__ void __launch_bounds__(kHashThreads)
+// REP: copies of every 16-byte table cell (8: copy j lives in bank group j and lane i reads
+// copy i & 7, so the random-row LDS.128 gathers are bank-conflict free; 1: plain layout for
+// tables too large to replicate).  Persistent blocks: the table is staged once per block.
+template <int NQ, int KW, bool RANK, int REP, int NT>
+__global__ void __launch_bounds__(NT)
 hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                  const float *__restrict__ T32,    // [len][20][4*NQ] of this chunk
                  const float *__restrict__ b32,    // [4*NQ]
@@ -26,10 +29,13 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                  HashChunkArgs args, int32_t *__restrict__ buckets_out,
                  unsigned long long *__restrict__ counters) {
   constexpr int P = 4 * NQ;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *sT = reinterpret_cast<float *>(smem_raw);                    // len*20*P floats
-  uint8_t *sC = smem_raw + (size_t)len * HS_AA * P * sizeof(float);   // kHashThreads*len bytes
-  uint8_t *sRec = sC + (size_t)kHashThreads * len;                    // kHashThreads*rec_stride (full_rec)
+  // 16-byte words of the next tile's codes held in registers: NT * 16 * NPF bytes >= NT * len
+  // (the replicated-table path is taken for len <= 16 only)
+  constexpr int NPF = REP > 1 ? 1 : 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *sT = reinterpret_cast<float4 *>(smem_raw);                             // len*20*NQ*REP cells
+  uint8_t *sC = smem_raw + (size_t)len * HS_AA * NQ * REP * sizeof(float4);      // NT*len bytes
+  uint8_t *sRec = sC + (((size_t)NT * len + 15) & ~(size_t)15);                  // NT*rec_stride (full_rec)
 
   const int tid = threadIdx.x;
   const bool full_rec = RANK && args.full_rec;
@@ -37,114 +43,143 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
   {
     const int n4 = len * HS_AA * NQ;
     const float4 *src = reinterpret_cast<const float4 *>(T32);
-    float4 *dst = reinterpret_cast<float4 *>(sT);
-    for (int i = tid; i < n4; i += kHashThreads) dst[i] = src[i];
-  }
-  const uint64_t frag0 = (uint64_t)blockIdx.x * kHashThreads;
-  const uint64_t nfrag = min((uint64_t)kHashThreads, N - frag0);
-  {
-    // tile of code bytes: contiguous in global memory, 16-byte aligned start
-    const uint64_t byte0 = frag0 * (uint64_t)len;
-    const uint32_t nbytes = (uint32_t)(nfrag * (uint64_t)len);
-    const uint32_t nvec = nbytes >> 4;
-    const uint4 *src = reinterpret_cast<const uint4 *>(codes + byte0);
-    uint4 *dst = reinterpret_cast<uint4 *>(sC);
-    for (uint32_t i = tid; i < nvec; i += kHashThreads) dst[i] = __ldg(src + i);
-    for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += kHashThreads) sC[i] = codes[byte0 + i];
-  }
-  if (full_rec) {
-    uint4 *z = reinterpret_cast<uint4 *>(sRec);
-    for (uint32_t i = tid; i < (uint32_t)kHashThreads * RS / 16; i += kHashThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  __syncthreads();
-  if ((uint64_t)tid < nfrag) {
-    const uint64_t frag = frag0 + tid;
-    const uint8_t *myc = sC + tid * len;
-    uint8_t *myrec = sRec + (size_t)tid * RS;
-
-    float acc[P];
-#pragma unroll
-    for (int s = 0; s < P; ++s) acc[s] = 0.f;
-    for (int pos = 0; pos < len; ++pos) {
-      const int c = myc[pos];
-      if (full_rec) myrec[pos] = (uint8_t)c;
-      const float4 *row = reinterpret_cast<const float4 *>(sT + (pos * HS_AA + c) * P);
-      // the quads of row c are stored rotated by c/2 (setup_projection), so that lanes with
-      // different residues hit different banks when they all want logical quad j
-      const int rot = c >> 1;
-#pragma unroll
-      for (int j = 0; j < NQ; ++j) {
-        const float4 v = row[(j + rot) & (NQ - 1)];
-        acc[4 * j + 0] += v.x;
-        acc[4 * j + 1] += v.y;
-        acc[4 * j + 2] += v.z;
-        acc[4 * j + 3] += v.w;
+    if (REP > 1) {
+      // replicated layout: undo the row rotation of the global table, so that the hot loop
+      // addresses quad j with a compile-time offset
+      for (int i = tid; i < n4 * REP; i += NT) {
+        const int cell = i / REP, j = cell % NQ, rc = cell / NQ, c = rc % HS_AA;
+        sT[i] = src[rc * NQ + ((j + (c >> 1)) & (NQ - 1))];
       }
+    } else {
+      for (int i = tid; i < n4; i += NT) sT[i] = src[i];
     }
+  }
+  const float4 *myT = sT + (REP > 1 ? (tid & (REP - 1)) : 0);
+  unsigned int my_guard = 0, my_corr = 0, my_over = 0;
+  const uint64_t ntiles = (N + NT - 1) / NT;
+  const uint64_t total_bytes = N * (uint64_t)len;
+  // the tile's code bytes are contiguous in global memory (16-byte aligned start): whole 16-byte
+  // words are prefetched into registers one tile ahead, the ragged end of the DB byte by byte
+  uint4 pf[NPF];
+  auto prefetch = [&](uint64_t tile) {
+    const uint64_t byte0 = tile * NT * (uint64_t)len;
+#pragma unroll
+    for (int v = 0; v < NPF; ++v) {
+      const uint64_t off = byte0 + ((uint64_t)v * NT + tid) * 16;
+      pf[v] = make_uint4(0u, 0u, 0u, 0u);
+      if (tile < ntiles && ((uint64_t)v * NT + tid) * 16 < (uint64_t)NT * len && off + 16 <= total_bytes)
+        pf[v] = __ldg(reinterpret_cast<const uint4 *>(codes + off));
+    }
+  };
+  prefetch(blockIdx.x);
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t frag0 = tile * NT;
+    const uint64_t nfrag = min((uint64_t)NT, N - frag0);
+    __syncthreads();  // the previous tile's sC / sRec are no longer read
+    {
+      const uint64_t byte0 = frag0 * (uint64_t)len;
+      const uint32_t nbytes = (uint32_t)(nfrag * (uint64_t)len);
+#pragma unroll
+      for (int v = 0; v < NPF; ++v) {
+        const uint32_t o = ((uint32_t)v * NT + tid) * 16u;
+        if (o + 16u <= nbytes) *reinterpret_cast<uint4 *>(sC + o) = pf[v];
+      }
+      for (uint32_t i = (nbytes & ~15u) + tid; i < nbytes; i += NT) sC[i] = codes[byte0 + i];
+    }
+    if (full_rec) {
+      uint4 *z = reinterpret_cast<uint4 *>(sRec);
+      for (uint32_t i = tid; i < (uint32_t)NT * RS / 16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    prefetch(tile + gridDim.x);
+    __syncthreads();
+    if ((uint64_t)tid < nfrag) {
+      const uint64_t frag = frag0 + tid;
+      const uint8_t *myc = sC + tid * len;
+      uint8_t *myrec = sRec + (size_t)tid * RS;
 
-    KeyBuilder<KW> kb;
-    kb.reset();
-    uint32_t tix = 0;
-    bool in_range = true;
-    int t = 0, k = 0;  // table within chunk, projection within table (uniform across the block)
-    unsigned int my_guard = 0, my_corr = 0, my_over = 0;
+      float acc[P];
 #pragma unroll
-    for (int s = 0; s < P; ++s) {
-      if (t < args.ntab && k < K) {
-        const float val = acc[s] + __ldg(b32 + s);
-        const float tt = val * invW;
-        const float f = floorf(tt);
-        int bucket = (int)f;
-        const float e = __ldg(eps32 + s);
-        if ((tt - f) < e || ((f + 1.0f) - tt) < e) {
-          const int l = args.l0 + t;
-          const int ex = exact_bucket_codes(myc, len, table64, a64 + ((size_t)l * K + k) * dim,
-                                            b64[l * K + k], W);
-          ++my_guard;
-          if (ex != bucket) ++my_corr;
-          bucket = ex;
+      for (int s = 0; s < P; ++s) acc[s] = 0.f;
+      for (int pos = 0; pos < len; ++pos) {
+        const int c = myc[pos];
+        if (full_rec) myrec[pos] = (uint8_t)c;
+        const float4 *row = myT + (size_t)(pos * HS_AA + c) * (NQ * REP);
+        // the quads of row c are stored rotated by c/2 (setup_projection): spreads the lanes of
+        // the unreplicated layout over the banks when they all want logical quad j
+        const int rot = REP > 1 ? 0 : (c >> 1);
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          const float4 v = row[((j + rot) & (NQ - 1)) * REP];
+          acc[4 * j + 0] += v.x;
+          acc[4 * j + 1] += v.y;
+          acc[4 * j + 2] += v.z;
+          acc[4 * j + 3] += v.w;
         }
-        if (RANK) in_range = rank_tuple_push(tix, bucket, args.lo[s], args.rng[s]) && in_range;
-        else kb.push_int(bucket);
-        if (buckets_out) buckets_out[(frag * L + (args.l0 + t)) * K + k] = bucket;
-        if (k == K - 1) {
-          if (RANK) {
-            uint16_t rank = 0;
-            if (in_range) rank = __ldg(args.lut[t] + tix);
-            else ++my_over;
-            args.ranks[t][frag] = rank;
-            if (full_rec)
-              *reinterpret_cast<uint16_t *>(myrec + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
-            else
-              *reinterpret_cast<uint16_t *>(args.rec + frag * RS + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
-            tix = 0;
-            in_range = true;
-          } else {
-            if (kb.nchars > 16 * KW) ++my_over;
-            uint64_t *dst = args.keys[t];
+      }
+
+      KeyBuilder<KW> kb;
+      kb.reset();
+      uint32_t tix = 0;
+      bool in_range = true;
+      int t = 0, k = 0;  // table within chunk, projection within table (uniform across the block)
 #pragma unroll
-            for (int w = 0; w < KW; ++w) dst[(uint64_t)w * N + frag] = kb.w[w];
-            kb.reset();
+      for (int s = 0; s < P; ++s) {
+        if (t < args.ntab && k < K) {
+          const float val = acc[s] + args.b32[s];
+          const float tt = val * invW;
+          const float f = floorf(tt);
+          int bucket = (int)f;
+          const float e = args.eps32[s];
+          if ((tt - f) < e || ((f + 1.0f) - tt) < e) {
+            const int l = args.l0 + t;
+            const int ex = exact_bucket_codes(myc, len, table64, a64 + ((size_t)l * K + k) * dim,
+                                              b64[l * K + k], W);
+            ++my_guard;
+            if (ex != bucket) ++my_corr;
+            bucket = ex;
+          }
+          if (RANK) in_range = rank_tuple_push(tix, bucket, args.lo[s], args.rng[s]) && in_range;
+          else kb.push_int(bucket);
+          if (buckets_out) buckets_out[(frag * L + (args.l0 + t)) * K + k] = bucket;
+          if (k == K - 1) {
+            if (RANK) {
+              uint16_t rank = 0;
+              if (in_range) rank = __ldg(args.lut[t] + tix);
+              else ++my_over;
+              args.ranks[t][frag] = rank;
+              if (full_rec)
+                *reinterpret_cast<uint16_t *>(myrec + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
+              else
+                *reinterpret_cast<uint16_t *>(args.rec + frag * RS + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
+              tix = 0;
+              in_range = true;
+            } else {
+              if (kb.nchars > 16 * KW) ++my_over;
+              uint64_t *dst = args.keys[t];
+#pragma unroll
+              for (int w = 0; w < KW; ++w) dst[(uint64_t)w * N + frag] = kb.w[w];
+              kb.reset();
+            }
           }
         }
-      }
-      if (++k == Kp) {
-        k = 0;
-        ++t;
+        if (++k == Kp) {
+          k = 0;
+          ++t;
+        }
       }
     }
-    if (my_guard) atomicAdd(counters + 0, (unsigned long long)my_guard);
-    if (my_corr) atomicAdd(counters + 1, (unsigned long long)my_corr);
-    if (my_over) atomicAdd(counters + 2, (unsigned long long)my_over);
+    if (full_rec) {
+      // the tile's records are contiguous in global memory: coalesced 16-byte copies
+      __syncthreads();
+      const uint32_t nvec = (uint32_t)(nfrag * RS / 16);
+      const uint4 *src = reinterpret_cast<const uint4 *>(sRec);
+      uint4 *dst = reinterpret_cast<uint4 *>(args.rec + frag0 * RS);
+      for (uint32_t i = tid; i < nvec; i += NT) dst[i] = src[i];
+    }
   }
-  if (full_rec) {
-    // the block's records are contiguous in global memory: coalesced 16-byte copies
-    __syncthreads();
-    const uint32_t nvec = (uint32_t)(nfrag * RS / 16);
-    const uint4 *src = reinterpret_cast<const uint4 *>(sRec);
-    uint4 *dst = reinterpret_cast<uint4 *>(args.rec + frag0 * RS);
-    for (uint32_t i = tid; i < nvec; i += kHashThreads) dst[i] = src[i];
-  }
+  if (my_guard) atomicAdd(counters + 0, (unsigned long long)my_guard);
+  if (my_corr) atomicAdd(counters + 1, (unsigned long long)my_corr);
+  if (my_over) atomicAdd(counters + 2, (unsigned long long)my_over);
 }
 
 // Fragment records without ranks: codes copied into rows of rec_stride bytes (zero padded).
@@ -240,18 +275,30 @@ __global__ void hash_queries_kernel(const double *__restrict__ q64, uint32_t Q, 
 }
 
 // ---- host side ---------------------------------------------------------------
-template <int NQ, int KW, bool RANK>
-static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
-                            unsigned long long *counters) {
+constexpr int kHashRepThreads = 768;            // one persistent block per SM on the replicated-table path
+constexpr size_t kHashRepBudget = 200 * 1024;   // replicated table + tile buffers
+
+static size_t hash_smem_bytes(const hs_ctx *ctx, int NQ, int rep, int nt, bool full_rec) {
+  const size_t len = ctx->prm.len;
+  return len * HS_AA * NQ * rep * sizeof(float4) + (((size_t)nt * len + 15) & ~(size_t)15) +
+         (full_rec ? (size_t)nt * ctx->rec_stride : 0);
+}
+
+template <int NQ, int KW, bool RANK, int REP, int NT>
+static int launch_fast_rep(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
+                           unsigned long long *counters) {
   const int P = 4 * NQ;
   const int len = (int)ctx->prm.len;
-  const size_t smem = (size_t)len * HS_AA * P * sizeof(float) + (size_t)kHashThreads * len +
-                      (args.full_rec ? (size_t)kHashThreads * args.rec_stride : 0);
-  auto kern = hash_fast_kernel<NQ, KW, RANK>;
+  const size_t smem = hash_smem_bytes(ctx, NQ, REP, NT, args.full_rec != 0);
+  auto kern = hash_fast_kernel<NQ, KW, RANK, REP, NT>;
   if (smem > 48 * 1024) HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)((ctx->N + kHashThreads - 1) / kHashThreads);
+  int per_sm = 1;
+  HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  if (per_sm < 1) per_sm = 1;
+  const uint64_t ntiles = (ctx->N + NT - 1) / NT;
+  const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm);
   const float *T = ctx->d_T32.as<float>() + (size_t)chunk * len * HS_AA * P;
-  kern<<<grid, kHashThreads, smem, ctx->stream>>>(
+  kern<<<grid, NT, smem, ctx->stream>>>(
       ctx->d_codes.as<uint8_t>(), ctx->N, len, T, ctx->d_b32.as<float>() + (size_t)chunk * P,
       ctx->d_eps32.as<float>() + (size_t)chunk * P, (float)(1.0 / ctx->prm.W), ctx->d_table64.as<double>(),
       ctx->d_a64.as<double>(), ctx->d_b64.as<double>(), ctx->prm.W, (int)ctx->prm.K, (int)ctx->Kp,
@@ -259,6 +306,15 @@ static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, i
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;
+}
+
+template <int NQ, int KW, bool RANK>
+static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
+                            unsigned long long *counters) {
+  // 768 threads leave 85 registers per thread: 16 accumulators without spills
+  if (NQ <= 4 && ctx->prm.len <= 16 && hash_smem_bytes(ctx, NQ, 8, kHashRepThreads, args.full_rec != 0) <= kHashRepBudget)
+    return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads>(ctx, chunk, args, buckets, counters);
+  return launch_fast_rep<NQ, KW, RANK, 1, kHashThreads>(ctx, chunk, args, buckets, counters);
 }
 
 template <int NQ>
@@ -294,9 +350,7 @@ int launch_hash_fast(hs_ctx *ctx, bool want_buckets) {
   const uint32_t K = ctx->prm.K;
   // the single-chunk rank launch writes whole records through shared memory; otherwise the
   // records must exist before the per-table ranks are stored into them
-  const bool full_rec = ctx->rank_mode && ctx->nchunks == 1 &&
-                        (size_t)ctx->prm.len * HS_AA * 4 * ctx->nq * sizeof(float) +
-                                (size_t)kHashThreads * (ctx->prm.len + ctx->rec_stride) <= 200 * 1024;
+  const bool full_rec = ctx->rank_mode && ctx->nchunks == 1 && hash_smem_bytes(ctx, (int)ctx->nq, 1, kHashThreads, true) <= 200 * 1024;
   if (ctx->rank_mode) {
     HS_TRY(ctx->d_ranks.reserve(sizeof(uint16_t) * (size_t)ctx->prm.L * ctx->npad + 64));  // table stride npad: 16-byte aligned rows
     if (full_rec) HS_TRY(ctx->d_rec.reserve((size_t)ctx->N * ctx->rec_stride + 64));
@@ -319,6 +373,10 @@ int launch_hash_fast(hs_ctx *ctx, bool want_buckets) {
       } else {
         args.keys[t] = ctx->d_keys[l].as<uint64_t>();
       }
+    }
+    for (uint32_t sl = 0; sl < 4 * ctx->nq; ++sl) {
+      args.b32[sl] = ctx->h_b32[(size_t)chunk * 4 * ctx->nq + sl];
+      args.eps32[sl] = ctx->h_eps32[(size_t)chunk * 4 * ctx->nq + sl];
     }
     args.rec = ctx->d_rec.as<uint8_t>();
     args.rec_stride = ctx->rec_stride;
@@ -578,6 +636,8 @@ int setup_projection(hs_ctx *ctx, const double *a, const double *b) {
   HS_CUDA(cudaMemcpyAsync(ctx->d_eps32.p, eps32.data(), eps32.size() * sizeof(float), cudaMemcpyHostToDevice,
                           ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+  ctx->h_b32 = b32;
+  ctx->h_eps32 = eps32;
   ctx->have_projection = true;
   ctx->hashed = false;
   ctx->indexed = false;

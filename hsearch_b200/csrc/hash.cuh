@@ -89,6 +89,7 @@ struct HashChunkArgs {
   uint16_t *ranks[8];        // per table of the chunk: [N]
   const uint16_t *lut[8];    // per table of the chunk
   int lo[32], rng[32];       // per projection slot of the chunk: smallest bucket, bucket count
+  float b32[32], eps32[32];  // per projection slot: offset b and guard band (FP32 fast path)
   uint8_t *rec;              // fragment records [N][rec_stride]
   uint32_t rec_stride, rec_rank_off;
   int full_rec;              // 1: this launch writes whole records (codes + ranks) through shared memory
