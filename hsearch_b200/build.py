@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhsearch_b200.so")
-CU = ["api.cu", "hash.cu", "radix_sort.cu", "verify.cu", "filter_tc.cu", "filter_mma.cu", "cluster.cu", "extract.cu"]
+CU = ["api.cu", "hash.cu", "radix_sort.cu", "verify.cu", "filter_tc.cu", "filter_mma.cu", "cluster.cu", "extract.cu", "sequence.cu"]
 CPP = ["tables.cpp", "comm.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -57,7 +57,7 @@ def build(force=False, verbose=False, ptxas_verbose=False):
     return LIB
 
 
-CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints"]
+CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints", "hclust2", "hclust3"]
 BIN = os.path.join(HERE, "bin")
 
 
@@ -70,10 +70,12 @@ def build_cli(force=False, verbose=False):
     os.makedirs(BIN, exist_ok=True)
     procs = []
     for name in CLI:
-        src = os.path.join(src_dir, name + ".cpp")
+        # hclust3 is hclust2 with one more progress line (hclust3.cpp:77)
+        src = os.path.join(src_dir, ("hclust2" if name == "hclust3" else name) + ".cpp")
         out = os.path.join(BIN, name)
         if force or _newer(out, [src, LIB] + hdrs):
-            cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-o", out, src, "-L" + HERE, "-lhsearch_b200",
+            cmd = [cxx, "-O2", "-std=c++17", "-Wall"] + (["-DHCLUST3"] if name == "hclust3" else []) + [
+                   "-o", out, src, "-L" + HERE, "-lhsearch_b200",
                    "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + "/usr/local/cuda/lib64"]
             if verbose:
                 print(" ".join(cmd))

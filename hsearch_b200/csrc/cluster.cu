@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "hash.cuh"
 #include "internal.cuh"
 
 namespace hs {
@@ -232,6 +233,187 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
   ctx->stats.n_edges = h_edges;
   ctx->stats.ms_filter = ms_filter;
   ctx->stats.ms_exact = ms_exact;
+  ctx->stats.ms_total = ev_ms(ev[0], ev[7]);
+  return HS_OK;
+}
+
+
+// ---- CL1: greedy centre clustering (hclust2.cpp:86-151, hclust3.cpp:87-152) -----------
+// L rounds; round l walks the buckets of table l.  Inside a bucket (members in ascending
+// id = insertion order) the centres are the members already marked 1, then every
+// unprocessed member (0), in order, joins the first centre within R (sqrt predicate,
+// hclust2.cpp:64-71,119-120) or becomes a candidate centre itself.  Points that joined (2)
+// leave all later rounds.  A live point sits in exactly one bucket per round and a bucket
+// touches only its own members, so buckets are independent: one warp per bucket, the
+// reference's sequential order kept inside the bucket (32 members at a time: each lane
+// scans the existing centres, then the still-unmatched lanes are resolved in lane order).
+constexpr int kGreedyThreads = 128;
+
+template <int NV>
+__device__ __forceinline__ void greedy_load(const uint8_t *rec, uint32_t RS, uint32_t id, uint32_t (&w)[4 * NV]) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(rec + (uint64_t)id * RS);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 r = __ldg(src + v);
+    w[4 * v + 0] = r.x;
+    w[4 * v + 1] = r.y;
+    w[4 * v + 2] = r.z;
+    w[4 * v + 3] = r.w;
+  }
+}
+
+// PairwiseDistance(a, b) <= R: FP32 bound first (provably never rejects a pair the FP64
+// computation accepts, filter_threshold()), then the reference's FP64 sum and sqrt.
+template <int NV>
+__device__ __forceinline__ bool greedy_near(const uint32_t (&x)[4 * NV], const uint32_t (&c)[4 * NV], int len,
+                                            const float *s_d32, const double *s_sq, float thr, double R) {
+  float f = 0.f;
+#pragma unroll
+  for (int p = 0; p < 16 * NV; ++p)
+    if (p < len) f += s_d32[((c[p >> 2] >> (8 * (p & 3))) & 0xff) * HS_AA + ((x[p >> 2] >> (8 * (p & 3))) & 0xff)];
+  if (f > thr) return false;
+  double dis = 0.0;
+#pragma unroll
+  for (int p = 0; p < 16 * NV; ++p)
+    if (p < len) {
+      const int xc = (x[p >> 2] >> (8 * (p & 3))) & 0xff, cc = (c[p >> 2] >> (8 * (p & 3))) & 0xff;
+      const double *row = s_sq + (cc * HS_AA + xc) * HS_CDIM;
+#pragma unroll
+      for (int j = 0; j < HS_CDIM; ++j) dis = __dadd_rn(dis, row[j]);
+    }
+  return !(sqrt(dis) > R);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kGreedyThreads)
+greedy_round_kernel(const uint32_t *__restrict__ bstart, uint64_t nslots, const uint32_t *__restrict__ ids,
+                    const uint8_t *__restrict__ rec, uint32_t RS, int len, const double *__restrict__ table64,
+                    const float *__restrict__ dsq32, float thr, double R, uint32_t round, uint8_t *__restrict__ merged,
+                    uint32_t *__restrict__ center_of, uint32_t *__restrict__ round_of,
+                    uint32_t *__restrict__ centers /* [N] scratch, one slice per bucket */) {
+  __shared__ double s_sq[HS_AA * HS_AA * HS_CDIM];  // (table[x][j] - table[c][j])^2, r * r as in hclust2.cpp:67-68
+  __shared__ float s_d32[HS_AA * HS_AA];
+  for (int i = threadIdx.x; i < HS_AA * HS_AA * HS_CDIM; i += blockDim.x) {
+    const int j = i % HS_CDIM, pair = i / HS_CDIM;
+    const int cc = pair / HS_AA, xc = pair - cc * HS_AA;
+    const double r = __dsub_rn(table64[xc * HS_CDIM + j], table64[cc * HS_CDIM + j]);
+    s_sq[i] = __dmul_rn(r, r);
+  }
+  for (int i = threadIdx.x; i < HS_AA * HS_AA; i += blockDim.x) s_d32[i] = dsq32[i];
+  __syncthreads();
+  const uint64_t b = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= nslots) return;
+  const uint32_t s = bstart[b], e = bstart[b + 1];
+  if (e <= s) return;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t *cen = centers + s;
+  uint32_t nc = 0;
+  // centres so far: the members already marked 1, in member order
+  for (uint32_t base = s; base < e; base += 32) {
+    const uint32_t i = base + lane;
+    const uint32_t id = i < e ? ids[i] : 0u;
+    const bool isc = i < e && merged[id] == 1;
+    const uint32_t m = __ballot_sync(0xffffffffu, isc);
+    if (isc) cen[nc + __popc(m & lt)] = id;
+    nc += __popc(m);
+  }
+  __syncwarp();
+  for (uint32_t base = s; base < e; base += 32) {
+    const uint32_t i = base + lane;
+    const uint32_t id = i < e ? ids[i] : 0u;
+    const bool live = i < e && merged[id] == 0;
+    uint32_t x[4 * NV];
+    if (live) greedy_load<NV>(rec, RS, id, x);
+    int found = -1;
+    if (live) {
+      for (uint32_t j = 0; j < nc; ++j) {
+        uint32_t c[4 * NV];
+        greedy_load<NV>(rec, RS, cen[j], c);
+        if (greedy_near<NV>(x, c, len, s_d32, s_sq, thr, R)) {
+          found = (int)j;
+          break;
+        }
+      }
+    }
+    // members that matched no existing centre, in order: the first becomes a candidate
+    // centre, the later ones are tested against it (first centre within R wins)
+    uint32_t rem = __ballot_sync(0xffffffffu, live && found < 0);
+    while (rem) {
+      const int k = __ffs((int)rem) - 1;
+      uint32_t c[4 * NV];
+#pragma unroll
+      for (int v = 0; v < 4 * NV; ++v) c[v] = __shfl_sync(0xffffffffu, x[v], k);
+      if (lane == k) cen[nc] = id;
+      rem &= ~(1u << k);
+      const bool join = ((rem >> lane) & 1u) && greedy_near<NV>(x, c, len, s_d32, s_sq, thr, R);
+      if (join) found = (int)nc;
+      rem &= ~__ballot_sync(0xffffffffu, join);
+      ++nc;
+    }
+    __syncwarp();
+    if (live && found >= 0) {
+      const uint32_t c = cen[found];
+      merged[id] = 2;          // has been added to another cluster
+      merged[c] = 1;           // to be the real centre (hclust2.cpp:122)
+      center_of[id] = c;
+      round_of[id] = round;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void greedy_init_kernel(uint64_t n, uint8_t *merged, uint32_t *center_of, uint32_t *round_of) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  merged[i] = 0;
+  center_of[i] = (uint32_t)i;
+  round_of[i] = 0xffffffffu;
+}
+
+int greedy_cluster_impl(hs_ctx *ctx, uint32_t *center_out, uint32_t *round_out, uint8_t *state_out) {
+  const uint64_t N = ctx->N;
+  const uint32_t L = ctx->prm.L;
+  stats_begin(ctx);
+  if (N == 0) return HS_OK;
+  if (ctx->prm.metric != HS_METRIC_EUCLID_FP64) {
+    set_error("hs_greedy_cluster: Euclidean metric only (hclust2.cpp:64-71)");
+    return HS_ERR_UNSUPPORTED;
+  }
+  cudaEvent_t *ev = ctx->ev;
+  HS_CUDA(cudaEventRecord(ev[0], ctx->stream));
+  HS_TRY(ensure_records(ctx));
+  HS_TRY(ctx->d_parent.reserve(sizeof(uint32_t) * 3 * N + N + 64));
+  uint32_t *center_of = ctx->d_parent.as<uint32_t>();
+  uint32_t *round_of = center_of + N;
+  uint32_t *centers = round_of + N;
+  uint8_t *merged = reinterpret_cast<uint8_t *>(centers + N);
+  greedy_init_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(N, merged, center_of, round_of);
+  ctx->stats.kernel_launches++;
+  const float thr = filter_threshold(ctx);
+  for (uint32_t l = 0; l < L; ++l) {
+    const TableIndex &T = ctx->tables[l];
+    if (T.nslots == 0) continue;
+    const uint64_t nthreads = T.nslots * 32;
+    const unsigned grid = (unsigned)((nthreads + kGreedyThreads - 1) / kGreedyThreads);
+    if (ctx->prm.len <= 16)
+      greedy_round_kernel<1><<<grid, kGreedyThreads, 0, ctx->stream>>>(
+          T.bstart.as<uint32_t>(), T.nslots, T.sorted_ids.as<uint32_t>(), ctx->d_rec.as<uint8_t>(), ctx->rec_stride,
+          (int)ctx->prm.len, ctx->d_table64.as<double>(), ctx->d_dsq32.as<float>(), thr, ctx->prm.R, l, merged,
+          center_of, round_of, centers);
+    else
+      greedy_round_kernel<2><<<grid, kGreedyThreads, 0, ctx->stream>>>(
+          T.bstart.as<uint32_t>(), T.nslots, T.sorted_ids.as<uint32_t>(), ctx->d_rec.as<uint8_t>(), ctx->rec_stride,
+          (int)ctx->prm.len, ctx->d_table64.as<double>(), ctx->d_dsq32.as<float>(), thr, ctx->prm.R, l, merged,
+          center_of, round_of, centers);
+    HS_CUDA(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+  }
+  if (center_out) HS_CUDA(cudaMemcpyAsync(center_out, center_of, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (round_out) HS_CUDA(cudaMemcpyAsync(round_out, round_of, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (state_out) HS_CUDA(cudaMemcpyAsync(state_out, merged, N, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaEventRecord(ev[7], ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.ms_total = ev_ms(ev[0], ev[7]);
   return HS_OK;
 }

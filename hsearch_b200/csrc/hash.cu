@@ -185,7 +185,7 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
 // Fragment records without ranks: codes copied into rows of rec_stride bytes (zero padded).
 __global__ void __launch_bounds__(kHashThreads)
 build_records_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len, uint32_t RS, uint8_t *__restrict__ rec) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint8_t *sRec = smem_raw;
   const int tid = threadIdx.x;
   const uint64_t frag0 = (uint64_t)blockIdx.x * kHashThreads;

@@ -214,3 +214,54 @@ class HSearch:
         out = np.zeros(self.num_fragments, dtype=np.uint32)
         check(self.lib.hs_cluster(self.ctx, ptr(out, C.c_uint32)))
         return out
+
+    def greedy_cluster(self):
+        """hclust2's Clustering(): (centre of every fragment, round it joined in, merged[] flags)."""
+        n = self.num_fragments
+        center = np.zeros(n, dtype=np.uint32)
+        rnd = np.zeros(n, dtype=np.uint32)
+        state = np.zeros(n, dtype=np.uint8)
+        check(self.lib.hs_greedy_cluster(self.ctx, ptr(center, C.c_uint32), ptr(rnd, C.c_uint32), ptr(state, C.c_uint8)))
+        return center, rnd, state
+
+    # ---- sequence front ends ------------------------------------------------
+    @staticmethod
+    def _concat(seqs):
+        data = b"".join(s.encode() if isinstance(s, str) else s for s in seqs)
+        start = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum([len(s) for s in seqs], out=start[1:])
+        return data, start
+
+    def kmer3_klsh(self, proteins, w, t, b, want_features=False):
+        """3-mer histograms + KLSH values of a list of protein strings (pcluster PreClustering)."""
+        data, start = self._concat(proteins)
+        n = len(proteins)
+        bits = w.shape[0]
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        feat = np.zeros((n, 512), dtype=np.uint32) if want_features else None
+        hv = np.zeros(n, dtype=np.uint64)
+        valid = np.zeros(n, dtype=np.uint8)
+        fixed = C.c_uint64(0)
+        check(self.lib.hs_kmer3_klsh(self.ctx, data, ptr(start, C.c_uint64), n, ptr(w, C.c_double), ptr(t, C.c_double),
+                                     ptr(b, C.c_double), bits, ptr(feat, C.c_uint32) if want_features else None,
+                                     ptr(hv, C.c_uint64), ptr(valid, C.c_uint8), C.byref(fixed)))
+        return hv, valid, feat, fixed.value
+
+    def orf6(self, dnas):
+        """Six-frame translation of a list of DNA strings: per sequence the list of the six
+        translated frames (the reference keeps those of length >= 6)."""
+        data, start = self._concat(dnas)
+        n = len(dnas)
+        cap = 2 * int(start[-1]) + 6 * n
+        out = C.create_string_buffer(max(cap, 1))
+        ln = np.zeros((n, 6), dtype=np.int32)
+        check(self.lib.hs_orf6(self.ctx, data, ptr(start, C.c_uint64), n, out, cap, ptr(ln, C.c_int32)))
+        raw = out.raw
+        res = []
+        for s in range(n):
+            ls = int(start[s + 1] - start[s])
+            base = 2 * int(start[s]) + 6 * s
+            res.append([raw[base + f * (ls // 3 + 1): base + f * (ls // 3 + 1) + int(ln[s, f])].decode() for f in range(6)])
+        return res

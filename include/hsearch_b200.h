@@ -229,6 +229,50 @@ int hs_bruteforce_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hi
  * (host) = smallest local id of the fragment's component. */
 int hs_cluster(hs_ctx_t *ctx, uint32_t *label_out);
 
+/* Greedy centre clustering, Clustering() of hclust2.cpp:86-151 (= hclust3.cpp:87-152):
+ * L rounds, round l over the buckets of table l; inside a bucket, in member (id) order,
+ * every unprocessed fragment joins the first centre within R (sqrt predicate) or becomes
+ * a candidate centre.  center_out[N]: the centre holding each fragment (itself when it
+ * heads a cluster or stayed alone); round_out[N] (optional): the round in which it joined
+ * (0xffffffff for cluster heads) -- a cluster's member list in the reference's order is
+ * its head, then its members by (round, id); state_out[N] (optional): the reference's
+ * merged[] flags (0 unprocessed, 1 centre, 2 joined).  Euclidean metric only. */
+int hs_greedy_cluster(hs_ctx_t *ctx, uint32_t *center_out, uint32_t *round_out, uint8_t *state_out);
+
+/* ---- sequence front ends (E4, E5, E6, KL1) ------------------------------------ */
+/* ProteinDB::ReadFASTAFile (pcluster/src/pcluster/read_proteins.cpp:6-41) over a FASTA text
+ * held in memory (host only).  residues[res_cap] receives the kept letters of all sequences
+ * back to back, start[start_cap] the nseq+1 boundaries, name_begin/name_len[name_cap] the
+ * byte range of each header's name inside `text` (header up to the first space).  The
+ * reference's quirks are kept: a name per header line but a sequence only when non-empty
+ * (*nnames may exceed *nseq); non-amino-acid letters become AA20[rand() % 20].  Any output
+ * buffer may be NULL / too small: the counts are still returned, with HS_ERR_CAPACITY. */
+int hs_parse_fasta(const char *text, uint64_t nbytes, char *residues, uint64_t res_cap, uint64_t *start,
+                   uint64_t start_cap, uint64_t *name_begin, uint32_t *name_len, uint64_t name_cap, uint32_t *nseq,
+                   uint32_t *nnames, uint64_t *nres);
+/* KLSH::KLSH (pcluster/src/pcluster/lsh.cpp:17-38): w[bits][feat] ~ N(0, sigma^2 as the
+ * STANDARD DEVIATION), t[bits] ~ U[-1,1), b[bits] ~ U[0,2pi) from a default-constructed
+ * std::default_random_engine (fixed seed: identical in every instance).  Host, libstdc++. */
+int hs_klsh_generate(uint32_t feat, uint32_t bits, double sigma, double *w, double *t, double *b);
+/* PreClustering (pcluster/src/pcluster/pcluster.cpp:11-35): per protein the 512-bin histogram
+ * of reduced-alphabet 3-mers (Kmer2Integer, util.hpp:244-250) and its KLSH value
+ * (GetHashValue, lsh.cpp:40-49; bit i = [cos(w_i.p + b_i) + t_i >= 0]).  residues: letters of
+ * all proteins back to back, start[nprot+1].  feat_out[nprot][512] and valid_out[nprot]
+ * (0: shorter than 3 residues, skipped by the reference) are optional.  Bits whose
+ * cos(..)+t lies within 1e-9 of zero are recomputed on the host with libm's cos (the
+ * function the reference calls); *n_host_fixed counts those proteins. */
+int hs_kmer3_klsh(hs_ctx_t *ctx, const char *residues, const uint64_t *start, uint32_t nprot, const double *w,
+                  const double *t, const double *b, uint32_t bits, uint32_t *feat_out, uint64_t *hash_out,
+                  uint8_t *valid_out, uint64_t *n_host_fixed);
+/* ORF::orf6 (orf/orf.cc:39-74, genetic code orf/orf.h:28-31): the six reading frames of
+ * every DNA sequence (0-2 forward, 3-5 reverse complement), each translated codon by codon
+ * up to its first stop.  Frame f of sequence s is written at
+ * aa_out + 2*start[s] + 6*s + f*(len_s/3 + 1); aa_len[nseq][6] = residues written (the
+ * frame is an ORF of the reference when >= 6, orf.cc:58).  aa_cap >= 2*start[nseq] + 6*nseq.
+ * Letters other than A, C, G, T -> HS_ERR_INVALID (ERROR_INFO in the reference). */
+int hs_orf6(hs_ctx_t *ctx, const char *dna, const uint64_t *start, uint32_t nseq, char *aa_out, uint64_t aa_cap,
+            int32_t *aa_len);
+
 /* ---- multi-GPU -------------------------------------------------- */
 /* Join an NCCL communicator (nccl_unique_id: the 128-byte ncclUniqueId made by
  * rank 0).  After this, hs_search_* on every rank takes the queries of rank 0

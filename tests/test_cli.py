@@ -162,3 +162,54 @@ def test_search_pipeline_matches_reference(tmp_path, W):
     sa, sb = strip_volatile(a[1]), strip_volatile(b[1])
     sb = [l.replace("our.", "ref.") for l in sb]
     assert sa == sb
+
+
+# ---------------------------------------------------------------- hclust2 / hclust3 (CL1)
+HCL = ["hclust2", "hclust3"]
+needs_ref_hcl = pytest.mark.skipif(not all(_have(REF, p) for p in HCL), reason="oracle/_ref/bin/hclust2 not built")
+
+
+@needs_ref_hcl
+@pytest.mark.parametrize("prog", HCL)
+@pytest.mark.parametrize("args", [[], ["-help"], ["-?"], ["-about"], ["-k", "x"], ["-kmers", "x", "-l", "10"],
+                                  ["-o", "out", "-l", "7", "-K", "4"]])
+def test_hclust_option_protocol_matches_reference(tmp_path, prog, args):
+    _ensure_built()
+    assert run(OURS, prog, args, tmp_path) == run(REF, prog, args, tmp_path)
+
+
+def write_kmers(path, n, length, seed, family=6):
+    """>name / KMER tokens (hclust2.cpp:232-240): near-duplicate families so that clusters form."""
+    rng = np.random.default_rng(seed)
+    nfam = max(1, n // family)
+    roots = rng.integers(0, 20, size=(nfam, length))
+    with open(path, "w") as f:
+        for i in range(n):
+            row = roots[rng.integers(0, nfam)].copy()
+            for _ in range(int(rng.integers(0, 3))):
+                row[rng.integers(0, length)] = rng.integers(0, 20)
+            f.write(f">kmer{i}\n{''.join(AA[c] for c in row)}\n")
+
+
+@pytest.mark.gpu
+@needs_ref_hcl
+@pytest.mark.parametrize("prog,length,K,L,W,R", [("hclust2", 10, 4, 4, "50", "25"), ("hclust3", 10, 4, 6, "30", "20"),
+                                                 ("hclust2", 25, 16, 8, "50", "60"), ("hclust2", 8, 2, 3, "20", "30")])
+def test_hclust_matches_reference(tmp_path, prog, length, K, L, W, R):
+    """Greedy centre clustering (Clustering(), hclust2.cpp:86-151) on the GPU against the
+    reference program itself: cluster file byte-identical, stdout equal up to the timings."""
+    _ensure_built()
+    write_kmers(tmp_path / "kmers.txt", 3000, length, seed=11)
+    env = {"HS_REF_SEED": "777"}
+    args = ["-k", "kmers.txt", "-l", str(length), "-K", str(K), "-L", str(L), "-W", W, "-T", R]
+    a = run(REF, prog, args + ["-o", "ref.clu"], tmp_path, env)
+    b = run(OURS, prog, args + ["-o", "our.clu"], tmp_path, env)
+    assert a[0] == 0 and b[0] == 0, b[2]
+    ref, our = open(tmp_path / "ref.clu").read(), open(tmp_path / "our.clu").read()
+    assert ref == our
+    nclusters = ref.count("#clusterid:")
+    assert 10 < nclusters < 3000  # real merging happened
+
+    def strip(s):
+        return [l for l in s.splitlines() if "takes" not in l]
+    assert strip(a[1]) == [l.replace("our.clu", "ref.clu") for l in strip(b[1])]
