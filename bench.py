@@ -314,7 +314,10 @@ def run_native(a):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = te.item() / a.steps
+        s_e = h.stats().as_dict()  # the last end-to-end search call
         e2e = {"value": N * world / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "search_stages_ms": {k[3:]: round(s_e[k], 3) for k in ("ms_qhash", "ms_probe", "ms_host", "ms_filter",
+                                                                        "ms_exact", "ms_hitsort", "ms_total")},
                "h2d_bytes_per_step": int(N * length + Q * dim * 8), "d2h_bytes_per_step": int(nh_e.value * 24),
                "api": "hs_load_fragments + hs_build_index + hs_search_points (host buffers, pinned)"}
         del host_codes, host_hits
@@ -337,22 +340,40 @@ def run_native(a):
     ncand, nsurv = s_search["n_candidates"], s_search["n_survivors"]
     ncand_tc = s_search["n_candidates_tc"]
     passes = s_build["sort_passes"]  # over all L tables
+    rank_path = bool(s_build["rank_path"])
+    # algorithmic bytes per launch family (DESIGN.md "Kernels"); rank path: u16 bucket ranks + 32-byte
+    # fragment records instead of 64-bit packed keys
+    rec = ((length + 1) // 2 * 2 + 2 * a.L + 15) // 16 * 16 if rank_path else (length + 15) // 16 * 16
+    if rank_path:
+        per_table_passes = passes // max(1, a.L)
+        hash_bytes = N * (length + 2 * a.L + rec)
+        up_bytes = N * 2 * passes
+        # first pass: read rank, write (rank, id); every later pass: read and write (rank, id)
+        down_bytes = N * a.L * ((2 + 6) + (per_table_passes - 1) * 12)
+        group_bytes = N * a.L * 2
+        permute_bytes = N * a.L * (4 + rec + length)
+    else:
+        hash_bytes = N * (length + 8 * KW * a.L)
+        up_bytes = N * 8 * passes
+        down_bytes = N * ((8 * KW + 4) * 2 * passes - 4 * a.L)
+        group_bytes = N * a.L * (8 * KW + 4)
+        permute_bytes = N * a.L * (4 + rec + length)
     kern = {
-        "hash_fast_kernel": {"ms": acc["ms_hash"] / steps, "bytes": N * (length + 8 * KW * a.L), "launches": 1},
-        "radix_downsweep_kernel": {"ms": acc["ms_sort_downsweep"] / steps,
-                                   "bytes": N * ((8 * KW + 4) * 2 * passes - 4 * a.L), "launches": passes},
-        "radix_upsweep_kernel": {"ms": acc["ms_sort_upsweep"] / steps, "bytes": N * 8 * passes, "launches": passes},
-        "bucket_grouping (head flags + scan + scatter)": {"ms": acc["ms_group"] / steps,
-                                                           "bytes": N * a.L * (8 * KW + 4), "launches": 5 * a.L},
-        "permute_codes_kernel": {"ms": acc["ms_permute"] / steps, "bytes": N * a.L * (4 + 2 * length),
-                                 "launches": a.L},
+        "hash_fast_kernel": {"ms": acc["ms_hash"] / steps, "bytes": hash_bytes, "launches": 1},
+        "radix_downsweep_kernel": {"ms": acc["ms_sort_downsweep"] / steps, "bytes": down_bytes, "launches": passes},
+        "radix_upsweep_kernel": {"ms": acc["ms_sort_upsweep"] / steps, "bytes": up_bytes, "launches": passes},
+        "bucket_grouping": {"ms": acc["ms_group"] / steps, "bytes": group_bytes, "launches": a.L},
+        "permute_rec_kernel": {"ms": acc["ms_permute"] / steps, "bytes": permute_bytes, "launches": a.L},
         "filter_kernel": {"ms": (acc["ms_filter"] - acc["ms_filter_tc"]) / steps,
                           "bytes": (ncand - ncand_tc) * (length + 4) + nsurv * 16, "launches": 1},
         # tensor-core candidate filter (Euclidean metric: filter_mma_kernel): algorithmic flops =
         # 2 * 8*len per (query, member) pair (the <x_m, q> contraction; DESIGN.md "roofline")
         "filter_mma_kernel": {"ms": acc["ms_filter_tc"] / steps, "bytes": ncand_tc * (length + 4), "launches": 1,
                               "flops": 2.0 * ncand_tc * 8 * length},
-        "exact_kernel": {"ms": acc["ms_exact"] / steps, "bytes": nsurv * (16 + length + 4) + nh * 24, "launches": 1},
+        # survivor (16) + id (4) + fragment record + hit (24)
+        "exact_kernel": {"ms": acc["ms_exact"] / steps, "bytes": nsurv * (16 + 4 + rec) + nh * 24, "launches": 1},
+        # one-word key build (24 + 8), radix passes over (key, perm) and the 24-byte gather
+        "hit_sort": {"ms": acc["ms_hitsort"] / steps, "bytes": nh * (32 + 6 * 32 + 4 + 48), "launches": 1},
     }
     for k, v in kern.items():
         v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
@@ -377,9 +398,9 @@ def run_native(a):
                     "algorithmic_flops_per_launch": d["flops"] / max(1, d["launches"]),
                     "avg_launch_ms": d["ms"] / max(1, d["launches"]), "share_of_step": d["share_of_step"],
                     "note": ("tcgen05 FP16 contraction <x_m, q> over every (query, bucket member) pair, 2*8*len flops "
-                             "per pair; the kernel is paced by its TMEM epilogue (one 3-input max per 2 accumulators "
-                             "+ survivor extraction), not by the MMA issue rate; DRAM traffic is ~len bytes per "
-                             "member per item")}
+                             "per pair; per-role cycle counters (profiles/) show the MMA pipe busy ~31% of the kernel: "
+                             "TMEM reads of the epilogue and the MMA's accumulator updates contend, so the two "
+                             "overlap poorly; DRAM traffic is ~len bytes per member per item")}
     else:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": d["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
@@ -394,7 +415,7 @@ def run_native(a):
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f16 tensor filter (f32 accumulate) + f64 exact (hash guard, distances); u64 keys",
+           "dtype": "f16 tensor filter (f32 accumulate) + f64 exact (hash guard, distances); u16 bucket ranks / u64 keys",
            "data": "synthetic",
            "config": {"workload": workload_name(a), "n_db_per_gpu": N, "n_query": Q, "len": length, "K": a.K,
                       "L": a.L, "W": a.W, "R": a.R, "table": "print6", "sharding": f"db-block x{world}",
@@ -409,7 +430,7 @@ def run_native(a):
                       "hits_total": int(nh_total), "query_frags_per_s": Q / ((acc["ms_qhash"] + acc["ms_probe"] +
                                                                              acc["ms_filter"] + acc["ms_exact"] +
                                                                              acc["ms_hitsort"]) / steps * 1e-3),
-                      "sort_passes": int(passes), "key_words": int(KW),
+                      "sort_passes": int(passes), "key_words": int(KW), "rank_path": rank_path,
                       "guard_hits": int(s_hash["guard_hits"]), "guard_corrected": int(s_hash["guard_corrected"]),
                       "residual_flips": int(s_hash["residual_flips"]) if a.audit else None}}
     print(json.dumps(out), flush=True)

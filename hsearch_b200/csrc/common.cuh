@@ -152,7 +152,9 @@ struct hs_ctx {
 
   // search scratch
   hs::DevBuf d_q64, d_qkeys, d_qvalid, d_qrange, d_tq, d_work, d_qlist, d_surv, d_hits, d_counters;
-  hs::DevBuf d_hit_keys[3], d_hit_perm, d_hits_sorted;
+  hs::DevBuf d_hit_keys[3], d_hit_perm, d_hits_sorted, d_hits_sorted_alt;
+  cudaStream_t copy_stream = nullptr;   // D2H of sorted hit blocks, overlapped with the next block's search
+  std::vector<cudaEvent_t> ev_chunk;
   hs::DevBuf d_misc, d_tabptrs, d_qcodes, d_hits_gathered, d_residues, d_starts;
   hs::DevBuf d_tq16, d_work_tc, d_qlist_tc;  // tensor-core filter: FP16 query tables, its work list
   hs::DevBuf d_tab16;                        // pipelined tensor filter: FP16 embedding rows + row norms

@@ -180,13 +180,13 @@ class HSearch:
         return n.value
 
     # ---- search ------------------------------------------------------------------
-    def _call_hits(self, fn, qarr, qctype, Q, cap):
+    def _call_hits(self, fn, qarr, qctype, Q, cap, grow=True):
         cap = int(cap)
         while True:
             hits = np.zeros(max(cap, 1), dtype=HIT_DTYPE)
             n = C.c_uint64(0)
             rc = fn(self.ctx, ptr(qarr, qctype) if qarr is not None else None, Q, hits.ctypes.data, cap, C.byref(n))
-            if rc == capi.HS_ERR_CAPACITY:
+            if rc == capi.HS_ERR_CAPACITY and grow:
                 cap = int(n.value)
                 continue
             check(rc)

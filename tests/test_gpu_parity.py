@@ -436,3 +436,32 @@ def test_rank_path_equals_packed_key_path(oracle, monkeypatch, length, K, L, W, 
     assert len(h0) > 0 and h0 == h1
     if l0 is not None:
         assert np.array_equal(l0, l1)
+
+
+def test_search_pipelined_blocks_equal_single_pass(oracle, monkeypatch):
+    """HS_PIPELINE=1: >= 2048 queries with a host hit buffer are searched in query blocks whose
+    sorted hits are copied out while the next block runs: same hits, same order as the single
+    pass, also at the capacity limit."""
+    length, K, L, W, R = 10, 4, 4, 50.0, 30.0
+    codes = random_codes(40000, length, seed=21)
+    qcodes = planted_queries(codes, 2600, seed=22, frac=0.5)
+    h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+    h.load_fragments(codes)
+    h.build_index()
+    monkeypatch.setenv("HS_PIPELINE", "0")
+    single = h.search_codes(qcodes)
+    monkeypatch.setenv("HS_PIPELINE", "1")
+    blocks = h.search_codes(qcodes)
+    assert len(single) > 1000
+    assert np.array_equal(single, blocks)
+    tab = oracle.coordinates(True)
+    want, _, _ = oracle.search(oracle.embed(codes, tab), oracle.embed(qcodes[:300], tab), a, b, W, R)
+    got300 = blocks[blocks["query"] < 300]
+    assert hits_as_tuples(got300) == hits_as_tuples(want)
+    # capacity protocol: too small a buffer is reported, and growing it gives the same hits
+    import ctypes
+    with pytest.raises(hb.HsError):
+        h._call_hits(h.lib.hs_search_codes, np.ascontiguousarray(qcodes), ctypes.c_uint8, len(qcodes),
+                     len(single) // 2, grow=False)
+    assert np.array_equal(h.search_codes(qcodes, cap=len(single) // 3), single)
+    h.close()
