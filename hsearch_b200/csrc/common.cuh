@@ -175,6 +175,7 @@ struct hs_ctx {
   int rank = 0, nranks = 1;
 
   hs_stats stats{};
+  hs_stats hash_stats{};   // counters / timing of the hash that produced the current keys
   cudaEvent_t ev[16];
   std::vector<cudaEvent_t> ev_pool;  // per-pass sort timing
 };

@@ -27,7 +27,7 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                  float invW, const double *__restrict__ table64, const double *__restrict__ a64,
                  const double *__restrict__ b64, double W, int K, int Kp, int L, int dim,
                  HashChunkArgs args, int32_t *__restrict__ buckets_out,
-                 unsigned long long *__restrict__ counters) {
+                 unsigned long long *__restrict__ counters, uint64_t f0 /* multiple of NT */, uint64_t f1) {
   constexpr int P = 4 * NQ;
   // 16-byte words of the next tile's codes held in registers: NT * 16 * NPF bytes >= NT * len
   // (the replicated-table path is taken for len <= 16 only)
@@ -56,8 +56,10 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
   }
   const float4 *myT = sT + (REP > 1 ? (tid & (REP - 1)) : 0);
   unsigned int my_guard = 0, my_corr = 0, my_over = 0;
-  const uint64_t ntiles = (N + NT - 1) / NT;
-  const uint64_t total_bytes = N * (uint64_t)len;
+  // this launch hashes the fragments [f0, f1)
+  const uint64_t tile0 = f0 / NT;
+  const uint64_t ntiles = (f1 + NT - 1) / NT;
+  const uint64_t total_bytes = f1 * (uint64_t)len;
   // the tile's code bytes are contiguous in global memory (16-byte aligned start): whole 16-byte
   // words are prefetched into registers one tile ahead, the ragged end of the DB byte by byte
   uint4 pf[NPF];
@@ -71,10 +73,10 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
         pf[v] = __ldg(reinterpret_cast<const uint4 *>(codes + off));
     }
   };
-  prefetch(blockIdx.x);
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  prefetch(tile0 + blockIdx.x);
+  for (uint64_t tile = tile0 + blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint64_t frag0 = tile * NT;
-    const uint64_t nfrag = min((uint64_t)NT, N - frag0);
+    const uint64_t nfrag = min((uint64_t)NT, f1 - frag0);
     __syncthreads();  // the previous tile's sC / sRec are no longer read
     {
       const uint64_t byte0 = frag0 * (uint64_t)len;
@@ -286,7 +288,7 @@ static size_t hash_smem_bytes(const hs_ctx *ctx, int NQ, int rep, int nt, bool f
 
 template <int NQ, int KW, bool RANK, int REP, int NT>
 static int launch_fast_rep(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
-                           unsigned long long *counters) {
+                           unsigned long long *counters, uint64_t f0, uint64_t f1) {
   const int P = 4 * NQ;
   const int len = (int)ctx->prm.len;
   const size_t smem = hash_smem_bytes(ctx, NQ, REP, NT, args.full_rec != 0);
@@ -295,14 +297,14 @@ static int launch_fast_rep(hs_ctx *ctx, int chunk, const HashChunkArgs &args, in
   int per_sm = 1;
   HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
   if (per_sm < 1) per_sm = 1;
-  const uint64_t ntiles = (ctx->N + NT - 1) / NT;
+  const uint64_t ntiles = (f1 + NT - 1) / NT - f0 / NT;
   const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm);
   const float *T = ctx->d_T32.as<float>() + (size_t)chunk * len * HS_AA * P;
   kern<<<grid, NT, smem, ctx->stream>>>(
       ctx->d_codes.as<uint8_t>(), ctx->N, len, T, ctx->d_b32.as<float>() + (size_t)chunk * P,
       ctx->d_eps32.as<float>() + (size_t)chunk * P, (float)(1.0 / ctx->prm.W), ctx->d_table64.as<double>(),
       ctx->d_a64.as<double>(), ctx->d_b64.as<double>(), ctx->prm.W, (int)ctx->prm.K, (int)ctx->Kp,
-      (int)ctx->prm.L, (int)ctx->dim, args, buckets, counters);
+      (int)ctx->prm.L, (int)ctx->dim, args, buckets, counters, f0, f1);
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;
@@ -310,21 +312,22 @@ static int launch_fast_rep(hs_ctx *ctx, int chunk, const HashChunkArgs &args, in
 
 template <int NQ, int KW, bool RANK>
 static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
-                            unsigned long long *counters) {
+                            unsigned long long *counters, uint64_t f0, uint64_t f1) {
   // 768 threads leave 85 registers per thread: 16 accumulators without spills
   if (NQ <= 4 && ctx->prm.len <= 16 && hash_smem_bytes(ctx, NQ, 8, kHashRepThreads, args.full_rec != 0) <= kHashRepBudget)
-    return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads>(ctx, chunk, args, buckets, counters);
-  return launch_fast_rep<NQ, KW, RANK, 1, kHashThreads>(ctx, chunk, args, buckets, counters);
+    return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads>(ctx, chunk, args, buckets, counters, f0, f1);
+  return launch_fast_rep<NQ, KW, RANK, 1, kHashThreads>(ctx, chunk, args, buckets, counters, f0, f1);
 }
 
 template <int NQ>
-static int launch_fast_kw(hs_ctx *ctx, int chunk, const HashChunkArgs &a, int32_t *b, unsigned long long *c) {
-  if (ctx->rank_mode) return launch_fast_inst<NQ, 1, true>(ctx, chunk, a, b, c);
+static int launch_fast_kw(hs_ctx *ctx, int chunk, const HashChunkArgs &a, int32_t *b, unsigned long long *c,
+                          uint64_t f0, uint64_t f1) {
+  if (ctx->rank_mode) return launch_fast_inst<NQ, 1, true>(ctx, chunk, a, b, c, f0, f1);
   switch (ctx->key_words) {
-    case 1: return launch_fast_inst<NQ, 1, false>(ctx, chunk, a, b, c);
-    case 2: return launch_fast_inst<NQ, 2, false>(ctx, chunk, a, b, c);
-    case 3: return launch_fast_inst<NQ, 3, false>(ctx, chunk, a, b, c);
-    default: return launch_fast_inst<NQ, 4, false>(ctx, chunk, a, b, c);
+    case 1: return launch_fast_inst<NQ, 1, false>(ctx, chunk, a, b, c, f0, f1);
+    case 2: return launch_fast_inst<NQ, 2, false>(ctx, chunk, a, b, c, f0, f1);
+    case 3: return launch_fast_inst<NQ, 3, false>(ctx, chunk, a, b, c, f0, f1);
+    default: return launch_fast_inst<NQ, 4, false>(ctx, chunk, a, b, c, f0, f1);
   }
 }
 
@@ -344,17 +347,27 @@ int ensure_records(hs_ctx *ctx) {
   return HS_OK;
 }
 
-int launch_hash_fast(hs_ctx *ctx, bool want_buckets) {
+bool hash_single_launch_records(const hs_ctx *ctx) {
+  return ctx->rank_mode && ctx->nchunks == 1 && hash_smem_bytes(ctx, (int)ctx->nq, 1, kHashThreads, true) <= 200 * 1024;
+}
+
+// Hashes the fragments [f0, f1) (f0 a multiple of kHashRangeAlign); the whole DB when f1 == 0.
+int launch_hash_fast(hs_ctx *ctx, bool want_buckets, uint64_t f0, uint64_t f1) {
+  if (f1 == 0) f1 = ctx->N;
   int32_t *buckets = want_buckets ? ctx->d_buckets.as<int32_t>() : nullptr;
   unsigned long long *counters = ctx->d_counters.as<unsigned long long>();
   const uint32_t K = ctx->prm.K;
   // the single-chunk rank launch writes whole records through shared memory; otherwise the
   // records must exist before the per-table ranks are stored into them
-  const bool full_rec = ctx->rank_mode && ctx->nchunks == 1 && hash_smem_bytes(ctx, (int)ctx->nq, 1, kHashThreads, true) <= 200 * 1024;
+  const bool full_rec = hash_single_launch_records(ctx);
   if (ctx->rank_mode) {
     HS_TRY(ctx->d_ranks.reserve(sizeof(uint16_t) * (size_t)ctx->prm.L * ctx->npad + 64));  // table stride npad: 16-byte aligned rows
     if (full_rec) HS_TRY(ctx->d_rec.reserve((size_t)ctx->N * ctx->rec_stride + 64));
-    else HS_TRY(ensure_records(ctx));
+    else if (f0 == 0 && f1 == ctx->N) HS_TRY(ensure_records(ctx));
+    else if (!ctx->have_rec) {
+      set_error("launch_hash_fast: ranged hashing needs the single-launch record path");
+      return HS_ERR_UNSUPPORTED;
+    }
   }
   for (uint32_t chunk = 0; chunk < ctx->nchunks; ++chunk) {
     HashChunkArgs args;
@@ -383,13 +396,13 @@ int launch_hash_fast(hs_ctx *ctx, bool want_buckets) {
     args.rec_rank_off = ctx->rec_rank_off;
     args.full_rec = full_rec ? 1 : 0;
     switch (ctx->nq) {
-      case 1: HS_TRY((launch_fast_kw<1>(ctx, chunk, args, buckets, counters))); break;
-      case 2: HS_TRY((launch_fast_kw<2>(ctx, chunk, args, buckets, counters))); break;
-      case 4: HS_TRY((launch_fast_kw<4>(ctx, chunk, args, buckets, counters))); break;
-      default: HS_TRY((launch_fast_kw<8>(ctx, chunk, args, buckets, counters))); break;
+      case 1: HS_TRY((launch_fast_kw<1>(ctx, chunk, args, buckets, counters, f0, f1))); break;
+      case 2: HS_TRY((launch_fast_kw<2>(ctx, chunk, args, buckets, counters, f0, f1))); break;
+      case 4: HS_TRY((launch_fast_kw<4>(ctx, chunk, args, buckets, counters, f0, f1))); break;
+      default: HS_TRY((launch_fast_kw<8>(ctx, chunk, args, buckets, counters, f0, f1))); break;
     }
   }
-  if (full_rec) ctx->have_rec = true;
+  if (full_rec && f1 == ctx->N) ctx->have_rec = true;
   return HS_OK;
 }
 

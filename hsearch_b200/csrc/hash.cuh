@@ -103,7 +103,9 @@ __device__ __forceinline__ bool rank_tuple_push(uint32_t &tix, int bucket, int l
   return d >= 0 && d < rng;
 }
 
-int launch_hash_fast(hs_ctx *ctx, bool want_buckets);
+constexpr uint64_t kHashRangeAlign = 768 * 256;  // multiple of every hash block size (768, 256)
+int launch_hash_fast(hs_ctx *ctx, bool want_buckets, uint64_t f0 = 0, uint64_t f1 = 0);
+bool hash_single_launch_records(const hs_ctx *ctx);  // the hash launch writes whole fragment records
 int launch_hash_exact(hs_ctx *ctx, bool want_buckets, bool audit);
 int ensure_records(hs_ctx *ctx);  // fragment records hold at least the codes
 int launch_hash_queries(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint64_t *d_qkeys, uint8_t *d_qvalid);

@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "overlapped or hash or index" > gpurun_out/t_load.log 2>&1; echo rc=$?
+tail -12 gpurun_out/t_load.log
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b18.log 2> gpurun_out/b18.err; echo rc=$?
+tail -2 gpurun_out/b18.err
+tail -1 gpurun_out/b18.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e'], d['gpu_launches'])"

@@ -465,3 +465,32 @@ def test_search_pipelined_blocks_equal_single_pass(oracle, monkeypatch):
                      len(single) // 2, grow=False)
     assert np.array_equal(h.search_codes(qcodes, cap=len(single) // 3), single)
     h.close()
+
+
+def test_load_fragments_overlapped_hash(oracle, monkeypatch):
+    """With a projection set, hs_load_fragments copies the DB in blocks and hashes each block as
+    it arrives: same ranks / keys / index / hits as the plain load followed by hs_hash."""
+    length, K, L, W, R = 10, 4, 4, 50.0, 30.0
+    n = 8 * 768 * 256 + 12345
+    codes = random_codes(n, length, seed=31)
+    qcodes = planted_queries(codes[:50000], 64, seed=32)
+    res = []
+    for no_overlap in ("1", "0"):
+        monkeypatch.setenv("HS_NO_LOAD_OVERLAP", no_overlap)
+        h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+        h.load_fragments(codes)
+        h.build_index()
+        st = h.stats()
+        keys = h.keys(2)
+        ids, starts = h.table(1)
+        hits = h.search_codes(qcodes)
+        res.append((keys, ids, starts, hits, st.guard_hits))
+        h.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    assert len(res[0][3]) > 0 and np.array_equal(res[0][3], res[1][3])
+    assert res[0][4] == res[1][4]
+    want = oracle.hash_codes(codes[:2000], oracle.coordinates(True), a, b, W)
+    strings = oracle.key_strings(want)
+    expect = np.stack([hb.pack_key_string(s, 1) for s in strings[:, 2]])
+    assert np.array_equal(res[1][0][:2000], expect)
