@@ -27,7 +27,7 @@ EXPORTS = [
     "hs_extract_windows", "hs_num_fragments", "hs_hash", "hs_get_keys", "hs_pack_key_string", "hs_build_index",
     "hs_table_sizes", "hs_get_table", "hs_search_points", "hs_search_codes", "hs_search_points_dev",
     "hs_bruteforce_codes", "hs_bruteforce_points", "hs_cluster", "hs_comm_init", "hs_comm_unique_id",
-    "hs_greedy_cluster", "hs_parse_fasta", "hs_klsh_generate", "hs_kmer3_klsh", "hs_orf6",
+    "hs_greedy_cluster", "hs_union_find", "hs_parse_fasta", "hs_klsh_generate", "hs_kmer3_klsh", "hs_orf6",
 ]
 
 
@@ -105,6 +105,7 @@ def load(build_if_missing=True):
     lib.hs_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.hs_comm_unique_id.argtypes = [vp]
     lib.hs_greedy_cluster.argtypes = [vp, u32p, u32p, u8p]
+    lib.hs_union_find.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint64, u32p]
     lib.hs_parse_fasta.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, u64p, C.c_uint64, u64p, u32p,
                                    C.c_uint64, u32p, u32p, u64p]
     lib.hs_klsh_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_double, dblp, dblp, dblp]

@@ -17,6 +17,7 @@ namespace hs {
 int setup_projection(hs_ctx *ctx, const double *a, const double *b);
 int cluster_impl(hs_ctx *ctx, uint32_t *label_out);
 int greedy_cluster_impl(hs_ctx *ctx, uint32_t *center_out, uint32_t *round_out, uint8_t *state_out);
+int union_find_impl(hs_ctx *ctx, uint32_t n, const uint32_t *eu, const uint32_t *ev, uint64_t ne, uint32_t *label_out);
 int extract_windows_impl(hs_ctx *ctx, const uint8_t *residues, const uint32_t *start_index, uint32_t nprot,
                          uint32_t stride, uint64_t id_base, uint32_t *pos_out, uint64_t pos_cap, uint64_t *nfrag);
 int comm_gather_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t *nhits, uint64_t cap);
@@ -1319,5 +1320,15 @@ int hs_greedy_cluster(hs_ctx_t *ctx, uint32_t *center_out, uint32_t *round_out, 
   }
   HS_CUDA(cudaSetDevice(ctx->device));
   return greedy_cluster_impl(ctx, center_out, round_out, state_out);
+}
+
+int hs_union_find(hs_ctx_t *ctx, uint32_t n, const uint32_t *eu, const uint32_t *ev, uint64_t ne, uint32_t *label_out) {
+  if (!ctx || (n && !label_out) || (ne && (!eu || !ev))) {
+    set_error("hs_union_find: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  stats_begin(ctx);
+  return union_find_impl(ctx, n, eu, ev, ne, label_out);
 }
 }

@@ -238,6 +238,49 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
 }
 
 
+// ---- union-find over an explicit edge list (cross-shard cluster) ---------
+__global__ void uf_edges_kernel(const uint32_t *__restrict__ eu, const uint32_t *__restrict__ ev, uint64_t ne,
+                                uint32_t n, uint32_t *__restrict__ parent, unsigned int *__restrict__ bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ne) return;
+  const uint32_t u = eu[i], v = ev[i];
+  if (u >= n || v >= n) {
+    *bad = 1u;
+    return;
+  }
+  if (u != v) uf_union(parent, u, v);
+}
+
+// FindRoot / JoinUnion (union_find.cpp:16-33) over ne edges between n ids; label_out[i] =
+// smallest id of i's component (the partition does not depend on the edge order).
+int union_find_impl(hs_ctx *ctx, uint32_t n, const uint32_t *eu, const uint32_t *ev, uint64_t ne, uint32_t *label_out) {
+  if (n == 0) return HS_OK;
+  HS_TRY(ctx->d_parent.reserve(sizeof(uint32_t) * 2 * (size_t)n));
+  HS_TRY(ctx->d_misc.reserve(sizeof(uint32_t) * 2 * (size_t)std::max<uint64_t>(ne, 1) + 16));
+  uint32_t *parent = ctx->d_parent.as<uint32_t>(), *label = parent + n;
+  uint32_t *d_eu = ctx->d_misc.as<uint32_t>(), *d_ev = d_eu + ne;
+  unsigned int *bad = reinterpret_cast<unsigned int *>(ctx->d_counters.as<unsigned long long>() + 12);
+  HS_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned int), ctx->stream));
+  iota32_kernel<<<(unsigned)(((uint64_t)n + 255) / 256), 256, 0, ctx->stream>>>(parent, n);
+  if (ne) {
+    HS_CUDA(cudaMemcpyAsync(d_eu, eu, sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaMemcpyAsync(d_ev, ev, sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, ctx->stream));
+    uf_edges_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(d_eu, d_ev, ne, n, parent, bad);
+  }
+  uf_flatten_kernel<<<(unsigned)(((uint64_t)n + 255) / 256), 256, 0, ctx->stream>>>(parent, n, label);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches += 3;
+  unsigned int h_bad = 0;
+  HS_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(label_out, label, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_bad) {
+    set_error("hs_union_find: an edge endpoint is >= n");
+    return HS_ERR_INVALID;
+  }
+  return HS_OK;
+}
+
 // ---- CL1: greedy centre clustering (hclust2.cpp:86-151, hclust3.cpp:87-152) -----------
 // L rounds; round l walks the buckets of table l.  Inside a bucket (members in ascending
 // id = insertion order) the centres are the members already marked 1, then every

@@ -296,29 +296,6 @@ int launch_filter(hs_ctx *ctx, const FilterArgs &args, uint32_t nblocks, int mod
 }
 
 // ---- exact stage --------------------------------------------------------------------
-__device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x) {
-  // path halving; parent[] only ever decreases, so racing updates stay valid
-  volatile uint32_t *p = parent;
-  while (true) {
-    const uint32_t px = p[x];
-    if (px == x) return x;
-    const uint32_t ppx = p[px];
-    if (ppx != px) p[x] = ppx;
-    x = px;
-  }
-}
-// JoinUnion (union_find.cpp:31-33) made order-independent: the larger root is
-// hooked under the smaller, so the final root of a component is its min id.
-__device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b) {
-  while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
-    if (atomicCAS(parent + hi, hi, lo) == hi) return;
-  }
-}
-
 // `len` bytes at an arbitrarily aligned address as little-endian words: aligned 32-bit
 // loads realigned by funnel shifts (reads at most 7 bytes past the end; buffers carry slack).
 template <int NWORDS>

@@ -215,6 +215,14 @@ class HSearch:
         check(self.lib.hs_cluster(self.ctx, ptr(out, C.c_uint32)))
         return out
 
+    def union_find(self, n, eu, ev):
+        """Connected components of an explicit edge list over ids 0..n-1 (label = smallest id)."""
+        eu = np.ascontiguousarray(eu, dtype=np.uint32)
+        ev = np.ascontiguousarray(ev, dtype=np.uint32)
+        out = np.zeros(n, dtype=np.uint32)
+        check(self.lib.hs_union_find(self.ctx, n, ptr(eu, C.c_uint32), ptr(ev, C.c_uint32), len(eu), ptr(out, C.c_uint32)))
+        return out
+
     def greedy_cluster(self):
         """hclust2's Clustering(): (centre of every fragment, round it joined in, merged[] flags)."""
         n = self.num_fragments

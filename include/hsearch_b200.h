@@ -229,6 +229,11 @@ int hs_bruteforce_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hi
  * (host) = smallest local id of the fragment's component. */
 int hs_cluster(hs_ctx_t *ctx, uint32_t *label_out);
 
+/* UnionFind (pcluster/src/pcluster/union_find.cpp:3-33) over an explicit edge list: ids
+ * 0..n-1, edges (eu[i], ev[i]) (host arrays).  label_out[n] = smallest id of each id's
+ * component.  Used to merge the per-shard near-pair edges of a sharded cluster run. */
+int hs_union_find(hs_ctx_t *ctx, uint32_t n, const uint32_t *eu, const uint32_t *ev, uint64_t ne, uint32_t *label_out);
+
 /* Greedy centre clustering, Clustering() of hclust2.cpp:86-151 (= hclust3.cpp:87-152):
  * L rounds, round l over the buckets of table l; inside a bucket, in member (id) order,
  * every unprocessed fragment joins the first centre within R (sqrt predicate) or becomes
