@@ -70,3 +70,128 @@ def sort_hits_reference_order(hits):
     ascending db id; motif_both_points.cpp:224-245)."""
     order = np.lexsort((hits["db_id"], hits["table_first"], hits["query"]))
     return hits[order]
+
+
+# ---- sharded near-pair clustering (BASELINE configs[3], SURVEY.md 8e) --------------------
+# Buckets span shards, so the cluster path has one real exchange step per table: every
+# (key, global id, codes) record goes to the rank that owns its bucket (owner = mix(key) mod
+# world), the owner finds the in-bucket near pairs of the complete buckets it holds, the
+# resulting edges are all-gathered and every rank runs the same union-find over them.
+def _device_of(t):
+    return t.device
+
+
+def allgather_rows(t):
+    """Variable-length all_gather along dim 0; returns the rows of all ranks in rank order."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return t
+    dev = t.device
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([t.shape[0]], dtype=torch.int64, device=dev))
+    counts = counts.tolist()
+    mx = max(counts + [1])
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+    pad[:t.shape[0]] = t
+    out = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+    dist.all_gather_into_tensor(out, pad)
+    return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(world)], dim=0)
+
+
+def exchange_rows(tensors, dest):
+    """Sends row i of every tensor in `tensors` to rank dest[i]; returns the rows this rank
+    receives (concatenated in source-rank order).  Grouped point-to-point sends: the
+    all-to-all of the cluster path."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return list(tensors)
+    rank = dist.get_rank()
+    dev = tensors[0].device
+    order = torch.argsort(dest, stable=True)
+    send_counts = torch.bincount(dest, minlength=world).to(torch.int64)
+    recv_counts = torch.zeros(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(recv_counts, send_counts.to(dev))
+    recv_counts = recv_counts.view(world, world)[:, rank].tolist()   # what each source sends to me
+    send_counts = send_counts.tolist()
+    outs = []
+    for t in tensors:
+        ts = t[order].contiguous()
+        out = torch.empty((sum(recv_counts),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        ops, so, ro = [], 0, 0
+        for r in range(world):
+            ns, nr = send_counts[r], recv_counts[r]
+            if r == rank:
+                out[ro:ro + nr].copy_(ts[so:so + ns])
+            else:
+                if ns:
+                    ops.append(dist.P2POp(dist.isend, ts[so:so + ns], r))
+                if nr:
+                    ops.append(dist.P2POp(dist.irecv, out[ro:ro + nr], r))
+            so += ns
+            ro += nr
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        outs.append(out)
+    return outs
+
+
+def bucket_owner(keys, world):
+    """keys: int64 tensor [n, KW] (the packed key words reinterpreted); owner rank of each bucket."""
+    h = torch.zeros(keys.shape[0], dtype=torch.int64, device=keys.device)
+    for w in range(keys.shape[1]):
+        h = (h * 1000003) ^ keys[:, w] ^ (keys[:, w] >> 29)
+    return (h & 0x7FFFFFFF) % world
+
+
+def cluster_sharded(codes_local, id_base, n_total, n_tables, key_fn, local_edges_fn, union_fn, device="cpu"):
+    """Near-pair clustering of a block-sharded DB.
+    key_fn(l) -> uint64 array [n_local, KW]: packed keys of the local fragments in table l.
+    local_edges_fn(l, codes [m, len] u8, gids [m] int64) -> (eu, ev) global-id edges among the
+    received fragments (complete buckets of table l).
+    union_fn(n_total, eu, ev) -> uint32 labels [n_total] (smallest id of each component).
+    Returns the labels of the local shard (global ids of the component minima)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    n_local = codes_local.shape[0]
+    codes_t = torch.as_tensor(np.ascontiguousarray(codes_local), device=device)
+    gids = torch.arange(id_base, id_base + n_local, dtype=torch.int64, device=device)
+    eus, evs = [], []
+    for l in range(n_tables):
+        keys = torch.as_tensor(np.ascontiguousarray(key_fn(l)).view(np.int64), device=device)
+        owner = bucket_owner(keys, world)
+        rc, rg = exchange_rows([codes_t, gids], owner)
+        eu, ev = local_edges_fn(l, rc.cpu().numpy(), rg.cpu().numpy())
+        eus.append(np.asarray(eu, dtype=np.int64))
+        evs.append(np.asarray(ev, dtype=np.int64))
+    e = np.stack([np.concatenate(eus), np.concatenate(evs)], axis=1) if eus else np.zeros((0, 2), dtype=np.int64)
+    e_all = allgather_rows(torch.as_tensor(e, device=device)).cpu().numpy()
+    labels = union_fn(n_total, e_all[:, 0].astype(np.uint32), e_all[:, 1].astype(np.uint32))
+    return labels[id_base:id_base + n_local]
+
+
+def gpu_cluster_callbacks(h, a, b, codes_local):
+    """The three callbacks of cluster_sharded on top of the C ABI: h is an HSearch with the
+    local shard loaded and hashed (all L tables); per-table contexts do the in-bucket pair
+    search of the received fragments (hs_cluster), hs_union_find merges the edges."""
+    from .index import HSearch
+
+    def key_fn(l):
+        return h.keys(l)
+
+    def local_edges_fn(l, codes, gids):
+        if len(codes) < 2:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        p = h.params
+        with HSearch(h.len, h.K, 1, p.W, p.R, table_variant=p.table_variant, metric=p.metric, predicate=p.predicate,
+                     flags=0, device=getattr(h, "device", 0)) as t:
+            t.set_projection(a[l:l + 1], b[l:l + 1])
+            t.load_fragments(codes)
+            t.build_index()
+            lab = t.cluster()
+        m = np.nonzero(lab != np.arange(len(lab)))[0]
+        return gids[m], gids[lab[m]]
+
+    def union_fn(n_total, eu, ev):
+        return h.union_find(n_total, eu, ev)
+
+    return key_fn, local_edges_fn, union_fn

@@ -73,6 +73,7 @@ class HSearch:
         self.len = kmer_length
         self.dim = 8 * kmer_length
         self.K, self.L = hash_K, hash_L
+        self.device = device
 
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx.value:

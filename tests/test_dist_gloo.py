@@ -91,3 +91,54 @@ def test_gather_hits_world2_matches_single_process(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert int(open(tmp_path / "ok").read()) > 0
+
+
+# ---------------------------------------------------------------- sharded cluster (configs[3])
+def _cluster_worker(rank, world, port, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.pyoracle import Oracle
+        from tests.util import planted_families
+        import hsearch_b200 as hb
+        o = Oracle()
+        length, K, L, W, R = 10, 4, 3, 50.0, 25.0
+        n_total = 3001
+        codes = planted_families(n_total, length, seed=13)
+        tab = o.coordinates(True)
+        a, b = o.lsh_tables(777, 8 * length, K, L, W)
+        lo, hi = hdist.shard_range(n_total, rank, world)
+        local = codes[lo:hi]
+        buckets = o.hash_codes(local, tab, a, b, W)            # [n_local, L, K]
+        strings = o.key_strings(buckets)
+
+        def key_fn(l):
+            return np.stack([hb.pack_key_string(s, 1) for s in strings[:, l]])
+
+        def local_edges_fn(l, rc, rg):
+            if len(rc) < 2:
+                return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+            lab, _ = o.cluster(rc, tab, a[l:l + 1], b[l:l + 1], W, R)
+            m = np.nonzero(lab != np.arange(len(lab)))[0]
+            return rg[m], rg[lab[m]]
+
+        def union_fn(n, eu, ev):
+            return o.union_find_labels(n, eu, ev)
+
+        got = hdist.cluster_sharded(local, lo, n_total, L, key_fn, local_edges_fn, union_fn)
+        want, ne = o.cluster(codes, tab, a, b, W, R)
+        assert ne > 0
+        # labels are component minima in both: compare directly
+        assert np.array_equal(got, want[lo:hi])
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write(str(len(np.unique(want))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_cluster_sharded_world2_matches_single_process(tmp_path):
+    world = 2
+    mp.spawn(_cluster_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    n0, n1 = int(open(tmp_path / "ok0").read()), int(open(tmp_path / "ok1").read())
+    assert n0 == n1 and 1 < n0 < 3001

@@ -494,3 +494,27 @@ def test_load_fragments_overlapped_hash(oracle, monkeypatch):
     strings = oracle.key_strings(want)
     expect = np.stack([hb.pack_key_string(s, 1) for s in strings[:, 2]])
     assert np.array_equal(res[1][0][:2000], expect)
+
+
+def test_cluster_sharded_path_on_one_rank(oracle):
+    """The sharded cluster path (per-table in-bucket pair search on the bucket owner, edge
+    union through hs_union_find) with world size 1 must give the labels of hs_cluster / the oracle."""
+    from hsearch_b200 import dist as hdist
+    length, K, L, W, R = 10, 4, 3, 50.0, 25.0
+    codes = planted_families(5003, length, seed=41)
+    h, a, b = make(length, K, L, W, R, predicate=hb.HS_PRED_SQRT_LE_R)
+    h.load_fragments(codes)
+    h.build_index()
+    direct = h.cluster()
+    key_fn, edges_fn, union_fn = hdist.gpu_cluster_callbacks(h, a, b, codes)
+    got = hdist.cluster_sharded(codes, 0, len(codes), L, key_fn, edges_fn, union_fn)
+    want, ne = oracle.cluster(codes, oracle.coordinates(True), a, b, W, R)
+    assert ne > 0 and np.array_equal(direct, want)
+    assert np.array_equal(got, want)
+    # hs_union_find alone against the oracle's UnionFind (SURVEY 8c known answer)
+    eu, ev = np.array([0, 20, 10, 50, 70]), np.array([10, 30, 30, 60, 50])
+    lab = h.union_find(80, eu, ev)
+    assert lab[[0, 10, 20, 30]].tolist() == [0, 0, 0, 0] and lab[40] == 40 and lab[[50, 60, 70]].tolist() == [50] * 3
+    with pytest.raises(hb.HsError):
+        h.union_find(10, np.array([3]), np.array([11]))
+    h.close()
