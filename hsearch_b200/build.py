@@ -57,7 +57,7 @@ def build(force=False, verbose=False, ptxas_verbose=False):
     return LIB
 
 
-CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints", "hclust2", "hclust3"]
+CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints", "hclust2", "hclust3", "evaluate2"]
 BIN = os.path.join(HERE, "bin")
 
 

@@ -1183,13 +1183,20 @@ int hs_build_index(hs_ctx_t *ctx) {
   if (ctx->N) {
     for (uint32_t l = 0; l < L; ++l) {
       HS_CUDA(cudaEventRecord(ev[2], ctx->stream));
-      HS_TRY(build_table_index(ctx, l, ev[3], ev[4]));
-      HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
-      HS_CUDA(cudaEventSynchronize(ev[5]));
+      HS_TRY(build_table_index(ctx, l, ev[3], ev[4], false));
+      HS_CUDA(cudaEventSynchronize(ev[4]));
       ms_sort += ev_ms(ev[2], ev[3]);
       ms_group += ev_ms(ev[3], ev[4]);
-      ms_permute += ev_ms(ev[4], ev[5]);
     }
+    // bucket-order code stores: one L2-blocked gather for all tables, else table by table
+    HS_CUDA(cudaEventRecord(ev[2], ctx->stream));
+    bool blocked = false;
+    HS_TRY(build_code_stores_blocked(ctx, &blocked));
+    if (!blocked)
+      for (uint32_t l = 0; l < L; ++l) HS_TRY(build_table_store(ctx, l));
+    HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
+    HS_CUDA(cudaEventSynchronize(ev[5]));
+    ms_permute = ev_ms(ev[2], ev[5]);
   } else {
     for (uint32_t l = 0; l < L; ++l) ctx->tables[l].nb = ctx->tables[l].nslots = 0;
   }

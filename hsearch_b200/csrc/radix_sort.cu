@@ -10,7 +10,10 @@
 // Keys are KW 64-bit words stored word-major (SoA); a pass ranks on one word
 // and moves all words.  Digit windows are placed only over bits that actually
 // vary across the input (OR/AND reduction), so constant nibbles cost nothing.
+#include <stdlib.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "hash.cuh"
 #include "sort.cuh"
@@ -558,6 +561,181 @@ int build_code_store(hs_ctx *ctx, const uint32_t *ids, DevBuf &out) {
   return HS_OK;
 }
 
+// ---- bucket-order code stores of all tables in one L2-blocked gather -------------------------
+// A random 32-byte record gather costs 128 bytes of DRAM traffic on B200 (ncu), and every
+// table gathers the same records.  Members of a bucket are in ascending id order, so the part
+// of a bucket whose ids fall into one block of the record array is one contiguous run of the
+// bucket.  The gather therefore walks the record array block by block (32 MB: L2-resident) and,
+// inside a block, all tables and all buckets, so that a record line fetched from DRAM is
+// served from L2 to several of the ~16 gathers that want it (4 records per line x L tables;
+// ncu: DRAM reads 52.9 GB -> 18.8 GB at L = 4).
+constexpr uint32_t kGatherBlockBytes = 16u << 20;  // measured best on B200 (8-16 MB; 4 and 32 MB are slower)
+constexpr int kGatherSlots = 256;     // slots per thread block
+constexpr uint32_t kGatherPart = 4096; // members per slot at most
+constexpr int kGatherThreads = 256;
+
+struct GatherTab {
+  const uint32_t *ids;     // [N] bucket order
+  const uint32_t *bstart;  // [nslots + 1]
+  uint8_t *out;            // [len][npad]
+  uint32_t nslots;         // slots: non-empty buckets, cut into parts of <= kGatherPart members
+  uint32_t ngroups;        // thread blocks of this table per record block
+  uint32_t groups_before;  // slot groups of the tables before this one
+  uint64_t run_off;        // offset of this table's run boundaries in the runs array
+};
+
+// runs[c * nslots + b] = first position of slot b whose id is >= c * chunk (c = 0..nchunks).
+// One thread per slot: its ids are ascending, so only the record-block boundaries between its
+// first and its last id need a search.
+__global__ void gather_runs_kernel(const GatherTab *__restrict__ tabs, uint32_t ntab, uint32_t nchunks, uint32_t chunk,
+                                   uint32_t *__restrict__ runs) {
+  const uint32_t gg = blockIdx.x;
+  uint32_t l = 0;
+  while (l + 1 < ntab && tabs[l + 1].groups_before <= gg) ++l;
+  const GatherTab T = tabs[l];
+  const uint32_t b = (gg - T.groups_before) * kGatherSlots + threadIdx.x;
+  if (b >= T.nslots) return;
+  const uint32_t lo0 = T.bstart[b], hi0 = T.bstart[b + 1];
+  const uint32_t c_first = hi0 > lo0 ? T.ids[lo0] / chunk : 0u;
+  const uint32_t c_last = hi0 > lo0 ? T.ids[hi0 - 1] / chunk : 0u;
+  uint32_t *out = runs + T.run_off + b;
+  uint32_t lo = lo0;
+  for (uint32_t c = 0; c <= nchunks; ++c) {
+    uint32_t r;
+    if (c <= c_first) r = lo0;
+    else if (c > c_last) r = hi0;
+    else {
+      const uint32_t key = c * chunk;  // (c <= c_last: c * chunk <= last id < 2^32)
+      uint32_t hi = hi0;
+      while (lo < hi) {  // lower bound, continuing from the previous boundary
+        const uint32_t m = lo + ((hi - lo) >> 1);
+        if (T.ids[m] < key) lo = m + 1; else hi = m;
+      }
+      r = lo;
+    }
+    out[(uint64_t)c * T.nslots] = r;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_blocked_kernel(const GatherTab *__restrict__ tabs, uint32_t ntab, uint32_t total_groups,
+                      const uint32_t *__restrict__ runs, const uint8_t *__restrict__ rec, uint32_t RS, uint64_t npad,
+                      int len) {
+  __shared__ uint32_t s_start[kGatherSlots];
+  __shared__ uint32_t s_pref[kGatherSlots + 1];
+  __shared__ uint32_t s_warp[kGatherThreads / 32];
+  // blockIdx.x = c * total_groups + (table, slot group): all work of record block c is adjacent
+  const uint32_t c = blockIdx.x / total_groups, gg = blockIdx.x - c * total_groups;
+  uint32_t l = 0;
+  while (l + 1 < ntab && tabs[l + 1].groups_before <= gg) ++l;
+  const GatherTab T = tabs[l];
+  const uint32_t b = (gg - T.groups_before) + threadIdx.x * T.ngroups;
+  uint32_t st = 0, n = 0;
+  if (b < T.nslots) {
+    st = runs[T.run_off + (uint64_t)c * T.nslots + b];
+    n = runs[T.run_off + (uint64_t)(c + 1) * T.nslots + b] - st;
+  }
+  uint32_t total;
+  const uint32_t ex = block_exclusive_scan_256<kGatherThreads / 32>(n, s_warp, total);
+  s_start[threadIdx.x] = st;
+  s_pref[threadIdx.x] = ex;
+  if (threadIdx.x == 0) s_pref[kGatherSlots] = total;
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < total; e += kGatherThreads) {
+    // slot of element e: last slot with prefix <= e
+    uint32_t lo = 0, hi = kGatherSlots;
+    while (hi - lo > 1) {
+      const uint32_t m = (lo + hi) >> 1;
+      if (s_pref[m] <= e) lo = m; else hi = m;
+    }
+    const uint32_t j = s_start[lo] + (e - s_pref[lo]);
+    const uint32_t id = __ldg(T.ids + j);
+    const uint4 *src = reinterpret_cast<const uint4 *>(rec + (uint64_t)id * RS);
+    uint32_t w[4 * NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const uint4 r = __ldg(src + v);
+      w[4 * v + 0] = r.x;
+      w[4 * v + 1] = r.y;
+      w[4 * v + 2] = r.z;
+      w[4 * v + 3] = r.w;
+    }
+#pragma unroll
+    for (int pos = 0; pos < 16 * NV; ++pos)
+      if (pos < len) T.out[(uint64_t)pos * npad + j] = (uint8_t)(((w[pos >> 2] >> (8 * (pos & 3))) & 0xffu) * kCodeScale);
+  }
+}
+
+// Builds codes_sorted of every table.  Returns HS_OK with *done = false when the blocked
+// gather does not apply (small DB, or too many bucket slots for the run table).
+int build_code_stores_blocked(hs_ctx *ctx, bool *done) {
+  *done = false;
+  const uint64_t n = ctx->N;
+  const uint32_t L = ctx->prm.L, RS = ctx->rec_stride;
+  const char *e = getenv("HS_NO_BLOCKED_GATHER");
+  if ((e && atoi(e)) || n * RS < 4ull * kGatherBlockBytes) return HS_OK;
+  uint32_t block_bytes = kGatherBlockBytes;
+  if (const char *m = getenv("HS_GATHER_MB")) block_bytes = (uint32_t)std::max(1, atoi(m)) << 20;
+  const uint32_t chunk = block_bytes / RS;
+  const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
+  std::vector<GatherTab> tabs(L);
+  uint64_t run_total = 0;
+  uint32_t groups = 0;
+  const size_t bytes = (size_t)ctx->prm.len * ctx->npad + 256;
+  // slot boundaries per table: the non-empty buckets, cut into parts of <= kGatherPart members
+  std::vector<uint32_t> vstart, bs;
+  std::vector<uint64_t> voff(L);
+  for (uint32_t l = 0; l < L; ++l) {
+    TableIndex &T = ctx->tables[l];
+    if ((T.nslots + n / kGatherPart) * (uint64_t)(nchunks + 1) > (64ull << 20)) return HS_OK;
+    bs.resize(T.nslots + 1);
+    HS_CUDA(cudaMemcpyAsync(bs.data(), T.bstart.p, sizeof(uint32_t) * (T.nslots + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    voff[l] = vstart.size();
+    for (uint64_t b = 0; b < T.nslots; ++b)
+      for (uint32_t p = bs[b]; p < bs[b + 1]; p += kGatherPart) vstart.push_back(p);
+    vstart.push_back((uint32_t)n);
+  }
+  HS_TRY(ctx->sort.block_sums.reserve(sizeof(uint32_t) * vstart.size() + 16));
+  HS_CUDA(cudaMemcpyAsync(ctx->sort.block_sums.p, vstart.data(), sizeof(uint32_t) * vstart.size(), cudaMemcpyHostToDevice,
+                          ctx->stream));
+  for (uint32_t l = 0; l < L; ++l) {
+    TableIndex &T = ctx->tables[l];
+    if (T.codes_sorted.cap < bytes) {
+      HS_TRY(T.codes_sorted.reserve(bytes));
+      HS_CUDA(cudaMemsetAsync(T.codes_sorted.p, 0, T.codes_sorted.cap, ctx->stream));
+    }
+    const uint64_t nv = (l + 1 < L ? voff[l + 1] : vstart.size()) - voff[l] - 1;
+    tabs[l].ids = T.sorted_ids.as<uint32_t>();
+    tabs[l].bstart = ctx->sort.block_sums.as<uint32_t>() + voff[l];
+    tabs[l].out = T.codes_sorted.as<uint8_t>();
+    tabs[l].nslots = (uint32_t)nv;
+    tabs[l].ngroups = (uint32_t)((nv + kGatherSlots - 1) / kGatherSlots);
+    tabs[l].groups_before = groups;
+    tabs[l].run_off = run_total;
+    groups += tabs[l].ngroups;
+    run_total += (uint64_t)(nchunks + 1) * nv;
+  }
+  if (groups == 0 || run_total > (64ull << 20) || (uint64_t)groups * nchunks > 0x7fffffffull) return HS_OK;
+  HS_TRY(ensure_records(ctx));
+  HS_TRY(ctx->sort.flags.reserve(sizeof(uint32_t) * run_total + 16));
+  HS_TRY(ctx->d_misc.reserve(sizeof(GatherTab) * L));
+  HS_CUDA(cudaMemcpyAsync(ctx->d_misc.p, tabs.data(), sizeof(GatherTab) * L, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // tabs is a host temporary
+  const GatherTab *d_tabs = ctx->d_misc.as<GatherTab>();
+  uint32_t *runs = ctx->sort.flags.as<uint32_t>();
+  gather_runs_kernel<<<groups, kGatherSlots, 0, ctx->stream>>>(d_tabs, L, nchunks, chunk, runs);
+  if (ctx->prm.len <= 16)
+    gather_blocked_kernel<1><<<groups * nchunks, kGatherThreads, 0, ctx->stream>>>(d_tabs, L, groups, runs, ctx->d_rec.as<uint8_t>(), RS, ctx->npad, (int)ctx->prm.len);
+  else
+    gather_blocked_kernel<2><<<groups * nchunks, kGatherThreads, 0, ctx->stream>>>(d_tabs, L, groups, runs, ctx->d_rec.as<uint8_t>(), RS, ctx->npad, (int)ctx->prm.len);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches += 2;
+  *done = true;
+  return HS_OK;
+}
+
 // ---- rank path: sort of u16 bucket ranks ----------------------------------------
 // Same upsweep / scan / downsweep structure as above, specialised for 16-bit keys:
 // at most two 8-bit passes, the first takes the implicit index as value, the last
@@ -702,7 +880,8 @@ rank_bounds_kernel(const uint16_t *__restrict__ sorted, uint64_t n, uint32_t nr,
 
 // Rank path of build_table_index: two-pass (or one-pass) sort of the table's u16 ranks,
 // bucket boundaries from the rank histogram (one slot per possible key string).
-static int build_table_index_ranks(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cudaEvent_t ev_group_end) {
+static int build_table_index_ranks(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cudaEvent_t ev_group_end,
+                                   bool with_store) {
   const uint64_t n = ctx->N;
   SortScratch &S = ctx->sort;
   TableIndex &T = ctx->tables[table];
@@ -778,12 +957,14 @@ static int build_table_index_ranks(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_s
     ctx->stats.ms_sort_scan += b;
     ctx->stats.ms_sort_downsweep += c;
   }
-  HS_TRY(build_code_store(ctx, ids, T.codes_sorted));
+  if (with_store) HS_TRY(build_code_store(ctx, ids, T.codes_sorted));
   return HS_OK;
 }
 
-int build_table_index(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cudaEvent_t ev_group_end) {
-  if (ctx->rank_mode) return build_table_index_ranks(ctx, table, ev_sort_end, ev_group_end);
+// with_store == false: the caller builds the code stores of all tables afterwards
+// (build_code_stores_blocked, or build_table_store per table).
+int build_table_index(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cudaEvent_t ev_group_end, bool with_store) {
+  if (ctx->rank_mode) return build_table_index_ranks(ctx, table, ev_sort_end, ev_group_end, with_store);
   KeyPtrs sorted;
   HS_TRY(sort_table(ctx, table, &sorted));
   HS_CUDA(cudaEventRecord(ev_sort_end, ctx->stream));
@@ -794,8 +975,12 @@ int build_table_index(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cuda
     default: HS_TRY(group_inst<4>(ctx, table, sorted)); break;
   }
   HS_CUDA(cudaEventRecord(ev_group_end, ctx->stream));
-  HS_TRY(build_code_store(ctx, ctx->tables[table].sorted_ids.as<uint32_t>(), ctx->tables[table].codes_sorted));
+  if (with_store) HS_TRY(build_table_store(ctx, table));
   return HS_OK;
+}
+
+int build_table_store(hs_ctx *ctx, uint32_t table) {
+  return build_code_store(ctx, ctx->tables[table].sorted_ids.as<uint32_t>(), ctx->tables[table].codes_sorted);
 }
 
 }  // namespace hs

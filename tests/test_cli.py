@@ -146,10 +146,12 @@ def test_search_pipeline_matches_reference(tmp_path, W):
     assert open(tmp_path / "ref.gtnotlessthan.txt").read() == open(tmp_path / "our.gtnotlessthan.txt").read()
 
     # evaluate2 sorts the ground truth (evaluate2.cpp:88-96); both searches read the same sorted file
-    ev = os.path.join(REF, "evaluate2")
-    subprocess.run([ev, "ref.gt"], cwd=tmp_path, capture_output=True, timeout=120)
+    ea = run(REF, "evaluate2", ["ref.gt"], tmp_path)
+    eb = run(OURS, "evaluate2", ["our.gt"], tmp_path)
+    assert ea[0] == eb[0] == 0 and ea[1] == eb[1].replace("our.gt", "ref.gt")
     gts = "ref.gtsort.txt"
     assert os.path.exists(tmp_path / gts)
+    assert open(tmp_path / gts).read() == open(tmp_path / "our.gtsort.txt").read()
 
     a = run(REF, "motif_both_points", ["-d", "ref.db", "-c", "ref.q", "-l", str(length), "-W", W, "-T", R, "-g", gts,
                                        "-o", "ref.hits"], tmp_path, env)
@@ -213,3 +215,24 @@ def test_hclust_matches_reference(tmp_path, prog, length, K, L, W, R):
     def strip(s):
         return [l for l in s.splitlines() if "takes" not in l]
     assert strip(a[1]) == [l.replace("our.clu", "ref.clu") for l in strip(b[1])]
+
+
+@pytest.mark.skipif(not _have(REF, "evaluate2"), reason="oracle/_ref/bin/evaluate2 not built")
+def test_evaluate2_matches_reference(tmp_path):
+    """Ground-truth sorter (evaluate2.cpp:75-96): same stdout, same <file>sort.txt."""
+    _ensure_built()
+    rng = np.random.default_rng(17)
+    rows = [(f"motif{int(rng.integers(0, 40))}", f"prot#{i}$0@K*1", float(rng.random() * 60)) for i in range(500)]
+    with open(tmp_path / "gt", "w") as f:
+        for m, p, d in rows:
+            f.write(f"{m} {p} {d:.6g}\n")
+    import shutil
+    shutil.copy(tmp_path / "gt", tmp_path / "gt2")
+    a = run(REF, "evaluate2", ["gt"], tmp_path)
+    b = run(OURS, "evaluate2", ["gt2"], tmp_path)
+    assert a[0] == b[0] == 0 and a[1] == b[1].replace("gt2", "gt")
+    assert open(tmp_path / "gtsort.txt").read() == open(tmp_path / "gt2sort.txt").read()
+    # missing input file: empty sorted file, exit 0, like the reference
+    a = run(REF, "evaluate2", ["nope"], tmp_path)
+    b = run(OURS, "evaluate2", ["nope"], tmp_path)
+    assert a[:2] == b[:2] and open(tmp_path / "nopesort.txt").read() == ""

@@ -518,3 +518,31 @@ def test_cluster_sharded_path_on_one_rank(oracle):
     with pytest.raises(hb.HsError):
         h.union_find(10, np.array([3]), np.array([11]))
     h.close()
+
+
+@pytest.mark.parametrize("W", [50.0, 20.0])
+def test_blocked_gather_equals_per_table_gather(oracle, monkeypatch, W):
+    """Above 128 MB of fragment records the bucket-order code stores of all tables are built by
+    one L2-blocked gather; the searches that stream those stores must return the same hits
+    as with the per-table gather (rank path at W = 50, packed-key path at W = 20)."""
+    length, K, L, R = 10, 4, 4, 30.0
+    n = 4_300_003
+    codes = random_codes(n, length, seed=51)
+    qcodes = planted_queries(codes[:100000], 300, seed=52, frac=0.5)
+    res = []
+    for off in ("1", "0"):
+        monkeypatch.setenv("HS_NO_BLOCKED_GATHER", off)
+        h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+        h.load_fragments(codes)
+        h.build_index()
+        res.append((h.search_codes(qcodes), h.table_sizes(), h.stats().rank_path))
+        h.close()
+    assert res[0][2] == res[1][2] == (1 if W == 50.0 else 0)
+    assert np.array_equal(res[0][1], res[1][1])
+    assert len(res[0][0]) > 300 and np.array_equal(res[0][0], res[1][0])
+    # and against the oracle on a slice of the queries (brute force over the hits' distances)
+    tab = oracle.coordinates(True)
+    hits = res[1][0]
+    sub = hits[hits["query"] < 20]
+    d = oracle.embed(codes[sub["db_id"]], tab) - oracle.embed(qcodes[sub["query"]], tab)
+    assert np.all((d * d).sum(axis=1) <= R * R * (1 + 1e-12))
