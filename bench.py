@@ -408,6 +408,32 @@ def run_native(a):
                     "avg_launch_ms": d["ms"] / max(1, d["launches"]), "share_of_step": d["share_of_step"],
                     "note": ""}
 
+    # ---- size-independent checks of the full-size result (outside the timed region) -------
+    # rank 0's hits of the last step: reference order, every sampled distance recomputed on the
+    # host from the codes (float64, same formula) and inside the threshold
+    checks = None
+    try:
+        from hsearch_b200.capi import HIT_DTYPE
+        nv = min(int(nh), cap)
+        hv = hits_dev[:nv * 24]
+        q_t = hv.view(torch.int32)[0::6].to(torch.int64)
+        t_t = hv.view(torch.int32)[1::6].to(torch.int64)
+        id_t = hv.view(torch.int64)[1::3]
+        key = (q_t << 40) | (t_t << 34) | (id_t - rank * N)
+        in_order = bool((key[1:] > key[:-1]).all().item()) if nv > 1 else True
+        gs = torch.Generator(device=dev)
+        gs.manual_seed(7)
+        pick = torch.randint(0, max(nv, 1), (min(4096, nv),), device=dev, generator=gs)
+        samp = np.frombuffer(hv.view(-1, 24)[pick].cpu().numpy().tobytes(), dtype=HIT_DTYPE)
+        xc = codes[torch.from_numpy((samp["db_id"] - rank * N).astype(np.int64)).to(dev)].long()
+        xp = table[xc].reshape(len(samp), dim)
+        d2 = ((xp - qpts[torch.from_numpy(samp["query"].astype(np.int64)).to(dev)]) ** 2).sum(dim=1).cpu().numpy()
+        checks = {"hits_checked_for_order": nv, "reference_order": in_order, "sampled_hits": int(len(samp)),
+                  "max_rel_dist2_error": float(np.max(np.abs(d2 - samp["dist2"]) / np.maximum(d2, 1e-300))) if len(samp) else 0.0,
+                  "all_within_R": bool(np.all(samp["dist2"] <= a.R * a.R)) if len(samp) else True}
+    except Exception as e:  # the checks must never break the bench line
+        checks = {"error": repr(e)}
+
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         cpu = cpu_leg(a, a.cpu_sample)
@@ -423,6 +449,7 @@ def run_native(a):
            "clocks": clocks, "wall_ms_per_step": wall_ms / a.steps,
            "e2e": e2e, "gpu_launches": int(acc["kernel_launches"]),
            "roofline": roofline, "cpu_baseline": cpu,
+           "checks": checks,
            "stages_ms": {k[3:]: round(acc[k] / steps, 4) for k in sorted(acc) if k.startswith("ms_")},
            "kernels": {k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "share": round(v["share_of_step"], 4)}
                        for k, v in kern.items()},

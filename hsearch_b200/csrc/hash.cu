@@ -123,50 +123,58 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
       kb.reset();
       uint32_t tix = 0;
       bool in_range = true;
-      int t = 0, k = 0;  // table within chunk, projection within table (uniform across the block)
+      // projection slot s = projection k of table t of the chunk
+      auto project = [&](int s, int t, int k, bool last_k) {
+        const float val = acc[s] + args.b32[s];
+        const float tt = val * invW;
+        const float f = floorf(tt);
+        int bucket = (int)f;
+        const float e = args.eps32[s];
+        if ((tt - f) < e || ((f + 1.0f) - tt) < e) {
+          const int l = args.l0 + t;
+          const int ex = exact_bucket_codes(myc, len, table64, a64 + ((size_t)l * K + k) * dim, b64[l * K + k], W);
+          ++my_guard;
+          if (ex != bucket) ++my_corr;
+          bucket = ex;
+        }
+        if (RANK) in_range = rank_tuple_push(tix, bucket, args.lo[s], args.rng[s]) && in_range;
+        else kb.push_int(bucket);
+        if (buckets_out) buckets_out[(frag * L + (args.l0 + t)) * K + k] = bucket;
+        if (last_k) {
+          if (RANK) {
+            uint16_t rank = 0;
+            if (in_range) rank = __ldg(args.lut[t] + tix);
+            else ++my_over;
+            args.ranks[t][frag] = rank;
+            if (full_rec)
+              *reinterpret_cast<uint16_t *>(myrec + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
+            else
+              *reinterpret_cast<uint16_t *>(args.rec + frag * RS + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
+            tix = 0;
+            in_range = true;
+          } else {
+            if (kb.nchars > 16 * KW) ++my_over;
+            uint64_t *dst = args.keys[t];
 #pragma unroll
-      for (int s = 0; s < P; ++s) {
-        if (t < args.ntab && k < K) {
-          const float val = acc[s] + args.b32[s];
-          const float tt = val * invW;
-          const float f = floorf(tt);
-          int bucket = (int)f;
-          const float e = args.eps32[s];
-          if ((tt - f) < e || ((f + 1.0f) - tt) < e) {
-            const int l = args.l0 + t;
-            const int ex = exact_bucket_codes(myc, len, table64, a64 + ((size_t)l * K + k) * dim,
-                                              b64[l * K + k], W);
-            ++my_guard;
-            if (ex != bucket) ++my_corr;
-            bucket = ex;
-          }
-          if (RANK) in_range = rank_tuple_push(tix, bucket, args.lo[s], args.rng[s]) && in_range;
-          else kb.push_int(bucket);
-          if (buckets_out) buckets_out[(frag * L + (args.l0 + t)) * K + k] = bucket;
-          if (k == K - 1) {
-            if (RANK) {
-              uint16_t rank = 0;
-              if (in_range) rank = __ldg(args.lut[t] + tix);
-              else ++my_over;
-              args.ranks[t][frag] = rank;
-              if (full_rec)
-                *reinterpret_cast<uint16_t *>(myrec + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
-              else
-                *reinterpret_cast<uint16_t *>(args.rec + frag * RS + args.rec_rank_off + 2 * (args.l0 + t)) = rank;
-              tix = 0;
-              in_range = true;
-            } else {
-              if (kb.nchars > 16 * KW) ++my_over;
-              uint64_t *dst = args.keys[t];
-#pragma unroll
-              for (int w = 0; w < KW; ++w) dst[(uint64_t)w * N + frag] = kb.w[w];
-              kb.reset();
-            }
+            for (int w = 0; w < KW; ++w) dst[(uint64_t)w * N + frag] = kb.w[w];
+            kb.reset();
           }
         }
-        if (++k == Kp) {
-          k = 0;
-          ++t;
+      };
+      if (args.k4_full) {
+        // K = 4 and every slot of the chunk in use (the reference's configuration): the
+        // (table, projection) walk is fully static
+#pragma unroll
+        for (int s = 0; s < P; ++s) project(s, s >> 2, s & 3, (s & 3) == 3);
+      } else {
+        int t = 0, k = 0;  // uniform across the block
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+          if (t < args.ntab && k < K) project(s, t, k, k == K - 1);
+          if (++k == Kp) {
+            k = 0;
+            ++t;
+          }
         }
       }
     }
@@ -395,6 +403,7 @@ int launch_hash_fast(hs_ctx *ctx, bool want_buckets, uint64_t f0, uint64_t f1) {
     args.rec_stride = ctx->rec_stride;
     args.rec_rank_off = ctx->rec_rank_off;
     args.full_rec = full_rec ? 1 : 0;
+    args.k4_full = (K == 4 && (uint32_t)args.ntab * 4 == 4 * ctx->nq) ? 1 : 0;
     switch (ctx->nq) {
       case 1: HS_TRY((launch_fast_kw<1>(ctx, chunk, args, buckets, counters, f0, f1))); break;
       case 2: HS_TRY((launch_fast_kw<2>(ctx, chunk, args, buckets, counters, f0, f1))); break;

@@ -93,6 +93,7 @@ struct HashChunkArgs {
   uint8_t *rec;              // fragment records [N][rec_stride]
   uint32_t rec_stride, rec_rank_off;
   int full_rec;              // 1: this launch writes whole records (codes + ranks) through shared memory
+  int k4_full;               // 1: K == 4 and all 4*NQ projection slots of the chunk are in use
 };
 
 // Mixed-radix index of one table's bucket tuple; returns false when a bucket lies

@@ -565,7 +565,7 @@ int build_code_store(hs_ctx *ctx, const uint32_t *ids, DevBuf &out) {
 // A random 32-byte record gather costs 128 bytes of DRAM traffic on B200 (ncu), and every
 // table gathers the same records.  Members of a bucket are in ascending id order, so the part
 // of a bucket whose ids fall into one block of the record array is one contiguous run of the
-// bucket.  The gather therefore walks the record array block by block (32 MB: L2-resident) and,
+// bucket.  The gather therefore walks the record array block by block (16 MB: L2-resident) and,
 // inside a block, all tables and all buckets, so that a record line fetched from DRAM is
 // served from L2 to several of the ~16 gathers that want it (4 records per line x L tables;
 // ncu: DRAM reads 52.9 GB -> 18.8 GB at L = 4).
