@@ -216,6 +216,7 @@ struct MmaArgs {
   const __half *qb16;         // [Q][kp] query rows (coordinates, c_q hi/lo, zero padding)
   uint32_t tq_base;           // qb16 row of query id x is x - tq_base
   const uint8_t *const *stores;
+  const uint32_t *const *sorted_ids;  // per table: ids in bucket order (nullptr entry: identity)
   uint64_t npad;
   int len, kp, nstages, qmax, cring;
   float thr, beta;
@@ -242,6 +243,7 @@ struct MmaShared {
   uint4 tab16[HS_AA][8];
   float nx32[HS_AA];
   float rowthr[kMmaRowRing][kMmaM];
+  uint32_t rowid[kMmaRowRing][kMmaM];   // fragment id of every row (the exact stage then skips the id gather)
   Survivor stage[kMmaEpiWarps][kMmaStageCap];
   uint32_t wcount[kMmaEpiWarps];  // survivors staged per epilogue warp
 };
@@ -407,10 +409,13 @@ filter_mma_kernel(MmaArgs a) {
       }
       const uint32_t base = un.m_begin & ~15u;
       const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
+      const uint32_t *ids = a.sorted_ids[it.table];
       for (uint32_t t = 0; t < ntiles; ++t, ++pt) {
         const uint32_t s = pt % S, d = pt % D;
         const uint32_t mypos = base + t * kMmaM + (uint32_t)r;
         const bool valid = mypos >= un.m_begin && mypos < un.m_end;
+        // the row's fragment id (coalesced; issued before the waits below, used after the A build)
+        const uint32_t myid = (valid && ids) ? __ldg(ids + mypos) : mypos;
         // my row's residue codes from the ring the loader fills
         {
           PROF_T0();
@@ -446,6 +451,7 @@ filter_mma_kernel(MmaArgs a) {
         float rt = 0.5f * (nx * (1.0f - 4e-6f) * (1.0f - a.beta) - a.thr);
         rt -= (nx + a.thr) * 2.4e-7f + 1e-6f;
         sh.rowthr[pt % kMmaRowRing][r] = valid ? rt : __int_as_float(0x7f800000);
+        sh.rowid[pt % kMmaRowRing][r] = myid;
         fence_async_shared();
         mbar_arrive_warp(smem_addr(&sh.a_full[s]), lane);
       }
@@ -596,8 +602,8 @@ filter_mma_kernel(MmaArgs a) {
       const uint32_t base = un.m_begin & ~15u;
       const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
       for (uint32_t t = 0; t < ntiles; ++t, ++et) {
-        const uint32_t pos = base + t * kMmaM + (uint32_t)row;
         float rt = 0.f;
+        uint32_t rid = 0u;  // fragment id of this lane's row
         for (uint32_t g = 0; g < ngroups; ++g, ++eg) {
           const uint32_t as = eg % kMmaAccStages;
           {
@@ -610,7 +616,10 @@ filter_mma_kernel(MmaArgs a) {
             tc_after();
             PROF_ADD(e_unit);
           }
-          if (g == 0) rt = sh.rowthr[et % kMmaRowRing][row];
+          if (g == 0) {
+            rt = sh.rowthr[et % kMmaRowRing][row];
+            rid = sh.rowid[et % kMmaRowRing][row];
+          }
           const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
           const uint32_t ngp = (ng + 15u) & ~15u;  // columns the MMA wrote
           const uint32_t nchunks = ngp >> 4;  // 16-column chunks; this warp takes c = sub, sub + 4, ...
@@ -644,8 +653,8 @@ filter_mma_kernel(MmaArgs a) {
                 Survivor sv;
                 sv.query = qbase + col0 + c;  // index into the query list; the exact stage resolves it
                 sv.table = it.table;
-                sv.pos = pos;
-                sv.pad = 1;
+                sv.pos = rid;
+                sv.pad = 3;  // query = index into the query list, pos = fragment id
                 if (k < (uint32_t)kMmaStageCap) {
                   stage[k] = sv;
                 } else {  // staging buffer full (dense hit regions): straight to the global list
@@ -867,6 +876,7 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
   a.qb16 = reinterpret_cast<const __half *>(d_qb16);
   a.tq_base = fa.tq_base;
   a.stores = fa.stores;
+  a.sorted_ids = dev_sorted_ids(ctx);
   a.npad = fa.npad;
   a.len = fa.len;
   a.kp = g.kp;

@@ -369,8 +369,9 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(ExactArgs a) {
     if (i < a.nsurv) {
       s = a.surv[i];
       const uint32_t *ids = a.sorted_ids[s.table];
-      id = ids ? (uint64_t)__ldg(ids + s.pos) : (uint64_t)s.pos;
-      qid = s.pad ? (uint64_t)a.qlist_mma[s.query] : (uint64_t)s.query;
+      // pad bit 1: the tensor filter already resolved the member's fragment id
+      id = ((s.pad & 2u) || !ids) ? (uint64_t)s.pos : (uint64_t)__ldg(ids + s.pos);
+      qid = (s.pad & 1u) ? (uint64_t)a.qlist_mma[s.query] : (uint64_t)s.query;
       bool live = !(a.mode == kModeAllPairs && !(qid < id));  // each unordered pair once
       const uint8_t *recp = a.rec + id * a.rec_stride;
       uint32_t mw[4 * NV], qw[4 * NV];

@@ -19,7 +19,8 @@ struct Survivor {
   uint32_t query;  // query index (search / brute force) or member position (self join)
   uint32_t table;
   uint32_t pos;    // member position in the table's bucket order
-  uint32_t pad;    // 1: `query` is an index into the pipelined tensor filter's query list
+  uint32_t pad;    // bit 0: `query` is an index into the pipelined tensor filter's query list;
+                   // bit 1: `pos` is already the fragment id
 };
 
 constexpr int kFilterThreads = 256;
