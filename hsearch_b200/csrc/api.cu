@@ -24,6 +24,34 @@ int comm_gather_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t *nhits, uint64_t cap)
 int comm_broadcast(hs_ctx *ctx, void *d_buf, size_t bytes);
 void comm_destroy(hs_ctx *ctx);
 
+// Small device -> host read-backs (counters, flags) go through a mapped pinned staging area
+// written by a kernel, not through cudaMemcpy: a DMA copy would queue behind a large transfer
+// in flight on the copy stream (the device-to-host engine is shared), stalling the pipeline.
+__global__ void small_readback_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, uint32_t nwords) {
+  for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
+int read_back(hs_ctx *ctx, const void *d_src, void *h_dst, size_t bytes) {
+  if (bytes == 0) return HS_OK;
+  if ((bytes & 3) || bytes > 1024 || (reinterpret_cast<uintptr_t>(d_src) & 3)) {
+    HS_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HS_OK;
+  }
+  if (!ctx->h_pinned) {
+    HS_CUDA(cudaHostAlloc(&ctx->h_pinned, 1024, cudaHostAllocMapped));
+    ctx->h_pinned_cap = 1024;
+    HS_CUDA(cudaHostGetDevicePointer(&ctx->d_pinned, ctx->h_pinned, 0));
+  }
+  small_readback_kernel<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(d_src),
+                                                   reinterpret_cast<uint32_t *>(ctx->d_pinned), (uint32_t)(bytes / 4));
+  HS_CUDA(cudaGetLastError());
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(h_dst, ctx->h_pinned, bytes);
+  return HS_OK;
+}
+
 static int upload_tables(hs_ctx *ctx) {
   HS_TRY(ctx->d_table64.reserve(sizeof(double) * HS_AA * HS_CDIM));
   HS_CUDA(cudaMemcpyAsync(ctx->d_table64.p, ctx->table64, sizeof(double) * HS_AA * HS_CDIM,
@@ -413,8 +441,7 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
     hit_key1_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, n, tshift, qshift, ctx->d_hit_keys[0].as<uint64_t>(), ovf);
     ctx->stats.kernel_launches++;
     unsigned int h_ovf = 0;
-    HS_CUDA(cudaMemcpyAsync(&h_ovf, ovf, sizeof h_ovf, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    HS_TRY(read_back(ctx, ovf, &h_ovf, sizeof h_ovf));
     one_word = h_ovf == 0;
   }
   if (one_word) {
@@ -441,6 +468,68 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
 }
 
 // ---- search ----------------------------------------------------------------------------
+constexpr uint32_t kSearchBlocks = 4;  // query blocks of the pipelined verify / sort / copy-out
+
+// Query blocks grow geometrically (1/16, 3/16, 1/4, 1/2 of the queries): the first block is
+// verified and sorted quickly, so that the PCIe copy chain -- the longer of the two pipelines --
+// starts early; the later, larger blocks are always ready before the copy engine needs them.
+struct SearchBlocks {
+  uint32_t end[kSearchBlocks];  // block c holds the queries [end[c-1], end[c])
+};
+static SearchBlocks search_blocks(uint32_t Q) {
+  SearchBlocks b;
+  b.end[0] = Q / 16;
+  b.end[1] = Q / 4;
+  b.end[2] = Q / 2;
+  b.end[3] = Q;
+  return b;
+}
+
+// Splits the survivor list by query block.  SCATTER = false:
+// counts per block; true: writes the survivors of each block contiguously (cursor[] preset to
+// the block offsets).  Counts are aggregated in shared memory: one global atomic per
+// (thread block, query block) and tile of 2048 survivors.
+constexpr int kSurvItems = 8;
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+survivor_block_kernel(const Survivor *__restrict__ surv, uint64_t n, const uint32_t *__restrict__ qlist_mma,
+                      SearchBlocks qb, uint32_t nblk, unsigned long long *__restrict__ cursor,
+                      Survivor *__restrict__ out) {
+  __shared__ unsigned int s_cnt[kSearchBlocks];
+  __shared__ unsigned long long s_base[kSearchBlocks];
+  const uint64_t tile = (uint64_t)blockDim.x * kSurvItems;
+  for (uint64_t t0 = (uint64_t)blockIdx.x * tile; t0 < n; t0 += (uint64_t)gridDim.x * tile) {
+    if (threadIdx.x < kSearchBlocks) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    Survivor sv[kSurvItems];
+    uint32_t blk[kSurvItems], slot[kSurvItems];
+#pragma unroll
+    for (int j = 0; j < kSurvItems; ++j) {
+      const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
+      blk[j] = 0xffffffffu;
+      if (i < n) {
+        sv[j] = surv[i];
+        const uint32_t q = (sv[j].pad & 1u) ? __ldg(qlist_mma + sv[j].query) : sv[j].query;
+        uint32_t bq = 0;
+#pragma unroll
+        for (int c = 0; c < (int)kSearchBlocks - 1; ++c) bq += q >= qb.end[c] ? 1u : 0u;
+        blk[j] = bq;
+        slot[j] = atomicAdd(&s_cnt[blk[j]], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < nblk && s_cnt[threadIdx.x])
+      s_base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (SCATTER) {
+#pragma unroll
+      for (int j = 0; j < kSurvItems; ++j)
+        if (blk[j] != 0xffffffffu) out[s_base[blk[j]] + slot[j]] = sv[j];
+    }
+    __syncthreads();
+  }
+}
+
 struct QueryInput {
   const double *h_points = nullptr;  // host [Q][dim]
   const void *d_points = nullptr;    // device [Q][dim]
@@ -617,11 +706,11 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   };
   // exact + dedup + emit of the current survivor list into d_hits[0 .. hit_cap)
   unsigned long long *hit_count = ctx->d_counters.as<unsigned long long>() + 9;
-  auto run_exact = [&](uint64_t nsurv, uint64_t hit_cap) -> int {
+  auto run_exact = [&](const Survivor *surv, uint64_t nsurv, uint64_t hit_cap) -> int {
     HS_CUDA(cudaMemsetAsync(hit_count, 0, sizeof(unsigned long long), ctx->stream));
     ExactArgs ea;
     fill_exact_common(ctx, ea, Q);
-    ea.surv = ctx->d_surv.as<Survivor>();
+    ea.surv = surv;
     ea.nsurv = nsurv;
     ea.mode = kModeSearch;
     ea.q64 = ctx->prm.metric == HS_METRIC_EUCLID_FP64 ? ctx->d_q64.as<double>() : nullptr;
@@ -644,51 +733,71 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   ctx->stats.ms_qhash = ev_ms(ev[0], ev[1]);
   ctx->stats.ms_probe = ev_ms(ev[1], ev[2]);
 
-  // Optional (HS_PIPELINE=1): the queries are taken in blocks and the sorted hits of a block
-  // cross PCIe on a second stream while the next block is filtered and verified (hits are
-  // ordered by query first, so the blocks concatenate into the final order).  Off by default:
-  // measured on B200 at 10 k queries x 100 M fragments it hides the 38 ms hit copy but
-  // quarters the queries per bucket, which doubles the tensor filter's time.
-  const char *pipe = getenv("HS_PIPELINE");
+  // Host hit buffer + reference order: the filter runs once over all queries; its survivors are
+  // then split by query block, and each block is verified, sorted and sent over PCIe on a
+  // second stream while the next block is verified and sorted (hits are ordered by query first,
+  // so the blocks concatenate into the final order).  HS_NO_PIPELINE=1 disables it.
+  // (Splitting the *filter* by query block was measured too: it quarters the queries per
+  // bucket and doubles the tensor filter's time, DESIGN.md.)
+  const char *nop = getenv("HS_NO_PIPELINE");
   const bool pipelined = hits_host && ctx->nranks == 1 && (ctx->prm.flags & HS_FLAG_SORT_HITS) && Q >= 2048 &&
-                         pipe && atoi(pipe);
+                         !(nop && atoi(nop));
   if (pipelined) {
-    const uint32_t nblk = 4;
+    const uint32_t nblk = kSearchBlocks;
     if (!ctx->copy_stream) HS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    while (ctx->ev_chunk.size() < 6 * nblk) {
+    while (ctx->ev_chunk.size() < 4 * nblk + 8) {
       cudaEvent_t e;
       HS_CUDA(cudaEventCreate(&e));
       ctx->ev_chunk.push_back(e);
     }
-    uint64_t done = 0, total = 0, nsurv_total = 0;
-    for (uint32_t c = 0; c < nblk; ++c) {
-      cudaEvent_t *ce = &ctx->ev_chunk[6 * c];  // [0] start [1] planned [2] filtered [3] verified [4] sorted [5] copied
-      const uint32_t qa = (uint32_t)((uint64_t)Q * c / nblk), qb = (uint32_t)((uint64_t)Q * (c + 1) / nblk);
-      HS_CUDA(cudaEventRecord(ce[0], ctx->stream));
-      FilterPlan plan;
-      HS_TRY(make_plan(plan, qa, qb));
-      HS_CUDA(cudaEventRecord(ce[1], ctx->stream));
-      uint64_t nsurv = 0;
-      HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
-      HS_CUDA(cudaEventRecord(ce[2], ctx->stream));
-      nsurv_total += nsurv;
-      const uint64_t cap_left = cap - std::min(done, cap);
-      HS_TRY(run_exact(nsurv, cap_left));
-      unsigned long long nh = 0;
-      HS_CUDA(cudaMemcpyAsync(&nh, hit_count, sizeof nh, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaEventRecord(ce[3], ctx->stream));
+    FilterPlan plan;
+    HS_TRY(make_plan(plan, 0, Q));
+    HS_CUDA(cudaEventRecord(ev[12], ctx->stream));
+    uint64_t nsurv = 0;
+    HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
+    ctx->stats.n_survivors = nsurv;
+    // survivors by query block
+    HS_TRY(ctx->d_surv_blk.reserve(sizeof(Survivor) * std::max<uint64_t>(nsurv, 1)));
+    unsigned long long *blk_cnt = ctx->d_counters.as<unsigned long long>() + 16;  // [nblk] counts, [nblk] cursors
+    HS_CUDA(cudaMemsetAsync(blk_cnt, 0, sizeof(unsigned long long) * 2 * nblk, ctx->stream));
+    unsigned long long h_cnt[kSearchBlocks] = {0};
+    if (nsurv) {
+      const unsigned grid = (unsigned)std::min<uint64_t>((nsurv + 2047) / 2048, (uint64_t)ctx->num_sms * 8);
+      survivor_block_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->d_surv.as<Survivor>(), nsurv, ctx->d_qlist_mma.as<uint32_t>(), search_blocks(Q), nblk, blk_cnt, nullptr);
+      HS_CUDA(cudaMemcpyAsync(h_cnt, blk_cnt, sizeof(unsigned long long) * nblk, cudaMemcpyDeviceToHost, ctx->stream));
       HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      unsigned long long h_cur[kSearchBlocks], run = 0;
+      for (uint32_t c = 0; c < nblk; ++c) {
+        h_cur[c] = run;
+        run += h_cnt[c];
+      }
+      HS_CUDA(cudaMemcpyAsync(blk_cnt + nblk, h_cur, sizeof(unsigned long long) * nblk, cudaMemcpyHostToDevice, ctx->stream));
+      survivor_block_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->d_surv.as<Survivor>(), nsurv, ctx->d_qlist_mma.as<uint32_t>(), search_blocks(Q), nblk, blk_cnt + nblk, ctx->d_surv_blk.as<Survivor>());
+      HS_CUDA(cudaGetLastError());
+      ctx->stats.kernel_launches += 2;
+    }
+    HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
+    uint64_t done = 0, total = 0, soff = 0;
+    for (uint32_t c = 0; c < nblk; ++c) {
+      cudaEvent_t *ce = &ctx->ev_chunk[4 * c];  // [0] start [1] verified [2] sorted [3] copied
+      HS_CUDA(cudaEventRecord(ce[0], ctx->stream));
+      const uint64_t cap_left = cap - std::min(done, cap);
+      HS_TRY(run_exact(ctx->d_surv_blk.as<Survivor>() + soff, h_cnt[c], cap_left));
+      soff += h_cnt[c];
+      unsigned long long nh = 0;
+      HS_CUDA(cudaEventRecord(ce[1], ctx->stream));
+      HS_TRY(read_back(ctx, hit_count, &nh, sizeof nh));
       const uint64_t nvalid = std::min<uint64_t>(nh, cap_left);
       // the sorted buffer written now was last read by the copy of block c-2
-      if (c >= 2) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[6 * (c - 2) + 5], 0));
+      if (c >= 2) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[4 * (c - 2) + 3], 0));
       HS_TRY(sort_hits(ctx, ctx->d_hits.as<hs_hit>(), nvalid));
-      HS_CUDA(cudaEventRecord(ce[4], ctx->stream));
+      HS_CUDA(cudaEventRecord(ce[2], ctx->stream));
       if (nvalid) {
-        HS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ce[4], 0));
+        HS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ce[2], 0));
         HS_CUDA(cudaMemcpyAsync(hits_host + done, ctx->d_hits_sorted.p, sizeof(hs_hit) * nvalid, cudaMemcpyDeviceToHost,
                                 ctx->copy_stream));
       }
-      HS_CUDA(cudaEventRecord(ce[5], ctx->copy_stream));
+      HS_CUDA(cudaEventRecord(ce[3], ctx->copy_stream));
       std::swap(ctx->d_hits_sorted, ctx->d_hits_sorted_alt);
       done += nvalid;
       total += nh;
@@ -696,14 +805,13 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
     HS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     HS_CUDA(cudaEventRecord(ev[7], ctx->stream));
     HS_CUDA(cudaEventSynchronize(ev[7]));
+    ctx->stats.ms_host = ev_ms(ev[2], ev[12]);
+    ctx->stats.ms_filter = ev_ms(ev[12], ev[3]);
     for (uint32_t c = 0; c < nblk; ++c) {
-      cudaEvent_t *ce = &ctx->ev_chunk[6 * c];
-      ctx->stats.ms_host += ev_ms(ce[0], ce[1]);
-      ctx->stats.ms_filter += ev_ms(ce[1], ce[2]);
-      ctx->stats.ms_exact += ev_ms(ce[2], ce[3]);
-      ctx->stats.ms_hitsort += ev_ms(ce[3], ce[4]);
+      cudaEvent_t *ce = &ctx->ev_chunk[4 * c];
+      ctx->stats.ms_exact += ev_ms(ce[0], ce[1]);
+      ctx->stats.ms_hitsort += ev_ms(ce[1], ce[2]);
     }
-    ctx->stats.n_survivors = nsurv_total;
     ctx->stats.n_hits = total;
     ctx->stats.ms_total = ev_ms(ev[0], ev[7]);
     *nhits = total;
@@ -721,7 +829,7 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
   HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
   ctx->stats.n_survivors = nsurv;
-  HS_TRY(run_exact(nsurv, dev_cap));
+  HS_TRY(run_exact(ctx->d_surv.as<Survivor>(), nsurv, dev_cap));
   unsigned long long nh = 0;
   HS_CUDA(cudaMemcpyAsync(&nh, hit_count, sizeof nh, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
@@ -910,7 +1018,7 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
     return HS_ERR_CUDA;
   }
   for (int i = 0; i < 16; ++i) cudaEventCreate(&ctx->ev[i]);
-  int rc = ctx->d_counters.reserve(sizeof(unsigned long long) * 16);
+  int rc = ctx->d_counters.reserve(sizeof(unsigned long long) * 32);
   if (rc == HS_OK) rc = upload_tables(ctx);
   if (rc != HS_OK) {
     hs_destroy(ctx);
@@ -932,7 +1040,7 @@ void hs_destroy(hs_ctx_t *ctx) {
                     &ctx->d_hit_keys[1], &ctx->d_hit_keys[2], &ctx->d_hit_perm, &ctx->d_hits_sorted,
                     &ctx->d_hits_gathered, &ctx->d_misc, &ctx->d_parent, &ctx->d_tabptrs, &ctx->d_residues,
                     &ctx->d_starts, &ctx->d_metric32, &ctx->d_tq16, &ctx->d_work_tc, &ctx->d_qlist_tc, &ctx->d_large,
-                    &ctx->d_qcodes_det, &ctx->d_qrow, &ctx->d_tab16, &ctx->d_qb16, &ctx->d_mma_items, &ctx->d_mma_units, &ctx->d_mma_cta, &ctx->d_qlist_mma, &ctx->d_lut, &ctx->d_rinfo, &ctx->d_ranks, &ctx->d_rec, &ctx->d_qrank, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
+                    &ctx->d_qcodes_det, &ctx->d_qrow, &ctx->d_tab16, &ctx->d_qb16, &ctx->d_mma_items, &ctx->d_mma_units, &ctx->d_mma_cta, &ctx->d_qlist_mma, &ctx->d_surv_blk, &ctx->d_lut, &ctx->d_rinfo, &ctx->d_ranks, &ctx->d_rec, &ctx->d_qrank, &ctx->sort.vals_alt, &ctx->sort.tile_hist, &ctx->sort.digit_hist,
                     &ctx->sort.flags, &ctx->sort.block_sums, &ctx->sort.or_and};
   for (DevBuf *b : bufs) b->release();
   for (int w = 0; w < kMaxKeyWords; ++w) {
@@ -950,6 +1058,7 @@ void hs_destroy(hs_ctx_t *ctx) {
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_chunk) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   ctx->d_hits_sorted_alt.release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -153,6 +153,7 @@ struct hs_ctx {
   // search scratch
   hs::DevBuf d_q64, d_qkeys, d_qvalid, d_qrange, d_tq, d_work, d_qlist, d_surv, d_hits, d_counters;
   hs::DevBuf d_hit_keys[3], d_hit_perm, d_hits_sorted, d_hits_sorted_alt;
+  hs::DevBuf d_surv_blk;                // survivors regrouped by query block (pipelined verify / copy-out)
   cudaStream_t copy_stream = nullptr;   // D2H of sorted hit blocks, overlapped with the next block's search
   std::vector<cudaEvent_t> ev_chunk;
   hs::DevBuf d_misc, d_tabptrs, d_qcodes, d_hits_gathered, d_residues, d_starts;
@@ -164,7 +165,8 @@ struct hs_ctx {
   bool have_qcodes = false;
   hs::DevBuf d_qcodes_det, d_qrow;  // codes recovered from dense queries (Euclid exact stage)
   hs::DevBuf d_qrank;               // u32 [L][Q] bucket slot of every query (0xffffffff: none)
-  void *h_pinned = nullptr;
+  void *h_pinned = nullptr;   // mapped pinned staging of read_back()
+  void *d_pinned = nullptr;
   size_t h_pinned_cap = 0;
 
   // cluster

@@ -18,4 +18,5 @@ struct MmaLaunch {
 int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out,
                FilterArgs *fa_tc = nullptr, uint32_t nblocks_tc = 0, const MmaLaunch *ml = nullptr);
 int ensure_identity_store(hs_ctx *ctx);
+int read_back(hs_ctx *ctx, const void *d_src, void *h_dst, size_t bytes);  // small, synchronising
 }  // namespace hs

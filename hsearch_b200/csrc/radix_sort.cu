@@ -17,6 +17,7 @@
 
 #include "hash.cuh"
 #include "sort.cuh"
+#include "internal.cuh"
 
 namespace hs {
 
@@ -426,8 +427,7 @@ int radix_sort_pairs(hs_ctx *ctx, const KeyPtrs &keys_in, const uint32_t *vals_i
     key_bits_kernel<<<148 * 4, 256, 0, ctx->stream>>>(keys_in.w[w], n, 1, d_oa + 2 * w);
     ctx->stats.kernel_launches++;
   }
-  HS_CUDA(cudaMemcpyAsync(h_oa, d_oa, sizeof h_oa, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  HS_TRY(read_back(ctx, d_oa, h_oa, sizeof h_oa));
   std::vector<Pass> passes;
   plan_passes(h_oa, nw, passes);
 

@@ -439,18 +439,18 @@ def test_rank_path_equals_packed_key_path(oracle, monkeypatch, length, K, L, W, 
 
 
 def test_search_pipelined_blocks_equal_single_pass(oracle, monkeypatch):
-    """HS_PIPELINE=1: >= 2048 queries with a host hit buffer are searched in query blocks whose
-    sorted hits are copied out while the next block runs: same hits, same order as the single
-    pass, also at the capacity limit."""
+    """>= 2048 queries with a host hit buffer: the survivors of the (single) filter pass are split
+    by query block, and each block's sorted hits are copied out while the next block is verified
+    and sorted: same hits, same order as the unpipelined path, also at the capacity limit."""
     length, K, L, W, R = 10, 4, 4, 50.0, 30.0
     codes = random_codes(40000, length, seed=21)
     qcodes = planted_queries(codes, 2600, seed=22, frac=0.5)
     h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
     h.load_fragments(codes)
     h.build_index()
-    monkeypatch.setenv("HS_PIPELINE", "0")
+    monkeypatch.setenv("HS_NO_PIPELINE", "1")
     single = h.search_codes(qcodes)
-    monkeypatch.setenv("HS_PIPELINE", "1")
+    monkeypatch.setenv("HS_NO_PIPELINE", "0")
     blocks = h.search_codes(qcodes)
     assert len(single) > 1000
     assert np.array_equal(single, blocks)
