@@ -10,7 +10,7 @@ $CMD > gpurun_out/plain.log 2>&1; echo plain_rc=$?
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo list_rc=$?
 # 3. one full capture per hot kernel (second launch of each: the first is the sizing pass)
-for K in filter_mma_kernel exact_kernel permute_rec_kernel hash_fast_kernel rank_downsweep_kernel radix_downsweep_kernel; do
+for K in filter_mma_kernel exact_kernel gather_blocked_kernel hash_fast_kernel rank_downsweep_kernel radix_downsweep_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -f -o gpurun_out/prof_$K $CMD > gpurun_out/ncu_$K.log 2>&1
   echo $K rc=$?
 done
