@@ -65,6 +65,49 @@ def gather_hits(hits_u8, nhits, dst=0):
     return None, counts
 
 
+class HitGather:
+    """Gather of the ranks' hit lists to rank `dst`, started asynchronously: the NCCL transfers
+    run beside whatever the caller enqueues next (the next batch's hash and index build) and
+    wait() completes them.  `out` (on dst) receives the lists concatenated in rank order."""
+
+    def __init__(self, hits_u8, nhits, dst=0, out=None):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.work, self.out, self.counts = [], None, [nhits]
+        if self.world == 1:
+            self.out = hits_u8[: nhits * HIT_BYTES]
+            return
+        rank = dist.get_rank()
+        dev = hits_u8.device
+        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, torch.tensor([nhits], dtype=torch.int64, device=dev))
+        self.counts = counts.tolist()
+        ops = []
+        if rank == dst:
+            need = sum(self.counts) * HIT_BYTES
+            self.out = out[:need] if out is not None and out.numel() >= need else \
+                torch.empty(need, dtype=torch.uint8, device=dev)
+            off = 0
+            for r in range(self.world):
+                nb = self.counts[r] * HIT_BYTES
+                if r == dst:
+                    self.out[off:off + nb].copy_(hits_u8[:nb], non_blocking=True)
+                elif nb:
+                    ops.append(dist.P2POp(dist.irecv, self.out[off:off + nb], r))
+                off += nb
+        else:
+            nb = nhits * HIT_BYTES
+            if nb:
+                ops.append(dist.P2POp(dist.isend, hits_u8[:nb], dst))
+        if ops:
+            self.work = dist.batch_isend_irecv(ops)
+
+    def wait(self):
+        for w in self.work:
+            w.wait()
+        self.work = []
+        return self.out, self.counts
+
+
 def sort_hits_reference_order(hits):
     """numpy structured hits -> the reference's output order (query, first table,
     ascending db id; motif_both_points.cpp:224-245)."""
