@@ -688,7 +688,9 @@ int build_code_stores_blocked(hs_ctx *ctx, bool *done) {
   std::vector<uint64_t> voff(L);
   for (uint32_t l = 0; l < L; ++l) {
     TableIndex &T = ctx->tables[l];
-    if ((T.nslots + n / kGatherPart) * (uint64_t)(nchunks + 1) > (64ull << 20)) return HS_OK;
+    // many small buckets (small W / large K): the slot table would be built on the host from
+    // millions of boundaries, and small buckets gain nothing from the blocking
+    if (T.nslots > (1u << 18) || (T.nslots + n / kGatherPart) * (uint64_t)(nchunks + 1) > (64ull << 20)) return HS_OK;
     bs.resize(T.nslots + 1);
     HS_CUDA(cudaMemcpyAsync(bs.data(), T.bstart.p, sizeof(uint32_t) * (T.nslots + 1), cudaMemcpyDeviceToHost, ctx->stream));
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
