@@ -625,9 +625,8 @@ filter_mma_kernel(MmaArgs a) {
           const uint32_t nchunks = ngp >> 4;  // 16-column chunks; this warp takes c = sub, sub + 4, ...
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMmaN;
           const uint32_t qbase = it.q_begin + g * kMmaN;  // index into the query list of column 0
-          uint32_t vv[16];
           // the 16 accumulators in vv = columns col0 .. col0+15 of the group
-          auto scan16 = [&](uint32_t col0) {
+          auto scan16 = [&](const uint32_t (&vv)[16], uint32_t col0) {
             float vf[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) vf[i] = __uint_as_float(vv[i]);
@@ -668,23 +667,39 @@ filter_mma_kernel(MmaArgs a) {
 #endif
             }
           };
-          uint32_t nmine = 0;
-          for (uint32_t c = (uint32_t)sub; c < nchunks; c += 4) {
-            tmem_ld16_issue(taddr + c * 16u, vv);
-            tmem_ld_wait();
-            if (c + 4 >= nchunks) {  // all of this warp's reads of the stage are in registers: release it
-              tc_before();
-              mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
-            }
-#ifdef HS_MMA_PROF
-            if (!(a.debug & 1u))
-#endif
-            scan16(c * 16u);
-            ++nmine;
-          }
-          if (nmine == 0) {  // no chunk for this warp in this group: still release the stage
+          // this warp's chunks c = sub, sub + 4, ...: the load of the next chunk is in flight while
+          // the current one is scanned (two register buffers); the stage is released as soon as the
+          // warp's last load has landed
+          auto release = [&]() {
             tc_before();
             mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
+          };
+#ifdef HS_MMA_PROF
+          const bool do_scan = !(a.debug & 1u);
+#else
+          const bool do_scan = true;
+#endif
+          uint32_t va[16], vb[16];
+          uint32_t c = (uint32_t)sub;
+          if (c < nchunks) {
+            tmem_ld16_issue(taddr + c * 16u, va);
+            for (;;) {
+              tmem_ld_wait();
+              const uint32_t c1 = c + 4u;
+              if (c1 < nchunks) tmem_ld16_issue(taddr + c1 * 16u, vb);
+              else release();
+              if (do_scan) scan16(va, c * 16u);
+              if (c1 >= nchunks) break;
+              tmem_ld_wait();
+              const uint32_t c2 = c1 + 4u;
+              if (c2 < nchunks) tmem_ld16_issue(taddr + c2 * 16u, va);
+              else release();
+              if (do_scan) scan16(vb, c1 * 16u);
+              if (c2 >= nchunks) break;
+              c = c2;
+            }
+          } else {
+            release();  // no chunk for this warp in this group: still release the stage
           }
           __syncwarp();
           const uint32_t wc = *(volatile uint32_t *)wcount;  // warp-uniform

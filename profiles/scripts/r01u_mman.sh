@@ -4,6 +4,3 @@ timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -
 tail -3 gpurun_out/t_mma3.log
 timeout 600 python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/b13.log 2> gpurun_out/b13.err; echo rc=$?
 tail -1 gpurun_out/b13.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N128', d['ms_per_step'], d['stages_ms']['filter_tc'])"
-HS_NVCC_EXTRA=-DHS_MMA_N=64 python hsearch_b200/build.py --force > gpurun_out/build_64.log 2>&1; echo build_rc=$?
-timeout 600 python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/b14.log 2> gpurun_out/b14.err; echo rc=$?
-tail -1 gpurun_out/b14.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N64', d['ms_per_step'], d['stages_ms']['filter_tc'], d['counts']['hits_total'])"
