@@ -225,7 +225,12 @@ def run_native(a):
     # size the hit buffer with one untimed pass
     h.build_index()
     nh0 = h.search_points_dev(qpts.data_ptr(), Q, 0, 0)
-    cap = int(nh0 * 1.05) + 1024
+    if world > 1:   # the same capacity on every rank (padded all-gather blocks)
+        mx = torch.tensor([nh0], dtype=torch.int64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        cap = int(mx.item() * 1.05) + 1024
+    else:
+        cap = int(nh0 * 1.05) + 1024
     # two hit buffers: at N > 1 the gather of batch i to rank 0 (NCCL over NVLink) runs beside
     # the hash / index build of batch i + 1, so a buffer is reused only two steps later
     nslot = 2 if world > 1 else 1

@@ -370,6 +370,8 @@ filter_mma_kernel(MmaArgs a) {
     PROF_DECL(p_wait_c);
     PROF_DECL(p_wait_a);
     PROF_DECL(p_bload);
+    PROF_DECL(p_build);
+    PROF_DECL(p_fence);
 #ifdef HS_MMA_PROF
     const long long p_start = clock64();
 #endif
@@ -433,17 +435,38 @@ filter_mma_kernel(MmaArgs a) {
           mbar_wait(smem_addr(&sh.a_empty[s]), ((pt / S) & 1u) ^ 1u);
           PROF_ADD(p_wait_a);
         }
+#ifdef HS_MMA_PROF
+        const long long _pb0 = clock64();
+#endif
         unsigned char *dst = sA + (size_t)s * a_stage_bytes + row_off;
         float nx = 0.f;
+        // batches of 5 positions: their table rows are loaded before the first is stored, so that the
+        // shared-memory loads overlap (one register quad reused for every position serialises
+        // LDS -> STS -> LDS ...: measured 1.7 k cycles per tile)
 #pragma unroll
-        for (int p = 0; p < LENB; ++p) {
+        for (int p0 = 0; p0 < LENB; p0 += 5) {
+          uint4 rowv[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int p = p0 + j;
+            if (p < LENB && p < len) {
 #ifdef HS_MMA_PROF
-          if (a.debug & 4u) break;  // experiment: no A build
+              if (a.debug & 4u) continue;  // experiment: no A build
 #endif
-          if (p < len) {
-            const int c = min((int)code[p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
-            *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = sh.tab16[c][lane & 7];
-            nx += sh.nx32[c];
+              const int c = min((int)code[p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
+              rowv[j] = sh.tab16[c][lane & 7];
+              nx += sh.nx32[c];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int p = p0 + j;
+            if (p < LENB && p < len) {
+#ifdef HS_MMA_PROF
+              if (a.debug & 4u) continue;
+#endif
+              *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = rowv[j];
+            }
           }
         }
         // rowthr = ((1 - beta) nx - thr) / 2, rounded down; +inf rows never pass
@@ -452,8 +475,15 @@ filter_mma_kernel(MmaArgs a) {
         rt -= (nx + a.thr) * 2.4e-7f + 1e-6f;
         sh.rowthr[pt % kMmaRowRing][r] = valid ? rt : __int_as_float(0x7f800000);
         sh.rowid[pt % kMmaRowRing][r] = myid;
+#ifdef HS_MMA_PROF
+        const long long _pb1 = clock64();
+        p_build += (unsigned long long)(_pb1 - _pb0);
+#endif
         fence_async_shared();
         mbar_arrive_warp(smem_addr(&sh.a_full[s]), lane);
+#ifdef HS_MMA_PROF
+        p_fence += (unsigned long long)(clock64() - _pb1);
+#endif
       }
     }
 #ifdef HS_MMA_PROF
@@ -462,6 +492,8 @@ filter_mma_kernel(MmaArgs a) {
       PROF_OUT(1, p_wait_c);
       PROF_OUT(2, p_wait_a);
       PROF_OUT(3, p_bload);
+      PROF_OUT(16, p_build);
+      PROF_OUT(17, p_fence);
     }
 #endif
   } else if (warp == kMmaIssueWarp) {
@@ -905,8 +937,8 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
   a.thr = thr;
   a.beta = (float)(g.beta * 1.0001);
 #ifdef HS_MMA_PROF
-  HS_TRY(ctx->d_misc.reserve(sizeof(unsigned long long) * 16));
-  HS_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, sizeof(unsigned long long) * 16, ctx->stream));
+  HS_TRY(ctx->d_misc.reserve(sizeof(unsigned long long) * 24));
+  HS_CUDA(cudaMemsetAsync(ctx->d_misc.p, 0, sizeof(unsigned long long) * 24, ctx->stream));
   a.prof = ctx->d_misc.as<unsigned long long>();
   if (const char *e = getenv("HS_MMA_DEBUG")) a.debug = (uint32_t)atoi(e);
 #endif
@@ -931,16 +963,16 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
 #undef HS_MMA
 #ifdef HS_MMA_PROF
   {
-    unsigned long long h[16];
+    unsigned long long h[24];
     cudaMemcpyAsync(h, a.prof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     const double g = (double)grid;
     fprintf(stderr,
             "[mma prof] grid %u units %u | producer: total %.0f wait_codes %.0f wait_a_empty %.0f bload %.0f | "
             "issuer: wait_a_full %.0f wait_t_empty %.0f wait_b %.0f groups %.0f | epilogue(warp0): total %.0f "
-            "wait_t_full %.0f issuer_unit %.0f rare %.0f issuer_mma %.0f issuer_commit %.0f unit_fetch %.0f issuer_total %.0f (cycles per CTA)\n",
+            "wait_t_full %.0f issuer_unit %.0f rare %.0f issuer_mma %.0f issuer_commit %.0f unit_fetch %.0f issuer_total %.0f | producer build %.0f fence+arrive %.0f (cycles per CTA)\n",
             grid, nunits, h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g, h[5] / g, h[6] / g, h[7] / g, h[8] / g,
-            h[9] / g, h[10] / g, h[11] / g, h[12] / g, h[13] / g, h[14] / g, h[15] / g);
+            h[9] / g, h[10] / g, h[11] / g, h[12] / g, h[13] / g, h[14] / g, h[15] / g, h[16] / g, h[17] / g);
   }
 #endif
   HS_CUDA(cudaGetLastError());

@@ -1,0 +1,5 @@
+set -x
+mkdir -p gpurun_out
+HS_NVCC_EXTRA=-DHS_MMA_PROF python hsearch_b200/build.py --force > gpurun_out/build_prof.log 2>&1; echo build_rc=$?
+HS_MMA_DEBUG=0 timeout 600 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --n-db 50000000 > gpurun_out/b21.log 2> gpurun_out/b21.err; echo rc=$?
+grep "mma prof" gpurun_out/b21.err | tail -1
