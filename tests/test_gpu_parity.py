@@ -546,3 +546,75 @@ def test_blocked_gather_equals_per_table_gather(oracle, monkeypatch, W):
     sub = hits[hits["query"] < 20]
     d = oracle.embed(codes[sub["db_id"]], tab) - oracle.embed(qcodes[sub["query"]], tab)
     assert np.all((d * d).sum(axis=1) <= R * R * (1 + 1e-12))
+
+
+def _greedy_reference(codes, table, a, b, W, R, oracle):
+    """Clustering() of hclust2.cpp:86-151 restated in Python on top of the oracle's hash and
+    distance (small inputs only)."""
+    n = len(codes)
+    L = a.shape[0]
+    pts = oracle.embed(codes, table)
+    strings = oracle.key_strings(oracle.hash_codes(codes, table, a, b, W))
+    merged = np.zeros(n, dtype=np.uint8)
+    center = np.arange(n, dtype=np.uint32)
+    rnd = np.full(n, 0xFFFFFFFF, dtype=np.uint32)
+    for l in range(L):
+        buckets = {}
+        for i in range(n):
+            if merged[i] != 2:
+                buckets.setdefault(strings[i, l], []).append(i)
+        for ids in buckets.values():
+            centers = [i for i in ids if merged[i] == 1]
+            for i in ids:
+                if merged[i] == 0:
+                    for c in centers:
+                        if not (np.sqrt(oracle.dist2(pts[i], pts[c])) > R):
+                            merged[c] = 1
+                            merged[i] = 2
+                            center[i] = c
+                            rnd[i] = l
+                            break
+                if merged[i] == 0:
+                    centers.append(i)
+    return center, rnd, merged
+
+
+@pytest.mark.parametrize("length,K,L,W,R,n", [(10, 4, 4, 50.0, 25.0, 1500), (10, 2, 3, 20.0, 30.0, 1200),
+                                              (25, 3, 2, 80.0, 60.0, 800), (8, 4, 1, 50.0, 1e9, 300)])
+def test_greedy_cluster_matches_restatement(oracle, length, K, L, W, R, n):
+    """hs_greedy_cluster against a direct restatement of hclust2's Clustering() (the CLI test
+    compares with the reference binary itself); R = 1e9 joins every bucket to its first member."""
+    codes = planted_families(n, length, seed=61)
+    h, a, b = make(length, K, L, W, R, table_variant=hb.HS_TABLE_FULL, predicate=hb.HS_PRED_SQRT_LE_R, flags=0)
+    h.load_fragments(codes)
+    h.build_index()
+    center, rnd, merged = h.greedy_cluster()
+    wc, wr, wm = _greedy_reference(codes, oracle.coordinates(False), a, b, W, R, oracle)
+    assert np.array_equal(merged, wm)
+    assert np.array_equal(center, wc)
+    assert np.array_equal(rnd, wr)
+    assert (merged == 2).sum() > 0
+    h.close()
+
+
+def test_search_pipelined_dense_queries_and_small_capacity(oracle, monkeypatch):
+    """The query-block pipeline with dense (non-residue) centres and a hit buffer that overflows
+    in a middle block: the needed size is reported and the retry returns the single-pass hits."""
+    length, K, L, W, R = 10, 4, 4, 50.0, 32.0
+    codes = random_codes(30000, length, seed=71)
+    tab = oracle.coordinates(True)
+    rng = np.random.default_rng(72)
+    q = oracle.embed(planted_queries(codes, 2300, seed=73, frac=0.8), tab)
+    q[::3] += rng.normal(0.0, 0.5, size=q[::3].shape)      # every third centre is not a residue string
+    h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+    h.load_fragments(codes)
+    h.build_index()
+    monkeypatch.setenv("HS_NO_PIPELINE", "1")
+    single = h.search_points(q)
+    monkeypatch.setenv("HS_NO_PIPELINE", "0")
+    assert len(single) > 500
+    assert np.array_equal(h.search_points(q), single)
+    assert np.array_equal(h.search_points(q, cap=len(single) // 2), single)
+    want, _, _ = oracle.search(oracle.embed(codes, tab), q[:200], a, b, W, R)
+    assert hits_as_tuples(single[single["query"] < 200]) == hits_as_tuples(want)
+    h.close()

@@ -127,3 +127,31 @@ def test_orf6_matches_oracle(oracle):
     with pytest.raises(hb.HsError):
         h.orf6(["ACGTNACGT"])
     h.close()
+
+
+def test_parse_fasta_capacity_protocol():
+    lib = capi.load()
+    data = b">a\nARND\n>b\nCEQG\n"
+    nseq, nnames, nres = C.c_uint32(), C.c_uint32(), C.c_uint64()
+    res = C.create_string_buffer(3)   # too small: 8 residues
+    start = np.zeros(3, dtype=np.uint64)
+    rc = lib.hs_parse_fasta(data, len(data), res, 3, capi.ptr(start, C.c_uint64), 3, None, None, 0,
+                            C.byref(nseq), C.byref(nnames), C.byref(nres))
+    assert rc == capi.HS_ERR_CAPACITY and (nseq.value, nnames.value, nres.value) == (2, 2, 8)
+    assert lib.hs_parse_fasta(None, 0, None, 0, None, 0, None, None, 0, None, None, None) == capi.HS_ERR_INVALID
+
+
+@pytest.mark.gpu
+def test_sequence_entry_points_edge_cases(oracle):
+    w, t, b = oracle.klsh_generate(512, 16, 0.2)
+    h = hb.HSearch(10, 4, 4, 50.0, 30.0)
+    hv, valid, feat, fixed = h.kmer3_klsh([], w, t, b)
+    assert len(hv) == 0 and fixed == 0
+    assert h.orf6([]) == []
+    # capacity error of hs_orf6
+    data = b"ACGTACGTACGT"
+    start = np.array([0, 12], dtype=np.uint64)
+    ln = np.zeros(6, dtype=np.int32)
+    out = C.create_string_buffer(8)
+    assert h.lib.hs_orf6(h.ctx, data, capi.ptr(start, C.c_uint64), 1, out, 8, capi.ptr(ln, C.c_int32)) == capi.HS_ERR_CAPACITY
+    h.close()
