@@ -161,7 +161,7 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
           }
         }
       };
-      if (args.k4_full) {
+      if (RANK && REP > 1 && args.k4_full) {
         // K = 4 and every slot of the chunk in use (the reference's configuration): the
         // (table, projection) walk is fully static
 #pragma unroll
@@ -322,8 +322,12 @@ template <int NQ, int KW, bool RANK>
 static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
                             unsigned long long *counters, uint64_t f0, uint64_t f1) {
   // 768 threads leave 85 registers per thread: 16 accumulators without spills
-  if (NQ <= 4 && ctx->prm.len <= 16 && hash_smem_bytes(ctx, NQ, 8, kHashRepThreads, args.full_rec != 0) <= kHashRepBudget)
-    return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads>(ctx, chunk, args, buckets, counters, f0, f1);
+  // the replicated-table kernel exists for the rank path with up to 16 projections per launch
+  // (the reference's configurations); everything else takes the plain layout
+  if constexpr (RANK && NQ <= 4) {
+    if (ctx->prm.len <= 16 && hash_smem_bytes(ctx, NQ, 8, kHashRepThreads, args.full_rec != 0) <= kHashRepBudget)
+      return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads>(ctx, chunk, args, buckets, counters, f0, f1);
+  }
   return launch_fast_rep<NQ, KW, RANK, 1, kHashThreads>(ctx, chunk, args, buckets, counters, f0, f1);
 }
 
