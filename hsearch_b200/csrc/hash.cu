@@ -13,12 +13,17 @@ namespace hs {
 
 constexpr int kHashThreads = 256;
 
+__device__ __noinline__ int exact_bucket_codes_cold(const uint8_t *codes, int len, const double *__restrict__ table64,
+                                                    const double *__restrict__ a_row, double b, double W) {
+  return exact_bucket_codes(codes, len, table64, a_row, b, W);
+}
+
 // counters[0] guard_hits, [1] guard_corrected, [2] key overflow / bucket out of range, [3] residual flips
 // RANK: write dense u16 bucket ranks (and the fragment records) instead of packed keys.
 // REP: copies of every 16-byte table cell (8: copy j lives in bank group j and lane i reads
 // copy i & 7, so the random-row LDS.128 gathers are bank-conflict free; 1: plain layout for
 // tables too large to replicate).  Persistent blocks: the table is staged once per block.
-template <int NQ, int KW, bool RANK, int REP, int NT>
+template <int NQ, int KW, bool RANK, int REP, int NT, bool K4>
 __global__ void __launch_bounds__(NT)
 hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                  const float *__restrict__ T32,    // [len][20][4*NQ] of this chunk
@@ -132,7 +137,9 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
         const float e = args.eps32[s];
         if ((tt - f) < e || ((f + 1.0f) - tt) < e) {
           const int l = args.l0 + t;
-          const int ex = exact_bucket_codes(myc, len, table64, a64 + ((size_t)l * K + k) * dim, b64[l * K + k], W);
+          // out of line: the FP64 evaluation runs for ~3e-5 of the projections; inlined 16 times it
+          // made the kernel 10 k instructions long and the hot path jump across it
+          const int ex = exact_bucket_codes_cold(myc, len, table64, a64 + ((size_t)l * K + k) * dim, b64[l * K + k], W);
           ++my_guard;
           if (ex != bucket) ++my_corr;
           bucket = ex;
@@ -161,7 +168,7 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
           }
         }
       };
-      if (RANK && REP > 1 && args.k4_full) {
+      if constexpr (K4) {
         // K = 4 and every slot of the chunk in use (the reference's configuration): the
         // (table, projection) walk is fully static
 #pragma unroll
@@ -294,13 +301,13 @@ static size_t hash_smem_bytes(const hs_ctx *ctx, int NQ, int rep, int nt, bool f
          (full_rec ? (size_t)nt * ctx->rec_stride : 0);
 }
 
-template <int NQ, int KW, bool RANK, int REP, int NT>
+template <int NQ, int KW, bool RANK, int REP, int NT, bool K4 = false>
 static int launch_fast_rep(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
                            unsigned long long *counters, uint64_t f0, uint64_t f1) {
   const int P = 4 * NQ;
   const int len = (int)ctx->prm.len;
   const size_t smem = hash_smem_bytes(ctx, NQ, REP, NT, args.full_rec != 0);
-  auto kern = hash_fast_kernel<NQ, KW, RANK, REP, NT>;
+  auto kern = hash_fast_kernel<NQ, KW, RANK, REP, NT, K4>;
   if (smem > 48 * 1024) HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -325,8 +332,11 @@ static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, i
   // the replicated-table kernel exists for the rank path with up to 16 projections per launch
   // (the reference's configurations); everything else takes the plain layout
   if constexpr (RANK && NQ <= 4) {
-    if (ctx->prm.len <= 16 && hash_smem_bytes(ctx, NQ, 8, kHashRepThreads, args.full_rec != 0) <= kHashRepBudget)
+    if (ctx->prm.len <= 16 && hash_smem_bytes(ctx, NQ, 8, kHashRepThreads, args.full_rec != 0) <= kHashRepBudget) {
+      if (args.k4_full)  // K = 4, all slots in use: statically unrolled (table, projection) walk
+        return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads, true>(ctx, chunk, args, buckets, counters, f0, f1);
       return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads>(ctx, chunk, args, buckets, counters, f0, f1);
+    }
   }
   return launch_fast_rep<NQ, KW, RANK, 1, kHashThreads>(ctx, chunk, args, buckets, counters, f0, f1);
 }
