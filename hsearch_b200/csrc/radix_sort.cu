@@ -26,6 +26,20 @@ constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per tile
 constexpr int kSortWarps = kSortThreads / 32;
 
+// Lanes of the warp holding the same digit d (0..256; 256 = out of range), from 9 ballots:
+// match.any walks the distinct values of the warp one by one, which for random 8-bit digits is
+// ~28 rounds per call; the ballot form is a fixed 9 votes + 9 logic ops.
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d) {
+  uint32_t peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t v = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? v : ~v;
+  }
+  return peers;
+}
+
 // ---- OR / AND reduction of the key words -------------------------------------
 __global__ void key_bits_kernel(const uint64_t *__restrict__ keys, uint64_t n, int nw,
                                 unsigned long long *__restrict__ or_and /* [nw][2] */) {
@@ -202,7 +216,7 @@ radix_downsweep_kernel(KeyPtrs in, const uint32_t *__restrict__ val_in, KeyPtrs 
   for (int j = 0; j < kSortItems; ++j) {
     const uint64_t idx = warp_base + (uint64_t)j * 32 + lane;
     const uint32_t d = idx < n ? ((uint32_t)(key[j] >> shift) & mask) : 256u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t peers = digit_peers(d);
     const uint32_t pre = s_whist[wid][d];
     __syncwarp();
     lp[j] = pre + __popc(peers & lt_mask);
@@ -808,7 +822,7 @@ rank_downsweep_kernel(const uint16_t *__restrict__ key_in, const uint32_t *__res
 #pragma unroll
   for (int j = 0; j < kRkItems; ++j) {
     const uint32_t d = key[j] != 0xffffffffu ? ((key[j] >> shift) & mask) : 256u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t peers = digit_peers(d);
     const uint32_t pre = s_whist[wid][d];
     __syncwarp();
     lp[j] = pre + __popc(peers & lt_mask);
