@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="DB fragments per host core in the CPU leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-recall", action="store_true", help="skip the full-size brute-force recall measurement")
     ap.add_argument("--audit", action="store_true", help="FP64 audit of every projection (residual flips)")
     ap.add_argument("--scalar-filter", action="store_true", help="A/B: keep all candidates on the scalar filter")
     return ap.parse_args()
@@ -472,6 +473,40 @@ def run_native(a):
     except Exception as e:  # the checks must never break the bench line
         checks = {"error": repr(e)}
 
+    # ---- recall at full size (outside the timed region; rank 0's shard) ---------------------
+    # brute force of all Q x N pairs on the same GPU path (hs_bruteforce_points_dev: tensor filter
+    # over the whole DB + exact FP64 stage); every LSH hit is a brute-force hit, so the recall is
+    # the ratio of the two lists, unweighted and with the reference's weight()
+    # (motif_both_points.cpp:67-87)
+    recall = None
+    if not a.no_recall:
+        try:
+            with torch.cuda.stream(stream):
+                hflags = h.params.flags
+                t0r = time.perf_counter()
+                nbf = h.bruteforce_points_dev(qpts.data_ptr(), Q, 0, 0)
+                bcap = nbf + 1024
+                bf = torch.empty(bcap * 24, dtype=torch.uint8, device=dev)
+                nbf = h.bruteforce_points_dev(qpts.data_ptr(), Q, bf.data_ptr(), bcap)
+                torch.cuda.synchronize()
+                bf_ms = 1e3 * (time.perf_counter() - t0r) / 2
+            s_bf = h.stats().as_dict()
+
+            def wsum(buf, n):
+                d = buf[:n * 24].view(torch.float64)[2::3].sqrt()
+                w = torch.where(d < 24.0, torch.ones_like(d), torch.clamp(1.0 / (d - 24.0), max=1.0))
+                return float(w.sum().item())
+            lsh_buf = hits_bufs[(step_no[0] - 1) % nslot]
+            nl = min(int(nh), cap)
+            recall = {"unweighted": nl / nbf if nbf else None,
+                      "weighted": wsum(lsh_buf, nl) / wsum(bf, nbf) if nbf else None,
+                      "lsh_hits": nl, "bruteforce_hits": int(nbf), "bruteforce_pairs": int(Q) * int(N),
+                      "bruteforce_ms": round(s_bf["ms_total"], 2), "bruteforce_wall_ms": round(bf_ms, 2),
+                      "note": "rank 0's shard; brute force = hs_bruteforce_points_dev (same predicate d2 <= R^2)"}
+            del bf
+        except Exception as e:
+            recall = {"error": repr(e)}
+
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         cpu = cpu_leg(a, a.cpu_sample)
@@ -491,7 +526,7 @@ def run_native(a):
            "clocks": clocks, "wall_ms_per_step": wall_ms / a.steps,
            "e2e": e2e, "gpu_launches": int(acc["kernel_launches"]),
            "roofline": roofline, "cpu_baseline": cpu,
-           "checks": checks,
+           "checks": checks, "recall": recall,
            "stages_ms": {k[3:]: round(acc[k] / steps, 4) for k in sorted(acc) if k.startswith("ms_")},
            "kernels": {k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "share": round(v["share_of_step"], 4)}
                        for k, v in kern.items()},

@@ -26,7 +26,7 @@ EXPORTS = [
     "hs_generate_projection", "hs_set_projection", "hs_load_fragments", "hs_load_fragments_dev",
     "hs_extract_windows", "hs_num_fragments", "hs_hash", "hs_get_keys", "hs_pack_key_string", "hs_build_index",
     "hs_table_sizes", "hs_get_table", "hs_search_points", "hs_search_codes", "hs_search_points_dev",
-    "hs_bruteforce_codes", "hs_bruteforce_points", "hs_cluster", "hs_comm_init", "hs_comm_unique_id",
+    "hs_bruteforce_codes", "hs_bruteforce_points", "hs_bruteforce_points_dev", "hs_cluster", "hs_comm_init", "hs_comm_unique_id",
     "hs_greedy_cluster", "hs_union_find", "hs_parse_fasta", "hs_klsh_generate", "hs_kmer3_klsh", "hs_orf6",
 ]
 
@@ -101,6 +101,7 @@ def load(build_if_missing=True):
     lib.hs_search_points_dev.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, u64p]
     lib.hs_bruteforce_codes.argtypes = [vp, u8p, C.c_uint32, vp, C.c_uint64, u64p]
     lib.hs_bruteforce_points.argtypes = [vp, dblp, C.c_uint32, vp, C.c_uint64, u64p]
+    lib.hs_bruteforce_points_dev.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, u64p]
     lib.hs_cluster.argtypes = [vp, u32p]
     lib.hs_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.hs_comm_unique_id.argtypes = [vp]

@@ -860,7 +860,7 @@ __global__ void build_tq_from_db_kernel(const uint8_t *__restrict__ codes, uint6
 }
 
 static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit *hits, uint64_t cap,
-                           uint64_t *nhits) {
+                           uint64_t *nhits, void *hits_dev = nullptr) {
   if (ctx->N == 0) {
     set_error("hs_bruteforce: no fragments loaded");
     return HS_ERR_INVALID;
@@ -938,7 +938,7 @@ static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit
   unsigned long long nh = 0;
   HS_CUDA(cudaMemcpyAsync(&nh, hit_count, sizeof nh, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  int rc = deliver_hits(ctx, nh, dev_cap, hits, nullptr, cap, nhits, ev[5], ev[6]);
+  int rc = deliver_hits(ctx, nh, dev_cap, hits, hits_dev, cap, nhits, ev[5], ev[6]);
   HS_CUDA(cudaEventRecord(ev[7], ctx->stream));
   HS_CUDA(cudaEventSynchronize(ev[7]));
   ctx->stats.ms_filter = ms_filter;
@@ -1410,6 +1410,18 @@ int hs_bruteforce_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hi
   QueryInput in;
   in.h_points = qpoints;
   return bruteforce_impl(ctx, &in, Q, hits, cap, nhits);
+}
+
+int hs_bruteforce_points_dev(hs_ctx_t *ctx, const void *qpoints_dev, uint32_t Q, void *hits_dev, uint64_t cap,
+                             uint64_t *nhits) {
+  if (!ctx || (!qpoints_dev && Q) || (!hits_dev && cap) || !nhits) {
+    set_error("hs_bruteforce_points_dev: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  QueryInput in;
+  in.d_points = qpoints_dev;
+  return bruteforce_impl(ctx, &in, Q, nullptr, cap, nhits, hits_dev);
 }
 
 int hs_cluster(hs_ctx_t *ctx, uint32_t *label_out) {

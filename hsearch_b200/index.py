@@ -180,6 +180,15 @@ class HSearch:
             check(rc)
         return n.value
 
+    def bruteforce_points_dev(self, q_dev_ptr, Q, hits_dev_ptr, cap):
+        """Brute force with device-resident queries / hit buffer; returns the hit count (may exceed cap)."""
+        n = C.c_uint64(0)
+        rc = self.lib.hs_bruteforce_points_dev(self.ctx, C.c_void_p(q_dev_ptr), Q, C.c_void_p(hits_dev_ptr), cap,
+                                               C.byref(n))
+        if rc != capi.HS_ERR_CAPACITY:
+            check(rc)
+        return n.value
+
     # ---- search ------------------------------------------------------------------
     def _call_hits(self, fn, qarr, qctype, Q, cap, grow=True):
         cap = int(cap)

@@ -221,6 +221,10 @@ int hs_bruteforce_codes(hs_ctx_t *ctx, const uint8_t *qcodes, uint32_t Q, hs_hit
                         uint64_t *nhits);
 int hs_bruteforce_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hit *hits, uint64_t cap,
                          uint64_t *nhits);
+/* Device-resident variant (queries and hit buffer are device pointers); with cap == 0 only the
+ * hit count is produced -- the denominator of the recall of an LSH search at full size. */
+int hs_bruteforce_points_dev(hs_ctx_t *ctx, const void *qpoints_dev, uint32_t Q, void *hits_dev, uint64_t cap,
+                             uint64_t *nhits);
 
 /* ---- cluster (U1) ----------------------------------------------------------- */
 /* Connected components of the near-pair graph: every pair sharing a bucket in
