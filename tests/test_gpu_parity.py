@@ -618,3 +618,29 @@ def test_search_pipelined_dense_queries_and_small_capacity(oracle, monkeypatch):
     want, _, _ = oracle.search(oracle.embed(codes, tab), q[:200], a, b, W, R)
     assert hits_as_tuples(single[single["query"] < 200]) == hits_as_tuples(want)
     h.close()
+
+
+def test_bruteforce_points_dev_matches_host_variant(oracle):
+    """Device-resident brute force (queries and hits on the device; cap == 0 gives the count only)."""
+    torch = pytest.importorskip("torch")
+    length, R = 10, 30.0
+    codes = random_codes(20000, length, seed=81)
+    tab = oracle.coordinates(True)
+    q = oracle.embed(planted_queries(codes, 50, seed=82, frac=0.6), tab)
+    h, a, b = make(length, 4, 4, 50.0, R, flags=hb.HS_FLAG_SORT_HITS)
+    h.load_fragments(codes)
+    want = h.bruteforce_points(q)
+    stream = torch.cuda.ExternalStream(h.stream_ptr())
+    with torch.cuda.stream(stream):
+        qd = torch.from_numpy(q).cuda()
+        torch.cuda.synchronize()
+        n = h.bruteforce_points_dev(qd.data_ptr(), len(q), 0, 0)
+        assert n == len(want) > 0
+        buf = torch.zeros(n * 24, dtype=torch.uint8, device="cuda")
+        assert h.bruteforce_points_dev(qd.data_ptr(), len(q), buf.data_ptr(), n) == n
+        torch.cuda.synchronize()
+    got = np.frombuffer(buf.cpu().numpy().tobytes(), dtype=hb.HIT_DTYPE)
+    assert np.array_equal(got, want)
+    ref = oracle.bruteforce(oracle.embed(codes, tab), q, R, pred=0)
+    assert hits_as_tuples(got, False) == hits_as_tuples(ref, False)
+    h.close()
