@@ -644,3 +644,27 @@ def test_bruteforce_points_dev_matches_host_variant(oracle):
     ref = oracle.bruteforce(oracle.embed(codes, tab), q, R, pred=0)
     assert hits_as_tuples(got, False) == hits_as_tuples(ref, False)
     h.close()
+
+
+def test_blocked_gather_long_fragments(oracle, monkeypatch):
+    """len 25: two 16-byte words of codes per record (48-byte records) through the blocked gather,
+    the tensor filter and the exact stage."""
+    length, K, L, W, R = 25, 4, 3, 120.0, 62.0
+    n = 1_500_007
+    codes = random_codes(n, length, seed=91)
+    qcodes = planted_queries(codes[:50000], 200, seed=92, frac=0.7)
+    res = []
+    for off in ("1", "0"):
+        monkeypatch.setenv("HS_NO_BLOCKED_GATHER", off)
+        h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+        h.load_fragments(codes)
+        h.build_index()
+        res.append((h.search_codes(qcodes), h.table_sizes()))
+        h.close()
+    assert np.array_equal(res[0][1], res[1][1])
+    assert len(res[0][0]) > 100 and np.array_equal(res[0][0], res[1][0])
+    tab = oracle.coordinates(True)
+    sub = res[1][0][res[1][0]["query"] < 40]
+    want, _, _ = oracle.search(oracle.embed(codes[:200000], tab), oracle.embed(qcodes[:40], tab), a, b, W, R)
+    got_sub = sub[sub["db_id"] < 200000]
+    assert hits_as_tuples(got_sub) == hits_as_tuples(want)
