@@ -345,6 +345,8 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
     HS_TRY(mma_geometry(ctx, &g));
     HS_TRY(ctx->d_qb16.reserve(sizeof(uint16_t) * (size_t)std::max<uint32_t>(tq_rows, 1) * g.kp + 16));
     if (mode == kModeAllPairs) HS_TRY(launch_build_qb_codes(ctx, tq_base, tq_rows, ctx->d_qb16.p));
+    else if (mode == kModeSelfJoin)  // queries = positions tq_base .. of the (single) table of the plan
+      HS_TRY(launch_build_qb_store(ctx, P.mma_items[0].table, tq_base, tq_rows, ctx->d_qb16.p));
     else HS_TRY(launch_build_qb_points(ctx, ctx->d_q64.as<double>(), tq_rows, ctx->d_qb16.p));
     ml.grid = grid;
     ml.nunits = nunits;
@@ -381,6 +383,26 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
     HS_TRY(launch_tq_to_half(ctx, ctx->d_tq.as<float>(), tq_rows, ctx->d_tq16.p));
   }
   return run_filter(ctx, fa, P.nblocks, mode, nsurv, &ft, P.nblocks_tc, &ml);
+}
+
+// Cluster: all pairs i < j inside the bucket [mb, me) of `table` through the tensor filter
+// (queries = the bucket's own members).  Returns false in *used when the tensor path does not
+// apply (integer metric, tiny bucket); survivors land in ctx->d_surv as usual.
+int selfjoin_bucket_mma(hs_ctx *ctx, uint32_t table, uint32_t mb, uint32_t me, uint64_t *nsurv, uint64_t *npairs,
+                        bool *used) {
+  *used = false;
+  *nsurv = 0;
+  FilterPlan P;
+  plan_init(ctx, P);
+  if (!P.mma || me - mb < 1024) return HS_OK;
+  std::vector<uint32_t> q(me - mb);
+  for (uint32_t i = 0; i < me - mb; ++i) q[i] = mb + i;
+  HS_TRY(plan_add(ctx, P, table, mb, me, q.data(), q.size(), true));
+  if (P.mma_units.empty() || !P.items.empty() || !P.items_tc.empty()) return HS_OK;
+  *npairs = (uint64_t)(me - mb) * (me - mb - 1) / 2;
+  HS_TRY(plan_run(ctx, P, me - mb, mb, kModeSelfJoin, nsurv));
+  *used = true;
+  return HS_OK;
 }
 
 // ---- hits in the reference's output order -----------------------------------------

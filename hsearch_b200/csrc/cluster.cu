@@ -159,6 +159,34 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
       std::vector<uint2> large(h_nlarge);
       HS_CUDA(cudaMemcpy(large.data(), ctx->d_large.p, sizeof(uint2) * h_nlarge, cudaMemcpyDeviceToHost));
       std::sort(large.begin(), large.end(), [](const uint2 &a, const uint2 &b) { return a.x < b.x; });
+      // buckets of >= 1024 members: all pairs through the tensor filter (queries = the bucket's
+      // own members), one bucket at a time; the rest through the tiled scalar self-join below
+      {
+        std::vector<uint2> rest;
+        for (const uint2 &bk : large) {
+          uint64_t nsurv = 0, np = 0;
+          bool used = false;
+          HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
+          HS_TRY(selfjoin_bucket_mma(ctx, l, bk.x, bk.y, &nsurv, &np, &used));
+          if (!used) {
+            rest.push_back(bk);
+            continue;
+          }
+          HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
+          ncand += np;
+          ctx->stats.n_candidates_tc += np;
+          ea.surv = ctx->d_surv.as<Survivor>();
+          ea.nsurv = nsurv;
+          ea.qlist_mma = ctx->d_qlist_mma.as<uint32_t>();
+          HS_TRY(launch_exact(ctx, ea));
+          HS_CUDA(cudaEventRecord(ev[6], ctx->stream));
+          HS_CUDA(cudaEventSynchronize(ev[6]));
+          nsurv_total += nsurv;
+          ms_f2 += ev_ms(ev[4], ev[5]);
+          ms_e2 += ev_ms(ev[5], ev[6]);
+        }
+        large.swap(rest);
+      }
       std::vector<WorkItem> items;
       uint32_t nblocks = 0;
       size_t bi = 0;

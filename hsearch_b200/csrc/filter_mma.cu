@@ -822,6 +822,27 @@ __global__ void build_qb_codes_kernel(const uint8_t *__restrict__ codes, uint64_
   write_cq(row, len * HS_CDIM, kp, n2, mx, beta);
 }
 
+// queries = the members at positions pos0 .. pos0+nq-1 of a bucket-ordered, position-major code
+// store (cluster self-join of a large bucket)
+__global__ void build_qb_store_kernel(const uint8_t *__restrict__ store, uint64_t npad, uint32_t pos0, uint32_t nq,
+                                      int len, int kp, const double *__restrict__ table64, double beta,
+                                      __half *__restrict__ qb16) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  __half *row = qb16 + (size_t)q * kp;
+  double n2 = 0.0, mx = 0.0;
+  for (int p = 0; p < len; ++p) {
+    const int c = min((int)store[(uint64_t)p * npad + pos0 + q] / kCodeScale, HS_AA - 1);
+    for (int j = 0; j < HS_CDIM; ++j) {
+      const double v = table64[c * HS_CDIM + j];
+      n2 += v * v;
+      mx = fmax(mx, fabs(v));
+      row[p * HS_CDIM + j] = __double2half(v);
+    }
+  }
+  write_cq(row, len * HS_CDIM, kp, n2, mx, beta);
+}
+
 // ---- host side ----------------------------------------------------------------------------
 static inline double mma_beta(int kp) {
   // |x~q~ - xq| <= (2^-10 + 2^-22)|x||q| per product (both operands rounded to FP16), FP32
@@ -901,6 +922,18 @@ int launch_build_qb_codes(hs_ctx *ctx, uint64_t q0, uint32_t nq, void *d_qb16) {
   build_qb_codes_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_codes.as<uint8_t>(), q0, nq,
                                                                    (int)ctx->prm.len, g.kp, ctx->d_table64.as<double>(),
                                                                    g.beta, reinterpret_cast<__half *>(d_qb16));
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+int launch_build_qb_store(hs_ctx *ctx, uint32_t table, uint32_t pos0, uint32_t nq, void *d_qb16) {
+  if (nq == 0) return HS_OK;
+  MmaGeometry g;
+  HS_TRY(mma_geometry(ctx, &g));
+  build_qb_store_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(
+      ctx->tables[table].codes_sorted.as<uint8_t>(), ctx->npad, pos0, nq, (int)ctx->prm.len, g.kp,
+      ctx->d_table64.as<double>(), g.beta, reinterpret_cast<__half *>(d_qb16));
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;

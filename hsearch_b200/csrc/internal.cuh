@@ -18,5 +18,7 @@ struct MmaLaunch {
 int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out,
                FilterArgs *fa_tc = nullptr, uint32_t nblocks_tc = 0, const MmaLaunch *ml = nullptr);
 int ensure_identity_store(hs_ctx *ctx);
+int selfjoin_bucket_mma(hs_ctx *ctx, uint32_t table, uint32_t mb, uint32_t me, uint64_t *nsurv, uint64_t *npairs,
+                        bool *used);
 int read_back(hs_ctx *ctx, const void *d_src, void *h_dst, size_t bytes);  // small, synchronising
 }  // namespace hs

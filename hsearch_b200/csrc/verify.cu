@@ -379,8 +379,12 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(ExactArgs a) {
       bool have_qc = false;
       if (live) {
         if (a.mode == kModeSelfJoin) {
-          qid = ids ? (uint64_t)__ldg(ids + s.query) : (uint64_t)s.query;
-          load_record<NV>(a.rec + qid * a.rec_stride, qw);
+          // s.query: position of the query member (scalar filter) or, from the tensor filter,
+          // the index of that position in its query list
+          const uint32_t qpos = (s.pad & 1u) ? a.qlist_mma[s.query] : s.query;
+          qid = ids ? (uint64_t)__ldg(ids + qpos) : (uint64_t)qpos;
+          live = (s.pad & 1u) ? (qid < id) : true;  // tensor filter: keep each unordered pair once
+          if (live) load_record<NV>(a.rec + qid * a.rec_stride, qw);
           have_qc = true;
         } else if (a.mode == kModeAllPairs && a.q64 == nullptr && a.qcodes == nullptr) {
           load_record<NV>(a.rec + qid * a.rec_stride, qw);  // all pairs of the DB: the query is a DB fragment

@@ -668,3 +668,25 @@ def test_blocked_gather_long_fragments(oracle, monkeypatch):
     want, _, _ = oracle.search(oracle.embed(codes[:200000], tab), oracle.embed(qcodes[:40], tab), a, b, W, R)
     got_sub = sub[sub["db_id"] < 200000]
     assert hits_as_tuples(got_sub) == hits_as_tuples(want)
+
+
+@pytest.mark.parametrize("R,pred", [(25.0, hb.HS_PRED_SQRT_LE_R), (30.0, hb.HS_PRED_D2_LE_R2)])
+def test_cluster_large_buckets_through_tensor_filter(oracle, R, pred):
+    """Buckets of >= 1024 members are self-joined by the tcgen05 filter (queries = the bucket's own
+    members): same partition as the oracle and as the scalar-filter path."""
+    length, K, L, W = 10, 4, 3, 50.0
+    codes = planted_families(40000, length, seed=95)     # W = 50: the largest buckets hold ~8 % of the DB
+    res = []
+    for flags in (0, hb.HS_FLAG_SCALAR_FILTER):
+        h, a, b = make(length, K, L, W, R, predicate=pred, flags=flags)
+        h.load_fragments(codes)
+        h.build_index()
+        res.append((h.cluster(), h.stats().as_dict()))
+        h.close()
+    assert res[0][1]["n_candidates_tc"] > 1e7 and res[1][1]["n_candidates_tc"] == 0
+    assert res[0][1]["n_edges"] == res[1][1]["n_edges"] > 0
+    assert np.array_equal(res[0][0], res[1][0])
+    want, ne = oracle.cluster(codes, oracle.coordinates(True), a, b, W, R, metric=0) if pred == hb.HS_PRED_SQRT_LE_R \
+        else (None, 0)
+    if want is not None:
+        assert np.array_equal(res[0][0], want)
