@@ -388,13 +388,16 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
 // Cluster: all pairs i < j inside the bucket [mb, me) of `table` through the tensor filter
 // (queries = the bucket's own members).  Returns false in *used when the tensor path does not
 // apply (integer metric, tiny bucket); survivors land in ctx->d_surv as usual.
+// (one launch + synchronisation per bucket: below ~8 k members the tiled scalar self-join, which
+// batches many buckets per launch, is faster -- measured at 1 M fragments)
+constexpr uint32_t kSelfJoinMmaMin = 8192;
 int selfjoin_bucket_mma(hs_ctx *ctx, uint32_t table, uint32_t mb, uint32_t me, uint64_t *nsurv, uint64_t *npairs,
                         bool *used) {
   *used = false;
   *nsurv = 0;
   FilterPlan P;
   plan_init(ctx, P);
-  if (!P.mma || me - mb < 1024) return HS_OK;
+  if (!P.mma || me - mb < kSelfJoinMmaMin) return HS_OK;
   std::vector<uint32_t> q(me - mb);
   for (uint32_t i = 0; i < me - mb; ++i) q[i] = mb + i;
   HS_TRY(plan_add(ctx, P, table, mb, me, q.data(), q.size(), true));

@@ -159,7 +159,7 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
       std::vector<uint2> large(h_nlarge);
       HS_CUDA(cudaMemcpy(large.data(), ctx->d_large.p, sizeof(uint2) * h_nlarge, cudaMemcpyDeviceToHost));
       std::sort(large.begin(), large.end(), [](const uint2 &a, const uint2 &b) { return a.x < b.x; });
-      // buckets of >= 1024 members: all pairs through the tensor filter (queries = the bucket's
+      // buckets of >= 8192 members: all pairs through the tensor filter (queries = the bucket's
       // own members), one bucket at a time; the rest through the tiled scalar self-join below
       {
         std::vector<uint2> rest;

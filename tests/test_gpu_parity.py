@@ -672,10 +672,10 @@ def test_blocked_gather_long_fragments(oracle, monkeypatch):
 
 @pytest.mark.parametrize("R,pred", [(25.0, hb.HS_PRED_SQRT_LE_R), (30.0, hb.HS_PRED_D2_LE_R2)])
 def test_cluster_large_buckets_through_tensor_filter(oracle, R, pred):
-    """Buckets of >= 1024 members are self-joined by the tcgen05 filter (queries = the bucket's own
+    """Buckets of >= 8192 members are self-joined by the tcgen05 filter (queries = the bucket's own
     members): same partition as the oracle and as the scalar-filter path."""
     length, K, L, W = 10, 4, 3, 50.0
-    codes = planted_families(40000, length, seed=95)     # W = 50: the largest buckets hold ~8 % of the DB
+    codes = planted_families(115000, length, seed=95)    # W = 50: the largest buckets hold ~8 % of the DB
     res = []
     for flags in (0, hb.HS_FLAG_SCALAR_FILTER):
         h, a, b = make(length, K, L, W, R, predicate=pred, flags=flags)
