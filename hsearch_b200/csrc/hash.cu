@@ -23,7 +23,7 @@ __device__ __noinline__ int exact_bucket_codes_cold(const uint8_t *codes, int le
 // REP: copies of every 16-byte table cell (8: copy j lives in bank group j and lane i reads
 // copy i & 7, so the random-row LDS.128 gathers are bank-conflict free; 1: plain layout for
 // tables too large to replicate).  Persistent blocks: the table is staged once per block.
-template <int NQ, int KW, bool RANK, int REP, int NT, bool K4>
+template <int NQ, int KW, bool RANK, int REP, int NT, bool K4, int G>
 __global__ void __launch_bounds__(NT)
 hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                  const float *__restrict__ T32,    // [len][20][4*NQ] of this chunk
@@ -37,12 +37,23 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
   // 16-byte words of the next tile's codes held in registers: NT * 16 * NPF bytes >= NT * len
   // (the replicated-table path is taken for len <= 16 only)
   constexpr int NPF = REP > 1 ? 1 : 2;
+  // G groups of GT = NT / G threads share the table but walk their own tiles (GT fragments each)
+  // with their own buffers and named barriers, so that one group computes while the other
+  // waits for its codes or copies its records out
+  constexpr int GT = NT / G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4 *sT = reinterpret_cast<float4 *>(smem_raw);                             // len*20*NQ*REP cells
-  uint8_t *sC = smem_raw + (size_t)len * HS_AA * NQ * REP * sizeof(float4);      // NT*len bytes
-  uint8_t *sRec = sC + (((size_t)NT * len + 15) & ~(size_t)15);                  // NT*rec_stride (full_rec)
-
   const int tid = threadIdx.x;
+  const int gid = tid / GT, gt = tid - gid * GT;
+  const size_t codes_bytes = ((size_t)GT * len + 15) & ~(size_t)15;
+  uint8_t *sC = smem_raw + (size_t)len * HS_AA * NQ * REP * sizeof(float4) + (size_t)gid * codes_bytes;  // GT*len bytes
+  uint8_t *sRec = smem_raw + (size_t)len * HS_AA * NQ * REP * sizeof(float4) + (size_t)G * codes_bytes +
+                  (size_t)gid * GT * args.rec_stride;                            // GT*rec_stride (full_rec)
+  auto group_sync = [&]() {
+    if (G == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(GT) : "memory");
+  };
+
   const bool full_rec = RANK && args.full_rec;
   const uint32_t RS = args.rec_stride;
   {
@@ -59,50 +70,52 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
       for (int i = tid; i < n4; i += NT) sT[i] = src[i];
     }
   }
+  if (G > 1) __syncthreads();  // the table is staged by all threads; the loop below only syncs groups
   const float4 *myT = sT + (REP > 1 ? (tid & (REP - 1)) : 0);
   unsigned int my_guard = 0, my_corr = 0, my_over = 0;
   // this launch hashes the fragments [f0, f1)
-  const uint64_t tile0 = f0 / NT;
-  const uint64_t ntiles = (f1 + NT - 1) / NT;
+  const uint64_t tile0 = f0 / GT;
+  const uint64_t ntiles = (f1 + GT - 1) / GT;
   const uint64_t total_bytes = f1 * (uint64_t)len;
   // the tile's code bytes are contiguous in global memory (16-byte aligned start): whole 16-byte
   // words are prefetched into registers one tile ahead, the ragged end of the DB byte by byte
   uint4 pf[NPF];
   auto prefetch = [&](uint64_t tile) {
-    const uint64_t byte0 = tile * NT * (uint64_t)len;
+    const uint64_t byte0 = tile * GT * (uint64_t)len;
 #pragma unroll
     for (int v = 0; v < NPF; ++v) {
-      const uint64_t off = byte0 + ((uint64_t)v * NT + tid) * 16;
+      const uint64_t off = byte0 + ((uint64_t)v * GT + gt) * 16;
       pf[v] = make_uint4(0u, 0u, 0u, 0u);
-      if (tile < ntiles && ((uint64_t)v * NT + tid) * 16 < (uint64_t)NT * len && off + 16 <= total_bytes)
+      if (tile < ntiles && ((uint64_t)v * GT + gt) * 16 < (uint64_t)GT * len && off + 16 <= total_bytes)
         pf[v] = __ldg(reinterpret_cast<const uint4 *>(codes + off));
     }
   };
-  prefetch(tile0 + blockIdx.x);
-  for (uint64_t tile = tile0 + blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint64_t frag0 = tile * NT;
-    const uint64_t nfrag = min((uint64_t)NT, f1 - frag0);
-    __syncthreads();  // the previous tile's sC / sRec are no longer read
+  const uint64_t tstride = (uint64_t)gridDim.x * G;
+  prefetch(tile0 + (uint64_t)blockIdx.x * G + gid);
+  for (uint64_t tile = tile0 + (uint64_t)blockIdx.x * G + gid; tile < ntiles; tile += tstride) {
+    const uint64_t frag0 = tile * GT;
+    const uint64_t nfrag = min((uint64_t)GT, f1 - frag0);
+    group_sync();  // the previous tile's sC / sRec are no longer read
     {
       const uint64_t byte0 = frag0 * (uint64_t)len;
       const uint32_t nbytes = (uint32_t)(nfrag * (uint64_t)len);
 #pragma unroll
       for (int v = 0; v < NPF; ++v) {
-        const uint32_t o = ((uint32_t)v * NT + tid) * 16u;
+        const uint32_t o = ((uint32_t)v * GT + gt) * 16u;
         if (o + 16u <= nbytes) *reinterpret_cast<uint4 *>(sC + o) = pf[v];
       }
-      for (uint32_t i = (nbytes & ~15u) + tid; i < nbytes; i += NT) sC[i] = codes[byte0 + i];
+      for (uint32_t i = (nbytes & ~15u) + gt; i < nbytes; i += GT) sC[i] = codes[byte0 + i];
     }
     if (full_rec) {
       uint4 *z = reinterpret_cast<uint4 *>(sRec);
-      for (uint32_t i = tid; i < (uint32_t)NT * RS / 16; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (uint32_t i = gt; i < (uint32_t)GT * RS / 16; i += GT) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    prefetch(tile + gridDim.x);
-    __syncthreads();
-    if ((uint64_t)tid < nfrag) {
-      const uint64_t frag = frag0 + tid;
-      const uint8_t *myc = sC + tid * len;
-      uint8_t *myrec = sRec + (size_t)tid * RS;
+    prefetch(tile + tstride);
+    group_sync();
+    if ((uint64_t)gt < nfrag) {
+      const uint64_t frag = frag0 + gt;
+      const uint8_t *myc = sC + gt * len;
+      uint8_t *myrec = sRec + (size_t)gt * RS;
 
       float acc[P];
 #pragma unroll
@@ -187,11 +200,11 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
     }
     if (full_rec) {
       // the tile's records are contiguous in global memory: coalesced 16-byte copies
-      __syncthreads();
+      group_sync();
       const uint32_t nvec = (uint32_t)(nfrag * RS / 16);
       const uint4 *src = reinterpret_cast<const uint4 *>(sRec);
       uint4 *dst = reinterpret_cast<uint4 *>(args.rec + frag0 * RS);
-      for (uint32_t i = tid; i < nvec; i += NT) dst[i] = src[i];
+      for (uint32_t i = gt; i < nvec; i += GT) dst[i] = src[i];
     }
   }
   if (my_guard) atomicAdd(counters + 0, (unsigned long long)my_guard);
@@ -292,28 +305,29 @@ __global__ void hash_queries_kernel(const double *__restrict__ q64, uint32_t Q, 
 }
 
 // ---- host side ---------------------------------------------------------------
-constexpr int kHashRepThreads = 768;            // one persistent block per SM on the replicated-table path
+constexpr int kHashRepThreads = 1024;           // one persistent block per SM on the replicated-table path
 constexpr size_t kHashRepBudget = 200 * 1024;   // replicated table + tile buffers
 
-static size_t hash_smem_bytes(const hs_ctx *ctx, int NQ, int rep, int nt, bool full_rec) {
+static size_t hash_smem_bytes(const hs_ctx *ctx, int NQ, int rep, int nt, bool full_rec, int groups = 1) {
   const size_t len = ctx->prm.len;
-  return len * HS_AA * NQ * rep * sizeof(float4) + (((size_t)nt * len + 15) & ~(size_t)15) +
+  return len * HS_AA * NQ * rep * sizeof(float4) + groups * ((((size_t)nt / groups) * len + 15) & ~(size_t)15) +
          (full_rec ? (size_t)nt * ctx->rec_stride : 0);
 }
 
-template <int NQ, int KW, bool RANK, int REP, int NT, bool K4 = false>
+template <int NQ, int KW, bool RANK, int REP, int NT, bool K4 = false, int G = 1>
 static int launch_fast_rep(hs_ctx *ctx, int chunk, const HashChunkArgs &args, int32_t *buckets,
                            unsigned long long *counters, uint64_t f0, uint64_t f1) {
   const int P = 4 * NQ;
   const int len = (int)ctx->prm.len;
-  const size_t smem = hash_smem_bytes(ctx, NQ, REP, NT, args.full_rec != 0);
-  auto kern = hash_fast_kernel<NQ, KW, RANK, REP, NT, K4>;
+  constexpr int GT = NT / G;
+  const size_t smem = hash_smem_bytes(ctx, NQ, REP, NT, args.full_rec != 0, G);
+  auto kern = hash_fast_kernel<NQ, KW, RANK, REP, NT, K4, G>;
   if (smem > 48 * 1024) HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
   if (per_sm < 1) per_sm = 1;
-  const uint64_t ntiles = (f1 + NT - 1) / NT - f0 / NT;
-  const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * per_sm);
+  const uint64_t ntiles = (f1 + GT - 1) / GT - f0 / GT;
+  const unsigned grid = (unsigned)std::min<uint64_t>((ntiles + G - 1) / G, (uint64_t)ctx->num_sms * per_sm);
   const float *T = ctx->d_T32.as<float>() + (size_t)chunk * len * HS_AA * P;
   kern<<<grid, NT, smem, ctx->stream>>>(
       ctx->d_codes.as<uint8_t>(), ctx->N, len, T, ctx->d_b32.as<float>() + (size_t)chunk * P,
@@ -334,8 +348,8 @@ static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, i
   if constexpr (RANK && NQ <= 4) {
     if (ctx->prm.len <= 16 && hash_smem_bytes(ctx, NQ, 8, kHashRepThreads, args.full_rec != 0) <= kHashRepBudget) {
       if (args.k4_full)  // K = 4, all slots in use: statically unrolled (table, projection) walk
-        return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads, true>(ctx, chunk, args, buckets, counters, f0, f1);
-      return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads>(ctx, chunk, args, buckets, counters, f0, f1);
+        return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads, true, 4>(ctx, chunk, args, buckets, counters, f0, f1);
+      return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads, false, 4>(ctx, chunk, args, buckets, counters, f0, f1);
     }
   }
   return launch_fast_rep<NQ, KW, RANK, 1, kHashThreads>(ctx, chunk, args, buckets, counters, f0, f1);
