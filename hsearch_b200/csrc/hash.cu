@@ -51,6 +51,7 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                   (size_t)gid * GT * args.rec_stride;                            // GT*rec_stride (full_rec)
   auto group_sync = [&]() {
     if (G == 1) __syncthreads();
+    else if (GT == 32) __syncwarp();  // one warp per tile: no block-level barrier at all
     else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(GT) : "memory");
   };
 
@@ -348,8 +349,8 @@ static int launch_fast_inst(hs_ctx *ctx, int chunk, const HashChunkArgs &args, i
   if constexpr (RANK && NQ <= 4) {
     if (ctx->prm.len <= 16 && hash_smem_bytes(ctx, NQ, 8, kHashRepThreads, args.full_rec != 0) <= kHashRepBudget) {
       if (args.k4_full)  // K = 4, all slots in use: statically unrolled (table, projection) walk
-        return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads, true, 4>(ctx, chunk, args, buckets, counters, f0, f1);
-      return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads, false, 4>(ctx, chunk, args, buckets, counters, f0, f1);
+        return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads, true, 8>(ctx, chunk, args, buckets, counters, f0, f1);
+      return launch_fast_rep<NQ, KW, RANK, 8, kHashRepThreads, false, 8>(ctx, chunk, args, buckets, counters, f0, f1);
     }
   }
   return launch_fast_rep<NQ, KW, RANK, 1, kHashThreads>(ctx, chunk, args, buckets, counters, f0, f1);
