@@ -63,7 +63,11 @@ def workload_name(a):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons every 50 ms.  Started before the warm-up steps (nvidia-smi
+    needs a few hundred ms to come up, longer than a short timed region); stop(t0, t1) keeps the
+    samples whose timestamps fall inside the timed region [t0, t1] (time.time() seconds) and falls
+    back to all samples under load (warm-up + timed steps, the same workload) when none does."""
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -80,9 +84,10 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)  # let the sample covering the end of the region be written
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -90,23 +95,27 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, smmax, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1]))
-                smmax.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[2]), float(c[3]), [n for n, v in zip(names, c[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nme, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
         os.unlink(self.f.name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t0 is not None and t0 - 0.05 <= r[0] <= t1 + 0.05]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed steps (no sample fell inside the timed region)"
+        sm = [r[1] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "samples": len(sm), "window": window, "reasons": reasons}
 
 
 # ------------------------------------------------------------------ CPU legs
@@ -290,17 +299,18 @@ def run_native(a):
                 pending[i] = None
 
     with torch.cuda.stream(stream):
+        sampler = ClockSampler(local)
+        sampler.start()
         for _ in range(a.warmup):
             step(False)
         drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        wall0 = time.time()
         e0.record(stream)
         for _ in range(a.steps):
             nh, nh_total, s_search, s_build, s_hash = step(True)
@@ -308,9 +318,10 @@ def run_native(a):
         e1.record(stream)
         torch.cuda.synchronize()
         wall_ms = 1e3 * (time.perf_counter() - t0)
+        wall1 = time.time()
         if world > 1:
             dist.barrier()
-        clocks = sampler.stop()
+        clocks = sampler.stop(wall0, wall1)
     dev_ms = e0.elapsed_time(e1)
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
