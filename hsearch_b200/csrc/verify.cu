@@ -366,6 +366,13 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(ExactArgs a) {
     uint64_t id = 0, qid = 0;
     Survivor s;
     s.table = 0;
+    // the record of the survivor this thread takes next: pulled into L2 now, so that the gather
+    // of the next iteration does not wait for DRAM (the exact stage stalls mostly on that load)
+    if (i + stride < a.nsurv) {
+      const Survivor nx = a.surv[i + stride];
+      if (nx.pad & 2u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rec + (uint64_t)nx.pos * a.rec_stride));
+    }
     if (i < a.nsurv) {
       s = a.surv[i];
       const uint32_t *ids = a.sorted_ids[s.table];
