@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 rm -f gpurun_out/prof_*.ncu-rep gpurun_out/launches.csv
-CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-recall"
 # 1. the command exits 0 without ncu
 $CMD > gpurun_out/plain.log 2>&1; echo plain_rc=$?
 # 2. launch list: per-launch durations (cold cache, serialised -- compare SHARES)

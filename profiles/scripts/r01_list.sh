@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-recall"
+$CMD > gpurun_out/plain.log 2>&1; echo plain_rc=$?
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+echo list_rc=$?
