@@ -457,9 +457,14 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
   uint32_t *perm = ctx->d_hit_perm.as<uint32_t>();
   const hs_stats before = ctx->stats;
   // one-word key when the three fields fit 64 bits (they do unless ids are astronomically large)
+  // fields packed tightly from bit 0 (db id, then table, then query): the radix sort walks 8-bit
+  // windows over the varying bits, so a gap between the fields would cost an extra pass.  Ids
+  // gathered from other ranks may exceed this rank's range: the kernel flags that (overflow) and
+  // the two-word path is taken.
   const int qbits = bits_for(std::max<uint64_t>(ctx->hit_qmax, 1)), tbits = bits_for((uint64_t)ctx->prm.L + 1);
-  const int qshift = 64 - qbits, tshift = qshift - tbits;
-  bool one_word = tshift >= 20;
+  const int ibits = bits_for(std::max<uint64_t>(ctx->hit_idmax ? ctx->hit_idmax : ctx->id_base + ctx->N, 2));
+  const int tshift = ibits, qshift = ibits + tbits;
+  bool one_word = qshift + qbits <= 64;
   if (one_word) {
     unsigned int *ovf = reinterpret_cast<unsigned int *>(ctx->d_counters.as<unsigned long long>() + 14);
     HS_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned int), ctx->stream));

@@ -162,6 +162,7 @@ struct hs_ctx {
   hs::DevBuf d_qb16, d_mma_items, d_mma_units, d_mma_cta, d_qlist_mma;
   int num_sms = 0;
   uint64_t hit_qmax = 0;   // query ids of the current call are < hit_qmax (hit sort key width)
+  uint64_t hit_idmax = 0;  // db ids of the hits being sorted are < hit_idmax (0: id_base + N)
   bool have_qcodes = false;
   hs::DevBuf d_qcodes_det, d_qrow;  // codes recovered from dense queries (Euclid exact stage)
   hs::DevBuf d_qrank;               // u32 [L][Q] bucket slot of every query (0xffffffff: none)
