@@ -476,7 +476,9 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
   }
   if (one_word) {
     in.w[0] = ctx->d_hit_keys[0].as<uint64_t>();
-    HS_TRY(radix_sort_pairs(ctx, in, nullptr, n, 1, perm, perm + n, &sorted));
+    const int kbits = qshift + qbits;
+    HS_TRY(radix_sort_pairs(ctx, in, nullptr, n, 1, perm, perm + n, &sorted,
+                            kbits >= 64 ? ~0ull : ((1ull << kbits) - 1ull)));
   } else {
     HS_TRY(ctx->d_hit_keys[1].reserve(sizeof(uint64_t) * n));
     hit_keys_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, n, ctx->d_hit_keys[0].as<uint64_t>(),

@@ -11,6 +11,7 @@
 // and moves all words.  Digit windows are placed only over bits that actually
 // vary across the input (OR/AND reduction), so constant nibbles cost nothing.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -421,7 +422,7 @@ static void launch_downsweep(hs_ctx *ctx, const KeyPtrs &in, const uint32_t *vin
 // sorted key words are left in the scratch (or in keys_in when no bit varies)
 // and returned through *sorted_keys, valid until the next sort.
 int radix_sort_pairs(hs_ctx *ctx, const KeyPtrs &keys_in, const uint32_t *vals_in, uint64_t n, int nw,
-                     uint32_t *v_final, uint32_t *v_tmp, KeyPtrs *sorted_keys) {
+                     uint32_t *v_final, uint32_t *v_tmp, KeyPtrs *sorted_keys, uint64_t vary_hint) {
   SortScratch &S = ctx->sort;
   *sorted_keys = keys_in;
   if (n == 0) return HS_OK;
@@ -436,12 +437,19 @@ int radix_sort_pairs(hs_ctx *ctx, const KeyPtrs &keys_in, const uint32_t *vals_i
     h_init[2 * w + 1] = ~0ull;
   }
   unsigned long long *d_oa = S.or_and.as<unsigned long long>();
-  HS_CUDA(cudaMemcpyAsync(d_oa, h_init, sizeof h_init, cudaMemcpyHostToDevice, ctx->stream));
-  for (int w = 0; w < nw; ++w) {
-    key_bits_kernel<<<148 * 4, 256, 0, ctx->stream>>>(keys_in.w[w], n, 1, d_oa + 2 * w);
-    ctx->stats.kernel_launches++;
+  if (vary_hint && nw == 1) {
+    // the caller knows which bits of the (single) key word can vary: no reduction pass, no sync
+    memcpy(h_oa, h_init, sizeof h_oa);
+    h_oa[0] = vary_hint;
+    h_oa[1] = 0ull;
+  } else {
+    HS_CUDA(cudaMemcpyAsync(d_oa, h_init, sizeof h_init, cudaMemcpyHostToDevice, ctx->stream));
+    for (int w = 0; w < nw; ++w) {
+      key_bits_kernel<<<148 * 4, 256, 0, ctx->stream>>>(keys_in.w[w], n, 1, d_oa + 2 * w);
+      ctx->stats.kernel_launches++;
+    }
+    HS_TRY(read_back(ctx, d_oa, h_oa, sizeof h_oa));
   }
-  HS_TRY(read_back(ctx, d_oa, h_oa, sizeof h_oa));
   std::vector<Pass> passes;
   plan_passes(h_oa, nw, passes);
 
