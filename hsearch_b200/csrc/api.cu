@@ -202,7 +202,6 @@ struct FilterPlan {
   uint32_t mma_qmax = 0;
   std::vector<MmaItemHost> mma_items;
   std::vector<MmaUnitHost> mma_units;
-  std::vector<uint64_t> mma_cost;  // per unit
   std::vector<uint32_t> qlist_mma;
 };
 
@@ -238,7 +237,6 @@ static int plan_add(const hs_ctx *ctx, FilterPlan &P, uint32_t table, uint32_t m
       const uint32_t item = (uint32_t)P.mma_items.size();
       P.mma_items.push_back(it);
       const uint32_t step = kMmaUnitTiles * 128u;
-      const uint64_t nqp = std::max<uint64_t>(64, ((ce - c) + 15) & ~(size_t)15);
       for (uint64_t m = m0; m < me; m += step) {
         MmaUnitHost un;
         un.item = item;
@@ -246,7 +244,6 @@ static int plan_add(const hs_ctx *ctx, FilterPlan &P, uint32_t table, uint32_t m
         un.m_end = (uint32_t)std::min<uint64_t>(me, m + step);
         un.pad = 0;
         P.mma_units.push_back(un);
-        P.mma_cost.push_back((uint64_t)((un.m_end - un.m_begin + 127) / 128) * nqp + 256);
       }
       const uint64_t pairs = (uint64_t)(me - m0) * (ce - c);
       P.ncand += pairs;

@@ -610,10 +610,7 @@ filter_mma_kernel(MmaArgs a) {
     uint32_t *wcount = &sh.wcount[warp];  // staged survivors (entries past the capacity went to global memory)
     uint32_t et = 0, eg = 0;
     PROF_DECL(e_wait_t);
-    PROF_DECL(e_ld);
     PROF_DECL(e_rare);
-    PROF_DECL(e_issue);
-    PROF_DECL(e_arrive);
     PROF_DECL(e_unit);
 #ifdef HS_MMA_PROF
     const long long e_start = clock64();
@@ -752,10 +749,7 @@ filter_mma_kernel(MmaArgs a) {
     if (tid == 0) {
       PROF_OUT(8, (unsigned long long)(clock64() - e_start));
       PROF_OUT(9, e_wait_t);
-      PROF_OUT(10, e_ld);
       PROF_OUT(11, e_rare);
-      PROF_OUT(12, e_issue);
-      PROF_OUT(13, e_arrive);
       PROF_OUT(14, e_unit);
     }
 #endif

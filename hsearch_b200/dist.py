@@ -135,10 +135,6 @@ def sort_hits_reference_order(hits):
 # (key, global id, codes) record goes to the rank that owns its bucket (owner = mix(key) mod
 # world), the owner finds the in-bucket near pairs of the complete buckets it holds, the
 # resulting edges are all-gathered and every rank runs the same union-find over them.
-def _device_of(t):
-    return t.device
-
-
 def allgather_rows(t):
     """Variable-length all_gather along dim 0; returns the rows of all ranks in rank order."""
     world = dist.get_world_size() if dist.is_initialized() else 1
