@@ -884,22 +884,45 @@ rank_downsweep_kernel(const uint16_t *__restrict__ key_in, const uint32_t *__res
 }
 
 // Bucket boundaries from the sorted ranks: slot r starts at the first position whose rank
-// is >= r (empty slots get start == end); *nb counts the non-empty slots.
+// is >= r (empty slots get start == end); *nb counts the non-empty slots.  Eight ranks per
+// thread (one 16-byte load).
 __global__ void __launch_bounds__(256)
 rank_bounds_kernel(const uint16_t *__restrict__ sorted, uint64_t n, uint32_t nr, uint32_t *__restrict__ bstart,
                    unsigned int *__restrict__ nb) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool head = false;
-  if (i < n) {
-    const int k = (int)sorted[i];
-    const int prev = i ? (int)sorted[i - 1] : -1;
-    head = k != prev;
-    for (int r = prev + 1; r <= k; ++r) bstart[r] = (uint32_t)i;
-    if (i == n - 1)
-      for (uint32_t r = (uint32_t)k + 1; r <= nr; ++r) bstart[r] = (uint32_t)n;
+  const uint64_t i8 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  unsigned int heads = 0;
+  if (i8 < n) {
+    uint32_t k[8];
+    if (i8 + 8 <= n) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(sorted + i8));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        k[2 * j] = w[j] & 0xffffu;
+        k[2 * j + 1] = w[j] >> 16;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) k[j] = i8 + j < n ? (uint32_t)sorted[i8 + j] : 0u;
+    }
+    int prev = i8 ? (int)sorted[i8 - 1] : -1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (i8 + j < n) {
+        const int cur = (int)k[j];
+        if (cur != prev) {
+          ++heads;
+          for (int r = prev + 1; r <= cur; ++r) bstart[r] = (uint32_t)(i8 + j);
+          prev = cur;
+        }
+      }
+    }
+    if (i8 + 8 >= n)
+      for (uint32_t r = (uint32_t)prev + 1; r <= nr; ++r) bstart[r] = (uint32_t)n;
   }
-  const uint32_t m = __ballot_sync(0xffffffffu, head);
-  if (m && (threadIdx.x & 31) == 0) atomicAdd(nb, (unsigned int)__popc(m));
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) heads += __shfl_xor_sync(0xffffffffu, heads, sft);
+  if (heads && (threadIdx.x & 31) == 0) atomicAdd(nb, heads);
 }
 
 // Rank path of build_table_index: two-pass (or one-pass) sort of the table's u16 ranks,
@@ -960,7 +983,7 @@ static int build_table_index_ranks(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_s
   HS_TRY(S.or_and.reserve(sizeof(unsigned long long) * 2 * kMaxKeyWords));
   unsigned int *d_nb = S.or_and.as<unsigned int>();
   HS_CUDA(cudaMemsetAsync(d_nb, 0, sizeof(unsigned int), ctx->stream));
-  rank_bounds_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ksorted, n, nr, T.bstart.as<uint32_t>(), d_nb);
+  rank_bounds_kernel<<<(unsigned)(((n + 7) / 8 + 255) / 256), 256, 0, ctx->stream>>>(ksorted, n, nr, T.bstart.as<uint32_t>(), d_nb);
   ctx->stats.kernel_launches++;
   HS_TRY(T.ukeys.reserve(sizeof(uint64_t) * KW * (uint64_t)nr));
   HS_CUDA(cudaMemcpyAsync(T.ukeys.p, ctx->h_rkeys[table].data(), sizeof(uint64_t) * KW * nr, cudaMemcpyHostToDevice,
