@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhsearch_b200.so")
+LIB_PATH = os.environ.get("HS_LIBRARY") or os.path.join(HERE, "libhsearch_b200.so")  # HS_LIBRARY: experiments only
 
 HS_OK = 0
 HS_ERR_INVALID, HS_ERR_CUDA, HS_ERR_CAPACITY, HS_ERR_UNSUPPORTED, HS_ERR_NOMEM, HS_ERR_COMM = -1, -2, -3, -4, -5, -6

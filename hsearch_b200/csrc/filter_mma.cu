@@ -52,7 +52,10 @@ constexpr int kMmaProdThread0 = kMmaEpiWarps * 32;                    // 512
 constexpr int kMmaIssueWarp = kMmaEpiWarps + kMmaProdWarps;           // 20
 constexpr int kMmaLoadWarp = kMmaIssueWarp + 1;                       // 21: unit scheduler + code loader
 constexpr int kMmaUnitRing = 4;      // units published ahead by the scheduler
-constexpr int kMmaUnitBatch = 4;     // consecutive units taken per atomic (keeps B resident)
+#ifndef HS_MMA_UNIT_BATCH
+#define HS_MMA_UNIT_BATCH 4
+#endif
+constexpr int kMmaUnitBatch = HS_MMA_UNIT_BATCH;  // consecutive units taken per atomic (keeps B resident)
 constexpr int kMmaMaxCodeRing = 8;   // tiles of residue codes in flight (bulk async copies)
 constexpr int kMmaM = 128;           // members per tile (UMMA M)
 #ifndef HS_MMA_N

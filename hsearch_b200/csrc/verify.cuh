@@ -86,7 +86,10 @@ struct MmaItemHost {
 struct MmaUnitHost {
   uint32_t item, m_begin, m_end, pad;
 };
-constexpr uint32_t kMmaUnitTiles = 32;        // 128-member tiles per unit
+#ifndef HS_MMA_UNIT_TILES
+#define HS_MMA_UNIT_TILES 32
+#endif
+constexpr uint32_t kMmaUnitTiles = HS_MMA_UNIT_TILES;  // 128-member tiles per unit
 constexpr uint32_t kMmaMinMembers = 64;
 int mma_geometry(const hs_ctx *ctx, MmaGeometry *g);
 bool mma_filter_usable(const hs_ctx *ctx);
