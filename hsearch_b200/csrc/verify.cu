@@ -500,8 +500,17 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(ExactArgs a) {
 int launch_exact(hs_ctx *ctx, const ExactArgs &args) {
   if (args.nsurv == 0) return HS_OK;
   const unsigned long long want = (args.nsurv + kExactThreads - 1) / kExactThreads;
-  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->num_sms * 8);
-  if (args.len <= 16) exact_kernel<1><<<grid, kExactThreads, 0, ctx->stream>>>(args);
+  // grid-stride kernel: exactly one wave of resident blocks (a partial second wave would start
+  // when the first ends and leave most SMs idle for its duration)
+  static int per_sm[2] = {0, 0};
+  const int v = args.len <= 16 ? 0 : 1;
+  if (!per_sm[v]) {
+    if (v == 0) HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], exact_kernel<1>, kExactThreads, 0));
+    else HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], exact_kernel<2>, kExactThreads, 0));
+    if (per_sm[v] < 1) per_sm[v] = 1;
+  }
+  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->num_sms * per_sm[v]);
+  if (v == 0) exact_kernel<1><<<grid, kExactThreads, 0, ctx->stream>>>(args);
   else exact_kernel<2><<<grid, kExactThreads, 0, ctx->stream>>>(args);
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
