@@ -593,7 +593,10 @@ int build_code_store(hs_ctx *ctx, const uint32_t *ids, DevBuf &out) {
 // ncu: DRAM reads 52.9 GB -> 18.8 GB at L = 4).
 constexpr uint32_t kGatherBlockBytes = 16u << 20;  // measured best on B200 (8-16 MB; 4 and 32 MB are slower)
 constexpr int kGatherSlots = 256;     // slots per thread block
-constexpr uint32_t kGatherPart = 4096; // members per slot at most
+#ifndef HS_GATHER_PART
+#define HS_GATHER_PART 2048  // measured at 100 M fragments: 512 -> 10.9, 1024 -> 10.1, 2048 -> 5.4, 4096 -> 6.0, 8192 -> 7.8 ms
+#endif
+constexpr uint32_t kGatherPart = HS_GATHER_PART;  // members per slot at most
 constexpr int kGatherThreads = 256;
 
 struct GatherTab {
