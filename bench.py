@@ -503,17 +503,23 @@ def run_native(a):
                 bf_ms = 1e3 * (time.perf_counter() - t0r) / 2
             s_bf = h.stats().as_dict()
 
-            def wsum(buf, n):
-                d = buf[:n * 24].view(torch.float64)[2::3].sqrt()
-                w = torch.where(d < 24.0, torch.ones_like(d), torch.clamp(1.0 / (d - 24.0), max=1.0))
-                return float(w.sum().item())
             lsh_buf = hits_bufs[(step_no[0] - 1) % nslot]
             nl = min(int(nh), cap)
-            recall = {"unweighted": nl / nbf if nbf else None,
-                      "weighted": wsum(lsh_buf, nl) / wsum(bf, nbf) if nbf else None,
+            # evaulate() of the reference on the two device-resident lists (hs_evaluate_recall_dev)
+            t0e = time.perf_counter()
+            ev = h.evaluate_recall_dev(bf.data_ptr(), int(nbf), lsh_buf.data_ptr(), nl, Q)
+            ev_ms = 1e3 * (time.perf_counter() - t0e)
+            nzb = [int(i) for i in ((ev["tp_bin"] + ev["fn_bin"]) > 0).nonzero()[0]]
+            deciles = {str(i): round(float(ev["tp_bin"][i]) / float(ev["tp_bin"][i] + ev["fn_bin"][i]), 4)
+                       for i in nzb if i % 10 == 9 or i == nzb[-1]}
+            recall = {"unweighted": ev["n_tp"] / nbf if nbf else None,
+                      "weighted": ev["recall"] if nbf else None,
                       "lsh_hits": nl, "bruteforce_hits": int(nbf), "bruteforce_pairs": int(Q) * int(N),
+                      "found_not_in_truth": ev["n_extra"],
+                      "recall_by_distance_bin": deciles, "evaluate_wall_ms": round(ev_ms, 2),
                       "bruteforce_ms": round(s_bf["ms_total"], 2), "bruteforce_wall_ms": round(bf_ms, 2),
-                      "note": "rank 0's shard; brute force = hs_bruteforce_points_dev (same predicate d2 <= R^2)"}
+                      "note": "rank 0's shard; brute force = hs_bruteforce_points_dev (same predicate d2 <= R^2); "
+                              "join = hs_evaluate_recall_dev (motif_both_points.cpp:100-165); bins are int(dis*10)"}
             del bf
         except Exception as e:
             recall = {"error": repr(e)}

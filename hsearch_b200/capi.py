@@ -28,6 +28,7 @@ EXPORTS = [
     "hs_table_sizes", "hs_get_table", "hs_search_points", "hs_search_codes", "hs_search_points_dev",
     "hs_bruteforce_codes", "hs_bruteforce_points", "hs_bruteforce_points_dev", "hs_cluster", "hs_comm_init", "hs_comm_unique_id",
     "hs_greedy_cluster", "hs_union_find", "hs_parse_fasta", "hs_klsh_generate", "hs_kmer3_klsh", "hs_orf6",
+    "hs_evaluate_recall", "hs_evaluate_recall_dev",
 ]
 
 
@@ -35,6 +36,15 @@ class Params(C.Structure):
     _fields_ = [("len", C.c_uint32), ("K", C.c_uint32), ("L", C.c_uint32), ("W", C.c_double), ("R", C.c_double),
                 ("table_variant", C.c_uint32), ("metric", C.c_uint32), ("predicate", C.c_uint32),
                 ("flags", C.c_uint32)]
+
+
+RECALL_BINS = 500
+
+
+class Recall(C.Structure):
+    """hs_recall"""
+    _fields_ = [("tp", C.c_double), ("fn", C.c_double), ("n_tp", C.c_uint64), ("n_fn", C.c_uint64),
+                ("n_extra", C.c_uint64), ("tp_bin", C.c_uint64 * RECALL_BINS), ("fn_bin", C.c_uint64 * RECALL_BINS)]
 
 
 class Stats(C.Structure):
@@ -113,6 +123,8 @@ def load(build_if_missing=True):
     lib.hs_kmer3_klsh.argtypes = [vp, C.c_char_p, u64p, C.c_uint32, dblp, dblp, dblp, C.c_uint32, u32p, u64p, u8p,
                                   u64p]
     lib.hs_orf6.argtypes = [vp, C.c_char_p, u64p, C.c_uint32, C.c_char_p, C.c_uint64, i32p]
+    lib.hs_evaluate_recall.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.POINTER(Recall)]
+    lib.hs_evaluate_recall_dev.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.POINTER(Recall)]
     _lib = lib
     return lib
 

@@ -220,6 +220,30 @@ class HSearch:
         q = np.ascontiguousarray(qcodes, dtype=np.uint8).reshape(-1, self.len)
         return self._call_hits(self.lib.hs_bruteforce_codes, q, C.c_uint8, q.shape[0], cap)
 
+    @staticmethod
+    def _recall_dict(r):
+        tpb = np.frombuffer(r.tp_bin, dtype=np.uint64).copy()
+        fnb = np.frombuffer(r.fn_bin, dtype=np.uint64).copy()
+        return {"tp": r.tp, "fn": r.fn, "recall": r.tp / (r.tp + r.fn) if (r.tp + r.fn) else float("nan"),
+                "n_tp": int(r.n_tp), "n_fn": int(r.n_fn), "n_extra": int(r.n_extra), "tp_bin": tpb, "fn_bin": fnb}
+
+    def evaluate_recall(self, truth, found, Q):
+        """evaulate() of motif_both_points.cpp:100-165 on binary hit lists (HIT_DTYPE arrays);
+        `found` in the order the search returns with HS_FLAG_SORT_HITS."""
+        truth = np.ascontiguousarray(truth, dtype=HIT_DTYPE)
+        found = np.ascontiguousarray(found, dtype=HIT_DTYPE)
+        r = capi.Recall()
+        check(self.lib.hs_evaluate_recall(self.ctx, truth.ctypes.data_as(C.c_void_p), len(truth),
+                                          found.ctypes.data_as(C.c_void_p), len(found), Q, C.byref(r)))
+        return self._recall_dict(r)
+
+    def evaluate_recall_dev(self, truth_ptr, n_truth, found_ptr, n_found, Q):
+        """Same with both lists resident on the device (raw device pointers)."""
+        r = capi.Recall()
+        check(self.lib.hs_evaluate_recall_dev(self.ctx, C.c_void_p(truth_ptr), n_truth, C.c_void_p(found_ptr), n_found,
+                                              Q, C.byref(r)))
+        return self._recall_dict(r)
+
     def cluster(self):
         out = np.zeros(self.num_fragments, dtype=np.uint32)
         check(self.lib.hs_cluster(self.ctx, ptr(out, C.c_uint32)))

@@ -226,6 +226,30 @@ int hs_bruteforce_points(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_hi
 int hs_bruteforce_points_dev(hs_ctx_t *ctx, const void *qpoints_dev, uint32_t Q, void *hits_dev, uint64_t cap,
                              uint64_t *nhits);
 
+/* ---- recall of a search against ground truth (R1) ---------------------------- */
+/* evaulate() + weight() of motif_both_points.cpp:66-86,100-165 on binary hit lists instead
+ * of the two text files: `truth` (any order; e.g. the output of hs_bruteforce_*) is joined
+ * with `found`, which must be in the order hs_search_* returns with HS_FLAG_SORT_HITS
+ * (query, first table, db id; pairs unique).  A truth pair that was found adds
+ * weight(dis) to tp, a missed one to fn, dis = sqrt(dist2) (the integer distance for
+ * BLOSUM_INT); recall = tp / (tp + fn).  tp_bin / fn_bin count the pairs by
+ * int(dis*100/10), the rows of <out>.accuracy.txt (:151-163); n_extra = found pairs absent
+ * from truth (the "xnomo" lines, :127-129).  A truth distance above R + 0.1 makes the
+ * reference print "err" and exit (:67-70): here HS_ERR_INVALID.  Counts are exact; tp and
+ * fn are summed in a fixed parallel order, within 1e-12 relative of the sequential sums. */
+#define HS_RECALL_BINS 500
+typedef struct {
+  double tp, fn;
+  uint64_t n_tp, n_fn, n_extra;
+  uint64_t tp_bin[HS_RECALL_BINS], fn_bin[HS_RECALL_BINS];
+} hs_recall;
+int hs_evaluate_recall(hs_ctx_t *ctx, const hs_hit *truth, uint64_t n_truth, const hs_hit *found, uint64_t n_found,
+                       uint32_t Q, hs_recall *out);
+/* Device-resident variant: both lists are device pointers (recall at 10^8 .. 10^9 fragments
+ * without a round trip through text or the host). */
+int hs_evaluate_recall_dev(hs_ctx_t *ctx, const void *truth_dev, uint64_t n_truth, const void *found_dev,
+                           uint64_t n_found, uint32_t Q, hs_recall *out);
+
 /* ---- cluster (U1) ----------------------------------------------------------- */
 /* Connected components of the near-pair graph: every pair sharing a bucket in
  * some table with distance within R is an edge; UnionFind

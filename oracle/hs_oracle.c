@@ -640,3 +640,55 @@ double orc_weight(double dis, double R) {
   if (w < 0) return 1;
   return w;
 }
+
+/* ---- R1: motif_both_points.cpp:100-165 evaulate() --------------------------- */
+/* The merge-join of the ground truth with the search output, restated on binary lists that
+ * are both sorted by (query, db id) -- the reference sorts by (motif name, protein name);
+ * any common total order gives the same matched set.  dis[] are the distances as the
+ * reference reads them from the third text column.  Sequential FP64 sums in list order
+ * (:117-141); bins by int(dis*100/10) (:120,131,138); n_extra counts the "xnomo" lines
+ * (:127-129).  Returns -1 where the reference would print "err" and exit (:67-70). */
+int orc_evaluate(const orc_hit *truth, const double *tdis, uint64_t nt, const orc_hit *found, uint64_t nf,
+                 double R, uint32_t nbins, double *tp_out, double *fn_out, uint64_t *n_tp, uint64_t *n_fn,
+                 uint64_t *n_extra, uint64_t *tp_bin, uint64_t *fn_bin) {
+  uint64_t i = 0, j = 0;
+  double tp = 0.0, fn = 0.0;
+  *n_tp = *n_fn = *n_extra = 0;
+  for (uint32_t b = 0; b < nbins; ++b) tp_bin[b] = fn_bin[b] = 0;
+  for (uint64_t t = 0; t < nt; ++t)
+    if (tdis[t] > R + 0.1) return -1;
+  while (i < nt && j < nf) {
+    int cmp;
+    if (truth[i].query != found[j].query) cmp = truth[i].query > found[j].query ? 1 : -1;
+    else if (truth[i].db_id != found[j].db_id) cmp = truth[i].db_id > found[j].db_id ? 1 : -1;
+    else cmp = 0;
+    if (cmp == 0) {
+      tp += orc_weight(tdis[i], R);
+      int b = (int)(tdis[i] * 100 / 10);
+      if (b >= 0 && (uint32_t)b < nbins) tp_bin[b]++;
+      ++*n_tp;
+      i++;
+      j++;
+    } else if (cmp == 1) {
+      ++*n_extra;
+      j++;
+    } else {
+      fn += orc_weight(tdis[i], R);
+      int b = (int)(tdis[i] * 100 / 10);
+      if (b >= 0 && (uint32_t)b < nbins) fn_bin[b]++;
+      ++*n_fn;
+      i++;
+    }
+  }
+  while (i < nt) {
+    fn += orc_weight(tdis[i], R);
+    int b = (int)(tdis[i] * 100 / 10);
+    if (b >= 0 && (uint32_t)b < nbins) fn_bin[b]++;
+    ++*n_fn;
+    i++;
+  }
+  *n_extra += nf - j;
+  *tp_out = tp;
+  *fn_out = fn;
+  return 0;
+}

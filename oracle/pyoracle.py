@@ -86,6 +86,8 @@ class Oracle:
         L.orc_orf6.argtypes = [C.c_char_p, C.c_int, C.c_char_p, _i32]
         L.orc_weight.argtypes = [C.c_double, C.c_double]
         L.orc_weight.restype = C.c_double
+        L.orc_evaluate.argtypes = [C.c_void_p, _dbl, C.c_uint64, C.c_void_p, C.c_uint64, C.c_double, C.c_uint32, _dbl,
+                                   _dbl, _u64, _u64, _u64, _u64, _u64]
         L.orc_distance_int.argtypes = [_u8, _u8, C.c_uint32, _i32]
         L.orc_similarity_int.argtypes = [_u8, _u8, C.c_uint32]
         L.orc_get_aa20.restype = C.c_char_p
@@ -293,6 +295,24 @@ class Oracle:
     def weight(self, dis, R):
         return self.L.orc_weight(dis, R)
 
+    def evaluate(self, truth, found, R, dis=None, nbins=500):
+        """evaulate() (motif_both_points.cpp:100-165) on HIT_DTYPE arrays; both are sorted by
+        (query, db id) here, dis defaults to sqrt(dist2) of the truth list."""
+        truth = np.sort(np.ascontiguousarray(truth, dtype=HIT_DTYPE), order=["query", "db_id"])
+        found = np.sort(np.ascontiguousarray(found, dtype=HIT_DTYPE), order=["query", "db_id"])
+        tdis = np.ascontiguousarray(np.sqrt(truth["dist2"]) if dis is None else dis, dtype=np.float64)
+        tp, fn = C.c_double(), C.c_double()
+        cnt = np.zeros(3, dtype=np.uint64)
+        tpb, fnb = np.zeros(nbins, dtype=np.uint64), np.zeros(nbins, dtype=np.uint64)
+        rc = self.L.orc_evaluate(truth.ctypes.data_as(C.c_void_p), _p(tdis, C.c_double), len(truth),
+                                 found.ctypes.data_as(C.c_void_p), len(found), R, nbins, C.byref(tp), C.byref(fn),
+                                 _p(cnt[0:1], C.c_uint64), _p(cnt[1:2], C.c_uint64), _p(cnt[2:3], C.c_uint64),
+                                 _p(tpb, C.c_uint64), _p(fnb, C.c_uint64))
+        if rc != 0:
+            raise ValueError("err: a ground-truth distance exceeds R + 0.1 (the reference exits)")
+        return {"tp": tp.value, "fn": fn.value, "recall": tp.value / (tp.value + fn.value) if tp.value + fn.value else float("nan"),
+                "n_tp": int(cnt[0]), "n_fn": int(cnt[1]), "n_extra": int(cnt[2]), "tp_bin": tpb, "fn_bin": fnb}
+
 
 class Reference:
     """The reference's own code (oracle/_ref), when it was built."""
@@ -314,6 +334,8 @@ class Reference:
         S.ref_build_tables_seconds.restype = C.c_double
         S.ref_weight.argtypes = [C.c_double, C.c_double]
         S.ref_weight.restype = C.c_double
+        S.ref_evaluate.argtypes = [C.c_char_p, C.c_char_p, C.c_double]
+        S.ref_evaluate.restype = C.c_double
         B = self.nolsh_lib
         B.ref_bruteforce.argtypes = [_dbl, C.c_uint64, _dbl, C.c_uint32, C.c_uint32, C.c_double, C.c_char_p,
                                      C.c_void_p, _dbl, C.c_uint64, _dbl]
@@ -397,6 +419,24 @@ class Reference:
                 if n <= cap:
                     return hits[:n], printed[:n], float(sec[0])
                 cap = int(n)
+
+    def evaluate(self, truth, found, R):
+        """The reference's evaulate() (motif_both_points.cpp:100-165) run on text files written from
+        the two HIT_DTYPE lists: zero-padded names make its string order equal (query, db id),
+        distances are written with 17 significant digits (read back exactly).  Returns
+        (tp/(tp+fn), rows of <out>.accuracy.txt as token lists)."""
+        truth = np.sort(np.ascontiguousarray(truth, dtype=HIT_DTYPE), order=["query", "db_id"])
+        with tempfile.TemporaryDirectory() as d:
+            gt, out = os.path.join(d, "gt.txt"), os.path.join(d, "out.txt")
+            with open(gt, "w") as f:
+                for h in truth:
+                    f.write("m%09d p%012d %.17g\n" % (h["query"], h["db_id"], np.sqrt(h["dist2"])))
+            with open(out, "w") as f:
+                for h in found:
+                    f.write("m%09d p%012d %.17g\n" % (h["query"], h["db_id"], np.sqrt(h["dist2"])))
+            r = self.search_lib.ref_evaluate(gt.encode(), out.encode(), R)
+            rows = [ln.split() for ln in open(out + ".accuracy.txt").read().splitlines() if ln.strip()]
+        return float(r), rows
 
     def union_find_roots(self, ids, eu, ev):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)

@@ -132,4 +132,10 @@ double ref_build_tables_seconds(const double *db, uint64_t N, uint32_t dim, uint
 
 // weight() (motif_both_points.cpp:67-87)
 double ref_weight(double dis, double R) { return weight(dis, R); }
+
+// evaulate() (motif_both_points.cpp:100-165) on the reference's two text files; also writes
+// <out>.accuracy.txt and prints the reference's own lines to stdout
+double ref_evaluate(const char *ground_truth, const char *output_file, double R) {
+  return evaulate(ground_truth, output_file, R);
+}
 }

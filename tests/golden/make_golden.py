@@ -73,5 +73,45 @@ def main():
     print("wrote", os.path.join(HERE, "reference_golden.npz"), len(out), "arrays")
 
 
+def evaluate_lists(seed=5, n=4000, Q=50, N=2000, R=30.0):
+    """Seeded ground-truth / found hit lists for the R1 (recall) fixtures: 60 % of the truth
+    found, 30 found pairs absent from the truth, found in (query, first table, db id) order."""
+    from oracle.pyoracle import HIT_DTYPE
+    rng = np.random.default_rng(seed)
+    t = np.zeros(n, dtype=HIT_DTYPE)
+    pairs = np.sort(rng.choice(Q * N, size=n, replace=False))
+    t["query"], t["db_id"] = pairs // N, pairs % N
+    t["dist2"] = rng.uniform(0, R, n) ** 2
+    keep = rng.random(n) < 0.6
+    f = t[keep].copy()
+    f["table_first"] = rng.integers(0, 4, int(keep.sum()))
+    e = np.zeros(30, dtype=HIT_DTYPE)
+    e["query"], e["db_id"], e["dist2"] = rng.integers(0, Q, 30), N + np.arange(30), 100.0
+    e["table_first"] = rng.integers(0, 4, 30)
+    f = np.sort(np.concatenate([f, e]), order=["query", "table_first", "db_id"])
+    return t, f, Q, R
+
+
+def main_evaluate():
+    """evaulate() of the reference (motif_both_points.cpp:100-165) on seeded lists."""
+    r = Reference()
+    t, f, Q, R = evaluate_lists()
+    recall, rows = r.evaluate(t, f, R)
+    tpb, fnb = np.zeros(500, dtype=np.uint64), np.zeros(500, dtype=np.uint64)
+    for row in rows:  # "<bin> <ratio> <tp> <fn>" | "<bin> 0 fn <fn>" | "<bin> 1 tp <tp>"  (:151-163)
+        b = int(row[0])
+        if row[2] == "fn":
+            fnb[b] = int(row[3])
+        elif row[2] == "tp":
+            tpb[b] = int(row[3])
+        else:
+            tpb[b], fnb[b] = int(row[2]), int(row[3])
+    np.savez_compressed(os.path.join(HERE, "evaluate_golden.npz"), truth=t, found=f, Q=Q, R=R, recall=recall,
+                        tp_bin=tpb, fn_bin=fnb)
+    print("wrote evaluate_golden.npz: recall", recall)
+
+
 if __name__ == "__main__":
-    main()
+    if "--evaluate-only" not in sys.argv:
+        main()
+    main_evaluate()

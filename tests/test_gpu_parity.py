@@ -690,3 +690,61 @@ def test_cluster_large_buckets_through_tensor_filter(oracle, R, pred):
         else (None, 0)
     if want is not None:
         assert np.array_equal(res[0][0], want)
+
+
+# ---------------------------------------------------------------- R1: recall evaluation on the device
+def test_evaluate_recall_golden(oracle):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "evaluate_golden.npz"))
+    R, Q = float(g["R"]), int(g["Q"])
+    h = hb.HSearch(10, 4, 4, 50.0, R)
+    r = h.evaluate_recall(g["truth"], g["found"], Q)
+    # counts and bins exact; the weighted sums are added in a parallel order (tolerance 1e-12)
+    assert np.array_equal(r["tp_bin"], g["tp_bin"]) and np.array_equal(r["fn_bin"], g["fn_bin"])
+    assert r["n_tp"] == int(g["tp_bin"].sum()) and r["n_fn"] == int(g["fn_bin"].sum()) and r["n_extra"] == 30
+    e = oracle.evaluate(g["truth"], g["found"], R)
+    assert abs(r["tp"] - e["tp"]) <= 1e-12 * e["tp"] and abs(r["fn"] - e["fn"]) <= 1e-12 * e["fn"]
+    assert abs(r["recall"] - float(g["recall"])) <= 1e-12
+    # truth in any order gives the same answer; found out of order is refused
+    perm = np.random.default_rng(3).permutation(len(g["truth"]))
+    r2 = h.evaluate_recall(g["truth"][perm], g["found"], Q)
+    assert r2["n_tp"] == r["n_tp"] and np.array_equal(r2["tp_bin"], r["tp_bin"])
+    with pytest.raises(hb.HsError):
+        h.evaluate_recall(g["truth"], g["found"][::-1], Q)
+    bad = g["truth"].copy()
+    bad["dist2"][7] = (R + 0.2) ** 2
+    with pytest.raises(hb.HsError):
+        h.evaluate_recall(bad, g["found"], Q)
+    # empty lists
+    z = h.evaluate_recall(g["truth"][:0], g["found"], Q)
+    assert z["n_tp"] == 0 and z["n_fn"] == 0 and z["n_extra"] == len(g["found"])
+    z = h.evaluate_recall(g["truth"], g["found"][:0], Q)
+    assert z["n_tp"] == 0 and z["n_fn"] == len(g["truth"]) and z["recall"] == 0.0
+    h.close()
+
+
+@pytest.mark.parametrize("length,W,R", [(10, 50.0, 30.0), (10, 20.0, 30.0), (25, 50.0, 55.0)])
+def test_evaluate_recall_of_a_search(oracle, length, W, R):
+    # the reference's pipeline: brute force = ground truth, LSH search = found, evaulate() joins them
+    n, q = 30000, 200
+    codes = random_codes(n, length, seed=81)
+    qcodes = planted_queries(codes, q, seed=82, frac=0.8, max_sub=4)
+    h, a, b = make(length, 4, 4, W, R, flags=hb.HS_FLAG_SORT_HITS)
+    h.load_fragments(codes)
+    h.build_index()
+    found = h.search_codes(qcodes)
+    truth = h.bruteforce_codes(qcodes)
+    assert 0 < len(found) <= len(truth)
+    r = h.evaluate_recall(truth, found, q)
+    e = oracle.evaluate(truth, found, R)
+    assert (r["n_tp"], r["n_fn"], r["n_extra"]) == (e["n_tp"], e["n_fn"], e["n_extra"]) == (len(found), len(truth) - len(found), 0)
+    assert np.array_equal(r["tp_bin"], e["tp_bin"]) and np.array_equal(r["fn_bin"], e["fn_bin"])
+    assert abs(r["tp"] - e["tp"]) <= 1e-12 * max(e["tp"], 1.0) and abs(r["fn"] - e["fn"]) <= 1e-12 * max(e["fn"], 1.0)
+    # device-resident variant
+    import torch
+    td = torch.from_numpy(truth.view(np.uint8).copy()).cuda()
+    fd = torch.from_numpy(found.view(np.uint8).copy()).cuda()
+    torch.cuda.synchronize()
+    rd = h.evaluate_recall_dev(td.data_ptr(), len(truth), fd.data_ptr(), len(found), q)
+    assert rd["tp"] == r["tp"] and rd["fn"] == r["fn"] and np.array_equal(rd["tp_bin"], r["tp_bin"])
+    h.close()

@@ -167,3 +167,36 @@ def test_reference_agrees_with_restatement_live(oracle, reference):
     h, ts, _ = oracle.search(oracle.embed(db, tab), oracle.embed(qc, tab), a, b, 50.0, 30.0)
     rh, _, rts, _ = reference.search(oracle.embed(db, tab), oracle.embed(qc, tab), 4, 4, 50.0, 30.0, 4242)
     assert hits_as_tuples(h, False) == hits_as_tuples(rh, False) and np.array_equal(ts, rts)
+
+
+# ---------------------------------------------------------------- R1: recall evaluation
+EVAL_GOLD = os.path.join(os.path.dirname(__file__), "golden", "evaluate_golden.npz")
+
+
+def test_evaluate_golden(oracle):
+    # evaulate() of the reference (motif_both_points.cpp:100-165) on seeded lists: same sequential
+    # sums, so the recall is bit-identical; bins are the rows of <out>.accuracy.txt
+    g = np.load(EVAL_GOLD)
+    e = oracle.evaluate(g["truth"], g["found"], float(g["R"]))
+    assert e["recall"] == float(g["recall"])
+    assert np.array_equal(e["tp_bin"], g["tp_bin"]) and np.array_equal(e["fn_bin"], g["fn_bin"])
+    assert e["n_tp"] == int(g["tp_bin"].sum()) and e["n_fn"] == int(g["fn_bin"].sum())
+    assert e["n_extra"] == len(g["found"]) - e["n_tp"] == 30
+
+
+def test_evaluate_against_reference_itself(oracle, reference):
+    from tests.golden.make_golden import evaluate_lists
+    for seed, n in [(11, 1), (12, 257), (13, 3000)]:
+        t, f, Q, R = evaluate_lists(seed=seed, n=n, Q=20, N=500, R=26.5)
+        rv, rows = reference.evaluate(t, f, R)
+        e = oracle.evaluate(t, f, R)
+        assert e["recall"] == rv
+        assert sum(int(r[0]) < 500 for r in rows) == int(((e["tp_bin"] + e["fn_bin"]) > 0).sum())
+
+
+def test_evaluate_rejects_distance_above_threshold(oracle):
+    g = np.load(EVAL_GOLD)
+    t = g["truth"].copy()
+    t["dist2"][5] = (float(g["R"]) + 0.2) ** 2  # weight() prints "err" and exits (:67-70)
+    with pytest.raises(ValueError):
+        oracle.evaluate(t, g["found"], float(g["R"]))
