@@ -81,3 +81,13 @@ def test_bad_parameters_rejected():
     assert lib.hs_create(C.byref(ctx), 0, C.byref(bad)) == capi.HS_ERR_INVALID
     assert lib.hs_create(None, 0, None) == capi.HS_ERR_INVALID
     assert b"null" in lib.hs_last_error()
+
+
+def test_evaluate_recall_null_arguments():
+    # argument checks come before any device work, so they answer without a GPU
+    lib = capi.load()
+    r = capi.Recall()
+    assert lib.hs_evaluate_recall(None, None, 0, None, 0, 1, C.byref(r)) == capi.HS_ERR_INVALID
+    assert lib.hs_evaluate_recall_dev(None, None, 0, None, 0, 1, C.byref(r)) == capi.HS_ERR_INVALID
+    assert b"null" in lib.hs_last_error()
+    assert C.sizeof(capi.Recall) == 16 + 3 * 8 + 2 * 8 * capi.RECALL_BINS  # hs_recall of include/hsearch_b200.h
