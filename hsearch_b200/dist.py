@@ -130,6 +130,30 @@ def sort_hits_reference_order(hits):
     return hits[order]
 
 
+# ---- recall of a sharded search (R1 at BASELINE configs[2], 1 B fragments over 8 GPUs) --------
+def recall_sharded(local, device="cpu"):
+    """evaulate() (motif_both_points.cpp:100-165) of a block-sharded DB: every (query, fragment)
+    pair lives on exactly one shard, so the per-shard tp / fn sums, counts and distance bins of
+    hs_evaluate_recall(_dev) (HSearch.evaluate_recall*: dict with tp, fn, n_tp, n_fn, n_extra,
+    tp_bin, fn_bin) add up; one all-reduce of 2 doubles and 3 + 2*500 counters, no hit list
+    leaves its GPU.  Returns the global dict on every rank."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    tpb = np.asarray(local["tp_bin"], dtype=np.int64)
+    fnb = np.asarray(local["fn_bin"], dtype=np.int64)
+    f = torch.tensor([local["tp"], local["fn"]], dtype=torch.float64, device=device)
+    c = torch.as_tensor(np.concatenate([[local["n_tp"], local["n_fn"], local["n_extra"]], tpb, fnb]).astype(np.int64),
+                        device=device)
+    if world > 1:
+        dist.all_reduce(f)
+        dist.all_reduce(c)
+    f, c = f.cpu().numpy(), c.cpu().numpy()
+    nb = len(tpb)
+    tp, fn = float(f[0]), float(f[1])
+    return {"tp": tp, "fn": fn, "recall": tp / (tp + fn) if tp + fn else float("nan"),
+            "n_tp": int(c[0]), "n_fn": int(c[1]), "n_extra": int(c[2]),
+            "tp_bin": c[3:3 + nb].astype(np.uint64), "fn_bin": c[3 + nb:3 + 2 * nb].astype(np.uint64)}
+
+
 # ---- sharded near-pair clustering (BASELINE configs[3], SURVEY.md 8e) --------------------
 # Buckets span shards, so the cluster path has one real exchange step per table: every
 # (key, global id, codes) record goes to the rank that owns its bucket (owner = mix(key) mod

@@ -142,3 +142,43 @@ def test_cluster_sharded_world2_matches_single_process(tmp_path):
     mp.spawn(_cluster_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     n0, n1 = int(open(tmp_path / "ok0").read()), int(open(tmp_path / "ok1").read())
     assert n0 == n1 and 1 < n0 < 3001
+
+
+# ---------------------------------------------------------------- sharded recall (R1)
+def _recall_worker(rank, world, port, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.pyoracle import Oracle
+        o = Oracle()
+        length, K, L, W, R = 10, 4, 4, 50.0, 30.0
+        n_total = 5003
+        codes = random_codes(n_total, length, seed=21)
+        tab = o.coordinates(True)
+        a, b = o.lsh_tables(4242, 8 * length, K, L, W)
+        qn = o.embed(planted_queries(codes, 30, seed=22, frac=0.8, max_sub=4), tab)
+        lo, hi = hdist.shard_range(n_total, rank, world)
+        db = o.embed(codes[lo:hi], tab)
+        found, _, _ = o.search(db, qn, a, b, W, R)
+        truth = o.bruteforce(db, qn, R, pred=0)
+        # the per-shard evaluation (on a GPU: HSearch.evaluate_recall_dev), then one all-reduce
+        got = hdist.recall_sharded(o.evaluate(truth, found, R))
+        fa, _, _ = o.search(o.embed(codes, tab), qn, a, b, W, R)
+        ta = o.bruteforce(o.embed(codes, tab), qn, R, pred=0)
+        want = o.evaluate(ta, fa, R)
+        assert want["n_tp"] > 0 and want["n_fn"] > 0
+        assert (got["n_tp"], got["n_fn"], got["n_extra"]) == (want["n_tp"], want["n_fn"], want["n_extra"])
+        assert np.array_equal(got["tp_bin"], want["tp_bin"]) and np.array_equal(got["fn_bin"], want["fn_bin"])
+        assert abs(got["tp"] - want["tp"]) <= 1e-12 * want["tp"] and abs(got["fn"] - want["fn"]) <= 1e-12 * want["fn"]
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write(repr(got["recall"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_recall_sharded_world2_matches_single_process(tmp_path):
+    world = 2
+    mp.spawn(_recall_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = float(open(tmp_path / "ok0").read()), float(open(tmp_path / "ok1").read())
+    assert r0 == r1 and 0.0 < r0 < 1.0
