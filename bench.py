@@ -50,8 +50,13 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="DB fragments per host core in the CPU leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-contexts", type=int, default=2, help="contexts alternating batches in the end-to-end leg (1 or 2)")
     ap.add_argument("--no-recall", action="store_true", help="skip the full-size brute-force recall measurement")
-    ap.add_argument("--audit", action="store_true", help="FP64 audit of every projection (residual flips)")
+    ap.add_argument("--audit", action="store_true", help="FP64 audit inside every timed hs_hash too (the bench always audits "
+                    "the keys once after the timed region)")
+    ap.add_argument("--no-subset-check", action="store_true", help="skip the exact CPU comparison of a slice of the result")
+    ap.add_argument("--subset-db", type=int, default=1_000_000)
+    ap.add_argument("--subset-q", type=int, default=1000)
     ap.add_argument("--scalar-filter", action="store_true", help="A/B: keep all candidates on the scalar filter")
     return ap.parse_args()
 
@@ -331,46 +336,120 @@ def run_native(a):
     value = N * world / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ------------------------
+    # Every step: H2D of the step's codes and queries from pinned host memory, index build, search,
+    # D2H of the step's hits (compact 12-byte layout, hs_search_points_compact) -- all inside the timed
+    # region.  Two contexts on the same GPU alternate batches from two host threads (double
+    # buffering): batch i's hits leave over PCIe while batch i+1's codes arrive on the other
+    # direction and its kernels run.  `sequential` is the same call sequence on one context.
     e2e = None
     if not a.no_e2e:
+        import ctypes as C
+        import threading
+        from hsearch_b200 import capi
+        lib = capi.load()
         host_codes = torch.empty((N, length), dtype=torch.uint8).pin_memory()
         host_codes.copy_(codes)
         host_q = torch.empty((Q, dim), dtype=torch.float64).pin_memory()
         host_q.copy_(qpts)
-        host_hits = torch.empty(cap * 24, dtype=torch.uint8).pin_memory()
         torch.cuda.synchronize()
-        import ctypes as C
-        from hsearch_b200 import capi
-        lib = capi.load()
-        nh_e = C.c_uint64(0)
+        nctx = 1 if a.e2e_contexts < 2 else 2
+        h2 = None
+        if nctx == 2:
+            h2 = hb.HSearch(length, a.K, a.L, a.W, a.R, table_variant=hb.HS_TABLE_PRINT6, flags=flags, device=local)
+            h2.seed_projection(12345)
+        lanes = []
+        for hh in ([h, h2] if nctx == 2 else [h]):
+            off = torch.empty(Q + 1, dtype=torch.int64).pin_memory()
+            idt = torch.empty(cap, dtype=torch.int32).pin_memory()
+            d2 = torch.empty(cap, dtype=torch.float64).pin_memory()
+            ch = capi.CompactHits(C.cast(off.data_ptr(), C.POINTER(C.c_uint64)), C.cast(idt.data_ptr(), C.POINTER(C.c_uint32)),
+                                  C.cast(d2.data_ptr(), C.POINTER(C.c_double)), cap, 0)
+            lanes.append({"h": hh, "off": off, "idt": idt, "d2": d2, "ch": ch, "n": C.c_uint64(0),
+                          "stream": torch.cuda.ExternalStream(hh.stream_ptr(), device=dev), "err": None})
 
-        def e2e_step():
-            capi.check(lib.hs_load_fragments(h.ctx, C.cast(host_codes.data_ptr(), C.POINTER(C.c_uint8)), N, rank * N))
-            capi.check(lib.hs_build_index(h.ctx))
-            capi.check(lib.hs_search_points(h.ctx, C.cast(host_q.data_ptr(), C.POINTER(C.c_double)), Q,
-                                            C.c_void_p(host_hits.data_ptr()), cap, C.byref(nh_e)))
-        with torch.cuda.stream(stream):
-            e2e_step()  # warm the pinned path
+        def e2e_step(ln):
+            hh = ln["h"]
+            capi.check(lib.hs_load_fragments(hh.ctx, C.cast(host_codes.data_ptr(), C.POINTER(C.c_uint8)), N, rank * N))
+            capi.check(lib.hs_build_index(hh.ctx))
+            capi.check(lib.hs_search_points_compact(hh.ctx, C.cast(host_q.data_ptr(), C.POINTER(C.c_double)), Q,
+                                                    C.byref(ln["ch"]), C.byref(ln["n"])))
+
+        def lane_run(ln, nsteps):
+            try:
+                torch.cuda.set_device(local)
+                for _ in range(nsteps):
+                    e2e_step(ln)
+            except Exception as e:   # reported after the join
+                ln["err"] = e
+
+        def timed(nsteps_per_lane):
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record(stream)
-            for _ in range(a.steps):
-                e2e_step()
-            f1.record(stream)
+            f0 = torch.cuda.Event(enable_timing=True)
+            f0.record(lanes[0]["stream"])
+            th = [threading.Thread(target=lane_run, args=(ln, k)) for ln, k in zip(lanes, nsteps_per_lane)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            ends = []
+            for ln in lanes:
+                f1 = torch.cuda.Event(enable_timing=True)
+                f1.record(ln["stream"])
+                ends.append(f1)
             torch.cuda.synchronize()
-        te = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e_ms = te.item() / a.steps
-        s_e = h.stats().as_dict()  # the last end-to-end search call
+            for ln in lanes:
+                if ln["err"] is not None:
+                    raise ln["err"]
+            te = torch.tensor([max(f0.elapsed_time(f1) for f1 in ends)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return te.item()
+
+        timed([1] * len(lanes))                                  # warm the pinned path of every context
+        split = [a.steps - a.steps // 2, a.steps // 2] if nctx == 2 else [a.steps]
+        e_ms = timed(split) / a.steps
+        seq_ms = timed([a.steps] + [0] * (len(lanes) - 1)) / a.steps   # one context, no overlap across batches
+        s_e = h.stats().as_dict()  # the last end-to-end search call of context 0
+        nh_e = int(lanes[0]["n"].value)
+        # the compact result of the last batch expands to the records of the device-resident run
+        e2e_same = None
+        try:
+            if rank != 0:
+                raise StopIteration
+            exp = np.zeros(max(nh_e, 1), dtype=capi.HIT_DTYPE)
+            capi.check(lib.hs_expand_hits(C.byref(lanes[0]["ch"]), Q, rank * N, exp.ctypes.data))
+            dev_hits = hits_bufs[(step_no[0] - 1) % nslot][:min(int(nh), cap) * 24].cpu().numpy().view(capi.HIT_DTYPE)
+            e2e_same = bool(nh_e == int(nh) and np.array_equal(exp[:nh_e], dev_hits))
+            del exp, dev_hits
+        except StopIteration:
+            pass
+        except Exception as e:
+            e2e_same = repr(e)
+        d2h = int(nh_e * 12 + (Q + 1) * 8)
         e2e = {"value": N * world / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "sequential_ms_per_step": seq_ms, "contexts": nctx,
                "search_stages_ms": {k[3:]: round(s_e[k], 3) for k in ("ms_qhash", "ms_probe", "ms_host", "ms_filter",
                                                                         "ms_exact", "ms_hitsort", "ms_total")},
-               "h2d_bytes_per_step": int(N * length + Q * dim * 8), "d2h_bytes_per_step": int(nh_e.value * 24),
-               "api": "hs_load_fragments + hs_build_index + hs_search_points (host buffers, pinned)"}
-        del host_codes, host_hits
+               "h2d_bytes_per_step": int(N * length + Q * dim * 8), "d2h_bytes_per_step": d2h,
+               "hits_equal_device_run_after_expansion": e2e_same,
+               "api": ("hs_load_fragments + hs_build_index + hs_search_points_compact (pinned host buffers; per-query CSR, "
+                       "12 bytes per hit); %d context(s) on the GPU alternate batches from host threads so that one "
+                       "batch's D2H overlaps the next batch's H2D and kernels; every copy is inside the timed region"
+                       % nctx)}
+        for ln in lanes:
+            ln["ch"] = None
+        del host_codes, lanes
+        if h2 is not None:
+            h2.close()
+
+    # ---- FP64 audit of the keys of the timed run (every projection of every fragment) -----------
+    h.hash()
+    flips = torch.tensor([h.hash_audit()], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(flips)
+    residual_flips = int(flips.item())
 
     if rank != 0:
         if world > 1:
@@ -484,6 +563,46 @@ def run_native(a):
     except Exception as e:  # the checks must never break the bench line
         checks = {"error": repr(e)}
 
+    # ---- exact comparison of a slice of the full-size result with the reference itself ----------
+    # Bucket membership is per fragment, so the hits of the full run restricted to an id subset equal
+    # the hits of that subset searched alone: the slice db_id < 10^6, query < 10^3 of the last step is
+    # compared with the reference's own Search() (oracle/_ref) on those fragments and queries -- order,
+    # ids and FP64 distances -- and with the oracle restatement for the first-table column.  A pair the
+    # FP16 tensor filter lost would show up here (the same-engine brute force below cannot see it).
+    if checks is not None and "error" not in checks and not a.no_subset_check:
+        try:
+            from oracle.pyoracle import Oracle, Reference
+            t0s = time.perf_counter()
+            ns, qs = min(N, a.subset_db), min(Q, a.subset_q)
+            nv = min(int(nh), cap)
+            hv2 = hits_bufs[(step_no[0] - 1) % nslot][:nv * 24].view(-1, 24)
+            q_t = hv2.view(torch.int32)[:, 0]
+            id_t = hv2.view(torch.int64)[:, 1] - rank * N
+            sel = np.ascontiguousarray(hv2[(q_t < qs) & (id_t < ns)].cpu().numpy()).view(HIT_DTYPE).reshape(-1)
+            o = Oracle()
+            tab = o.coordinates(True)
+            db_s = o.embed(codes[:ns].cpu().numpy(), tab)
+            qp_s = np.ascontiguousarray(qpts[:qs].cpu().numpy())
+            a_s, b_s = o.lsh_tables(12345, dim, a.K, a.L, a.W)
+            want, _, _ = o.search(db_s, qp_s, a_s, b_s, a.W, a.R, pred=0, cap=len(sel) + 4096)
+            ok_port = bool(len(want) == len(sel) and np.array_equal(sel["query"], want["query"]) and
+                           np.array_equal(sel["table_first"], want["table_first"]) and
+                           np.array_equal(sel["db_id"], want["db_id"]) and np.array_equal(sel["dist2"], want["dist2"]))
+            ok_ref = None
+            if Reference.available():
+                ref, _, _, _ = Reference().search(db_s, qp_s, a.K, a.L, a.W, a.R, 12345, cap=len(sel) + 4096)
+                ok_ref = bool(len(ref) == len(sel) and np.array_equal(sel["query"], ref["query"]) and
+                              np.array_equal(sel["db_id"], ref["db_id"]) and np.array_equal(sel["dist2"], ref["dist2"]))
+            checks["subset_exact"] = bool(ok_port and ok_ref is not False)
+            checks["subset"] = {"db_ids_below": int(ns), "queries_below": int(qs), "hits_in_slice": int(len(sel)),
+                                "vs_reference_search": ok_ref, "vs_oracle_port_incl_first_table": ok_port,
+                                "reference": "oracle/_ref Search()" if ok_ref is not None else "oracle port only",
+                                "cpu_seconds": round(time.perf_counter() - t0s, 1)}
+            del db_s, want
+        except Exception as e:
+            checks["subset_exact"] = None
+            checks["subset"] = {"error": repr(e)}
+
     # ---- recall at full size (outside the timed region; rank 0's shard) ---------------------
     # brute force of all Q x N pairs on the same GPU path (hs_bruteforce_points_dev: tensor filter
     # over the whole DB + exact FP64 stage); every LSH hit is a brute-force hit, so the recall is
@@ -553,7 +672,7 @@ def run_native(a):
                                                                              acc["ms_hitsort"]) / steps * 1e-3),
                       "sort_passes": int(passes), "key_words": int(KW), "rank_path": rank_path,
                       "guard_hits": int(s_hash["guard_hits"]), "guard_corrected": int(s_hash["guard_corrected"]),
-                      "residual_flips": int(s_hash["residual_flips"]) if a.audit else None}}
+                      "residual_flips": residual_flips}}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhsearch_b200.so")
-CU = ["api.cu", "hash.cu", "radix_sort.cu", "verify.cu", "filter_tc.cu", "filter_mma.cu", "cluster.cu", "extract.cu", "sequence.cu", "evaluate.cu"]
+CU = ["api.cu", "hash.cu", "radix_sort.cu", "verify.cu", "filter_tc.cu", "filter_mma.cu", "cluster.cu", "extract.cu", "sequence.cu", "evaluate.cu", "hits.cu"]
 CPP = ["tables.cpp", "comm.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -49,7 +49,10 @@ def build(force=False, verbose=False, ptxas_verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _newer(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+        # -cudart shared: the library binds to libcudart.so.12 at load time (the copy torch already
+        # mapped, or /usr/local/cuda/lib64 for the CLI programs) instead of embedding a static one
+        cmd = [nvcc, "-shared", "-cudart", "shared", "-o", LIB] + objs + [
+            "-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

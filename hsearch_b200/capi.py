@@ -29,6 +29,7 @@ EXPORTS = [
     "hs_bruteforce_codes", "hs_bruteforce_points", "hs_bruteforce_points_dev", "hs_cluster", "hs_comm_init", "hs_comm_unique_id",
     "hs_greedy_cluster", "hs_union_find", "hs_parse_fasta", "hs_klsh_generate", "hs_kmer3_klsh", "hs_orf6",
     "hs_evaluate_recall", "hs_evaluate_recall_dev",
+    "hs_search_points_compact", "hs_expand_hits", "hs_hits_checksum", "hs_hits_checksum_dev", "hs_hash_audit",
 ]
 
 
@@ -45,6 +46,12 @@ class Recall(C.Structure):
     """hs_recall"""
     _fields_ = [("tp", C.c_double), ("fn", C.c_double), ("n_tp", C.c_uint64), ("n_fn", C.c_uint64),
                 ("n_extra", C.c_uint64), ("tp_bin", C.c_uint64 * RECALL_BINS), ("fn_bin", C.c_uint64 * RECALL_BINS)]
+
+
+class CompactHits(C.Structure):
+    """hs_compact_hits"""
+    _fields_ = [("offsets", C.POINTER(C.c_uint64)), ("idt", C.POINTER(C.c_uint32)), ("dist2", C.POINTER(C.c_double)),
+                ("cap", C.c_uint64), ("id_bits", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -125,6 +132,11 @@ def load(build_if_missing=True):
     lib.hs_orf6.argtypes = [vp, C.c_char_p, u64p, C.c_uint32, C.c_char_p, C.c_uint64, i32p]
     lib.hs_evaluate_recall.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.POINTER(Recall)]
     lib.hs_evaluate_recall_dev.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.POINTER(Recall)]
+    lib.hs_search_points_compact.argtypes = [vp, dblp, C.c_uint32, C.POINTER(CompactHits), u64p]
+    lib.hs_expand_hits.argtypes = [C.POINTER(CompactHits), C.c_uint32, C.c_uint64, vp]
+    lib.hs_hash_audit.argtypes = [vp, u64p]
+    lib.hs_hits_checksum.argtypes = [vp, C.c_uint64, u64p]
+    lib.hs_hits_checksum_dev.argtypes = [vp, vp, C.c_uint64, u64p]
     _lib = lib
     return lib
 

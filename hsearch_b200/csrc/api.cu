@@ -356,8 +356,8 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
   MmaLaunch ml;
   if (!P.mma_units.empty()) {
     const uint32_t nunits = (uint32_t)P.mma_units.size();
-    if (const char *e = getenv("HS_PLAN_STATS")) {
-      if (atoi(e)) {
+    {
+      if (ctx->plan_stats) {
         // width histogram of the tensor filter's (tile, query group) work: columns per MMA group
         uint64_t hist[9] = {0}, groups = 0, padded = 0;
         for (const MmaUnitHost &un : P.mma_units) {
@@ -478,22 +478,72 @@ __global__ void hit_key1_kernel(const hs_hit *__restrict__ hits, uint64_t n, int
   k0[i] = ((uint64_t)h.query << qshift) | ((uint64_t)h.table_first << tshift) | h.db_id;
 }
 
+// Compact (CSR) result: entry i of the sorted order as local id | table << id_bits, and dist2.
+__global__ void hit_gather_compact_kernel(const hs_hit *__restrict__ in, const uint32_t *__restrict__ perm, uint64_t n,
+                                          uint64_t id_base, int id_bits, uint32_t *__restrict__ idt,
+                                          double *__restrict__ dist2) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const hs_hit h = in[perm[i]];
+  idt[i] = (uint32_t)(h.db_id - id_base) | (h.table_first << id_bits);
+  dist2[i] = h.dist2;
+}
+// offsets[q] = base + first sorted entry whose query is >= q, for the queries q in [qa, qb]
+// (qb included: the end of the block's last segment).  keys: the sorted one-word hit keys.
+__global__ void hit_offsets_kernel(const uint64_t *__restrict__ keys, uint64_t n, int qshift, uint32_t qa, uint32_t qb,
+                                   uint64_t base, uint64_t *__restrict__ offsets) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint32_t q_prev = i == 0 ? qa : (uint32_t)(keys[i - 1] >> qshift) + 1u;  // first query not yet closed
+  const uint32_t q_here = i == n ? qb : (uint32_t)(keys[i] >> qshift);
+  for (uint32_t q = q_prev; q <= q_here; ++q) offsets[q] = base + i;
+}
+
 static int bits_for(uint64_t nvalues) {  // bits that hold 0 .. nvalues-1
   int b = 1;
   while (b < 64 && (nvalues - 1) >> b) ++b;
   return b;
 }
 
-// Sort d_hits[0..n) by (query, first table, db id); result in ctx->d_hits_sorted.
-static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
-  if (n == 0) return HS_OK;
+// Compact output of sort_hits: the block holds the queries [qa, qb), its entries start at `base`.
+struct CompactBlock {
+  uint32_t qa = 0, qb = 0;
+  uint64_t base = 0;
+  int id_bits = 0;
+};
+static int compact_id_bits(const hs_ctx *ctx, int *id_bits) {
+  const int lb = bits_for(std::max<uint64_t>(ctx->N, 2)), tb = bits_for((uint64_t)ctx->prm.L + 1);
+  if (lb + tb > 32) {
+    set_error("compact hits: %d id bits + %d table bits exceed 32", lb, tb);
+    return HS_ERR_UNSUPPORTED;
+  }
+  *id_bits = lb;
+  return HS_OK;
+}
+
+// Sort d_hits[0..n) by (query, first table, db id); result in ctx->d_hits_sorted, or, with
+// `cb`, as compact entries in ctx->d_cidt / d_cdist plus the block's offsets in ctx->d_coffsets.
+static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n, const CompactBlock *cb = nullptr) {
+  if (cb) {
+    HS_TRY(ctx->d_cidt.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1)));
+    HS_TRY(ctx->d_cdist.reserve(sizeof(double) * std::max<uint64_t>(n, 1)));
+  }
+  if (n == 0) {
+    if (cb) {
+      hit_offsets_kernel<<<1, 256, 0, ctx->stream>>>(nullptr, 0, 0, cb->qa, cb->qb, cb->base, ctx->d_coffsets.as<uint64_t>());
+      // (n == 0: thread 0 alone writes offsets[qa .. qb] = base)
+      ctx->stats.kernel_launches++;
+      HS_CUDA(cudaGetLastError());
+    }
+    return HS_OK;
+  }
   if (n >= (1ull << 32)) {
     set_error("sort_hits: more than 2^32 hits");
     return HS_ERR_UNSUPPORTED;
   }
   HS_TRY(ctx->d_hit_keys[0].reserve(sizeof(uint64_t) * n));
   HS_TRY(ctx->d_hit_perm.reserve(sizeof(uint32_t) * 2 * n));
-  HS_TRY(ctx->d_hits_sorted.reserve(sizeof(hs_hit) * n));
+  if (!cb) HS_TRY(ctx->d_hits_sorted.reserve(sizeof(hs_hit) * n));
   const unsigned grid = (unsigned)((n + 255) / 256);
   KeyPtrs in, sorted;
   memset(&in, 0, sizeof in);
@@ -517,6 +567,10 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
     HS_TRY(read_back(ctx, ovf, &h_ovf, sizeof h_ovf));
     one_word = h_ovf == 0;
   }
+  if (cb && !one_word) {
+    set_error("compact hits need the one-word hit key (query, table and id within 64 bits)");
+    return HS_ERR_UNSUPPORTED;
+  }
   if (one_word) {
     in.w[0] = ctx->d_hit_keys[0].as<uint64_t>();
     const int kbits = qshift + qbits;
@@ -536,8 +590,16 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n) {
   ctx->stats.ms_sort_upsweep = before.ms_sort_upsweep;
   ctx->stats.ms_sort_scan = before.ms_sort_scan;
   ctx->stats.ms_sort_downsweep = before.ms_sort_downsweep;
-  hit_gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, perm, n, ctx->d_hits_sorted.as<hs_hit>());
-  ctx->stats.kernel_launches++;
+  if (cb) {
+    hit_gather_compact_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, perm, n, ctx->id_base, cb->id_bits,
+                                                            ctx->d_cidt.as<uint32_t>(), ctx->d_cdist.as<double>());
+    hit_offsets_kernel<<<(unsigned)((n + 256) / 256), 256, 0, ctx->stream>>>(sorted.w[0], n, qshift, cb->qa, cb->qb, cb->base,
+                                                                            ctx->d_coffsets.as<uint64_t>());
+    ctx->stats.kernel_launches += 2;
+  } else {
+    hit_gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, perm, n, ctx->d_hits_sorted.as<hs_hit>());
+    ctx->stats.kernel_launches++;
+  }
   HS_CUDA(cudaGetLastError());
   return HS_OK;
 }
@@ -722,7 +784,7 @@ static int deliver_hits(hs_ctx *ctx, uint64_t nh, uint64_t dev_cap, hs_hit *hits
 }
 
 static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hits_host, void *hits_dev,
-                       uint64_t cap, uint64_t *nhits) {
+                       uint64_t cap, uint64_t *nhits, hs_compact_hits *compact = nullptr) {
   if (!ctx->indexed) {
     set_error("hs_search: call hs_build_index first");
     return HS_ERR_INVALID;
@@ -770,11 +832,9 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
         if (r.y > r.x) order.push_back(((uint64_t)r.x << 32) | q);
       }
       std::sort(order.begin(), order.end());
-      if (l == 0)
-        if (const char *e = getenv("HS_PLAN_STATS"))
-          if (atoi(e))
-            fprintf(stderr, "[plan] table 0 sorted at %.3f ms\n",
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - _tp0).count());
+      if (l == 0 && ctx->plan_stats)
+        fprintf(stderr, "[plan] table 0 sorted at %.3f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - _tp0).count());
       size_t i = 0;
       while (i < order.size() && rcs[l] == HS_OK) {
         const uint32_t mb = (uint32_t)(order[i] >> 32);
@@ -794,10 +854,9 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
     } else {
       for (uint32_t l = 0; l < L; ++l) build(l);
     }
-    if (const char *e = getenv("HS_PLAN_STATS"))
-      if (atoi(e))
-        fprintf(stderr, "[plan] sub-plans built at %.3f ms\n",
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - _tp0).count());
+    if (ctx->plan_stats)
+      fprintf(stderr, "[plan] sub-plans built at %.3f ms\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - _tp0).count());
     {
       size_t ni = 0, nit = 0, nmi = 0, nmu = 0, nq = 0, nqt = 0, nqm = 0;
       for (const FilterPlan &P : sub) {
@@ -854,11 +913,21 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   // so the blocks concatenate into the final order).  HS_NO_PIPELINE=1 disables it.
   // (Splitting the *filter* by query block was measured too: it quarters the queries per
   // bucket and doubles the tensor filter's time, DESIGN.md.)
-  const char *nop = getenv("HS_NO_PIPELINE");
-  const bool pipelined = hits_host && ctx->nranks == 1 && (ctx->prm.flags & HS_FLAG_SORT_HITS) && Q >= 2048 &&
-                         !(nop && atoi(nop));
+  int id_bits = 0;
+  if (compact) {
+    if (ctx->nranks > 1) {
+      set_error("hs_search_points_compact: not available on a context that joined a communicator");
+      return HS_ERR_UNSUPPORTED;
+    }
+    HS_TRY(compact_id_bits(ctx, &id_bits));
+    compact->id_bits = (uint32_t)id_bits;
+    HS_TRY(ctx->d_coffsets.reserve(sizeof(uint64_t) * ((size_t)Q + 1)));
+  }
+  const bool pipelined = compact || (hits_host && ctx->nranks == 1 && (ctx->prm.flags & HS_FLAG_SORT_HITS) && Q >= 2048 &&
+                                     !ctx->no_pipeline);
   if (pipelined) {
     const uint32_t nblk = kSearchBlocks;
+    const SearchBlocks sblk = search_blocks(Q);
     if (!ctx->copy_stream) HS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while (ctx->ev_chunk.size() < 4 * nblk + 8) {
       cudaEvent_t e;
@@ -905,15 +974,33 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
       const uint64_t nvalid = std::min<uint64_t>(nh, cap_left);
       // the sorted buffer written now was last read by the copy of block c-2
       if (c >= 2) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[4 * (c - 2) + 3], 0));
-      HS_TRY(sort_hits(ctx, ctx->d_hits.as<hs_hit>(), nvalid));
+      CompactBlock cb;
+      cb.qa = c ? sblk.end[c - 1] : 0u;
+      cb.qb = sblk.end[c];
+      cb.base = done;
+      cb.id_bits = id_bits;
+      HS_TRY(sort_hits(ctx, ctx->d_hits.as<hs_hit>(), nvalid, compact ? &cb : nullptr));
       HS_CUDA(cudaEventRecord(ce[2], ctx->stream));
-      if (nvalid) {
-        HS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ce[2], 0));
+      if (nvalid || (compact && c + 1 == nblk)) HS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ce[2], 0));
+      if (nvalid && compact) {
+        HS_CUDA(cudaMemcpyAsync(compact->idt + done, ctx->d_cidt.p, sizeof(uint32_t) * nvalid, cudaMemcpyDeviceToHost,
+                                ctx->copy_stream));
+        HS_CUDA(cudaMemcpyAsync(compact->dist2 + done, ctx->d_cdist.p, sizeof(double) * nvalid, cudaMemcpyDeviceToHost,
+                                ctx->copy_stream));
+      } else if (nvalid) {
         HS_CUDA(cudaMemcpyAsync(hits_host + done, ctx->d_hits_sorted.p, sizeof(hs_hit) * nvalid, cudaMemcpyDeviceToHost,
                                 ctx->copy_stream));
       }
+      if (compact && c + 1 == nblk)  // every block's offsets are written: one copy of the whole array
+        HS_CUDA(cudaMemcpyAsync(compact->offsets, ctx->d_coffsets.p, sizeof(uint64_t) * ((size_t)Q + 1),
+                                cudaMemcpyDeviceToHost, ctx->copy_stream));
       HS_CUDA(cudaEventRecord(ce[3], ctx->copy_stream));
-      std::swap(ctx->d_hits_sorted, ctx->d_hits_sorted_alt);
+      if (compact) {
+        std::swap(ctx->d_cidt, ctx->d_cidt_alt);
+        std::swap(ctx->d_cdist, ctx->d_cdist_alt);
+      } else {
+        std::swap(ctx->d_hits_sorted, ctx->d_hits_sorted_alt);
+      }
       done += nvalid;
       total += nh;
     }
@@ -940,10 +1027,9 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   FilterPlan plan;
   const auto _t0 = std::chrono::steady_clock::now();
   HS_TRY(make_plan(plan, 0, Q));
-  if (const char *e = getenv("HS_PLAN_STATS"))
-    if (atoi(e))
-      fprintf(stderr, "[plan] host planning %.3f ms\n",
-              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - _t0).count());
+  if (ctx->plan_stats)
+    fprintf(stderr, "[plan] host planning %.3f ms\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - _t0).count());
   HS_CUDA(cudaEventRecord(ev[12], ctx->stream));
   uint64_t nsurv = 0;
   HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
@@ -1068,6 +1154,57 @@ static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit
   return rc;
 }
 
+// Residue codes index every table of the path (projection partial sums, embedding rows, residue-pair
+// tables): a byte >= 20 in the DB would read past them.  Counted here, once per load, on the device.
+__global__ void validate_codes_kernel(const uint8_t *__restrict__ codes, uint64_t b0, uint64_t b1,
+                                      unsigned long long *__restrict__ bad) {
+  // [b0, b1) with b0 a multiple of 16: whole 16-byte words, then the ragged tail byte by byte
+  const uint64_t nvec = (b1 - b0) / 16;
+  const uint4 *src = reinterpret_cast<const uint4 *>(codes + b0);
+  unsigned int mine = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(src + i);
+    mine |= __vcmpgeu4(v.x, 0x14141414u) | __vcmpgeu4(v.y, 0x14141414u) | __vcmpgeu4(v.z, 0x14141414u) |
+            __vcmpgeu4(v.w, 0x14141414u);
+  }
+  if (blockIdx.x == 0)
+    for (uint64_t i = b0 + nvec * 16 + threadIdx.x; i < b1; i += blockDim.x) mine |= codes[i] >= HS_AA ? 1u : 0u;
+  if (__any_sync(0xffffffffu, mine != 0) && (threadIdx.x & 31) == 0) atomicAdd(bad, 1ull);
+}
+constexpr int kBadCodeSlot = 30;  // d_counters slot
+// Enqueues the check of fragments [f0, f1) (f0 * len a multiple of 16) on the ctx stream.
+static int validate_codes_enqueue(hs_ctx *ctx, uint64_t f0, uint64_t f1) {
+  if (f1 <= f0) return HS_OK;
+  const uint64_t b0 = f0 * ctx->prm.len, b1 = f1 * ctx->prm.len;
+  const unsigned grid = (unsigned)std::min<uint64_t>(((b1 - b0) / 16 + 255) / 256 + 1, (uint64_t)ctx->num_sms * 8);
+  validate_codes_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_codes.as<uint8_t>(), b0, b1,
+                                                      ctx->d_counters.as<unsigned long long>() + kBadCodeSlot);
+  HS_CUDA(cudaGetLastError());
+  return HS_OK;
+}
+static int validate_codes_begin(hs_ctx *ctx) {
+  HS_CUDA(cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + kBadCodeSlot, 0, sizeof(unsigned long long), ctx->stream));
+  return HS_OK;
+}
+// Reads the verdict (synchronises the ctx stream); a bad DB is dropped.
+static int validate_codes_end(hs_ctx *ctx, const char *who) {
+  unsigned long long bad = 0;
+  HS_TRY(read_back(ctx, ctx->d_counters.as<unsigned long long>() + kBadCodeSlot, &bad, sizeof bad));
+  if (bad) {
+    ctx->N = 0;
+    ctx->npad = 0;
+    ctx->hashed = ctx->indexed = ctx->have_codes_pm = ctx->have_rec = false;
+    set_error("%s: the fragments hold residue codes outside 0..19 (hs_letter_to_code returns -1 for B, J, O, U, X, Z)", who);
+    return HS_ERR_INVALID;
+  }
+  return HS_OK;
+}
+int validate_codes(hs_ctx *ctx, const char *who) {
+  HS_TRY(validate_codes_begin(ctx));
+  HS_TRY(validate_codes_enqueue(ctx, 0, ctx->N));
+  return validate_codes_end(ctx, who);
+}
+
 }  // namespace hs
 
 using namespace hs;
@@ -1126,6 +1263,14 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   hs_ctx *ctx = new (std::nothrow) hs_ctx();
   if (!ctx) return HS_ERR_NOMEM;
   ctx->device = device;
+  auto env_on = [](const char *name) {
+    const char *e = getenv(name);
+    return e && atoi(e) != 0;
+  };
+  ctx->no_pipeline = env_on("HS_NO_PIPELINE");
+  ctx->no_load_overlap = env_on("HS_NO_LOAD_OVERLAP");
+  ctx->plan_stats = env_on("HS_PLAN_STATS");
+  ctx->no_mma_filter = env_on("HS_NO_MMA_FILTER");
   ctx->num_sms = prop.multiProcessorCount;
   ctx->prm = *params;
   ctx->dim = params->len * HS_CDIM;
@@ -1180,6 +1325,8 @@ void hs_destroy(hs_ctx_t *ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   ctx->d_hits_sorted_alt.release();
+  DevBuf *cbufs[] = {&ctx->d_cidt, &ctx->d_cidt_alt, &ctx->d_cdist, &ctx->d_cdist_alt, &ctx->d_coffsets};
+  for (DevBuf *b : cbufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1237,9 +1384,8 @@ static int load_common(hs_ctx *ctx, uint64_t N, uint64_t id_base) {
 // the PCIe transfer.  Returns HS_OK with *done = false when the plain path must be taken.
 static int load_and_hash_overlapped(hs_ctx *ctx, const uint8_t *codes, uint64_t N, bool *done) {
   *done = false;
-  const char *e = getenv("HS_NO_LOAD_OVERLAP");
   if (!ctx->have_projection || !hash_single_launch_records(ctx) || N < 8 * kHashRangeAlign ||
-      (ctx->prm.flags & (HS_FLAG_HASH_EXACT | HS_FLAG_HASH_AUDIT)) || (e && atoi(e)))
+      (ctx->prm.flags & (HS_FLAG_HASH_EXACT | HS_FLAG_HASH_AUDIT)) || ctx->no_load_overlap)
     return HS_OK;
   const uint32_t nblk = 8, len = ctx->prm.len;
   const uint64_t blk = ((N + nblk - 1) / nblk + kHashRangeAlign - 1) / kHashRangeAlign * kHashRangeAlign;
@@ -1252,6 +1398,7 @@ static int load_and_hash_overlapped(hs_ctx *ctx, const uint8_t *codes, uint64_t 
   stats_begin(ctx);
   unsigned long long *cnt = ctx->d_counters.as<unsigned long long>();
   HS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 8, ctx->stream));
+  HS_TRY(validate_codes_begin(ctx));
   HS_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   HS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[0], 0));  // earlier work on the ctx stream is done with d_codes
   for (uint64_t f0 = 0, c = 0; f0 < N; f0 += blk, ++c) {
@@ -1260,12 +1407,14 @@ static int load_and_hash_overlapped(hs_ctx *ctx, const uint8_t *codes, uint64_t 
                             cudaMemcpyHostToDevice, ctx->copy_stream));
     HS_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
     HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
+    HS_TRY(validate_codes_enqueue(ctx, f0, f1));
     HS_TRY(launch_hash_fast(ctx, false, f0, f1));
   }
   HS_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   unsigned long long h[4];
   HS_CUDA(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  HS_TRY(validate_codes_end(ctx, "hs_load_fragments"));
   ctx->stats.guard_hits = h[0];
   ctx->stats.guard_corrected = h[1];
   ctx->stats.ms_hash = ev_ms(ctx->ev[0], ctx->ev[1]);  // includes the transfer it overlaps
@@ -1291,8 +1440,7 @@ int hs_load_fragments(hs_ctx_t *ctx, const uint8_t *codes, uint64_t N, uint64_t 
   HS_TRY(load_and_hash_overlapped(ctx, codes, N, &hashed));
   if (hashed) return HS_OK;
   if (N) HS_CUDA(cudaMemcpyAsync(ctx->d_codes.p, codes, (size_t)N * ctx->prm.len, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  return HS_OK;
+  return validate_codes(ctx, "hs_load_fragments");
 }
 
 int hs_load_fragments_dev(hs_ctx_t *ctx, const void *codes_dev, uint64_t N, uint64_t id_base) {
@@ -1303,8 +1451,7 @@ int hs_load_fragments_dev(hs_ctx_t *ctx, const void *codes_dev, uint64_t N, uint
   HS_CUDA(cudaSetDevice(ctx->device));
   HS_TRY(load_common(ctx, N, id_base));
   if (N) HS_CUDA(cudaMemcpyAsync(ctx->d_codes.p, codes_dev, (size_t)N * ctx->prm.len, cudaMemcpyDeviceToDevice, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  return HS_OK;
+  return validate_codes(ctx, "hs_load_fragments_dev");
 }
 
 int hs_extract_windows(hs_ctx_t *ctx, const uint8_t *residues, const uint32_t *start_index, uint32_t nprot,
@@ -1360,6 +1507,26 @@ int hs_hash(hs_ctx_t *ctx, int32_t *buckets_out) {
   ctx->hashed = true;
   ctx->indexed = false;
   ctx->hash_stats = ctx->stats;
+  return HS_OK;
+}
+
+int hs_hash_audit(hs_ctx_t *ctx, uint64_t *residual_flips) {
+  if (!ctx || !residual_flips || !ctx->hashed) {
+    set_error("hs_hash_audit: null argument or hs_hash not run");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  *residual_flips = 0;
+  if (ctx->N == 0) return HS_OK;
+  unsigned long long *cnt = ctx->d_counters.as<unsigned long long>();
+  HS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 8, ctx->stream));
+  HS_TRY(launch_hash_exact(ctx, false, true));
+  unsigned long long h[4];
+  HS_CUDA(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  *residual_flips = h[3];
+  ctx->stats.residual_flips = h[3];
+  ctx->hash_stats.residual_flips = h[3];
   return HS_OK;
 }
 
@@ -1493,6 +1660,35 @@ int hs_search_codes(hs_ctx_t *ctx, const uint8_t *qcodes, uint32_t Q, hs_hit *hi
   QueryInput in;
   in.h_codes = qcodes;
   return search_impl(ctx, in, Q, hits, nullptr, cap, nhits);
+}
+
+int hs_search_points_compact(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_compact_hits *out, uint64_t *nhits) {
+  if (!ctx || (!qpoints && Q) || !out || !out->offsets || (out->cap && (!out->idt || !out->dist2)) || !nhits) {
+    set_error("hs_search_points_compact: null argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  QueryInput in;
+  in.h_points = qpoints;
+  return search_impl(ctx, in, Q, nullptr, nullptr, out->cap, nhits, out);
+}
+
+int hs_expand_hits(const hs_compact_hits *in, uint32_t Q, uint64_t id_base, hs_hit *hits_out) {
+  if (!in || !in->offsets || (in->offsets[Q] && (!in->idt || !in->dist2 || !hits_out)) || in->id_bits == 0 || in->id_bits > 31) {
+    set_error("hs_expand_hits: bad argument");
+    return HS_ERR_INVALID;
+  }
+  const uint32_t id_mask = (1u << in->id_bits) - 1u;
+  for (uint32_t q = 0; q < Q; ++q)
+    for (uint64_t i = in->offsets[q]; i < in->offsets[q + 1]; ++i) {
+      hs_hit h;
+      h.query = q;
+      h.table_first = in->idt[i] >> in->id_bits;
+      h.db_id = id_base + (in->idt[i] & id_mask);
+      h.dist2 = in->dist2[i];
+      hits_out[i] = h;
+    }
+  return HS_OK;
 }
 
 int hs_search_points_dev(hs_ctx_t *ctx, const void *qpoints_dev, uint32_t Q, void *hits_dev, uint64_t cap,

@@ -154,6 +154,7 @@ struct hs_ctx {
   hs::DevBuf d_q64, d_qkeys, d_qvalid, d_qrange, d_tq, d_work, d_qlist, d_surv, d_hits, d_counters;
   hs::DevBuf d_hit_keys[3], d_hit_perm, d_hits_sorted, d_hits_sorted_alt;
   hs::DevBuf d_surv_blk;                // survivors regrouped by query block (pipelined verify / copy-out)
+  hs::DevBuf d_cidt, d_cidt_alt, d_cdist, d_cdist_alt, d_coffsets;  // compact (CSR) hit output, double buffered
   cudaStream_t copy_stream = nullptr;   // D2H of sorted hit blocks, overlapped with the next block's search
   std::vector<cudaEvent_t> ev_chunk;
   hs::DevBuf d_misc, d_tabptrs, d_qcodes, d_hits_gathered, d_residues, d_starts;
@@ -176,6 +177,12 @@ struct hs_ctx {
   // comm
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+
+  // debugging switches, read from the environment once in hs_create
+  bool no_pipeline = false;      // HS_NO_PIPELINE: host-buffer searches in one pass (no query blocks)
+  bool no_load_overlap = false;  // HS_NO_LOAD_OVERLAP: hs_load_fragments copies first, hashes later
+  bool plan_stats = false;       // HS_PLAN_STATS: print the filter work-list statistics
+  bool no_mma_filter = false;    // HS_NO_MMA_FILTER: keep the Euclidean metric off the pipelined tensor filter
 
   hs_stats stats{};
   hs_stats hash_stats{};   // counters / timing of the hash that produced the current keys

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "internal.cuh"
 
 namespace hs {
 
@@ -55,7 +56,7 @@ int extract_windows_impl(hs_ctx *ctx, const uint8_t *residues, const uint32_t *s
   ctx->N = n;
   ctx->id_base = id_base;
   ctx->npad = (n + 15) & ~15ull;
-  ctx->hashed = ctx->indexed = ctx->have_codes_pm = false;
+  ctx->hashed = ctx->indexed = ctx->have_codes_pm = ctx->have_rec = false;
   HS_TRY(ctx->d_codes.reserve((size_t)n * len + 64));
   if (n == 0) return HS_OK;
   HS_TRY(ctx->d_residues.reserve(total + 16));
@@ -76,8 +77,7 @@ int extract_windows_impl(hs_ctx *ctx, const uint8_t *residues, const uint32_t *s
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   if (pos_out) HS_CUDA(cudaMemcpyAsync(pos_out, d_pos, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  return HS_OK;
+  return validate_codes(ctx, "hs_extract_windows");
 }
 
 }  // namespace hs

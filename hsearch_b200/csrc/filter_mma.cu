@@ -870,8 +870,7 @@ int mma_geometry(const hs_ctx *ctx, MmaGeometry *g) {
 bool mma_filter_usable(const hs_ctx *ctx) {
   if (ctx->prm.metric != HS_METRIC_EUCLID_FP64) return false;
   if (ctx->prm.flags & HS_FLAG_SCALAR_FILTER) return false;
-  const char *e = getenv("HS_NO_MMA_FILTER");
-  if (e && atoi(e)) return false;
+  if (ctx->no_mma_filter) return false;
   MmaGeometry g;
   if (mma_geometry(ctx, &g) != HS_OK) return false;
   for (int i = 0; i < HS_AA * HS_CDIM; ++i)

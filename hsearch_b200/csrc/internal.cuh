@@ -21,4 +21,5 @@ int ensure_identity_store(hs_ctx *ctx);
 int selfjoin_bucket_mma(hs_ctx *ctx, uint32_t table, uint32_t mb, uint32_t me, uint64_t *nsurv, uint64_t *npairs,
                         bool *used);
 int read_back(hs_ctx *ctx, const void *d_src, void *h_dst, size_t bytes);  // small, synchronising
+int validate_codes(hs_ctx *ctx, const char *who);  // residue codes of the loaded DB are 0..19 (synchronising)
 }  // namespace hs

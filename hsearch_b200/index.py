@@ -74,6 +74,7 @@ class HSearch:
         self.dim = 8 * kmer_length
         self.K, self.L = hash_K, hash_L
         self.device = device
+        self.id_base = 0
 
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx.value:
@@ -112,9 +113,11 @@ class HSearch:
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         assert codes.ndim == 2 and codes.shape[1] == self.len
         check(self.lib.hs_load_fragments(self.ctx, ptr(codes, C.c_uint8), codes.shape[0], id_base))
+        self.id_base = id_base
 
     def load_fragments_dev(self, dev_ptr, n, id_base=0):
         check(self.lib.hs_load_fragments_dev(self.ctx, C.c_void_p(dev_ptr), n, id_base))
+        self.id_base = id_base
 
     def extract_windows(self, residues, start_index, stride=1, id_base=0, want_pos=True):
         residues = np.ascontiguousarray(residues, dtype=np.uint8)
@@ -126,6 +129,7 @@ class HSearch:
         check(self.lib.hs_extract_windows(self.ctx, ptr(residues, C.c_uint8), ptr(start_index, C.c_uint32), nprot,
                                           stride, id_base, ptr(pos, C.c_uint32) if want_pos else None, cap,
                                           C.byref(nfrag)))
+        self.id_base = id_base
         return nfrag.value, (pos[:nfrag.value] if want_pos else None)
 
     @property
@@ -138,6 +142,12 @@ class HSearch:
         out = np.zeros((n, self.L, self.K), dtype=np.int32) if want_buckets else None
         check(self.lib.hs_hash(self.ctx, ptr(out, C.c_int32) if want_buckets else None))
         return out
+
+    def hash_audit(self):
+        """Residual FP32 boundary flips of the current keys against the all-FP64 hash (must be 0)."""
+        n = C.c_uint64(0)
+        check(self.lib.hs_hash_audit(self.ctx, C.byref(n)))
+        return n.value
 
     def keys(self, table):
         kw = self.stats().key_words
@@ -210,6 +220,35 @@ class HSearch:
         q = np.ascontiguousarray(qcodes, dtype=np.uint8).reshape(-1, self.len)
         return self._call_hits(self.lib.hs_search_codes, q, C.c_uint8, q.shape[0], cap)
 
+    def search_points_compact(self, qpoints, cap=1 << 20, expand=True):
+        """hs_search_points_compact: per-query CSR (offsets, id | table << id_bits, dist2); with
+        expand=True the hs_hit records hs_search_points would return (hs_expand_hits)."""
+        q = np.ascontiguousarray(qpoints, dtype=np.float64).reshape(-1, self.dim)
+        Q = q.shape[0]
+        cap = int(cap)
+        while True:
+            off = np.zeros(Q + 1, dtype=np.uint64)
+            idt = np.zeros(max(cap, 1), dtype=np.uint32)
+            d2 = np.zeros(max(cap, 1), dtype=np.float64)
+            ch = capi.CompactHits(ptr(off, C.c_uint64), ptr(idt, C.c_uint32), ptr(d2, C.c_double), cap, 0)
+            n = C.c_uint64(0)
+            rc = self.lib.hs_search_points_compact(self.ctx, ptr(q, C.c_double), Q, C.byref(ch), C.byref(n))
+            if rc == capi.HS_ERR_CAPACITY:
+                cap = int(n.value)
+                continue
+            check(rc)
+            break
+        if not expand:
+            return off, idt[:n.value], d2[:n.value], int(ch.id_bits)
+        hits = np.zeros(max(int(n.value), 1), dtype=HIT_DTYPE)
+        check(self.lib.hs_expand_hits(C.byref(ch), Q, self.id_base, hits.ctypes.data))
+        return hits[:n.value]
+
+    def hits_checksum_dev(self, hits_dev_ptr, n):
+        s = C.c_uint64(0)
+        check(self.lib.hs_hits_checksum_dev(self.ctx, C.c_void_p(hits_dev_ptr), n, C.byref(s)))
+        return s.value
+
     def bruteforce_points(self, qpoints, cap=1 << 20):
         q = np.ascontiguousarray(qpoints, dtype=np.float64).reshape(-1, self.dim)
         return self._call_hits(self.lib.hs_bruteforce_points, q, C.c_double, q.shape[0], cap)
@@ -219,6 +258,14 @@ class HSearch:
             return self._call_hits(self.lib.hs_bruteforce_codes, None, C.c_uint8, 0, cap)
         q = np.ascontiguousarray(qcodes, dtype=np.uint8).reshape(-1, self.len)
         return self._call_hits(self.lib.hs_bruteforce_codes, q, C.c_uint8, q.shape[0], cap)
+
+    @staticmethod
+    def hits_checksum(hits):
+        """Order-independent checksum of a HIT_DTYPE array (hs_hits_checksum, host)."""
+        hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
+        s = C.c_uint64(0)
+        check(capi.load().hs_hits_checksum(hits.ctypes.data_as(C.c_void_p), len(hits), C.byref(s)))
+        return s.value
 
     @staticmethod
     def _recall_dict(r):

@@ -181,6 +181,11 @@ uint64_t hs_num_fragments(hs_ctx_t *ctx);
  * the packed digit-string keys.  buckets_out[N][L][K] (host) may be NULL.
  * Replaces LSH::HashKey over motif_both_points.cpp:212-216. */
 int hs_hash(hs_ctx_t *ctx, int32_t *buckets_out);
+/* FP64 audit of the keys hs_hash (or the overlapped hash of hs_load_fragments) produced:
+ * every projection of every fragment is recomputed in FP64 in the reference's operation order
+ * (lsh.hpp:33-49) and compared; *residual_flips = (fragment, table) keys that differ -- required
+ * to be zero.  The same check HS_FLAG_HASH_AUDIT runs inside hs_hash, callable after the fact. */
+int hs_hash_audit(hs_ctx_t *ctx, uint64_t *residual_flips);
 /* keys_out[N][key_words] (host, word 0 = least significant) of table `table`. */
 int hs_get_keys(hs_ctx_t *ctx, uint32_t table, uint64_t *keys_out);
 /* Pack a reference key string (digits and '-') the way the device does:
@@ -212,6 +217,34 @@ int hs_search_codes(hs_ctx_t *ctx, const uint8_t *qcodes, uint32_t Q, hs_hit *hi
  * nothing crosses PCIe except the hit count. */
 int hs_search_points_dev(hs_ctx_t *ctx, const void *qpoints_dev, uint32_t Q, void *hits_dev,
                          uint64_t cap, uint64_t *nhits);
+
+/* Compact result layout (12 bytes per hit instead of the 24 of hs_hit): the hit list of
+ * motif_both_points.cpp:224-245 as a per-query CSR.  The hits of query q are the entries
+ * [offsets[q], offsets[q+1]) of idt / dist2, in the reference's output order (first table,
+ * then ascending db id).  idt = local id | table_first << id_bits with local id = db_id -
+ * id_base; the query of an entry is implied by its segment.  The caller owns the three
+ * arrays (offsets: Q+1 entries; idt, dist2: cap entries); id_bits is set by the call. */
+typedef struct {
+  uint64_t *offsets; /* [Q+1] */
+  uint32_t *idt;     /* [cap] */
+  double *dist2;     /* [cap] */
+  uint64_t cap;
+  uint32_t id_bits;  /* out */
+} hs_compact_hits;
+/* hs_search_points with the compact result layout (host buffers; HS_FLAG_SORT_HITS is implied).
+ * Half the device-to-host bytes of hs_search_points.  HS_ERR_UNSUPPORTED when local id and
+ * table do not fit 32 bits together; HS_ERR_CAPACITY as for hs_search_points. */
+int hs_search_points_compact(hs_ctx_t *ctx, const double *qpoints, uint32_t Q, hs_compact_hits *out, uint64_t *nhits);
+/* Expands a compact result into the hs_hit records hs_search_points returns (host only):
+ * hits_out[offsets[Q]] receives exactly the same bytes. */
+int hs_expand_hits(const hs_compact_hits *in, uint32_t Q, uint64_t id_base, hs_hit *hits_out);
+
+/* Order-independent 64-bit checksum of a hit list: the sum mod 2^64 over the hits of a mix of
+ * (query, table_first, db_id, bit pattern of dist2).  Equal multisets of hits give equal sums
+ * whatever their order or their split over ranks (partial sums add), so an N-GPU run is
+ * compared with a 1-GPU run by one number.  _dev: the list is in device memory. */
+int hs_hits_checksum(const hs_hit *hits, uint64_t n, uint64_t *sum_out);
+int hs_hits_checksum_dev(hs_ctx_t *ctx, const void *hits_dev, uint64_t n, uint64_t *sum_out);
 
 /* ---- brute force (G1) ------------------------------------------------------- */
 /* All Q x N distances, hits only (motif_both_points_noLSH.cpp:36-56; the

@@ -91,3 +91,41 @@ def test_evaluate_recall_null_arguments():
     assert lib.hs_evaluate_recall_dev(None, None, 0, None, 0, 1, C.byref(r)) == capi.HS_ERR_INVALID
     assert b"null" in lib.hs_last_error()
     assert C.sizeof(capi.Recall) == 16 + 3 * 8 + 2 * 8 * capi.RECALL_BINS  # hs_recall of include/hsearch_b200.h
+
+
+def test_hit_checksum_host_properties():
+    rng = np.random.default_rng(5)
+    hits = np.zeros(1000, dtype=capi.HIT_DTYPE)
+    hits["query"] = rng.integers(0, 100, 1000)
+    hits["table_first"] = rng.integers(0, 4, 1000)
+    hits["db_id"] = rng.integers(0, 1 << 40, 1000)
+    hits["dist2"] = rng.random(1000) * 900
+    s = hb.HSearch.hits_checksum(hits)
+    assert s == hb.HSearch.hits_checksum(hits[rng.permutation(1000)])
+    parts = (hb.HSearch.hits_checksum(hits[:300]) + hb.HSearch.hits_checksum(hits[300:])) % (1 << 64)
+    assert parts == s
+    for field in ("query", "table_first", "db_id"):
+        other = hits.copy()
+        other[field][17] += 1
+        assert hb.HSearch.hits_checksum(other) != s
+    assert hb.HSearch.hits_checksum(hits[:0]) == 0
+
+
+def test_expand_compact_hits_host():
+    lib = capi.load()
+    Q, id_bits = 5, 20
+    counts = np.array([3, 0, 2, 0, 1])
+    off = np.zeros(Q + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(counts)
+    ids = np.array([5, 9, 7, 1, 2, 1048575], dtype=np.uint32)
+    tabs = np.array([0, 0, 2, 1, 3, 3], dtype=np.uint32)
+    idt = (ids | (tabs << id_bits)).astype(np.uint32)
+    d2 = np.array([0.0, 1.5, 2.5, 3.5, 4.5, 899.999])
+    ch = capi.CompactHits(capi.ptr(off, C.c_uint64), capi.ptr(idt, C.c_uint32), capi.ptr(d2, C.c_double), 6, id_bits)
+    out = np.zeros(6, dtype=capi.HIT_DTYPE)
+    capi.check(lib.hs_expand_hits(C.byref(ch), Q, 10 ** 10, out.ctypes.data))
+    assert out["query"].tolist() == [0, 0, 0, 2, 2, 4]
+    assert out["table_first"].tolist() == tabs.tolist()
+    assert out["db_id"].tolist() == (ids.astype(np.uint64) + 10 ** 10).tolist()
+    assert out["dist2"].tolist() == d2.tolist()
+    assert lib.hs_expand_hits(None, Q, 0, None) == capi.HS_ERR_INVALID

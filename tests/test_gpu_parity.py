@@ -445,12 +445,16 @@ def test_search_pipelined_blocks_equal_single_pass(oracle, monkeypatch):
     length, K, L, W, R = 10, 4, 4, 50.0, 30.0
     codes = random_codes(40000, length, seed=21)
     qcodes = planted_queries(codes, 2600, seed=22, frac=0.5)
+    monkeypatch.setenv("HS_NO_PIPELINE", "1")   # read once, by hs_create
+    h1, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+    h1.load_fragments(codes)
+    h1.build_index()
+    single = h1.search_codes(qcodes)
+    h1.close()
+    monkeypatch.setenv("HS_NO_PIPELINE", "0")
     h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
     h.load_fragments(codes)
     h.build_index()
-    monkeypatch.setenv("HS_NO_PIPELINE", "1")
-    single = h.search_codes(qcodes)
-    monkeypatch.setenv("HS_NO_PIPELINE", "0")
     blocks = h.search_codes(qcodes)
     assert len(single) > 1000
     assert np.array_equal(single, blocks)
@@ -606,12 +610,16 @@ def test_search_pipelined_dense_queries_and_small_capacity(oracle, monkeypatch):
     rng = np.random.default_rng(72)
     q = oracle.embed(planted_queries(codes, 2300, seed=73, frac=0.8), tab)
     q[::3] += rng.normal(0.0, 0.5, size=q[::3].shape)      # every third centre is not a residue string
+    monkeypatch.setenv("HS_NO_PIPELINE", "1")   # read once, by hs_create
+    h1, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+    h1.load_fragments(codes)
+    h1.build_index()
+    single = h1.search_points(q)
+    h1.close()
+    monkeypatch.setenv("HS_NO_PIPELINE", "0")
     h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
     h.load_fragments(codes)
     h.build_index()
-    monkeypatch.setenv("HS_NO_PIPELINE", "1")
-    single = h.search_points(q)
-    monkeypatch.setenv("HS_NO_PIPELINE", "0")
     assert len(single) > 500
     assert np.array_equal(h.search_points(q), single)
     assert np.array_equal(h.search_points(q, cap=len(single) // 2), single)
