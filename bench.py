@@ -240,29 +240,37 @@ def run_native(a):
     # size the hit buffer with one untimed pass
     h.build_index()
     nh0 = h.search_points_dev(qpts.data_ptr(), Q, 0, 0)
-    if world > 1:   # the same capacity on every rank (padded all-gather blocks)
+    if world > 1:   # the same capacity on every rank
         mx = torch.tensor([nh0], dtype=torch.int64, device=dev)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         cap = int(mx.item() * 1.05) + 1024
     else:
         cap = int(nh0 * 1.05) + 1024
-    # two hit buffers: at N > 1 the gather of batch i to rank 0 (NCCL over NVLink) runs beside
-    # the hash / index build of batch i + 1, so a buffer is reused only two steps later
-    nslot = 2 if world > 1 else 1
-    hits_bufs = [torch.empty(cap * 24, dtype=torch.uint8, device=dev) for _ in range(nslot)]
-    hits_dev = hits_bufs[0]
-    recv_bufs = [None] * nslot
+    # N > 1: the contexts join an NCCL communicator inside the library (hs_comm_init; the unique id
+    # travels over torch.distributed, the launcher's plumbing); every search then broadcasts rank 0's
+    # queries and merges all ranks' hits into rank 0's memory in the reference's order (comm.cu: counts
+    # exchanged with NCCL, hits written by their producers straight to their final positions over
+    # NVLink), asynchronously, beside the hash / index build of the next batch.
+    import ctypes as C
+    from hsearch_b200 import capi
+    lib = capi.load()
+    nslot = 1
     if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = np.zeros(128, dtype=np.uint8)
+            capi.check(lib.hs_comm_unique_id(raw.ctypes.data_as(C.c_void_p)))
+            uid = torch.from_numpy(raw)
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        raw = uid.cpu().numpy()
+        capi.check(lib.hs_comm_init(h.ctx, raw.ctypes.data_as(C.c_void_p), rank, world))
         tot = torch.tensor([nh0], dtype=torch.int64, device=dev)
         dist.all_reduce(tot)
-        use_ag = os.environ.get("HS_GATHER_ALLGATHER", "1") == "1"   # measured at N = 8: 95.1 vs 99.7 ms per step
-        if use_ag:   # padded all-gather: every rank holds a receive buffer of world x cap hits
-            recv_bufs = [torch.empty(world * cap * 24, dtype=torch.uint8, device=dev) for _ in range(nslot)]
-        elif rank == 0:
-            recv_bufs = [torch.empty(int(tot.item() * 1.05 + 1024) * 24, dtype=torch.uint8, device=dev)
-                         for _ in range(nslot)]
-    pending = [None] * nslot
+        capi.check(lib.hs_comm_reserve(h.ctx, int(tot.item() * 1.05) + 4096))
+    hits_bufs = [torch.empty(cap * 24, dtype=torch.uint8, device=dev)]
     step_no = [0]
+    merged = {"ptr": 0, "total": 0}
 
     acc = {}
 
@@ -279,29 +287,19 @@ def run_native(a):
         h.build_index()
         s_build = add_stats(["ms_sort", "ms_group", "ms_permute", "ms_sort_upsweep", "ms_sort_scan",
                              "ms_sort_downsweep"]) if collect else h.stats().as_dict()
-        slot = step_no[0] % nslot
         step_no[0] += 1
-        if pending[slot] is not None:      # the gather that last used this buffer pair
-            pending[slot].wait()
-            pending[slot] = None
-        buf = hits_bufs[slot]
-        n = h.search_points_dev(qpts.data_ptr(), Q, buf.data_ptr(), cap)
+        buf = hits_bufs[0]
+        n = h.search_points_dev(qpts.data_ptr(), Q, buf.data_ptr(), cap)   # N > 1: also starts the merge on rank 0
         s_search = add_stats(["ms_qhash", "ms_probe", "ms_host", "ms_filter", "ms_filter_tc", "ms_exact", "ms_hitsort"]) if collect \
             else h.stats().as_dict()
-        total = n
-        if world > 1:
-            if os.environ.get("HS_GATHER_ALLGATHER", "1") == "1":
-                pending[slot] = hdist.HitGather(buf, min(n, cap), 0, allgather_pad=recv_bufs[slot])
-            else:
-                pending[slot] = hdist.HitGather(buf, min(n, cap), 0, out=recv_bufs[slot])
-            total = sum(pending[slot].counts)
-        return n, total, s_search, s_build, s_hash
+        return n, n, s_search, s_build, s_hash
 
     def drain():
-        for i in range(nslot):
-            if pending[i] is not None:
-                pending[i].wait()
-                pending[i] = None
+        """N > 1: completes the merge of the latest batch (earlier ones completed before it, in stream order)."""
+        if world > 1:
+            p, t = C.c_void_p(), C.c_uint64(0)
+            capi.check(lib.hs_comm_result(h.ctx, C.byref(p), C.byref(t)))
+            merged["ptr"], merged["total"] = p.value or 0, int(t.value)
 
     with torch.cuda.stream(stream):
         sampler = ClockSampler(local)
@@ -320,6 +318,8 @@ def run_native(a):
         for _ in range(a.steps):
             nh, nh_total, s_search, s_build, s_hash = step(True)
         drain()                            # every batch's hits are on rank 0 before the clock stops
+        if world > 1:
+            nh_total = merged["total"]
         e1.record(stream)
         torch.cuda.synchronize()
         wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -343,22 +343,21 @@ def run_native(a):
     # direction and its kernels run.  `sequential` is the same call sequence on one context.
     e2e = None
     if not a.no_e2e:
-        import ctypes as C
         import threading
-        from hsearch_b200 import capi
-        lib = capi.load()
         host_codes = torch.empty((N, length), dtype=torch.uint8).pin_memory()
         host_codes.copy_(codes)
         host_q = torch.empty((Q, dim), dtype=torch.float64).pin_memory()
         host_q.copy_(qpts)
         torch.cuda.synchronize()
         nctx = 1 if a.e2e_contexts < 2 else 2
-        h2 = None
-        if nctx == 2:
-            h2 = hb.HSearch(length, a.K, a.L, a.W, a.R, table_variant=hb.HS_TABLE_PRINT6, flags=flags, device=local)
-            h2.seed_projection(12345)
+        # (a context that joined the communicator gathers its hits on rank 0 instead: N > 1 uses fresh ones)
+        extra = []
+        for _ in range(nctx if world > 1 else nctx - 1):
+            hx = hb.HSearch(length, a.K, a.L, a.W, a.R, table_variant=hb.HS_TABLE_PRINT6, flags=flags, device=local)
+            hx.seed_projection(12345)
+            extra.append(hx)
         lanes = []
-        for hh in ([h, h2] if nctx == 2 else [h]):
+        for hh in (extra if world > 1 else [h] + extra):
             off = torch.empty(Q + 1, dtype=torch.int64).pin_memory()
             idt = torch.empty(cap, dtype=torch.int32).pin_memory()
             d2 = torch.empty(cap, dtype=torch.float64).pin_memory()
@@ -411,7 +410,7 @@ def run_native(a):
         split = [a.steps - a.steps // 2, a.steps // 2] if nctx == 2 else [a.steps]
         e_ms = timed(split) / a.steps
         seq_ms = timed([a.steps] + [0] * (len(lanes) - 1)) / a.steps   # one context, no overlap across batches
-        s_e = h.stats().as_dict()  # the last end-to-end search call of context 0
+        s_e = lanes[0]["h"].stats().as_dict()  # the last end-to-end search call of context 0
         nh_e = int(lanes[0]["n"].value)
         # the compact result of the last batch expands to the records of the device-resident run
         e2e_same = None
@@ -441,8 +440,36 @@ def run_native(a):
         for ln in lanes:
             ln["ch"] = None
         del host_codes, lanes
-        if h2 is not None:
-            h2.close()
+        for hx in extra:
+            hx.close()
+
+    # ---- N > 1: the merged list on rank 0 against the ranks' own lists ----------------------------
+    # order-independent 64-bit checksum of (query, first table, db id, dist2 bits): the sum of the ranks'
+    # checksums must equal the checksum of the list merged on rank 0, which must be in the reference's order
+    multi = None
+    if world > 1:
+        cs = torch.tensor([h.hits_checksum_dev(hits_bufs[0].data_ptr(), min(int(nh), cap)) - (1 << 63)], dtype=torch.int64, device=dev)
+        parts = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(parts, cs)
+        cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(cnts, torch.tensor([int(nh)], dtype=torch.int64, device=dev))
+        if rank == 0:
+            want = sum(int(p.item()) + (1 << 63) for p in parts) % (1 << 64)
+            got = h.hits_checksum_dev(merged["ptr"], merged["total"])
+
+            class _Raw:
+                def __init__(self, ptr, nbytes):
+                    self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            mv = torch.as_tensor(_Raw(merged["ptr"], merged["total"] * 24), device=dev)
+            ib = max(1, (world * N - 1).bit_length())
+            mkey = (mv.view(torch.int32)[0::6].to(torch.int64) << (ib + 6)) | (mv.view(torch.int32)[1::6].to(torch.int64) << ib) | \
+                mv.view(torch.int64)[1::3]
+            m_order = bool((mkey[1:] > mkey[:-1]).all().item()) if merged["total"] > 1 else True
+            del mkey, mv
+            multi = {"ranks": world, "hits_per_rank": [int(c.item()) for c in cnts], "merged_hits_on_rank0": merged["total"],
+                     "sum_of_rank_checksums": "%016x" % want, "merged_list_checksum": "%016x" % got,
+                     "checksums_equal": bool(want == got and merged["total"] == sum(int(c.item()) for c in cnts)),
+                     "merged_list_in_reference_order": m_order}
 
     # ---- FP64 audit of the keys of the timed run (every projection of every fragment) -----------
     h.hash()
@@ -611,22 +638,25 @@ def run_native(a):
     recall = None
     if not a.no_recall:
         try:
+            hr = h
+            if world > 1:   # every call on a context that joined the communicator is collective: a private one here
+                hr = hb.HSearch(length, a.K, a.L, a.W, a.R, table_variant=hb.HS_TABLE_PRINT6, flags=flags, device=local)
+                hr.load_fragments_dev(codes.data_ptr(), N, id_base=rank * N)
             with torch.cuda.stream(stream):
-                hflags = h.params.flags
                 t0r = time.perf_counter()
-                nbf = h.bruteforce_points_dev(qpts.data_ptr(), Q, 0, 0)
+                nbf = hr.bruteforce_points_dev(qpts.data_ptr(), Q, 0, 0)
                 bcap = nbf + 1024
                 bf = torch.empty(bcap * 24, dtype=torch.uint8, device=dev)
-                nbf = h.bruteforce_points_dev(qpts.data_ptr(), Q, bf.data_ptr(), bcap)
+                nbf = hr.bruteforce_points_dev(qpts.data_ptr(), Q, bf.data_ptr(), bcap)
                 torch.cuda.synchronize()
                 bf_ms = 1e3 * (time.perf_counter() - t0r) / 2
-            s_bf = h.stats().as_dict()
+            s_bf = hr.stats().as_dict()
 
             lsh_buf = hits_bufs[(step_no[0] - 1) % nslot]
             nl = min(int(nh), cap)
             # evaulate() of the reference on the two device-resident lists (hs_evaluate_recall_dev)
             t0e = time.perf_counter()
-            ev = h.evaluate_recall_dev(bf.data_ptr(), int(nbf), lsh_buf.data_ptr(), nl, Q)
+            ev = hr.evaluate_recall_dev(bf.data_ptr(), int(nbf), lsh_buf.data_ptr(), nl, Q)
             ev_ms = 1e3 * (time.perf_counter() - t0e)
             nzb = [int(i) for i in ((ev["tp_bin"] + ev["fn_bin"]) > 0).nonzero()[0]]
             deciles = {str(i): round(float(ev["tp_bin"][i]) / float(ev["tp_bin"][i] + ev["fn_bin"][i]), 4)
@@ -654,15 +684,17 @@ def run_native(a):
            "data": "synthetic",
            "config": {"workload": workload_name(a), "n_db_per_gpu": N, "n_query": Q, "len": length, "K": a.K,
                       "L": a.L, "W": a.W, "R": a.R, "table": "print6", "sharding": f"db-block x{world}",
-                      "hit_gather": ("hits of every batch all-gathered (NCCL over NVLink/NVSwitch, padded blocks; rank 0 "
-                                     "reads the lists in rank order), started asynchronously beside the next batch's "
-                                     "hash + index build; all gathers complete before the timed region ends")
+                      "hit_gather": ("library path (hs_comm_init / hs_comm_reserve / hs_comm_result): queries broadcast with NCCL; "
+                                     "per-(query, table) hit counts all-gathered with NCCL; every rank writes its sorted hits "
+                                     "to their final positions of the merged list in rank 0's memory (CUDA IPC mapping, peer "
+                                     "stores over NVLink) on a second stream beside the next batch's hash + index build; all "
+                                     "merges complete before the timed region ends")
                       if world > 1 else "single rank",
                       "l2": "inputs (>= 1 GB codes, multi-GB keys) exceed the 126 MB L2; no flush needed"},
            "clocks": clocks, "wall_ms_per_step": wall_ms / a.steps,
            "e2e": e2e, "gpu_launches": int(acc["kernel_launches"]),
            "roofline": roofline, "cpu_baseline": cpu,
-           "checks": checks, "recall": recall,
+           "checks": checks, "multi_gpu_checks": multi, "recall": recall,
            "stages_ms": {k[3:]: round(acc[k] / steps, 4) for k in sorted(acc) if k.startswith("ms_")},
            "kernels": {k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "share": round(v["share_of_step"], 4)}
                        for k, v in kern.items()},

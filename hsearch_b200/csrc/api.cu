@@ -22,35 +22,103 @@ int greedy_cluster_impl(hs_ctx *ctx, uint32_t *center_out, uint32_t *round_out, 
 int union_find_impl(hs_ctx *ctx, uint32_t n, const uint32_t *eu, const uint32_t *ev, uint64_t ne, uint32_t *label_out);
 int extract_windows_impl(hs_ctx *ctx, const uint8_t *residues, const uint32_t *start_index, uint32_t nprot,
                          uint32_t stride, uint64_t id_base, uint32_t *pos_out, uint64_t pos_cap, uint64_t *nfrag);
-int comm_gather_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t *nhits, uint64_t cap);
+int comm_gather_start(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const uint64_t *d_keys, int tshift, uint32_t Q,
+                      bool local_overflow);
 int comm_broadcast(hs_ctx *ctx, void *d_buf, size_t bytes);
 void comm_destroy(hs_ctx *ctx);
 
-// Small device -> host read-backs (counters, flags) go through a mapped pinned staging area
-// written by a kernel, not through cudaMemcpy: a DMA copy would queue behind a large transfer
-// in flight on the copy stream (the device-to-host engine is shared), stalling the pipeline.
-__global__ void small_readback_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, uint32_t nwords) {
-  for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+// Control traffic -- counters, bucket ranges, work lists, a few KB to a few MB per call -- does
+// not use cudaMemcpy: a DMA copy queues on the copy engine of its direction behind whatever bulk
+// transfer is in flight there (this context's hit list, or another context's database load on the
+// same GPU), which stalls the pipeline for the length of that transfer (measured: 19 ms per
+// step).  Instead a kernel moves the bytes between device memory and a mapped pinned staging
+// area over PCIe, on the ctx stream.
+__global__ void ctl_copy_kernel(void *__restrict__ dst, const void *__restrict__ src, size_t nbytes) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | nbytes;
+  if ((al & 15) == 0) {
+    for (size_t i = i0; i < nbytes / 16; i += stride) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+  } else if ((al & 3) == 0) {
+    for (size_t i = i0; i < nbytes / 4; i += stride) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+  } else {
+    for (size_t i = i0; i < nbytes; i += stride) reinterpret_cast<uint8_t *>(dst)[i] = reinterpret_cast<const uint8_t *>(src)[i];
+  }
   __threadfence_system();
 }
+static int ctl_launch(hs_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  const unsigned grid = (unsigned)std::min<size_t>((bytes / 16 + 255) / 256 + 1, 64);
+  ctl_copy_kernel<<<grid, 256, 0, ctx->stream>>>(dst, src, bytes);
+  HS_CUDA(cudaGetLastError());
+  return HS_OK;
+}
+constexpr size_t kCtlDownMax = 8u << 20, kCtlUpArena = 16u << 20;
 
+// Device -> host, synchronising.  (Also the point where the upload arena is known to be drained.)
 int read_back(hs_ctx *ctx, const void *d_src, void *h_dst, size_t bytes) {
   if (bytes == 0) return HS_OK;
-  if ((bytes & 3) || bytes > 1024 || (reinterpret_cast<uintptr_t>(d_src) & 3)) {
+  if (bytes > kCtlDownMax) {
     HS_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->up_used = 0;
     return HS_OK;
   }
-  if (!ctx->h_pinned) {
-    HS_CUDA(cudaHostAlloc(&ctx->h_pinned, 1024, cudaHostAllocMapped));
-    ctx->h_pinned_cap = 1024;
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (ctx->h_pinned_cap < need) {
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_up) cudaFreeHost(ctx->h_up);
+    ctx->h_pinned = nullptr;
+    ctx->h_pinned_cap = 0;
+    const size_t want = std::max<size_t>(need + need / 4, 4096);
+    HS_CUDA(cudaHostAlloc(&ctx->h_pinned, want, cudaHostAllocMapped));
+    ctx->h_pinned_cap = want;
     HS_CUDA(cudaHostGetDevicePointer(&ctx->d_pinned, ctx->h_pinned, 0));
   }
-  small_readback_kernel<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(d_src),
-                                                   reinterpret_cast<uint32_t *>(ctx->d_pinned), (uint32_t)(bytes / 4));
-  HS_CUDA(cudaGetLastError());
+  HS_TRY(ctl_launch(ctx, ctx->d_pinned, d_src, bytes));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->up_used = 0;
   memcpy(h_dst, ctx->h_pinned, bytes);
+  return HS_OK;
+}
+
+// Host -> device, asynchronous: the bytes are copied into the pinned arena now (the caller's
+// buffer may be a temporary) and moved by a kernel in stream order.
+int upload(hs_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+  if (bytes == 0) return HS_OK;
+  if (bytes > kCtlUpArena / 2) {
+    HS_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));  // h_src may be a temporary
+    ctx->up_used = 0;
+    return HS_OK;
+  }
+  if (!ctx->h_up) {
+    HS_CUDA(cudaHostAlloc(&ctx->h_up, kCtlUpArena, cudaHostAllocMapped));
+    HS_CUDA(cudaHostGetDevicePointer(&ctx->d_up, ctx->h_up, 0));
+    ctx->up_used = 0;
+  }
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (ctx->up_used + need > kCtlUpArena) {  // kernels may still read the arena: wait for them
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->up_used = 0;
+  }
+  memcpy((char *)ctx->h_up + ctx->up_used, h_src, bytes);
+  HS_TRY(ctl_launch(ctx, d_dst, (const char *)ctx->d_up + ctx->up_used, bytes));
+  ctx->up_used += need;
+  return HS_OK;
+}
+// the ctx stream was synchronised by the caller: the arena is free again
+void upload_drained(hs_ctx *ctx) { ctx->up_used = 0; }
+
+// Host -> device of a caller's buffer that may be large (queries): read by a kernel straight from
+// the caller's memory when that is pinned, else an ordinary copy.
+static int upload_user(hs_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+  if (bytes == 0) return HS_OK;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, h_src) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
+      bytes <= (64u << 20))
+    return ctl_launch(ctx, d_dst, at.devicePointer, bytes);
+  cudaGetLastError();
+  HS_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return HS_OK;
 }
 
@@ -126,10 +194,7 @@ static int upload_table_pointers(hs_ctx *ctx) {
   h[L] = ctx->d_codes_pm.p;
   h[(HS_MAX_L + 1) + L] = nullptr;
   HS_TRY(ctx->d_tabptrs.reserve(h.size() * sizeof(void *)));
-  HS_CUDA(cudaMemcpyAsync(ctx->d_tabptrs.p, h.data(), h.size() * sizeof(void *), cudaMemcpyHostToDevice,
-                          ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  return HS_OK;
+  return upload(ctx, ctx->d_tabptrs.p, h.data(), h.size() * sizeof(void *));
 }
 const uint8_t *const *dev_stores(hs_ctx *ctx) { return ctx->d_tabptrs.as<const uint8_t *>(); }
 const uint32_t *const *dev_sorted_ids(hs_ctx *ctx) {
@@ -176,8 +241,7 @@ int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t
       HS_CUDA(cudaEventRecord(ctx->ev[14], ctx->stream));
     }
     unsigned long long n = 0;
-    HS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    HS_TRY(read_back(ctx, cnt, &n, sizeof n));
     if (fa_tc && nblocks_tc) ctx->stats.ms_filter_tc += ev_ms(ctx->ev[10], ctx->ev[11]);
     if (ml && ml->grid) ctx->stats.ms_filter_tc += ev_ms(ctx->ev[13], ctx->ev[14]);
     if (n <= fa.surv_cap) {
@@ -381,9 +445,9 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
     HS_TRY(ctx->d_mma_items.reserve(sizeof(MmaItemHost) * P.mma_items.size()));
     HS_TRY(ctx->d_mma_units.reserve(sizeof(MmaUnitHost) * P.mma_units.size()));
     HS_TRY(ctx->d_qlist_mma.reserve(sizeof(uint32_t) * P.qlist_mma.size()));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_mma_items.p, P.mma_items.data(), sizeof(MmaItemHost) * P.mma_items.size(), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_mma_units.p, P.mma_units.data(), sizeof(MmaUnitHost) * P.mma_units.size(), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist_mma.p, P.qlist_mma.data(), sizeof(uint32_t) * P.qlist_mma.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_TRY(upload(ctx, ctx->d_mma_items.p, P.mma_items.data(), sizeof(MmaItemHost) * P.mma_items.size()));
+    HS_TRY(upload(ctx, ctx->d_mma_units.p, P.mma_units.data(), sizeof(MmaUnitHost) * P.mma_units.size()));
+    HS_TRY(upload(ctx, ctx->d_qlist_mma.p, P.qlist_mma.data(), sizeof(uint32_t) * P.qlist_mma.size()));
     MmaGeometry g;
     HS_TRY(mma_geometry(ctx, &g));
     HS_TRY(ctx->d_qb16.reserve(sizeof(uint16_t) * (size_t)std::max<uint32_t>(tq_rows, 1) * g.kp + 16));
@@ -408,8 +472,8 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
   if (!P.items.empty()) {
     HS_TRY(ctx->d_work.reserve(sizeof(WorkItem) * P.items.size()));
     HS_TRY(ctx->d_qlist.reserve(sizeof(uint32_t) * P.qlist.size()));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_work.p, P.items.data(), sizeof(WorkItem) * P.items.size(), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist.p, P.qlist.data(), sizeof(uint32_t) * P.qlist.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_TRY(upload(ctx, ctx->d_work.p, P.items.data(), sizeof(WorkItem) * P.items.size()));
+    HS_TRY(upload(ctx, ctx->d_qlist.p, P.qlist.data(), sizeof(uint32_t) * P.qlist.size()));
     fa.items = ctx->d_work.as<WorkItem>();
     fa.nitems = (uint32_t)P.items.size();
     fa.qlist = ctx->d_qlist.as<uint32_t>();
@@ -417,8 +481,8 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
   if (!P.items_tc.empty()) {
     HS_TRY(ctx->d_work_tc.reserve(sizeof(WorkItem) * P.items_tc.size()));
     HS_TRY(ctx->d_qlist_tc.reserve(sizeof(uint32_t) * P.qlist_tc.size()));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_work_tc.p, P.items_tc.data(), sizeof(WorkItem) * P.items_tc.size(), cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaMemcpyAsync(ctx->d_qlist_tc.p, P.qlist_tc.data(), sizeof(uint32_t) * P.qlist_tc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_TRY(upload(ctx, ctx->d_work_tc.p, P.items_tc.data(), sizeof(WorkItem) * P.items_tc.size()));
+    HS_TRY(upload(ctx, ctx->d_qlist_tc.p, P.qlist_tc.data(), sizeof(uint32_t) * P.qlist_tc.size()));
     ft.items = ctx->d_work_tc.as<WorkItem>();
     ft.nitems = (uint32_t)P.items_tc.size();
     ft.qlist = ctx->d_qlist_tc.as<uint32_t>();
@@ -523,7 +587,11 @@ static int compact_id_bits(const hs_ctx *ctx, int *id_bits) {
 
 // Sort d_hits[0..n) by (query, first table, db id); result in ctx->d_hits_sorted, or, with
 // `cb`, as compact entries in ctx->d_cidt / d_cdist plus the block's offsets in ctx->d_coffsets.
-static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n, const CompactBlock *cb = nullptr) {
+struct SortedKeys {
+  const uint64_t *keys = nullptr;  // one-word keys in sorted order (valid until the next sort)
+  int tshift = 0;                  // the table field starts at this bit, the query field follows it
+};
+static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n, const CompactBlock *cb = nullptr, SortedKeys *sk = nullptr) {
   if (cb) {
     HS_TRY(ctx->d_cidt.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1)));
     HS_TRY(ctx->d_cdist.reserve(sizeof(double) * std::max<uint64_t>(n, 1)));
@@ -567,8 +635,8 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n, const CompactBlock
     HS_TRY(read_back(ctx, ovf, &h_ovf, sizeof h_ovf));
     one_word = h_ovf == 0;
   }
-  if (cb && !one_word) {
-    set_error("compact hits need the one-word hit key (query, table and id within 64 bits)");
+  if ((cb || sk) && !one_word) {
+    set_error("compact / gathered hits need the one-word hit key (query, table and id within 64 bits)");
     return HS_ERR_UNSUPPORTED;
   }
   if (one_word) {
@@ -590,6 +658,10 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n, const CompactBlock
   ctx->stats.ms_sort_upsweep = before.ms_sort_upsweep;
   ctx->stats.ms_sort_scan = before.ms_sort_scan;
   ctx->stats.ms_sort_downsweep = before.ms_sort_downsweep;
+  if (sk) {
+    sk->keys = sorted.w[0];
+    sk->tshift = tshift;
+  }
   if (cb) {
     hit_gather_compact_kernel<<<grid, 256, 0, ctx->stream>>>(d_hits, perm, n, ctx->id_base, cb->id_bits,
                                                             ctx->d_cidt.as<uint32_t>(), ctx->d_cdist.as<double>());
@@ -680,7 +752,7 @@ static int stage_queries(hs_ctx *ctx, const QueryInput &in, uint32_t Q) {
   if (in.d_points) {
     HS_CUDA(cudaMemcpyAsync(ctx->d_q64.p, in.d_points, sizeof(double) * Q * dim, cudaMemcpyDeviceToDevice, ctx->stream));
   } else if (in.h_points) {
-    HS_CUDA(cudaMemcpyAsync(ctx->d_q64.p, in.h_points, sizeof(double) * Q * dim, cudaMemcpyHostToDevice, ctx->stream));
+    HS_TRY(upload_user(ctx, ctx->d_q64.p, in.h_points, sizeof(double) * Q * dim));
   } else {
     // residue-code queries: embed with the ctx table (M1) on the host; Q is small
     std::vector<double> pts((size_t)Q * dim);
@@ -693,10 +765,9 @@ static int stage_queries(hs_ctx *ctx, const QueryInput &in, uint32_t Q) {
         }
         memcpy(&pts[(size_t)q * dim + p * HS_CDIM], ctx->table64 + c * HS_CDIM, sizeof(double) * HS_CDIM);
       }
-    HS_CUDA(cudaMemcpyAsync(ctx->d_q64.p, pts.data(), sizeof(double) * Q * dim, cudaMemcpyHostToDevice, ctx->stream));
+    HS_TRY(upload(ctx, ctx->d_q64.p, pts.data(), sizeof(double) * Q * dim));
     HS_TRY(ctx->d_qcodes.reserve((size_t)Q * len + 16));  // slack: word-wise reads (load_bytes)
-    HS_CUDA(cudaMemcpyAsync(ctx->d_qcodes.p, in.h_codes, (size_t)Q * len, cudaMemcpyHostToDevice, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    HS_TRY(upload(ctx, ctx->d_qcodes.p, in.h_codes, (size_t)Q * len));
     ctx->have_qcodes = true;
   }
   if (ctx->nranks > 1) {
@@ -746,25 +817,27 @@ void fill_exact_common(hs_ctx *ctx, ExactArgs &ea, uint32_t Q) {
   ea.qlist_mma = ctx->d_qlist_mma.as<uint32_t>();
 }
 
-// Finish a search / brute-force call: optional ordering, multi-GPU gather, copy out.
+// Finish a search / brute-force call: optional ordering, copy out, and -- on a context that
+// joined a communicator -- the start of the merge of all ranks' lists into rank 0's memory
+// (comm.cu; completed by hs_comm_result).  The caller's buffer always receives this rank's hits.
 static int deliver_hits(hs_ctx *ctx, uint64_t nh, uint64_t dev_cap, hs_hit *hits_host, void *hits_dev,
-                        uint64_t cap, uint64_t *nhits, cudaEvent_t ev_sort0, cudaEvent_t ev_sort1) {
+                        uint64_t cap, uint64_t *nhits, cudaEvent_t ev_sort0, cudaEvent_t ev_sort1, uint32_t Q) {
   hs_hit *d_src = ctx->d_hits.as<hs_hit>();
-  uint64_t nvalid = std::min<uint64_t>(nh, dev_cap);
+  const uint64_t nvalid = std::min<uint64_t>(nh, dev_cap);
+  const bool gather = ctx->nranks > 1 && cap > 0;   // cap == 0: count-only call, nothing to merge
+  // the gather that used these buffers two searches ago must have read them
+  if (gather && ctx->gather_seq >= 2) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather[ctx->gather_seq & 1u], 0));
   HS_CUDA(cudaEventRecord(ev_sort0, ctx->stream));
-  if ((ctx->prm.flags & HS_FLAG_SORT_HITS) && nh <= dev_cap) {
-    HS_TRY(sort_hits(ctx, d_src, nvalid));
+  SortedKeys sk;
+  if (((ctx->prm.flags & HS_FLAG_SORT_HITS) || gather) && nh <= dev_cap) {
+    HS_TRY(sort_hits(ctx, d_src, nvalid, nullptr, gather ? &sk : nullptr));
     if (nvalid) d_src = ctx->d_hits_sorted.as<hs_hit>();
   }
   HS_CUDA(cudaEventRecord(ev_sort1, ctx->stream));
-  if (ctx->nranks > 1) {
-    HS_TRY(comm_gather_hits(ctx, d_src, &nh, dev_cap));
-    d_src = ctx->d_hits_gathered.as<hs_hit>();
-    nvalid = ctx->rank == 0 ? nh : 0;
-    if (ctx->rank == 0 && (ctx->prm.flags & HS_FLAG_SORT_HITS) && nvalid) {
-      HS_TRY(sort_hits(ctx, d_src, nvalid));
-      d_src = ctx->d_hits_sorted.as<hs_hit>();
-    }
+  if (gather) {
+    const bool overflow = nh > dev_cap;
+    HS_TRY(comm_gather_start(ctx, d_src, overflow ? 0 : nvalid, sk.keys, sk.tshift, Q, overflow));
+    if (nvalid && !overflow) std::swap(ctx->d_hits_sorted, ctx->d_hits_sorted_alt);  // the gather reads d_src
   }
   *nhits = nh;
   ctx->stats.n_hits = nh;
@@ -807,10 +880,8 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
                          ctx->d_qrank.as<uint32_t>()));
   HS_TRY(build_tq(ctx, Q));
   std::vector<uint2> qrange((size_t)L * Q);
-  if (!qrange.empty())
-    HS_CUDA(cudaMemcpyAsync(qrange.data(), ctx->d_qrange.p, sizeof(uint2) * qrange.size(), cudaMemcpyDeviceToHost,
-                            ctx->stream));
   HS_CUDA(cudaEventRecord(ev[2], ctx->stream));
+  HS_TRY(read_back(ctx, ctx->d_qrange.p, qrange.data(), sizeof(uint2) * qrange.size()));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
 
   // work list of the queries [qa, qb): queries grouped by bucket, chunked
@@ -948,14 +1019,13 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
     if (nsurv) {
       const unsigned grid = (unsigned)std::min<uint64_t>((nsurv + 2047) / 2048, (uint64_t)ctx->num_sms * 8);
       survivor_block_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->d_surv.as<Survivor>(), nsurv, ctx->d_qlist_mma.as<uint32_t>(), search_blocks(Q), nblk, blk_cnt, nullptr);
-      HS_CUDA(cudaMemcpyAsync(h_cnt, blk_cnt, sizeof(unsigned long long) * nblk, cudaMemcpyDeviceToHost, ctx->stream));
-      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      HS_TRY(read_back(ctx, blk_cnt, h_cnt, sizeof(unsigned long long) * nblk));
       unsigned long long h_cur[kSearchBlocks], run = 0;
       for (uint32_t c = 0; c < nblk; ++c) {
         h_cur[c] = run;
         run += h_cnt[c];
       }
-      HS_CUDA(cudaMemcpyAsync(blk_cnt + nblk, h_cur, sizeof(unsigned long long) * nblk, cudaMemcpyHostToDevice, ctx->stream));
+      HS_TRY(upload(ctx, blk_cnt + nblk, h_cur, sizeof(unsigned long long) * nblk));
       survivor_block_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->d_surv.as<Survivor>(), nsurv, ctx->d_qlist_mma.as<uint32_t>(), search_blocks(Q), nblk, blk_cnt + nblk, ctx->d_surv_blk.as<Survivor>());
       HS_CUDA(cudaGetLastError());
       ctx->stats.kernel_launches += 2;
@@ -1037,11 +1107,10 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   ctx->stats.n_survivors = nsurv;
   HS_TRY(run_exact(ctx->d_surv.as<Survivor>(), nsurv, dev_cap));
   unsigned long long nh = 0;
-  HS_CUDA(cudaMemcpyAsync(&nh, hit_count, sizeof nh, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  HS_TRY(read_back(ctx, hit_count, &nh, sizeof nh));
 
-  int rc = deliver_hits(ctx, nh, dev_cap, hits_host, hits_dev, cap, nhits, ev[5], ev[6]);
+  int rc = deliver_hits(ctx, nh, dev_cap, hits_host, hits_dev, cap, nhits, ev[5], ev[6], Q);
   HS_CUDA(cudaEventRecord(ev[7], ctx->stream));
   HS_CUDA(cudaEventSynchronize(ev[7]));
   ctx->stats.ms_host = ev_ms(ev[2], ev[12]);
@@ -1142,9 +1211,8 @@ static int bruteforce_impl(hs_ctx *ctx, const QueryInput *in, uint32_t Q, hs_hit
   ctx->stats.n_candidates = ncand;
   ctx->stats.n_survivors = nsurv_total;
   unsigned long long nh = 0;
-  HS_CUDA(cudaMemcpyAsync(&nh, hit_count, sizeof nh, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  int rc = deliver_hits(ctx, nh, dev_cap, hits, hits_dev, cap, nhits, ev[5], ev[6]);
+  HS_TRY(read_back(ctx, hit_count, &nh, sizeof nh));
+  int rc = deliver_hits(ctx, nh, dev_cap, hits, hits_dev, cap, nhits, ev[5], ev[6], (uint32_t)total_q);
   HS_CUDA(cudaEventRecord(ev[7], ctx->stream));
   HS_CUDA(cudaEventSynchronize(ev[7]));
   ctx->stats.ms_filter = ms_filter;
@@ -1324,6 +1392,7 @@ void hs_destroy(hs_ctx_t *ctx) {
   for (cudaEvent_t e : ctx->ev_chunk) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_up) cudaFreeHost(ctx->h_up);
   ctx->d_hits_sorted_alt.release();
   DevBuf *cbufs[] = {&ctx->d_cidt, &ctx->d_cidt_alt, &ctx->d_cdist, &ctx->d_cdist_alt, &ctx->d_coffsets};
   for (DevBuf *b : cbufs) b->release();
@@ -1412,8 +1481,7 @@ static int load_and_hash_overlapped(hs_ctx *ctx, const uint8_t *codes, uint64_t 
   }
   HS_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   unsigned long long h[4];
-  HS_CUDA(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  HS_TRY(read_back(ctx, cnt, h, sizeof h));
   HS_TRY(validate_codes_end(ctx, "hs_load_fragments"));
   ctx->stats.guard_hits = h[0];
   ctx->stats.guard_corrected = h[1];
@@ -1491,10 +1559,9 @@ int hs_hash(hs_ctx_t *ctx, int32_t *buckets_out) {
   HS_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   if (ctx->prm.flags & HS_FLAG_HASH_AUDIT) HS_TRY(launch_hash_exact(ctx, false, true));
   unsigned long long h[4];
-  HS_CUDA(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
   if (buckets_out)
     HS_CUDA(cudaMemcpyAsync(buckets_out, ctx->d_buckets.p, sizeof(int32_t) * N * L * K, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  HS_TRY(read_back(ctx, cnt, h, sizeof h));
   ctx->stats.guard_hits = h[0];
   ctx->stats.guard_corrected = h[1];
   ctx->stats.residual_flips = h[3];

@@ -170,13 +170,27 @@ struct hs_ctx {
   void *h_pinned = nullptr;   // mapped pinned staging of read_back()
   void *d_pinned = nullptr;
   size_t h_pinned_cap = 0;
+  void *h_up = nullptr;       // mapped pinned arena of upload(): host -> device control data
+  void *d_up = nullptr;
+  size_t up_used = 0;
 
   // cluster
   hs::DevBuf d_parent;
 
-  // comm
-  void *nccl_comm = nullptr;
+  // comm (comm.cu): NCCL for the small collectives, peer stores into rank 0's receive buffers
+  // (mapped into every process with CUDA IPC) for the hit lists
+  void *nccl_comm = nullptr;    // ctx stream: query broadcast, set-up exchanges
+  void *nccl_comm2 = nullptr;   // gather stream: segment counts, completion barrier
   int rank = 0, nranks = 1;
+  cudaStream_t gather_stream = nullptr;
+  cudaEvent_t ev_gather[2] = {nullptr, nullptr}, ev_gather_in = nullptr;
+  void *recv_local[2] = {nullptr, nullptr};   // rank 0: the receive buffers (hs_hit[recv_cap]), double buffered
+  void *recv_mapped[2] = {nullptr, nullptr};  // every rank: rank 0's buffers as seen from this process
+  uint64_t recv_cap = 0;
+  uint32_t gather_seq = 0;      // gathers started so far (slot = seq & 1)
+  bool gather_pending = false;
+  unsigned long long h_gather_flag[2] = {0, 0};
+  hs::DevBuf d_segoff[2], d_segcnt, d_segcnt_all, d_segdst, d_gather_info;
 
   // debugging switches, read from the environment once in hs_create
   bool no_pipeline = false;      // HS_NO_PIPELINE: host-buffer searches in one pass (no query blocks)

@@ -549,8 +549,7 @@ static int group_inst(hs_ctx *ctx, uint32_t table, const KeyPtrs &keys) {
   ctx->stats.kernel_launches++;
   HS_TRY(exclusive_scan_u32(ctx, flags, scanned, n, d_total));
   uint32_t nb = 0;
-  HS_CUDA(cudaMemcpyAsync(&nb, d_total, sizeof nb, cudaMemcpyDeviceToHost, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  HS_TRY(read_back(ctx, d_total, &nb, sizeof nb));
   T.nb = nb;
   T.nslots = nb;
   HS_TRY(T.ukeys.reserve(sizeof(uint64_t) * NW * (uint64_t)std::max<uint32_t>(nb, 1)));
@@ -717,16 +716,14 @@ int build_code_stores_blocked(hs_ctx *ctx, bool *done) {
     // millions of boundaries, and small buckets gain nothing from the blocking
     if (T.nslots > (1u << 18) || (T.nslots + n / kGatherPart) * (uint64_t)(nchunks + 1) > (64ull << 20)) return HS_OK;
     bs.resize(T.nslots + 1);
-    HS_CUDA(cudaMemcpyAsync(bs.data(), T.bstart.p, sizeof(uint32_t) * (T.nslots + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    HS_TRY(read_back(ctx, T.bstart.p, bs.data(), sizeof(uint32_t) * (T.nslots + 1)));
     voff[l] = vstart.size();
     for (uint64_t b = 0; b < T.nslots; ++b)
       for (uint32_t p = bs[b]; p < bs[b + 1]; p += kGatherPart) vstart.push_back(p);
     vstart.push_back((uint32_t)n);
   }
   HS_TRY(ctx->sort.block_sums.reserve(sizeof(uint32_t) * vstart.size() + 16));
-  HS_CUDA(cudaMemcpyAsync(ctx->sort.block_sums.p, vstart.data(), sizeof(uint32_t) * vstart.size(), cudaMemcpyHostToDevice,
-                          ctx->stream));
+  HS_TRY(upload(ctx, ctx->sort.block_sums.p, vstart.data(), sizeof(uint32_t) * vstart.size()));
   for (uint32_t l = 0; l < L; ++l) {
     TableIndex &T = ctx->tables[l];
     if (T.codes_sorted.cap < bytes) {
@@ -748,8 +745,7 @@ int build_code_stores_blocked(hs_ctx *ctx, bool *done) {
   HS_TRY(ensure_records(ctx));
   HS_TRY(ctx->sort.flags.reserve(sizeof(uint32_t) * run_total + 16));
   HS_TRY(ctx->d_misc.reserve(sizeof(GatherTab) * L));
-  HS_CUDA(cudaMemcpyAsync(ctx->d_misc.p, tabs.data(), sizeof(GatherTab) * L, cudaMemcpyHostToDevice, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));  // tabs is a host temporary
+  HS_TRY(upload(ctx, ctx->d_misc.p, tabs.data(), sizeof(GatherTab) * L));
   const GatherTab *d_tabs = ctx->d_misc.as<GatherTab>();
   uint32_t *runs = ctx->sort.flags.as<uint32_t>();
   gather_runs_kernel<<<groups, kGatherSlots, 0, ctx->stream>>>(d_tabs, L, nchunks, chunk, runs);
@@ -989,12 +985,10 @@ static int build_table_index_ranks(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_s
   rank_bounds_kernel<<<(unsigned)(((n + 7) / 8 + 255) / 256), 256, 0, ctx->stream>>>(ksorted, n, nr, T.bstart.as<uint32_t>(), d_nb);
   ctx->stats.kernel_launches++;
   HS_TRY(T.ukeys.reserve(sizeof(uint64_t) * KW * (uint64_t)nr));
-  HS_CUDA(cudaMemcpyAsync(T.ukeys.p, ctx->h_rkeys[table].data(), sizeof(uint64_t) * KW * nr, cudaMemcpyHostToDevice,
-                          ctx->stream));
+  HS_TRY(upload(ctx, T.ukeys.p, ctx->h_rkeys[table].data(), sizeof(uint64_t) * KW * nr));
   unsigned int h_nb = 0;
-  HS_CUDA(cudaMemcpyAsync(&h_nb, d_nb, sizeof h_nb, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaEventRecord(ev_group_end, ctx->stream));
-  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  HS_TRY(read_back(ctx, d_nb, &h_nb, sizeof h_nb));
   T.nb = h_nb;
   T.nslots = nr;
   for (int pi = 0; pi < npass; ++pi) {

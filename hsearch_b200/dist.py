@@ -87,7 +87,12 @@ class HitGather:
             # NVSwitch box this runs closer to line rate than 7 point-to-point receives into one GPU
             blk = max(self.counts) * HIT_BYTES
             need = blk * self.world
-            if allgather_pad.numel() >= need and hits_u8.numel() >= blk:
+            # the choice between the two transports must be the same on every rank (a rank in the
+            # all-gather and another in send/recv would hang): decide on the smallest buffers of all
+            sizes = torch.tensor([allgather_pad.numel(), hits_u8.numel()], dtype=torch.int64, device=dev)
+            dist.all_reduce(sizes, op=dist.ReduceOp.MIN)
+            min_pad, min_hits = sizes.tolist()
+            if min_pad >= need and min_hits >= blk:
                 self.pad = (allgather_pad[:need], blk)
                 self.work = [dist.all_gather_into_tensor(self.pad[0], hits_u8[:blk], async_op=True)]
                 self.dst, self.rank = dst, rank
@@ -121,6 +126,26 @@ class HitGather:
             # the lists sit at stride blk; rank dst's consumers read them through views
             self.out = [buf[r * blk: r * blk + self.counts[r] * HIT_BYTES] for r in range(self.world)]
         return self.out, self.counts
+
+
+def segment_counts(hits, n_query, n_tables):
+    """Hits in reference order -> count per (query, first table) segment, segment = query * T + table
+    with T the table field's width used by the library (comm.cu: 1 << bits(L + 1))."""
+    tb = max(1, int(n_tables).bit_length())
+    seg = (hits["query"].astype(np.int64) << tb) | hits["table_first"].astype(np.int64)
+    return np.bincount(seg, minlength=int(n_query) << tb).astype(np.int64)
+
+
+def merged_positions(counts_all, rank):
+    """The arithmetic of the library's merge on rank 0 (comm.cu, seg_dest_kernel): counts_all[r][s] =
+    hits of rank r in segment s.  Ranks own ascending id blocks, so in the merged list (query, first
+    table, ascending db id) every segment holds rank 0's hits, then rank 1's, ...  Returns the position
+    of the first hit of each of `rank`'s segments and the total number of hits."""
+    counts_all = np.asarray(counts_all, dtype=np.int64)
+    tot = counts_all.sum(axis=0)
+    start = np.concatenate(([0], np.cumsum(tot)[:-1]))
+    before = counts_all[:rank].sum(axis=0)
+    return start + before, int(tot.sum())
 
 
 def sort_hits_reference_order(hits):

@@ -339,12 +339,30 @@ int hs_kmer3_klsh(hs_ctx_t *ctx, const char *residues, const uint64_t *start, ui
 int hs_orf6(hs_ctx_t *ctx, const char *dna, const uint64_t *start, uint32_t nseq, char *aa_out, uint64_t aa_cap,
             int32_t *aa_len);
 
-/* ---- multi-GPU -------------------------------------------------- */
-/* Join an NCCL communicator (nccl_unique_id: the 128-byte ncclUniqueId made by
- * rank 0).  After this, hs_search_* on every rank takes the queries of rank 0
- * (ncclBroadcast) and gathers all ranks' hits to rank 0. */
+/* ---- multi-GPU --------------------------------------------------
+ * One process and one context per GPU; rank r loads the id block [id_base_r, id_base_r + N_r)
+ * of the database with id_base ascending in rank order.  Nothing of this exists in the
+ * reference (a single-threaded process); what it must reproduce is the output order of
+ * motif_both_points.cpp:224-245 over the whole database. */
+/* Join an NCCL communicator (nccl_unique_id: the 128-byte ncclUniqueId made by rank 0 with
+ * hs_comm_unique_id and handed to the other processes by the launcher).  After this,
+ * hs_search_* / hs_bruteforce_* on every rank take the queries of rank 0 (ncclBroadcast). */
 int hs_comm_init(hs_ctx_t *ctx, const void *nccl_unique_id, int rank, int nranks);
 int hs_comm_unique_id(void *out128);
+/* Collective.  Rank 0 allocates two receive buffers of cap_hits hs_hit records (the largest
+ * request of all ranks) and every rank maps them into its address space (CUDA IPC over NVLink).
+ * From then on every search with a non-empty hit buffer, besides returning the rank's own hits
+ * as usual, merges the lists of all ranks into rank 0's current receive buffer in the reference's
+ * order (query, first table, ascending db id): the ranks exchange their hit counts per (query,
+ * table) and each writes its hits straight to their final positions in rank 0's memory.  The
+ * merge runs on its own stream and overlaps whatever the ranks do next (the next batch's hash and
+ * index build); a search reuses the buffer of the search before the previous one. */
+int hs_comm_reserve(hs_ctx_t *ctx, uint64_t cap_hits);
+/* Completes the merge started by the rank's latest search.  *nhits_total = hits of all ranks;
+ * on rank 0 *hits_dev points at the merged list in device memory (valid until the search after
+ * the next); NULL on the other ranks.  HS_ERR_CAPACITY when the receive buffer or some rank's own
+ * hit buffer was too small (then *nhits_total is the size hs_comm_reserve needs). */
+int hs_comm_result(hs_ctx_t *ctx, const void **hits_dev, uint64_t *nhits_total);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,58 @@ def test_gather_hits_world2_matches_single_process(tmp_path):
     assert int(open(tmp_path / "ok").read()) > 0
 
 
+def _merge_worker(rank, world, port, tmpdir):
+    """The library's merge (every rank writes its hits to their final positions of rank 0's list) with
+    the transport replaced by gloo: counts all-gathered, positions from dist.merged_positions."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.pyoracle import Oracle
+        o = Oracle()
+        length, K, L, W, R = 10, 4, 4, 50.0, 30.0
+        n_total, nq = 9001, 40
+        codes = random_codes(n_total, length, seed=3)
+        qc = planted_queries(codes, nq, seed=4)
+        tab = o.coordinates(True)
+        a, b = o.lsh_tables(12345, 8 * length, K, L, W)
+        lo, hi = hdist.shard_range(n_total, rank, world)
+        local, _, _ = o.search(o.embed(codes[lo:hi], tab), o.embed(qc, tab), a, b, W, R)
+        local = local.copy()
+        local["db_id"] += lo
+        cnt = torch.from_numpy(hdist.segment_counts(local, nq, L))
+        allc = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        pos, total = hdist.merged_positions(np.stack([c.numpy() for c in allc]), rank)
+        # destination of every local hit: its segment's position + its index inside the segment
+        tb = max(1, L.bit_length())
+        seg = (local["query"].astype(np.int64) << tb) | local["table_first"].astype(np.int64)
+        first = np.concatenate(([0], np.cumsum(cnt.numpy())[:-1]))
+        dest = pos[seg] + (np.arange(len(local)) - first[seg])
+        lists = [None] * world
+        dist.all_gather_object(lists, (dest, local))
+        if rank == 0:
+            out = np.zeros(total, dtype=local.dtype)
+            seen = np.zeros(total, dtype=bool)
+            for d, hits in lists:
+                assert not seen[d].any()
+                out[d] = hits
+                seen[d] = True
+            assert seen.all()
+            want, _, _ = o.search(o.embed(codes, tab), o.embed(qc, tab), a, b, W, R)
+            assert len(want) > 0 and hits_as_tuples(out) == hits_as_tuples(want)
+            open(os.path.join(tmpdir, "ok"), "w").write(str(len(want)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_merge_positions_world_n_matches_single_process(tmp_path, world):
+    mp.spawn(_merge_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert int(open(tmp_path / "ok").read()) > 0
+
+
 # ---------------------------------------------------------------- sharded cluster (configs[3])
 def _cluster_worker(rank, world, port, tmpdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
