@@ -66,7 +66,6 @@ int read_back(hs_ctx *ctx, const void *d_src, void *h_dst, size_t bytes) {
   if (ctx->h_pinned_cap < need) {
     HS_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  if (ctx->h_up) cudaFreeHost(ctx->h_up);
     ctx->h_pinned = nullptr;
     ctx->h_pinned_cap = 0;
     const size_t want = std::max<size_t>(need + need / 4, 4096);
