@@ -148,17 +148,38 @@ seg_dest_kernel(const uint32_t *__restrict__ cnt_all /* [G][S] */, uint32_t S, i
 }
 
 // Every hit of the local sorted list goes to its final position of the merged list (rank 0's
-// memory, mapped here): consecutive threads write consecutive 24-byte records inside a segment,
-// so the peer stores coalesce into full lines on the NVLink.
+// memory, mapped here).  Consecutive threads take consecutive hits, which inside a segment land
+// on consecutive 24-byte records, so the peer stores coalesce into full lines on the NVLink;
+// four hits per thread are loaded before the first is stored (the kernel runs with few thread
+// blocks -- it is bound by the link, not by the SMs it takes from the next batch's kernels).
+constexpr int kScatterUnroll = 4;
 __global__ void __launch_bounds__(256)
 scatter_merged_kernel(const hs_hit *__restrict__ hits, uint64_t n, int tbits, const uint64_t *__restrict__ off,
                       const uint64_t *__restrict__ dst, const unsigned long long *__restrict__ info,
                       hs_hit *__restrict__ out) {
   if (info[1]) return;  // receive buffer too small: reported by hs_comm_result
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const hs_hit h = hits[i];
-    const uint64_t s = ((uint64_t)h.query << tbits) | (uint64_t)h.table_first;
-    out[dst[s] + (i - off[s])] = h;
+  const uint64_t tile = (uint64_t)blockDim.x * kScatterUnroll;
+  for (uint64_t t0 = (uint64_t)blockIdx.x * tile; t0 < n; t0 += (uint64_t)gridDim.x * tile) {
+    hs_hit h[kScatterUnroll];
+    uint64_t pos[kScatterUnroll];
+#pragma unroll
+    for (int j = 0; j < kScatterUnroll; ++j) {
+      const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
+      if (i < n) h[j] = hits[i];
+    }
+#pragma unroll
+    for (int j = 0; j < kScatterUnroll; ++j) {
+      const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
+      if (i < n) {
+        const uint64_t s = ((uint64_t)h[j].query << tbits) | (uint64_t)h[j].table_first;
+        pos[j] = __ldg(dst + s) + (i - __ldg(off + s));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kScatterUnroll; ++j) {
+      const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
+      if (i < n) out[pos[j]] = h[j];
+    }
   }
 }
 
@@ -211,7 +232,9 @@ int comm_gather_start(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const uint6
   if (n) {
     // few, small thread blocks: the transfer is bound by the link, and the SMs they sit on are
     // taken from the next batch's hash / index build
-    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 16);
+    // the senders share rank 0's ingress: the more of them, the fewer blocks each needs to fill its share
+    const unsigned want = (unsigned)std::max(4, 32 / std::max(1, G - 1));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 1023) / 1024, want);
     scatter_merged_kernel<<<grid, 256, 0, gs>>>(d_hits, n, tbits, off, ctx->d_segdst.as<uint64_t>(), info,
                                                 reinterpret_cast<hs_hit *>(ctx->recv_mapped[slot]));
   }

@@ -46,7 +46,17 @@
 namespace hs {
 
 constexpr int kMmaEpiWarps = 16;     // 4 per TMEM lane quadrant
+constexpr int kMmaEpiPerStage = kMmaEpiWarps;  // all epilogue warps drain every accumulator stage
 constexpr int kMmaProdWarps = 4;
+// The producer warps can work in kMmaProdGroups independent groups, group i building the tiles
+// i, i + groups, ... with 128 / groups threads (several rows per thread), so that several tiles
+// are in flight on the producer side.  Measured slower (39.2 against 36.2 ms at bench C2) and not
+// validated for more than one group: one group is the supported configuration.
+#ifndef HS_MMA_PROD_GROUPS
+#define HS_MMA_PROD_GROUPS 1
+#endif
+constexpr int kMmaProdGroups = HS_MMA_PROD_GROUPS;
+constexpr int kMmaProdGroupThreads = kMmaProdWarps * 32 / kMmaProdGroups;
 constexpr int kMmaThreads = (kMmaEpiWarps + kMmaProdWarps + 2) * 32;  // 704
 constexpr int kMmaProdThread0 = kMmaEpiWarps * 32;                    // 512
 constexpr int kMmaIssueWarp = kMmaEpiWarps + kMmaProdWarps;           // 20
@@ -65,9 +75,18 @@ constexpr int kMmaN = HS_MMA_N;      // accumulator columns per stage (<= 256, t
 constexpr int kMmaAccStages = 512 / kMmaN;  // the stages fill the 512 TMEM columns
 constexpr uint32_t kMmaTmemCols = 512;
 constexpr int kMmaMaxStages = 4;     // A stages
+#ifdef HS_MMA_PACK
+constexpr int kMmaRowRing = 16;      // >= A stages + tiles in the accumulator stages (kMmaAccStages * 4) + 1
+#else
 constexpr int kMmaRowRing = 8;       // >= A stages + accumulator stages
-constexpr int kMmaStageCap = 128;    // survivors staged per epilogue warp between flushes
-constexpr int kMmaFlushAt = 64;      // staged survivors that trigger a flush (one global atomic each)
+#endif
+#ifdef HS_MMA_PACK
+constexpr int kMmaRing = 6;          // (the larger row ring takes the shared memory of two slots)
+constexpr int kMmaRingFlush = 4;
+#else
+constexpr int kMmaRing = 8;          // survivors staged per epilogue LANE between flushes (lane-private slots, no atomics)
+constexpr int kMmaRingFlush = 6;     // a lane holding this many makes its warp flush at the next group boundary
+#endif
 constexpr int kMmaAGroupBytes = 2048;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,9 +118,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #endif
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef HS_MBAR_SPIN
+  while (!mbar_test_wait(bar, parity)) {
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
+}
+// single-thread roles (MMA issuer, loader): poll without suspending
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+#if defined(HS_MBAR_SPIN1) || defined(HS_MBAR_SPIN)
+  while (!mbar_test_wait(bar, parity)) {
+  }
+#else
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -120,9 +167,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+#ifdef HS_DIAG_NOPROXYFENCE
+#define HS_PROXY_FENCE()
+#else
+#define HS_PROXY_FENCE() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
+#endif
+#ifdef HS_DIAG_NOFENCE
+__device__ __forceinline__ void tc_before() {}
+__device__ __forceinline__ void tc_after() {}
+#else
 __device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+__device__ __forceinline__ void fence_async_shared() { HS_PROXY_FENCE(); }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100: version 1).
 __device__ __forceinline__ uint64_t mma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -145,6 +202,10 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
+#ifdef HS_DIAG_ARRIVE
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  return;
+#endif
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
@@ -175,16 +236,48 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
-// Append a warp's staged survivors to the global list: one atomic per flush.  Returns 0.
-__device__ __noinline__ uint32_t mma_flush(const Survivor *stage, uint32_t n, Survivor *surv, unsigned long long cap,
-                                           unsigned long long *count, int lane) {
+// Append the survivors the lanes of a warp hold in their private slots to the global list: a warp
+// prefix sum of the per-lane counts, one global atomic, every lane writes its own run.  Returns 0
+// (the lane's new count).
+__device__ __noinline__ uint32_t mma_flush(const uint2 (*ring)[32], uint32_t lc, uint32_t table, Survivor *surv,
+                                           unsigned long long cap, unsigned long long *count, int lane) {
+  uint32_t inc = lc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  if (total == 0u) return 0u;
   unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(count, (unsigned long long)n);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  for (uint32_t i = lane; i < n; i += 32)
-    if (base + i < cap) surv[base + i] = stage[i];
+  if (lane == 0) base = atomicAdd(count, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 0) + (inc - lc);
+  for (uint32_t j = 0; j < lc; ++j) {
+    const uint2 e = ring[j][lane];
+    if (base + j < cap) {
+      Survivor sv;
+      sv.query = e.x;  // index into the query list; the exact stage resolves it
+      sv.table = table;
+      sv.pos = e.y;    // fragment id
+      sv.pad = 3;
+      surv[base + j] = sv;
+    }
+  }
   __syncwarp();
-  return 0;
+  return 0u;
+}
+
+__device__ __noinline__ void mma_emit_global(Survivor *surv, unsigned long long cap, unsigned long long *count, uint32_t qidx,
+                                             uint32_t table, uint32_t rid) {
+  const unsigned long long gi = atomicAdd(count, 1ull);
+  if (gi < cap) {
+    Survivor sv;
+    sv.query = qidx;
+    sv.table = table;
+    sv.pos = rid;
+    sv.pad = 3;  // query = index into the query list, pos = fragment id
+    surv[gi] = sv;
+  }
 }
 
 #ifdef HS_MMA_PROF
@@ -247,9 +340,24 @@ struct MmaShared {
   float nx32[HS_AA];
   float rowthr[kMmaRowRing][kMmaM];
   uint32_t rowid[kMmaRowRing][kMmaM];   // fragment id of every row (the exact stage then skips the id gather)
-  Survivor stage[kMmaEpiWarps][kMmaStageCap];
-  uint32_t wcount[kMmaEpiWarps];  // survivors staged per epilogue warp
+  // survivors staged per lane: (index into the query list, fragment id); slot-major so that a
+  // warp-wide access touches consecutive words
+  uint2 ring[kMmaEpiWarps][kMmaRing][32];
 };
+
+// Tile packing (-DHS_MMA_PACK; off: measured 36.1 ms against 35.0 at bench C2, profiles/r02_filter_
+// experiments.md).  An item whose queries fit one group (<= kMmaN) narrower than half a stage shares
+// each accumulator stage between 2 or 4 consecutive tiles of the unit: tile j of the batch gets
+// the column block [j * kMmaN / P, ...) (same B operand, its own A stage), so the hand-off between
+// the MMA issuer and the epilogue is paid once per P tiles.  Issuer and epilogue derive P from the
+// item the same way.
+__device__ __forceinline__ uint32_t mma_pack(uint32_t nq) {
+#ifdef HS_MMA_PACK
+  return nq <= (uint32_t)kMmaN / 4u ? 4u : nq <= (uint32_t)kMmaN / 2u ? 2u : 1u;
+#else
+  return 1u;
+#endif
+}
 
 // Every role walks the same sequence of units, published by the scheduler lane
 // through a small ring: returns the next unit index, or >= nunits at the end.
@@ -265,6 +373,7 @@ __device__ __forceinline__ uint32_t mma_next_unit(MmaShared &sh, uint32_t k, int
 // Survivors carry the index of their query in the query list (pad = 1); the exact stage
 // resolves it and, for all-pairs runs, keeps only pairs with query id < member position.
 // LENB: compile-time bound of the fragment length (unroll bound of the A-tile producers).
+// (22 warps are allocated like 24: 80 registers per thread is the limit, 88 does not launch)
 template <int LENB>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 filter_mma_kernel(MmaArgs a) {
@@ -283,12 +392,12 @@ filter_mma_kernel(MmaArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < kMmaMaxStages; ++s) {
-      mbar_init(smem_addr(&sh.a_full[s]), kMmaProdWarps);
+      mbar_init(smem_addr(&sh.a_full[s]), kMmaProdWarps / kMmaProdGroups);
       mbar_init(smem_addr(&sh.a_empty[s]), 1);
     }
     for (int s = 0; s < kMmaAccStages; ++s) {
       mbar_init(smem_addr(&sh.t_full[s]), 1);
-      mbar_init(smem_addr(&sh.t_empty[s]), kMmaEpiWarps);
+      mbar_init(smem_addr(&sh.t_empty[s]), kMmaEpiPerStage);
     }
     mbar_init(smem_addr(&sh.b_full), kMmaProdWarps);
     for (int s = 0; s < kMmaUnitRing; ++s) {
@@ -297,13 +406,12 @@ filter_mma_kernel(MmaArgs a) {
     }
     for (int s = 0; s < kMmaMaxCodeRing; ++s) {
       mbar_init(smem_addr(&sh.c_full[s]), 1);
-      mbar_init(smem_addr(&sh.c_empty[s]), kMmaProdWarps);
+      mbar_init(smem_addr(&sh.c_empty[s]), kMmaProdWarps / kMmaProdGroups);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < HS_AA * 8) sh.tab16[tid >> 3][tid & 7] = a.tab16[tid >> 3];
   if (tid < HS_AA) sh.nx32[tid] = a.nx32[tid];
-  if (tid < kMmaEpiWarps) sh.wcount[tid] = 0u;
   if (warp == kMmaIssueWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&sh.tmem_base)),
                  "r"(kMmaTmemCols)
@@ -352,6 +460,9 @@ filter_mma_kernel(MmaArgs a) {
         const uint8_t *store = a.stores[it.table];
         const uint32_t base = un.m_begin & ~15u;
         const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
+#if defined(HS_DIAG_NOLOAD)
+        if (ntiles) continue;
+#endif
         for (uint32_t t = 0; t < ntiles; ++t, ++ct) {
           const uint32_t d = ct % D;
           mbar_wait(smem_addr(&sh.c_empty[d]), ((ct / D) & 1u) ^ 1u);
@@ -366,9 +477,16 @@ filter_mma_kernel(MmaArgs a) {
     __syncwarp();
   } else if (warp >= kMmaEpiWarps && warp < kMmaIssueWarp) {
     // ============================ producers ============================================
-    const int r = tid - kMmaProdThread0;  // member row of the tile
-    const uint32_t row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
-    uint32_t pt = 0;                       // tiles produced so far (all units)
+    const int r = tid - kMmaProdThread0;  // 0 .. 127 (B rows are loaded by all producer threads together)
+    constexpr int NR = kMmaProdGroups;     // member rows of a tile per thread
+    const int grp = r / kMmaProdGroupThreads, lr = r % kMmaProdGroupThreads;
+    uint32_t row_off[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int ri = lr + i * kMmaProdGroupThreads;
+      row_off[i] = (uint32_t)(ri >> 3) * 128u + (uint32_t)(ri & 7) * 16u;
+    }
+    uint32_t pt = 0;                       // tiles of all units so far (this group builds pt % groups == grp)
     uint32_t prev_item = 0xffffffffu;
     PROF_DECL(p_wait_c);
     PROF_DECL(p_wait_a);
@@ -416,22 +534,31 @@ filter_mma_kernel(MmaArgs a) {
       const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
       const uint32_t *ids = a.sorted_ids[it.table];
       for (uint32_t t = 0; t < ntiles; ++t, ++pt) {
+        if ((int)(pt % (uint32_t)kMmaProdGroups) != grp) continue;
         const uint32_t s = pt % S, d = pt % D;
-        const uint32_t mypos = base + t * kMmaM + (uint32_t)r;
-        const bool valid = mypos >= un.m_begin && mypos < un.m_end;
-        // the row's fragment id (coalesced; issued before the waits below, used after the A build)
-        const uint32_t myid = (valid && ids) ? __ldg(ids + mypos) : mypos;
-        // my row's residue codes from the ring the loader fills
+        uint32_t myid[NR];
+        bool valid[NR];
+        // the rows' fragment ids (coalesced; issued before the waits below, used after the A build)
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const uint32_t mypos = base + t * kMmaM + (uint32_t)(lr + i * kMmaProdGroupThreads);
+          valid[i] = mypos >= un.m_begin && mypos < un.m_end;
+          myid[i] = (valid[i] && ids) ? __ldg(ids + mypos) : mypos;
+        }
+        // the rows' residue codes from the ring the loader fills
         {
           PROF_T0();
           mbar_wait(smem_addr(&sh.c_full[d]), (pt / D) & 1u);
           PROF_ADD(p_wait_c);
         }
-        const unsigned char *crow = sC + (size_t)d * len * 128 + r;
-        uint8_t code[LENB];
+        uint8_t code[NR][LENB];
 #pragma unroll
-        for (int p = 0; p < LENB; ++p)
-          if (p < len) code[p] = crow[p * 128];
+        for (int i = 0; i < NR; ++i) {
+          const unsigned char *crow = sC + (size_t)d * len * 128 + lr + i * kMmaProdGroupThreads;
+#pragma unroll
+          for (int p = 0; p < LENB; ++p)
+            if (p < len) code[i][p] = crow[p * 128];
+        }
         mbar_arrive_warp(smem_addr(&sh.c_empty[d]), lane);
         {
           PROF_T0();
@@ -441,43 +568,57 @@ filter_mma_kernel(MmaArgs a) {
 #ifdef HS_MMA_PROF
         const long long _pb0 = clock64();
 #endif
-        unsigned char *dst = sA + (size_t)s * a_stage_bytes + row_off;
-        float nx = 0.f;
+        unsigned char *dst = sA + (size_t)s * a_stage_bytes;
+        float nx[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) nx[i] = 0.f;
         // batches of 5 positions: their table rows are loaded before the first is stored, so that the
         // shared-memory loads overlap (one register quad reused for every position serialises
         // LDS -> STS -> LDS ...: measured 1.7 k cycles per tile)
 #pragma unroll
-        for (int p0 = 0; p0 < LENB; p0 += 5) {
-          uint4 rowv[5];
+        for (int i = 0; i < NR; ++i)
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const int p = p0 + j;
-            if (p < LENB && p < len) {
-#ifdef HS_MMA_PROF
-              if (a.debug & 4u) continue;  // experiment: no A build
+          for (int p0 = 0; p0 < LENB; p0 += 5) {
+            uint4 rowv[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const int p = p0 + j;
+              if (p < LENB && p < len) {
+#if defined(HS_DIAG_NOPROD)
+                continue;
 #endif
-              const int c = min((int)code[p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
-              rowv[j] = sh.tab16[c][lane & 7];
-              nx += sh.nx32[c];
+#ifdef HS_MMA_PROF
+                if (a.debug & 4u) continue;  // experiment: no A build
+#endif
+                const int c = min((int)code[i][p] / kCodeScale, HS_AA - 1);  // (rows outside the unit hold foreign bytes)
+                rowv[j] = sh.tab16[c][lane & 7];
+                nx[i] += sh.nx32[c];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const int p = p0 + j;
+              if (p < LENB && p < len) {
+#if defined(HS_DIAG_NOPROD)
+                continue;
+#endif
+#ifdef HS_MMA_PROF
+                if (a.debug & 4u) continue;
+#endif
+                *reinterpret_cast<uint4 *>(dst + row_off[i] + (size_t)p * kMmaAGroupBytes) = rowv[j];
+              }
             }
           }
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const int p = p0 + j;
-            if (p < LENB && p < len) {
-#ifdef HS_MMA_PROF
-              if (a.debug & 4u) continue;
-#endif
-              *reinterpret_cast<uint4 *>(dst + (size_t)p * kMmaAGroupBytes) = rowv[j];
-            }
-          }
+        for (int i = 0; i < NR; ++i) {
+          // rowthr = ((1 - beta) nx - thr) / 2, rounded down; +inf rows never pass
+          // (nx is a sum of <= 32 FP32 terms: 4e-6 covers its rounding)
+          float rt = 0.5f * (nx[i] * (1.0f - 4e-6f) * (1.0f - a.beta) - a.thr);
+          rt -= (nx[i] + a.thr) * 2.4e-7f + 1e-6f;
+          const int ri = lr + i * kMmaProdGroupThreads;
+          sh.rowthr[pt % kMmaRowRing][ri] = valid[i] ? rt : __int_as_float(0x7f800000);
+          sh.rowid[pt % kMmaRowRing][ri] = myid[i];
         }
-        // rowthr = ((1 - beta) nx - thr) / 2, rounded down; +inf rows never pass
-        // (nx is a sum of <= 32 FP32 terms: 4e-6 covers its rounding)
-        float rt = 0.5f * (nx * (1.0f - 4e-6f) * (1.0f - a.beta) - a.thr);
-        rt -= (nx + a.thr) * 2.4e-7f + 1e-6f;
-        sh.rowthr[pt % kMmaRowRing][r] = valid ? rt : __int_as_float(0x7f800000);
-        sh.rowid[pt % kMmaRowRing][r] = myid;
 #ifdef HS_MMA_PROF
         const long long _pb1 = clock64();
         p_build += (unsigned long long)(_pb1 - _pb0);
@@ -530,7 +671,7 @@ filter_mma_kernel(MmaArgs a) {
         if (un.item != prev_item) {
           {
             PROF_T0();
-            mbar_wait(smem_addr(&sh.b_full), nb & 1u);
+            mbar_wait_spin(smem_addr(&sh.b_full), nb & 1u);
             PROF_ADD(m_wait_b);
           }
           ++nb;
@@ -540,18 +681,15 @@ filter_mma_kernel(MmaArgs a) {
         const uint32_t ngroups = (nq + kMmaN - 1) / kMmaN;
         const uint32_t base = un.m_begin & ~15u;
         const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
-        for (uint32_t t = 0; t < ntiles; ++t, ++mt) {
-          const uint32_t s = mt % S;
-          {
-            PROF_T0();
-            mbar_wait(smem_addr(&sh.a_full[s]), (mt / S) & 1u);
-            PROF_ADD(m_wait_a);
-          }
-          for (uint32_t g = 0; g < ngroups; ++g, ++mg) {
+        const uint32_t P = mma_pack(nq);            // tiles per accumulator stage (1 unless the group is narrow)
+        const uint32_t blockw = (uint32_t)kMmaN / P;   // columns of a tile's block
+        for (uint32_t t = 0; t < ntiles;) {
+          const uint32_t nbatch = min(P, ntiles - t);
+          for (uint32_t g = 0; g < ngroups; ++g, ++mg) {   // (P > 1 only with ngroups == 1)
             const uint32_t as = mg % kMmaAccStages;
             {
               PROF_T0();
-              mbar_wait(smem_addr(&sh.t_empty[as]), ((mg / kMmaAccStages) & 1u) ^ 1u);
+              mbar_wait_spin(smem_addr(&sh.t_empty[as]), ((mg / kMmaAccStages) & 1u) ^ 1u);
               PROF_ADD(m_wait_t);
             }
 #ifdef HS_MMA_PROF
@@ -561,30 +699,44 @@ filter_mma_kernel(MmaArgs a) {
             const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
             const uint32_t ngp = (ng + 15u) & ~15u;
             const uint32_t idesc = (1u << 4) | ((ngp >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);  // F16xF16->F32
-            const uint32_t d_tmem = tmem_base + as * kMmaN;
-            const uint32_t a0 = sA_u32 + s * a_stage_bytes;
             const uint32_t b0 = sB_u32 + (g * kMmaN >> 3) * 128u;
+            for (uint32_t j = 0; j < nbatch; ++j) {
+              const uint32_t s = (mt + j) % S;
+              if (g == 0) {
+                PROF_T0();
+                mbar_wait_spin(smem_addr(&sh.a_full[s]), ((mt + j) / S) & 1u);
+                PROF_ADD(m_wait_a);
+                tc_after();
+              }
+              const uint32_t d_tmem = tmem_base + as * kMmaN + j * blockw;
+              const uint32_t a0 = sA_u32 + s * a_stage_bytes;
 #ifdef HS_MMA_PROF
-            const long long _mi0 = clock64();
+              const long long _mi0 = clock64();
 #endif
-            for (int kk = 0; kk < ksteps; ++kk) {
-              const uint64_t ad = mma_desc(a0 + (uint32_t)kk * 2u * kMmaAGroupBytes, kMmaAGroupBytes, 128u);
-              const uint64_t bd = mma_desc(b0 + (uint32_t)kk * 2u * b_lbo, b_lbo, 128u);
+              for (int kk = 0; kk < ksteps; ++kk) {
+                const uint64_t ad = mma_desc(a0 + (uint32_t)kk * 2u * kMmaAGroupBytes, kMmaAGroupBytes, 128u);
+                const uint64_t bd = mma_desc(b0 + (uint32_t)kk * 2u * b_lbo, b_lbo, 128u);
 #ifdef HS_MMA_PROF
-              if ((a.debug & 2u) && kk > 0) continue;  // experiment: one MMA per group instead of kp/16
+                if ((a.debug & 2u) && kk > 0) continue;  // experiment: one MMA per group instead of kp/16
 #endif
-              mma_f16_ss(d_tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
+#ifdef HS_DIAG_NMMA
+                if (kk >= HS_DIAG_NMMA) continue;        // experiment: fewer MMAs per group
+#endif
+                mma_f16_ss(d_tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
+              }
+#ifdef HS_MMA_PROF
+              m_issue += (unsigned long long)(clock64() - _mi0);
+#endif
+              if (g + 1 == ngroups) mma_commit(smem_addr(&sh.a_empty[s]));
             }
-#ifdef HS_MMA_PROF
-            const long long _mi1 = clock64();
-            m_issue += (unsigned long long)(_mi1 - _mi0);
-#endif
-            if (g + 1 == ngroups) mma_commit(smem_addr(&sh.a_empty[s]));
-            mma_commit(smem_addr(&sh.t_full[as]));
-#ifdef HS_MMA_PROF
-            m_commit += (unsigned long long)(clock64() - _mi1);
-#endif
+            {
+              PROF_T0();
+              mma_commit(smem_addr(&sh.t_full[as]));
+              PROF_ADD(m_commit);
+            }
           }
+          t += nbatch;
+          mt += nbatch;
         }
       }
 #ifdef HS_MMA_PROF
@@ -609,8 +761,8 @@ filter_mma_kernel(MmaArgs a) {
     // flush.
     const int quad = warp & 3, sub = warp >> 2;
     const int row = quad * 32 + lane;
-    Survivor *stage = sh.stage[warp];
-    uint32_t *wcount = &sh.wcount[warp];  // staged survivors (entries past the capacity went to global memory)
+    uint2 (*ring)[32] = sh.ring[warp];
+    uint32_t lc = 0;  // survivors this lane holds in its slots
     uint32_t et = 0, eg = 0;
     PROF_DECL(e_wait_t);
     PROF_DECL(e_rare);
@@ -633,9 +785,10 @@ filter_mma_kernel(MmaArgs a) {
       const uint32_t ngroups = (nq + kMmaN - 1) / kMmaN;
       const uint32_t base = un.m_begin & ~15u;
       const uint32_t ntiles = (un.m_end - base + kMmaM - 1) / kMmaM;
-      for (uint32_t t = 0; t < ntiles; ++t, ++et) {
-        float rt = 0.f;
-        uint32_t rid = 0u;  // fragment id of this lane's row
+      const uint32_t P = mma_pack(nq);            // tiles per accumulator stage (see mma_pack)
+      const uint32_t blockw = (uint32_t)kMmaN / P;   // columns of a tile's block
+      for (uint32_t t = 0; t < ntiles;) {
+        const uint32_t nbatch = min(P, ntiles - t);
         for (uint32_t g = 0; g < ngroups; ++g, ++eg) {
           const uint32_t as = eg % kMmaAccStages;
           {
@@ -648,17 +801,25 @@ filter_mma_kernel(MmaArgs a) {
             tc_after();
             PROF_ADD(e_unit);
           }
-          if (g == 0) {
-            rt = sh.rowthr[et % kMmaRowRing][row];
-            rid = sh.rowid[et % kMmaRowRing][row];
-          }
+          float rt = 0.f;
+          uint32_t rid = 0u;           // threshold and fragment id of this lane's row in tile rj of the batch
+          uint32_t rj = 0xffffffffu;
           const uint32_t ng = min((uint32_t)kMmaN, nq - g * kMmaN);
-          const uint32_t ngp = (ng + 15u) & ~15u;  // columns the MMA wrote
-          const uint32_t nchunks = ngp >> 4;  // 16-column chunks; this warp takes c = sub, sub + 4, ...
+          const uint32_t ngp = (ng + 15u) & ~15u;  // columns the MMA wrote per tile
+          const uint32_t nchunks = ngp >> 4;  // 16-column chunks per tile; this warp takes c = sub, sub + 4, ...
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMmaN;
           const uint32_t qbase = it.q_begin + g * kMmaN;  // index into the query list of column 0
-          // the 16 accumulators in vv = columns col0 .. col0+15 of the group
-          auto scan16 = [&](const uint32_t (&vv)[16], uint32_t col0) {
+          // The 16 accumulators in vv = columns col0 .. col0+15 of tile j's block: their maximum (tree
+          // of 3-input max) against the row threshold.  A row that reaches it (about 2 % of the rows
+          // of a chunk) builds a branch-free column mask and puts its passing columns into its own
+          // slots in shared memory -- no atomic, no other lane involved; the warp flushes the slots
+          // at a group boundary once some lane runs full.
+          auto scan16 = [&](const uint32_t (&vv)[16], uint32_t j, uint32_t col0) {
+            if (j != rj) {
+              rt = sh.rowthr[(et + j) % kMmaRowRing][row];
+              rid = sh.rowid[(et + j) % kMmaRowRing][row];
+              rj = j;
+            }
             float vf[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) vf[i] = __uint_as_float(vv[i]);
@@ -666,87 +827,89 @@ filter_mma_kernel(MmaArgs a) {
             const float t3 = fmax3(vf[9], vf[10], vf[11]), t4 = fmax3(vf[12], vf[13], vf[14]);
             const float m = fmaxf(fmax3(t0, t1, t2), fmax3(t3, t4, vf[15]));
             if (m >= rt) {
-              // a row that reaches its threshold (about 2 % of the rows of a chunk) appends its
-              // passing columns itself: one shared-memory atomic per survivor, no warp-wide round
 #ifdef HS_MMA_PROF
               const long long _r0 = clock64();
 #endif
-              // branch-free column mask, one shared-memory atomic reserving all of the row's slots
               uint32_t pm = 0u;
 #pragma unroll
               for (int c = 0; c < 16; ++c) pm |= (vf[c] >= rt ? 1u : 0u) << c;
               const uint32_t ncol = ng - col0;  // valid columns of this chunk (>= 1)
               if (ncol < 16u) pm &= (1u << ncol) - 1u;
-              uint32_t k = atomicAdd(wcount, (uint32_t)__popc(pm));
+#ifndef HS_MMA_NO_RARE
               while (pm) {
                 const uint32_t c = (uint32_t)__ffs((int)pm) - 1u;
                 pm &= pm - 1u;
-                Survivor sv;
-                sv.query = qbase + col0 + c;  // index into the query list; the exact stage resolves it
-                sv.table = it.table;
-                sv.pos = rid;
-                sv.pad = 3;  // query = index into the query list, pos = fragment id
-                if (k < (uint32_t)kMmaStageCap) {
-                  stage[k] = sv;
-                } else {  // staging buffer full (dense hit regions): straight to the global list
-                  const unsigned long long gi = atomicAdd(a.surv_count, 1ull);
-                  if (gi < a.surv_cap) a.surv[gi] = sv;
+                if (lc < (uint32_t)kMmaRing) {
+                  ring[lc][lane] = make_uint2(qbase + col0 + c, rid);
+                  ++lc;
+                } else {  // slots full (dense hit regions): straight to the global list
+                  mma_emit_global(a.surv, a.surv_cap, a.surv_count, qbase + col0 + c, it.table, rid);
                 }
-                ++k;
               }
+#else
+              if (pm == 0xdeadbeefu) lc = pm;   // (timing experiment: survivors are dropped)
+#endif
 #ifdef HS_MMA_PROF
               e_rare += (unsigned long long)(clock64() - _r0);
 #endif
             }
           };
-          // this warp's chunks c = sub, sub + 4, ...: the load of the next chunk is in flight while
-          // the current one is scanned (two register buffers); the stage is released as soon as the
-          // warp's last load has landed
+          // The warp's chunks, tile block by tile block: the load of the next chunk is in flight
+          // while the current one is scanned (two register buffers); the stage is released as soon
+          // as the warp's last load has landed.
           auto release = [&]() {
             tc_before();
             mbar_arrive_warp(smem_addr(&sh.t_empty[as]), lane);
+          };
+          auto advance = [&](uint32_t &j, uint32_t &c) {
+            c += 4u;
+            if (c >= nchunks) {
+              c = (uint32_t)sub;
+              ++j;
+            }
           };
 #ifdef HS_MMA_PROF
           const bool do_scan = !(a.debug & 1u);
 #else
           const bool do_scan = true;
 #endif
+#if defined(HS_DIAG_NOEPI)
+          release();   // (timing experiment: the accumulators are never read)
+#else
           uint32_t va[16], vb[16];
-          uint32_t c = (uint32_t)sub;
+          uint32_t j = 0, c = (uint32_t)sub;
           if (c < nchunks) {
-            tmem_ld16_issue(taddr + c * 16u, va);
+            tmem_ld16_issue(taddr + j * blockw + c * 16u, va);
             for (;;) {
               tmem_ld_wait();
-              const uint32_t c1 = c + 4u;
-              if (c1 < nchunks) tmem_ld16_issue(taddr + c1 * 16u, vb);
+              uint32_t j1 = j, c1 = c;
+              advance(j1, c1);
+              if (j1 < nbatch) tmem_ld16_issue(taddr + j1 * blockw + c1 * 16u, vb);
               else release();
-              if (do_scan) scan16(va, c * 16u);
-              if (c1 >= nchunks) break;
+              if (do_scan) scan16(va, j, c * 16u);
+              if (j1 >= nbatch) break;
               tmem_ld_wait();
-              const uint32_t c2 = c1 + 4u;
-              if (c2 < nchunks) tmem_ld16_issue(taddr + c2 * 16u, va);
+              uint32_t j2 = j1, c2 = c1;
+              advance(j2, c2);
+              if (j2 < nbatch) tmem_ld16_issue(taddr + j2 * blockw + c2 * 16u, va);
               else release();
-              if (do_scan) scan16(vb, c1 * 16u);
-              if (c2 >= nchunks) break;
+              if (do_scan) scan16(vb, j1, c1 * 16u);
+              if (j2 >= nbatch) break;
+              j = j2;
               c = c2;
             }
           } else {
             release();  // no chunk for this warp in this group: still release the stage
           }
-          __syncwarp();
-          const uint32_t wc = *(volatile uint32_t *)wcount;  // warp-uniform
-          if (wc >= (uint32_t)kMmaFlushAt) {
-            mma_flush(stage, min(wc, (uint32_t)kMmaStageCap), a.surv, a.surv_cap, a.surv_count, lane);
-            if (lane == 0) *(volatile uint32_t *)wcount = 0u;
-            __syncwarp();
-          }
+#endif
+          if (__any_sync(0xffffffffu, lc >= (uint32_t)kMmaRingFlush))
+            lc = mma_flush(ring, lc, it.table, a.surv, a.surv_cap, a.surv_count, lane);
         }
+        t += nbatch;
+        et += nbatch;
       }
-    }
-    __syncwarp();
-    {
-      const uint32_t wc = min(*(volatile uint32_t *)wcount, (uint32_t)kMmaStageCap);
-      if (wc) mma_flush(stage, wc, a.surv, a.surv_cap, a.surv_count, lane);
+      // the slots do not carry the table: emptied before the next unit (which may belong to another)
+      lc = mma_flush(ring, lc, it.table, a.surv, a.surv_cap, a.surv_count, lane);
     }
 #ifdef HS_MMA_PROF
     if (tid == 0) {

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "hash.cuh"
+#include "internal.cuh"
 
 namespace hs {
 
@@ -32,7 +33,8 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
                  float invW, const double *__restrict__ table64, const double *__restrict__ a64,
                  const double *__restrict__ b64, double W, int K, int Kp, int L, int dim,
                  HashChunkArgs args, int32_t *__restrict__ buckets_out,
-                 unsigned long long *__restrict__ counters, uint64_t f0 /* multiple of NT */, uint64_t f1) {
+                 unsigned long long *__restrict__ counters, uint64_t f0 /* multiple of NT */, uint64_t f1,
+                 unsigned int *__restrict__ tile_counter /* preset to 2 * gridDim.x * G */) {
   constexpr int P = 4 * NQ;
   // 16-byte words of the next tile's codes held in registers: NT * 16 * NPF bytes >= NT * len
   // (the replicated-table path is taken for len <= 16 only)
@@ -91,12 +93,25 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
         pf[v] = __ldg(reinterpret_cast<const uint4 *>(codes + off));
     }
   };
+  // Tiles are handed out dynamically: a block that starts late (its SM was held by another
+  // kernel -- the hit merge of the previous batch, another context's work) takes fewer tiles
+  // instead of making the launch wait for it.  Every group's first two tiles are static; from
+  // then on thread 0 of the group takes the tile after next from a global counter, one
+  // iteration ahead of its use, so that the atomic's latency is never waited for.
+  __shared__ unsigned int s_next[G];
   const uint64_t tstride = (uint64_t)gridDim.x * G;
-  prefetch(tile0 + (uint64_t)blockIdx.x * G + gid);
-  for (uint64_t tile = tile0 + (uint64_t)blockIdx.x * G + gid; tile < ntiles; tile += tstride) {
+  uint64_t tile = tile0 + (uint64_t)blockIdx.x * G + gid, tile_nxt = tile + tstride;
+  unsigned int pending = 0;
+  if (gt == 0) pending = atomicAdd(tile_counter, 1u);
+  prefetch(tile);
+  for (; tile < ntiles;) {
     const uint64_t frag0 = tile * GT;
     const uint64_t nfrag = min((uint64_t)GT, f1 - frag0);
     group_sync();  // the previous tile's sC / sRec are no longer read
+    if (gt == 0) {
+      s_next[gid] = pending;                     // the tile after next (taken one iteration ago)
+      pending = atomicAdd(tile_counter, 1u);
+    }
     {
       const uint64_t byte0 = frag0 * (uint64_t)len;
       const uint32_t nbytes = (uint32_t)(nfrag * (uint64_t)len);
@@ -111,8 +126,9 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
       uint4 *z = reinterpret_cast<uint4 *>(sRec);
       for (uint32_t i = gt; i < (uint32_t)GT * RS / 16; i += GT) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    prefetch(tile + tstride);
+    prefetch(tile_nxt);
     group_sync();
+    const uint64_t tile_nn = tile0 + (uint64_t)s_next[gid];
     if ((uint64_t)gt < nfrag) {
       const uint64_t frag = frag0 + gt;
       const uint8_t *myc = sC + gt * len;
@@ -207,6 +223,8 @@ hash_fast_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
       uint4 *dst = reinterpret_cast<uint4 *>(args.rec + frag0 * RS);
       for (uint32_t i = gt; i < nvec; i += GT) dst[i] = src[i];
     }
+    tile = tile_nxt;
+    tile_nxt = tile_nn;
   }
   if (my_guard) atomicAdd(counters + 0, (unsigned long long)my_guard);
   if (my_corr) atomicAdd(counters + 1, (unsigned long long)my_corr);
@@ -323,18 +341,23 @@ static int launch_fast_rep(hs_ctx *ctx, int chunk, const HashChunkArgs &args, in
   constexpr int GT = NT / G;
   const size_t smem = hash_smem_bytes(ctx, NQ, REP, NT, args.full_rec != 0, G);
   auto kern = hash_fast_kernel<NQ, KW, RANK, REP, NT, K4, G>;
-  if (smem > 48 * 1024) HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (the kernel also has a little static shared memory: opt in before the sum reaches 48 KB)
+  if (smem + 2048 > 48 * 1024) HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
   if (per_sm < 1) per_sm = 1;
   const uint64_t ntiles = (f1 + GT - 1) / GT - f0 / GT;
   const unsigned grid = (unsigned)std::min<uint64_t>((ntiles + G - 1) / G, (uint64_t)ctx->num_sms * per_sm);
   const float *T = ctx->d_T32.as<float>() + (size_t)chunk * len * HS_AA * P;
+  // dynamic tile counter (counters slot 28): the first two tiles of every group are static
+  unsigned int *tile_counter = reinterpret_cast<unsigned int *>(counters + 28);
+  const unsigned int tc0 = 2u * grid * G;
+  HS_TRY(upload(ctx, tile_counter, &tc0, sizeof tc0));
   kern<<<grid, NT, smem, ctx->stream>>>(
       ctx->d_codes.as<uint8_t>(), ctx->N, len, T, ctx->d_b32.as<float>() + (size_t)chunk * P,
       ctx->d_eps32.as<float>() + (size_t)chunk * P, (float)(1.0 / ctx->prm.W), ctx->d_table64.as<double>(),
       ctx->d_a64.as<double>(), ctx->d_b64.as<double>(), ctx->prm.W, (int)ctx->prm.K, (int)ctx->Kp,
-      (int)ctx->prm.L, (int)ctx->dim, args, buckets, counters, f0, f1);
+      (int)ctx->prm.L, (int)ctx->dim, args, buckets, counters, f0, f1, tile_counter);
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;
