@@ -60,7 +60,7 @@ def build(force=False, verbose=False, ptxas_verbose=False):
     return LIB
 
 
-CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints", "hclust2", "hclust3", "evaluate2"]
+CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints", "hclust2", "hclust3", "evaluate2", "orf"]
 BIN = os.path.join(HERE, "bin")
 
 
@@ -78,7 +78,7 @@ def build_cli(force=False, verbose=False):
         out = os.path.join(BIN, name)
         if force or _newer(out, [src, LIB] + hdrs):
             cmd = [cxx, "-O2", "-std=c++17", "-Wall"] + (["-DHCLUST3"] if name == "hclust3" else []) + [
-                   "-o", out, src, "-L" + HERE, "-lhsearch_b200",
+                   "-o", out, src, "-L" + HERE, "-lhsearch_b200", "-pthread",
                    "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + "/usr/local/cuda/lib64"]
             if verbose:
                 print(" ".join(cmd))

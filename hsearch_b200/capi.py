@@ -29,7 +29,7 @@ EXPORTS = [
     "hs_bruteforce_codes", "hs_bruteforce_points", "hs_bruteforce_points_dev", "hs_cluster", "hs_comm_init", "hs_comm_unique_id",
     "hs_greedy_cluster", "hs_union_find", "hs_parse_fasta", "hs_klsh_generate", "hs_kmer3_klsh", "hs_orf6",
     "hs_evaluate_recall", "hs_evaluate_recall_dev",
-    "hs_search_points_compact", "hs_expand_hits", "hs_hits_checksum", "hs_hits_checksum_dev", "hs_hash_audit", "hs_comm_reserve", "hs_comm_result",
+    "hs_search_points_compact", "hs_expand_hits", "hs_hits_checksum", "hs_hits_checksum_dev", "hs_hash_audit", "hs_comm_reserve", "hs_comm_result", "hs_protein_id", "hs_fragment_name",
 ]
 
 
@@ -135,6 +135,9 @@ def load(build_if_missing=True):
     lib.hs_search_points_compact.argtypes = [vp, dblp, C.c_uint32, C.POINTER(CompactHits), u64p]
     lib.hs_expand_hits.argtypes = [C.POINTER(CompactHits), C.c_uint32, C.c_uint64, vp]
     lib.hs_hash_audit.argtypes = [vp, u64p]
+    lib.hs_protein_id.argtypes = [vp, u32p, C.c_uint32, u32p, C.c_uint64, u32p]
+    lib.hs_fragment_name.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint64, C.c_char_p,
+                                     C.c_uint64]
     lib.hs_comm_reserve.argtypes = [vp, C.c_uint64]
     lib.hs_comm_result.argtypes = [vp, C.POINTER(vp), u64p]
     lib.hs_hits_checksum.argtypes = [vp, C.c_uint64, u64p]

@@ -16,6 +16,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -165,6 +166,98 @@ std::vector<hs_hit> collect_hits(F call, uint64_t first_cap = 1u << 20) {
     hits.resize(n);
     return hits;
   }
+}
+
+// ---- multi-GPU mode of the search programs -------------------------------------------
+// HS_DEVICES=0,1,...: the database is cut into contiguous id blocks, one per device; every
+// device builds its own tables with the same projection and answers all centres (one host
+// thread and one context per device); the lists are merged on the host into the reference's
+// output order -- centre, table, ascending kmer id (motif_both_points.cpp:224-245): ids ascend
+// with the device index, so inside a (centre, table) segment the devices' runs follow each other.
+inline std::vector<int> devices_from_env() {
+  std::vector<int> dev;
+  if (const char *e = getenv("HS_DEVICES")) {
+    std::stringstream ss(e);
+    std::string tok;
+    while (std::getline(ss, tok, ','))
+      if (!tok.empty()) dev.push_back(atoi(tok.c_str()));
+  }
+  if (dev.empty()) dev.push_back(device_from_env());
+  return dev;
+}
+
+struct ShardedResult {
+  std::vector<hs_hit> hits;             // merged, reference order
+  std::vector<uint64_t> table_sizes;    // distinct buckets per table over the whole database
+};
+
+// run(ctx, shard_codes, shard_n, id_base) prepares one device (projection, load, index) ;
+// search(ctx, buf, cap, n) is the hit-producing call.  want_sizes: count the buckets (LSH tables).
+template <class Prep, class Search>
+ShardedResult sharded_search(const std::vector<int> &devices, const hs_params &prm, const uint8_t *codes, uint64_t n,
+                             uint32_t n_tables, Prep prep, Search search) {
+  const size_t G = devices.size();
+  std::vector<std::vector<hs_hit>> lists(G);
+  std::vector<std::vector<std::vector<uint64_t>>> keys(G);   // [device][table] -> packed keys of the shard
+  std::vector<std::string> errors(G);
+  std::vector<std::thread> threads;
+  for (size_t g = 0; g < G; ++g)
+    threads.emplace_back([&, g]() {
+      try {
+        const uint64_t lo = n * g / G, hi = n * (g + 1) / G;
+        Ctx ctx(devices[g], prm);
+        prep(ctx.h, codes + lo * prm.len, hi - lo, lo);
+        if (n_tables) {
+          hs_stats st;
+          check(hs_get_stats(ctx.h, &st), "hs_get_stats");
+          const uint32_t kw = st.key_words ? st.key_words : 1;
+          keys[g].resize(n_tables);
+          for (uint32_t l = 0; l < n_tables && hi > lo; ++l) {
+            std::vector<uint64_t> k((size_t)(hi - lo) * kw);
+            check(hs_get_keys(ctx.h, l, k.data()), "hs_get_keys");
+            // one 64-bit digest per key is enough to count distinct buckets (FNV over the words)
+            keys[g][l].resize(hi - lo);
+            for (uint64_t i = 0; i < hi - lo; ++i) {
+              uint64_t hsh = 1469598103934665603ull;
+              for (uint32_t w = 0; w < kw; ++w) hsh = (hsh ^ k[i * kw + w]) * 1099511628211ull;
+              keys[g][l][i] = kw == 1 ? k[i] : hsh;
+            }
+            std::sort(keys[g][l].begin(), keys[g][l].end());
+            keys[g][l].erase(std::unique(keys[g][l].begin(), keys[g][l].end()), keys[g][l].end());
+          }
+        }
+        lists[g] = collect_hits([&](hs_hit *buf, uint64_t cap, uint64_t *nh) { return search(ctx.h, buf, cap, nh); });
+      } catch (const std::exception &e) {
+        errors[g] = e.what();
+      }
+    });
+  for (std::thread &t : threads) t.join();
+  for (const std::string &e : errors)
+    if (!e.empty()) throw CliError(e);
+  ShardedResult r;
+  for (uint32_t l = 0; l < n_tables; ++l) {
+    std::vector<uint64_t> all;
+    for (size_t g = 0; g < G; ++g) all.insert(all.end(), keys[g][l].begin(), keys[g][l].end());
+    std::sort(all.begin(), all.end());
+    r.table_sizes.push_back((uint64_t)(std::unique(all.begin(), all.end()) - all.begin()));
+  }
+  // merge: every list is in (query, table, id) order
+  size_t total = 0;
+  for (const auto &v : lists) total += v.size();
+  r.hits.reserve(total);
+  std::vector<size_t> cur(G, 0);
+  while (r.hits.size() < total) {
+    // the smallest (query, table) at the cursors, then each device's run of it in device order
+    uint64_t best = ~0ull;
+    for (size_t g = 0; g < G; ++g)
+      if (cur[g] < lists[g].size())
+        best = std::min(best, ((uint64_t)lists[g][cur[g]].query << 32) | lists[g][cur[g]].table_first);
+    for (size_t g = 0; g < G; ++g)
+      while (cur[g] < lists[g].size() &&
+             (((uint64_t)lists[g][cur[g]].query << 32) | lists[g][cur[g]].table_first) == best)
+        r.hits.push_back(lists[g][cur[g]++]);
+  }
+  return r;
 }
 
 // ---- recall evaluation (motif_both_points.cpp:27-165) -----------------------------

@@ -63,24 +63,25 @@ int main(int argc, const char **argv) {
     prm.metric = HS_METRIC_EUCLID_FP64;
     prm.predicate = HS_PRED_D2_LE_R2;  // dis_square <= hash_R_square (:204,239)
     prm.flags = HS_FLAG_SORT_HITS;     // center order, table order, ascending kmer id (:224-245)
-    Ctx ctx(device_from_env(), prm);
-
     // one LSH object per table, each seeded by its own random_device draw (:206-211)
     const uint64_t seed = projection_seed_base();
     std::vector<double> a((size_t)hash_L * hash_K * dim), b((size_t)hash_L * hash_K);
     for (unsigned l = 0; l < hash_L; ++l)
       check(hs_generate_projection(seed + l, dim, hash_K, hash_W, &a[(size_t)l * hash_K * dim], &b[(size_t)l * hash_K]),
             "hs_generate_projection");
-    check(hs_set_projection(ctx.h, a.data(), b.data()), "hs_set_projection");
-    check(hs_load_fragments(ctx.h, codes.data(), kmers.size(), 0), "hs_load_fragments");
-    check(hs_build_index(ctx.h), "hs_build_index");
-    std::vector<uint64_t> sizes(hash_L);
-    check(hs_table_sizes(ctx.h, sizes.data()), "hs_table_sizes");
-    for (unsigned l = 0; l < hash_L; ++l) std::cout << "table size " << sizes[l] << std::endl;
-
-    const std::vector<hs_hit> hits = collect_hits([&](hs_hit *buf, uint64_t cap, uint64_t *n) {
-      return hs_search_points(ctx.h, centers.data.data(), (uint32_t)centers.size(), buf, cap, n);
-    });
+    // HS_DEVICES=0,1,...: the kmers are sharded over several GPUs (common.hpp, sharded_search)
+    const ShardedResult res = sharded_search(
+        devices_from_env(), prm, codes.data(), kmers.size(), hash_L,
+        [&](hs_ctx_t *h, const uint8_t *shard, uint64_t n, uint64_t id_base) {
+          check(hs_set_projection(h, a.data(), b.data()), "hs_set_projection");
+          check(hs_load_fragments(h, shard, n, id_base), "hs_load_fragments");
+          check(hs_build_index(h), "hs_build_index");
+        },
+        [&](hs_ctx_t *h, hs_hit *buf, uint64_t cap, uint64_t *n) {
+          return hs_search_points(h, centers.data.data(), (uint32_t)centers.size(), buf, cap, n);
+        });
+    for (unsigned l = 0; l < hash_L; ++l) std::cout << "table size " << res.table_sizes[l] << std::endl;
+    const std::vector<hs_hit> &hits = res.hits;
     {
       std::ofstream fout(output_file.c_str());
       for (const hs_hit &h : hits)

@@ -55,12 +55,16 @@ int main(int argc, const char **argv) {
     std::ofstream fnot((output_file + "notlessthan.txt").c_str());
     std::ofstream fout(output_file.c_str());
     {
-      Ctx ctx(device_from_env(), prm);
-      check(hs_load_fragments(ctx.h, codes.data(), kmers.size(), 0), "hs_load_fragments");
-      const std::vector<hs_hit> hits = collect_hits([&](hs_hit *buf, uint64_t cap, uint64_t *n) {
-        return hs_bruteforce_points(ctx.h, centers.data.data(), (uint32_t)centers.size(), buf, cap, n);
-      });
-      for (const hs_hit &h : hits)
+      // HS_DEVICES=0,1,...: the kmers are sharded over several GPUs (common.hpp, sharded_search)
+      const ShardedResult res = sharded_search(
+          devices_from_env(), prm, codes.data(), kmers.size(), 0,
+          [&](hs_ctx_t *h, const uint8_t *shard, uint64_t n, uint64_t id_base) {
+            check(hs_load_fragments(h, shard, n, id_base), "hs_load_fragments");
+          },
+          [&](hs_ctx_t *h, hs_hit *buf, uint64_t cap, uint64_t *n) {
+            return hs_bruteforce_points(h, centers.data.data(), (uint32_t)centers.size(), buf, cap, n);
+          });
+      for (const hs_hit &h : res.hits)
         fout << centers.names[h.query] << " " << kmers.names[h.db_id] << " " << fmt_g(sqrt(h.dist2)) << "\n";
     }
     if (const char *e = getenv("HS_NOLSH_NONHITS")) {

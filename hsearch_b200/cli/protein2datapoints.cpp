@@ -52,12 +52,12 @@ int main(int argc, const char **argv) {
           j += 30 + rand() % 20;
           continue;
         }
-        std::string name;
-        if (i < db.names.size()) {
-          std::istringstream iss(db.names[i]);
-          iss >> name;
-        }
-        fout << name << "#" << i << "$" << j << "@" << kmer << "*" << cnt << "\n";
+        // name#i$j@KMER*cnt (protein2datapoints.cpp:61-65) through the C ABI
+        const std::string &header = i < db.names.size() ? db.names[i] : std::string();
+        std::vector<char> line(header.size() + kmer.size() + 64);
+        if (hs_fragment_name(header.c_str(), i, j, kmer.c_str(), kmer_length, cnt, line.data(), line.size()) != HS_OK)
+          throw CliError(hs_last_error());
+        fout << line.data() << "\n";
         for (uint32_t l = 0; l < kmer_length; ++l) {
           const double *row = table + db.codes[pos + l] * HS_CDIM;
           for (int p = 0; p < HS_CDIM; ++p) {

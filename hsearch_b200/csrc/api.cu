@@ -1266,6 +1266,7 @@ static int validate_codes_end(hs_ctx *ctx, const char *who) {
   }
   return HS_OK;
 }
+int protein_id_impl(hs_ctx *ctx, const uint32_t *start_index, uint32_t nstart, const uint32_t *pos, uint64_t n, uint32_t *out);
 int validate_codes(hs_ctx *ctx, const char *who) {
   HS_TRY(validate_codes_begin(ctx));
   HS_TRY(validate_codes_enqueue(ctx, 0, ctx->N));
@@ -1529,6 +1530,37 @@ int hs_extract_windows(hs_ctx_t *ctx, const uint8_t *residues, const uint32_t *s
   }
   HS_CUDA(cudaSetDevice(ctx->device));
   return extract_windows_impl(ctx, residues, start_index, nprot, stride, id_base, pos_out, pos_cap, nfrag);
+}
+
+int hs_protein_id(hs_ctx_t *ctx, const uint32_t *start_index, uint32_t nstart, const uint32_t *pos, uint64_t n,
+                  uint32_t *protein_out) {
+  if (!ctx || !start_index || nstart == 0 || (n && (!pos || !protein_out))) {
+    set_error("hs_protein_id: bad argument");
+    return HS_ERR_INVALID;
+  }
+  HS_CUDA(cudaSetDevice(ctx->device));
+  return protein_id_impl(ctx, start_index, nstart, pos, n, protein_out);
+}
+
+int hs_fragment_name(const char *protein_header, uint32_t protein_index, uint32_t offset, const char *kmer, uint32_t len,
+                     uint64_t cnt, char *out, uint64_t out_cap) {
+  if (!protein_header || (!kmer && len) || !out || out_cap == 0) {
+    set_error("hs_fragment_name: bad argument");
+    return HS_ERR_INVALID;
+  }
+  // `istringstream iss(name); iss >> name;` (protein2datapoints.cpp:61-63): leading white space skipped,
+  // the token ends at the next white space
+  const char *b = protein_header;
+  while (*b == ' ' || *b == '\t' || *b == '\n' || *b == '\v' || *b == '\f' || *b == '\r') ++b;
+  const char *e = b;
+  while (*e && !(*e == ' ' || *e == '\t' || *e == '\n' || *e == '\v' || *e == '\f' || *e == '\r')) ++e;
+  const int need = snprintf(out, (size_t)out_cap, "%.*s#%u$%u@%.*s*%llu", (int)(e - b), b, protein_index, offset, (int)len,
+                            kmer ? kmer : "", (unsigned long long)cnt);
+  if (need < 0 || (uint64_t)need >= out_cap) {
+    set_error("hs_fragment_name: %d characters needed, capacity %llu", need + 1, (unsigned long long)out_cap);
+    return HS_ERR_CAPACITY;
+  }
+  return HS_OK;
 }
 
 uint64_t hs_num_fragments(hs_ctx_t *ctx) { return ctx ? ctx->N : 0; }

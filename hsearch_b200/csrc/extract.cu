@@ -80,4 +80,36 @@ int extract_windows_impl(hs_ctx *ctx, const uint8_t *residues, const uint32_t *s
   return validate_codes(ctx, "hs_extract_windows");
 }
 
+// ProteinDB::ProteinID (hclust/src/hclust/protein.hpp:28-39): the largest l with pos >= start_index[l],
+// searched over ALL nstart entries of start_index (the final sentinel included, as the reference
+// does: a position at or past the end maps to nstart - 1).
+__global__ void protein_id_kernel(const uint32_t *__restrict__ start_index, uint32_t nstart, const uint32_t *__restrict__ pos,
+                                  uint64_t n, uint32_t *__restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t p = pos[i];
+  uint32_t l = 0, h = nstart - 1;
+  while (l < h) {
+    const uint32_t m = l + (h - l + 1) / 2;
+    if (p >= __ldg(start_index + m)) l = m; else h = m - 1;
+  }
+  out[i] = l;
+}
+
+int protein_id_impl(hs_ctx *ctx, const uint32_t *start_index, uint32_t nstart, const uint32_t *pos, uint64_t n,
+                    uint32_t *out) {
+  if (n == 0) return HS_OK;
+  HS_TRY(ctx->d_starts.reserve(sizeof(uint32_t) * (size_t)nstart));
+  HS_TRY(ctx->d_misc.reserve(sizeof(uint32_t) * 2 * n));
+  uint32_t *d_pos = ctx->d_misc.as<uint32_t>(), *d_out = d_pos + n;
+  HS_CUDA(cudaMemcpyAsync(ctx->d_starts.p, start_index, sizeof(uint32_t) * nstart, cudaMemcpyHostToDevice, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(d_pos, pos, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  protein_id_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_starts.as<uint32_t>(), nstart, d_pos, n, d_out);
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  HS_CUDA(cudaMemcpyAsync(out, d_out, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+
 }  // namespace hs

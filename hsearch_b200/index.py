@@ -56,6 +56,13 @@ def encode(seqs):
     return out
 
 
+def fragment_name(header, protein_index, offset, kmer, cnt):
+    """`name#i$j@KMER*cnt` of protein2datapoints.cpp:61-65."""
+    buf = C.create_string_buffer(len(header) + len(kmer) + 64)
+    check(capi.load().hs_fragment_name(header.encode(), protein_index, offset, kmer.encode(), len(kmer), cnt, buf, len(buf)))
+    return buf.value.decode()
+
+
 def pack_key_string(s, key_words):
     w = np.zeros(key_words, dtype=np.uint64)
     check(capi.load().hs_pack_key_string(s.encode(), key_words, ptr(w, C.c_uint64)))
@@ -131,6 +138,15 @@ class HSearch:
                                           C.byref(nfrag)))
         self.id_base = id_base
         return nfrag.value, (pos[:nfrag.value] if want_pos else None)
+
+    def protein_id(self, start_index, pos):
+        """ProteinDB::ProteinID for an array of global residue positions (device binary search)."""
+        start_index = np.ascontiguousarray(start_index, dtype=np.uint32)
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        out = np.zeros(len(pos), dtype=np.uint32)
+        check(self.lib.hs_protein_id(self.ctx, ptr(start_index, C.c_uint32), len(start_index), ptr(pos, C.c_uint32),
+                                     len(pos), ptr(out, C.c_uint32)))
+        return out
 
     @property
     def num_fragments(self):

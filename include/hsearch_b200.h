@@ -175,6 +175,18 @@ int hs_extract_windows(hs_ctx_t *ctx, const uint8_t *residues, const uint32_t *s
                        uint32_t nprot, uint32_t stride, uint64_t id_base, uint32_t *pos_out,
                        uint64_t pos_cap, uint64_t *nfrag);
 uint64_t hs_num_fragments(hs_ctx_t *ctx);
+/* ProteinDB::ProteinID (protein.hpp:28-39): protein_out[i] = the protein holding the global residue
+ * position pos[i] -- the largest l with pos >= start_index[l], searched like the reference over all
+ * nstart entries of start_index (nprot + 1: the end sentinel included, so a position at or past the
+ * end gives nstart - 1).  With the positions hs_extract_windows returns this maps hits (fragment ids)
+ * back to proteins.  Device binary search; host arrays. */
+int hs_protein_id(hs_ctx_t *ctx, const uint32_t *start_index, uint32_t nstart, const uint32_t *pos, uint64_t n,
+                  uint32_t *protein_out);
+/* The data-point name protein2datapoints writes (protein2datapoints.cpp:61-65): the first
+ * white-space-delimited token of the protein's header line, then #protein_index $offset @KMER *cnt.
+ * Host only.  HS_ERR_CAPACITY when out_cap is too small. */
+int hs_fragment_name(const char *protein_header, uint32_t protein_index, uint32_t offset, const char *kmer, uint32_t len,
+                     uint64_t cnt, char *out, uint64_t out_cap);
 
 /* ---- hash (H2..H4) ---------------------------------------------------------- */
 /* Bucket ints floor((a.v+b)/W) for every fragment, table and projection, and

@@ -129,3 +129,14 @@ def test_expand_compact_hits_host():
     assert out["db_id"].tolist() == (ids.astype(np.uint64) + 10 ** 10).tolist()
     assert out["dist2"].tolist() == d2.tolist()
     assert lib.hs_expand_hits(None, Q, 0, None) == capi.HS_ERR_INVALID
+
+
+def test_fragment_name_host():
+    # name#i$j@KMER*cnt, the name being the first token of the header (protein2datapoints.cpp:61-65)
+    assert hb.index.fragment_name("sp|P1|X some text", 3, 77, "ARNDC", 12) == "sp|P1|X#3$77@ARNDC*12"
+    assert hb.index.fragment_name("  \tlead", 0, 0, "A", 0) == "lead#0$0@A*0"
+    assert hb.index.fragment_name("", 4294967295, 5, "WYV", 2 ** 40) == "#4294967295$5@WYV*%d" % 2 ** 40
+    lib = capi.load()
+    buf = C.create_string_buffer(8)
+    assert lib.hs_fragment_name(b"name", 1, 2, b"ARN", 3, 4, buf, 8) == capi.HS_ERR_CAPACITY
+    assert lib.hs_fragment_name(None, 1, 2, b"ARN", 3, 4, buf, 8) == capi.HS_ERR_INVALID

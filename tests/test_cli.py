@@ -94,6 +94,42 @@ def test_protein2datapoints_matches_reference(tmp_path, length, plen):
     assert strip_time(a[1]) == strip_time(b[1].replace("our.pts", "ref.pts"))
 
 
+@needs_ref
+@pytest.mark.parametrize("length,seed", [(10, 7), (25, 12345)])
+def test_protein2datapoints_multi_window_branch(tmp_path, length, seed):
+    """Long proteins: several windows per protein at the random stride 30 + rand() % 20 and the
+    duplicate-k-mer skip (protein2datapoints.cpp:47-70).  rand() is pinned on both sides: the
+    reference binary runs under oracle/_ref/libsrand_shim.so (its srand(time(NULL)) seeds HS_SEED),
+    the drop-in honours HS_SEED itself.  Non-amino-acid letters exercise ProteinDB's rand() % 20
+    replacement (protein.hpp:58-62) with the same stream."""
+    shim = os.path.join(ROOT, "oracle", "_ref", "libsrand_shim.so")
+    if not os.path.exists(shim):
+        pytest.skip("oracle/_ref/libsrand_shim.so not built")
+    _ensure_built()
+    rng = np.random.default_rng(seed)
+    unit = "".join(AA[c] for c in rng.integers(0, 20, size=200))
+    with open(tmp_path / "db.fa", "w") as f:
+        for i in range(40):
+            plen = int(rng.integers(150, 900))
+            seq = "".join(AA[c] for c in rng.integers(0, 20, size=plen))
+            if i % 5 == 0:       # repeated material: the same k-mers come back (dedup branch)
+                seq = unit + seq[:100] + unit
+            if i % 7 == 0:       # letters outside the 20 (B, X, Z ...): replaced with rand() % 20
+                seq = seq[:50] + "BXZ" + seq[50:]
+            f.write(f">sp|P{i:05d}|name{i} description words\n{seq}\n")
+    env = {"HS_SEED": str(seed)}
+    a = run(REF, "protein2datapoints", ["-d", "db.fa", "-l", str(length), "-n", "40", "-o", "ref.pts"], tmp_path,
+            env=dict(env, LD_PRELOAD=shim))
+    b = run(OURS, "protein2datapoints", ["-d", "db.fa", "-l", str(length), "-n", "40", "-o", "our.pts"], tmp_path, env=env)
+    assert a[0] == b[0] == 0
+    ref, our = open(tmp_path / "ref.pts").read(), open(tmp_path / "our.pts").read()
+    assert ref == our
+    names = ref.splitlines()[0::2]
+    assert len(names) > 200                                   # several windows per protein
+    assert any("$0@" not in n for n in names)                 # offsets beyond the first window
+    assert names[0].startswith("sp|P00000|name0#0$0@") and names[-1].endswith("*%d" % (len(names) - 1))
+
+
 def strip_volatile(stdout):
     """Drop the lines that carry timings."""
     keep = []
@@ -164,6 +200,26 @@ def test_search_pipeline_matches_reference(tmp_path, W):
     sa, sb = strip_volatile(a[1]), strip_volatile(b[1])
     sb = [l.replace("our.", "ref.") for l in sb]
     assert sa == sb
+
+    # multi-GPU mode of the two search programs (HS_DEVICES: one context per listed device, the kmers
+    # sharded in contiguous blocks, lists merged into the reference's order on the host): same files and
+    # the same stdout as the reference.  "0,0,0" runs three shards on one GPU.
+    ndev = 1
+    try:
+        import torch
+        ndev = max(1, torch.cuda.device_count())
+    except Exception:
+        pass
+    devs = ",".join(str(i % ndev) for i in range(3))
+    c = run(OURS, "motif_both_points_noLSH", ["-d", "our.db", "-c", "our.q", "-l", str(length), "-T", R, "-o", "mg.gt"],
+            tmp_path, dict(env, HS_DEVICES=devs))
+    assert c[0] == 0, c[2]
+    assert open(tmp_path / "mg.gt").read() == ref_gt
+    c = run(OURS, "motif_both_points", ["-d", "our.db", "-c", "our.q", "-l", str(length), "-W", W, "-T", R, "-g", gts,
+                                        "-o", "mg.hits"], tmp_path, dict(env, HS_DEVICES=devs))
+    assert c[0] == 0, c[2]
+    assert open(tmp_path / "mg.hits").read() == ref_hits
+    assert [l.replace("mg.", "ref.") for l in strip_volatile(c[1])] == sa      # incl. the "table size" lines
 
 
 # ---------------------------------------------------------------- hclust2 / hclust3 (CL1)
@@ -236,3 +292,28 @@ def test_evaluate2_matches_reference(tmp_path):
     a = run(REF, "evaluate2", ["nope"], tmp_path)
     b = run(OURS, "evaluate2", ["nope"], tmp_path)
     assert a[:2] == b[:2] and open(tmp_path / "nopesort.txt").read() == ""
+
+
+# ---------------------------------------------------------------- orf (E6)
+@pytest.mark.gpu
+def test_orf_program_matches_oracle(tmp_path, oracle):
+    """`orf -q file` (orf/orf_main.cc:8-20): the kept frames of every sequence, named name_j, against the
+    oracle's restatement of ORF::orf6 (the reference's own program does not compile: headers missing)."""
+    _ensure_built()
+    rng = np.random.default_rng(3)
+    seqs = ["".join("ACGT"[c] for c in rng.integers(0, 4, size=int(n))) for n in rng.integers(5, 400, size=50)]
+    seqs += ["ATG" * 30, "AC", ""]           # a long open frame, a sequence shorter than a codon, an empty one
+    with open(tmp_path / "q.fa", "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(f">read{i} x\n")
+            for k in range(0, len(s), 60):    # multi-line FASTA
+                f.write(s[k:k + 60] + "\n")
+    rc, out, err = run(OURS, "orf", ["-q", "q.fa"], tmp_path)
+    assert rc == 0, err
+    got = open(tmp_path / "q.fa_translatedAA.fasta").read().splitlines()
+    want = []
+    for i, s in enumerate(seqs):
+        for j, frame in enumerate(oracle.orf6(s)):     # the kept frames (>= 6 residues), in frame order
+            want += [f"read{i} x_{j}", frame]
+    assert len(want) > 20 and got == want
+    assert run(OURS, "orf", [], tmp_path)[0] != 0

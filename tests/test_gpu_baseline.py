@@ -165,3 +165,30 @@ def test_context_reuse_load_then_extract(oracle, monkeypatch, no_rank):
     got2 = h.search_codes(q2)
     assert len(want2) > 0 and hits_as_tuples(got2) == hits_as_tuples(want2)
     h.close()
+
+
+def test_protein_id_of_hits(oracle):
+    """ProteinDB::ProteinID (protein.hpp:28-39) on the device: window start positions -> proteins, so
+    that a hit (fragment id) maps back to its protein; the end sentinel and positions past the end
+    behave like the reference's search over all of start_index."""
+    rng = np.random.default_rng(8)
+    lens = rng.integers(1, 300, size=2000)
+    lens[::97] = 0                                     # empty proteins share a start with their successor
+    start = np.concatenate(([0], np.cumsum(lens))).astype(np.uint32)
+    h = hb.HSearch(10, 4, 4, 50.0, 30.0)
+    pos = np.concatenate((rng.integers(0, int(start[-1]) + 50, size=100000), start, start[1:] - 1)).astype(np.uint32)
+    got = h.protein_id(start, pos)
+    want = np.array([oracle.protein_id(start, int(p)) for p in pos[:3000]], dtype=np.uint32)
+    assert np.array_equal(got[:3000], want)
+    ref = np.searchsorted(start, pos, side="right").astype(np.int64) - 1     # last l with start[l] <= pos
+    assert np.array_equal(got.astype(np.int64), ref)
+    # through the window extractor: fragment -> protein -> data-point name
+    res = random_codes(1, int(start[-1]), seed=9).reshape(-1)
+    nfrag, fpos = h.extract_windows(res, start, stride=7)
+    prot = h.protein_id(start, fpos)
+    assert nfrag > 1000
+    assert np.all(fpos >= start[prot]) and np.all(fpos + 10 <= start[prot + 1])
+    kmer = "".join(hb.AA_ORDER[c] for c in res[fpos[5]:fpos[5] + 10])
+    assert hb.index.fragment_name("p%d desc" % prot[5], int(prot[5]), int(fpos[5] - start[prot[5]]), kmer, 5) == \
+        "p%d#%d$%d@%s*5" % (prot[5], prot[5], fpos[5] - start[prot[5]], kmer)
+    h.close()
