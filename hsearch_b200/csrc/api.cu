@@ -497,21 +497,29 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
 // (one launch + synchronisation per bucket: below ~8 k members the tiled scalar self-join, which
 // batches many buckets per launch, is faster -- measured at 1 M fragments)
 constexpr uint32_t kSelfJoinMmaMin = 8192;
-int selfjoin_bucket_mma(hs_ctx *ctx, uint32_t table, uint32_t mb, uint32_t me, uint64_t *nsurv, uint64_t *npairs,
-                        bool *used) {
+// The pairs (q, m), q in [q_lo, q_hi), m in (q, me): the caller walks the bucket in query chunks so
+// that the survivors of one call stay bounded (a whole 4 M-member bucket at once is 8e12 pairs).
+int selfjoin_bucket_mma(hs_ctx *ctx, uint32_t table, uint32_t mb, uint32_t me, uint32_t q_lo, uint32_t q_hi,
+                        uint64_t *nsurv, uint64_t *npairs, bool *used) {
   *used = false;
   *nsurv = 0;
+  *npairs = 0;
   FilterPlan P;
   plan_init(ctx, P);
   if (!P.mma || me - mb < kSelfJoinMmaMin) return HS_OK;
-  std::vector<uint32_t> q(me - mb);
-  for (uint32_t i = 0; i < me - mb; ++i) q[i] = mb + i;
-  HS_TRY(plan_add(ctx, P, table, mb, me, q.data(), q.size(), true));
-  if (P.mma_units.empty() || !P.items.empty() || !P.items_tc.empty()) return HS_OK;
-  *npairs = (uint64_t)(me - mb) * (me - mb - 1) / 2;
-  HS_TRY(plan_run(ctx, P, me - mb, mb, kModeSelfJoin, nsurv));
   *used = true;
-  return HS_OK;
+  if (q_hi <= q_lo) return HS_OK;
+  std::vector<uint32_t> q(q_hi - q_lo);
+  for (uint32_t i = 0; i < q_hi - q_lo; ++i) q[i] = q_lo + i;
+  HS_TRY(plan_add(ctx, P, table, mb, me, q.data(), q.size(), true));
+  if (!P.items.empty() || !P.items_tc.empty()) {
+    set_error("selfjoin_bucket_mma: unexpected scalar work items");
+    return HS_ERR_UNSUPPORTED;
+  }
+  if (P.mma_units.empty()) return HS_OK;
+  // pairs with m > q inside the bucket
+  for (uint32_t x = q_lo; x < q_hi; ++x) *npairs += (uint64_t)(me - 1 - x);
+  return plan_run(ctx, P, q_hi - q_lo, q_lo, kModeSelfJoin, nsurv);
 }
 
 // ---- hits in the reference's output order -----------------------------------------
@@ -1339,6 +1347,8 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->no_load_overlap = env_on("HS_NO_LOAD_OVERLAP");
   ctx->plan_stats = env_on("HS_PLAN_STATS");
   ctx->no_mma_filter = env_on("HS_NO_MMA_FILTER");
+  if (const char *e = getenv("HS_SELFJOIN_CHUNK"))
+    if (atoi(e) >= 256) ctx->selfjoin_chunk = (uint32_t)atoi(e);
   ctx->num_sms = prop.multiProcessorCount;
   ctx->prm = *params;
   ctx->dim = params->len * HS_CDIM;

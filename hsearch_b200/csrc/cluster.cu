@@ -164,26 +164,32 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
       {
         std::vector<uint2> rest;
         for (const uint2 &bk : large) {
-          uint64_t nsurv = 0, np = 0;
-          bool used = false;
-          HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
-          HS_TRY(selfjoin_bucket_mma(ctx, l, bk.x, bk.y, &nsurv, &np, &used));
-          if (!used) {
-            rest.push_back(bk);
-            continue;
+          // in chunks of ctx->selfjoin_chunk query members: the survivors of a chunk are verified and
+          // united before the next chunk is filtered, so the survivor buffer stays bounded
+          // whatever the bucket size (50 M fragments: buckets of millions of members)
+          bool used = true;
+          const uint32_t chunk = ctx->selfjoin_chunk;
+          for (uint64_t q_lo64 = bk.x; q_lo64 + 1 < bk.y && used; q_lo64 += chunk) {
+            const uint32_t q_lo = (uint32_t)q_lo64;
+            const uint32_t q_hi = (uint32_t)std::min<uint64_t>(q_lo64 + chunk, bk.y - 1);
+            uint64_t nsurv = 0, np = 0;
+            HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
+            HS_TRY(selfjoin_bucket_mma(ctx, l, bk.x, bk.y, q_lo, q_hi, &nsurv, &np, &used));
+            if (!used) break;
+            HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
+            ncand += np;
+            ctx->stats.n_candidates_tc += np;
+            ea.surv = ctx->d_surv.as<Survivor>();
+            ea.nsurv = nsurv;
+            ea.qlist_mma = ctx->d_qlist_mma.as<uint32_t>();
+            HS_TRY(launch_exact(ctx, ea));
+            HS_CUDA(cudaEventRecord(ev[6], ctx->stream));
+            HS_CUDA(cudaEventSynchronize(ev[6]));
+            nsurv_total += nsurv;
+            ms_f2 += ev_ms(ev[4], ev[5]);
+            ms_e2 += ev_ms(ev[5], ev[6]);
           }
-          HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
-          ncand += np;
-          ctx->stats.n_candidates_tc += np;
-          ea.surv = ctx->d_surv.as<Survivor>();
-          ea.nsurv = nsurv;
-          ea.qlist_mma = ctx->d_qlist_mma.as<uint32_t>();
-          HS_TRY(launch_exact(ctx, ea));
-          HS_CUDA(cudaEventRecord(ev[6], ctx->stream));
-          HS_CUDA(cudaEventSynchronize(ev[6]));
-          nsurv_total += nsurv;
-          ms_f2 += ev_ms(ev[4], ev[5]);
-          ms_e2 += ev_ms(ev[5], ev[6]);
+          if (!used) rest.push_back(bk);
         }
         large.swap(rest);
       }

@@ -196,6 +196,7 @@ struct hs_ctx {
   bool no_pipeline = false;      // HS_NO_PIPELINE: host-buffer searches in one pass (no query blocks)
   bool no_load_overlap = false;  // HS_NO_LOAD_OVERLAP: hs_load_fragments copies first, hashes later
   bool plan_stats = false;       // HS_PLAN_STATS: print the filter work-list statistics
+  uint32_t selfjoin_chunk = 1u << 16;  // HS_SELFJOIN_CHUNK: query members per tensor-filter pass of a large bucket (hs_cluster)
   bool no_mma_filter = false;    // HS_NO_MMA_FILTER: keep the Euclidean metric off the pipelined tensor filter
 
   hs_stats stats{};

@@ -679,6 +679,27 @@ def test_blocked_gather_long_fragments(oracle, monkeypatch):
 
 
 @pytest.mark.parametrize("R,pred", [(25.0, hb.HS_PRED_SQRT_LE_R), (30.0, hb.HS_PRED_D2_LE_R2)])
+def test_cluster_large_buckets_in_query_chunks(oracle, monkeypatch):
+    """A large bucket is self-joined in chunks of its members (bounded survivor buffer, what lets the
+    50 M configuration run): 1 k-member chunks over ~9 k-member buckets give the same edges and labels as
+    one pass per bucket."""
+    length, K, L, W, R = 10, 4, 3, 50.0, 25.0
+    codes = planted_families(115000, length, seed=96)
+    res = []
+    for chunk in ("1024", "1000000"):
+        monkeypatch.setenv("HS_SELFJOIN_CHUNK", chunk)     # read by hs_create
+        h, a, b = make(length, K, L, W, R, predicate=hb.HS_PRED_SQRT_LE_R)
+        h.load_fragments(codes)
+        h.build_index()
+        res.append((h.cluster(), h.stats().as_dict()))
+        h.close()
+    assert res[0][1]["n_candidates_tc"] == res[1][1]["n_candidates_tc"] > 1e7
+    assert res[0][1]["n_candidates"] == res[1][1]["n_candidates"]
+    assert res[0][1]["n_edges"] == res[1][1]["n_edges"] > 0
+    assert np.array_equal(res[0][0], res[1][0])
+
+
+@pytest.mark.parametrize("R,pred", [(25.0, hb.HS_PRED_SQRT_LE_R), (30.0, hb.HS_PRED_D2_LE_R2)])
 def test_cluster_large_buckets_through_tensor_filter(oracle, R, pred):
     """Buckets of >= 8192 members are self-joined by the tcgen05 filter (queries = the bucket's own
     members): same partition as the oracle and as the scalar-filter path."""
