@@ -221,6 +221,7 @@ int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t
     fa.surv_cap = ctx->d_surv.cap / sizeof(Survivor);
     fa.surv_count = cnt;
     HS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
+    HS_CUDA(cudaMemsetAsync(cnt + 7, 0, sizeof(unsigned long long), ctx->stream));
     HS_TRY(launch_filter(ctx, fa, nblocks, mode));
     if (fa_tc && nblocks_tc) {
       fa_tc->surv = fa.surv;
@@ -239,15 +240,19 @@ int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t
                                ctx->d_qb16.p, mode));
       HS_CUDA(cudaEventRecord(ctx->ev[14], ctx->stream));
     }
-    unsigned long long n = 0;
-    HS_TRY(read_back(ctx, cnt, &n, sizeof n));
+    // slot 8: survivors; slot 15: threshold events staged by the pipelined tensor filter (the event
+    // list has the survivor list's capacity: either overflowing means a bigger buffer and a rerun)
+    unsigned long long h8[8] = {0};
+    HS_TRY(read_back(ctx, cnt, h8, sizeof h8));
+    const unsigned long long n = h8[0], n_ev = (ml && ml->grid && HS_MMA_EVENTS) ? h8[7] : 0ull;
     if (fa_tc && nblocks_tc) ctx->stats.ms_filter_tc += ev_ms(ctx->ev[10], ctx->ev[11]);
     if (ml && ml->grid) ctx->stats.ms_filter_tc += ev_ms(ctx->ev[13], ctx->ev[14]);
-    if (n <= fa.surv_cap) {
+    if (n <= fa.surv_cap && n_ev <= fa.surv_cap) {
       *nsurv_out = n;
       return HS_OK;
     }
-    HS_TRY(ctx->d_surv.reserve(sizeof(Survivor) * (size_t)(n + n / 8 + 1024)));
+    const unsigned long long need = std::max(n, n_ev);
+    HS_TRY(ctx->d_surv.reserve(sizeof(Survivor) * (size_t)(need + need / 8 + 1024)));
   }
   set_error("filter: survivor buffer kept overflowing");
   return HS_ERR_NOMEM;
@@ -1404,6 +1409,7 @@ void hs_destroy(hs_ctx_t *ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_up) cudaFreeHost(ctx->h_up);
   ctx->d_hits_sorted_alt.release();
+  ctx->d_events.release();
   DevBuf *cbufs[] = {&ctx->d_cidt, &ctx->d_cidt_alt, &ctx->d_cdist, &ctx->d_cdist_alt, &ctx->d_coffsets};
   for (DevBuf *b : cbufs) b->release();
   cudaStreamDestroy(ctx->stream);

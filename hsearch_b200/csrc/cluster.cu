@@ -20,6 +20,7 @@
 namespace hs {
 
 constexpr uint32_t kSmallBucket = 64;
+constexpr uint32_t kSelfJoinTail = 512;  // members at the end of a tensor-joined bucket left to the scalar self-join
 
 __global__ void iota32_kernel(uint32_t *p, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,15 +168,18 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
           // in chunks of ctx->selfjoin_chunk query members: the survivors of a chunk are verified and
           // united before the next chunk is filtered, so the survivor buffer stays bounded
           // whatever the bucket size (50 M fragments: buckets of millions of members)
-          bool used = true;
-          const uint32_t chunk = ctx->selfjoin_chunk;
-          for (uint64_t q_lo64 = bk.x; q_lo64 + 1 < bk.y && used; q_lo64 += chunk) {
-            const uint32_t q_lo = (uint32_t)q_lo64;
-            const uint32_t q_hi = (uint32_t)std::min<uint64_t>(q_lo64 + chunk, bk.y - 1);
+          // The last kSelfJoinTail members pair among themselves on the scalar self-join (too few
+          // members are left after them for a tensor tile); every tensor chunk keeps >= 1024 queries.
+          bool used = bk.y - bk.x >= 4 * kSelfJoinTail;
+          const uint32_t chunk = std::max<uint32_t>(ctx->selfjoin_chunk, 1024u);
+          const uint32_t tail_lo = bk.y - kSelfJoinTail;
+          for (uint32_t q_lo = bk.x; used && q_lo < tail_lo;) {
+            uint32_t q_hi = (uint32_t)std::min<uint64_t>((uint64_t)q_lo + chunk, tail_lo);
+            if (tail_lo - q_hi < 1024u) q_hi = tail_lo;
             uint64_t nsurv = 0, np = 0;
             HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
             HS_TRY(selfjoin_bucket_mma(ctx, l, bk.x, bk.y, q_lo, q_hi, &nsurv, &np, &used));
-            if (!used) break;
+            if (!used) break;   // (decided by the first chunk: tensor path not available)
             HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
             ncand += np;
             ctx->stats.n_candidates_tc += np;
@@ -188,8 +192,9 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
             nsurv_total += nsurv;
             ms_f2 += ev_ms(ev[4], ev[5]);
             ms_e2 += ev_ms(ev[5], ev[6]);
+            q_lo = q_hi;
           }
-          if (!used) rest.push_back(bk);
+          rest.push_back(used ? make_uint2(tail_lo, bk.y) : bk);
         }
         large.swap(rest);
       }

@@ -161,6 +161,7 @@ struct hs_ctx {
   hs::DevBuf d_tq16, d_work_tc, d_qlist_tc;  // tensor-core filter: FP16 query tables, its work list
   hs::DevBuf d_tab16;                        // pipelined tensor filter: FP16 embedding rows + row norms
   hs::DevBuf d_qb16, d_mma_items, d_mma_units, d_mma_cta, d_qlist_mma;
+  hs::DevBuf d_events;                       // pipelined tensor filter: staged threshold events (filter_mma.cu)
   int num_sms = 0;
   uint64_t hit_qmax = 0;   // query ids of the current call are < hit_qmax (hit sort key width)
   uint64_t hit_idmax = 0;  // db ids of the hits being sorted are < hit_idmax (0: id_base + N)

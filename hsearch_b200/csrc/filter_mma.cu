@@ -280,6 +280,17 @@ __device__ __noinline__ void mma_emit_global(Survivor *surv, unsigned long long 
   }
 }
 
+// Copy a warp's queued events (n * 5 sixteen-byte words) to the global event list: one atomic, coalesced.
+__device__ __noinline__ void mma_flush_events(const uint4 *q, uint32_t n, uint4 *events, unsigned long long cap,
+                                              unsigned long long *count, int lane) {
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(count, (unsigned long long)n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const uint32_t nw = base + n <= cap ? n * 5u : (base < cap ? (uint32_t)(cap - base) * 5u : 0u);
+  for (uint32_t i = lane; i < nw; i += 32) events[base * 5u + i] = q[i];
+  __syncwarp();
+}
+
 #ifdef HS_MMA_PROF
 #define PROF_DECL(n) unsigned long long n = 0
 #define PROF_T0() const long long _t0 = clock64()
@@ -291,6 +302,24 @@ __device__ __noinline__ void mma_emit_global(Survivor *surv, unsigned long long 
 #define PROF_ADD(n)
 #define PROF_OUT(i, n)
 #endif
+
+// Event staging (HS_MMA_EVENTS).  Finding WHICH of a chunk's 16 columns pass is ~75 instructions
+// executed by the one or two lanes of a warp whose row reached its threshold -- 3-6 % SIMD
+// efficiency, 40 % of the kernel's instructions, 9 ms of a 35 ms launch (profiles/r02_filter_
+// experiments.md).  Instead the lane stores the 16 raw accumulators with the row's threshold and
+// ids (80 bytes, a dozen instructions) into its warp's queue; the queues are flushed to global
+// memory and resolve_events_kernel applies the very same test `value >= threshold`, one event
+// per lane at full SIMD width, and writes the survivors.
+struct MmaEvent {
+  uint32_t v[16];        // the accumulators of columns qidx0 .. qidx0 + 15 (FP32 bit patterns)
+  uint32_t qidx0;        // index of column 0 in the query list
+  uint32_t rid;          // fragment id of the row
+  uint32_t rt;           // the row threshold (FP32 bit pattern)
+  uint32_t ncol_table;   // valid columns (1..16) | table << 8
+};
+static_assert(sizeof(MmaEvent) == 80, "five 16-byte words");
+constexpr int kMmaEvCap = 25;      // events queued per epilogue warp (2000 bytes)
+constexpr int kMmaEvFlushAt = 10;  // queued events that make the warp flush at the next group boundary
 
 struct MmaItem {
   uint32_t table;
@@ -323,6 +352,9 @@ struct MmaArgs {
   Survivor *surv;
   unsigned long long surv_cap;
   unsigned long long *surv_count;
+  MmaEvent *events;           // HS_MMA_EVENTS: rows that reached their threshold, with their 16 accumulators
+  unsigned long long ev_cap;
+  unsigned long long *ev_count;
 };
 
 struct MmaShared {
@@ -342,7 +374,12 @@ struct MmaShared {
   uint32_t rowid[kMmaRowRing][kMmaM];   // fragment id of every row (the exact stage then skips the id gather)
   // survivors staged per lane: (index into the query list, fragment id); slot-major so that a
   // warp-wide access touches consecutive words
+#if HS_MMA_EVENTS
+  uint4 evq[kMmaEpiWarps][kMmaEvCap * 5];
+  uint32_t evcount[kMmaEpiWarps];
+#else
   uint2 ring[kMmaEpiWarps][kMmaRing][32];
+#endif
 };
 
 // Tile packing (-DHS_MMA_PACK; off: measured 36.1 ms against 35.0 at bench C2, profiles/r02_filter_
@@ -412,6 +449,9 @@ filter_mma_kernel(MmaArgs a) {
   }
   if (tid < HS_AA * 8) sh.tab16[tid >> 3][tid & 7] = a.tab16[tid >> 3];
   if (tid < HS_AA) sh.nx32[tid] = a.nx32[tid];
+#if HS_MMA_EVENTS
+  if (tid < kMmaEpiWarps) sh.evcount[tid] = 0u;
+#endif
   if (warp == kMmaIssueWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&sh.tmem_base)),
                  "r"(kMmaTmemCols)
@@ -761,8 +801,13 @@ filter_mma_kernel(MmaArgs a) {
     // flush.
     const int quad = warp & 3, sub = warp >> 2;
     const int row = quad * 32 + lane;
+#if HS_MMA_EVENTS
+    uint4 *evq = sh.evq[warp];
+    uint32_t *evcount = &sh.evcount[warp];
+#else
     uint2 (*ring)[32] = sh.ring[warp];
     uint32_t lc = 0;  // survivors this lane holds in its slots
+#endif
     uint32_t et = 0, eg = 0;
     PROF_DECL(e_wait_t);
     PROF_DECL(e_rare);
@@ -830,6 +875,25 @@ filter_mma_kernel(MmaArgs a) {
 #ifdef HS_MMA_PROF
               const long long _r0 = clock64();
 #endif
+#if HS_MMA_EVENTS
+              // the 16 accumulators, untested, into the warp's event queue (resolve_events_kernel finds the columns)
+              const uint32_t slot = atomicAdd(evcount, 1u);
+              const uint4 meta = make_uint4(qbase + col0, rid, __float_as_uint(rt), min(ng - col0, 16u) | (it.table << 8));
+              uint4 *dst;
+              if (slot < (uint32_t)kMmaEvCap) {
+                dst = evq + slot * 5u;
+              } else {  // queue full (dense hit regions): straight to the global list
+                const unsigned long long gi = atomicAdd(a.ev_count, 1ull);
+                dst = gi < a.ev_cap ? reinterpret_cast<uint4 *>(a.events + gi) : nullptr;
+              }
+              if (dst) {
+                dst[0] = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+                dst[1] = make_uint4(vv[4], vv[5], vv[6], vv[7]);
+                dst[2] = make_uint4(vv[8], vv[9], vv[10], vv[11]);
+                dst[3] = make_uint4(vv[12], vv[13], vv[14], vv[15]);
+                dst[4] = meta;
+              }
+#else
               uint32_t pm = 0u;
 #pragma unroll
               for (int c = 0; c < 16; ++c) pm |= (vf[c] >= rt ? 1u : 0u) << c;
@@ -848,6 +912,7 @@ filter_mma_kernel(MmaArgs a) {
               }
 #else
               if (pm == 0xdeadbeefu) lc = pm;   // (timing experiment: survivors are dropped)
+#endif
 #endif
 #ifdef HS_MMA_PROF
               e_rare += (unsigned long long)(clock64() - _r0);
@@ -902,15 +967,34 @@ filter_mma_kernel(MmaArgs a) {
             release();  // no chunk for this warp in this group: still release the stage
           }
 #endif
+#if HS_MMA_EVENTS
+          __syncwarp();
+          const uint32_t wc = *(volatile uint32_t *)evcount;  // warp-uniform
+          if (wc >= (uint32_t)kMmaEvFlushAt) {
+            mma_flush_events(evq, min(wc, (uint32_t)kMmaEvCap), reinterpret_cast<uint4 *>(a.events), a.ev_cap, a.ev_count, lane);
+            if (lane == 0) *(volatile uint32_t *)evcount = 0u;
+            __syncwarp();
+          }
+#else
           if (__any_sync(0xffffffffu, lc >= (uint32_t)kMmaRingFlush))
             lc = mma_flush(ring, lc, it.table, a.surv, a.surv_cap, a.surv_count, lane);
+#endif
         }
         t += nbatch;
         et += nbatch;
       }
+#if !HS_MMA_EVENTS
       // the slots do not carry the table: emptied before the next unit (which may belong to another)
       lc = mma_flush(ring, lc, it.table, a.surv, a.surv_cap, a.surv_count, lane);
+#endif
     }
+#if HS_MMA_EVENTS
+    __syncwarp();
+    {
+      const uint32_t wc = min(*(volatile uint32_t *)evcount, (uint32_t)kMmaEvCap);
+      if (wc) mma_flush_events(evq, wc, reinterpret_cast<uint4 *>(a.events), a.ev_cap, a.ev_count, lane);
+    }
+#endif
 #ifdef HS_MMA_PROF
     if (tid == 0) {
       PROF_OUT(8, (unsigned long long)(clock64() - e_start));
@@ -926,6 +1010,60 @@ filter_mma_kernel(MmaArgs a) {
   if (warp == kMmaIssueWarp) {
     tc_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kMmaTmemCols) : "memory");
+  }
+}
+
+// One event per lane: the column test the filter's epilogue skipped (value >= row threshold on
+// the same FP32 values, so the survivors are exactly those of the in-kernel test), survivors
+// appended with one atomic per warp.
+__global__ void __launch_bounds__(256)
+resolve_events_kernel(const MmaEvent *__restrict__ events, const unsigned long long *__restrict__ ev_count,
+                      unsigned long long ev_cap, Survivor *__restrict__ surv, unsigned long long surv_cap,
+                      unsigned long long *__restrict__ surv_count) {
+  const unsigned long long n = min(*ev_count, ev_cap);
+  const int lane = threadIdx.x & 31;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+    const unsigned long long i = i0 + lane;
+    uint32_t pm = 0u, qidx0 = 0u, rid = 0u, table = 0u;
+    if (i < n) {
+      const uint4 *e = reinterpret_cast<const uint4 *>(events + i);
+      const uint4 w0 = __ldg(e), w1 = __ldg(e + 1), w2 = __ldg(e + 2), w3 = __ldg(e + 3), meta = __ldg(e + 4);
+      const float rt = __uint_as_float(meta.z);
+      const uint32_t v[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+      for (int c = 0; c < 16; ++c) pm |= (__uint_as_float(v[c]) >= rt ? 1u : 0u) << c;
+      const uint32_t ncol = meta.w & 0xffu;
+      if (ncol < 16u) pm &= (1u << ncol) - 1u;
+      qidx0 = meta.x;
+      rid = meta.y;
+      table = meta.w >> 8;
+    }
+    const uint32_t cnt = (uint32_t)__popc(pm);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += x;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0u) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(surv_count, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0) + (inc - cnt);
+    while (pm) {
+      const uint32_t c = (uint32_t)__ffs((int)pm) - 1u;
+      pm &= pm - 1u;
+      if (base < surv_cap) {
+        Survivor sv;
+        sv.query = qidx0 + c;  // index into the query list; the exact stage resolves it
+        sv.table = table;
+        sv.pos = rid;          // fragment id
+        sv.pad = 3;
+        surv[base] = sv;
+      }
+      ++base;
+    }
   }
 }
 
@@ -1139,6 +1277,15 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
   a.surv = fa.surv;
   a.surv_cap = fa.surv_cap;
   a.surv_count = fa.surv_count;
+#if HS_MMA_EVENTS
+  // event list: as many entries as the survivor list (an event holds at least one survivor, apart from
+  // rows whose only passing columns are padding); run_filter grows both together on overflow
+  HS_TRY(ctx->d_events.reserve(sizeof(MmaEvent) * (size_t)fa.surv_cap));
+  a.events = ctx->d_events.as<MmaEvent>();
+  a.ev_cap = fa.surv_cap;
+  a.ev_count = ctx->d_counters.as<unsigned long long>() + 15;
+  HS_CUDA(cudaMemsetAsync(a.ev_count, 0, sizeof(unsigned long long), ctx->stream));
+#endif
   (void)mode;
 #define HS_MMA(LB)                                                                                            \
   do {                                                                                                        \
@@ -1153,6 +1300,10 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
   else if (a.len <= 25) HS_MMA(25);
   else HS_MMA(32);
 #undef HS_MMA
+#if HS_MMA_EVENTS
+  resolve_events_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(a.events, a.ev_count, a.ev_cap, a.surv, a.surv_cap, a.surv_count);
+  ctx->stats.kernel_launches++;
+#endif
 #ifdef HS_MMA_PROF
   {
     unsigned long long h[24];

@@ -86,6 +86,12 @@ struct MmaItemHost {
 struct MmaUnitHost {
   uint32_t item, m_begin, m_end, pad;
 };
+// 1: the pipelined tensor filter stages threshold events (16 raw accumulators) and
+// resolve_events_kernel finds the passing columns; 0 (default): the epilogue tests the columns
+// itself.  Measured at bench C2: 41.6 ms (incl. 2-3 ms resolver) against 34.3 ms.
+#ifndef HS_MMA_EVENTS
+#define HS_MMA_EVENTS 0
+#endif
 #ifndef HS_MMA_UNIT_TILES
 #define HS_MMA_UNIT_TILES 32
 #endif

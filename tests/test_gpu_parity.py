@@ -678,7 +678,6 @@ def test_blocked_gather_long_fragments(oracle, monkeypatch):
     assert hits_as_tuples(got_sub) == hits_as_tuples(want)
 
 
-@pytest.mark.parametrize("R,pred", [(25.0, hb.HS_PRED_SQRT_LE_R), (30.0, hb.HS_PRED_D2_LE_R2)])
 def test_cluster_large_buckets_in_query_chunks(oracle, monkeypatch):
     """A large bucket is self-joined in chunks of its members (bounded survivor buffer, what lets the
     50 M configuration run): 1 k-member chunks over ~9 k-member buckets give the same edges and labels as
