@@ -706,49 +706,101 @@ static SearchBlocks search_blocks(uint32_t Q) {
   return b;
 }
 
-// Splits the survivor list by query block.  SCATTER = false:
-// counts per block; true: writes the survivors of each block contiguously (cursor[] preset to
-// the block offsets).  Counts are aggregated in shared memory: one global atomic per
-// (thread block, query block) and tile of 2048 survivors.
-constexpr int kSurvItems = 8;
+// Regroups the survivor list by (query block, fragment-id block).  The query blocks are what the
+// pipelined verify / sort / copy-out of a host-buffer search works through one after the other; the
+// id blocks give the exact stage its locality: it gathers one 32-byte fragment record per survivor,
+// and in filter order those gathers are random over the whole record array (128 bytes of DRAM
+// traffic per record, 13 GB for 10^8 survivors), while inside an id block of 2^id_shift records
+// (16 MB) they stay in L2 and every DRAM sector is fetched about once.  SCATTER = false: counts per
+// bin; true: writes the survivors bin by bin (cursor[] preset to the bin offsets).  Counts are
+// aggregated in shared memory: one global atomic per (thread block, bin) and tile of 4096 survivors.
+constexpr int kSurvItems = 16;
+constexpr uint32_t kSurvIdBins = 256, kSurvMaxBins = kSearchBlocks * kSurvIdBins;
+struct SurvBinning {
+  SearchBlocks qb;
+  uint32_t nqblk;    // query blocks in use (1: no split by query)
+  uint32_t nid;      // id blocks per query block
+  int id_shift;      // id block of a fragment = id >> id_shift (clamped to nid - 1)
+};
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
-survivor_block_kernel(const Survivor *__restrict__ surv, uint64_t n, const uint32_t *__restrict__ qlist_mma,
-                      SearchBlocks qb, uint32_t nblk, unsigned long long *__restrict__ cursor,
-                      Survivor *__restrict__ out) {
-  __shared__ unsigned int s_cnt[kSearchBlocks];
-  __shared__ unsigned long long s_base[kSearchBlocks];
+survivor_bin_kernel(const Survivor *__restrict__ surv, uint64_t n, const uint32_t *__restrict__ qlist_mma, SurvBinning sb,
+                    unsigned long long *__restrict__ cursor, Survivor *__restrict__ out) {
+  __shared__ unsigned int s_cnt[kSurvMaxBins];
+  __shared__ unsigned long long s_base[kSurvMaxBins];
+  const uint32_t nbins = sb.nqblk * sb.nid;
   const uint64_t tile = (uint64_t)blockDim.x * kSurvItems;
   for (uint64_t t0 = (uint64_t)blockIdx.x * tile; t0 < n; t0 += (uint64_t)gridDim.x * tile) {
-    if (threadIdx.x < kSearchBlocks) s_cnt[threadIdx.x] = 0u;
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) s_cnt[b] = 0u;
     __syncthreads();
-    Survivor sv[kSurvItems];
-    uint32_t blk[kSurvItems], slot[kSurvItems];
+    uint32_t bs[kSurvItems];   // bin | slot << 16 (a tile holds 4096 survivors: the slot fits 16 bits)
 #pragma unroll
     for (int j = 0; j < kSurvItems; ++j) {
       const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
-      blk[j] = 0xffffffffu;
+      bs[j] = 0xffffffffu;
       if (i < n) {
-        sv[j] = surv[i];
-        const uint32_t q = (sv[j].pad & 1u) ? __ldg(qlist_mma + sv[j].query) : sv[j].query;
+        const Survivor sv = surv[i];
         uint32_t bq = 0;
+        if (sb.nqblk > 1) {
+          const uint32_t q = (sv.pad & 1u) ? __ldg(qlist_mma + sv.query) : sv.query;
 #pragma unroll
-        for (int c = 0; c < (int)kSearchBlocks - 1; ++c) bq += q >= qb.end[c] ? 1u : 0u;
-        blk[j] = bq;
-        slot[j] = atomicAdd(&s_cnt[blk[j]], 1u);
+          for (int c = 0; c < (int)kSearchBlocks - 1; ++c) bq += q >= sb.qb.end[c] ? 1u : 0u;
+        }
+        // (survivors of the scalar filter carry a bucket position, not an id: first id block)
+        const uint32_t ib = (sv.pad & 2u) ? min(sv.pos >> sb.id_shift, sb.nid - 1u) : 0u;
+        const uint32_t bin = bq * sb.nid + ib;
+        bs[j] = bin | (atomicAdd(&s_cnt[bin], 1u) << 16);
       }
     }
     __syncthreads();
-    if (threadIdx.x < nblk && s_cnt[threadIdx.x])
-      s_base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x)
+      if (s_cnt[b]) s_base[b] = atomicAdd(cursor + b, (unsigned long long)s_cnt[b]);
     __syncthreads();
     if (SCATTER) {
 #pragma unroll
       for (int j = 0; j < kSurvItems; ++j)
-        if (blk[j] != 0xffffffffu) out[s_base[blk[j]] + slot[j]] = sv[j];
+        if (bs[j] != 0xffffffffu) {
+          const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
+          out[s_base[bs[j] & 0xffffu] + (bs[j] >> 16)] = surv[i];   // (re-read: L2-hot)
+        }
     }
     __syncthreads();
   }
+}
+
+// d_surv[0 .. nsurv) -> d_surv_blk, by (query block, id block); cnt_qblk[c] = survivors of query block c.
+static int bin_survivors(hs_ctx *ctx, uint64_t nsurv, uint32_t Q, uint32_t nqblk, unsigned long long *cnt_qblk,
+                         bool by_id = true) {
+  for (uint32_t c = 0; c < nqblk; ++c) cnt_qblk[c] = 0;
+  if (nsurv == 0) return HS_OK;
+  SurvBinning sb;
+  sb.qb = search_blocks(Q);
+  sb.nqblk = nqblk;
+  sb.nid = by_id ? kSurvIdBins : 1u;
+  int nbits = 1;
+  while (nbits < 32 && (ctx->N >> nbits)) ++nbits;   // ids < 2^nbits
+  sb.id_shift = std::max(0, nbits - 8);
+  const uint32_t nbins = sb.nqblk * sb.nid;
+  HS_TRY(ctx->d_surv_blk.reserve(sizeof(Survivor) * nsurv));
+  HS_TRY(ctx->d_binctr.reserve(sizeof(unsigned long long) * 2 * kSurvMaxBins));
+  unsigned long long *ctr = ctx->d_binctr.as<unsigned long long>();
+  HS_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * nbins, ctx->stream));
+  const unsigned grid = (unsigned)std::min<uint64_t>((nsurv + 4095) / 4096, (uint64_t)ctx->num_sms * 8);
+  survivor_bin_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->d_surv.as<Survivor>(), nsurv, ctx->d_qlist_mma.as<uint32_t>(), sb, ctr, nullptr);
+  HS_CUDA(cudaGetLastError());
+  std::vector<unsigned long long> h(nbins), cur(nbins);
+  HS_TRY(read_back(ctx, ctr, h.data(), sizeof(unsigned long long) * nbins));
+  unsigned long long run = 0;
+  for (uint32_t b = 0; b < nbins; ++b) {
+    cur[b] = run;
+    run += h[b];
+    cnt_qblk[b / sb.nid] += h[b];
+  }
+  HS_TRY(upload(ctx, ctr + kSurvMaxBins, cur.data(), sizeof(unsigned long long) * nbins));
+  survivor_bin_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->d_surv.as<Survivor>(), nsurv, ctx->d_qlist_mma.as<uint32_t>(), sb, ctr + kSurvMaxBins, ctx->d_surv_blk.as<Survivor>());
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches += 2;
+  return HS_OK;
 }
 
 struct QueryInput {
@@ -1023,25 +1075,9 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
     uint64_t nsurv = 0;
     HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
     ctx->stats.n_survivors = nsurv;
-    // survivors by query block
-    HS_TRY(ctx->d_surv_blk.reserve(sizeof(Survivor) * std::max<uint64_t>(nsurv, 1)));
-    unsigned long long *blk_cnt = ctx->d_counters.as<unsigned long long>() + 16;  // [nblk] counts, [nblk] cursors
-    HS_CUDA(cudaMemsetAsync(blk_cnt, 0, sizeof(unsigned long long) * 2 * nblk, ctx->stream));
+    // survivors by query block (and, inside a query block, by fragment-id block: bin_survivors)
     unsigned long long h_cnt[kSearchBlocks] = {0};
-    if (nsurv) {
-      const unsigned grid = (unsigned)std::min<uint64_t>((nsurv + 2047) / 2048, (uint64_t)ctx->num_sms * 8);
-      survivor_block_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->d_surv.as<Survivor>(), nsurv, ctx->d_qlist_mma.as<uint32_t>(), search_blocks(Q), nblk, blk_cnt, nullptr);
-      HS_TRY(read_back(ctx, blk_cnt, h_cnt, sizeof(unsigned long long) * nblk));
-      unsigned long long h_cur[kSearchBlocks], run = 0;
-      for (uint32_t c = 0; c < nblk; ++c) {
-        h_cur[c] = run;
-        run += h_cnt[c];
-      }
-      HS_TRY(upload(ctx, blk_cnt + nblk, h_cur, sizeof(unsigned long long) * nblk));
-      survivor_block_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->d_surv.as<Survivor>(), nsurv, ctx->d_qlist_mma.as<uint32_t>(), search_blocks(Q), nblk, blk_cnt + nblk, ctx->d_surv_blk.as<Survivor>());
-      HS_CUDA(cudaGetLastError());
-      ctx->stats.kernel_launches += 2;
-    }
+    HS_TRY(bin_survivors(ctx, nsurv, Q, nblk, h_cnt, ctx->surv_bins));
     HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
     uint64_t done = 0, total = 0, soff = 0;
     for (uint32_t c = 0; c < nblk; ++c) {
@@ -1117,7 +1153,16 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
   HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
   ctx->stats.n_survivors = nsurv;
-  HS_TRY(run_exact(ctx->d_surv.as<Survivor>(), nsurv, dev_cap));
+  // HS_SURV_BINS=1 regroups large lists by fragment-id block first so that the record gathers of the
+  // exact stage stay in L2 (bin_survivors).  Off: measured at bench C2 the two regrouping passes cost
+  // more (1.6 ms) than the exact stage gains (8.2 -> 7.6 ms).
+  if (nsurv >= (1u << 20) && ctx->surv_bins) {
+    unsigned long long one[kSearchBlocks];
+    HS_TRY(bin_survivors(ctx, nsurv, Q, 1, one));
+    HS_TRY(run_exact(ctx->d_surv_blk.as<Survivor>(), nsurv, dev_cap));
+  } else {
+    HS_TRY(run_exact(ctx->d_surv.as<Survivor>(), nsurv, dev_cap));
+  }
   unsigned long long nh = 0;
   HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
   HS_TRY(read_back(ctx, hit_count, &nh, sizeof nh));
@@ -1352,6 +1397,7 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->no_load_overlap = env_on("HS_NO_LOAD_OVERLAP");
   ctx->plan_stats = env_on("HS_PLAN_STATS");
   ctx->no_mma_filter = env_on("HS_NO_MMA_FILTER");
+  ctx->surv_bins = env_on("HS_SURV_BINS");
   if (const char *e = getenv("HS_SELFJOIN_CHUNK"))
     if (atoi(e) >= 256) ctx->selfjoin_chunk = (uint32_t)atoi(e);
   ctx->num_sms = prop.multiProcessorCount;
@@ -1410,6 +1456,7 @@ void hs_destroy(hs_ctx_t *ctx) {
   if (ctx->h_up) cudaFreeHost(ctx->h_up);
   ctx->d_hits_sorted_alt.release();
   ctx->d_events.release();
+  ctx->d_binctr.release();
   DevBuf *cbufs[] = {&ctx->d_cidt, &ctx->d_cidt_alt, &ctx->d_cdist, &ctx->d_cdist_alt, &ctx->d_coffsets};
   for (DevBuf *b : cbufs) b->release();
   cudaStreamDestroy(ctx->stream);

@@ -232,8 +232,11 @@ int comm_gather_start(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const uint6
   if (n) {
     // few, small thread blocks: the transfer is bound by the link, and the SMs they sit on are
     // taken from the next batch's hash / index build
-    // the senders share rank 0's ingress: the more of them, the fewer blocks each needs to fill its share
-    const unsigned want = (unsigned)std::max(4, 32 / std::max(1, G - 1));
+    // Peer stores are latency-bound per thread block (4 K hits in flight, ~40 GB/s): 16 blocks fill a
+    // sender's share of rank 0's ingress at 8 ranks (900 GB/s / 7) and 32 the whole link at 2; the
+    // blocks hold their SMs only for the length of the transfer (measured at 8 ranks with 4 blocks:
+    // 66 ms per batch, most of the next step).
+    const unsigned want = G > 4 ? 16u : 32u;
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 1023) / 1024, want);
     scatter_merged_kernel<<<grid, 256, 0, gs>>>(d_hits, n, tbits, off, ctx->d_segdst.as<uint64_t>(), info,
                                                 reinterpret_cast<hs_hit *>(ctx->recv_mapped[slot]));

@@ -161,6 +161,7 @@ struct hs_ctx {
   hs::DevBuf d_tq16, d_work_tc, d_qlist_tc;  // tensor-core filter: FP16 query tables, its work list
   hs::DevBuf d_tab16;                        // pipelined tensor filter: FP16 embedding rows + row norms
   hs::DevBuf d_qb16, d_mma_items, d_mma_units, d_mma_cta, d_qlist_mma;
+  hs::DevBuf d_binctr;                       // survivor regrouping: per-bin counts and cursors
   hs::DevBuf d_events;                       // pipelined tensor filter: staged threshold events (filter_mma.cu)
   int num_sms = 0;
   uint64_t hit_qmax = 0;   // query ids of the current call are < hit_qmax (hit sort key width)
@@ -198,6 +199,7 @@ struct hs_ctx {
   bool no_load_overlap = false;  // HS_NO_LOAD_OVERLAP: hs_load_fragments copies first, hashes later
   bool plan_stats = false;       // HS_PLAN_STATS: print the filter work-list statistics
   uint32_t selfjoin_chunk = 1u << 16;  // HS_SELFJOIN_CHUNK: query members per tensor-filter pass of a large bucket (hs_cluster)
+  bool surv_bins = false;        // HS_SURV_BINS: survivors regrouped by fragment-id block before the exact stage
   bool no_mma_filter = false;    // HS_NO_MMA_FILTER: keep the Euclidean metric off the pipelined tensor filter
 
   hs_stats stats{};
