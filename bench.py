@@ -281,7 +281,32 @@ def run_native(a):
         acc["kernel_launches"] = acc.get("kernel_launches", 0) + s["kernel_launches"]
         return s
 
+    trace = {"hash": 0.0, "build": 0.0, "search": 0.0, "search_dev_ms": 0.0, "sort": 0.0, "group": 0.0, "permute": 0.0,
+             "filter": 0.0, "exact": 0.0, "hitsort": 0.0} if os.environ.get("HS_BENCH_TRACE") else None
+
     def step(collect):
+        if trace is not None and collect:
+            t_a = time.perf_counter()
+            h.hash()
+            t_b = time.perf_counter()
+            h.build_index()
+            t_c = time.perf_counter()
+            sb_ = h.stats().as_dict()
+            for k_ in ("sort", "group", "permute"):
+                trace[k_] += sb_["ms_" + k_]
+            t_c = time.perf_counter()
+            n = h.search_points_dev(qpts.data_ptr(), Q, hits_bufs[0].data_ptr(), cap)
+            t_d = time.perf_counter()
+            ss_ = h.stats().as_dict()
+            for k_ in ("filter", "exact", "hitsort"):
+                trace[k_] += ss_["ms_" + k_]
+            trace["hash"] += 1e3 * (t_b - t_a)
+            trace["build"] += 1e3 * (t_c - t_b)
+            trace["search"] += 1e3 * (t_d - t_c)
+            trace["search_dev_ms"] += h.stats().as_dict()["ms_total"]
+            step_no[0] += 1
+            s0 = h.stats().as_dict()
+            return n, n, s0, s0, s0
         h.hash()
         s_hash = add_stats(["ms_hash"]) if collect else h.stats().as_dict()
         h.build_index()
@@ -328,6 +353,15 @@ def run_native(a):
             dist.barrier()
         clocks = sampler.stop(wall0, wall1)
     dev_ms = e0.elapsed_time(e1)
+    if trace is not None:
+        print("[trace] rank %d per step: hash %.2f build %.2f (sort %.2f group %.2f permute %.2f) search %.2f (filter %.2f exact %.2f "
+              "hitsort %.2f; device total %.2f) ms; step %.2f" %
+              (rank, trace["hash"] / a.steps, trace["build"] / a.steps, trace["sort"] / a.steps, trace["group"] / a.steps,
+               trace["permute"] / a.steps, trace["search"] / a.steps, trace["filter"] / a.steps, trace["exact"] / a.steps,
+               trace["hitsort"] / a.steps, trace["search_dev_ms"] / a.steps, dev_ms / a.steps), file=sys.stderr, flush=True)
+        if world > 1:
+            dist.barrier()
+        raise SystemExit(0)
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -24,6 +24,7 @@ int extract_windows_impl(hs_ctx *ctx, const uint8_t *residues, const uint32_t *s
                          uint32_t stride, uint64_t id_base, uint32_t *pos_out, uint64_t pos_cap, uint64_t *nfrag);
 int comm_gather_start(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const uint64_t *d_keys, int tshift, uint32_t Q,
                       bool local_overflow);
+int comm_gather_flush(hs_ctx *ctx);
 int comm_broadcast(hs_ctx *ctx, void *d_buf, size_t bytes);
 void comm_destroy(hs_ctx *ctx);
 
@@ -222,6 +223,8 @@ int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t
     fa.surv_count = cnt;
     HS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
     HS_CUDA(cudaMemsetAsync(cnt + 7, 0, sizeof(unsigned long long), ctx->stream));
+    // the previous search's hit merge (multi-GPU) starts its bulk transfer now, beside this filter (comm.cu)
+    if (ctx->nranks > 1) HS_TRY(comm_gather_flush(ctx));
     HS_TRY(launch_filter(ctx, fa, nblocks, mode));
     if (fa_tc && nblocks_tc) {
       fa_tc->surv = fa.surv;

@@ -148,37 +148,50 @@ seg_dest_kernel(const uint32_t *__restrict__ cnt_all /* [G][S] */, uint32_t S, i
 }
 
 // Every hit of the local sorted list goes to its final position of the merged list (rank 0's
-// memory, mapped here).  Consecutive threads take consecutive hits, which inside a segment land
-// on consecutive 24-byte records, so the peer stores coalesce into full lines on the NVLink;
-// four hits per thread are loaded before the first is stored (the kernel runs with few thread
-// blocks -- it is bound by the link, not by the SMs it takes from the next batch's kernels).
-constexpr int kScatterUnroll = 4;
-__global__ void __launch_bounds__(256)
+// memory, mapped here).  A warp takes 32 consecutive hits; inside a segment they land on 32
+// consecutive 24-byte records, i.e. 96 consecutive 8-byte words: the warp transposes them through
+// shared memory and writes three fully contiguous 256-byte rows (well-formed NVLink packets; a hit
+// per lane would be 8-byte pieces at a 24-byte stride).  Warps that straddle a segment boundary
+// write hit by hit.  Streaming (evict-first) loads: the list is read once.  Few thread blocks: the
+// transfer is bound by the link, not by the SMs.
+constexpr int kScatterWarps = 8;
+__global__ void __launch_bounds__(kScatterWarps * 32, 8)
 scatter_merged_kernel(const hs_hit *__restrict__ hits, uint64_t n, int tbits, const uint64_t *__restrict__ off,
                       const uint64_t *__restrict__ dst, const unsigned long long *__restrict__ info,
                       hs_hit *__restrict__ out) {
   if (info[1]) return;  // receive buffer too small: reported by hs_comm_result
-  const uint64_t tile = (uint64_t)blockDim.x * kScatterUnroll;
-  for (uint64_t t0 = (uint64_t)blockIdx.x * tile; t0 < n; t0 += (uint64_t)gridDim.x * tile) {
-    hs_hit h[kScatterUnroll];
-    uint64_t pos[kScatterUnroll];
-#pragma unroll
-    for (int j = 0; j < kScatterUnroll; ++j) {
-      const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
-      if (i < n) h[j] = hits[i];
+  __shared__ unsigned long long s_w[kScatterWarps][96];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint64_t nwarps = (uint64_t)gridDim.x * kScatterWarps;
+  for (uint64_t i0 = ((uint64_t)blockIdx.x * kScatterWarps + wid) * 32; i0 < n; i0 += nwarps * 32) {
+    const uint64_t i = i0 + lane;
+    unsigned long long w0 = 0, w1 = 0, w2 = 0;
+    uint64_t pos = 0;
+    if (i < n) {
+      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(hits + i);
+      w0 = __ldcs(src);      // query | table_first << 32
+      w1 = __ldcs(src + 1);  // db id
+      w2 = __ldcs(src + 2);  // dist2
+      const uint64_t s = ((w0 & 0xffffffffull) << tbits) | (w0 >> 32);
+      pos = __ldg(dst + s) + (i - __ldg(off + s));
     }
-#pragma unroll
-    for (int j = 0; j < kScatterUnroll; ++j) {
-      const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
-      if (i < n) {
-        const uint64_t s = ((uint64_t)h[j].query << tbits) | (uint64_t)h[j].table_first;
-        pos[j] = __ldg(dst + s) + (i - __ldg(off + s));
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kScatterUnroll; ++j) {
-      const uint64_t i = t0 + (uint64_t)j * blockDim.x + threadIdx.x;
-      if (i < n) out[pos[j]] = h[j];
+    const uint64_t pos0 = __shfl_sync(0xffffffffu, pos, 0);
+    const bool run = __all_sync(0xffffffffu, i < n && pos == pos0 + (uint64_t)lane);
+    if (run) {
+      s_w[wid][3 * lane + 0] = w0;
+      s_w[wid][3 * lane + 1] = w1;
+      s_w[wid][3 * lane + 2] = w2;
+      __syncwarp();
+      unsigned long long *o = reinterpret_cast<unsigned long long *>(out + pos0);
+      o[lane] = s_w[wid][lane];
+      o[32 + lane] = s_w[wid][32 + lane];
+      o[64 + lane] = s_w[wid][64 + lane];
+      __syncwarp();
+    } else if (i < n) {
+      unsigned long long *o = reinterpret_cast<unsigned long long *>(out + pos);
+      o[0] = w0;
+      o[1] = w1;
+      o[2] = w2;
     }
   }
 }
@@ -194,9 +207,11 @@ static int bits_for(uint64_t nvalues) {
 // reference order, keys = their sorted one-word keys (query | table | id; the table field starts
 // at bit tshift).  Segment offsets are taken from the keys now (the sort scratch is reused by
 // whatever runs next); the rest runs on the gather stream.
+int comm_gather_flush(hs_ctx *ctx);
 int comm_gather_start(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const uint64_t *d_keys, int tshift, uint32_t Q,
                       bool local_overflow) {
   const int G = ctx->nranks;
+  HS_TRY(comm_gather_flush(ctx));   // (an older transfer no filter launch has picked up)
   if (!ctx->recv_cap) {
     set_error("hs_search on a context that joined a communicator: call hs_comm_reserve first");
     return HS_ERR_INVALID;
@@ -229,36 +244,60 @@ int comm_gather_start(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const uint6
   }
   seg_dest_kernel<<<1, kDestThreads, 0, gs>>>(ctx->d_segcnt_all.as<uint32_t>(), S, G, ctx->rank, ctx->recv_cap,
                                               ctx->d_segdst.as<uint64_t>(), info);
-  if (n) {
-    // few, small thread blocks: the transfer is bound by the link, and the SMs they sit on are
-    // taken from the next batch's hash / index build
-    // Peer stores are latency-bound per thread block (4 K hits in flight, ~40 GB/s): 16 blocks fill a
-    // sender's share of rank 0's ingress at 8 ranks (900 GB/s / 7) and 32 the whole link at 2; the
-    // blocks hold their SMs only for the length of the transfer (measured at 8 ranks with 4 blocks:
-    // 66 ms per batch, most of the next step).
-    const unsigned want = G > 4 ? 16u : 32u;
-    const unsigned grid = (unsigned)std::min<uint64_t>((n + 1023) / 1024, want);
-    scatter_merged_kernel<<<grid, 256, 0, gs>>>(d_hits, n, tbits, off, ctx->d_segdst.as<uint64_t>(), info,
-                                                reinterpret_cast<hs_hit *>(ctx->recv_mapped[slot]));
-  }
   HS_CUDA(cudaGetLastError());
-  // every rank's stores have left its GPU when its kernel has ended; the all-reduce that follows in
-  // stream order is the barrier after which rank 0 may read the merged list
-  // (its value counts the ranks whose own hit buffer overflowed: their lists are missing)
-  ctx->h_gather_flag[slot] = local_overflow ? 1ull : 0ull;
-  HS_CUDA(cudaMemcpyAsync(ctx->d_gather_info.as<unsigned long long>() + 4, &ctx->h_gather_flag[slot], sizeof(unsigned long long),
-                          cudaMemcpyHostToDevice, gs));
-  HS_NCCL(g_nccl.AllReduce(ctx->d_gather_info.as<unsigned long long>() + 4, ctx->d_gather_info.as<unsigned long long>() + 5,
-                           1, ncclUint64, ncclSum, comm, gs));
-  HS_CUDA(cudaEventRecord(ctx->ev_gather[slot], gs));
+  // The bulk transfer is deferred to the next search's filter launch (comm_gather_flush): while a
+  // sender pushes into rank 0's congested link its own memory-bound kernels crawl (measured at 8
+  // ranks: the next batch's rank sort 6.8 -> 15.6 ms, bucket grouping 0.4 -> 3.3 ms), whereas the
+  // tensor filter barely touches HBM and hides the transfer.  hs_comm_result flushes it too.
+  ctx->gather_def.pending = true;
+  ctx->gather_def.hits = d_hits;
+  ctx->gather_def.n = n;
+  ctx->gather_def.tbits = tbits;
+  ctx->gather_def.slot = slot;
+  ctx->gather_def.overflow = local_overflow;
   ctx->stats.kernel_launches += 3;
   ctx->gather_seq++;
   ctx->gather_pending = true;
   return HS_OK;
 }
 
+// Starts the deferred bulk transfer of the latest gather (no-op when there is none).
+int comm_gather_flush(hs_ctx *ctx) {
+  if (!ctx->gather_def.pending) return HS_OK;
+  ctx->gather_def.pending = false;
+  const int G = ctx->nranks, slot = ctx->gather_def.slot;
+  const uint64_t n = ctx->gather_def.n;
+  cudaStream_t gs = ctx->gather_stream;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm2;
+  unsigned long long *info = ctx->d_gather_info.as<unsigned long long>() + 2 * slot;
+  if (n) {
+    // Peer stores are latency-bound per thread block (4 K hits in flight, ~40 GB/s), and the senders
+    // share rank 0's ingress (900 GB/s): as many blocks as fill this sender's share, no more -- the
+    // blocks start before the filter's and keep their SMs from it for the length of the transfer.
+    const unsigned want = (unsigned)std::min(32, std::max(4, 900 / (39 * std::max(1, G - 1)) + 1));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, want);
+    scatter_merged_kernel<<<grid, kScatterWarps * 32, 0, gs>>>(ctx->gather_def.hits, n, ctx->gather_def.tbits, ctx->d_segoff[slot].as<uint64_t>(),
+                                                ctx->d_segdst.as<uint64_t>(), info,
+                                                reinterpret_cast<hs_hit *>(ctx->recv_mapped[slot]));
+  }
+  HS_CUDA(cudaGetLastError());
+  // every rank's stores have left its GPU when its kernel has ended; the all-reduce that follows in
+  // stream order is the barrier after which rank 0 may read the merged list
+  // (its value counts the ranks whose own hit buffer overflowed: their lists are missing)
+  ctx->h_gather_flag[slot] = ctx->gather_def.overflow ? 1ull : 0ull;
+  HS_CUDA(cudaMemcpyAsync(ctx->d_gather_info.as<unsigned long long>() + 4, &ctx->h_gather_flag[slot], sizeof(unsigned long long),
+                          cudaMemcpyHostToDevice, gs));
+  HS_NCCL(g_nccl.AllReduce(ctx->d_gather_info.as<unsigned long long>() + 4, ctx->d_gather_info.as<unsigned long long>() + 5,
+                           1, ncclUint64, ncclSum, comm, gs));
+  HS_CUDA(cudaEventRecord(ctx->ev_gather[slot], gs));
+  return HS_OK;
+}
+
 void comm_destroy(hs_ctx *ctx) {
-  if (ctx->gather_stream) cudaStreamSynchronize(ctx->gather_stream);
+  if (ctx->gather_stream) {
+    comm_gather_flush(ctx);
+    cudaStreamSynchronize(ctx->gather_stream);
+  }
   for (int i = 0; i < 2; ++i) {
     if (ctx->recv_mapped[i] && ctx->recv_mapped[i] != ctx->recv_local[i]) cudaIpcCloseMemHandle(ctx->recv_mapped[i]);
     if (ctx->recv_local[i]) cudaFree(ctx->recv_local[i]);
@@ -347,7 +386,10 @@ int hs_comm_init(hs_ctx_t *ctx, const void *nccl_unique_id, int rank, int nranks
     return HS_ERR_COMM;
   }
   ctx->nccl_comm2 = comm2;
-  HS_CUDA(cudaStreamCreateWithFlags(&ctx->gather_stream, cudaStreamNonBlocking));
+  // lowest priority: where the merge's blocks and the next batch's kernels both wait for an SM, the batch goes first
+  int prio_lo = 0, prio_hi = 0;
+  HS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  HS_CUDA(cudaStreamCreateWithPriority(&ctx->gather_stream, cudaStreamNonBlocking, prio_lo));
   for (int i = 0; i < 2; ++i) HS_CUDA(cudaEventCreateWithFlags(&ctx->ev_gather[i], cudaEventDisableTiming));
   HS_CUDA(cudaEventCreateWithFlags(&ctx->ev_gather_in, cudaEventDisableTiming));
   return HS_OK;
@@ -420,6 +462,7 @@ int hs_comm_result(hs_ctx_t *ctx, const void **hits_dev, uint64_t *nhits_total) 
     return HS_ERR_INVALID;
   }
   HS_CUDA(cudaSetDevice(ctx->device));
+  HS_TRY(comm_gather_flush(ctx));
   const int slot = (int)((ctx->gather_seq - 1) & 1u);
   unsigned long long info[2] = {0, 0}, lost = 0;
   HS_CUDA(cudaMemcpyAsync(info, ctx->d_gather_info.as<unsigned long long>() + 2 * slot, sizeof info, cudaMemcpyDeviceToHost,

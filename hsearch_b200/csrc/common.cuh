@@ -192,6 +192,12 @@ struct hs_ctx {
   uint32_t gather_seq = 0;      // gathers started so far (slot = seq & 1)
   bool gather_pending = false;
   unsigned long long h_gather_flag[2] = {0, 0};
+  struct {                      // bulk transfer of the latest gather, started by the next filter launch
+    bool pending = false, overflow = false;
+    const hs_hit *hits = nullptr;
+    uint64_t n = 0;
+    int tbits = 0, slot = 0;
+  } gather_def;
   hs::DevBuf d_segoff[2], d_segcnt, d_segcnt_all, d_segdst, d_gather_info;
 
   // debugging switches, read from the environment once in hs_create
