@@ -180,7 +180,11 @@ def run_reference(a):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(a), "sample": last["sample"]},
+           "config": {"workload": workload_name(a), "sample": last["sample"],
+                      "note": ("the reference holds 8*len doubles per fragment (640 B) and cannot hold the workload's database: "
+                               "every host core runs the reference's own Search() on a %d-fragment shard against all queries; "
+                               "its per-query memset of 4 bytes per fragment (motif_both_points.cpp:225) is nearly free at this "
+                               "size, so the ratio against this arm is a conservative extrapolation" % n_sample)},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
                             "sample": last["sample"]},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -553,7 +557,7 @@ def run_native(a):
         "radix_downsweep_kernel": {"ms": acc["ms_sort_downsweep"] / steps, "bytes": down_bytes, "launches": passes},
         "radix_upsweep_kernel": {"ms": acc["ms_sort_upsweep"] / steps, "bytes": up_bytes, "launches": passes},
         "bucket_grouping": {"ms": acc["ms_group"] / steps, "bytes": group_bytes, "launches": a.L},
-        "permute_rec_kernel": {"ms": acc["ms_permute"] / steps, "bytes": permute_bytes, "launches": a.L},
+        "gather_blocked_kernel": {"ms": acc["ms_permute"] / steps, "bytes": permute_bytes, "launches": 1},
         "filter_kernel": {"ms": (acc["ms_filter"] - acc["ms_filter_tc"]) / steps,
                           "bytes": (ncand - ncand_tc) * (length + 4) + nsurv * 16, "launches": 1},
         # tensor-core candidate filter (Euclidean metric: filter_mma_kernel): algorithmic flops =
@@ -588,9 +592,9 @@ def run_native(a):
                     "algorithmic_flops_per_launch": d["flops"] / max(1, d["launches"]),
                     "avg_launch_ms": d["ms"] / max(1, d["launches"]), "share_of_step": d["share_of_step"],
                     "note": ("tcgen05 FP16 contraction <x_m, q> over every (query, bucket member) pair, 2*8*len flops "
-                             "per pair; per-role cycle counters (profiles/) show the MMA pipe busy ~31% of the kernel: "
-                             "TMEM reads of the epilogue and the MMA's accumulator updates contend, so the two "
-                             "overlap poorly; DRAM traffic is ~len bytes per member per item")}
+                             "per pair; ablations (profiles/r02_filter_experiments.md): MMAs 4 ms, TMEM loads 2 ms, scan 9 ms, "
+                             "barrier traffic between the 22 warps 17 ms of the 35 ms launch; 21 G warp instructions, issue slots "
+                             "57 % busy: bound by instruction issue, not by the tensor pipe")}
     else:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": d["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
@@ -724,13 +728,19 @@ def run_native(a):
                                      "stores over NVLink) on a second stream beside the next batch's hash + index build; all "
                                      "merges complete before the timed region ends")
                       if world > 1 else "single rank",
-                      "l2": "inputs (>= 1 GB codes, multi-GB keys) exceed the 126 MB L2; no flush needed"},
+                      "l2": "inputs (>= 1 GB codes, multi-GB keys) exceed the 126 MB L2; no flush needed",
+                      "reference_arm": ("--impl reference runs the reference's own Search() on one 10,000-fragment shard per host "
+                                        "core against all queries (it stores 640 B per fragment and cannot hold this database); "
+                                        "the ratio of the two arms is therefore an extrapolation, and a conservative one")},
            "clocks": clocks, "wall_ms_per_step": wall_ms / a.steps,
            "e2e": e2e, "gpu_launches": int(acc["kernel_launches"]),
            "roofline": roofline, "cpu_baseline": cpu,
            "checks": checks, "multi_gpu_checks": multi, "recall": recall,
            "stages_ms": {k[3:]: round(acc[k] / steps, 4) for k in sorted(acc) if k.startswith("ms_")},
-           "kernels": {k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "share": round(v["share_of_step"], 4)}
+           # gbs = algorithmic bytes / time; for the two filter kernels that figure is nominal (a bucket tile is
+           # streamed once for all its queries: the tensor filter's bound is flops, see `roofline`), so it is omitted
+           "kernels": {k: ({"ms": round(v["ms"], 4), "share": round(v["share_of_step"], 4)} if k.startswith("filter") else
+                           {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "share": round(v["share_of_step"], 4)})
                        for k, v in kern.items()},
            "counts": {"candidates": int(ncand), "survivors": int(nsurv), "hits_rank0": int(nh),
                       "hits_total": int(nh_total), "query_frags_per_s": Q / ((acc["ms_qhash"] + acc["ms_probe"] +

@@ -155,7 +155,7 @@ seg_dest_kernel(const uint32_t *__restrict__ cnt_all /* [G][S] */, uint32_t S, i
 // write hit by hit.  Streaming (evict-first) loads: the list is read once.  Few thread blocks: the
 // transfer is bound by the link, not by the SMs.
 constexpr int kScatterWarps = 8;
-__global__ void __launch_bounds__(kScatterWarps * 32, 8)
+__global__ void __launch_bounds__(kScatterWarps * 32, 4)
 scatter_merged_kernel(const hs_hit *__restrict__ hits, uint64_t n, int tbits, const uint64_t *__restrict__ off,
                       const uint64_t *__restrict__ dst, const unsigned long long *__restrict__ info,
                       hs_hit *__restrict__ out) {
@@ -163,35 +163,51 @@ scatter_merged_kernel(const hs_hit *__restrict__ hits, uint64_t n, int tbits, co
   __shared__ unsigned long long s_w[kScatterWarps][96];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint64_t nwarps = (uint64_t)gridDim.x * kScatterWarps;
-  for (uint64_t i0 = ((uint64_t)blockIdx.x * kScatterWarps + wid) * 32; i0 < n; i0 += nwarps * 32) {
-    const uint64_t i = i0 + lane;
-    unsigned long long w0 = 0, w1 = 0, w2 = 0;
-    uint64_t pos = 0;
-    if (i < n) {
-      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(hits + i);
-      w0 = __ldcs(src);      // query | table_first << 32
-      w1 = __ldcs(src + 1);  // db id
-      w2 = __ldcs(src + 2);  // dist2
-      const uint64_t s = ((w0 & 0xffffffffull) << tbits) | (w0 >> 32);
-      pos = __ldg(dst + s) + (i - __ldg(off + s));
+  constexpr int U = 4;  // groups of 32 hits per warp and iteration: their loads are all in flight before the first store
+  for (uint64_t i0 = ((uint64_t)blockIdx.x * kScatterWarps + wid) * (32 * U); i0 < n; i0 += nwarps * (32 * U)) {
+    unsigned long long w0[U], w1[U], w2[U];
+    uint64_t pos[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * 32 + lane;
+      w0[u] = w1[u] = w2[u] = 0ull;
+      if (i < n) {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(hits + i);
+        w0[u] = __ldcs(src);      // query | table_first << 32
+        w1[u] = __ldcs(src + 1);  // db id
+        w2[u] = __ldcs(src + 2);  // dist2
+      }
     }
-    const uint64_t pos0 = __shfl_sync(0xffffffffu, pos, 0);
-    const bool run = __all_sync(0xffffffffu, i < n && pos == pos0 + (uint64_t)lane);
-    if (run) {
-      s_w[wid][3 * lane + 0] = w0;
-      s_w[wid][3 * lane + 1] = w1;
-      s_w[wid][3 * lane + 2] = w2;
-      __syncwarp();
-      unsigned long long *o = reinterpret_cast<unsigned long long *>(out + pos0);
-      o[lane] = s_w[wid][lane];
-      o[32 + lane] = s_w[wid][32 + lane];
-      o[64 + lane] = s_w[wid][64 + lane];
-      __syncwarp();
-    } else if (i < n) {
-      unsigned long long *o = reinterpret_cast<unsigned long long *>(out + pos);
-      o[0] = w0;
-      o[1] = w1;
-      o[2] = w2;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * 32 + lane;
+      pos[u] = 0;
+      if (i < n) {
+        const uint64_t s = ((w0[u] & 0xffffffffull) << tbits) | (w0[u] >> 32);
+        pos[u] = __ldg(dst + s) + (i - __ldg(off + s));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * 32 + lane;
+      const uint64_t pos0 = __shfl_sync(0xffffffffu, pos[u], 0);
+      const bool run = __all_sync(0xffffffffu, i < n && pos[u] == pos0 + (uint64_t)lane);
+      if (run) {
+        s_w[wid][3 * lane + 0] = w0[u];
+        s_w[wid][3 * lane + 1] = w1[u];
+        s_w[wid][3 * lane + 2] = w2[u];
+        __syncwarp();
+        unsigned long long *o = reinterpret_cast<unsigned long long *>(out + pos0);
+        o[lane] = s_w[wid][lane];
+        o[32 + lane] = s_w[wid][32 + lane];
+        o[64 + lane] = s_w[wid][64 + lane];
+        __syncwarp();
+      } else if (i < n) {
+        unsigned long long *o = reinterpret_cast<unsigned long long *>(out + pos[u]);
+        o[0] = w0[u];
+        o[1] = w1[u];
+        o[2] = w2[u];
+      }
     }
   }
 }
@@ -275,7 +291,7 @@ int comm_gather_flush(hs_ctx *ctx) {
     // share rank 0's ingress (900 GB/s): as many blocks as fill this sender's share, no more -- the
     // blocks start before the filter's and keep their SMs from it for the length of the transfer.
     const unsigned want = (unsigned)std::min(32, std::max(4, 900 / (39 * std::max(1, G - 1)) + 1));
-    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, want);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 1023) / 1024, want);
     scatter_merged_kernel<<<grid, kScatterWarps * 32, 0, gs>>>(ctx->gather_def.hits, n, ctx->gather_def.tbits, ctx->d_segoff[slot].as<uint64_t>(),
                                                 ctx->d_segdst.as<uint64_t>(), info,
                                                 reinterpret_cast<hs_hit *>(ctx->recv_mapped[slot]));

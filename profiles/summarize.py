@@ -22,7 +22,12 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size", "lts__t_bytes.sum"]
+        "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size", "lts__t_bytes.sum",
+        # tensor pipe activity (whatever of these the sm_100 ncu exposes)
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.sum",
+        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_uniform.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tmem.sum", "smsp__inst_executed_pipe_tmem.sum"]
 
 
 def launches(tag):
@@ -64,13 +69,54 @@ def full(tag):
             if w in hdr:
                 i = hdr.index(w)
                 d[w] = f"{vals[i]} {units[i]}".strip()
+        for i, name_i in enumerate(hdr):   # every tensor-pipe / TMEM metric the capture holds
+            if ("tensor" in name_i or "tmem" in name_i) and name_i not in d and i < len(vals):
+                d[name_i] = f"{vals[i]} {units[i]}".strip()
         out[name] = d
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full.json"), "w") as f:
         json.dump(out, f, indent=1)
+    # DRAM bytes (read + write) per launch of every captured kernel: bench.py copies the dominant
+    # kernel's entry into roofline.traffic
+    traffic = {}
+    for k, d in out.items():
+        def gb(x):
+            v, u = x.split()[:2]
+            return float(v.replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+        if "dram__bytes_read.sum" in d and "dram__bytes_write.sum" in d:
+            traffic[k] = gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
+    if traffic:
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
     return out
+
+
+def sass_histogram(tag):
+    """Opcode histogram of the dominant kernel's SASS (cuobjdump of the built library, no GPU needed)."""
+    lib = os.path.join(ROOT, "hsearch_b200", "libhsearch_b200.so")
+    fun = "_ZN2hs17filter_mma_kernelILi10EEEvNS_7MmaArgsE"
+    txt = subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], capture_output=True, text=True).stdout
+    hist = collections.Counter()
+    for line in txt.splitlines():
+        parts = line.split("*/")
+        if len(parts) < 2 or "/*" not in parts[0]:
+            continue
+        ins = parts[1].strip().split(";")[0].split()
+        if not ins:
+            continue
+        op = ins[1] if ins[0].startswith("@") and len(ins) > 1 else ins[0]
+        hist[op.split(".")[0]] += 1
+    if not hist:
+        return
+    with open(os.path.join(ROOT, "profiles", f"{tag}_filter_sass_histogram.md"), "w") as f:
+        f.write(f"# {tag}: SASS opcode histogram of `filter_mma_kernel<10>` (cuobjdump -sass of libhsearch_b200.so)\n\n"
+                f"{sum(hist.values())} instructions.  UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, "
+                "UBLKCP = cp.async.bulk (TMA engine), SYNCS = mbarrier operations.\n\n| opcode | count |\n|---|---:|\n")
+        for op, n in hist.most_common():
+            f.write(f"| `{op}` | {n} |\n")
 
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     launches(tag)
+    sass_histogram(tag)
     print(json.dumps(full(tag), indent=1)[:400])
