@@ -30,6 +30,15 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_tmem.sum", "smsp__inst_executed_pipe_tmem.sum"]
 
 
+TENSOR = ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+          "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+          "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+          "sm__ops_path_tensor_src_fp16_dst_fp32.sum", "sm__ops_path_tensor_src_fp16_dst_fp32.sum.pct_of_peak_sustained_elapsed",
+          "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum",
+          "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+          "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active"]
+
+
 def launches(tag):
     path = os.path.join(ROOT, "gpurun_out", "launches.csv")
     if not os.path.exists(path):
@@ -48,7 +57,7 @@ def launches(tag):
         tot += v
     with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none)\n\n"
-                "Command: see profiles/r01_ncu_commands.sh.  Times are cold-cache and serialised: compare SHARES.\n\n"
+                "Command: see profiles/{tag[:3]}_ncu_commands.sh.  Times are cold-cache and serialised: compare SHARES.\n\n"
                 f"total {tot:.1f} ms over {sum(a[0] for a in agg.values())} launches\n\n"
                 "| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -69,8 +78,8 @@ def full(tag):
             if w in hdr:
                 i = hdr.index(w)
                 d[w] = f"{vals[i]} {units[i]}".strip()
-        for i, name_i in enumerate(hdr):   # every tensor-pipe / TMEM metric the capture holds
-            if ("tensor" in name_i or "tmem" in name_i) and name_i not in d and i < len(vals):
+        for i, name_i in enumerate(hdr):   # tensor-pipe / TMEM activity
+            if name_i in TENSOR and i < len(vals) and vals[i] not in ("0", ""):
                 d[name_i] = f"{vals[i]} {units[i]}".strip()
         out[name] = d
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full.json"), "w") as f:
