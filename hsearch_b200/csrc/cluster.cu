@@ -34,20 +34,21 @@ __global__ void small_bucket_pairs_kernel(const uint32_t *__restrict__ bstart, u
                                           Survivor *__restrict__ surv, unsigned long long surv_cap,
                                           unsigned long long *__restrict__ surv_count,
                                           uint2 *__restrict__ large, unsigned int *__restrict__ nlarge,
-                                          unsigned long long *__restrict__ npairs) {
+                                          unsigned long long *__restrict__ npairs, uint32_t part, uint32_t nparts) {
   const uint64_t b = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= nb) return;
   const uint32_t s = bstart[b], e = bstart[b + 1];
   const uint32_t n = e - s;
   if (n < 2) return;
-  if (n > kSmallBucket) {
+  if (n > kSmallBucket) {   // (every part collects all large buckets and takes its share of them later)
     if (lane == 0) {
       const unsigned int i = atomicAdd(nlarge, 1u);
       large[i] = make_uint2(s, e);
     }
     return;
   }
+  if (b % nparts != part) return;  // pair work split over the ranks of a communicator (replicated DB)
   const uint32_t np = n * (n - 1) / 2;
   if (lane == 0) atomicAdd(npairs, (unsigned long long)np);
   for (uint32_t p = lane; p < np; p += 32) {
@@ -87,9 +88,28 @@ __global__ void uf_flatten_kernel(const uint32_t *__restrict__ parent, uint64_t 
   label[i] = x;
 }
 
+// Labels of the other ranks' partial clusterings (each: smallest id of the fragment's component under
+// that rank's share of the pairs) united into this rank's forest.
+__global__ void uf_merge_labels_kernel(uint32_t *__restrict__ parent, const uint32_t *__restrict__ labels, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t l = labels[i];
+  if (l != (uint32_t)i) uf_union(parent, (uint32_t)i, l);
+}
+
+int comm_allgather_u32(hs_ctx *ctx, const uint32_t *d_send, uint32_t *d_recv, uint64_t n);
+
+// On a context that joined a communicator every rank holds the SAME database and index, and the
+// pair work -- what the run time consists of: 2.4e14 pairs at 50 M fragments -- is split: small and
+// medium buckets by bucket number, the query chunks of the large buckets round-robin.  Each rank
+// unites the edges of its share; the flattened labels (4 bytes per fragment and rank) are
+// all-gathered with NCCL and every rank unites the others' labels into its forest: all ranks end
+// with the labels of the complete edge set.  No bucket, key or code leaves its GPU.
 int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
   const uint64_t N = ctx->N;
   const uint32_t L = ctx->prm.L;
+  const uint32_t nparts = ctx->nranks > 1 ? (uint32_t)ctx->nranks : 1u, part = ctx->nranks > 1 ? (uint32_t)ctx->rank : 0u;
+  uint64_t work_no = 0;   // large-bucket chunks and medium buckets, numbered alike on every rank
   stats_begin(ctx);
   if (N == 0) return HS_OK;
   cudaEvent_t *ev = ctx->ev;
@@ -125,7 +145,7 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
       small_bucket_pairs_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
           T.bstart.as<uint32_t>(), T.nslots, l, T.codes_sorted.as<uint8_t>(), ctx->npad, (int)ctx->prm.len, pair32, thr,
           ctx->d_surv.as<Survivor>(), ctx->d_surv.cap / sizeof(Survivor), scnt, ctx->d_large.as<uint2>(), nlarge,
-          npairs);
+          npairs, part, nparts);
       HS_CUDA(cudaGetLastError());
       ctx->stats.kernel_launches++;
       HS_CUDA(cudaMemcpyAsync(&h_cnt, scnt, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
@@ -170,16 +190,23 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
           // whatever the bucket size (50 M fragments: buckets of millions of members)
           // The last kSelfJoinTail members pair among themselves on the scalar self-join (too few
           // members are left after them for a tensor tile); every tensor chunk keeps >= 1024 queries.
-          bool used = bk.y - bk.x >= 4 * kSelfJoinTail;
+          bool used = bk.y - bk.x >= 4 * kSelfJoinTail && selfjoin_uses_mma(ctx, bk.y - bk.x);
           const uint32_t chunk = std::max<uint32_t>(ctx->selfjoin_chunk, 1024u);
           const uint32_t tail_lo = bk.y - kSelfJoinTail;
           for (uint32_t q_lo = bk.x; used && q_lo < tail_lo;) {
             uint32_t q_hi = (uint32_t)std::min<uint64_t>((uint64_t)q_lo + chunk, tail_lo);
             if (tail_lo - q_hi < 1024u) q_hi = tail_lo;
+            if ((work_no++ % nparts) != part) {   // another rank's chunk
+              q_lo = q_hi;
+              continue;
+            }
             uint64_t nsurv = 0, np = 0;
             HS_CUDA(cudaEventRecord(ev[4], ctx->stream));
             HS_TRY(selfjoin_bucket_mma(ctx, l, bk.x, bk.y, q_lo, q_hi, &nsurv, &np, &used));
-            if (!used) break;   // (decided by the first chunk: tensor path not available)
+            if (!used) {
+              set_error("hs_cluster: the tensor self-join refused a bucket it had accepted");
+              return HS_ERR_UNSUPPORTED;
+            }
             HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
             ncand += np;
             ctx->stats.n_candidates_tc += np;
@@ -207,6 +234,7 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
         // batch buckets until the block budget is reached
         for (; bi < large.size(); ++bi) {
           const uint32_t ms = large[bi].x, me = large[bi].y;
+          if (((work_no + bi) % nparts) != part) continue;   // another rank's bucket
           uint64_t need = 0;
           for (uint32_t qb = ms; qb + 1 < me; qb += kQueriesPerItem)
             need += ((uint64_t)me - ((qb + 1) & ~3u) + kFilterTile - 1) / kFilterTile;
@@ -253,6 +281,7 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
         ms_f2 += ev_ms(ev[4], ev[5]);
         ms_e2 += ev_ms(ev[5], ev[6]);
       }
+      work_no += large.size();
     }
     HS_CUDA(cudaEventSynchronize(ev[3]));
     ms_filter += ev_ms(ev[1], ev[2]) + ms_f2;
@@ -262,6 +291,20 @@ int cluster_impl(hs_ctx *ctx, uint32_t *label_out) {
   uf_flatten_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(parent, N, label);
   ctx->stats.kernel_launches++;
   HS_CUDA(cudaGetLastError());
+  if (nparts > 1) {
+    // the exchange step: every rank's labels to every rank, united into the local forest
+    HS_TRY(ctx->d_misc.reserve(sizeof(uint32_t) * (size_t)N * nparts));
+    uint32_t *all = ctx->d_misc.as<uint32_t>();
+    HS_TRY(comm_allgather_u32(ctx, label, all, N));
+    for (uint32_t r = 0; r < nparts; ++r) {
+      if (r == part) continue;
+      uf_merge_labels_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(parent, all + (size_t)r * N, N);
+      ctx->stats.kernel_launches++;
+    }
+    uf_flatten_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(parent, N, label);
+    ctx->stats.kernel_launches++;
+    HS_CUDA(cudaGetLastError());
+  }
   unsigned long long h_edges = 0;
   HS_CUDA(cudaMemcpyAsync(&h_edges, edge_count, sizeof h_edges, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaMemcpyAsync(label_out, label, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));

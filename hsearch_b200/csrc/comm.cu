@@ -80,6 +80,16 @@ int comm_broadcast(hs_ctx *ctx, void *d_buf, size_t bytes) {
   return HS_OK;
 }
 
+// n 32-bit words of every rank, in rank order, to every rank (cluster labels: cluster.cu)
+int comm_allgather_u32(hs_ctx *ctx, const uint32_t *d_send, uint32_t *d_recv, uint64_t n) {
+  if (ctx->nranks <= 1) {
+    set_error("hs_comm: all-gather on a context without a communicator");
+    return HS_ERR_COMM;
+  }
+  HS_NCCL(g_nccl.AllGather(d_send, d_recv, n, ncclUint32, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  return HS_OK;
+}
+
 // ---- kernels ---------------------------------------------------------------------------------
 // off[s] = first index of the sorted key list whose segment (key >> shift) is >= s, s in [0, S];
 // cnt[s] = off[s+1] - off[s] is written by the thread that closes segment s.

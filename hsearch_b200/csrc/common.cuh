@@ -67,9 +67,31 @@ struct DevBuf {
 constexpr int kMaxKeyWords = HS_MAX_KEY_WORDS;
 constexpr int kCodeScale = 4;  // bucket-ordered code store keeps code*4 (a byte offset into a float row)
 
+// 64-bit hash of a packed key (hashed-key path of the index build, radix_sort.cu; probe, verify.cu).
+// Equal keys hash equally; the build checks every bucket member's full key against its bucket's, so a
+// collision of distinct keys is detected, never silently merged.
+template <int NW>
+__host__ __device__ __forceinline__ uint64_t key_hash(const uint64_t *k) {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    uint64_t x = h ^ k[w];
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    h = x + 0x9E3779B97F4A7C15ull * (uint64_t)(w + 1);
+  }
+  return h;
+}
+
 struct TableIndex {
   DevBuf sorted_ids;    // u32 [N]  fragment ids in bucket order
   DevBuf ukeys;         // u64 [key_words][nslots]  keys of the bucket slots, ascending
+  DevBuf ukeys_full;    // u64 [key_words][nslots]  hashed-key path only: the key strings of the slots
+                        // (ukeys then holds the ascending 64-bit hashes of the key strings)
+  bool hashed_keys = false;
   DevBuf bstart;        // u32 [nslots+1]           bucket boundaries into sorted_ids
   DevBuf codes_sorted;  // u8  [len][npad]      code*4, position-major, bucket order
   uint64_t nb = 0;      // non-empty buckets (the reference's "table size")
@@ -203,6 +225,7 @@ struct hs_ctx {
   // debugging switches, read from the environment once in hs_create
   bool no_pipeline = false;      // HS_NO_PIPELINE: host-buffer searches in one pass (no query blocks)
   bool no_load_overlap = false;  // HS_NO_LOAD_OVERLAP: hs_load_fragments copies first, hashes later
+  bool no_hash_sort = false;     // HS_NO_HASH_SORT: multi-word keys sorted on every word (no 64-bit key hash)
   bool plan_stats = false;       // HS_PLAN_STATS: print the filter work-list statistics
   uint32_t selfjoin_chunk = 1u << 16;  // HS_SELFJOIN_CHUNK: query members per tensor-filter pass of a large bucket (hs_cluster)
   bool surv_bins = false;        // HS_SURV_BINS: survivors regrouped by fragment-id block before the exact stage

@@ -1005,10 +1005,102 @@ static int build_table_index_ranks(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_s
   return HS_OK;
 }
 
+// ---- hashed-key path: multi-word keys (K >= 8 or a small W: 2-4 words, up to 16 radix passes per table
+// over all words) are sorted on a 64-bit hash of the key instead: 8 passes over one word.  The reference's
+// HashTable is an unordered_map (motif_both_points.cpp:212-218, lsh.hpp:51-59): the order of the buckets
+// is immaterial, a bucket is the ascending id list of the fragments sharing a key string.  Equal keys
+// hash equally, so after the stable sort every hash group is in ascending id order; a group is a bucket
+// iff all its members carry the same full key, which hashed_buckets_kernel checks member by member
+// against the group's head (any mismatch -> the caller falls back to the sort on all words).
+template <int NW>
+__global__ void key_hash_kernel(KeyPtrs keys, uint64_t n, uint64_t *__restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) k[w] = keys.w[w][i];
+  out[i] = key_hash<NW>(k);
+}
+
+template <int NW>
+__global__ void hashed_buckets_kernel(KeyPtrs keys /* by fragment id */, uint64_t n, const uint32_t *__restrict__ ids,
+                                      const uint32_t *__restrict__ flags, const uint32_t *__restrict__ scanned,
+                                      const uint32_t *__restrict__ bstart, uint64_t nb,
+                                      uint64_t *__restrict__ ukeys_full /* [NW][nb] */,
+                                      unsigned int *__restrict__ mismatches) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t id = ids[i];
+  if (flags[i]) {
+    const uint32_t b = scanned[i];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) ukeys_full[(uint64_t)w * nb + b] = keys.w[w][id];
+    return;
+  }
+  const uint32_t head = ids[bstart[scanned[i] - 1]];
+  bool same = true;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) same = same && (keys.w[w][id] == keys.w[w][head]);
+  if (!same) atomicAdd(mismatches, 1u);
+}
+
+template <int NW>
+static int build_table_index_hashed(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, bool *ok) {
+  const uint64_t n = ctx->N;
+  SortScratch &S = ctx->sort;
+  TableIndex &T = ctx->tables[table];
+  *ok = false;
+  HS_TRY(T.sorted_ids.reserve(sizeof(uint32_t) * n));
+  HS_TRY(S.vals_alt.reserve(sizeof(uint32_t) * n));
+  HS_TRY(S.keys_cur[1].reserve(sizeof(uint64_t) * n));
+  KeyPtrs in;
+  for (int w = 0; w < kMaxKeyWords; ++w)
+    in.w[w] = w < NW ? ctx->d_keys[table].as<uint64_t>() + (uint64_t)w * n : nullptr;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  key_hash_kernel<NW><<<grid, 256, 0, ctx->stream>>>(in, n, S.keys_cur[1].as<uint64_t>());
+  ctx->stats.kernel_launches++;
+  KeyPtrs hin, hsorted;
+  for (int w = 0; w < kMaxKeyWords; ++w) hin.w[w] = nullptr;
+  hin.w[0] = S.keys_cur[1].as<uint64_t>();
+  HS_TRY(radix_sort_pairs(ctx, hin, nullptr, n, 1, T.sorted_ids.as<uint32_t>(), S.vals_alt.as<uint32_t>(), &hsorted, ~0ull));
+  HS_CUDA(cudaEventRecord(ev_sort_end, ctx->stream));
+  HS_TRY(group_inst<1>(ctx, table, hsorted));   // ukeys = the ascending hashes, bstart
+  const uint64_t nb = T.nb;
+  HS_TRY(T.ukeys_full.reserve(sizeof(uint64_t) * NW * std::max<uint64_t>(nb, 1)));
+  unsigned int *mism = S.or_and.as<unsigned int>() + 2;
+  HS_CUDA(cudaMemsetAsync(mism, 0, sizeof(unsigned int), ctx->stream));
+  uint32_t *flags = S.flags.as<uint32_t>();
+  hashed_buckets_kernel<NW><<<grid, 256, 0, ctx->stream>>>(in, n, T.sorted_ids.as<uint32_t>(), flags, flags + n,
+                                                          T.bstart.as<uint32_t>(), nb, T.ukeys_full.as<uint64_t>(), mism);
+  ctx->stats.kernel_launches++;
+  HS_CUDA(cudaGetLastError());
+  unsigned int h_mism = 0;
+  HS_TRY(read_back(ctx, mism, &h_mism, sizeof h_mism));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  *ok = h_mism == 0 && !ctx->force_hash_collision;
+  T.hashed_keys = *ok;
+  return HS_OK;
+}
+
 // with_store == false: the caller builds the code stores of all tables afterwards
 // (build_code_stores_blocked, or build_table_store per table).
 int build_table_index(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cudaEvent_t ev_group_end, bool with_store) {
   if (ctx->rank_mode) return build_table_index_ranks(ctx, table, ev_sort_end, ev_group_end, with_store);
+  ctx->tables[table].hashed_keys = false;
+  if (ctx->key_words >= 2 && !ctx->no_hash_sort && ctx->N) {
+    bool ok = false;
+    switch (ctx->key_words) {
+      case 2: HS_TRY(build_table_index_hashed<2>(ctx, table, ev_sort_end, &ok)); break;
+      case 3: HS_TRY(build_table_index_hashed<3>(ctx, table, ev_sort_end, &ok)); break;
+      default: HS_TRY(build_table_index_hashed<4>(ctx, table, ev_sort_end, &ok)); break;
+    }
+    if (ok) {
+      HS_CUDA(cudaEventRecord(ev_group_end, ctx->stream));
+      if (with_store) HS_TRY(build_table_store(ctx, table));
+      return HS_OK;
+    }
+    ctx->stats.hash_sort_fallbacks++;   // two distinct keys with one hash: sort on all words
+  }
   KeyPtrs sorted;
   HS_TRY(sort_table(ctx, table, &sorted));
   HS_CUDA(cudaEventRecord(ev_sort_end, ctx->stream));

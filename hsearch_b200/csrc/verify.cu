@@ -69,6 +69,42 @@ __global__ void probe_kernel(const uint64_t *__restrict__ qkeys /* [Q][KW] of th
   qrank[q] = slot;
 }
 
+// Hashed-key path (radix_sort.cu): binary search over the ascending key hashes, then the full key
+// of the slot decides (a query whose key merely shares a bucket's hash finds nothing).
+template <int KW>
+__global__ void probe_hashed_kernel(const uint64_t *__restrict__ qkeys, const uint8_t *__restrict__ qvalid, uint32_t Q,
+                                    const uint64_t *__restrict__ uhash /* [nb] */,
+                                    const uint64_t *__restrict__ ukeys_full /* [KW][nb] */, uint64_t nb,
+                                    const uint32_t *__restrict__ bstart, uint2 *__restrict__ qrange,
+                                    uint32_t *__restrict__ qrank) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  uint2 r = make_uint2(0u, 0u);
+  uint32_t slot = 0xffffffffu;
+  if (qvalid[q] && nb > 0) {
+    uint64_t k[KW];
+#pragma unroll
+    for (int w = 0; w < KW; ++w) k[w] = qkeys[(size_t)q * KW + w];
+    const uint64_t h = key_hash<KW>(k);
+    uint64_t lo = 0, hi = nb;
+    while (lo < hi) {
+      const uint64_t m = (lo + hi) >> 1;
+      if (uhash[m] < h) lo = m + 1; else hi = m;
+    }
+    if (lo < nb && uhash[lo] == h) {
+      bool eq = true;
+#pragma unroll
+      for (int w = 0; w < KW; ++w) eq = eq && (ukeys_full[(uint64_t)w * nb + lo] == k[w]);
+      if (eq) {
+        r = make_uint2(bstart[lo], bstart[lo + 1]);
+        slot = (uint32_t)lo;
+      }
+    }
+  }
+  qrange[q] = r;
+  qrank[q] = slot;
+}
+
 int launch_probe(hs_ctx *ctx, uint32_t table, const uint64_t *d_qkeys, const uint8_t *d_qvalid, uint32_t Q,
                  uint2 *d_qrange, uint32_t *d_qrank) {
   if (Q == 0) return HS_OK;
@@ -78,6 +114,21 @@ int launch_probe(hs_ctx *ctx, uint32_t table, const uint64_t *d_qkeys, const uin
   const uint8_t *qv = d_qvalid + (size_t)table * Q;
   uint2 *qr = d_qrange + (size_t)table * Q;
   uint32_t *qs = d_qrank + (size_t)table * Q;
+  if (T.hashed_keys) {
+#define HS_PROBE_H(KWV)                                                                                    \
+  probe_hashed_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(qk, qv, Q, T.ukeys.as<uint64_t>(),                \
+                                                          T.ukeys_full.as<uint64_t>(), T.nslots,            \
+                                                          T.bstart.as<uint32_t>(), qr, qs)
+    switch (ctx->key_words) {
+      case 2: HS_PROBE_H(2); break;
+      case 3: HS_PROBE_H(3); break;
+      default: HS_PROBE_H(4); break;
+    }
+#undef HS_PROBE_H
+    HS_CUDA(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    return HS_OK;
+  }
 #define HS_PROBE(KWV)                                                                                      \
   probe_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(qk, qv, Q, T.ukeys.as<uint64_t>(), T.nslots,            \
                                                    T.bstart.as<uint32_t>(), qr, qs)

@@ -111,3 +111,50 @@ def test_two_gpu_merge_equals_one_gpu_search(tmp_path, cuts):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, str(tmp_path), cuts), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok")
+
+
+def _cluster_worker(rank, world, tmpdir, n_total, W):
+    """hs_cluster on a communicator: every rank holds the whole DB, the pair work is split and the
+    labels are exchanged (cluster.cu); each rank's labels must equal the one-GPU labels."""
+    import torch
+    import hsearch_b200 as hb
+    from hsearch_b200 import capi
+    from tests.util import planted_families
+    lib = capi.load()
+    torch.cuda.set_device(rank)
+    length, K, L, R = 10, 4, 4, 25.0
+    codes = planted_families(n_total, length, seed=9)
+    h = hb.HSearch(length, K, L, W, R, predicate=hb.HS_PRED_SQRT_LE_R, device=rank)
+    h.seed_projection(4242)
+    h.load_fragments(codes)
+    h.build_index()
+    want = h.cluster()                       # before joining: the whole pair work on this GPU
+    edges_whole = h.stats().n_edges
+    uid_path = os.path.join(tmpdir, "uid.bin")
+    if rank == 0:
+        raw = np.zeros(128, dtype=np.uint8)
+        capi.check(lib.hs_comm_unique_id(raw.ctypes.data_as(C.c_void_p)))
+        raw.tofile(uid_path + ".tmp")
+        os.rename(uid_path + ".tmp", uid_path)
+    else:
+        t0 = time.time()
+        while not os.path.exists(uid_path):
+            assert time.time() - t0 < 120
+            time.sleep(0.05)
+        raw = np.fromfile(uid_path, dtype=np.uint8)
+    capi.check(lib.hs_comm_init(h.ctx, raw.ctypes.data_as(C.c_void_p), rank, world))
+    got = h.cluster()
+    assert np.array_equal(got, want)
+    assert len(np.unique(want)) < n_total          # something was united
+    assert 0 < h.stats().n_edges < edges_whole      # this rank united only its share of the pairs
+    h.close()
+    open(os.path.join(tmpdir, f"ok{rank}"), "w").write("1")
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("n_total,W", [(60_000, 20.0), (300_000, 50.0)])
+@pytest.mark.timeout(600)
+def test_two_gpu_cluster_equals_one_gpu_cluster(tmp_path, n_total, W):
+    import torch.multiprocessing as mp
+    mp.spawn(_cluster_worker, args=(2, str(tmp_path), n_total, W), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
