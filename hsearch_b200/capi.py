@@ -30,6 +30,7 @@ EXPORTS = [
     "hs_greedy_cluster", "hs_union_find", "hs_parse_fasta", "hs_klsh_generate", "hs_kmer3_klsh", "hs_orf6",
     "hs_evaluate_recall", "hs_evaluate_recall_dev",
     "hs_search_points_compact", "hs_expand_hits", "hs_hits_checksum", "hs_hits_checksum_dev", "hs_hash_audit", "hs_comm_reserve", "hs_comm_result", "hs_protein_id", "hs_fragment_name",
+    "hs_parse_fasta_gpu",
 ]
 
 
@@ -64,7 +65,7 @@ class Stats(C.Structure):
                 ("ms_sort_upsweep", C.c_float), ("ms_sort_scan", C.c_float), ("ms_sort_downsweep", C.c_float),
                 ("ms_qhash", C.c_float), ("ms_probe", C.c_float), ("ms_filter", C.c_float), ("ms_exact", C.c_float),
                 ("ms_hitsort", C.c_float), ("ms_total", C.c_float), ("ms_filter_tc", C.c_float),
-                ("ms_host", C.c_float), ("n_candidates_tc", C.c_uint64)]
+                ("ms_host", C.c_float), ("n_candidates_tc", C.c_uint64), ("hash_sort_fallbacks", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -126,6 +127,8 @@ def load(build_if_missing=True):
     lib.hs_union_find.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint64, u32p]
     lib.hs_parse_fasta.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, u64p, C.c_uint64, u64p, u32p,
                                    C.c_uint64, u32p, u32p, u64p]
+    lib.hs_parse_fasta_gpu.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, u64p, C.c_uint64, u64p, u32p,
+                                       C.c_uint64, u32p, u32p, u64p]
     lib.hs_klsh_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_double, dblp, dblp, dblp]
     lib.hs_kmer3_klsh.argtypes = [vp, C.c_char_p, u64p, C.c_uint32, dblp, dblp, dblp, C.c_uint32, u32p, u64p, u8p,
                                   u64p]

@@ -211,6 +211,45 @@ int ensure_identity_store(hs_ctx *ctx) {
   return upload_table_pointers(ctx);
 }
 
+// Bucket-ordered code stores of all tables (what the filters stream).  hs_build_index leaves them
+// out for an index of tiny buckets (large K, small W: millions of buckets of one or two members)
+// -- there a search examines a few thousand candidates and the stores, one random record gather per
+// fragment and table, were most of the build -- and whoever needs them builds them on demand.
+int ensure_code_stores(hs_ctx *ctx) {
+  if (ctx->stores_built || ctx->N == 0) return HS_OK;
+  bool blocked = false;
+  HS_TRY(build_code_stores_blocked(ctx, &blocked));
+  if (!blocked)
+    for (uint32_t l = 0; l < ctx->prm.L; ++l) HS_TRY(build_table_store(ctx, l));
+  ctx->stores_built = true;
+  return upload_table_pointers(ctx);
+}
+
+// Filter bypass: every member of every probed bucket becomes a survivor (the exact stage decides).
+// One warp per (table, query) range; off[] = exclusive prefix sums of the range sizes.
+__global__ void expand_candidates_kernel(const uint2 *__restrict__ qrange, const uint32_t *__restrict__ off, uint32_t Q,
+                                         uint32_t nranges, Survivor *__restrict__ surv) {
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= nranges) return;
+  const uint2 rg = qrange[r];
+  const uint32_t table = r / Q, q = r - table * Q;
+  Survivor *dst = surv + off[r];
+  for (uint32_t i = rg.x + lane; i < rg.y; i += 32) {
+    Survivor sv;
+    sv.query = q;
+    sv.table = table;
+    sv.pos = i;
+    sv.pad = 0;
+    dst[i - rg.x] = sv;
+  }
+}
+__global__ void range_sizes_kernel(const uint2 *__restrict__ qrange, uint32_t n, uint32_t *__restrict__ sz) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sz[i] = qrange[i].y - qrange[i].x;
+}
+constexpr uint64_t kBypassMaxCandidates = 1ull << 22;
+
 // Run the filter (scalar leg and, when given, the tensor-core leg; both append to
 // the same survivor list), growing the survivor buffer and retrying on overflow.
 int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out, FilterArgs *fa_tc,
@@ -953,6 +992,35 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
   HS_TRY(read_back(ctx, ctx->d_qrange.p, qrange.data(), sizeof(uint2) * qrange.size()));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
 
+  // An index without code stores (tiny buckets, see ensure_code_stores): a small candidate set goes
+  // to the exact stage unfiltered, a large one has the stores built now.
+  bool bypass = false;
+  if (!ctx->stores_built) {
+    uint64_t ncand = 0;
+    for (const uint2 &r : qrange) ncand += r.y - r.x;
+    if (ncand <= ctx->bypass_max && ctx->prm.metric == HS_METRIC_EUCLID_FP64) bypass = true;
+    else HS_TRY(ensure_code_stores(ctx));
+  }
+  auto run_bypass = [&](uint64_t *nsurv) -> int {
+    const uint32_t nr = L * Q;
+    HS_TRY(ctx->d_misc.reserve(sizeof(uint32_t) * 2 * ((size_t)nr + 1)));
+    uint32_t *sz = ctx->d_misc.as<uint32_t>(), *off = sz + nr + 1;
+    uint32_t *d_total = reinterpret_cast<uint32_t *>(ctx->d_counters.as<unsigned long long>() + 16);
+    range_sizes_kernel<<<(nr + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_qrange.as<uint2>(), nr, sz);
+    HS_TRY(exclusive_scan_u32(ctx, sz, off, nr, d_total));
+    uint32_t total = 0;
+    HS_TRY(read_back(ctx, d_total, &total, sizeof total));
+    HS_TRY(ctx->d_surv.reserve(sizeof(Survivor) * std::max<size_t>(total, 1)));
+    if (total)
+      expand_candidates_kernel<<<(unsigned)(((uint64_t)nr * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->d_qrange.as<uint2>(), off, Q, nr, ctx->d_surv.as<Survivor>());
+    HS_CUDA(cudaGetLastError());
+    ctx->stats.kernel_launches += 2;
+    ctx->stats.n_candidates += total;
+    *nsurv = total;
+    return HS_OK;
+  };
+
   // work list of the queries [qa, qb): queries grouped by bucket, chunked
   // (one sub-plan per table, built on its own host thread and merged in table order: the
   // planning of 10 k queries x 4 tables is ~0.7 ms per table of pure host time)
@@ -1075,10 +1143,11 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
       ctx->ev_chunk.push_back(e);
     }
     FilterPlan plan;
-    HS_TRY(make_plan(plan, 0, Q));
+    if (!bypass) HS_TRY(make_plan(plan, 0, Q));
     HS_CUDA(cudaEventRecord(ev[12], ctx->stream));
     uint64_t nsurv = 0;
-    HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
+    if (bypass) HS_TRY(run_bypass(&nsurv));
+    else HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
     ctx->stats.n_survivors = nsurv;
     // survivors by query block (and, inside a query block, by fragment-id block: bin_survivors)
     unsigned long long h_cnt[kSearchBlocks] = {0};
@@ -1149,13 +1218,14 @@ static int search_impl(hs_ctx *ctx, const QueryInput &in, uint32_t Q, hs_hit *hi
 
   FilterPlan plan;
   const auto _t0 = std::chrono::steady_clock::now();
-  HS_TRY(make_plan(plan, 0, Q));
+  if (!bypass) HS_TRY(make_plan(plan, 0, Q));
   if (ctx->plan_stats)
     fprintf(stderr, "[plan] host planning %.3f ms\n",
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - _t0).count());
   HS_CUDA(cudaEventRecord(ev[12], ctx->stream));
   uint64_t nsurv = 0;
-  HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
+  if (bypass) HS_TRY(run_bypass(&nsurv));
+  else HS_TRY(plan_run(ctx, plan, Q, 0, kModeSearch, &nsurv));
   HS_CUDA(cudaEventRecord(ev[3], ctx->stream));
   ctx->stats.n_survivors = nsurv;
   // HS_SURV_BINS=1 regroups large lists by fragment-id block first so that the record gathers of the
@@ -1402,6 +1472,12 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->no_load_overlap = env_on("HS_NO_LOAD_OVERLAP");
   ctx->plan_stats = env_on("HS_PLAN_STATS");
   ctx->no_hash_sort = env_on("HS_NO_HASH_SORT");
+  ctx->no_lazy_stores = env_on("HS_NO_LAZY_STORES");
+  ctx->bypass_max = kBypassMaxCandidates;
+  if (const char *e = getenv("HS_BYPASS_MAX")) ctx->bypass_max = strtoull(e, nullptr, 10);
+  if (const char *e = getenv("HS_EXACT_REP")) ctx->exact_rep = atoi(e) != 0;
+  ctx->force_hash_collision = env_on("HS_FORCE_HASH_COLLISION");
+  ctx->force_hash_sort = ctx->force_hash_collision || env_on("HS_FORCE_HASH_SORT");
   ctx->no_mma_filter = env_on("HS_NO_MMA_FILTER");
   ctx->surv_bins = env_on("HS_SURV_BINS");
   if (const char *e = getenv("HS_SELFJOIN_CHUNK"))
@@ -1752,17 +1828,21 @@ int hs_build_index(hs_ctx_t *ctx) {
       ms_sort += ev_ms(ev[2], ev[3]);
       ms_group += ev_ms(ev[3], ev[4]);
     }
-    // bucket-order code stores: one L2-blocked gather for all tables, else table by table
+    // bucket-order code stores: one L2-blocked gather for all tables, else table by table;
+    // left to the first user when the buckets are tiny (ensure_code_stores)
     HS_CUDA(cudaEventRecord(ev[2], ctx->stream));
-    bool blocked = false;
-    HS_TRY(build_code_stores_blocked(ctx, &blocked));
-    if (!blocked)
-      for (uint32_t l = 0; l < L; ++l) HS_TRY(build_table_store(ctx, l));
+    uint64_t nb_sum = 0;
+    for (uint32_t l = 0; l < L; ++l) nb_sum += ctx->tables[l].nb;
+    ctx->stores_built = false;
+    const bool lazy = !ctx->no_lazy_stores && ctx->N >= (1u << 20) && nb_sum * 4 > (uint64_t)L * ctx->N &&
+                      ctx->prm.metric == HS_METRIC_EUCLID_FP64;
+    if (!lazy) HS_TRY(ensure_code_stores(ctx));
     HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
     HS_CUDA(cudaEventSynchronize(ev[5]));
     ms_permute = ev_ms(ev[2], ev[5]);
   } else {
     for (uint32_t l = 0; l < L; ++l) ctx->tables[l].nb = ctx->tables[l].nslots = 0;
+    ctx->stores_built = true;
   }
   HS_CUDA(cudaEventRecord(ev[9], ctx->stream));
   HS_CUDA(cudaEventSynchronize(ev[9]));
@@ -1918,6 +1998,7 @@ int hs_cluster(hs_ctx_t *ctx, uint32_t *label_out) {
     return HS_ERR_INVALID;
   }
   HS_CUDA(cudaSetDevice(ctx->device));
+  HS_TRY(ensure_code_stores(ctx));
   return cluster_impl(ctx, label_out);
 }
 

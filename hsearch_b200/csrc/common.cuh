@@ -226,6 +226,12 @@ struct hs_ctx {
   bool no_pipeline = false;      // HS_NO_PIPELINE: host-buffer searches in one pass (no query blocks)
   bool no_load_overlap = false;  // HS_NO_LOAD_OVERLAP: hs_load_fragments copies first, hashes later
   bool no_hash_sort = false;     // HS_NO_HASH_SORT: multi-word keys sorted on every word (no 64-bit key hash)
+  bool force_hash_sort = false;       // HS_FORCE_HASH_SORT: multi-word keys always take the hashed sort (tests)
+  bool force_hash_collision = false;  // HS_FORCE_HASH_COLLISION: test hook, the hashed sort reports a collision
+  bool exact_rep = true;         // HS_EXACT_REP=0: exact stage without the 8-fold replicated residue-pair table
+  bool no_lazy_stores = false;   // HS_NO_LAZY_STORES: hs_build_index always builds the bucket-ordered code stores
+  uint64_t bypass_max = 0;       // candidates up to which a search on an index without code stores skips the filter
+  bool stores_built = false;     // the tables' codes_sorted are valid (ensure_code_stores)
   bool plan_stats = false;       // HS_PLAN_STATS: print the filter work-list statistics
   uint32_t selfjoin_chunk = 1u << 16;  // HS_SELFJOIN_CHUNK: query members per tensor-filter pass of a large bucket (hs_cluster)
   bool surv_bins = false;        // HS_SURV_BINS: survivors regrouped by fragment-id block before the exact stage

@@ -18,6 +18,7 @@ struct MmaLaunch {
 int run_filter(hs_ctx *ctx, FilterArgs &fa, uint32_t nblocks, int mode, uint64_t *nsurv_out,
                FilterArgs *fa_tc = nullptr, uint32_t nblocks_tc = 0, const MmaLaunch *ml = nullptr);
 int ensure_identity_store(hs_ctx *ctx);
+int ensure_code_stores(hs_ctx *ctx);
 bool selfjoin_uses_mma(const hs_ctx *ctx, uint32_t n);
 int selfjoin_bucket_mma(hs_ctx *ctx, uint32_t table, uint32_t mb, uint32_t me, uint32_t q_lo, uint32_t q_hi,
                         uint64_t *nsurv, uint64_t *npairs, bool *used);

@@ -521,6 +521,29 @@ int radix_sort_pairs(hs_ctx *ctx, const KeyPtrs &keys_in, const uint32_t *vals_i
   return HS_OK;
 }
 
+// Number of radix passes a sort of these keys on all their words would take (one reduction pass
+// over the keys: which bits vary).
+static int count_full_passes(hs_ctx *ctx, const KeyPtrs &keys_in, uint64_t n, int nw, size_t *npasses) {
+  SortScratch &S = ctx->sort;
+  HS_TRY(S.or_and.reserve(sizeof(unsigned long long) * 2 * kMaxKeyWords));
+  unsigned long long h_init[2 * kMaxKeyWords], h_oa[2 * kMaxKeyWords];
+  for (int w = 0; w < kMaxKeyWords; ++w) {
+    h_init[2 * w] = 0ull;
+    h_init[2 * w + 1] = ~0ull;
+  }
+  unsigned long long *d_oa = S.or_and.as<unsigned long long>();
+  HS_TRY(upload(ctx, d_oa, h_init, sizeof h_init));
+  for (int w = 0; w < nw; ++w) {
+    key_bits_kernel<<<148 * 4, 256, 0, ctx->stream>>>(keys_in.w[w], n, 1, d_oa + 2 * w);
+    ctx->stats.kernel_launches++;
+  }
+  HS_TRY(read_back(ctx, d_oa, h_oa, sizeof h_oa));
+  std::vector<Pass> passes;
+  plan_passes(h_oa, nw, passes);
+  *npasses = passes.size();
+  return HS_OK;
+}
+
 static int sort_table(hs_ctx *ctx, uint32_t table, KeyPtrs *sorted_keys) {
   const uint64_t n = ctx->N;
   const int nw = (int)ctx->key_words;
@@ -1045,17 +1068,26 @@ __global__ void hashed_buckets_kernel(KeyPtrs keys /* by fragment id */, uint64_
 }
 
 template <int NW>
-static int build_table_index_hashed(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, bool *ok) {
+static int build_table_index_hashed(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, bool *ok, bool *declined) {
   const uint64_t n = ctx->N;
   SortScratch &S = ctx->sort;
   TableIndex &T = ctx->tables[table];
   *ok = false;
+  *declined = false;
   HS_TRY(T.sorted_ids.reserve(sizeof(uint32_t) * n));
   HS_TRY(S.vals_alt.reserve(sizeof(uint32_t) * n));
   HS_TRY(S.keys_cur[1].reserve(sizeof(uint64_t) * n));
   KeyPtrs in;
   for (int w = 0; w < kMaxKeyWords; ++w)
     in.w[w] = w < NW ? ctx->d_keys[table].as<uint64_t>() + (uint64_t)w * n : nullptr;
+  // worth it?  bytes moved per key: P passes over NW words + id against 8 passes over one word + id,
+  // plus the hash pass and the full-key check (two gathers of NW words)
+  size_t full_passes = 0;
+  HS_TRY(count_full_passes(ctx, in, n, NW, &full_passes));
+  if (!ctx->force_hash_sort && full_passes * (8 * NW + 4) <= 8 * 12 + 8 * NW + 64 * NW) {
+    *declined = true;
+    return HS_OK;
+  }
   const unsigned grid = (unsigned)((n + 255) / 256);
   key_hash_kernel<NW><<<grid, 256, 0, ctx->stream>>>(in, n, S.keys_cur[1].as<uint64_t>());
   ctx->stats.kernel_launches++;
@@ -1088,18 +1120,18 @@ int build_table_index(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_sort_end, cuda
   if (ctx->rank_mode) return build_table_index_ranks(ctx, table, ev_sort_end, ev_group_end, with_store);
   ctx->tables[table].hashed_keys = false;
   if (ctx->key_words >= 2 && !ctx->no_hash_sort && ctx->N) {
-    bool ok = false;
+    bool ok = false, declined = false;
     switch (ctx->key_words) {
-      case 2: HS_TRY(build_table_index_hashed<2>(ctx, table, ev_sort_end, &ok)); break;
-      case 3: HS_TRY(build_table_index_hashed<3>(ctx, table, ev_sort_end, &ok)); break;
-      default: HS_TRY(build_table_index_hashed<4>(ctx, table, ev_sort_end, &ok)); break;
+      case 2: HS_TRY(build_table_index_hashed<2>(ctx, table, ev_sort_end, &ok, &declined)); break;
+      case 3: HS_TRY(build_table_index_hashed<3>(ctx, table, ev_sort_end, &ok, &declined)); break;
+      default: HS_TRY(build_table_index_hashed<4>(ctx, table, ev_sort_end, &ok, &declined)); break;
     }
     if (ok) {
       HS_CUDA(cudaEventRecord(ev_group_end, ctx->stream));
       if (with_store) HS_TRY(build_table_store(ctx, table));
       return HS_OK;
     }
-    ctx->stats.hash_sort_fallbacks++;   // two distinct keys with one hash: sort on all words
+    if (!declined) ctx->stats.hash_sort_fallbacks++;   // two distinct keys with one hash: sort on all words
   }
   KeyPtrs sorted;
   HS_TRY(sort_table(ctx, table, &sorted));

@@ -381,27 +381,42 @@ __device__ __forceinline__ void load_record(const uint8_t *p, uint32_t (&w)[4 * 
 }
 
 constexpr int kExactThreads = 256;
-constexpr int kSqStride = 10;  // doubles per residue-pair row (8 + 2 padding: spreads rows over the banks)
+constexpr int kSqStride = 10;  // REP == 1: doubles per residue-pair row (8 + 2 padding: spreads rows over the banks)
+// REP == 8: the residue-pair table is stored eight times, copy c in the 16-byte bank group c, and lane
+// l reads copy l & 7: the eight lanes of one LDS.128 phase never share a bank whatever rows they
+// want (ncu, round 1: 59 % of the kernel's shared-memory wavefronts were bank conflicts and the
+// l1tex data pipe was at 82 % of its peak).  200 KB of shared memory, one 1024-thread block per SM.
+constexpr int kExactThreadsRep = 1024;
+constexpr size_t kSqBytes1 = sizeof(double) * HS_AA * HS_AA * kSqStride;
+constexpr size_t kSqBytes8 = sizeof(double2) * HS_AA * HS_AA * (HS_CDIM / 2) * 8;
 
 // One thread per survivor, grid-stride.  NV: 16-byte words of residue codes per fragment
 // (len <= 16 * NV).  The member's codes (and, on the rank path, its bucket ranks) come from
 // its fragment record: one 32-byte sector per survivor.  Distances between residue strings
 // read the squared coordinate differences from a shared residue-pair table, in the
 // reference's summation order; hits are appended with one atomic per warp.
-template <int NV>
-__global__ void __launch_bounds__(kExactThreads) exact_kernel(ExactArgs a) {
-  __shared__ __align__(16) double s_sq[HS_AA * HS_AA * kSqStride];  // (table[x][j] - table[q][j])^2
+template <int NV, int REP>
+__global__ void __launch_bounds__(REP == 8 ? kExactThreadsRep : kExactThreads) exact_kernel(ExactArgs a) {
+  extern __shared__ __align__(16) unsigned char exact_smem[];
+  double2 *s_sq2 = reinterpret_cast<double2 *>(exact_smem);  // (table[x][j] - table[q][j])^2
   __shared__ __align__(16) double s_table[HS_AA * HS_CDIM];
   __shared__ int s_metric[HS_AA * HS_AA];
   for (int i = threadIdx.x; i < HS_AA * HS_CDIM; i += blockDim.x) s_table[i] = a.table64[i];
   for (int i = threadIdx.x; i < HS_AA * HS_AA; i += blockDim.x) s_metric[i] = a.metric_tab[i];
   if (a.metric != HS_METRIC_BLOSUM_INT) {
-    for (int i = threadIdx.x; i < HS_AA * HS_AA * HS_CDIM; i += blockDim.x) {
-      const int j = i % HS_CDIM, pair = i / HS_CDIM;
+    for (int i = threadIdx.x; i < HS_AA * HS_AA * (HS_CDIM / 2); i += blockDim.x) {
+      const int j2 = i % (HS_CDIM / 2), pair = i / (HS_CDIM / 2);
       const int qc = pair / HS_AA, xc = pair - qc * HS_AA;
       // r = a - b; r * r (motif_both_points.cpp:180-181); (-r) * (-r) is the same double
-      const double r = __dsub_rn(a.table64[xc * HS_CDIM + j], a.table64[qc * HS_CDIM + j]);
-      s_sq[pair * kSqStride + j] = __dmul_rn(r, r);
+      const double r0 = __dsub_rn(a.table64[xc * HS_CDIM + 2 * j2], a.table64[qc * HS_CDIM + 2 * j2]);
+      const double r1 = __dsub_rn(a.table64[xc * HS_CDIM + 2 * j2 + 1], a.table64[qc * HS_CDIM + 2 * j2 + 1]);
+      const double2 v = make_double2(__dmul_rn(r0, r0), __dmul_rn(r1, r1));
+      if (REP == 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s_sq2[(pair * (HS_CDIM / 2) + j2) * 8 + c] = v;
+      } else {
+        s_sq2[pair * (kSqStride / 2) + j2] = v;
+      }
     }
   }
   __syncthreads();
@@ -491,10 +506,11 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(ExactArgs a) {
             for (int p = 0; p < 16 * NV; ++p)
               if (p < len) {
                 const int xc = (mw[p >> 2] >> (8 * (p & 3))) & 0xff, qc = (qw[p >> 2] >> (8 * (p & 3))) & 0xff;
-                const double2 *row = reinterpret_cast<const double2 *>(s_sq + (qc * HS_AA + xc) * kSqStride);
+                const double2 *row = REP == 8 ? s_sq2 + (qc * HS_AA + xc) * (HS_CDIM / 2) * 8 + (lane & 7)
+                                              : s_sq2 + (qc * HS_AA + xc) * (kSqStride / 2);
 #pragma unroll
                 for (int j = 0; j < HS_CDIM / 2; ++j) {
-                  const double2 t = row[j];
+                  const double2 t = row[REP == 8 ? j * 8 : j];
                   dis = __dadd_rn(dis, t.x);
                   dis = __dadd_rn(dis, t.y);
                 }
@@ -550,19 +566,31 @@ __global__ void __launch_bounds__(kExactThreads) exact_kernel(ExactArgs a) {
 
 int launch_exact(hs_ctx *ctx, const ExactArgs &args) {
   if (args.nsurv == 0) return HS_OK;
-  const unsigned long long want = (args.nsurv + kExactThreads - 1) / kExactThreads;
   // grid-stride kernel: exactly one wave of resident blocks (a partial second wave would start
   // when the first ends and leave most SMs idle for its duration)
-  static int per_sm[2] = {0, 0};
+  static int per_sm[2][2] = {{0, 0}, {0, 0}};
   const int v = args.len <= 16 ? 0 : 1;
-  if (!per_sm[v]) {
-    if (v == 0) HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], exact_kernel<1>, kExactThreads, 0));
-    else HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], exact_kernel<2>, kExactThreads, 0));
-    if (per_sm[v] < 1) per_sm[v] = 1;
+  // the replicated table pays once the survivors outnumber its set-up (200 KB per block)
+  const int rep = (ctx->exact_rep && args.metric != HS_METRIC_BLOSUM_INT && args.nsurv >= (1ull << 20)) ? 1 : 0;
+  const int threads = rep ? kExactThreadsRep : kExactThreads;
+  const size_t smem = rep ? kSqBytes8 : kSqBytes1;
+  const unsigned long long want = (args.nsurv + threads - 1) / threads;
+  if (!per_sm[v][rep]) {
+    HS_CUDA(cudaFuncSetAttribute(exact_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSqBytes8));
+    HS_CUDA(cudaFuncSetAttribute(exact_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSqBytes8));
+    HS_CUDA(cudaFuncSetAttribute(exact_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSqBytes1));
+    HS_CUDA(cudaFuncSetAttribute(exact_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSqBytes1));
+    if (v == 0 && rep == 0) HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v][rep], exact_kernel<1, 1>, threads, smem));
+    if (v == 1 && rep == 0) HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v][rep], exact_kernel<2, 1>, threads, smem));
+    if (v == 0 && rep == 1) HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v][rep], exact_kernel<1, 8>, threads, smem));
+    if (v == 1 && rep == 1) HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v][rep], exact_kernel<2, 8>, threads, smem));
+    if (per_sm[v][rep] < 1) per_sm[v][rep] = 1;
   }
-  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->num_sms * per_sm[v]);
-  if (v == 0) exact_kernel<1><<<grid, kExactThreads, 0, ctx->stream>>>(args);
-  else exact_kernel<2><<<grid, kExactThreads, 0, ctx->stream>>>(args);
+  const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->num_sms * per_sm[v][rep]);
+  if (v == 0 && rep == 0) exact_kernel<1, 1><<<grid, threads, smem, ctx->stream>>>(args);
+  else if (v == 1 && rep == 0) exact_kernel<2, 1><<<grid, threads, smem, ctx->stream>>>(args);
+  else if (v == 0) exact_kernel<1, 8><<<grid, threads, smem, ctx->stream>>>(args);
+  else exact_kernel<2, 8><<<grid, threads, smem, ctx->stream>>>(args);
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;

@@ -121,6 +121,8 @@ typedef struct {
   float ms_filter_tc;       /* inside ms_filter: the tensor-core (tcgen05) filter kernel */
   float ms_host;            /* search: host-side work-list construction between probe and filter */
   uint64_t n_candidates_tc; /* of n_candidates, pairs examined by the tensor-core filter */
+  uint64_t hash_sort_fallbacks; /* index build, multi-word keys: tables whose sort on the 64-bit key hash met two
+                               distinct keys with one hash and was redone on all key words (expected 0) */
 } hs_stats;
 
 /* ---- lifetime -------------------------------------------------------------- */
@@ -328,6 +330,16 @@ int hs_greedy_cluster(hs_ctx_t *ctx, uint32_t *center_out, uint32_t *round_out, 
 int hs_parse_fasta(const char *text, uint64_t nbytes, char *residues, uint64_t res_cap, uint64_t *start,
                    uint64_t start_cap, uint64_t *name_begin, uint32_t *name_len, uint64_t name_cap, uint32_t *nseq,
                    uint32_t *nnames, uint64_t *nres);
+/* The same parse on the device (fasta.cu): the text is copied to the GPU, two byte-parallel passes
+ * classify every byte (header line or sequence line from the start of its line), count and place
+ * the kept letters, the replaced letters and the header names; the replacement letters are drawn
+ * with rand() on the host, one per replaced letter in file order as the reference does, and
+ * patched in.  Outputs, counts, status and the state of rand() afterwards are those of
+ * hs_parse_fasta; texts of 4 GB and more are refused (HS_ERR_UNSUPPORTED).  The context's loaded
+ * database is not touched. */
+int hs_parse_fasta_gpu(hs_ctx_t *ctx, const char *text, uint64_t nbytes, char *residues, uint64_t res_cap,
+                       uint64_t *start, uint64_t start_cap, uint64_t *name_begin, uint32_t *name_len,
+                       uint64_t name_cap, uint32_t *nseq, uint32_t *nnames, uint64_t *nres);
 /* KLSH::KLSH (pcluster/src/pcluster/lsh.cpp:17-38): w[bits][feat] ~ N(0, sigma^2 as the
  * STANDARD DEVIATION), t[bits] ~ U[-1,1), b[bits] ~ U[0,2pi) from a default-constructed
  * std::default_random_engine (fixed seed: identical in every instance).  Host, libstdc++. */

@@ -67,6 +67,11 @@ def allpairs_config(n, length, metric, R):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:   # only the named sweep points: K,L,W ...
+        for t in sys.argv[1:]:
+            K, L, W = t.split(",")
+            search_config("C2 sweep", 10_000_000, 10_000, 10, int(K), int(L), float(W), 30.0)
+        sys.exit(0)
     search_config("C1 (configs[0])", 1_000_000, 1000, 10, 4, 4, 50.0, 30.0)
     search_config("C1 W=20", 1_000_000, 1000, 10, 4, 4, 20.0, 30.0)
     for K, L, W in [(2, 1, 50.0), (2, 4, 20.0), (4, 1, 50.0), (4, 4, 50.0), (4, 16, 50.0), (4, 4, 20.0), (4, 4, 10.0),

@@ -438,6 +438,87 @@ def test_rank_path_equals_packed_key_path(oracle, monkeypatch, length, K, L, W, 
         assert np.array_equal(l0, l1)
 
 
+@pytest.mark.parametrize("length,K,L,W,R", [(10, 16, 4, 200.0, 30.0), (10, 8, 3, 10.0, 30.0), (30, 8, 3, 50.0, 70.0),
+                                            (10, 16, 5, 20.0, 30.0)])
+def test_hashed_key_sort_equals_full_key_sort(oracle, monkeypatch, length, K, L, W, R):
+    """Multi-word keys (K >= 8 / small W) are sorted on a 64-bit hash of the key string, one word
+    instead of 2-4; every member's full key is checked against its bucket's.  The buckets (as sets of
+    ascending id lists: the reference's HashTable is an unordered_map, lsh.hpp:51-59), the table sizes
+    and the hits must equal the sort on all key words, also when a collision is reported (fallback)."""
+    codes = planted_families(30011, length, seed=15)
+    qcodes = planted_queries(codes, 300, seed=16)
+    res = []
+    for env in ({"HS_FORCE_HASH_SORT": "1"}, {"HS_NO_HASH_SORT": "1"}, {"HS_FORCE_HASH_COLLISION": "1"}, {}):
+        for k in ("HS_NO_HASH_SORT", "HS_FORCE_HASH_COLLISION", "HS_FORCE_HASH_SORT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+        h.load_fragments(codes)
+        h.build_index()
+        st = h.stats()
+        assert st.key_words >= 2 and st.rank_path == 0
+        assert st.hash_sort_fallbacks == (L if "HS_FORCE_HASH_COLLISION" in env else 0)
+        sizes = h.table_sizes()
+        buckets = []
+        for l in range(L):
+            ids, starts = h.table(l)
+            assert starts[0] == 0 and starts[-1] == len(codes) and np.all(np.diff(starts.astype(np.int64)) > 0)
+            bl = sorted(tuple(ids[starts[i]:starts[i + 1]].tolist()) for i in range(len(starts) - 1))
+            assert all(list(t) == sorted(t) for t in bl)
+            buckets.append(bl)
+        hits = h.search_codes(qcodes)
+        labels = h.cluster()
+        res.append((sizes, buckets, hits_as_tuples(hits), labels, st.sort_passes))
+        h.close()
+    for r in res[1:]:
+        assert np.array_equal(res[0][0], r[0])
+        assert res[0][1] == r[1]
+        assert len(r[2]) > 0 and res[0][2] == r[2]
+        assert np.array_equal(res[0][3], r[3])
+    assert res[0][4] <= 8 * L               # one word, <= 8 passes per table
+    assert res[3][4] in (res[0][4], res[1][4])   # the default picks one of the two
+    tab = oracle.coordinates(True)
+    want, ts, _ = oracle.search(oracle.embed(codes, tab), oracle.embed(qcodes, tab), a, b, W, R, pred=0)
+    assert np.array_equal(res[0][0], ts) and res[0][2] == hits_as_tuples(want)
+
+
+def test_lazy_code_stores_and_filter_bypass(monkeypatch):
+    """An index of tiny buckets (K = 16: millions of buckets of one or two members) is built without
+    the bucket-ordered code stores; a search with few candidates sends them straight to the exact
+    stage, a search with many (or hs_cluster) builds the stores first.  Hits and labels must equal
+    the eager build's."""
+    length, K, L, W, R = 10, 16, 3, 20.0, 30.0
+    n = (1 << 20) + 12345
+    codes = planted_families(200_000, length, seed=25)
+    codes = np.concatenate([codes, random_codes(n - len(codes), length, seed=26)])
+    qcodes = planted_queries(codes[:200_000], 2500, seed=27)
+    res = []
+    for env in ({"HS_NO_LAZY_STORES": "1"}, {}, {"HS_BYPASS_MAX": "10"}):
+        for k in ("HS_NO_LAZY_STORES", "HS_BYPASS_MAX"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        h, a, b = make(length, K, L, W, R, flags=hb.HS_FLAG_SORT_HITS)
+        h.load_fragments(codes)
+        h.build_index()
+        permute_ms = h.stats().ms_permute
+        hits = h.search_codes(qcodes)
+        st = h.stats()
+        hits2 = h.search_codes(qcodes[:100])
+        labels = h.cluster()
+        res.append((hits_as_tuples(hits), hits_as_tuples(hits2), labels, permute_ms, st.n_candidates, st.n_survivors,
+                    st.n_work_items))
+        h.close()
+    assert len(res[0][0]) > 0
+    for r in res[1:]:
+        assert r[0] == res[0][0] and r[1] == res[0][1] and np.array_equal(r[2], res[0][2])
+        assert r[3] == 0.0 < res[0][3]             # no store build inside hs_build_index
+    assert res[1][4] == res[1][5] and res[1][6] == 0   # bypass: every candidate is a survivor, no filter work list
+    assert res[2][5] <= res[2][4] and res[2][6] > 0    # stores built on demand, filter ran
+    assert res[0][4] == res[1][4] == res[2][4]
+
+
 def test_search_pipelined_blocks_equal_single_pass(oracle, monkeypatch):
     """>= 2048 queries with a host hit buffer: the survivors of the (single) filter pass are split
     by query block, and each block's sorted hits are copied out while the next block is verified

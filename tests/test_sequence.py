@@ -13,21 +13,32 @@ from oracle.pyoracle import Reference
 AA20 = "ARNDCEQGHILKMFPSTWYV"
 
 
-def parse_fasta(text):
+def parse_fasta(text, ctx=None, seed=None):
+    """hs_parse_fasta, or hs_parse_fasta_gpu on the context ctx; seed: srand() before each call."""
     lib = capi.load()
-    data = text.encode()
+    libc = C.CDLL(None)
+    data = text if isinstance(text, bytes) else text.encode()
     nseq, nnames, nres = C.c_uint32(), C.c_uint32(), C.c_uint64()
-    rc = lib.hs_parse_fasta(data, len(data), None, 0, None, 0, None, None, 0, C.byref(nseq), C.byref(nnames), C.byref(nres))
+    if ctx is not None:
+        def fn(*a):
+            return lib.hs_parse_fasta_gpu(ctx, *a)
+    else:
+        fn = lib.hs_parse_fasta
+    if seed is not None:
+        libc.srand(seed)
+    rc = fn(data, len(data), None, 0, None, 0, None, None, 0, C.byref(nseq), C.byref(nnames), C.byref(nres))
     assert rc in (capi.HS_OK, -3)
+    if seed is not None:
+        libc.srand(seed)
     res = C.create_string_buffer(max(1, nres.value))
     start = np.zeros(nseq.value + 1, dtype=np.uint64)
     nb = np.zeros(max(1, nnames.value), dtype=np.uint64)
     nl = np.zeros(max(1, nnames.value), dtype=np.uint32)
-    capi.check(lib.hs_parse_fasta(data, len(data), res, nres.value, capi.ptr(start, C.c_uint64), len(start),
-                                  capi.ptr(nb, C.c_uint64), capi.ptr(nl, C.c_uint32), nnames.value, C.byref(nseq),
-                                  C.byref(nnames), C.byref(nres)))
-    seqs = [res.raw[int(start[i]):int(start[i + 1])].decode() for i in range(nseq.value)]
-    names = [data[int(nb[i]):int(nb[i]) + int(nl[i])].decode() for i in range(nnames.value)]
+    capi.check(fn(data, len(data), res, nres.value, capi.ptr(start, C.c_uint64), len(start),
+                  capi.ptr(nb, C.c_uint64), capi.ptr(nl, C.c_uint32), nnames.value, C.byref(nseq),
+                  C.byref(nnames), C.byref(nres)))
+    seqs = [res.raw[int(start[i]):int(start[i + 1])].decode("latin-1") for i in range(nseq.value)]
+    names = [data[int(nb[i]):int(nb[i]) + int(nl[i])].decode("latin-1") for i in range(nnames.value)]
     return names, seqs
 
 
@@ -154,4 +165,41 @@ def test_sequence_entry_points_edge_cases(oracle):
     ln = np.zeros(6, dtype=np.int32)
     out = C.create_string_buffer(8)
     assert h.lib.hs_orf6(h.ctx, data, capi.ptr(start, C.c_uint64), 1, out, 8, capi.ptr(ln, C.c_int32)) == capi.HS_ERR_CAPACITY
+    h.close()
+
+
+def _fasta_cases():
+    rng = np.random.default_rng(11)
+    cases = [b"", b">only\n", b"ARND\n>x\n12 3*-\nAR ND\n", b">a\n>b\n>c\nAR\n", b"\n\n>p q r\r\nARND\r\nbjz\n\n",
+             b">no newline at the end", b"ARNDX", b">h\n" + b"ARNDCEQGHI" * 2000 + b"\n>t\nxyz\n",   # a line longer than 4 chunks
+             b">" + b"n" * 9000 + b" tail\nAR\n",                                                      # a header longer than 2 chunks
+             b"A\x00R\xffN\n>x\x00y\n"]
+    alphabet = np.frombuffer(b"ARNDCEQGHILKMFPSTWYVBJOUXZarndxbz*- 0123456789>\r", dtype=np.uint8)
+    for nlines, maxlen in ((4000, 80), (300, 5000), (30000, 12)):
+        parts = []
+        for i in range(nlines):
+            r = rng.random()
+            if r < 0.15:
+                parts.append(b">prot%d" % i + (b" desc %d" % i if i % 3 else b""))
+            elif r < 0.2:
+                parts.append(b"")
+            else:
+                parts.append(alphabet[rng.integers(0, len(alphabet), size=int(rng.integers(0, maxlen)))].tobytes())
+        cases.append(b"\n".join(parts) + (b"\n" if nlines % 2 else b""))
+    return cases
+
+
+@pytest.mark.gpu
+def test_parse_fasta_gpu_equals_host_parser():
+    """hs_parse_fasta_gpu (byte-parallel, fasta.cu) against hs_parse_fasta (ReadFASTAFile,
+    read_proteins.cpp:6-41) under the same srand: names, sequences and replaced letters."""
+    h = hb.HSearch(10, 4, 4, 50.0, 30.0)
+    libc = C.CDLL(None)
+    for k, text in enumerate(_fasta_cases()):
+        want = parse_fasta(text, seed=100 + k)
+        after_host = libc.rand()
+        got = parse_fasta(text, ctx=h.ctx, seed=100 + k)
+        after_dev = libc.rand()
+        assert got == want, k
+        assert after_host == after_dev     # the same number of rand() draws
     h.close()
