@@ -30,7 +30,7 @@ EXPORTS = [
     "hs_greedy_cluster", "hs_union_find", "hs_parse_fasta", "hs_klsh_generate", "hs_kmer3_klsh", "hs_orf6",
     "hs_evaluate_recall", "hs_evaluate_recall_dev",
     "hs_search_points_compact", "hs_expand_hits", "hs_hits_checksum", "hs_hits_checksum_dev", "hs_hash_audit", "hs_comm_reserve", "hs_comm_result", "hs_protein_id", "hs_fragment_name",
-    "hs_parse_fasta_gpu",
+    "hs_parse_fasta_gpu", "hs_get_blosum_filter_embedding",
 ]
 
 
@@ -127,6 +127,7 @@ def load(build_if_missing=True):
     lib.hs_union_find.argtypes = [vp, C.c_uint32, u32p, u32p, C.c_uint64, u32p]
     lib.hs_parse_fasta.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, u64p, C.c_uint64, u64p, u32p,
                                    C.c_uint64, u32p, u32p, u64p]
+    lib.hs_get_blosum_filter_embedding.argtypes = [dblp]
     lib.hs_parse_fasta_gpu.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, u64p, C.c_uint64, u64p, u32p,
                                        C.c_uint64, u32p, u32p, u64p]
     lib.hs_klsh_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_double, dblp, dblp, dblp]

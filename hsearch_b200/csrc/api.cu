@@ -146,6 +146,12 @@ static int upload_tables(hs_ctx *ctx) {
   for (int i = 0; i < HS_AA * HS_AA; ++i) metric32[i] = (float)metric[i];
   HS_TRY(ctx->d_metric32.reserve(sizeof metric32));
   HS_CUDA(cudaMemcpyAsync(ctx->d_metric32.p, metric32, sizeof metric32, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->have_ftable = true;
+  if (ctx->prm.metric == HS_METRIC_BLOSUM_INT) ctx->have_ftable = blosum_filter_embedding(ctx->ftable64);
+  else memcpy(ctx->ftable64, ctx->table64, sizeof ctx->ftable64);
+  HS_TRY(ctx->d_ftable64.reserve(sizeof ctx->ftable64));
+  if (ctx->have_ftable)
+    HS_CUDA(cudaMemcpyAsync(ctx->d_ftable64.p, ctx->ftable64, sizeof ctx->ftable64, cudaMemcpyHostToDevice, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   return mma_upload_tables(ctx);
 }
@@ -500,6 +506,8 @@ static int plan_run(hs_ctx *ctx, FilterPlan &P, uint32_t tq_rows, uint32_t tq_ba
     if (mode == kModeAllPairs) HS_TRY(launch_build_qb_codes(ctx, tq_base, tq_rows, ctx->d_qb16.p));
     else if (mode == kModeSelfJoin)  // queries = positions tq_base .. of the (single) table of the plan
       HS_TRY(launch_build_qb_store(ctx, P.mma_items[0].table, tq_base, tq_rows, ctx->d_qb16.p));
+    else if (ctx->prm.metric == HS_METRIC_BLOSUM_INT)   // queries are residue codes (stage_queries checks)
+      HS_TRY(launch_build_qb_qcodes(ctx, ctx->d_qcodes.as<uint8_t>(), tq_rows, ctx->d_qb16.p));
     else HS_TRY(launch_build_qb_points(ctx, ctx->d_q64.as<double>(), tq_rows, ctx->d_qb16.p));
     ml.grid = grid;
     ml.nunits = nunits;
@@ -1479,6 +1487,7 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->force_hash_collision = env_on("HS_FORCE_HASH_COLLISION");
   ctx->force_hash_sort = ctx->force_hash_collision || env_on("HS_FORCE_HASH_SORT");
   ctx->no_mma_filter = env_on("HS_NO_MMA_FILTER");
+  ctx->no_mma_int = env_on("HS_NO_MMA_INT");
   ctx->surv_bins = env_on("HS_SURV_BINS");
   if (const char *e = getenv("HS_SELFJOIN_CHUNK"))
     if (atoi(e) >= 256) ctx->selfjoin_chunk = (uint32_t)atoi(e);

@@ -124,6 +124,11 @@ struct hs_ctx {
   // tables
   double table64[HS_AA * HS_CDIM];
   hs::DevBuf d_table64;  // f64 [20][8]
+  // the table the pipelined tensor filter embeds residues with: the coordinates (Euclidean metric)
+  // or a contracting embedding of the integer BLOSUM metric (tables.cpp: blosum_filter_embedding)
+  double ftable64[HS_AA * HS_CDIM];
+  hs::DevBuf d_ftable64;
+  bool have_ftable = false;
   hs::DevBuf d_dsq32;    // f32 [20][20] squared residue distances (filter)
   hs::DevBuf d_metric;   // i32 [20][20] integer BLOSUM metric
   hs::DevBuf d_metric32; // f32 copy (filter tables of the integer metric)
@@ -235,6 +240,7 @@ struct hs_ctx {
   bool plan_stats = false;       // HS_PLAN_STATS: print the filter work-list statistics
   uint32_t selfjoin_chunk = 1u << 16;  // HS_SELFJOIN_CHUNK: query members per tensor-filter pass of a large bucket (hs_cluster)
   bool surv_bins = false;        // HS_SURV_BINS: survivors regrouped by fragment-id block before the exact stage
+  bool no_mma_int = false;       // HS_NO_MMA_INT: the integer metric stays on the one-hot tensor filter (filter_tc.cu)
   bool no_mma_filter = false;    // HS_NO_MMA_FILTER: keep the Euclidean metric off the pipelined tensor filter
 
   hs_stats stats{};

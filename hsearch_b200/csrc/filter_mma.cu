@@ -1169,13 +1169,14 @@ int mma_geometry(const hs_ctx *ctx, MmaGeometry *g) {
 
 // The tensor path needs every table entry representable in FP16 without overflow.
 bool mma_filter_usable(const hs_ctx *ctx) {
-  if (ctx->prm.metric != HS_METRIC_EUCLID_FP64) return false;
+  if (!ctx->have_ftable) return false;   // (integer metric: no contracting embedding could be built)
+  if (ctx->prm.metric == HS_METRIC_BLOSUM_INT && ctx->no_mma_int) return false;
   if (ctx->prm.flags & HS_FLAG_SCALAR_FILTER) return false;
   if (ctx->no_mma_filter) return false;
   MmaGeometry g;
   if (mma_geometry(ctx, &g) != HS_OK) return false;
   for (int i = 0; i < HS_AA * HS_CDIM; ++i)
-    if (!(fabs(ctx->table64[i]) <= 1.0e3)) return false;
+    if (!(fabs(ctx->ftable64[i]) <= 1.0e3)) return false;
   return true;
 }
 
@@ -1186,7 +1187,7 @@ int mma_upload_tables(hs_ctx *ctx) {
   for (int c = 0; c < HS_AA; ++c) {
     double s = 0.0;
     for (int j = 0; j < HS_CDIM; ++j) {
-      const double v = ctx->table64[c * HS_CDIM + j];
+      const double v = ctx->have_ftable ? ctx->ftable64[c * HS_CDIM + j] : 0.0;
       h[c * HS_CDIM + j] = __double2half(v);
       s += v * v;
     }
@@ -1217,8 +1218,21 @@ int launch_build_qb_codes(hs_ctx *ctx, uint64_t q0, uint32_t nq, void *d_qb16) {
   MmaGeometry g;
   HS_TRY(mma_geometry(ctx, &g));
   build_qb_codes_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_codes.as<uint8_t>(), q0, nq,
-                                                                   (int)ctx->prm.len, g.kp, ctx->d_table64.as<double>(),
+                                                                   (int)ctx->prm.len, g.kp, ctx->d_ftable64.as<double>(),
                                                                    g.beta, reinterpret_cast<__half *>(d_qb16));
+  HS_CUDA(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return HS_OK;
+}
+
+// queries = nq residue strings at d_qcodes (integer metric: the embedded rows come from the filter table)
+int launch_build_qb_qcodes(hs_ctx *ctx, const uint8_t *d_qcodes, uint32_t nq, void *d_qb16) {
+  if (nq == 0) return HS_OK;
+  MmaGeometry g;
+  HS_TRY(mma_geometry(ctx, &g));
+  build_qb_codes_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(d_qcodes, 0, nq, (int)ctx->prm.len, g.kp,
+                                                                   ctx->d_ftable64.as<double>(), g.beta,
+                                                                   reinterpret_cast<__half *>(d_qb16));
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;
@@ -1230,7 +1244,7 @@ int launch_build_qb_store(hs_ctx *ctx, uint32_t table, uint32_t pos0, uint32_t n
   HS_TRY(mma_geometry(ctx, &g));
   build_qb_store_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(
       ctx->tables[table].codes_sorted.as<uint8_t>(), ctx->npad, pos0, nq, (int)ctx->prm.len, g.kp,
-      ctx->d_table64.as<double>(), g.beta, reinterpret_cast<__half *>(d_qb16));
+      ctx->d_ftable64.as<double>(), g.beta, reinterpret_cast<__half *>(d_qb16));
   HS_CUDA(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return HS_OK;
@@ -1260,8 +1274,10 @@ int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, co
   a.nstages = g.nstages;
   a.qmax = g.qmax;
   a.cring = g.cring;
-  // a reference hit has d2 <= R^2 (1 + 1e-12) in exact arithmetic
-  const double r2 = ctx->prm.R * ctx->prm.R * (1.0 + 1e-12) + 1e-30;
+  // a reference hit has d2 <= R^2 (1 + 1e-12) in exact arithmetic; with the integer metric a hit has
+  // integer distance <= (int)R, hence embedded squared distance <= (int)R (contracting embedding)
+  const double rr = ctx->prm.metric == HS_METRIC_BLOSUM_INT ? (double)(int)ctx->prm.R : ctx->prm.R * ctx->prm.R;
+  const double r2 = rr * (1.0 + 1e-12) + 1e-30;
   float thr = (float)r2;
   if ((double)thr < r2) thr = nextafterf(thr, INFINITY);
   a.thr = thr;

@@ -13,4 +13,5 @@ void set_error(const char *fmt, ...);
 const char *get_error();
 void coordinates_table(uint32_t variant, double *out160);
 void blosum_metric(int32_t *out400);
+bool blosum_filter_embedding(double *out160);
 }  // namespace hs

@@ -99,6 +99,104 @@ void blosum_metric(int32_t *out400) {
       out400[i * HS_AA + j] = kBlosum62[i][i] + kBlosum62[j][j] - 2 * kBlosum62[i][j];
 }
 
+// A contracting 8-dimensional embedding of the integer BLOSUM metric D (BLOSUM-Metric/src/
+// BLOSUM-metric/distance_matrix.hpp:13-20): points e(a) with |e(a) - e(b)|^2 <= D[a][b] for all
+// residues, so that for two fragments sum_p |e(x_p) - e(y_p)|^2 <= sum_p D[x_p][y_p], the window
+// distance of evaluate_correlation.cpp:26-41.  The pipelined tensor filter (filter_mma.cu) then
+// serves the integer metric unchanged: it keeps every pair whose embedded squared distance is
+// <= R, a superset of the pairs with integer distance <= R, and the exact stage decides on the
+// integers.  Classical multidimensional scaling of sqrt(D) (Jacobi eigen-decomposition of the
+// doubly centred matrix, eight largest eigenvalues), scaled down until every pair contracts; the
+// result is checked pair by pair and the function reports failure rather than return a table
+// that does not contract.  Tightness only affects the number of survivors (5e-6 of random pairs
+// at length 10, R = 30), never the result.
+bool blosum_filter_embedding(double *out160) {
+  constexpr int n = HS_AA;
+  int32_t D[n * n];
+  blosum_metric(D);
+  double B[n][n], V[n][n], rm[n], gm = 0.0;
+  for (int i = 0; i < n; ++i) {
+    rm[i] = 0.0;
+    for (int j = 0; j < n; ++j) rm[i] += (double)D[i * n + j];
+    rm[i] /= n;
+    gm += rm[i];
+  }
+  gm /= n;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      // symmetrised: the table is symmetric, this guards the decomposition only
+      const double d = 0.5 * ((double)D[i * n + j] + (double)D[j * n + i]);
+      B[i][j] = -0.5 * (d - rm[i] - rm[j] + gm);
+      V[i][j] = i == j ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) off += B[p][q] * B[p][q];
+    if (off < 1e-22) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        if (fabs(B[p][q]) < 1e-300) continue;
+        const double theta = (B[q][q] - B[p][p]) / (2.0 * B[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double bkp = B[k][p], bkq = B[k][q];
+          B[k][p] = c * bkp - sn * bkq;
+          B[k][q] = sn * bkp + c * bkq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double bpk = B[p][k], bqk = B[q][k];
+          B[p][k] = c * bpk - sn * bqk;
+          B[q][k] = sn * bpk + c * bqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - sn * vkq;
+          V[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  int order[n];
+  for (int i = 0; i < n; ++i) order[i] = i;
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      if (B[order[j]][order[j]] > B[order[i]][order[i]]) {
+        const int t = order[i];
+        order[i] = order[j];
+        order[j] = t;
+      }
+  for (int a = 0; a < n; ++a)
+    for (int j = 0; j < HS_CDIM; ++j) {
+      const double lam = B[order[j]][order[j]];
+      out160[a * HS_CDIM + j] = lam > 0.0 ? V[a][order[j]] * sqrt(lam) : 0.0;
+    }
+  auto d2 = [&](int a, int b) {
+    double s = 0.0;
+    for (int j = 0; j < HS_CDIM; ++j) {
+      const double r = out160[a * HS_CDIM + j] - out160[b * HS_CDIM + j];
+      s += r * r;
+    }
+    return s;
+  };
+  double s2 = 1e300;
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) {
+      if (a == b) continue;
+      if (D[a * n + b] < 0) return false;
+      const double e = d2(a, b);
+      if (e > 0.0) s2 = fmin(s2, (double)D[a * n + b] / e);
+    }
+  if (!(s2 > 0.0) || !(s2 < 1e300)) return false;
+  const double sc = sqrt(s2) * (1.0 - 1e-9);
+  for (int i = 0; i < n * HS_CDIM; ++i) out160[i] *= sc;
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b)
+      if (!(d2(a, b) <= (double)D[a * n + b] * (1.0 - 1e-10) + 0.0)) return false;
+  return true;
+}
+
+
 }  // namespace hs
 
 extern "C" {
@@ -117,6 +215,15 @@ int hs_get_coordinates(uint32_t table_variant, double *out160) {
 int hs_get_blosum_metric(int32_t *out400) {
   if (!out400) return HS_ERR_INVALID;
   hs::blosum_metric(out400);
+  return HS_OK;
+}
+
+int hs_get_blosum_filter_embedding(double *out160) {
+  if (!out160) return HS_ERR_INVALID;
+  if (!hs::blosum_filter_embedding(out160)) {
+    hs::set_error("hs_get_blosum_filter_embedding: no contracting embedding of the metric was found");
+    return HS_ERR_UNSUPPORTED;
+  }
   return HS_OK;
 }
 

@@ -102,6 +102,7 @@ bool mma_filter_usable(const hs_ctx *ctx);
 int mma_upload_tables(hs_ctx *ctx);
 int launch_build_qb_points(hs_ctx *ctx, const double *d_q64, uint32_t Q, void *d_qb16);
 int launch_build_qb_codes(hs_ctx *ctx, uint64_t q0, uint32_t nq, void *d_qb16);
+int launch_build_qb_qcodes(hs_ctx *ctx, const uint8_t *d_qcodes, uint32_t nq, void *d_qb16);
 int launch_build_qb_store(hs_ctx *ctx, uint32_t table, uint32_t pos0, uint32_t nq, void *d_qb16);
 int launch_filter_mma(hs_ctx *ctx, const FilterArgs &fa, const void *d_items, const void *d_units, uint32_t nunits,
                       uint32_t *d_unit_counter, uint32_t grid, const void *d_qb16, int mode);

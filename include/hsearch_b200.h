@@ -143,6 +143,11 @@ int hs_get_stream(hs_ctx_t *ctx, void **stream_out);
 int hs_get_coordinates(uint32_t table_variant, double *out160);
 /* out400 <- D[i][j] = B[i][i]+B[j][j]-2B[i][j] (distance_matrix.hpp:13-20). */
 int hs_get_blosum_metric(int32_t *out400);
+/* out160 <- the 20x8 table e the tensor filter embeds residues with under HS_METRIC_BLOSUM_INT:
+ * |e(a) - e(b)|^2 <= D[a][b] for every residue pair, so the embedded squared distance of two fragments
+ * never exceeds their integer window distance (evaluate_correlation.cpp:26-41) and a filter on it
+ * loses no pair within R; the exact stage decides on the integers.  Host function. */
+int hs_get_blosum_filter_embedding(double *out160);
 /* Override the ctx's embedding table (default: params.table_variant). */
 int hs_set_coordinates(hs_ctx_t *ctx, const double *table160);
 /* letter -> code (base[letter-'A'], util.hpp:92); -1 for non-amino-acid letters. */

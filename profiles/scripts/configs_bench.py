@@ -45,7 +45,10 @@ def search_config(name, n, q, length, K, L, W, R):
         db_fragments_per_s=round(n / (dev_ms * 1e-3)), hash_ms=round(s_hash["ms_hash"], 3),
         build_ms=round(s_build["ms_total"], 3), sort_passes=s_build["sort_passes"], search_ms=round(srch, 3),
         filter_ms=round(s_search["ms_filter"], 3), exact_ms=round(s_search["ms_exact"], 3),
-        hitsort_ms=round(s_search["ms_hitsort"], 3))
+        hitsort_ms=round(s_search["ms_hitsort"], 3), qhash_ms=round(s_search["ms_qhash"], 3),
+        probe_ms=round(s_search["ms_probe"], 3), host_ms=round(s_search["ms_host"], 3),
+        sort_ms=round(s_build["ms_sort"], 3), group_ms=round(s_build["ms_group"], 3),
+        permute_ms=round(s_build["ms_permute"], 3), hash_sort_fallbacks=s_build["hash_sort_fallbacks"])
     h.close()
 
 
@@ -69,6 +72,11 @@ def allpairs_config(n, length, metric, R):
 if __name__ == "__main__":
     if len(sys.argv) > 1:   # only the named sweep points: K,L,W ...
         for t in sys.argv[1:]:
+            if t == "allpairs":
+                n = int(os.environ.get("HS_C5_N", "1000000"))
+                for length in (8, 10, 12, 16, 20, 25, 30):
+                    allpairs_config(n, length, hb.HS_METRIC_BLOSUM_INT, float(3 * length))
+                continue
             K, L, W = t.split(",")
             search_config("C2 sweep", 10_000_000, 10_000, 10, int(K), int(L), float(W), 30.0)
         sys.exit(0)

@@ -140,3 +140,24 @@ def test_fragment_name_host():
     buf = C.create_string_buffer(8)
     assert lib.hs_fragment_name(b"name", 1, 2, b"ARN", 3, 4, buf, 8) == capi.HS_ERR_CAPACITY
     assert lib.hs_fragment_name(None, 1, 2, b"ARN", 3, 4, buf, 8) == capi.HS_ERR_INVALID
+
+
+def test_blosum_filter_embedding_contracts():
+    """The table the tensor filter uses for the integer metric must contract: |e(a) - e(b)|^2 <= D[a][b]
+    for all residue pairs (then sum_p |e(x_p) - e(y_p)|^2 <= the integer window distance,
+    evaluate_correlation.cpp:26-41, and the filter cannot lose a pair within R)."""
+    lib = capi.load()
+    e = np.zeros(160, dtype=np.float64)
+    capi.check(lib.hs_get_blosum_filter_embedding(e.ctypes.data_as(C.POINTER(C.c_double))))
+    D = np.zeros(400, dtype=np.int32)
+    capi.check(lib.hs_get_blosum_metric(D.ctypes.data_as(C.POINTER(C.c_int32))))
+    e = e.reshape(20, 8)
+    D = D.reshape(20, 20)
+    d2 = ((e[:, None, :] - e[None, :, :]) ** 2).sum(-1)
+    assert np.all(d2 <= D * (1 - 1e-11) + 1e-15)
+    off = ~np.eye(20, dtype=bool)
+    ratio = d2[off] / D[off]
+    assert ratio.max() > 0.999 and ratio.mean() > 0.5      # scaled until the tightest pair touches
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, 20, size=(2, 200000, 10))
+    assert np.all(d2[a, b].sum(1) <= D[a, b].sum(1))

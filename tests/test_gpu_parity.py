@@ -234,6 +234,41 @@ def test_bruteforce_int_metric_all_pairs(oracle, length, R):
     h.close()
 
 
+@pytest.mark.parametrize("length,R", [(8, 24), (10, 34), (12, 40), (25, 90), (30, 120)])
+def test_int_metric_on_pipelined_tensor_filter(oracle, monkeypatch, length, R):
+    """The integer BLOSUM metric runs through the pipelined tensor filter with a contracting embedding
+    (hs_get_blosum_filter_embedding): all-pairs, explicit-query brute force, LSH search and cluster
+    must equal the one-hot tensor filter (HS_NO_MMA_INT) and the scalar filter, and the oracle."""
+    n = 40000
+    codes = np.concatenate([planted_families(6000, length, seed=161), random_codes(n - 6000, length, seed=162)])
+    qcodes = planted_queries(codes[:6000], 300, seed=163)
+    res = []
+    for env, flags in (({}, 0), ({"HS_NO_MMA_INT": "1"}, 0), ({}, hb.HS_FLAG_SCALAR_FILTER)):
+        monkeypatch.delenv("HS_NO_MMA_INT", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        h = hb.HSearch(length, 4, 4, 50.0, float(R), metric=hb.HS_METRIC_BLOSUM_INT, predicate=hb.HS_PRED_SQRT_LE_R,
+                       flags=flags | hb.HS_FLAG_SORT_HITS)
+        h.seed_projection(12345)
+        h.load_fragments(codes)
+        allp = h.bruteforce_codes(None, cap=1 << 22)
+        st_all = h.stats()
+        expl = h.bruteforce_codes(qcodes, cap=1 << 22)
+        h.build_index()
+        srch = h.search_codes(qcodes, cap=1 << 22)
+        lab = h.cluster()
+        res.append((hits_as_tuples(allp, False), hits_as_tuples(expl, False), hits_as_tuples(srch), lab,
+                    st_all.n_candidates_tc, st_all.n_survivors))
+        h.close()
+    assert len(res[0][0]) > 0 and len(res[0][1]) > 0 and len(res[0][2]) > 0
+    for r in res[1:]:
+        assert r[0] == res[0][0] and r[1] == res[0][1] and r[2] == res[0][2] and np.array_equal(r[3], res[0][3])
+    assert res[0][4] > 0 and res[2][4] == 0          # tensor filter in use / scalar only
+    want = oracle.bruteforce_int(codes[:6000], None, R)
+    sub = [t for t in res[0][0] if t[1] < 6000]       # (query, db_id, dist): all-pairs hits inside the first 6000
+    assert sub == hits_as_tuples(want, False)
+
+
 def test_search_int_metric(oracle):
     """LSH candidates verified with the integer window distance (V3)."""
     n, q, R = 20000, 200, 40
