@@ -1518,7 +1518,7 @@ void hs_destroy(hs_ctx_t *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   comm_destroy(ctx);
-  DevBuf *bufs[] = {&ctx->d_table64, &ctx->d_dsq32, &ctx->d_metric, &ctx->d_a64, &ctx->d_b64, &ctx->d_T32,
+  DevBuf *bufs[] = {&ctx->d_table64, &ctx->d_dsq32, &ctx->d_metric, &ctx->d_a64, &ctx->d_a64t, &ctx->d_b64, &ctx->d_T32,
                     &ctx->d_b32, &ctx->d_eps32, &ctx->d_codes, &ctx->d_buckets, &ctx->d_codes_pm, &ctx->d_q64,
                     &ctx->d_qcodes, &ctx->d_qkeys, &ctx->d_qvalid, &ctx->d_qrange, &ctx->d_tq, &ctx->d_work,
                     &ctx->d_qlist, &ctx->d_surv, &ctx->d_hits, &ctx->d_counters, &ctx->d_hit_keys[0],
@@ -1536,7 +1536,6 @@ void hs_destroy(hs_ctx_t *ctx) {
     ctx->d_keys[l].release();
     ctx->tables[l].sorted_ids.release();
     ctx->tables[l].ukeys.release();
-    ctx->tables[l].ukeys_full.release();
     ctx->tables[l].bstart.release();
     ctx->tables[l].codes_sorted.release();
   }
@@ -1846,6 +1845,7 @@ int hs_build_index(hs_ctx_t *ctx) {
     const bool lazy = !ctx->no_lazy_stores && ctx->N >= (1u << 20) && nb_sum * 4 > (uint64_t)L * ctx->N &&
                       ctx->prm.metric == HS_METRIC_EUCLID_FP64;
     if (!lazy) HS_TRY(ensure_code_stores(ctx));
+    else HS_TRY(ensure_records(ctx));   // (the exact stage reads the fragment records; the store build makes them otherwise)
     HS_CUDA(cudaEventRecord(ev[5], ctx->stream));
     HS_CUDA(cudaEventSynchronize(ev[5]));
     ms_permute = ev_ms(ev[2], ev[5]);

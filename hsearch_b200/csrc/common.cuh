@@ -89,9 +89,8 @@ __host__ __device__ __forceinline__ uint64_t key_hash(const uint64_t *k) {
 struct TableIndex {
   DevBuf sorted_ids;    // u32 [N]  fragment ids in bucket order
   DevBuf ukeys;         // u64 [key_words][nslots]  keys of the bucket slots, ascending
-  DevBuf ukeys_full;    // u64 [key_words][nslots]  hashed-key path only: the key strings of the slots
-                        // (ukeys then holds the ascending 64-bit hashes of the key strings)
-  bool hashed_keys = false;
+  bool hashed_keys = false;  // hashed-key path (radix_sort.cu): ukeys holds the ascending 64-bit hashes of the slots'
+                             // key strings, one word per slot; a slot's key string is that of its first member
   DevBuf bstart;        // u32 [nslots+1]           bucket boundaries into sorted_ids
   DevBuf codes_sorted;  // u8  [len][npad]      code*4, position-major, bucket order
   uint64_t nb = 0;      // non-empty buckets (the reference's "table size")
@@ -138,6 +137,8 @@ struct hs_ctx {
   bool have_projection = false;
   std::vector<double> h_a, h_b;
   hs::DevBuf d_a64, d_b64;   // f64 [L][K][DIM], [L][K]
+  hs::DevBuf d_a64t;         // f64 [L][DIM][qh_group]: the projection rows transposed for the query hash
+  uint32_t qh_group = 1;     // K rounded up to a power of two
   hs::DevBuf d_T32;          // f32 [L][len][20][Kp]  residue-projection partial sums
   hs::DevBuf d_b32, d_eps32; // f32 [L][Kp]
   std::vector<float> h_b32, h_eps32;  // host copies (passed to the hash kernel as parameters)

@@ -1155,7 +1155,7 @@ int mma_geometry(const hs_ctx *ctx, MmaGeometry *g) {
   const size_t budget = 168 * 1024;  // operands; the code ring (<= 16 KB) and ~38 KB static come on top
   int S = 3;
   if ((size_t)S * a_stage > budget / 2) S = 2;
-  if ((size_t)S * a_stage > budget * 3 / 4) return HS_ERR_UNSUPPORTED;
+  if ((size_t)S * a_stage > budget - 32 * 1024) return HS_ERR_UNSUPPORTED;   // (len 30: two 64 KB stages, 80 queries)
   size_t rows = (budget - (size_t)S * a_stage) / ((size_t)(g->kp >> 3) * 16);
   int qmax = (int)std::min<size_t>(512, rows) & ~15;
   if (qmax < 16) return HS_ERR_UNSUPPORTED;

@@ -305,22 +305,40 @@ hash_exact_kernel(const uint8_t *__restrict__ codes, uint64_t N, int len,
 // Query hash (motif_both_points.cpp:227): one thread per (query, table), FP64
 // in reference order.  qkeys [L][Q][KW]; qvalid[L][Q] = 0 when the key string
 // is longer than any DB key can be (then it matches no bucket).
+// GP = K rounded up to a power of two (<= 32) lanes evaluate the K projections of one (query,
+// table) pair, lane k the k-th: the query point is read once per group (broadcast), the projection
+// rows from a transposed copy a64t[l][i][k] (consecutive lanes, consecutive doubles).  Each lane runs
+// the reference's sequential multiply-add over the dim coordinates (exact_bucket_point's order);
+// the group's first lane then strings the K buckets together.  (One thread per pair, K projections
+// in sequence, read the points with a 640-byte stride between lanes: 5 ms at K = 16, L = 32.)
 template <int KW>
 __global__ void hash_queries_kernel(const double *__restrict__ q64, uint32_t Q, int dim,
-                                    const double *__restrict__ a64, const double *__restrict__ b64,
-                                    double W, int K, int L, uint64_t *__restrict__ qkeys,
+                                    const double *__restrict__ a64t, const double *__restrict__ b64,
+                                    double W, int K, int GP, int L, uint64_t *__restrict__ qkeys,
                                     uint8_t *__restrict__ qvalid) {
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Q * (uint32_t)L) return;
-  const uint32_t l = idx / Q, q = idx - l * Q;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t pair = t / (uint32_t)GP;
+  const int k = (int)(t % (uint32_t)GP);
+  const bool live = pair < (uint64_t)Q * (uint32_t)L;
+  const uint32_t l = live ? (uint32_t)(pair / Q) : 0u, q = live ? (uint32_t)(pair - (uint64_t)l * Q) : 0u;
+  int bucket = 0;
+  if (live && k < K) {
+    const double *pt = q64 + (size_t)q * dim;
+    const double *arow = a64t + (size_t)l * dim * GP + k;
+    double dot = 0.0;
+    for (int i = 0; i < dim; ++i) dot = __dadd_rn(dot, __dmul_rn(pt[i], arow[(size_t)i * GP]));
+    const double val = __dadd_rn(dot, b64[l * K + k]);
+    bucket = (int)floor(__ddiv_rn(val, W));
+  }
   KeyBuilder<KW> kb;
   kb.reset();
-  const double *pt = q64 + (size_t)q * dim;
-  for (int k = 0; k < K; ++k)
-    kb.push_int(exact_bucket_point(pt, dim, a64 + ((size_t)l * K + k) * dim, b64[l * K + k], W));
+  const int gbase = (threadIdx.x & 31) & ~(GP - 1);
+  for (int kk = 0; kk < K; ++kk) kb.push_int(__shfl_sync(0xffffffffu, bucket, gbase + kk));
+  if (live && k == 0) {
 #pragma unroll
-  for (int w = 0; w < KW; ++w) qkeys[((size_t)l * Q + q) * KW + w] = kb.w[w];
-  qvalid[(size_t)l * Q + q] = kb.nchars <= 16 * KW ? 1 : 0;
+    for (int w = 0; w < KW; ++w) qkeys[((size_t)l * Q + q) * KW + w] = kb.w[w];
+    qvalid[(size_t)l * Q + q] = kb.nchars <= 16 * KW ? 1 : 0;
+  }
 }
 
 // ---- host side ---------------------------------------------------------------
@@ -501,13 +519,13 @@ int launch_hash_exact(hs_ctx *ctx, bool want_buckets, bool audit) {
 }
 
 int launch_hash_queries(hs_ctx *ctx, const double *d_q64, uint32_t Q, uint64_t *d_qkeys, uint8_t *d_qvalid) {
-  const uint32_t n = Q * ctx->prm.L;
+  const uint64_t n = (uint64_t)Q * ctx->prm.L * ctx->qh_group;
   if (n == 0) return HS_OK;
-  const unsigned grid = (n + 127) / 128;
+  const unsigned grid = (unsigned)((n + 127) / 128);
 #define HS_QH(KWV)                                                                                        \
-  hash_queries_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(d_q64, Q, (int)ctx->dim, ctx->d_a64.as<double>(), \
-                                                          ctx->d_b64.as<double>(), ctx->prm.W,             \
-                                                          (int)ctx->prm.K, (int)ctx->prm.L, d_qkeys, d_qvalid)
+  hash_queries_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(d_q64, Q, (int)ctx->dim, ctx->d_a64t.as<double>(), \
+                                                          ctx->d_b64.as<double>(), ctx->prm.W, (int)ctx->prm.K, \
+                                                          (int)ctx->qh_group, (int)ctx->prm.L, d_qkeys, d_qvalid)
   switch (ctx->key_words) {
     case 1: HS_QH(1); break;
     case 2: HS_QH(2); break;
@@ -632,6 +650,19 @@ int setup_projection(hs_ctx *ctx, const double *a, const double *b) {
   HS_TRY(ctx->d_b64.reserve(sizeof(double) * L * K));
   HS_CUDA(cudaMemcpyAsync(ctx->d_a64.p, a, sizeof(double) * L * K * dim, cudaMemcpyHostToDevice, ctx->stream));
   HS_CUDA(cudaMemcpyAsync(ctx->d_b64.p, b, sizeof(double) * L * K, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    // transposed copy for the query hash: a64t[l][i][k], k padded to a power of two (hash_queries_kernel)
+    uint32_t gp = 1;
+    while (gp < K) gp <<= 1;
+    ctx->qh_group = gp;
+    std::vector<double> at((size_t)L * dim * gp, 0.0);
+    for (uint32_t l = 0; l < L; ++l)
+      for (uint32_t k = 0; k < K; ++k)
+        for (uint32_t i = 0; i < dim; ++i) at[((size_t)l * dim + i) * gp + k] = a[((size_t)l * K + k) * dim + i];
+    HS_TRY(ctx->d_a64t.reserve(sizeof(double) * at.size()));
+    HS_CUDA(cudaMemcpyAsync(ctx->d_a64t.p, at.data(), sizeof(double) * at.size(), cudaMemcpyHostToDevice, ctx->stream));
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));   // `at` is a temporary
+  }
 
   ctx->Kp = (K + 3u) & ~3u;
   ctx->tpc = std::max<uint32_t>(1u, std::min<uint32_t>(L, 32u / ctx->Kp));

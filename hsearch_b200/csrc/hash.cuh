@@ -39,21 +39,27 @@ struct KeyBuilder {
     w[0] = (w[0] << 4) | (uint64_t)nib;
     ++nchars;
   }
-  // std::to_string(int)
+  // std::to_string(int): the whole string (sign and digits, <= 11 characters) is assembled in one
+  // word and appended with a single multi-word shift
   __device__ __forceinline__ void push_int(int v) {
     uint32_t u = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
-    if (v < 0) push(11u);
-    if (u < 10u) {
-      push(u + 1u);
-      return;
+    uint64_t str = 0;
+    int nc = 0;
+    do {
+      const uint32_t q = u / 10u;
+      str |= (uint64_t)(u - q * 10u + 1u) << (4 * nc);
+      u = q;
+      ++nc;
+    } while (u);
+    if (v < 0) {
+      str |= 11ull << (4 * nc);
+      ++nc;
     }
-    uint32_t p = 10u;
-    while (u / p >= 10u) p *= 10u;
-    for (; p > 0u; p /= 10u) {
-      uint32_t d = u / p;
-      u -= d * p;
-      push(d + 1u);
-    }
+    const int sh = 4 * nc;  // 4 .. 44
+#pragma unroll
+    for (int j = KW - 1; j > 0; --j) w[j] = (w[j] << sh) | (w[j - 1] >> (64 - sh));
+    w[0] = (w[0] << sh) | str;
+    nchars += nc;
   }
 };
 

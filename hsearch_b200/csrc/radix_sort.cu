@@ -1045,21 +1045,16 @@ __global__ void key_hash_kernel(KeyPtrs keys, uint64_t n, uint64_t *__restrict__
   out[i] = key_hash<NW>(k);
 }
 
+// Every member that is not the head of its hash group compares its full key with the head's (the
+// heads' keys are re-read by the whole group: cached); singletons -- nearly all groups at large K --
+// cost nothing.  The probe fetches a slot's full key through the head's id (verify.cu).
 template <int NW>
 __global__ void hashed_buckets_kernel(KeyPtrs keys /* by fragment id */, uint64_t n, const uint32_t *__restrict__ ids,
                                       const uint32_t *__restrict__ flags, const uint32_t *__restrict__ scanned,
-                                      const uint32_t *__restrict__ bstart, uint64_t nb,
-                                      uint64_t *__restrict__ ukeys_full /* [NW][nb] */,
-                                      unsigned int *__restrict__ mismatches) {
+                                      const uint32_t *__restrict__ bstart, unsigned int *__restrict__ mismatches) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || flags[i]) return;
   const uint32_t id = ids[i];
-  if (flags[i]) {
-    const uint32_t b = scanned[i];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) ukeys_full[(uint64_t)w * nb + b] = keys.w[w][id];
-    return;
-  }
   const uint32_t head = ids[bstart[scanned[i] - 1]];
   bool same = true;
 #pragma unroll
@@ -1097,13 +1092,11 @@ static int build_table_index_hashed(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_
   HS_TRY(radix_sort_pairs(ctx, hin, nullptr, n, 1, T.sorted_ids.as<uint32_t>(), S.vals_alt.as<uint32_t>(), &hsorted, ~0ull));
   HS_CUDA(cudaEventRecord(ev_sort_end, ctx->stream));
   HS_TRY(group_inst<1>(ctx, table, hsorted));   // ukeys = the ascending hashes, bstart
-  const uint64_t nb = T.nb;
-  HS_TRY(T.ukeys_full.reserve(sizeof(uint64_t) * NW * std::max<uint64_t>(nb, 1)));
   unsigned int *mism = S.or_and.as<unsigned int>() + 2;
   HS_CUDA(cudaMemsetAsync(mism, 0, sizeof(unsigned int), ctx->stream));
   uint32_t *flags = S.flags.as<uint32_t>();
   hashed_buckets_kernel<NW><<<grid, 256, 0, ctx->stream>>>(in, n, T.sorted_ids.as<uint32_t>(), flags, flags + n,
-                                                          T.bstart.as<uint32_t>(), nb, T.ukeys_full.as<uint64_t>(), mism);
+                                                          T.bstart.as<uint32_t>(), mism);
   ctx->stats.kernel_launches++;
   HS_CUDA(cudaGetLastError());
   unsigned int h_mism = 0;

@@ -70,11 +70,13 @@ __global__ void probe_kernel(const uint64_t *__restrict__ qkeys /* [Q][KW] of th
 }
 
 // Hashed-key path (radix_sort.cu): binary search over the ascending key hashes, then the full key
-// of the slot decides (a query whose key merely shares a bucket's hash finds nothing).
+// of the slot -- the key of its first member -- decides (a query whose key merely shares a
+// bucket's hash finds nothing).
 template <int KW>
 __global__ void probe_hashed_kernel(const uint64_t *__restrict__ qkeys, const uint8_t *__restrict__ qvalid, uint32_t Q,
                                     const uint64_t *__restrict__ uhash /* [nb] */,
-                                    const uint64_t *__restrict__ ukeys_full /* [KW][nb] */, uint64_t nb,
+                                    const uint64_t *__restrict__ dbkeys /* [KW][N] by fragment id */, uint64_t N,
+                                    const uint32_t *__restrict__ ids, uint64_t nb,
                                     const uint32_t *__restrict__ bstart, uint2 *__restrict__ qrange,
                                     uint32_t *__restrict__ qrank) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,11 +94,13 @@ __global__ void probe_hashed_kernel(const uint64_t *__restrict__ qkeys, const ui
       if (uhash[m] < h) lo = m + 1; else hi = m;
     }
     if (lo < nb && uhash[lo] == h) {
+      const uint32_t b0 = bstart[lo];
+      const uint32_t head = ids[b0];
       bool eq = true;
 #pragma unroll
-      for (int w = 0; w < KW; ++w) eq = eq && (ukeys_full[(uint64_t)w * nb + lo] == k[w]);
+      for (int w = 0; w < KW; ++w) eq = eq && (dbkeys[(uint64_t)w * N + head] == k[w]);
       if (eq) {
-        r = make_uint2(bstart[lo], bstart[lo + 1]);
+        r = make_uint2(b0, bstart[lo + 1]);
         slot = (uint32_t)lo;
       }
     }
@@ -117,7 +121,8 @@ int launch_probe(hs_ctx *ctx, uint32_t table, const uint64_t *d_qkeys, const uin
   if (T.hashed_keys) {
 #define HS_PROBE_H(KWV)                                                                                    \
   probe_hashed_kernel<KWV><<<grid, 128, 0, ctx->stream>>>(qk, qv, Q, T.ukeys.as<uint64_t>(),                \
-                                                          T.ukeys_full.as<uint64_t>(), T.nslots,            \
+                                                          ctx->d_keys[table].as<uint64_t>(), ctx->N,         \
+                                                          T.sorted_ids.as<uint32_t>(), T.nslots,            \
                                                           T.bstart.as<uint32_t>(), qr, qs)
     switch (ctx->key_words) {
       case 2: HS_PROBE_H(2); break;
