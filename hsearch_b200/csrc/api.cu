@@ -1828,6 +1828,7 @@ int hs_build_index(hs_ctx_t *ctx) {
   float ms_sort = 0.f, ms_group = 0.f, ms_permute = 0.f;
   cudaEvent_t *ev = ctx->ev;
   HS_CUDA(cudaEventRecord(ev[8], ctx->stream));
+  ctx->hash_sort_choice = -1;
   if (ctx->N) {
     for (uint32_t l = 0; l < L; ++l) {
       HS_CUDA(cudaEventRecord(ev[2], ctx->stream));

@@ -232,6 +232,7 @@ struct hs_ctx {
   bool no_pipeline = false;      // HS_NO_PIPELINE: host-buffer searches in one pass (no query blocks)
   bool no_load_overlap = false;  // HS_NO_LOAD_OVERLAP: hs_load_fragments copies first, hashes later
   bool no_hash_sort = false;     // HS_NO_HASH_SORT: multi-word keys sorted on every word (no 64-bit key hash)
+  int hash_sort_choice = -1;          // this index build: -1 undecided, 0 sort on all key words, 1 sort on the key hash
   bool force_hash_sort = false;       // HS_FORCE_HASH_SORT: multi-word keys always take the hashed sort (tests)
   bool force_hash_collision = false;  // HS_FORCE_HASH_COLLISION: test hook, the hashed sort reports a collision
   bool exact_rep = true;         // HS_EXACT_REP=0: exact stage without the 8-fold replicated residue-pair table

