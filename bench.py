@@ -785,7 +785,7 @@ def run_cluster(a):
     N, length = a.n_db, a.len
     h = hb.HSearch(length, a.K, a.L, a.W, a.R, table_variant=hb.HS_TABLE_PRINT6, predicate=hb.HS_PRED_SQRT_LE_R,
                    device=local)
-    h.seed_projection(12345)
+    pa, pb = h.seed_projection(12345)
     # families of ten: a root per ten fragments, each member with up to two substituted residues
     g = torch.Generator(device=dev)
     g.manual_seed(5)                      # the same DB on every rank
@@ -857,6 +857,30 @@ def run_cluster(a):
         same = bool(lo.item() == hi.item())
     else:
         ms_step, pairs_all, surv_all, edges_all = dev_ms / a.steps, pairs, surv, edges
+    # Exact check against the oracle on whole families: the components the oracle finds among a sub-sample
+    # alone (its own buckets, its own pairs) must each lie inside one component of the full result --
+    # every edge of the sub-sample is an edge of the whole database.  (Equality cannot be asked: fragments
+    # outside the sub-sample may connect two of its components.)
+    sub_check = None
+    if rank == 0 and not a.no_subset_check:
+        try:
+            from oracle.pyoracle import Oracle
+            o = Oracle()
+            nfam = min(3_000, nroot)   # 30,000 fragments: ~10 s of CPU (the oracle joins every in-bucket pair)
+            sub_ids = np.sort((np.arange(nfam)[:, None] + nroot * np.arange(10)[None, :]).reshape(-1))
+            sub_ids = sub_ids[sub_ids < N]
+            sub_codes = codes[torch.from_numpy(sub_ids).to(dev)].cpu().numpy()
+            t0c = time.perf_counter()
+            lab_sub, ne_sub = o.cluster(sub_codes, hb.coordinates(hb.HS_TABLE_PRINT6), pa, pb, a.W, a.R, metric=0)
+            full_sub = labels[sub_ids]
+            ok = bool(np.array_equal(full_sub, full_sub[lab_sub]))
+            sub_check = {"fragments": int(len(sub_ids)), "oracle_edges": int(ne_sub),
+                         "oracle_components": int(len(np.unique(lab_sub))),
+                         "oracle_components_inside_full_components": ok,
+                         "full_components_over_the_sample": int(len(np.unique(full_sub))),
+                         "cpu_seconds": round(time.perf_counter() - t0c, 1)}
+        except Exception as e:  # the check is reported, never silently dropped
+            sub_check = {"error": repr(e)}
     if rank == 0:
         out = {"metric": "in_bucket_pairs_joined_per_s", "value": pairs_all / (ms_step * 1e-3), "unit": "pairs/s",
                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
@@ -872,7 +896,8 @@ def run_cluster(a):
                "gpu_launches": int(launches),
                "counts": {"pairs": pairs_all, "survivors": surv_all, "edges": edges_all,
                           "clusters": int(len(np.unique(labels)))},
-               "checks": {"labels_equal_on_all_ranks": same, "label_checksum": f"{csum:016x}"}}
+               "checks": {"labels_equal_on_all_ranks": same, "label_checksum": f"{csum:016x}",
+                          "subsample_vs_oracle": sub_check}}
         print(json.dumps(out), flush=True)
     h.close()
     if world > 1:

@@ -298,3 +298,33 @@ def gpu_cluster_callbacks(h, a, b, codes_local):
         return h.union_find(n_total, eu, ev)
 
     return key_fn, local_edges_fn, union_fn
+
+
+# ---- hs_cluster on a communicator (cluster.cu): host mirror of its arithmetic ---------------------
+def component_labels(n, eu, ev):
+    """label[i] = smallest id of i's component under the edges (eu[k], ev[k]) -- what hs_cluster and
+    hs_union_find return (union_find.cpp:16-33: FindRoot / JoinUnion; the partition does not depend
+    on the edge order).  Plain numpy label propagation, for tests and small inputs."""
+    label = np.arange(n, dtype=np.int64)
+    eu = np.asarray(eu, dtype=np.int64)
+    ev = np.asarray(ev, dtype=np.int64)
+    while True:
+        lo = np.minimum(label[eu], label[ev])
+        new = label.copy()
+        np.minimum.at(new, eu, lo)
+        np.minimum.at(new, ev, lo)
+        new = new[new]                      # pointer jumping
+        if np.array_equal(new, label):
+            return label.astype(np.uint32)
+        label = new
+
+
+def merge_partial_labels(all_labels):
+    """The exchange step of hs_cluster on several GPUs: every rank labelled the components of ITS share
+    of the pairs; label l of fragment i under any rank's share is the edge (i, l) of the whole graph
+    (uf_merge_labels_kernel), so the components of all those edges are the components of the whole
+    edge set.  all_labels: [world][n] (the all-gathered labels); returns the complete labels."""
+    all_labels = np.asarray(all_labels)
+    world, n = all_labels.shape
+    i = np.tile(np.arange(n, dtype=np.int64), world)
+    return component_labels(n, i, all_labels.reshape(-1).astype(np.int64))

@@ -234,3 +234,37 @@ def test_recall_sharded_world2_matches_single_process(tmp_path):
     mp.spawn(_recall_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r0, r1 = float(open(tmp_path / "ok0").read()), float(open(tmp_path / "ok1").read())
     assert r0 == r1 and 0.0 < r0 < 1.0
+
+
+def _label_merge_worker(rank, world, port, tmpdir):
+    """hs_cluster on a communicator (cluster.cu) with the transport replaced by gloo: every rank
+    labels the components of its round-robin share of the edges, the labels are all-gathered and
+    merged (dist.merge_partial_labels); every rank must end with the labels of the whole edge set."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(17)               # the same graph on every rank
+        n = 4000
+        # chains, stars and random edges: components that only close across the ranks' shares
+        eu = np.concatenate([np.arange(0, 999), np.full(300, 1500), rng.integers(2000, n, size=900)])
+        ev = np.concatenate([np.arange(1, 1000), np.arange(1501, 1801), rng.integers(2000, n, size=900)])
+        mine = np.arange(len(eu)) % world == rank
+        part = torch.from_numpy(hdist.component_labels(n, eu[mine], ev[mine]).astype(np.int64))
+        allp = [torch.zeros_like(part) for _ in range(world)]
+        dist.all_gather(allp, part)
+        got = hdist.merge_partial_labels(np.stack([p.numpy() for p in allp]))
+        want = hdist.component_labels(n, eu, ev)
+        assert np.array_equal(got, want)
+        assert want[999] == 0 and want[1800] == 1500 and len(np.unique(want)) < n
+        assert not np.array_equal(part.numpy(), want)   # a single share does not give the answer
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("1")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_cluster_label_merge_world_n(tmp_path, world):
+    mp.spawn(_label_merge_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
