@@ -60,7 +60,7 @@ def build(force=False, verbose=False, ptxas_verbose=False):
     return LIB
 
 
-CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints", "hclust2", "hclust3", "evaluate2", "orf"]
+CLI = ["motif_both_points", "motif_both_points_noLSH", "protein2datapoints", "hclust2", "hclust3", "evaluate2", "orf", "pcluster"]
 BIN = os.path.join(HERE, "bin")
 
 

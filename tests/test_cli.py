@@ -317,3 +317,54 @@ def test_orf_program_matches_oracle(tmp_path, oracle):
             want += [f"read{i} x_{j}", frame]
     assert len(want) > 20 and got == want
     assert run(OURS, "orf", [], tmp_path)[0] != 0
+
+
+# ---------------------------------------------------------------- pcluster (E4 + KL1)
+@pytest.mark.gpu
+def test_pcluster_program_pregroups(tmp_path, oracle):
+    """`pcluster -d fasta -o out` (pcluster.cpp:84-181): FASTA read on the device, 3-mer KLSH pre-clustering,
+    the reference's progress lines; the pre-groups must be those of the oracle's restatement of
+    Kmer2Integer + KLSH::GetHashValue (pinned to the reference's own in test_sequence.py) over the sequences the host parser (ReadFASTAFile) yields
+    under the same srand."""
+    import ctypes as C
+    from tests.test_sequence import parse_fasta
+    _ensure_built()
+    rng = np.random.default_rng(8)
+    aa = "ARNDCEQGHILKMFPSTWYV"
+    lines = []
+    for i in range(400):
+        lines.append(f">p{i} some description" if i % 4 else f">p{i}")
+        n = int(rng.integers(0, 200)) if i % 17 else int(rng.integers(0, 3))     # some shorter than a 3-mer
+        seq = "".join(aa[c] for c in rng.integers(0, 20, size=n))
+        if i % 11 == 0 and n > 5:
+            seq = seq[:3] + "xbz" + seq[3:]                                       # letters the reader replaces
+        for k in range(0, len(seq), 60):
+            lines.append(seq[k:k + 60])
+    text = "\n".join(lines) + "\n"
+    (tmp_path / "db.fa").write_text(text)
+    rc, out, err = run(OURS, "pcluster", ["-d", "db.fa", "-o", "groups.txt"], tmp_path, env={"HS_SEED": "7"})
+    assert rc == 0, err
+    names, seqs = parse_fasta(text, seed=7)
+    w, t, b = oracle.klsh_generate(512, 16, 0.2)
+    want = {}
+    for i, s_ in enumerate(seqs):
+        if len(s_) < 3:
+            continue
+        want.setdefault(oracle.klsh_hash(oracle.kmer3_features(s_), w, t, b), []).append(i)
+    got = {}
+    for line in open(tmp_path / "groups.txt").read().splitlines():
+        hv, n, members = line.split("\t")
+        got[int(hv)] = [int(x) for x in members.split()]
+        assert len(got[int(hv)]) == int(n)
+    assert len(want) > 5 and got == want
+    assert list(got) == sorted(got)
+    e = err.splitlines()
+    assert e[0] == "[WELCOME TO PCLUSTER v1.0]" and e[1] == "[pcluster -d db.fa -o groups.txt]"
+    assert e[2] == f"[THE TOTAL NUMBER OF PROTEINS IN THE DATABASE IS {len(seqs)}]"
+    assert e[3] == f"[NUMBER OF PRE-GROUPS {len(want)}]"
+    assert e[4].startswith("[Locality-Sensitive Hashing Pre-Clustering TAKES ")
+    assert e[5] == f"[CLUSTERING GROUP 0 of {len(want)}]"
+    # the reference's exit protocol: help / missing option on stderr, status 0 (pcluster.cpp:132-143)
+    assert run(OURS, "pcluster", [], tmp_path)[0] == 0
+    rc, out, err = run(OURS, "pcluster", ["-d", "db.fa"], tmp_path)
+    assert rc == 0 and "required argument missing" in err
