@@ -596,8 +596,9 @@ def run_native(a):
                     "avg_launch_ms": d["ms"] / max(1, d["launches"]), "share_of_step": d["share_of_step"],
                     "note": ("tcgen05 FP16 contraction <x_m, q> over every (query, bucket member) pair, 2*8*len flops "
                              "per pair; ablations (profiles/r02_filter_experiments.md): MMAs 4 ms, TMEM loads 2 ms, scan 9 ms, "
-                             "barrier traffic between the 22 warps 17 ms of the 35 ms launch; 21 G warp instructions, issue slots "
-                             "57 % busy: bound by instruction issue, not by the tensor pipe")}
+                             "hand-offs between the 22 warps 17 ms of the 35 ms launch; floors: tensor time 6.8 ms, shared-memory "
+                             "operand and A-tile traffic 10.5 ms (2.65 GB per SM at 128 B/clk); the tensor pipe is active 22 % of "
+                             "the cycles (DESIGN.md, open items)")}
     else:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": d["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
