@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhsearch_b200.so")
-CU = ["api.cu", "hash.cu", "radix_sort.cu", "verify.cu", "filter_tc.cu", "filter_mma.cu", "cluster.cu", "extract.cu", "sequence.cu", "evaluate.cu", "hits.cu", "comm.cu", "fasta.cu"]
+CU = ["api.cu", "hash.cu", "radix_sort.cu", "verify.cu", "filter_tc.cu", "filter_mma.cu", "cluster.cu", "extract.cu", "sequence.cu", "evaluate.cu", "hits.cu", "comm.cu", "fasta.cu", "hitsort.cu"]
 CPP = ["tables.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

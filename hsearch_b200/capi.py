@@ -65,7 +65,8 @@ class Stats(C.Structure):
                 ("ms_sort_upsweep", C.c_float), ("ms_sort_scan", C.c_float), ("ms_sort_downsweep", C.c_float),
                 ("ms_qhash", C.c_float), ("ms_probe", C.c_float), ("ms_filter", C.c_float), ("ms_exact", C.c_float),
                 ("ms_hitsort", C.c_float), ("ms_total", C.c_float), ("ms_filter_tc", C.c_float),
-                ("ms_host", C.c_float), ("n_candidates_tc", C.c_uint64), ("hash_sort_fallbacks", C.c_uint64)]
+                ("ms_host", C.c_float), ("n_candidates_tc", C.c_uint64), ("hash_sort_fallbacks", C.c_uint64),
+                ("segsort_lists", C.c_uint64), ("segsort_fallbacks", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

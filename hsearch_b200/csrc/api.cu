@@ -14,6 +14,7 @@
 #include "sort.cuh"
 #include "verify.cuh"
 #include "internal.cuh"
+#include "hitsort.cuh"
 
 namespace hs {
 int setup_projection(hs_ctx *ctx, const double *a, const double *b);
@@ -673,9 +674,28 @@ static int sort_hits(hs_ctx *ctx, hs_hit *d_hits, uint64_t n, const CompactBlock
     set_error("sort_hits: more than 2^32 hits");
     return HS_ERR_UNSUPPORTED;
   }
+  if (!cb) HS_TRY(ctx->d_hits_sorted.reserve(sizeof(hs_hit) * n));
+  if (!sk) {
+    // partition by the top key bits + per-bin sort in shared memory (hitsort.cu); it hands the
+    // list back untouched when a field does not fit or a bin cannot be processed
+    SegSortRequest rq;
+    rq.compact = cb != nullptr;
+    rq.hits_out = ctx->d_hits_sorted.as<hs_hit>();
+    if (cb) {
+      rq.idt = ctx->d_cidt.as<uint32_t>();
+      rq.dist2 = ctx->d_cdist.as<double>();
+      rq.offsets = ctx->d_coffsets.as<uint64_t>();
+      rq.qa = cb->qa;
+      rq.qb = cb->qb;
+      rq.base = cb->base;
+      rq.id_bits = cb->id_bits;
+    }
+    bool used = false;
+    HS_TRY(sort_hits_segmented(ctx, d_hits, n, rq, &used));
+    if (used) return HS_OK;
+  }
   HS_TRY(ctx->d_hit_keys[0].reserve(sizeof(uint64_t) * n));
   HS_TRY(ctx->d_hit_perm.reserve(sizeof(uint32_t) * 2 * n));
-  if (!cb) HS_TRY(ctx->d_hits_sorted.reserve(sizeof(hs_hit) * n));
   const unsigned grid = (unsigned)((n + 255) / 256);
   KeyPtrs in, sorted;
   memset(&in, 0, sizeof in);
@@ -1489,6 +1509,9 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->no_mma_filter = env_on("HS_NO_MMA_FILTER");
   ctx->no_mma_int = env_on("HS_NO_MMA_INT");
   ctx->surv_bins = env_on("HS_SURV_BINS");
+  ctx->segsort = env_on("HS_SEGSORT");
+  if (const char *e = getenv("HS_SEGSORT_MIN")) ctx->segsort_min = strtoull(e, nullptr, 10);
+  if (const char *e = getenv("HS_SEGSORT_BUF")) ctx->segsort_buf = (uint32_t)std::max(0, atoi(e));
   if (const char *e = getenv("HS_SELFJOIN_CHUNK"))
     if (atoi(e) >= 256) ctx->selfjoin_chunk = (uint32_t)atoi(e);
   ctx->num_sms = prop.multiProcessorCount;
@@ -1548,7 +1571,8 @@ void hs_destroy(hs_ctx_t *ctx) {
   ctx->d_hits_sorted_alt.release();
   ctx->d_events.release();
   ctx->d_binctr.release();
-  DevBuf *cbufs[] = {&ctx->d_cidt, &ctx->d_cidt_alt, &ctx->d_cdist, &ctx->d_cdist_alt, &ctx->d_coffsets};
+  DevBuf *cbufs[] = {&ctx->d_cidt, &ctx->d_cidt_alt, &ctx->d_cdist, &ctx->d_cdist_alt, &ctx->d_coffsets,
+                     &ctx->d_seg_tab, &ctx->d_seg_key, &ctx->d_seg_dist, &ctx->d_seg_ctl};
   for (DevBuf *b : cbufs) b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -183,6 +183,7 @@ struct hs_ctx {
   hs::DevBuf d_hit_keys[3], d_hit_perm, d_hits_sorted, d_hits_sorted_alt;
   hs::DevBuf d_surv_blk;                // survivors regrouped by query block (pipelined verify / copy-out)
   hs::DevBuf d_cidt, d_cidt_alt, d_cdist, d_cdist_alt, d_coffsets;  // compact (CSR) hit output, double buffered
+  hs::DevBuf d_seg_tab, d_seg_key, d_seg_dist, d_seg_ctl;           // segmented hit sort (hitsort.cu)
   cudaStream_t copy_stream = nullptr;   // D2H of sorted hit blocks, overlapped with the next block's search
   std::vector<cudaEvent_t> ev_chunk;
   hs::DevBuf d_misc, d_tabptrs, d_qcodes, d_hits_gathered, d_residues, d_starts;
@@ -244,6 +245,9 @@ struct hs_ctx {
   bool surv_bins = false;        // HS_SURV_BINS: survivors regrouped by fragment-id block before the exact stage
   bool no_mma_int = false;       // HS_NO_MMA_INT: the integer metric stays on the one-hot tensor filter (filter_tc.cu)
   bool no_mma_filter = false;    // HS_NO_MMA_FILTER: keep the Euclidean metric off the pipelined tensor filter
+  bool segsort = false;          // HS_SEGSORT=1: hit lists ordered by the segmented sort (hitsort.cu) instead of the radix passes
+  uint64_t segsort_min = 1u << 18;   // HS_SEGSORT_MIN: ... for lists of at least this many hits
+  uint32_t segsort_buf = 1u << 30;   // HS_SEGSORT_BUF: keys per shared-memory buffer (test hook: forces the range path)
 
   hs_stats stats{};
   hs_stats hash_stats{};   // counters / timing of the hash that produced the current keys

@@ -123,6 +123,10 @@ typedef struct {
   uint64_t n_candidates_tc; /* of n_candidates, pairs examined by the tensor-core filter */
   uint64_t hash_sort_fallbacks; /* index build, multi-word keys: tables whose sort on the 64-bit key hash met two
                                distinct keys with one hash and was redone on all key words (expected 0) */
+  uint64_t segsort_lists;   /* search: hit lists put into the reference's order by the segmented sort (partition
+                               by the top key bits, per-bin sort in shared memory; hitsort.cu) */
+  uint64_t segsort_fallbacks; /* ... lists it handed back to the radix passes (a key field did not fit, or one
+                               value of a bin's top 8 key bits alone exceeds the shared-memory buffer) */
 } hs_stats;
 
 /* ---- lifetime -------------------------------------------------------------- */

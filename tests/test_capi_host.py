@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(capi.Params) == 48
     assert capi.HIT_DTYPE.itemsize == 24
-    assert C.sizeof(capi.Stats) == 9 * 8 + 4 * 4 + 15 * 4 + 4 + 8 + 8  # 15 floats, padded to 8, two more u64
+    assert C.sizeof(capi.Stats) == 9 * 8 + 4 * 4 + 15 * 4 + 4 + 8 + 8 + 8 + 8  # 15 floats, padded to 8, four more u64
 
 
 def test_host_tables_match_oracle(oracle):
