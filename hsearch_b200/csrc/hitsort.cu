@@ -36,7 +36,10 @@ constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegItems = 4;
 constexpr int kSegTile = kSegThreads * kSegItems;     // keys ranked per step of a radix pass
 constexpr uint32_t kSegBufMax = 22528;                // keys per shared-memory buffer (two buffers: 176 KB)
-constexpr int kSegMaxBinBits = 15;                    // <= 32768 bins (cursors of the partition: 128 KB)
+#ifndef HS_SEG_BIN_BITS
+#define HS_SEG_BIN_BITS 15
+#endif
+constexpr int kSegMaxBinBits = HS_SEG_BIN_BITS;       // <= 32768 bins (cursors of the partition: 128 KB)
 
 struct SegFields {
   int tshift, qshift;     // key = query << qshift | table << tshift | db id

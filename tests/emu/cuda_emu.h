@@ -1,0 +1,194 @@
+// Minimal CPU emulation of the CUDA execution model for kernel logic checks without a GPU:
+// the threads of a block are user-level fibers (a 10-instruction x86-64 stack switch) run round-robin by one OS thread,
+// switching at __syncthreads / __syncwarp / warp collectives; blocks run one after another.
+// Test infrastructure only (tests/emu/): it checks indices, barrier uniformity (a divergent
+// barrier deadlocks and is reported) and data flow of a kernel, not memory-model subtleties.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(x) alignas(x)
+#define __shared__ static
+
+struct emu_dim3 {
+  unsigned x = 1, y = 1, z = 1;
+};
+struct uint2 {
+  uint32_t x, y;
+};
+struct uint4 {
+  uint32_t x, y, z, w;
+};
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+
+static emu_dim3 threadIdx, blockIdx, blockDim, gridDim;   // threadIdx: the running fiber's
+
+struct EmuBarrier {
+  unsigned expected = 0, arrived = 0;
+  uint64_t gen = 0;
+};
+struct EmuWarp {
+  EmuBarrier bar;
+  uint32_t val[2][32];
+  unsigned op = 0;   // collective operations completed (parity selects the slot array)
+};
+#if !defined(__x86_64__)
+#error "tests/emu/cuda_emu.h: the fiber switch is written for x86-64"
+#endif
+// Saves the callee-saved registers on the current stack, stores its pointer, continues on the other stack.
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+
+struct EmuFiber {
+  void *sp = nullptr;
+  std::vector<unsigned char> stack;
+  bool done = false;
+  EmuBarrier *wait = nullptr;
+  uint64_t wait_gen = 0;
+};
+static void *emu_sched_sp = nullptr;
+static std::vector<EmuFiber> emu_fibers;
+static std::vector<EmuWarp> emu_warps;
+static EmuBarrier emu_block_bar;
+static unsigned emu_cur = 0;
+static const std::function<void()> *emu_body = nullptr;
+alignas(16) static unsigned char emu_dyn_smem[232448];
+
+static inline void emu_wait(EmuBarrier &b) {
+  EmuFiber &f = emu_fibers[emu_cur];
+  const uint64_t g = b.gen;
+  if (++b.arrived == b.expected) {
+    b.arrived = 0;
+    ++b.gen;
+    return;   // the last arrival runs on
+  }
+  f.wait = &b;
+  f.wait_gen = g;
+  emu_switch(&f.sp, emu_sched_sp);
+}
+static inline EmuWarp &emu_warp() { return emu_warps[threadIdx.x >> 5]; }
+static inline void __syncthreads() { emu_wait(emu_block_bar); }
+static inline void __syncwarp() { emu_wait(emu_warp().bar); }
+// A collective: every lane deposits its value in the slot array of the operation's parity and
+// waits for the warp; the array is reused two operations later, after every lane has read it.
+static inline const uint32_t *emu_exchange(uint32_t v) {
+  EmuWarp &w = emu_warp();
+  const unsigned lane = threadIdx.x & 31;
+  // the operation index a lane is at = completed ops of the warp as seen before it arrives
+  const unsigned slot = (unsigned)(w.bar.gen & 1u);
+  w.val[slot][lane] = v;
+  emu_wait(w.bar);
+  return w.val[slot];
+}
+static inline uint32_t __ballot_sync(uint32_t, bool pred) {
+  const uint32_t *v = emu_exchange(pred ? 1u : 0u);
+  uint32_t m = 0;
+  const unsigned nl = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+  for (unsigned i = 0; i < nl; ++i) m |= v[i] << i;
+  return m;
+}
+static inline uint32_t __shfl_sync(uint32_t, uint32_t x, int src) { return emu_exchange(x)[src & 31]; }
+static inline uint32_t __shfl_up_sync(uint32_t, uint32_t x, int delta) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t *v = emu_exchange(x);
+  return lane >= delta ? v[lane - delta] : x;
+}
+static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t x, int m) { return emu_exchange(x)[(threadIdx.x & 31) ^ m]; }
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+template <typename T>
+static inline T __ldg(const T *p) {
+  return *p;
+}
+static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) {
+  const uint32_t o = *p;
+  *p = o + v;
+  return o;
+}
+
+static void emu_trampoline() {
+  (*emu_body)();
+  emu_fibers[emu_cur].done = true;
+  emu_switch(&emu_fibers[emu_cur].sp, emu_sched_sp);
+  abort();   // a finished fiber is never resumed
+}
+
+// Runs `body` as a grid of `grid` blocks of `block` threads, block after block.  Returns false
+// on a deadlock (some threads wait at a barrier the others never reach).
+static inline bool emu_launch(unsigned grid, unsigned block, const std::function<void()> &body) {
+  blockDim.x = block;
+  gridDim.x = grid;
+  emu_body = &body;
+  const unsigned nwarps = (block + 31) / 32;
+  for (unsigned b = 0; b < grid; ++b) {
+    blockIdx.x = b;
+    emu_block_bar = EmuBarrier();
+    emu_block_bar.expected = block;
+    emu_warps.assign(nwarps, EmuWarp());
+    for (unsigned w = 0; w < nwarps; ++w) emu_warps[w].bar.expected = std::min(32u, block - 32 * w);
+    emu_fibers.clear();
+    emu_fibers.resize(block);
+    for (unsigned t = 0; t < block; ++t) {
+      EmuFiber &f = emu_fibers[t];
+      f.stack.resize(96 * 1024);
+      // initial frame: six zeroed callee-saved registers, then the entry point as return address
+      uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack.data()) + f.stack.size()) & ~(uintptr_t)15;
+      uint64_t *frame = reinterpret_cast<uint64_t *>(top - 64);
+      memset(frame, 0, 64);
+      frame[6] = reinterpret_cast<uint64_t>(&emu_trampoline);
+      f.sp = frame;
+    }
+    unsigned live = block;
+    while (live) {
+      bool progressed = false;
+      for (unsigned t = 0; t < block; ++t) {
+        EmuFiber &f = emu_fibers[t];
+        if (f.done) continue;
+        if (f.wait && f.wait->gen == f.wait_gen) continue;   // still blocked
+        f.wait = nullptr;
+        emu_cur = t;
+        threadIdx.x = t;
+        emu_switch(&emu_sched_sp, f.sp);
+        progressed = true;
+        if (f.done) --live;
+      }
+      if (!progressed) {
+        fprintf(stderr, "emu: deadlock in block %u (%u threads blocked at divergent barriers)\n", b, live);
+        return false;
+      }
+    }
+  }
+  return true;
+}
