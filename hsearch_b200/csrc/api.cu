@@ -1511,6 +1511,8 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->surv_bins = env_on("HS_SURV_BINS");
   ctx->segsort = env_on("HS_SEGSORT");
   if (const char *e = getenv("HS_SEGSORT_MIN")) ctx->segsort_min = strtoull(e, nullptr, 10);
+  if (const char *e = getenv("HS_SEGSORT_NBLK")) ctx->segsort_nblk = (uint32_t)std::max(0, atoi(e));
+  ctx->segsort_prof = env_on("HS_SEGSORT_PROF");
   if (const char *e = getenv("HS_SEGSORT_BUF")) ctx->segsort_buf = (uint32_t)std::max(0, atoi(e));
   if (const char *e = getenv("HS_SELFJOIN_CHUNK"))
     if (atoi(e) >= 256) ctx->selfjoin_chunk = (uint32_t)atoi(e);

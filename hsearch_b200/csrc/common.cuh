@@ -248,6 +248,8 @@ struct hs_ctx {
   bool segsort = false;          // HS_SEGSORT=1: hit lists ordered by the segmented sort (hitsort.cu) instead of the radix passes
   uint64_t segsort_min = 1u << 18;   // HS_SEGSORT_MIN: ... for lists of at least this many hits
   uint32_t segsort_buf = 1u << 30;   // HS_SEGSORT_BUF: keys per shared-memory buffer (test hook: forces the range path)
+  uint32_t segsort_nblk = 0;         // HS_SEGSORT_NBLK: blocks of its partition pass (0: two per SM)
+  bool segsort_prof = false;         // HS_SEGSORT_PROF: per-kernel times of every segmented sort on stderr
 
   hs_stats stats{};
   hs_stats hash_stats{};   // counters / timing of the hash that produced the current keys

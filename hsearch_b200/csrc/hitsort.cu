@@ -102,13 +102,29 @@ seg_scatter_kernel(const hs_hit *__restrict__ hits, uint64_t n, SegFields f, con
   __syncthreads();
   const uint64_t beg = (uint64_t)blockIdx.x * f.chunk;
   const uint64_t end = beg + f.chunk < n ? beg + f.chunk : n;
-  for (uint64_t i = beg + threadIdx.x; i < end; i += kSegThreads) {
-    const hs_hit h = seg_load_key(hits + i);
-    uint32_t bin, low;
-    if (!seg_key(h, f, bin, low)) continue;  // (flagged by seg_hist_kernel: the result is discarded)
-    const uint32_t pos = atomicAdd(&seg_cur[bin], 1u);
-    pkey[pos] = low;
-    pdist[pos] = hits[i].dist2;
+  // four hits in flight per thread: with few blocks (long runs per bin, see sort_hits_segmented) the
+  // kernel lives on memory-level parallelism
+  for (uint64_t i0 = beg + threadIdx.x; i0 < end; i0 += 4 * kSegThreads) {
+    hs_hit h[4];
+    double d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * kSegThreads;
+      if (i < end) {
+        h[u] = seg_load_key(hits + i);
+        d[u] = __ldg(&hits[i].dist2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * kSegThreads;
+      if (i >= end) continue;
+      uint32_t bin, low;
+      if (!seg_key(h[u], f, bin, low)) continue;  // (flagged by seg_hist_kernel: the result is discarded)
+      const uint32_t pos = atomicAdd(&seg_cur[bin], 1u);
+      pkey[pos] = low;
+      pdist[pos] = d[u];
+    }
   }
 }
 
@@ -357,7 +373,7 @@ seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pd
 }
 
 // offsets[q] = base + first entry (in the sorted order) whose query is >= q, q in [qa, qb]
-__global__ void seg_offsets_kernel(const uint32_t *__restrict__ start, uint64_t n, SegFields f, uint32_t qa, uint32_t qb,
+__global__ void seg_query_offsets_kernel(const uint32_t *__restrict__ start, uint64_t n, SegFields f, uint32_t qa, uint32_t qb,
                                    uint64_t base, uint64_t *__restrict__ offsets) {
   const uint64_t q = (uint64_t)qa + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q > qb) return;
@@ -390,7 +406,11 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   f.nbins = (uint32_t)((((qmax << f.qshift) - 1ull) >> f.shift) + 1ull);
   if (f.nbins > (1u << kSegMaxBinBits)) return HS_OK;
   const uint64_t want_blk = (n + 8191) / 8192;
-  f.nblk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want_blk, 2ull * (uint64_t)ctx->num_sms));
+  // Blocks of the partition: every (bin, block) pair is one run of the partitioned arrays, written a hit at
+  // a time -- the fewer blocks, the longer the runs and the fewer cache lines are open at once
+  // (HS_SEGSORT_NBLK, default two per SM)
+  const uint64_t max_blk = ctx->segsort_nblk ? ctx->segsort_nblk : 2ull * (uint64_t)ctx->num_sms;
+  f.nblk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want_blk, max_blk));
   f.chunk = (n + f.nblk - 1) / f.nblk;
   const uint64_t ntab = (uint64_t)f.nbins * f.nblk;
 
@@ -409,10 +429,17 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   double *pdist = ctx->d_seg_dist.as<double>();
   unsigned int *ctl = ctx->d_seg_ctl.as<unsigned int>();  // [0] field overflow, [1] range overflow, [2] bin counter
   HS_CUDA(cudaMemsetAsync(ctl, 0, sizeof(unsigned int) * 4, ctx->stream));
+  cudaEvent_t pe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // HS_SEGSORT_PROF: per-kernel times to stderr
+  if (ctx->segsort_prof)
+    for (cudaEvent_t &e : pe) HS_CUDA(cudaEventCreate(&e));
+  if (ctx->segsort_prof) HS_CUDA(cudaEventRecord(pe[0], ctx->stream));
   seg_hist_kernel<<<f.nblk, kSegThreads, part_smem, ctx->stream>>>(d_hits, n, f, tab, ctl);
   HS_CUDA(cudaGetLastError());
+  if (ctx->segsort_prof) HS_CUDA(cudaEventRecord(pe[1], ctx->stream));
   HS_TRY(exclusive_scan_u32(ctx, tab, tab, ntab, nullptr));
+  if (ctx->segsort_prof) HS_CUDA(cudaEventRecord(pe[2], ctx->stream));
   seg_scatter_kernel<<<f.nblk, kSegThreads, part_smem, ctx->stream>>>(d_hits, n, f, tab, pkey, pdist);
+  if (ctx->segsort_prof) HS_CUDA(cudaEventRecord(pe[3], ctx->stream));
   SegOut o;
   o.hits = rq.compact ? nullptr : rq.hits_out;
   o.idt = rq.idt;
@@ -425,12 +452,20 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   ctx->stats.kernel_launches += 3;
   if (rq.compact) {
     const uint32_t nq = rq.qb - rq.qa + 1;
-    seg_offsets_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(tab, n, f, rq.qa, rq.qb, rq.base, rq.offsets);
+    seg_query_offsets_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(tab, n, f, rq.qa, rq.qb, rq.base, rq.offsets);
     ctx->stats.kernel_launches++;
   }
   HS_CUDA(cudaGetLastError());
+  if (ctx->segsort_prof) HS_CUDA(cudaEventRecord(pe[4], ctx->stream));
   unsigned int h_flags[2] = {0, 0};
   HS_TRY(read_back(ctx, ctl, h_flags, sizeof h_flags));
+  if (ctx->segsort_prof) {
+    float ms[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], pe[i], pe[i + 1]);
+    fprintf(stderr, "segsort: n=%llu bins=%u blocks=%u rb=%d  hist %.3f  scan %.3f  scatter %.3f  sort %.3f ms  flags %u %u\n",
+            (unsigned long long)n, f.nbins, f.nblk, f.rb, ms[0], ms[1], ms[2], ms[3], h_flags[0], h_flags[1]);
+    for (cudaEvent_t e : pe) cudaEventDestroy(e);
+  }
   if (h_flags[0] || h_flags[1]) {
     ctx->stats.segsort_fallbacks++;
     return HS_OK;  // the caller sorts with the radix path (d_hits is untouched)

@@ -108,7 +108,7 @@ static bool run_case(const Case &c, unsigned seed) {
   launched = launched && emu_launch(grid, kSegThreads, [&]() { seg_sort_kernel(pkey.data(), pdist.data(), n, f, tab.data(), o, c.bufcap, ctl + 2, ctl); });
   if (c.compact) {
     const uint32_t nq = c.Q + 1;
-    launched = launched && emu_launch((nq + 255) / 256, 256, [&]() { seg_offsets_kernel(tab.data(), n, f, 0, c.Q, 1000, offsets.data()); });
+    launched = launched && emu_launch((nq + 255) / 256, 256, [&]() { seg_query_offsets_kernel(tab.data(), n, f, 0, c.Q, 1000, offsets.data()); });
   }
   if (!launched) return false;
   // expectation
