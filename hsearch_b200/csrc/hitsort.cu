@@ -35,7 +35,8 @@ constexpr int kSegThreads = 1024;
 constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegItems = 4;
 constexpr int kSegTile = kSegThreads * kSegItems;     // keys ranked per step of a radix pass
-constexpr uint32_t kSegBufMax = 22528;                // keys per shared-memory buffer (two buffers: 176 KB)
+constexpr uint32_t kSegBufMax = 22528;                // keys per shared-memory buffer (two buffers: 176 KB), 1024-thread sort blocks
+constexpr uint32_t kSegBufMax512 = 10240;             // ... of the 512-thread sort blocks (two blocks per SM)
 #ifndef HS_SEG_BIN_BITS
 #define HS_SEG_BIN_BITS 15
 #endif
@@ -140,8 +141,9 @@ __device__ __forceinline__ uint32_t seg_digit_peers(uint32_t d) {
   return peers;
 }
 
+template <int NT>
 struct SegSortShared {
-  uint32_t whist[kSegWarps][257];  // per-warp digit counters of a step (+ tail bin), then run starts
+  uint32_t whist[NT / 32][257];  // per-warp digit counters of a step (+ tail bin), then run starts
   uint32_t cnt[256];               // digit histogram of a pass / top-8-bit histogram of a large bin
   uint32_t gbase[256];             // next free output position of every digit
   uint32_t wsum[8];
@@ -150,13 +152,14 @@ struct SegSortShared {
 };
 
 // One stable LSD pass over n keys in shared memory: in -> out by the digit (key >> shift) & mask.
-__device__ __forceinline__ void seg_radix_pass(SegSortShared &sh, const uint32_t *in, uint32_t *out, uint32_t n, int shift,
+template <int NT>
+__device__ __forceinline__ void seg_radix_pass(SegSortShared<NT> &sh, const uint32_t *in, uint32_t *out, uint32_t n, int shift,
                                                uint32_t mask) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   if (tid < 256) sh.cnt[tid] = 0u;
   __syncthreads();
-  for (uint32_t i = tid; i < n; i += kSegThreads) atomicAdd(&sh.cnt[(in[i] >> shift) & mask], 1u);
+  for (uint32_t i = tid; i < n; i += NT) atomicAdd(&sh.cnt[(in[i] >> shift) & mask], 1u);
   __syncthreads();
   // exclusive scan of the 256 digit counts (threads 0..255)
   uint32_t c = 0, incl = 0;
@@ -178,9 +181,9 @@ __device__ __forceinline__ void seg_radix_pass(SegSortShared &sh, const uint32_t
       if (w < wid) off += sh.wsum[w];
     sh.gbase[tid] = off + incl - c;
   }
-  // steps of kSegTile keys: warp w ranks the keys [w * 128, w * 128 + 128) of the step, item-major
-  for (uint32_t tile = 0; tile < n; tile += kSegTile) {
-    for (int i = tid; i < kSegWarps * 257; i += kSegThreads) (&sh.whist[0][0])[i] = 0u;
+  // steps of (NT * kSegItems) keys: warp w ranks the keys [w * 128, w * 128 + 128) of the step, item-major
+  for (uint32_t tile = 0; tile < n; tile += (NT * kSegItems)) {
+    for (int i = tid; i < (NT / 32) * 257; i += NT) (&sh.whist[0][0])[i] = 0u;
     __syncthreads();  // (also orders the gbase writes above / of the previous step)
     uint32_t key[kSegItems], lp[kSegItems], dg[kSegItems];
 #pragma unroll
@@ -202,7 +205,7 @@ __device__ __forceinline__ void seg_radix_pass(SegSortShared &sh, const uint32_t
     if (tid < 256) {
       uint32_t run = sh.gbase[tid];
 #pragma unroll
-      for (int w = 0; w < kSegWarps; ++w) {
+      for (int w = 0; w < (NT / 32); ++w) {
         const uint32_t cw = sh.whist[w][tid];
         sh.whist[w][tid] = run;
         run += cw;
@@ -227,13 +230,14 @@ struct SegOut {
   int id_bits;
 };
 
-__global__ void __launch_bounds__(kSegThreads, 1)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2)
 seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pdist, uint64_t n, SegFields f,
-                const uint32_t *__restrict__ start /*[nbins][nblk], scanned*/, SegOut o, uint32_t bufcap,
+                const uint32_t *__restrict__ start /*[nbins][nblk], scanned*/, SegOut o, uint32_t bufcap, uint32_t bufmax,
                 unsigned int *__restrict__ bin_counter, unsigned int *__restrict__ flags) {
   extern __shared__ __align__(16) uint32_t seg_buf[];
-  __shared__ SegSortShared sh;
-  uint32_t *buf0 = seg_buf, *buf1 = seg_buf + kSegBufMax;
+  __shared__ SegSortShared<NT> sh;
+  uint32_t *buf0 = seg_buf, *buf1 = seg_buf + bufmax;   // bufmax keys each (bufcap <= bufmax)
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const int hb = f.rb > 8 ? f.rb - 8 : 0;   // a large bin is cut by the top 8 bits of its low keys
@@ -261,7 +265,7 @@ seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pd
     } else {
       if (tid < 256) sh.cnt[tid] = 0u;
       __syncthreads();
-      for (uint32_t j = tid; j < s; j += kSegThreads) atomicAdd(&sh.cnt[seg[j] >> hb], 1u);
+      for (uint32_t j = tid; j < s; j += NT) atomicAdd(&sh.cnt[seg[j] >> hb], 1u);
       __syncthreads();
       if (tid == 0) {
         uint32_t nr = 0, lo = 0, acc = 0;
@@ -298,14 +302,14 @@ seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pd
       const uint32_t lo = sh.r_lo[r], hi = sh.r_hi[r];
       uint32_t nn;
       if (single) {
-        for (uint32_t j = tid; j < s; j += kSegThreads) buf0[j] = seg[j];
+        for (uint32_t j = tid; j < s; j += NT) buf0[j] = seg[j];
         nn = s;
         __syncthreads();
       } else {
         if (tid == 0) sh.count = 0u;
         __syncthreads();
         // the keys of the range, in any order (warp-aggregated append)
-        for (uint32_t j0 = (uint32_t)(tid & ~31); j0 < s; j0 += kSegThreads) {
+        for (uint32_t j0 = (uint32_t)(tid & ~31); j0 < s; j0 += NT) {
           const uint32_t j = j0 + lane;
           uint32_t k = 0;
           bool in = false;
@@ -329,14 +333,14 @@ seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pd
       uint32_t *src = buf0, *dst = buf1;
       for (int p = 0; p < npass; ++p) {
         const int bits = f.rb - 8 * p < 8 ? f.rb - 8 * p : 8;
-        seg_radix_pass(sh, src, dst, nn, 8 * p, (1u << bits) - 1u);
+        seg_radix_pass<NT>(sh, src, dst, nn, 8 * p, (1u << bits) - 1u);
         uint32_t *t = src;
         src = dst;
         dst = t;
       }
       const uint32_t *sorted = src;
       // the keys in their final format, in order
-      for (uint32_t i = tid; i < nn; i += kSegThreads) {
+      for (uint32_t i = tid; i < nn; i += NT) {
         const uint64_t full = ((uint64_t)bin << f.shift) | (uint64_t)sorted[i];
         const uint32_t query = (uint32_t)(full >> f.qshift);
         const uint32_t table = (uint32_t)(full >> f.tshift) & tmask;
@@ -350,7 +354,7 @@ seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pd
         }
       }
       // every hit's distance to the rank of its key
-      for (uint32_t j = tid; j < s; j += kSegThreads) {
+      for (uint32_t j = tid; j < s; j += NT) {
         const uint32_t k = seg[j];
         if (!single) {
           const uint32_t b = k >> hb;
@@ -415,11 +419,16 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   const uint64_t ntab = (uint64_t)f.nbins * f.nblk;
 
   const size_t part_smem = sizeof(uint32_t) * f.nbins;
-  const size_t sort_smem = sizeof(uint32_t) * 2 * kSegBufMax;
+  // the per-bin sort: one 1024-thread block per SM with two buffers of kSegBufMax keys, or (HS_SEGSORT_THREADS=512)
+  // two 512-thread blocks per SM with buffers of kSegBufMax512 keys
+  const bool half = ctx->segsort_threads == 512;
+  const uint32_t bufmax = half ? kSegBufMax512 : kSegBufMax;
+  const size_t sort_smem = sizeof(uint32_t) * 2 * bufmax;
   // (per device: a process may drive several GPUs, each with its own context)
   HS_CUDA(cudaFuncSetAttribute(seg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) << kSegMaxBinBits)));
   HS_CUDA(cudaFuncSetAttribute(seg_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) << kSegMaxBinBits)));
-  HS_CUDA(cudaFuncSetAttribute(seg_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+  HS_CUDA(cudaFuncSetAttribute(seg_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * 2 * kSegBufMax)));
+  HS_CUDA(cudaFuncSetAttribute(seg_sort_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * 2 * kSegBufMax512)));
   HS_TRY(ctx->d_seg_tab.reserve(sizeof(uint32_t) * (ntab + 1)));
   HS_TRY(ctx->d_seg_key.reserve(sizeof(uint32_t) * n));
   HS_TRY(ctx->d_seg_dist.reserve(sizeof(double) * n));
@@ -446,9 +455,10 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   o.dist2 = rq.dist2;
   o.id_base = ctx->id_base;
   o.id_bits = rq.id_bits;
-  const uint32_t bufcap = std::min<uint32_t>(kSegBufMax, ctx->segsort_buf);  // (0, a test hook: no bin fits, every list is handed back)
-  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)f.nbins, (uint64_t)ctx->num_sms);
-  seg_sort_kernel<<<grid, kSegThreads, sort_smem, ctx->stream>>>(pkey, pdist, n, f, tab, o, bufcap, ctl + 2, ctl);
+  const uint32_t bufcap = std::min<uint32_t>(bufmax, ctx->segsort_buf);  // (0, a test hook: no bin fits, every list is handed back)
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)f.nbins, (uint64_t)ctx->num_sms * (half ? 2 : 1));
+  if (half) seg_sort_kernel<512><<<grid, 512, sort_smem, ctx->stream>>>(pkey, pdist, n, f, tab, o, bufcap, bufmax, ctl + 2, ctl);
+  else seg_sort_kernel<1024><<<grid, 1024, sort_smem, ctx->stream>>>(pkey, pdist, n, f, tab, o, bufcap, bufmax, ctl + 2, ctl);
   ctx->stats.kernel_launches += 3;
   if (rq.compact) {
     const uint32_t nq = rq.qb - rq.qa + 1;
@@ -462,8 +472,8 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   if (ctx->segsort_prof) {
     float ms[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], pe[i], pe[i + 1]);
-    fprintf(stderr, "segsort: n=%llu bins=%u blocks=%u rb=%d  hist %.3f  scan %.3f  scatter %.3f  sort %.3f ms  flags %u %u\n",
-            (unsigned long long)n, f.nbins, f.nblk, f.rb, ms[0], ms[1], ms[2], ms[3], h_flags[0], h_flags[1]);
+    fprintf(stderr, "segsort: n=%llu bins=%u blocks=%u threads=%d rb=%d  hist %.3f  scan %.3f  scatter %.3f  sort %.3f ms  flags %u %u\n",
+            (unsigned long long)n, f.nbins, f.nblk, half ? 512 : 1024, f.rb, ms[0], ms[1], ms[2], ms[3], h_flags[0], h_flags[1]);
     for (cudaEvent_t e : pe) cudaEventDestroy(e);
   }
   if (h_flags[0] || h_flags[1]) {

@@ -6,34 +6,45 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 T0=$(date +%s)
 timeout 120 python -m pytest tests/test_gpu_segsort.py -q -x -s > gpurun_out/r02ak_segsort_tests.log 2>&1; echo "segsort tests rc=$? t=$(( $(date +%s) - T0 ))"
 grep -E "segsort \(lists|passed|failed|Error|assert" gpurun_out/r02ak_segsort_tests.log | head -12
-for NB in 296 96 32 12; do
-  HS_SEGSORT=1 HS_SEGSORT_PROF=1 HS_SEGSORT_NBLK=$NB timeout 120 python bench.py --steps 3 --warmup 2 --no-e2e --no-recall --no-cpu-baseline --no-subset-check \
+for CFG in 296:1024 48:512 12:1024 96:512; do
+  NB=${CFG%%:*}; NT=${CFG##*:}
+  HS_SEGSORT=1 HS_SEGSORT_PROF=1 HS_SEGSORT_NBLK=$NB HS_SEGSORT_THREADS=$NT timeout 120 python bench.py --steps 3 --warmup 2 --no-e2e --no-recall --no-cpu-baseline --no-subset-check \
     > gpurun_out/r02ak_bench_nblk$NB.json 2> gpurun_out/r02ak_bench_nblk$NB.err
-  echo "nblk=$NB rc=$? t=$(( $(date +%s) - T0 ))"
+  echo "nblk=$NB threads=$NT rc=$? t=$(( $(date +%s) - T0 ))"
   grep "^segsort:" gpurun_out/r02ak_bench_nblk$NB.err | tail -2
 done
 BEST=$(python - <<'PY'
-import json
-best, bms = "", 7.5
-for nb in (296, 96, 32, 12):
+import json, re
+part, sort = {}, {}
+for nb, nt in ((296, 1024), (48, 512), (12, 1024), (96, 512)):
     try:
         d = json.loads(open(f"gpurun_out/r02ak_bench_nblk{nb}.json").read().strip().splitlines()[-1])
-        ms = d["stages_ms"]["hitsort"]
-        ok = d["checks"]["reference_order"]
-        print(f"# nblk={nb} hitsort {ms:.3f} ms step {d['ms_per_step']:.2f} order_ok {ok}", flush=True)
-        if ok and ms < bms:
-            best, bms = str(nb), ms
+        lines = [l for l in open(f"gpurun_out/r02ak_bench_nblk{nb}.err") if l.startswith("segsort:")]
+        m = re.search(r"hist ([\d.]+)  scan ([\d.]+)  scatter ([\d.]+)  sort ([\d.]+) ms  flags (\d+) (\d+)", lines[-1])
+        h, sc, st, so = (float(m.group(i)) for i in range(1, 5))
+        ok = d["checks"]["reference_order"] and m.group(5) == "0" and m.group(6) == "0"
+        print(f"# nblk={nb} threads={nt}: hitsort {d['stages_ms']['hitsort']:.3f} ms (hist {h} scan {sc} scatter {st} sort {so}) step {d['ms_per_step']:.2f} order_ok {ok}", flush=True)
+        if ok:
+            part[nb] = h + sc + st
+            sort[nt] = min(sort.get(nt, 1e9), so)
     except Exception as e:
-        print(f"# nblk={nb} parse failed {e}")
-print(best)
+        print(f"# nblk={nb} failed: {e}")
+if part and sort:
+    nb = min(part, key=part.get)
+    nt = min(sort, key=sort.get)
+    print(f"# predicted best: nblk={nb} threads={nt}: {part[nb] + sort[nt]:.3f} ms against 7.9 for the radix passes")
+    print(f"{nb}:{nt}" if part[nb] + sort[nt] < 7.3 else "")
+else:
+    print("")
 PY
 )
 echo "$BEST" | grep "^#"
 BEST=$(echo "$BEST" | tail -1)
-echo "best nblk: '$BEST'"
+echo "best: '$BEST'"
 if [ -n "$BEST" ]; then
-  HS_SEGSORT=1 HS_SEGSORT_NBLK=$BEST timeout 200 python bench.py --steps 10 --warmup 3 --no-recall --no-cpu-baseline > gpurun_out/r02ak_bench_full_seg.json 2> gpurun_out/r02ak_bench_full_seg.err
-  echo "full bench (segsort, nblk=$BEST) rc=$? t=$(( $(date +%s) - T0 ))"
+  NB=${BEST%%:*}; NT=${BEST##*:}
+  HS_SEGSORT=1 HS_SEGSORT_PROF=1 HS_SEGSORT_NBLK=$NB HS_SEGSORT_THREADS=$NT timeout 200 python bench.py --steps 10 --warmup 3 --no-recall --no-cpu-baseline > gpurun_out/r02ak_bench_full_seg.json 2> gpurun_out/r02ak_bench_full_seg.err
+  echo "full bench (segsort, nblk=$NB threads=$NT) rc=$? t=$(( $(date +%s) - T0 ))"
   python - <<'PY'
 import json
 try:
@@ -45,6 +56,7 @@ try:
 except Exception as e:
     print("parse failed", e)
 PY
+  grep "^segsort:" gpurun_out/r02ak_bench_full_seg.err | tail -6
 fi
 LEFT=$(( 425 - ( $(date +%s) - T0 ) ))
 echo "left for the suite: $LEFT s"

@@ -31,6 +31,7 @@ struct Case {
   uint32_t bufcap;
   bool compact;
   unsigned skew;  // 0: uniform queries; k: most hits in k queries
+  int threads = 1024;  // sort-kernel block size (1024 or 512)
 };
 
 static bool run_case(const Case &c, unsigned seed) {
@@ -105,7 +106,12 @@ static bool run_case(const Case &c, unsigned seed) {
   o.id_base = c.id_base;
   o.id_bits = bits_for(std::max<uint64_t>(c.N, 2));
   const unsigned grid = std::min<uint32_t>(f.nbins, 3);
-  launched = launched && emu_launch(grid, kSegThreads, [&]() { seg_sort_kernel(pkey.data(), pdist.data(), n, f, tab.data(), o, c.bufcap, ctl + 2, ctl); });
+  if (c.threads == 512) {
+    const uint32_t cap = std::min<uint32_t>(c.bufcap, kSegBufMax512);
+    launched = launched && emu_launch(grid, 512, [&]() { seg_sort_kernel<512>(pkey.data(), pdist.data(), n, f, tab.data(), o, cap, kSegBufMax512, ctl + 2, ctl); });
+  } else {
+    launched = launched && emu_launch(grid, 1024, [&]() { seg_sort_kernel<1024>(pkey.data(), pdist.data(), n, f, tab.data(), o, c.bufcap, kSegBufMax, ctl + 2, ctl); });
+  }
   if (c.compact) {
     const uint32_t nq = c.Q + 1;
     launched = launched && emu_launch((nq + 255) / 256, 256, [&]() { seg_query_offsets_kernel(tab.data(), n, f, 0, c.Q, 1000, offsets.data()); });
@@ -168,6 +174,7 @@ int main(int argc, char **argv) {
       {1, 1, 5, 0, 5, 22528, true, 0},                      // every bit in the bin
       {2600, 4, 60000, 0, 5000, 0, false, 0},               // buffer 0: handed back
       {32768, 32, 1000, 125000000ull, 20000, 22528, true, 5},
+      {10000, 4, 100000000ull, 0, 40000, 22528, true, 3, 512},
   };
 #else
   // (a build with few bins, -DHS_SEG_BIN_BITS=6: the same kernels, the per-bin loop is short)
@@ -182,6 +189,9 @@ int main(int argc, char **argv) {
       {33, 4, 60000, 0, 5000, 0, false, 0},                 // buffer 0: handed back
       {1, 1, 5, 0, 5, 22528, true, 0},                      // every bit in the bin
       {7, 2, 100, 0, 600, 9, true, 0},                      // tiny key, tiny buffer
+      {64, 4, 100000000ull, 0, 40000, 22528, false, 3, 512}, // 512-thread sort blocks: ~12 k keys per bin > their 10240-key buffer
+      {50, 4, 60000, 0, 3000, 22528, true, 0, 512},
+      {60, 4, 200000, 0, 30000, 2000, true, 2, 512},
   };
 #endif
   int bad = 0, i = 0;
@@ -191,8 +201,8 @@ int main(int argc, char **argv) {
       continue;
     }
     const bool ok = run_case(c, 1234 + i);
-    printf("case %d: Q=%u L=%u N=%llu id_base=%llu n=%llu buf=%u %s -> %s\n", i, c.Q, c.L, (unsigned long long)c.N,
-           (unsigned long long)c.id_base, (unsigned long long)c.n, c.bufcap, c.compact ? "compact" : "plain", ok ? "ok" : "FAILED");
+    printf("case %d: Q=%u L=%u N=%llu id_base=%llu n=%llu buf=%u threads=%d %s -> %s\n", i, c.Q, c.L, (unsigned long long)c.N,
+           (unsigned long long)c.id_base, (unsigned long long)c.n, c.bufcap, c.threads, c.compact ? "compact" : "plain", ok ? "ok" : "FAILED");
     if (!ok) ++bad;
     ++i;
   }
