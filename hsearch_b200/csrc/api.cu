@@ -1513,7 +1513,7 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   if (const char *e = getenv("HS_SEGSORT_MIN")) ctx->segsort_min = strtoull(e, nullptr, 10);
   if (const char *e = getenv("HS_SEGSORT_NBLK")) ctx->segsort_nblk = (uint32_t)std::max(0, atoi(e));
   ctx->segsort_prof = env_on("HS_SEGSORT_PROF");
-  if (const char *e = getenv("HS_SEGSORT_THREADS")) ctx->segsort_threads = atoi(e) == 512 ? 512u : 1024u;
+  ctx->segsort_radix = env_on("HS_SEGSORT_RADIX");
   if (const char *e = getenv("HS_SEGSORT_BUF")) ctx->segsort_buf = (uint32_t)std::max(0, atoi(e));
   if (const char *e = getenv("HS_SELFJOIN_CHUNK"))
     if (atoi(e) >= 256) ctx->selfjoin_chunk = (uint32_t)atoi(e);

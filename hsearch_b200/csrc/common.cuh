@@ -249,7 +249,7 @@ struct hs_ctx {
   uint64_t segsort_min = 1u << 18;   // HS_SEGSORT_MIN: ... for lists of at least this many hits
   uint32_t segsort_buf = 1u << 30;   // HS_SEGSORT_BUF: keys per shared-memory buffer (test hook: forces the range path)
   uint32_t segsort_nblk = 0;         // HS_SEGSORT_NBLK: blocks of its partition pass (0: two per SM)
-  uint32_t segsort_threads = 1024;   // HS_SEGSORT_THREADS: 1024 (one sort block per SM) or 512 (two)
+  bool segsort_radix = false;        // HS_SEGSORT_RADIX: its per-bin sort always takes the radix passes (A/B, tests)
   bool segsort_prof = false;         // HS_SEGSORT_PROF: per-kernel times of every segmented sort on stderr
 
   hs_stats stats{};

@@ -36,7 +36,9 @@ constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegItems = 4;
 constexpr int kSegTile = kSegThreads * kSegItems;     // keys ranked per step of a radix pass
 constexpr uint32_t kSegBufMax = 22528;                // keys per shared-memory buffer (two buffers: 176 KB), 1024-thread sort blocks
-constexpr uint32_t kSegBufMax512 = 10240;             // ... of the 512-thread sort blocks (two blocks per SM)
+constexpr int kSegBucketBits = 12;
+constexpr int kSegBuckets = 1 << kSegBucketBits;      // buckets of the per-bin bucket sort
+constexpr uint32_t kSegBucketMax = 48;                // keys in the fullest bucket up to which a range takes the bucket path
 #ifndef HS_SEG_BIN_BITS
 #define HS_SEG_BIN_BITS 15
 #endif
@@ -147,8 +149,9 @@ struct SegSortShared {
   uint32_t cnt[256];               // digit histogram of a pass / top-8-bit histogram of a large bin
   uint32_t gbase[256];             // next free output position of every digit
   uint32_t wsum[8];
+  uint32_t wsum32[32];             // bucket path: per-warp sums of the bucket scan
   uint32_t r_lo[256], r_hi[256];   // ranges of a large bin
-  uint32_t nranges, count, bin;
+  uint32_t nranges, count, bin, maxc;
 };
 
 // One stable LSD pass over n keys in shared memory: in -> out by the digit (key >> shift) & mask.
@@ -231,13 +234,16 @@ struct SegOut {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2)
+__global__ void __launch_bounds__(NT, 1)
 seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pdist, uint64_t n, SegFields f,
                 const uint32_t *__restrict__ start /*[nbins][nblk], scanned*/, SegOut o, uint32_t bufcap, uint32_t bufmax,
-                unsigned int *__restrict__ bin_counter, unsigned int *__restrict__ flags) {
+                uint32_t force_radix, unsigned int *__restrict__ bin_counter, unsigned int *__restrict__ flags) {
   extern __shared__ __align__(16) uint32_t seg_buf[];
   __shared__ SegSortShared<NT> sh;
-  uint32_t *buf0 = seg_buf, *buf1 = seg_buf + bufmax;   // bufmax keys each (bufcap <= bufmax)
+  uint32_t *buf0 = seg_buf, *buf1 = seg_buf + bufmax;   // radix path: bufmax keys each (bufcap <= bufmax)
+  uint2 *pair = reinterpret_cast<uint2 *>(seg_buf);     // bucket path: bufmax (key, position in the bin) pairs, the same bytes
+  static_assert((NT / 32) * 257 >= 2 * kSegBuckets && kSegBuckets % NT == 0, "bucket tables live in the per-warp counters");
+  uint32_t *bstart = &sh.whist[0][0], *bcur = bstart + kSegBuckets;
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const int hb = f.rb > 8 ? f.rb - 8 : 0;   // a large bin is cut by the top 8 bits of its low keys
@@ -300,10 +306,121 @@ seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pd
     uint64_t outpos = beg;
     for (uint32_t r = 0; r < nranges; ++r) {
       const uint32_t lo = sh.r_lo[r], hi = sh.r_hi[r];
+      // ---- bucket path: the keys of the range fall into kSegBuckets buckets by their leading bits; a
+      // histogram, a scan and one scatter of (key, position) pairs put every bucket in place, each
+      // bucket (a handful of keys when the keys are spread evenly) is insertion-sorted by one thread.
+      // No ranking, no passes; the radix passes below remain for ranges whose keys pile up.
+      const uint32_t kbase = single ? 0u : (lo << hb);
+      const uint64_t span = single ? (1ull << f.rb) : ((uint64_t)(hi - lo) << hb);   // keys of the range: [kbase, kbase + span)
+      int sbits = 0;
+      while (sbits < 33 && ((span - 1ull) >> sbits)) ++sbits;
+      const int bshift = sbits > kSegBucketBits ? sbits - kSegBucketBits : 0;
+      for (int i = tid; i < 2 * kSegBuckets; i += NT) bstart[i] = 0u;
+      if (tid == 0) sh.maxc = 0u;
+      __syncthreads();
+#pragma unroll 4
+      for (uint32_t j = tid; j < s; j += NT) {
+        const uint32_t k = seg[j];
+        if (!single) {
+          const uint32_t b8 = k >> hb;
+          if (b8 < lo || b8 >= hi) continue;
+        }
+        atomicAdd(&bstart[(k - kbase) >> bshift], 1u);
+      }
+      __syncthreads();
       uint32_t nn;
+      {
+        // exclusive scan of the bucket counts (kSegBuckets / NT consecutive buckets per thread) and their maximum
+        constexpr int PER = kSegBuckets / NT;
+        uint32_t c[PER], sum = 0, mx = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          c[i] = bstart[tid * PER + i];
+          sum += c[i];
+          mx = c[i] > mx ? c[i] : mx;
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += y;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const uint32_t y = __shfl_xor_sync(0xffffffffu, mx, d);
+          mx = y > mx ? y : mx;
+        }
+        if (lane == 31) sh.wsum32[tid >> 5] = incl;
+        if (lane == 0 && mx) atomicMax(&sh.maxc, mx);
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) {
+          const uint32_t t = sh.wsum32[w];
+          if (w < (tid >> 5)) woff += t;
+          total += t;
+        }
+        uint32_t run = woff + incl - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          bstart[tid * PER + i] = run;
+          bcur[tid * PER + i] = run;
+          run += c[i];
+        }
+        nn = total;
+        __syncthreads();
+      }
+      if (nn == 0u) continue;  // (block-uniform)
+      if (sh.maxc <= kSegBucketMax && !force_radix) {
+#pragma unroll 4
+        for (uint32_t j = tid; j < s; j += NT) {
+          const uint32_t k = seg[j];
+          if (!single) {
+            const uint32_t b8 = k >> hb;
+            if (b8 < lo || b8 >= hi) continue;
+          }
+          const uint32_t pos = atomicAdd(&bcur[(k - kbase) >> bshift], 1u);
+          pair[pos] = make_uint2(k, j);
+        }
+        __syncthreads();
+        for (int bk = tid; bk < kSegBuckets; bk += NT) {
+          const uint32_t b0 = bstart[bk], b1 = bcur[bk];
+          for (uint32_t i = b0 + 1; i < b1; ++i) {
+            const uint2 x = pair[i];
+            uint32_t q = i;
+            while (q > b0 && pair[q - 1].x > x.x) {
+              pair[q] = pair[q - 1];
+              --q;
+            }
+            pair[q] = x;
+          }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (uint32_t i = tid; i < nn; i += NT) {
+          const uint2 e = pair[i];
+          const uint64_t full = ((uint64_t)bin << f.shift) | (uint64_t)e.x;
+          const uint32_t query = (uint32_t)(full >> f.qshift);
+          const uint32_t table = (uint32_t)(full >> f.tshift) & tmask;
+          const uint64_t dbid = full & idmask;
+          const double d = pdist[beg + e.y];
+          if (o.hits) {
+            hs_hit *dst_hit = o.hits + outpos + i;   // (24-byte records: 8-byte stores)
+            *reinterpret_cast<uint2 *>(dst_hit) = make_uint2(query, table);
+            dst_hit->db_id = dbid;
+            dst_hit->dist2 = d;
+          } else {
+            o.idt[outpos + i] = (uint32_t)(dbid - o.id_base) | (table << o.id_bits);
+            o.dist2[outpos + i] = d;
+          }
+        }
+        outpos += nn;
+        __syncthreads();
+        continue;
+      }
+      // ---- radix path (keys piled up in a few buckets): the keys of the range into buf0, LSD passes, binary search
       if (single) {
         for (uint32_t j = tid; j < s; j += NT) buf0[j] = seg[j];
-        nn = s;
         __syncthreads();
       } else {
         if (tid == 0) sh.count = 0u;
@@ -327,9 +444,7 @@ seg_sort_kernel(const uint32_t *__restrict__ pkey, const double *__restrict__ pd
           }
         }
         __syncthreads();
-        nn = sh.count;
       }
-      if (nn == 0u) continue;  // (block-uniform)
       uint32_t *src = buf0, *dst = buf1;
       for (int p = 0; p < npass; ++p) {
         const int bits = f.rb - 8 * p < 8 ? f.rb - 8 * p : 8;
@@ -419,16 +534,14 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   const uint64_t ntab = (uint64_t)f.nbins * f.nblk;
 
   const size_t part_smem = sizeof(uint32_t) * f.nbins;
-  // the per-bin sort: one 1024-thread block per SM with two buffers of kSegBufMax keys, or (HS_SEGSORT_THREADS=512)
-  // two 512-thread blocks per SM with buffers of kSegBufMax512 keys
-  const bool half = ctx->segsort_threads == 512;
-  const uint32_t bufmax = half ? kSegBufMax512 : kSegBufMax;
+  // the per-bin sort: one 1024-thread block per SM, shared memory for kSegBufMax (key, position) pairs
+  // (two blocks of 512 threads with half the buffer each were measured: twice as slow)
+  const uint32_t bufmax = kSegBufMax;
   const size_t sort_smem = sizeof(uint32_t) * 2 * bufmax;
   // (per device: a process may drive several GPUs, each with its own context)
   HS_CUDA(cudaFuncSetAttribute(seg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) << kSegMaxBinBits)));
   HS_CUDA(cudaFuncSetAttribute(seg_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) << kSegMaxBinBits)));
-  HS_CUDA(cudaFuncSetAttribute(seg_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * 2 * kSegBufMax)));
-  HS_CUDA(cudaFuncSetAttribute(seg_sort_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * 2 * kSegBufMax512)));
+  HS_CUDA(cudaFuncSetAttribute(seg_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
   HS_TRY(ctx->d_seg_tab.reserve(sizeof(uint32_t) * (ntab + 1)));
   HS_TRY(ctx->d_seg_key.reserve(sizeof(uint32_t) * n));
   HS_TRY(ctx->d_seg_dist.reserve(sizeof(double) * n));
@@ -456,9 +569,9 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   o.id_base = ctx->id_base;
   o.id_bits = rq.id_bits;
   const uint32_t bufcap = std::min<uint32_t>(bufmax, ctx->segsort_buf);  // (0, a test hook: no bin fits, every list is handed back)
-  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)f.nbins, (uint64_t)ctx->num_sms * (half ? 2 : 1));
-  if (half) seg_sort_kernel<512><<<grid, 512, sort_smem, ctx->stream>>>(pkey, pdist, n, f, tab, o, bufcap, bufmax, ctl + 2, ctl);
-  else seg_sort_kernel<1024><<<grid, 1024, sort_smem, ctx->stream>>>(pkey, pdist, n, f, tab, o, bufcap, bufmax, ctl + 2, ctl);
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)f.nbins, (uint64_t)ctx->num_sms);
+  seg_sort_kernel<1024><<<grid, 1024, sort_smem, ctx->stream>>>(pkey, pdist, n, f, tab, o, bufcap, bufmax, ctx->segsort_radix ? 1u : 0u,
+                                                                  ctl + 2, ctl);
   ctx->stats.kernel_launches += 3;
   if (rq.compact) {
     const uint32_t nq = rq.qb - rq.qa + 1;
@@ -472,8 +585,8 @@ int sort_hits_segmented(hs_ctx *ctx, const hs_hit *d_hits, uint64_t n, const Seg
   if (ctx->segsort_prof) {
     float ms[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], pe[i], pe[i + 1]);
-    fprintf(stderr, "segsort: n=%llu bins=%u blocks=%u threads=%d rb=%d  hist %.3f  scan %.3f  scatter %.3f  sort %.3f ms  flags %u %u\n",
-            (unsigned long long)n, f.nbins, f.nblk, half ? 512 : 1024, f.rb, ms[0], ms[1], ms[2], ms[3], h_flags[0], h_flags[1]);
+    fprintf(stderr, "segsort: n=%llu bins=%u blocks=%u radix=%d rb=%d  hist %.3f  scan %.3f  scatter %.3f  sort %.3f ms  flags %u %u\n",
+            (unsigned long long)n, f.nbins, f.nblk, ctx->segsort_radix ? 1 : 0, f.rb, ms[0], ms[1], ms[2], ms[3], h_flags[0], h_flags[1]);
     for (cudaEvent_t e : pe) cudaEventDestroy(e);
   }
   if (h_flags[0] || h_flags[1]) {

@@ -132,6 +132,11 @@ template <typename T>
 static inline T __ldg(const T *p) {
   return *p;
 }
+static inline uint32_t atomicMax(uint32_t *p, uint32_t v) {
+  const uint32_t o = *p;
+  if (v > o) *p = v;
+  return o;
+}
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) {
   const uint32_t o = *p;
   *p = o + v;

@@ -31,7 +31,7 @@ struct Case {
   uint32_t bufcap;
   bool compact;
   unsigned skew;  // 0: uniform queries; k: most hits in k queries
-  int threads = 1024;  // sort-kernel block size (1024 or 512)
+  int radix = 0;       // 1: the per-bin sort is forced onto the radix passes
 };
 
 static bool run_case(const Case &c, unsigned seed) {
@@ -72,11 +72,17 @@ static bool run_case(const Case &c, unsigned seed) {
   f.tshift = ibits;
   f.qshift = ibits + tbits;
   const int kbits = f.qshift + f.qbits;
-  if (kbits > 64 || f.qbits > kSegMaxBinBits) return true;
+  if (kbits > 64 || f.qbits > kSegMaxBinBits) {
+    printf("  (not applicable: key layout)\n");
+    return true;
+  }
   const int pb = std::min(kbits, kSegMaxBinBits);
   f.shift = kbits - pb;
   f.rb = f.shift;
-  if (f.rb > 32) return true;
+  if (f.rb > 32) {
+    printf("  (not applicable: rb > 32)\n");
+    return true;
+  }
   f.nbins = (uint32_t)(((((uint64_t)c.Q << f.qshift) - 1ull) >> f.shift) + 1ull);
   const uint64_t want_blk = (n + 8191) / 8192;
   f.nblk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want_blk, 6));
@@ -106,12 +112,9 @@ static bool run_case(const Case &c, unsigned seed) {
   o.id_base = c.id_base;
   o.id_bits = bits_for(std::max<uint64_t>(c.N, 2));
   const unsigned grid = std::min<uint32_t>(f.nbins, 3);
-  if (c.threads == 512) {
-    const uint32_t cap = std::min<uint32_t>(c.bufcap, kSegBufMax512);
-    launched = launched && emu_launch(grid, 512, [&]() { seg_sort_kernel<512>(pkey.data(), pdist.data(), n, f, tab.data(), o, cap, kSegBufMax512, ctl + 2, ctl); });
-  } else {
-    launched = launched && emu_launch(grid, 1024, [&]() { seg_sort_kernel<1024>(pkey.data(), pdist.data(), n, f, tab.data(), o, c.bufcap, kSegBufMax, ctl + 2, ctl); });
-  }
+  launched = launched && emu_launch(grid, 1024, [&]() {
+    seg_sort_kernel<1024>(pkey.data(), pdist.data(), n, f, tab.data(), o, c.bufcap, kSegBufMax, c.radix ? 1u : 0u, ctl + 2, ctl);
+  });
   if (c.compact) {
     const uint32_t nq = c.Q + 1;
     launched = launched && emu_launch((nq + 255) / 256, 256, [&]() { seg_query_offsets_kernel(tab.data(), n, f, 0, c.Q, 1000, offsets.data()); });
@@ -174,7 +177,7 @@ int main(int argc, char **argv) {
       {1, 1, 5, 0, 5, 22528, true, 0},                      // every bit in the bin
       {2600, 4, 60000, 0, 5000, 0, false, 0},               // buffer 0: handed back
       {32768, 32, 1000, 125000000ull, 20000, 22528, true, 5},
-      {10000, 4, 100000000ull, 0, 40000, 22528, true, 3, 512},
+      {10000, 4, 100000000ull, 0, 40000, 22528, true, 3, 1},
   };
 #else
   // (a build with few bins, -DHS_SEG_BIN_BITS=6: the same kernels, the per-bin loop is short)
@@ -189,9 +192,11 @@ int main(int argc, char **argv) {
       {33, 4, 60000, 0, 5000, 0, false, 0},                 // buffer 0: handed back
       {1, 1, 5, 0, 5, 22528, true, 0},                      // every bit in the bin
       {7, 2, 100, 0, 600, 9, true, 0},                      // tiny key, tiny buffer
-      {64, 4, 100000000ull, 0, 40000, 22528, false, 3, 512}, // 512-thread sort blocks: ~12 k keys per bin > their 10240-key buffer
-      {50, 4, 60000, 0, 3000, 22528, true, 0, 512},
-      {60, 4, 200000, 0, 30000, 2000, true, 2, 512},
+      {64, 4, 100000000ull, 0, 40000, 22528, false, 3, 1},  // the same lists with the per-bin sort forced onto the radix passes
+      {50, 4, 60000, 0, 3000, 22528, true, 0, 1},
+      {60, 4, 200000, 0, 30000, 2000, true, 2, 1},
+      {60, 4, 200000, 0, 60000, 22528, false, 2, 1},
+      {64, 4, 3000, 8000000ull, 30000, 22528, true, 1},     // ids in a narrow band far from 0: keys pile up in a few buckets -> radix passes by themselves
   };
 #endif
   int bad = 0, i = 0;
@@ -201,8 +206,8 @@ int main(int argc, char **argv) {
       continue;
     }
     const bool ok = run_case(c, 1234 + i);
-    printf("case %d: Q=%u L=%u N=%llu id_base=%llu n=%llu buf=%u threads=%d %s -> %s\n", i, c.Q, c.L, (unsigned long long)c.N,
-           (unsigned long long)c.id_base, (unsigned long long)c.n, c.bufcap, c.threads, c.compact ? "compact" : "plain", ok ? "ok" : "FAILED");
+    printf("case %d: Q=%u L=%u N=%llu id_base=%llu n=%llu buf=%u radix=%d %s -> %s\n", i, c.Q, c.L, (unsigned long long)c.N,
+           (unsigned long long)c.id_base, (unsigned long long)c.n, c.bufcap, c.radix, c.compact ? "compact" : "plain", ok ? "ok" : "FAILED");
     if (!ok) ++bad;
     ++i;
   }

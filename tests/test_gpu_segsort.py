@@ -2,7 +2,7 @@
 memory) against the radix passes and the oracle: the hit list of motif_both_points.cpp:224-245 --
 per query, per first table, ascending db id -- must come out byte for byte the same whichever
 path orders it, in both output formats, including the range path of bins larger than the
-shared-memory buffer and the hand-back to the radix passes."""
+shared-memory buffer, both per-bin sorts (buckets, radix passes) and the hand-back to the radix passes."""
 import numpy as np
 import pytest
 
@@ -14,13 +14,14 @@ pytestmark = pytest.mark.gpu
 MODES = {
     "radix": {"HS_SEGSORT": "0"},
     "seg": {"HS_SEGSORT": "1", "HS_SEGSORT_MIN": "0"},
+    "seg_radix": {"HS_SEGSORT": "1", "HS_SEGSORT_MIN": "0", "HS_SEGSORT_RADIX": "1"},   # per-bin sort on the radix passes, not the buckets
     "seg_ranges": {"HS_SEGSORT": "1", "HS_SEGSORT_MIN": "0", "HS_SEGSORT_BUF": "48"},
     "seg_handback": {"HS_SEGSORT": "1", "HS_SEGSORT_MIN": "0", "HS_SEGSORT_BUF": "0"},   # no bin fits: every list is handed back
 }
 
 
 def set_mode(monkeypatch, name):
-    for k in ("HS_SEGSORT", "HS_SEGSORT_MIN", "HS_SEGSORT_BUF"):
+    for k in ("HS_SEGSORT", "HS_SEGSORT_MIN", "HS_SEGSORT_BUF", "HS_SEGSORT_RADIX"):
         monkeypatch.delenv(k, raising=False)
     for k, v in MODES[name].items():
         monkeypatch.setenv(k, v)   # read once, by hs_create
@@ -85,7 +86,7 @@ def test_segsort_large_bins_brute_force(oracle, monkeypatch):
     near = np.arange(12) * 700 + 5
     qpts[near] = oracle.embed(planted_queries(codes, 12, seed=52, frac=0.5), tab)
     res, used = {}, {}
-    for mode in ("radix", "seg", "seg_ranges"):
+    for mode in ("radix", "seg", "seg_radix", "seg_ranges"):
         set_mode(monkeypatch, mode)
         h, a, b = make(length, 4, 4, 50.0, R, flags=hb.HS_FLAG_SORT_HITS)
         h.load_fragments(codes)
@@ -101,11 +102,11 @@ def test_segsort_large_bins_brute_force(oracle, monkeypatch):
     assert per_query.max() > 30000, per_query.max()    # larger than one shared-memory buffer (22528 keys)
     key = base["query"].astype(np.int64) * (1 << 32) + base["db_id"].astype(np.int64)
     assert np.all(np.diff(key) > 0)
-    for mode in ("seg", "seg_ranges"):
+    for mode in ("seg", "seg_radix", "seg_ranges"):
         assert np.array_equal(res[mode], base), mode
     assert used["radix"][:2] == (0, 0)
-    for mode in ("seg", "seg_ranges"):
-        assert used[mode][0] + used[mode][1] >= 1, used   # the segmented sort took the list (or handed it back)
+    assert used["seg"][:2] == (1, 0) and used["seg_radix"][:2] == (1, 0), used   # bins of > 100 k keys: taken in ranges
+    assert used["seg_ranges"][:2] == (0, 1), used    # a 48-key buffer cannot hold one value of the top 8 key bits: handed back
 
 
 def test_segsort_empty_and_tiny_lists(monkeypatch):
