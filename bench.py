@@ -538,6 +538,7 @@ def run_native(a):
     ncand_tc = s_search["n_candidates_tc"]
     passes = s_build["sort_passes"]  # over all L tables
     rank_path = bool(s_build["rank_path"])
+    seg_lists = int(s_search.get("segsort_lists", 0) or 0)   # the last search's hit list was ordered by the segmented sort
     # algorithmic bytes per launch family (DESIGN.md "Kernels"); rank path: u16 bucket ranks + 32-byte
     # fragment records instead of 64-bit packed keys
     rec = ((length + 1) // 2 * 2 + 2 * a.L + 15) // 16 * 16 if rank_path else (length + 15) // 16 * 16
@@ -569,8 +570,11 @@ def run_native(a):
                               "flops": 2.0 * ncand_tc * 8 * length},
         # survivor (16) + id (4) + fragment record + hit (24)
         "exact_kernel": {"ms": acc["ms_exact"] / steps, "bytes": nsurv * (16 + 4 + rec) + nh * 24, "launches": 1},
-        # one-word key build (24 + 8), radix passes over (key, perm) and the 24-byte gather
-        "hit_sort": {"ms": acc["ms_hitsort"] / steps, "bytes": nh * (32 + 6 * 32 + 4 + 48), "launches": 1},
+        # radix path: one-word key build (24 + 8), radix passes over (key, perm) and the 24-byte gather;
+        # segmented path (csrc/hitsort.cu): bin histogram (24), partition (24 + 12), per-bin sort (2 * 4 + 8 + 24)
+        "hit_sort": {"ms": acc["ms_hitsort"] / steps,
+                     "bytes": nh * (24 + 36 + 40) if seg_lists else nh * (32 + 6 * 32 + 4 + 48), "launches": 1,
+                     "path": "segmented (partition by query + per-bin bucket sort)" if seg_lists else "radix passes"},
     }
     for k, v in kern.items():
         v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
@@ -751,6 +755,7 @@ def run_native(a):
                                                                              acc["ms_filter"] + acc["ms_exact"] +
                                                                              acc["ms_hitsort"]) / steps * 1e-3),
                       "sort_passes": int(passes), "key_words": int(KW), "rank_path": rank_path,
+                      "hit_sort_path": "segmented" if seg_lists else "radix",
                       "guard_hits": int(s_hash["guard_hits"]), "guard_corrected": int(s_hash["guard_corrected"]),
                       "residual_flips": residual_flips}}
     print(json.dumps(out), flush=True)

@@ -1509,7 +1509,7 @@ int hs_create(hs_ctx_t **out, int device, const hs_params *params) {
   ctx->no_mma_filter = env_on("HS_NO_MMA_FILTER");
   ctx->no_mma_int = env_on("HS_NO_MMA_INT");
   ctx->surv_bins = env_on("HS_SURV_BINS");
-  ctx->segsort = env_on("HS_SEGSORT");
+  if (const char *e = getenv("HS_SEGSORT")) ctx->segsort = atoi(e) != 0;
   if (const char *e = getenv("HS_SEGSORT_MIN")) ctx->segsort_min = strtoull(e, nullptr, 10);
   if (const char *e = getenv("HS_SEGSORT_NBLK")) ctx->segsort_nblk = (uint32_t)std::max(0, atoi(e));
   ctx->segsort_prof = env_on("HS_SEGSORT_PROF");

@@ -245,7 +245,7 @@ struct hs_ctx {
   bool surv_bins = false;        // HS_SURV_BINS: survivors regrouped by fragment-id block before the exact stage
   bool no_mma_int = false;       // HS_NO_MMA_INT: the integer metric stays on the one-hot tensor filter (filter_tc.cu)
   bool no_mma_filter = false;    // HS_NO_MMA_FILTER: keep the Euclidean metric off the pipelined tensor filter
-  bool segsort = false;          // HS_SEGSORT=1: hit lists ordered by the segmented sort (hitsort.cu) instead of the radix passes
+  bool segsort = true;           // HS_SEGSORT=0: hit lists ordered by the radix passes only, never by the segmented sort (hitsort.cu)
   uint64_t segsort_min = 1u << 18;   // HS_SEGSORT_MIN: ... for lists of at least this many hits
   uint32_t segsort_buf = 1u << 30;   // HS_SEGSORT_BUF: keys per shared-memory buffer (test hook: forces the range path)
   uint32_t segsort_nblk = 0;         // HS_SEGSORT_NBLK: blocks of its partition pass (0: two per SM)
