@@ -127,6 +127,21 @@ static inline uint32_t __shfl_up_sync(uint32_t, uint32_t x, int delta) {
   return lane >= delta ? v[lane - delta] : x;
 }
 static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t x, int m) { return emu_exchange(x)[(threadIdx.x & 31) ^ m]; }
+static inline unsigned long long __shfl_xor_sync(uint32_t, unsigned long long x, int m) {
+  const uint32_t lo = emu_exchange((uint32_t)x)[(threadIdx.x & 31) ^ m];
+  const uint32_t hi = emu_exchange((uint32_t)(x >> 32))[(threadIdx.x & 31) ^ m];
+  return ((unsigned long long)hi << 32) | lo;
+}
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) {
+  const unsigned long long o = *p;
+  *p = o | v;
+  return o;
+}
+static inline unsigned long long atomicAnd(unsigned long long *p, unsigned long long v) {
+  const unsigned long long o = *p;
+  *p = o & v;
+  return o;
+}
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 template <typename T>
 static inline T __ldg(const T *p) {

@@ -1,0 +1,170 @@
+// CPU emulation run of the index-build sort kernels of hsearch_b200/csrc/radix_sort.cu (B1: the
+// unordered_map insert of motif_both_points.cpp:212-218 as a stable sort): the rank path (u16 bucket
+// ranks, two 8-bit passes, bucket boundaries), the device-wide exclusive scan, and one pass of the
+// general (key word, index) radix sort.  The kernel text is compiled unchanged over cuda_emu.h
+// (radixsort_kernels.inc is cut out of the .cu file by tests/test_emu_ranksort.py); the host
+// orchestration below mirrors build_table_index_ranks / exclusive_scan_u32 / radix_sort_pairs.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <numeric>
+#include <random>
+#include <vector>
+
+#include "cuda_emu.h"
+
+namespace hs {
+constexpr int kMaxKeyWords = 4;
+struct KeyPtrs {
+  uint64_t *w[kMaxKeyWords];
+};
+#include "radixsort_kernels.inc"
+}  // namespace hs
+
+using namespace hs;
+
+// exclusive_scan_u32 with the library's three kernels
+static bool scan_u32(std::vector<uint32_t> &v, uint32_t *total) {
+  const uint64_t n = v.size();
+  if (n == 0) return true;
+  const uint32_t nblocks = (uint32_t)((n + kScanTile - 1) / kScanTile);
+  std::vector<uint32_t> sums(nblocks + 1, 0);
+  bool ok = emu_launch(nblocks, kScanThreads, [&]() { scan_reduce_kernel(v.data(), n, sums.data()); });
+  ok = ok && emu_launch(1, kScanThreads, [&]() { scan_sums_kernel(sums.data(), nblocks, total); });
+  ok = ok && emu_launch(nblocks, kScanThreads, [&]() { scan_downsweep_kernel(v.data(), v.data(), n, sums.data()); });
+  return ok;
+}
+
+static bool test_scan(uint64_t n, unsigned seed) {
+  std::mt19937 rng(seed);
+  std::vector<uint32_t> v(n), want(n);
+  for (auto &x : v) x = rng() % 1000;
+  uint32_t run = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    want[i] = run;
+    run += v[i];
+  }
+  uint32_t total = 0;
+  if (!scan_u32(v, &total)) return false;
+  return v == want && total == run;
+}
+
+// build_table_index_ranks: ids in bucket order, sorted ranks, slot boundaries
+static bool test_rank_index(uint64_t n, uint32_t nr, unsigned seed) {
+  std::mt19937 rng(seed);
+  std::vector<uint16_t> ranks(n + 16, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t r = rng() % nr;
+    if (rng() % 4 == 0) r = (rng() % 3) * (nr / 3) % nr;   // a few heavy buckets
+    ranks[i] = (uint16_t)r;
+  }
+  const uint32_t ntiles = (uint32_t)((n + kRkTile - 1) / kRkTile);
+  std::vector<uint32_t> tile_hist((uint64_t)ntiles * 256 + 1, 0), vtmp(n), ids(n);
+  std::vector<uint16_t> ktmp(n + 16, 0), ksorted(n + 16, 0);
+  int hibits = 0;
+  while (((uint64_t)256 << hibits) < nr) ++hibits;
+  const int npass = nr > 256 ? 2 : 1;
+  bool ok = true;
+  for (int pi = 0; pi < npass; ++pi) {
+    const int shift = 8 * pi;
+    const uint32_t mask = pi == 0 ? 0xffu : ((1u << hibits) - 1u);
+    const uint16_t *kin = pi == 0 ? ranks.data() : ktmp.data();
+    ok = ok && emu_launch(ntiles, kRkThreads, [&]() { rank_upsweep_kernel(kin, n, shift, mask, tile_hist.data(), ntiles); });
+    tile_hist.resize((uint64_t)ntiles * 256);
+    ok = ok && scan_u32(tile_hist, nullptr);
+    tile_hist.resize((uint64_t)ntiles * 256 + 1);
+    if (npass == 1)
+      ok = ok && emu_launch(ntiles, kRkThreads, [&]() {
+        rank_downsweep_kernel<true, true>(kin, nullptr, ksorted.data(), ids.data(), n, shift, mask, tile_hist.data(), ntiles);
+      });
+    else if (pi == 0)
+      ok = ok && emu_launch(ntiles, kRkThreads, [&]() {
+        rank_downsweep_kernel<true, false>(kin, nullptr, ktmp.data(), vtmp.data(), n, shift, mask, tile_hist.data(), ntiles);
+      });
+    else
+      ok = ok && emu_launch(ntiles, kRkThreads, [&]() {
+        rank_downsweep_kernel<false, true>(kin, vtmp.data(), ksorted.data(), ids.data(), n, shift, mask, tile_hist.data(), ntiles);
+      });
+  }
+  std::vector<uint32_t> bstart(nr + 1, 0xdeadbeefu);
+  unsigned int nb = 0;
+  ok = ok && emu_launch((unsigned)(((n + 7) / 8 + 255) / 256), 256, [&]() { rank_bounds_kernel(ksorted.data(), n, nr, bstart.data(), &nb); });
+  if (!ok) return false;
+  // expectation: stable sort of the ids by rank
+  std::vector<uint32_t> want(n);
+  std::iota(want.begin(), want.end(), 0u);
+  std::stable_sort(want.begin(), want.end(), [&](uint32_t a, uint32_t b) { return ranks[a] < ranks[b]; });
+  unsigned int distinct = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (ids[i] != want[i] || ksorted[i] != ranks[want[i]]) {
+      printf("  rank index: mismatch at %llu\n", (unsigned long long)i);
+      return false;
+    }
+    if (i == 0 || ksorted[i] != ksorted[i - 1]) ++distinct;
+  }
+  for (uint32_t r = 0; r <= nr; ++r) {
+    const uint32_t lb = (uint32_t)(std::lower_bound(ksorted.begin(), ksorted.begin() + n, (uint16_t)std::min<uint32_t>(r, 65535)) - ksorted.begin());
+    const uint32_t expect = r == nr ? (uint32_t)n : lb;
+    if (bstart[r] != expect) {
+      printf("  rank index: slot %u starts at %u, expected %u\n", r, bstart[r], expect);
+      return false;
+    }
+  }
+  if (nb != distinct) {
+    printf("  rank index: %u non-empty slots, expected %u\n", nb, distinct);
+    return false;
+  }
+  return true;
+}
+
+// one pass of the general sort: stable partition of (key word, index) by an 8-bit digit
+static bool test_radix_pass(uint64_t n, int shift, bool with_vals, unsigned seed) {
+  std::mt19937_64 rng(seed);
+  std::vector<uint64_t> kin(n), kout(n, 0);
+  std::vector<uint32_t> vin(n), vout(n, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    kin[i] = rng();
+    vin[i] = (uint32_t)(rng() % 1000000);
+  }
+  const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+  std::vector<uint32_t> tile_hist((uint64_t)ntiles * 256, 0);
+  bool ok = emu_launch(ntiles, kSortThreads, [&]() { radix_upsweep_kernel(kin.data(), n, shift, 0xffu, tile_hist.data(), ntiles); });
+  ok = ok && scan_u32(tile_hist, nullptr);
+  KeyPtrs in{}, out{};
+  in.w[0] = kin.data();
+  out.w[0] = kout.data();
+  ok = ok && emu_launch(ntiles, kSortThreads, [&]() {
+    radix_downsweep_kernel<1>(in, with_vals ? vin.data() : nullptr, out, vout.data(), n, 0, shift, 0xffu, tile_hist.data(), ntiles);
+  });
+  if (!ok) return false;
+  std::vector<uint32_t> order(n);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ((kin[a] >> shift) & 0xff) < ((kin[b] >> shift) & 0xff); });
+  for (uint64_t i = 0; i < n; ++i)
+    if (kout[i] != kin[order[i]] || vout[i] != (with_vals ? vin[order[i]] : order[i])) {
+      printf("  radix pass: mismatch at %llu\n", (unsigned long long)i);
+      return false;
+    }
+  return true;
+}
+
+int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
+  int bad = 0;
+  auto report = [&](const char *what, bool ok) {
+    printf("%s -> %s\n", what, ok ? "ok" : "FAILED");
+    if (!ok) ++bad;
+  };
+  report("scan n=1", test_scan(1, 1));
+  report("scan n=4096", test_scan(4096, 2));
+  report("scan n=70001", test_scan(70001, 3));
+  report("rank index n=20011 nr=14641 (two passes)", test_rank_index(20011, 14641, 4));
+  report("rank index n=4096 nr=14641 (one whole tile)", test_rank_index(4096, 14641, 5));
+  report("rank index n=9000 nr=200 (one pass)", test_rank_index(9000, 200, 6));
+  report("rank index n=5 nr=65536", test_rank_index(5, 65536, 7));
+  report("rank index n=12289 nr=257", test_rank_index(12289, 257, 8));
+  report("radix pass n=9000 shift=8 implicit index", test_radix_pass(9000, 8, false, 9));
+  report("radix pass n=4097 shift=56 values", test_radix_pass(4097, 56, true, 10));
+  return bad ? 1 : 0;
+}
