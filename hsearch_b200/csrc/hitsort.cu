@@ -10,17 +10,22 @@
 //   exclusive_scan_u32  over the (bin, block) table: the start of every block's run in every bin
 //   seg_scatter_kernel  each block re-reads its chunk of hits and writes (low key u32, dist2 f64)
 //                       to the next free position of the hit's bin (shared-memory cursors)
-//   seg_sort_kernel     one 1024-thread block per bin: the bin's low keys are sorted in shared
-//                       memory (LSD radix, 8-bit digits, stable ballot ranking), written out in
-//                       their final format, and every hit's distance is placed at the rank of its
-//                       key (binary search: the keys of a bin are unique -- a (query, fragment)
-//                       pair is reported once).  A bin larger than the shared-memory buffer is
-//                       processed in ranges of its top 8 key bits, each range <= the buffer.
+//   seg_sort_kernel     one 1024-thread block per SM, bins handed out by a counter.  A bin's keys fall
+//                       into 4096 buckets by their leading bits: histogram, block scan and one scatter
+//                       of (key, position) pairs put every bucket in place in shared memory, each bucket
+//                       (a few keys when ids are spread evenly) is insertion-sorted by one thread, and
+//                       the records are written in their final format.  A bin larger than the buffer is
+//                       taken in ranges of its top 8 key bits, each range <= the buffer.  A range whose
+//                       keys pile up in few buckets is sorted by stable LSD radix passes (8-bit digits,
+//                       ballot ranking) instead, its distances placed by binary search (the keys of a
+//                       bin are unique -- a (query, fragment) pair is reported once).
 //
-// Traffic: 24 + 24 + 12 bytes read, 12 + 12..24 written per hit, against 6 passes x 24 bytes
+// Traffic: 24 + 24 + 12 + 16 bytes read, 12 + 12..24 written per hit, against 6 passes x 24 bytes
 // plus keys and a random 24-byte gather for the radix sort (api.cu, sort_hits: the fallback
-// whenever a field does not fit, a bin's range overflows the buffer, or the caller needs the
-// sorted one-word keys).
+// whenever a field does not fit, one value of a bin's top 8 key bits alone exceeds the buffer, or
+// the caller needs the sorted one-word keys).  Measured at bench C2 (87 M hits): 6.6 ms against
+// 7.9 ms (profiles/r02c_hitsort.md).  The kernels run unchanged under the CPU emulation of
+// tests/emu/ (tests/test_emu_segsort.py).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -35,7 +40,7 @@ constexpr int kSegThreads = 1024;
 constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegItems = 4;
 constexpr int kSegTile = kSegThreads * kSegItems;     // keys ranked per step of a radix pass
-constexpr uint32_t kSegBufMax = 22528;                // keys per shared-memory buffer (two buffers: 176 KB), 1024-thread sort blocks
+constexpr uint32_t kSegBufMax = 22528;                // (key, position) pairs of the per-bin sort's buffer = keys per radix buffer (176 KB)
 constexpr int kSegBucketBits = 12;
 constexpr int kSegBuckets = 1 << kSegBucketBits;      // buckets of the per-bin bucket sort
 constexpr uint32_t kSegBucketMax = 48;                // keys in the fullest bucket up to which a range takes the bucket path
