@@ -21,6 +21,7 @@
 #define __launch_bounds__(...)
 #define __align__(x) alignas(x)
 #define __shared__ static
+#define __constant__ static const
 
 struct emu_dim3 {
   unsigned x = 1, y = 1, z = 1;
@@ -146,6 +147,11 @@ static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 template <typename T>
 static inline T __ldg(const T *p) {
   return *p;
+}
+static inline uint32_t atomicCAS(uint32_t *p, uint32_t expect, uint32_t v) {
+  const uint32_t o = *p;
+  if (o == expect) *p = v;
+  return o;
 }
 static inline uint32_t atomicMax(uint32_t *p, uint32_t v) {
   const uint32_t o = *p;
