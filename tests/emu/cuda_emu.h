@@ -144,6 +144,17 @@ static inline unsigned long long atomicAnd(unsigned long long *p, unsigned long 
   return o;
 }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+// IEEE double operations, round to nearest (compile the harness with -ffp-contract=off: no fused multiply-add)
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline int __shfl_sync(uint32_t m, int x, int src) { return (int)__shfl_sync(m, (uint32_t)x, src); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+  const unsigned long long o = *p;
+  *p = o + v;
+  return o;
+}
 template <typename T>
 static inline T __ldg(const T *p) {
   return *p;
