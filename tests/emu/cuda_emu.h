@@ -19,7 +19,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 #define __shared__ static
 #define __constant__ static const
 
@@ -33,6 +33,10 @@ struct uint4 {
   uint32_t x, y, z, w;
 };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+struct alignas(16) double2 {
+  double x, y;
+};
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 static emu_dim3 threadIdx, blockIdx, blockDim, gridDim;   // threadIdx: the running fiber's
 
@@ -150,6 +154,13 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline int __shfl_sync(uint32_t m, int x, int src) { return (int)__shfl_sync(m, (uint32_t)x, src); }
+static inline unsigned long long __shfl_sync(uint32_t m, unsigned long long x, int src) {
+  const uint32_t lo = __shfl_sync(m, (uint32_t)x, src), hi = __shfl_sync(m, (uint32_t)(x >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
+}
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
   const unsigned long long o = *p;
   *p = o + v;
