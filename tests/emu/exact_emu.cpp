@@ -137,7 +137,7 @@ static std::vector<HitKey> as_keys(const std::vector<orc_hit> &h, uint64_t n) {
 
 // LSH search: survivors = every member of every query's bucket in every table
 template <int NV, int REP>
-static bool test_search(int len, double W, double R, uint64_t N, uint32_t Q, bool string_queries, unsigned seed) {
+static bool test_search(int len, double W, double R, uint64_t N, uint32_t Q, bool string_queries, unsigned seed, bool rank_path = false) {
   Setup S;
   S.len = len; S.K = 4; S.L = 4; S.W = W; S.R = R; S.N = N; S.Q = Q;
   make_setup(S, seed);
@@ -190,6 +190,37 @@ static bool test_search(int len, double W, double R, uint64_t N, uint32_t Q, boo
   ea.keys = kptr.data();
   ea.qkeys = qkeys.data();
   ea.qvalid = qvalid.data();
+  // rank path (the headline configuration): a fragment's bucket in table l is the u16 rank of its key among the
+  // table's keys, kept in its 32-byte record behind the codes; a query's is qrank[l][q] (0xffffffff: no bucket)
+  std::vector<uint8_t> rec32;
+  std::vector<uint32_t> qrank;
+  if (rank_path) {
+    const uint32_t RS = 32, off = (uint32_t)((len + 1) & ~1);
+    rec32.assign(N * RS + 64, 0);
+    qrank.assign((size_t)S.L * Q, 0xffffffffu);
+    for (uint64_t i = 0; i < N; ++i) memcpy(&rec32[i * RS], &S.codes[i * len], len);
+    for (int l = 0; l < S.L; ++l) {
+      std::vector<uint64_t> distinct(keys[l]);
+      std::sort(distinct.begin(), distinct.end());
+      distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+      if (distinct.size() > 65535) return false;
+      for (uint64_t i = 0; i < N; ++i) {
+        const uint16_t r = (uint16_t)(std::lower_bound(distinct.begin(), distinct.end(), keys[l][i]) - distinct.begin());
+        memcpy(&rec32[i * RS + off + 2 * l], &r, 2);
+      }
+      for (uint32_t q = 0; q < Q; ++q) {
+        auto it = std::lower_bound(distinct.begin(), distinct.end(), qkeys[(size_t)l * Q + q]);
+        if (it != distinct.end() && *it == qkeys[(size_t)l * Q + q]) qrank[(size_t)l * Q + q] = (uint32_t)(it - distinct.begin());
+      }
+    }
+    ea.rec = rec32.data();
+    ea.rec_stride = RS;
+    ea.rec_rank_off = off;
+    ea.qrank = qrank.data();
+    ea.keys = nullptr;
+    ea.qkeys = nullptr;
+    ea.qvalid = nullptr;
+  }
   ea.hit_cap = surv.size() + 1;
   std::vector<HitKey> got;
   if (!run_exact<NV, REP>(S, ea, got)) return false;
@@ -255,6 +286,9 @@ int main() {
   report("search len 10 W 50 R 30, residue-string queries, plain pair table", test_search<1, 1>(10, 50.0, 30.0, 4000, 40, true, 1));
   report("search len 10 W 50 R 30, residue-string queries, replicated pair table", test_search<1, 8>(10, 50.0, 30.0, 4000, 40, true, 2));
   report("search len 10 W 50 R 36, dense queries", test_search<1, 1>(10, 50.0, 36.0, 3000, 30, false, 3));
+  report("search len 10 W 50 R 30, rank path (u16 ranks in 32-byte records), replicated pair table",
+         test_search<1, 8>(10, 50.0, 30.0, 4000, 40, true, 8, true));
+  report("search len 10 W 50 R 34, rank path, dense queries", test_search<1, 1>(10, 50.0, 34.0, 3000, 30, false, 9, true));
   report("search len 25 W 120 R 60, residue-string queries", test_search<2, 1>(25, 120.0, 60.0, 2000, 30, true, 4));
   report("brute force len 10 R 38 (sqrt predicate)", test_brute(10, 38.0, 1500, 20, false, 5));
   report("brute force len 10 R 40, integer metric", test_brute(10, 40.0, 1500, 20, true, 6));

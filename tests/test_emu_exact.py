@@ -2,7 +2,7 @@
 operation order, predicate, first-table-wins, hit emission; csrc/verify.cu) is compiled unchanged over
 tests/emu/cuda_emu.h (-ffp-contract=off) and handed every member of every query's buckets as survivors; the hits
 must equal the oracle's Search() / brute force -- set, first table and FP64 distance bit for bit -- for residue-
-string and dense queries, both layouts of the residue-pair table, len 10 / 20 / 25 and the integer metric."""
+string and dense queries, the packed-key and the rank path of the first-table rule, both layouts of the residue-pair table, len 10 / 20 / 25 and the integer metric."""
 import os
 import re
 import subprocess
@@ -49,4 +49,4 @@ def test_exact_stage_under_cpu_emulation(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stdout + out.stderr
     results = re.findall(r" -> (\w+)$", out.stdout, flags=re.M)
-    assert len(results) == 7 and all(r == "ok" for r in results), out.stdout
+    assert len(results) == 9 and all(r == "ok" for r in results), out.stdout
