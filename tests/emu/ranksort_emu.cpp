@@ -20,6 +20,7 @@ struct KeyPtrs {
   uint64_t *w[kMaxKeyWords];
 };
 #include "radixsort_kernels.inc"
+#include "probe_kernels.inc"
 }  // namespace hs
 
 using namespace hs;
@@ -149,6 +150,95 @@ static bool test_radix_pass(uint64_t n, int shift, bool with_vals, unsigned seed
   return true;
 }
 
+// probe: a query's key -> the slot holding it and the slot's member range (HashTable::find,
+// motif_both_points.cpp:228-231), on ascending multi-word keys and on the hashed-key index
+template <int KW>
+static bool test_probe(uint64_t nb, uint32_t Q, unsigned seed) {
+  std::mt19937_64 rng(seed);
+  // nb distinct keys in ascending order (word KW-1 most significant), bucket sizes 1..5
+  std::vector<std::vector<uint64_t>> ks(nb, std::vector<uint64_t>(KW));
+  for (auto &k : ks)
+    for (int w = 0; w < KW; ++w) k[w] = rng() % 7;   // few values per word: ties in the high words are common
+  auto less = [](const std::vector<uint64_t> &x, const std::vector<uint64_t> &y) {
+    for (int w = KW - 1; w >= 0; --w)
+      if (x[w] != y[w]) return x[w] < y[w];
+    return false;
+  };
+  std::sort(ks.begin(), ks.end(), less);
+  ks.erase(std::unique(ks.begin(), ks.end()), ks.end());
+  nb = ks.size();
+  std::vector<uint64_t> ukeys((size_t)KW * nb);
+  std::vector<uint32_t> bstart(nb + 1, 0);
+  for (uint64_t i = 0; i < nb; ++i) {
+    for (int w = 0; w < KW; ++w) ukeys[(uint64_t)w * nb + i] = ks[i][w];
+    bstart[i + 1] = bstart[i] + 1 + (uint32_t)(rng() % 5);
+  }
+  std::vector<uint64_t> qkeys((size_t)Q * KW);
+  std::vector<uint8_t> qvalid(Q, 1);
+  for (uint32_t q = 0; q < Q; ++q) {
+    if (q % 3 == 0) {
+      const auto &k = ks[rng() % nb];
+      for (int w = 0; w < KW; ++w) qkeys[(size_t)q * KW + w] = k[w];
+    } else {
+      for (int w = 0; w < KW; ++w) qkeys[(size_t)q * KW + w] = rng() % 8;
+    }
+    if (q % 17 == 0) qvalid[q] = 0;
+  }
+  std::vector<uint2> qrange(Q, uint2{7, 7});
+  std::vector<uint32_t> qrank(Q, 7);
+  if (!emu_launch((Q + 127) / 128, 128, [&]() {
+        probe_kernel<KW>(qkeys.data(), qvalid.data(), Q, ukeys.data(), nb, bstart.data(), qrange.data(), qrank.data());
+      }))
+    return false;
+  // the hashed-key index over the same buckets: slots in ascending order of the 64-bit key hash, a slot's key
+  // is that of its first member
+  std::vector<uint64_t> order(nb);
+  std::iota(order.begin(), order.end(), 0ull);
+  std::vector<uint64_t> hs_(nb);
+  for (uint64_t i = 0; i < nb; ++i) hs_[i] = key_hash<KW>(ks[i].data());
+  std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return hs_[x] < hs_[y]; });
+  const uint64_t N = bstart[nb];
+  std::vector<uint64_t> uhash(nb), dbkeys((size_t)KW * N, ~0ull);
+  std::vector<uint32_t> hstart(nb + 1, 0), ids(N);
+  std::iota(ids.begin(), ids.end(), 0u);
+  std::shuffle(ids.begin(), ids.end(), rng);
+  for (uint64_t s = 0; s < nb; ++s) {
+    const uint64_t i = order[s];
+    uhash[s] = hs_[i];
+    hstart[s + 1] = hstart[s] + (bstart[i + 1] - bstart[i]);
+    for (uint32_t m = hstart[s]; m < hstart[s + 1]; ++m)
+      for (int w = 0; w < KW; ++w) dbkeys[(uint64_t)w * N + ids[m]] = ks[i][w];
+  }
+  std::vector<uint2> hrange(Q, uint2{7, 7});
+  std::vector<uint32_t> hrank(Q, 7);
+  if (!emu_launch((Q + 127) / 128, 128, [&]() {
+        probe_hashed_kernel<KW>(qkeys.data(), qvalid.data(), Q, uhash.data(), dbkeys.data(), N, ids.data(), nb, hstart.data(),
+                                hrange.data(), hrank.data());
+      }))
+    return false;
+  uint32_t found = 0;
+  for (uint32_t q = 0; q < Q; ++q) {
+    std::vector<uint64_t> k(qkeys.begin() + (size_t)q * KW, qkeys.begin() + (size_t)(q + 1) * KW);
+    auto it = std::lower_bound(ks.begin(), ks.end(), k, less);
+    const bool hit = qvalid[q] && it != ks.end() && *it == k;
+    const uint64_t i = hit ? (uint64_t)(it - ks.begin()) : 0;
+    const uint32_t want_slot = hit ? (uint32_t)i : 0xffffffffu;
+    const uint2 want_r = hit ? uint2{bstart[i], bstart[i + 1]} : uint2{0, 0};
+    if (qrank[q] != want_slot || qrange[q].x != want_r.x || qrange[q].y != want_r.y) {
+      printf("  probe: query %u\n", q);
+      return false;
+    }
+    const uint64_t s = hit ? (uint64_t)(std::find(order.begin(), order.end(), i) - order.begin()) : 0;
+    const uint2 want_h = hit ? uint2{hstart[s], hstart[s + 1]} : uint2{0, 0};
+    if (hrank[q] != (hit ? (uint32_t)s : 0xffffffffu) || hrange[q].x != want_h.x || hrange[q].y != want_h.y) {
+      printf("  hashed probe: query %u\n", q);
+      return false;
+    }
+    found += hit;
+  }
+  return found > 0 && found < Q;
+}
+
 int main() {
   setvbuf(stdout, nullptr, _IONBF, 0);
   int bad = 0;
@@ -166,5 +256,8 @@ int main() {
   report("rank index n=12289 nr=257", test_rank_index(12289, 257, 8));
   report("radix pass n=9000 shift=8 implicit index", test_radix_pass(9000, 8, false, 9));
   report("radix pass n=4097 shift=56 values", test_radix_pass(4097, 56, true, 10));
+  report("probe, one-word keys, 300 slots", test_probe<1>(300, 500, 11));
+  report("probe, three-word keys, 200 slots", test_probe<3>(200, 400, 12));
+  report("probe, one slot", test_probe<2>(1, 40, 13));
   return bad ? 1 : 0;
 }

@@ -1,5 +1,6 @@
 """CPU check of the index-build sort kernels (hsearch_b200/csrc/radix_sort.cu: rank upsweep / downsweep /
-bounds, the device-wide scan, one pass of the general radix sort) under the fiber-based emulation of
+bounds, the device-wide scan, one pass of the general radix sort; csrc/verify.cu: the probe of a query's key into the
+sorted slots and into the hashed-key index) under the fiber-based emulation of
 tests/emu/cuda_emu.h: the kernel text is compiled unchanged and run against std::stable_sort -- ids in
 bucket order must be the stable order (ascending id inside a bucket = the reference's insertion order,
 motif_both_points.cpp:212-218), slot boundaries the lower bounds of the ranks."""
@@ -29,13 +30,24 @@ def kernel_text():
     return text
 
 
+def probe_text():
+    common = open(os.path.join(ROOT, "hsearch_b200", "csrc", "common.cuh")).read()
+    verify = open(os.path.join(ROOT, "hsearch_b200", "csrc", "verify.cu")).read()
+    a = common.index("template <int NW>\n__host__ __device__ __forceinline__ uint64_t key_hash")
+    text = common[a:common.index("struct TableIndex", a)]
+    text += cut(verify, "// ---- probe: query key -> bucket range", "int launch_probe(")
+    assert "asm" not in text and "<<<" not in text
+    return text
+
+
 @pytest.mark.skipif(os.uname().machine != "x86_64", reason="the emulation's fiber switch is x86-64 assembly")
 def test_index_sort_kernels_under_cpu_emulation(tmp_path):
     (tmp_path / "radixsort_kernels.inc").write_text(kernel_text())
+    (tmp_path / "probe_kernels.inc").write_text(probe_text())
     exe = tmp_path / "ranksort_emu"
     subprocess.check_call(["g++", "-O1", "-std=c++17", f"-I{tmp_path}", f"-I{os.path.join(ROOT, 'tests', 'emu')}",
                            "-o", str(exe), os.path.join(ROOT, "tests", "emu", "ranksort_emu.cpp")])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     results = re.findall(r" -> (\w+)$", out.stdout, flags=re.M)
-    assert len(results) == 10 and all(r == "ok" for r in results), out.stdout
+    assert len(results) == 13 and all(r == "ok" for r in results), out.stdout
