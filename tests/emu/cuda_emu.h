@@ -148,6 +148,7 @@ static inline unsigned long long atomicAnd(unsigned long long *p, unsigned long 
   return o;
 }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 // IEEE double operations, round to nearest (compile the harness with -ffp-contract=off: no fused multiply-add)
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
