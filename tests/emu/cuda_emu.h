@@ -159,6 +159,20 @@ static inline unsigned long long __shfl_sync(uint32_t m, unsigned long long x, i
   const uint32_t lo = __shfl_sync(m, (uint32_t)x, src), hi = __shfl_sync(m, (uint32_t)(x >> 32), src);
   return ((unsigned long long)hi << 32) | lo;
 }
+static inline uint32_t __shfl_down_sync(uint32_t, uint32_t x, int delta) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t *v = emu_exchange(x);
+  return lane + delta < 32 ? v[lane + delta] : x;
+}
+static inline double __shfl_down_sync(uint32_t m, double x, int delta) {
+  uint64_t u;
+  memcpy(&u, &x, 8);
+  const uint32_t lo = __shfl_down_sync(m, (uint32_t)u, delta), hi = __shfl_down_sync(m, (uint32_t)(u >> 32), delta);
+  u = ((uint64_t)hi << 32) | lo;
+  double r;
+  memcpy(&r, &u, 8);
+  return r;
+}
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
   return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
 }
