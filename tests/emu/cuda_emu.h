@@ -137,6 +137,16 @@ static inline unsigned long long __shfl_xor_sync(uint32_t, unsigned long long x,
   const uint32_t hi = emu_exchange((uint32_t)(x >> 32))[(threadIdx.x & 31) ^ m];
   return ((unsigned long long)hi << 32) | lo;
 }
+static inline unsigned int atomicOr(unsigned int *p, unsigned int v) {
+  const unsigned int o = *p;
+  *p = o | v;
+  return o;
+}
+static inline int atomicAdd(int *p, int v) {
+  const int o = *p;
+  *p = o + v;
+  return o;
+}
 static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) {
   const unsigned long long o = *p;
   *p = o | v;

@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <math.h>
+
 #include <random>
 #include <string>
 #include <vector>
@@ -19,6 +21,9 @@ uint64_t orc_extract_windows(const uint8_t *residues, const uint32_t *start_inde
 uint32_t orc_protein_id(const uint32_t *start_index, uint32_t nstart, uint32_t pos);
 int orc_orf6(const char *dna, int n, char *out, int *kept);
 void orc_union_find_labels(uint32_t n, const uint32_t *eu, const uint32_t *ev, uint64_t ne, uint32_t *label_out);
+void orc_klsh_generate(uint32_t feat, uint32_t bits, double sigma, double *w, double *t, double *b);
+uint64_t orc_klsh_hash(const double *p, uint32_t feat, uint32_t bits, const double *w, const double *t, const double *b);
+void orc_kmer3_features(const char *seq, uint32_t n, double *feat512);
 }
 
 namespace hs {
@@ -114,6 +119,53 @@ static bool test_orf6(uint32_t nseq, unsigned seed) {
   return true;
 }
 
+// E5 + KL1: 3-mer histogram over the reduced alphabet and the 16 random-Fourier bits (pcluster.cpp:19-32,
+// lsh.cpp:8-15,40-49).  Under the emulation cos() is libm's, the function the reference calls, so every bit must
+// equal the oracle's (on the GPU a bit inside the 1e-9 guard band is recomputed on the host).
+static bool test_kmer3_klsh(uint32_t nprot, unsigned seed) {
+  std::mt19937 rng(seed);
+  const uint32_t bits = 16;
+  std::vector<double> w((size_t)bits * kFeat), t(bits), b(bits), wT((size_t)kFeat * bits);
+  orc_klsh_generate(kFeat, bits, 0.2, w.data(), t.data(), b.data());
+  for (uint32_t i = 0; i < bits; ++i)
+    for (int j = 0; j < kFeat; ++j) wT[(size_t)j * bits + i] = w[(size_t)i * kFeat + j];
+  const char *aa = "ARNDCQEGHILKMFPSTWYV";
+  std::string res;
+  std::vector<uint64_t> start(nprot + 1, 0);
+  for (uint32_t p = 0; p < nprot; ++p) {
+    const uint32_t n = p < 5 ? p : 20 + rng() % 400;      // proteins shorter than a 3-mer too
+    for (uint32_t i = 0; i < n; ++i) res.push_back(aa[rng() % 20]);
+    start[p + 1] = res.size();
+  }
+  std::vector<uint32_t> feat((size_t)nprot * kFeat, 7);
+  std::vector<uint64_t> hash(nprot, 7);
+  std::vector<uint8_t> flags(nprot, 7);
+  if (!emu_launch(4, 128, [&]() {
+        kmer3_klsh_kernel(res.data(), start.data(), nprot, wT.data(), t.data(), b.data(), bits, feat.data(), hash.data(), flags.data());
+      }))
+    return false;
+  for (uint32_t p = 0; p < nprot; ++p) {
+    const uint32_t n = (uint32_t)(start[p + 1] - start[p]);
+    double want[512];
+    orc_kmer3_features(res.data() + start[p], n, want);
+    for (int i = 0; i < kFeat; ++i)
+      if ((double)feat[(size_t)p * kFeat + i] != want[i]) {
+        printf("  3-mer histogram of protein %u differs\n", p);
+        return false;
+      }
+    if (n < 3) {
+      if (flags[p] != 0) return false;
+      continue;
+    }
+    if ((flags[p] & 1) == 0 || (flags[p] & 4)) return false;
+    if (hash[p] != orc_klsh_hash(want, kFeat, bits, w.data(), t.data(), b.data())) {
+      printf("  KLSH value of protein %u differs\n", p);
+      return false;
+    }
+  }
+  return true;
+}
+
 static bool test_union_find(uint32_t n, uint64_t ne, unsigned seed) {
   std::mt19937 rng(seed);
   std::vector<uint32_t> eu(ne), ev(ne);
@@ -163,6 +215,7 @@ int main() {
   report("windows + protein id: 200 proteins, len 25, stride 3", test_extract(200, 25, 3, 2));
   report("windows + protein id: 1 protein, len 1, stride 1", test_extract(1, 1, 1, 3));
   report("six-frame translation: 120 sequences", test_orf6(120, 4));
+  report("3-mer histograms + KLSH bits: 80 proteins", test_kmer3_klsh(80, 8));
   report("union-find: 5000 ids, 3000 edges", test_union_find(5000, 3000, 5));
   report("union-find: 400 ids, 4000 edges", test_union_find(400, 4000, 6));
   report("union-find: 1000 ids, no edge", test_union_find(1000, 0, 7));
