@@ -107,6 +107,17 @@ static inline void emu_wait(EmuBarrier &b) {
 static inline EmuWarp &emu_warp() { return emu_warps[threadIdx.x >> 5]; }
 static inline void __syncthreads() { emu_wait(emu_block_bar); }
 static inline void __syncwarp() { emu_wait(emu_warp().bar); }
+// Block barrier that also ORs a predicate over the block.  The accumulator of a barrier generation is reset by
+// the generation's first arrival; it was last used two generations earlier, and every thread read that result
+// before it could arrive at the generation in between.
+static uint32_t emu_or_acc[2];
+static inline int __syncthreads_or(int pred) {
+  const unsigned slot = (unsigned)(emu_block_bar.gen & 1u);
+  if (emu_block_bar.arrived == 0) emu_or_acc[slot] = 0;
+  if (pred) emu_or_acc[slot] = 1;
+  emu_wait(emu_block_bar);
+  return (int)emu_or_acc[slot];
+}
 // A collective: every lane deposits its value in the slot array of the operation's parity and
 // waits for the warp; the array is reused two operations later, after every lane has read it.
 static inline const uint32_t *emu_exchange(uint32_t v) {
@@ -198,6 +209,11 @@ static inline T __ldg(const T *p) {
 static inline uint32_t atomicCAS(uint32_t *p, uint32_t expect, uint32_t v) {
   const uint32_t o = *p;
   if (o == expect) *p = v;
+  return o;
+}
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
+  const unsigned long long o = *p;
+  if (v > o) *p = v;
   return o;
 }
 static inline uint32_t atomicMax(uint32_t *p, uint32_t v) {
