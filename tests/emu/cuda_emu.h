@@ -22,6 +22,7 @@
 #define __align__(x) __attribute__((aligned(x)))
 #define __shared__ static
 #define __constant__ static const
+#define __noinline__
 
 struct emu_dim3 {
   unsigned x = 1, y = 1, z = 1;
@@ -33,6 +34,18 @@ struct uint4 {
   uint32_t x, y, z, w;
 };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+struct alignas(16) float4 {
+  float x, y, z, w;
+};
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+template <typename T>
+static inline T min(T a, T b) {
+  return b < a ? b : a;
+}
+template <typename T>
+static inline T max(T a, T b) {
+  return a < b ? b : a;
+}
 struct alignas(16) double2 {
   double x, y;
 };
@@ -90,7 +103,7 @@ static std::vector<EmuWarp> emu_warps;
 static EmuBarrier emu_block_bar;
 static unsigned emu_cur = 0;
 static const std::function<void()> *emu_body = nullptr;
-alignas(16) static unsigned char emu_dyn_smem[232448];
+alignas(128) static unsigned char emu_dyn_smem[232448];
 
 static inline void emu_wait(EmuBarrier &b) {
   EmuFiber &f = emu_fibers[emu_cur];
@@ -107,6 +120,13 @@ static inline void emu_wait(EmuBarrier &b) {
 static inline EmuWarp &emu_warp() { return emu_warps[threadIdx.x >> 5]; }
 static inline void __syncthreads() { emu_wait(emu_block_bar); }
 static inline void __syncwarp() { emu_wait(emu_warp().bar); }
+// bar.sync id, count: a named barrier over `count` threads (a kernel's inline PTX is replaced by this call)
+static EmuBarrier emu_named[16];
+static inline void emu_named_barrier(int id, int count) {
+  EmuBarrier &b = emu_named[id & 15];
+  if (b.arrived == 0) b.expected = (unsigned)count;
+  emu_wait(b);
+}
 // Block barrier that also ORs a predicate over the block.  The accumulator of a barrier generation is reset by
 // the generation's first arrival; it was last used two generations earlier, and every thread read that result
 // before it could arrive at the generation in between.
@@ -245,6 +265,7 @@ static inline bool emu_launch(unsigned grid, unsigned block, const std::function
     blockIdx.x = b;
     emu_block_bar = EmuBarrier();
     emu_block_bar.expected = block;
+    for (EmuBarrier &nb : emu_named) nb = EmuBarrier();
     emu_warps.assign(nwarps, EmuWarp());
     for (unsigned w = 0; w < nwarps; ++w) emu_warps[w].bar.expected = std::min(32u, block - 32 * w);
     emu_fibers.clear();
