@@ -117,6 +117,14 @@ static inline void emu_wait(EmuBarrier &b) {
   f.wait_gen = g;
   emu_switch(&f.sp, emu_sched_sp);
 }
+// A polling loop gives the other fibers a turn (the fiber stays runnable)
+static uint64_t emu_yields = 0;
+static inline void emu_yield() {
+  EmuFiber &f = emu_fibers[emu_cur];
+  f.wait = nullptr;
+  ++emu_yields;
+  emu_switch(&f.sp, emu_sched_sp);
+}
 static inline EmuWarp &emu_warp() { return emu_warps[threadIdx.x >> 5]; }
 static inline void __syncthreads() { emu_wait(emu_block_bar); }
 static inline void __syncwarp() { emu_wait(emu_warp().bar); }
@@ -156,6 +164,13 @@ static inline uint32_t __ballot_sync(uint32_t, bool pred) {
   for (unsigned i = 0; i < nl; ++i) m |= v[i] << i;
   return m;
 }
+static inline int __any_sync(uint32_t, int pred) {
+  const uint32_t *v = emu_exchange(pred ? 1u : 0u);
+  const unsigned nl = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+  int r = 0;
+  for (unsigned i = 0; i < nl; ++i) r |= (int)v[i];
+  return r;
+}
 static inline uint32_t __shfl_sync(uint32_t, uint32_t x, int src) { return emu_exchange(x)[src & 31]; }
 static inline uint32_t __shfl_up_sync(uint32_t, uint32_t x, int delta) {
   const int lane = threadIdx.x & 31;
@@ -190,6 +205,17 @@ static inline unsigned long long atomicAnd(unsigned long long *p, unsigned long 
 }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline float __uint_as_float(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline uint32_t __float_as_uint(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+static inline float __int_as_float(int i) { return __uint_as_float((uint32_t)i); }
 // IEEE double operations, round to nearest (compile the harness with -ffp-contract=off: no fused multiply-add)
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
