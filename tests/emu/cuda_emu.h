@@ -240,6 +240,24 @@ static inline double __shfl_down_sync(uint32_t m, double x, int delta) {
   memcpy(&r, &u, 8);
   return r;
 }
+static inline unsigned long __shfl_sync(uint32_t m, unsigned long x, int src) {
+  return (unsigned long)__shfl_sync(m, (unsigned long long)x, src);
+}
+static inline unsigned long long __shfl_up_sync(uint32_t m, unsigned long long x, int delta) {
+  const uint32_t lo = __shfl_up_sync(m, (uint32_t)x, delta), hi = __shfl_up_sync(m, (uint32_t)(x >> 32), delta);
+  return ((unsigned long long)hi << 32) | lo;
+}
+static inline int __all_sync(uint32_t, int pred) {
+  const uint32_t *v = emu_exchange(pred ? 1u : 0u);
+  const unsigned nl = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+  int r = 1;
+  for (unsigned i = 0; i < nl; ++i) r &= (int)v[i];
+  return r;
+}
+template <typename T>
+static inline T __ldcs(const T *p) {
+  return *p;
+}
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
   return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
 }
