@@ -15,12 +15,14 @@
 #include "cuda_emu.h"
 
 namespace hs {
+constexpr int kCodeScale = 4;   // (csrc/common.cuh) the bucket-ordered code store keeps code * 4
 constexpr int kMaxKeyWords = 4;
 struct KeyPtrs {
   uint64_t *w[kMaxKeyWords];
 };
 #include "radixsort_kernels.inc"
 #include "probe_kernels.inc"
+#include "gather_kernels.inc"
 }  // namespace hs
 
 using namespace hs;
@@ -239,6 +241,61 @@ static bool test_probe(uint64_t nb, uint32_t Q, unsigned seed) {
   return found > 0 && found < Q;
 }
 
+// The bucket-ordered, position-major code stores of all tables by the L2-blocked gather (build_code_stores_blocked):
+// the record array is walked block by block, every bucket part's run inside a block found by gather_runs_kernel.
+// (Built with -DHS_GATHER_PART=64 so that buckets are cut into several parts at this size.)
+static bool test_gather(uint64_t n, uint32_t L, uint32_t nr, int len, uint32_t chunk, unsigned seed) {
+  std::mt19937 rng(seed);
+  const uint32_t RS = (uint32_t)((len + 15) & ~15);
+  const uint64_t npad = (n + 15) & ~15ull;
+  std::vector<uint8_t> rec(n * RS + 64, 0);
+  for (uint64_t i = 0; i < n; ++i)
+    for (int p = 0; p < len; ++p) rec[i * RS + p] = (uint8_t)(rng() % 20);
+  const uint32_t nchunks = (uint32_t)((n + chunk - 1) / chunk);
+  std::vector<std::vector<uint32_t>> ids(L), slots(L);
+  std::vector<std::vector<uint8_t>> out(L, std::vector<uint8_t>((size_t)len * npad + 256, 0xee));
+  std::vector<GatherTab> tabs(L);
+  uint64_t run_total = 0;
+  uint32_t groups = 0;
+  for (uint32_t l = 0; l < L; ++l) {
+    std::vector<uint16_t> rank(n);
+    for (auto &r : rank) r = (uint16_t)(rng() % 5 == 0 ? 3 : rng() % nr);   // one large bucket among small ones
+    ids[l].resize(n);
+    std::iota(ids[l].begin(), ids[l].end(), 0u);
+    std::stable_sort(ids[l].begin(), ids[l].end(), [&](uint32_t a, uint32_t b) { return rank[a] < rank[b]; });
+    std::vector<uint32_t> bstart(nr + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) bstart[rank[i] + 1]++;
+    for (uint32_t r = 0; r < nr; ++r) bstart[r + 1] += bstart[r];
+    for (uint32_t b = 0; b < nr; ++b)
+      for (uint32_t p = bstart[b]; p < bstart[b + 1]; p += kGatherPart) slots[l].push_back(p);
+    slots[l].push_back((uint32_t)n);
+    const uint64_t nv = slots[l].size() - 1;
+    tabs[l].ids = ids[l].data();
+    tabs[l].bstart = slots[l].data();
+    tabs[l].out = out[l].data();
+    tabs[l].nslots = (uint32_t)nv;
+    tabs[l].ngroups = (uint32_t)((nv + kGatherSlots - 1) / kGatherSlots);
+    tabs[l].groups_before = groups;
+    tabs[l].run_off = run_total;
+    groups += tabs[l].ngroups;
+    run_total += (uint64_t)(nchunks + 1) * nv;
+  }
+  std::vector<uint32_t> runs(run_total + 16, 0xdeadbeefu);
+  bool ok = emu_launch(groups, kGatherSlots, [&]() { gather_runs_kernel(tabs.data(), L, nchunks, chunk, runs.data()); });
+  ok = ok && emu_launch(groups * nchunks, kGatherThreads, [&]() {
+    gather_blocked_kernel<1>(tabs.data(), L, groups, runs.data(), rec.data(), RS, npad, len);
+  });
+  if (!ok) return false;
+  for (uint32_t l = 0; l < L; ++l)
+    for (uint64_t j = 0; j < n; ++j)
+      for (int p = 0; p < len; ++p)
+        if (out[l][(uint64_t)p * npad + j] != (uint8_t)(rec[(uint64_t)ids[l][j] * RS + p] * kCodeScale)) {
+          printf("  table %u position %llu residue %d differs\n", l, (unsigned long long)j, p);
+          return false;
+        }
+  return true;
+}
+
 int main() {
   setvbuf(stdout, nullptr, _IONBF, 0);
   int bad = 0;
@@ -259,5 +316,7 @@ int main() {
   report("probe, one-word keys, 300 slots", test_probe<1>(300, 500, 11));
   report("probe, three-word keys, 200 slots", test_probe<3>(200, 400, 12));
   report("probe, one slot", test_probe<2>(1, 40, 13));
+  report("blocked gather: 5000 fragments, 2 tables, record blocks of 300", test_gather(5000, 2, 40, 10, 300, 14));
+  report("blocked gather: 3001 fragments, 4 tables, record blocks of 1000, len 16", test_gather(3001, 4, 700, 16, 1000, 15));
   return bad ? 1 : 0;
 }

@@ -1,6 +1,6 @@
 """CPU check of the index-build sort kernels (hsearch_b200/csrc/radix_sort.cu: rank upsweep / downsweep /
 bounds, the device-wide scan, one pass of the general radix sort; csrc/verify.cu: the probe of a query's key into the
-sorted slots and into the hashed-key index) under the fiber-based emulation of
+sorted slots and into the hashed-key index; the L2-blocked gather of the bucket-ordered code stores) under the fiber-based emulation of
 tests/emu/cuda_emu.h: the kernel text is compiled unchanged and run against std::stable_sort -- ids in
 bucket order must be the stable order (ascending id inside a bucket = the reference's insertion order,
 motif_both_points.cpp:212-218), slot boundaries the lower bounds of the ranks."""
@@ -44,10 +44,12 @@ def probe_text():
 def test_index_sort_kernels_under_cpu_emulation(tmp_path):
     (tmp_path / "radixsort_kernels.inc").write_text(kernel_text())
     (tmp_path / "probe_kernels.inc").write_text(probe_text())
+    src = open(os.path.join(ROOT, "hsearch_b200", "csrc", "radix_sort.cu")).read()
+    (tmp_path / "gather_kernels.inc").write_text(cut(src, "constexpr uint32_t kGatherBlockBytes", "// Builds codes_sorted of every table."))
     exe = tmp_path / "ranksort_emu"
-    subprocess.check_call(["g++", "-O1", "-std=c++17", f"-I{tmp_path}", f"-I{os.path.join(ROOT, 'tests', 'emu')}",
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DHS_GATHER_PART=64", f"-I{tmp_path}", f"-I{os.path.join(ROOT, 'tests', 'emu')}",
                            "-o", str(exe), os.path.join(ROOT, "tests", "emu", "ranksort_emu.cpp")])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     results = re.findall(r" -> (\w+)$", out.stdout, flags=re.M)
-    assert len(results) == 13 and all(r == "ok" for r in results), out.stdout
+    assert len(results) == 15 and all(r == "ok" for r in results), out.stdout
